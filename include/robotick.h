@@ -1,0 +1,197 @@
+/* robotick.h -- C-ABI of the B200-native batched control-tick engine.
+ *
+ * Drop-in boundary for the numeric control tick of Moryu-Io/Roboken-FMSKF-robot-controller
+ * (SURVEY.md section 8b).  The reference has no FFI layer: its boundary is ordinary C++ member
+ * functions on static objects.  Every entry point below names the reference member it
+ * replaces (file:line relative to the reference tree).  Plain pointers and sizes only; no
+ * torch / C++ types.  The single-instance "handle" calls are batches of one over the same
+ * CUDA kernels, so there is exactly one implementation of the arithmetic and it lives on
+ * the GPU (sm_100a).  There is NO CPU fallback: every call fails with RK_ERR_CUDA when no
+ * device is usable.
+ *
+ * Threading: a handle / state block is single-owner (not thread-safe); distinct blocks are
+ * independent.  All batch calls are asynchronous on the given CUDA stream (a cudaStream_t
+ * passed as void*; NULL = legacy default stream).
+ *
+ * ---------------------------------------------------------------------------------------
+ * Data layout in HBM ("SoA of 128-bit planes")
+ * ---------------------------------------------------------------------------------------
+ * A state block for n instances is P planes; plane p is n contiguous 16-byte cells, cell i
+ * belonging to instance i:   word w of instance i lives at
+ *        ((uint32_t*)block)[ ((w / 4) * n + i) * 4 + (w % 4) ]
+ * so that one warp moves 32 x 16 B = 512 contiguous bytes per plane with one 128-bit
+ * load/store per thread.  n is the "pitch"; blocks must be 16-byte aligned.  A block that is
+ * all-zero is the firmware's power-on state (the reference relies on zero-initialised
+ * globals, e.g. VD_task_main.cpp:75-108).
+ */
+#ifndef ROBOTICK_H_
+#define ROBOTICK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RK_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ------------------------------------------------------------------ */
+enum {
+  RK_OK           = 0,
+  RK_ERR_ARG      = 1, /* bad pointer / size / alignment / unsupported option */
+  RK_ERR_CUDA     = 2, /* CUDA runtime error or no sm_100 device              */
+  RK_ERR_NOMEM    = 3,
+  RK_ERR_UNSUPPORTED = 4
+};
+
+int         rk_version(void);
+const char *rk_last_error(void); /* thread-local message of the last failing call */
+/* device properties the bench needs for its roofline (SM count, SM clock in kHz) */
+int rk_device_info(int device, int *sm_count, int *sm_clock_khz, size_t *hbm_bytes);
+
+/* =====================================================================================
+ * Vehicle (src/VehicleDrive + the src/Utility math it calls)
+ * ===================================================================================== */
+
+/* Broadcast configuration; mirrors the constants wired in VD_task_main.cpp:22-48,75-108,
+ * 157-160, VD_vehicle_controller.hpp:82-86 and VD_motor_if_m2006.hpp:64,76-82. */
+typedef struct rk_vdt_params {
+  float   wheel_radius_mm;   /* WHEEL_RADIUS_MM  37.5f        VD_vehicle_controller.hpp:82 */
+  float   wheel_l_mm;        /* WHEEL_L_MM       13.08148f    :85 */
+  float   sqrtf2;            /* SQRTF2           1.41421356f  :86 */
+  float   ts;                /* VelInterpConstJerk sample time 1.0f/1000  VD_task_main.cpp:95-97 */
+  float   ctrl_freq;         /* FF_PI_D c_freq   100.0f (sic: task rate)  VD_task_main.cpp:86 */
+  float   kff, kp, ki, kd;   /* 0.0075f 0.02f 0.01f 0.0f      :86-89 */
+  float   i_limit;           /* 0.5f */
+  float   lpf_freq;          /* 10.0f */
+  float   ff_limit;          /* set_FF_limit(1.0f)            :157-160 */
+  float   accel_move[3];     /* C_ACCEL_MAX_MOVE {1000,1000,30}      :29-33 */
+  float   jerk_move[3];      /* C_JERK_MAX_MOVE  {10000,10000,300}   :34-38 */
+  float   accel_stop[3];     /* C_ACCEL_MAX_STOP {2000,2000,70}      :39-43 */
+  float   jerk_stop[3];      /* C_JERK_MAX_STOP  {30000,30000,1000}  :44-48 */
+  int32_t motor_dir[4];      /* FL,BL,BR,FR = +1,+1,-1,-1            :75-78 */
+  int32_t raw_curr_lim;      /* s16_rawCurr_lim 3000          VD_motor_if_m2006.hpp:64 */
+} rk_vdt_params_t;
+
+void rk_vdt_default_params(rk_vdt_params_t *p);
+
+/* ---- vehicle state words (per instance) -------------------------------------------- */
+enum {
+  /* plane 0 : VEHICLE_CTRL::now_vhcl_pos_m_, isPowerOn   (VD_vehicle_controller.hpp:73,79) */
+  RK_VS_POS_X = 0, RK_VS_POS_Y, RK_VS_POS_TH, RK_VS_FLAGS,
+  /* plane 1-2 : now_vhcl_vel_mmps, now_vhcl_vel_tgt_mmps  (:74-75) */
+  RK_VS_VEL_X, RK_VS_VEL_Y, RK_VS_VEL_TH, RK_VS_TGT_X,
+  RK_VS_TGT_Y, RK_VS_TGT_TH, RK_VS_RSV0, RK_VS_RSV1,
+  /* planes 3..11 : three VelInterpConstJerk (x, y, th), 12 words each: vel_now_/acl_now_ and
+   * the ACTIVE StatusBuf page (util_vel_interp.hpp:20-21,27-39).  The inactive page is fully
+   * overwritten by set_target_params() before it can be read, so it carries no state. */
+  RK_VS_INTERP0 = 12,
+  /* planes 12..19 : four FF_PI_D (FL,BL,BR,FR), 8 words each (util_controller.hpp:19-31,140-147) */
+  RK_VS_CTRL0 = RK_VS_INTERP0 + 3 * 12,
+  /* planes 20..27 : four MOTOR_IF_M2006, 8 words each (VD_motor_if_m2006.hpp:60-72)
+   *                 + VEHICLE_CTRL::s64_rawAngleSumPrev + the synthetic plant's state */
+  RK_VS_MOTOR0 = RK_VS_CTRL0 + 4 * 8,
+  RK_VS_WORDS  = RK_VS_MOTOR0 + 4 * 8 /* = 112 words = 28 planes = 448 B / vehicle */
+};
+/* word offsets inside one interpolator */
+enum {
+  RK_VI_VEL_NOW = 0, RK_VI_ACL_NOW, RK_VI_VEL_TGT, RK_VI_ACL_MAX,
+  RK_VI_JERK_P, RK_VI_JERK_M, RK_VI_DT1, RK_VI_DT2,
+  RK_VI_DT3, RK_VI_VEL_INI, RK_VI_ACL_INI, RK_VI_DT
+};
+/* word offsets inside one wheel controller.  now_val_ == prev_val_ and now_error_ ==
+ * prev_error_ hold after every update()/reset(), so each pair is one word. */
+enum {
+  RK_VC_PREV_VAL = 0, RK_VC_INTEG, RK_VC_LPF_Y, RK_VC_LPF_X,
+  RK_VC_NOW_TGT, RK_VC_NOW_ERR, RK_VC_NOW_CTRL, RK_VC_RSV
+};
+/* word offsets inside one motor */
+enum {
+  RK_VM_SUM_LO = 0, RK_VM_SUM_HI,   /* s64_rawAngleSum */
+  RK_VM_PREV_LO, RK_VM_PREV_HI,     /* VEHICLE_CTRL::s64_rawAngleSumPrev[w] */
+  RK_VM_ANG_RPM,  /* head Status: s16_rawAngle | s16_rawSpeedRpm << 16 */
+  RK_VM_CUR_TGT,  /* head Status: s16_rawCurr  | s16_rawCurr_tgt  << 16 */
+  RK_VM_USEC,     /* head Status: s16_microsec_id (low 16) | status_head << 16 */
+  RK_VM_PLANT     /* synthetic plant (not in the reference): ang | rpm << 16, motor frame */
+};
+#define RK_VS_FLAG_POWER_ON 1u
+
+size_t rk_vdt_state_words(void);        /* RK_VS_WORDS */
+size_t rk_vdt_state_bytes(int64_t n);   /* bytes of an n-instance block */
+
+/* ---- rollout: K fused 1 kHz ticks of N vehicles ------------------------------------- */
+enum {
+  RK_SENSOR_HOLD   = 0, /* no new CAN frames: tick re-reads the last Status (as the ISR does) */
+  RK_SENSOR_PLANT  = 1, /* closed loop through the synthetic integer motor plant (below)     */
+  RK_SENSOR_STREAM = 2  /* one recorded 8-byte M2006 frame per wheel per tick from HBM       */
+};
+/* command kinds, the vocabulary of VDT::main (VD_task_main.cpp:178-322) reduced to targets */
+enum {
+  RK_CMD_NONE = 0, /* no message this segment                                    */
+  RK_CMD_MOVE = 1, /* start(); set_target_vel(v, C_ACCEL_MAX_MOVE, C_JERK_MAX_MOVE)  :294-295 */
+  RK_CMD_STOP = 2  /* start(); set_target_vel(v, C_ACCEL_MAX_STOP, C_JERK_MAX_STOP)  :271-281,305-319 */
+};
+typedef struct rk_vdt_cmd { float vx, vy, vth; int32_t kind; } rk_vdt_cmd_t; /* 16 B */
+
+/* Trace record written per tick when d_trace != NULL (tests / small N only):
+ * word 0-2 pos, 3-5 vel, 6-8 vel_tgt, 9-12 s16_rawCurr_tgt (sign-extended), 13-15 zero. */
+#define RK_VDT_TRACE_WORDS 16
+
+typedef struct rk_vdt_rollout {
+  int32_t steps;        /* K >= 0 */
+  int32_t sensor_mode;  /* RK_SENSOR_* */
+  /* commands: cell [s * n + i] applied to instance i BEFORE tick s*seg_len; NULL = none */
+  const rk_vdt_cmd_t *d_cmd;
+  int32_t n_seg, seg_len;
+  /* IMU yaw in radians (what can_tx_routine_intr() passes to set_now_yaw_world(),
+   * VD_task_main.cpp:368): cell [y * n + i] applied BEFORE tick y*yaw_period; NULL = keep */
+  const float *d_yaw;
+  int32_t n_yaw, yaw_period;
+  /* RK_SENSOR_STREAM: 8-byte frames, cell [(t * 4 + w) * n + i] for tick t, wheel w */
+  const uint64_t *d_frames;
+  /* optional per-tick trace: word j of tick t, instance i at [(t * 16 + j) * n + i] */
+  uint32_t *d_trace;
+  /* optional rollout cost: (pos.x-gx)^2 + (pos.y-gy)^2 at the end; d_goal = float2[n] */
+  const float *d_goal;
+  float *d_cost;
+} rk_vdt_rollout_t;
+
+/* VEHICLE_CTRL::update() x steps   (VD_vehicle_controller.cpp:6-99), fused with the callers
+ * that feed it each tick: set_now_yaw_world (:57), MOTOR_IF_M2006::rx_callback
+ * (VD_motor_if_m2006.cpp:32-72) and set_target_vel (:101-105). */
+int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n,
+                   const rk_vdt_rollout_t *args, void *stream);
+
+/* Batched setters for callers that do not use the fused command table. */
+/* VEHICLE_CTRL::start()/stop()  VD_vehicle_controller.hpp:54-55 ; d_on NULL = all on */
+int rk_vdt_set_power(void *d_state, int64_t n, const uint8_t *d_on, void *stream);
+/* VEHICLE_CTRL::set_target_vel  VD_vehicle_controller.cpp:101-105 ; v/a/j = float[3][n] */
+int rk_vdt_set_target_vel(const rk_vdt_params_t *p, void *d_state, int64_t n, const float *d_v,
+                          const float *d_a, const float *d_j, void *stream);
+/* MOTOR_IF_M2006::rx_callback  VD_motor_if_m2006.cpp:32-72 ; frames = uint64[n] for one wheel */
+int rk_vdt_motor_rx(const rk_vdt_params_t *p, void *d_state, int64_t n, int wheel,
+                    const uint64_t *d_frames, const int16_t *d_usec, void *stream);
+
+/* ---- single-instance handle (drop-in for the static objects of VD_task_main.cpp:75-108) */
+typedef struct rk_vdt rk_vdt_t;
+int  rk_vdt_create(rk_vdt_t **out, const rk_vdt_params_t *p /* NULL = defaults */);
+void rk_vdt_destroy(rk_vdt_t *h);
+int  rk_vdt_update(rk_vdt_t *h);                                  /* VEHICLE_CTRL::update()  */
+int  rk_vdt_start(rk_vdt_t *h);                                   /* ::start()               */
+int  rk_vdt_stop(rk_vdt_t *h);                                    /* ::stop()                */
+int  rk_vdt_set_target(rk_vdt_t *h, const float v[3], const float a[3], const float j[3]);
+int  rk_vdt_set_yaw(rk_vdt_t *h, float yaw_rad);                  /* ::set_now_yaw_world()   */
+int  rk_vdt_rx(rk_vdt_t *h, int wheel, const uint8_t frame[8], int16_t usec_id);
+int  rk_vdt_get_pos(rk_vdt_t *h, float out[3]);     /* get_vehicle_pos_m_latest      :59 */
+int  rk_vdt_get_vel(rk_vdt_t *h, float out[3]);     /* get_vehicle_vel_mmps_latest   :60 */
+int  rk_vdt_get_vel_tgt(rk_vdt_t *h, float out[3]); /* get_vehicle_vel_tgt_mmps_latest :61 */
+int  rk_vdt_get_raw_current(rk_vdt_t *h, int16_t out[4]); /* MOTOR_IF_M2006::get_rawCurr_tgt :52 */
+int  rk_vdt_get_angle_sum(rk_vdt_t *h, int64_t out[4]);   /* MOTOR_IF_M2006::get_rawAngleSum :42 */
+int  rk_vdt_get_state(rk_vdt_t *h, uint32_t words[RK_VS_WORDS]);
+int  rk_vdt_set_state(rk_vdt_t *h, const uint32_t words[RK_VS_WORDS]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBOTICK_H_ */

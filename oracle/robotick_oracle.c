@@ -1,0 +1,476 @@
+/* TEST INFRASTRUCTURE (oracle) -- never linked into the product library.
+ *
+ * Plain-C restatement of the reference's numeric control tick.  Every function cites the
+ * reference file:line it follows (paths relative to the reference tree).  It is compiled
+ * with the pinned flags of oracle/Makefile (-O2 -ffp-contract=off, SSE float evaluation),
+ * and is PINNED by tests/test_oracle_pin.py against
+ *   (a) oracle/_ref -- the reference's own sources compiled unmodified for x86 -- on seeded
+ *       streams, state word for state word, bit-exact; and
+ *   (b) the golden fixtures in tests/golden/ (generated from oracle/_ref by
+ *       tests/golden/make_golden.py) which include the SURVEY.md Appendix D probe values.
+ * The reference itself ships no tests or golden vectors (test/README is a placeholder).
+ *
+ * One boundary stays UNPINNED: CMSIS-DSP arm_sin_f32/arm_cos_f32 (un-vendored, un-pinned
+ * dependency; restated from the published algorithm -- see oracle/cmsis_shim.c).  It only
+ * influences pos.x / pos.y.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use this file.
+ */
+#include "robotick_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------ */
+/* constants: VD_motor_if_m2006.hpp:76-82, util_mymath.hpp + CMSIS PI                    */
+#define ORC_PI 3.14159265358979f
+static const float RPM_TO_RADPS          = 2.0f * 3.1415926f / 60.0f;
+static const float AMPERE_TO_RAW_CURR    = 1000.0f;
+static const float GEAR_RATIO            = 36.0f;
+static const float GEAR_RATIO_INV        = 1.0f / 36.0f;
+static const float OUT_RAD_PER_RAW_ANGLE = 2.0f * 3.1415926f / 8191.0f;
+
+typedef struct {
+  float vel, acl, vel_tgt, acl_max, jerk_p, jerk_m, dt1, dt2, dt3, vel_ini, acl_ini, dt;
+} interp_t;
+typedef struct {
+  float prev_val, integ, lpf_y, lpf_x, now_tgt, now_err, now_ctrl;
+} ctrl_t;
+typedef struct {
+  int64_t sum, prev;
+  int16_t ang, rpm, cur, cur_tgt, usec;
+  uint8_t head;
+  int32_t p_ang, p_rpm;
+} motor_t;
+typedef struct {
+  float    pos[3], vel[3], tgt[3];
+  int      power;
+  interp_t it[3];
+  ctrl_t   c[4];
+  motor_t  m[4];
+} veh_t;
+
+static uint32_t f2u(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+static float u2f(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+static int      lo16(uint32_t w) { return (int16_t)(w & 0xFFFFu); }
+static int      hi16(uint32_t w) { return (int16_t)(w >> 16); }
+
+static void unpack(veh_t *v, const uint32_t *w) {
+  int a, k;
+  for(a = 0; a < 3; a++) {
+    v->pos[a] = u2f(w[RK_VS_POS_X + a]);
+    v->vel[a] = u2f(w[RK_VS_VEL_X + a]);
+    v->tgt[a] = u2f(w[RK_VS_TGT_X + a]);
+  }
+  v->power = (w[RK_VS_FLAGS] & RK_VS_FLAG_POWER_ON) != 0;
+  for(a = 0; a < 3; a++) {
+    const uint32_t *q = w + RK_VS_INTERP0 + 12 * a;
+    interp_t       *t = &v->it[a];
+    t->vel = u2f(q[RK_VI_VEL_NOW]), t->acl = u2f(q[RK_VI_ACL_NOW]);
+    t->vel_tgt = u2f(q[RK_VI_VEL_TGT]), t->acl_max = u2f(q[RK_VI_ACL_MAX]);
+    t->jerk_p = u2f(q[RK_VI_JERK_P]), t->jerk_m = u2f(q[RK_VI_JERK_M]);
+    t->dt1 = u2f(q[RK_VI_DT1]), t->dt2 = u2f(q[RK_VI_DT2]), t->dt3 = u2f(q[RK_VI_DT3]);
+    t->vel_ini = u2f(q[RK_VI_VEL_INI]), t->acl_ini = u2f(q[RK_VI_ACL_INI]), t->dt = u2f(q[RK_VI_DT]);
+  }
+  for(k = 0; k < 4; k++) {
+    const uint32_t *q = w + RK_VS_CTRL0 + 8 * k;
+    ctrl_t         *c = &v->c[k];
+    c->prev_val = u2f(q[RK_VC_PREV_VAL]), c->integ = u2f(q[RK_VC_INTEG]);
+    c->lpf_y = u2f(q[RK_VC_LPF_Y]), c->lpf_x = u2f(q[RK_VC_LPF_X]);
+    c->now_tgt = u2f(q[RK_VC_NOW_TGT]), c->now_err = u2f(q[RK_VC_NOW_ERR]), c->now_ctrl = u2f(q[RK_VC_NOW_CTRL]);
+  }
+  for(k = 0; k < 4; k++) {
+    const uint32_t *q = w + RK_VS_MOTOR0 + 8 * k;
+    motor_t        *m = &v->m[k];
+    m->sum     = (int64_t)(((uint64_t)q[RK_VM_SUM_HI] << 32) | q[RK_VM_SUM_LO]);
+    m->prev    = (int64_t)(((uint64_t)q[RK_VM_PREV_HI] << 32) | q[RK_VM_PREV_LO]);
+    m->ang     = (int16_t)lo16(q[RK_VM_ANG_RPM]);
+    m->rpm     = (int16_t)hi16(q[RK_VM_ANG_RPM]);
+    m->cur     = (int16_t)lo16(q[RK_VM_CUR_TGT]);
+    m->cur_tgt = (int16_t)hi16(q[RK_VM_CUR_TGT]);
+    m->usec    = (int16_t)lo16(q[RK_VM_USEC]);
+    m->head    = (uint8_t)(hi16(q[RK_VM_USEC]) % 3);
+    m->p_ang   = lo16(q[RK_VM_PLANT]);
+    m->p_rpm   = hi16(q[RK_VM_PLANT]);
+  }
+}
+
+static void pack(const veh_t *v, uint32_t *w) {
+  int a, k;
+  memset(w, 0, sizeof(uint32_t) * RK_VS_WORDS);
+  for(a = 0; a < 3; a++) {
+    w[RK_VS_POS_X + a] = f2u(v->pos[a]);
+    w[RK_VS_VEL_X + a] = f2u(v->vel[a]);
+    w[RK_VS_TGT_X + a] = f2u(v->tgt[a]);
+  }
+  w[RK_VS_FLAGS] = v->power ? RK_VS_FLAG_POWER_ON : 0u;
+  for(a = 0; a < 3; a++) {
+    uint32_t       *q = w + RK_VS_INTERP0 + 12 * a;
+    const interp_t *t = &v->it[a];
+    q[RK_VI_VEL_NOW] = f2u(t->vel), q[RK_VI_ACL_NOW] = f2u(t->acl);
+    q[RK_VI_VEL_TGT] = f2u(t->vel_tgt), q[RK_VI_ACL_MAX] = f2u(t->acl_max);
+    q[RK_VI_JERK_P] = f2u(t->jerk_p), q[RK_VI_JERK_M] = f2u(t->jerk_m);
+    q[RK_VI_DT1] = f2u(t->dt1), q[RK_VI_DT2] = f2u(t->dt2), q[RK_VI_DT3] = f2u(t->dt3);
+    q[RK_VI_VEL_INI] = f2u(t->vel_ini), q[RK_VI_ACL_INI] = f2u(t->acl_ini), q[RK_VI_DT] = f2u(t->dt);
+  }
+  for(k = 0; k < 4; k++) {
+    uint32_t     *q = w + RK_VS_CTRL0 + 8 * k;
+    const ctrl_t *c = &v->c[k];
+    q[RK_VC_PREV_VAL] = f2u(c->prev_val), q[RK_VC_INTEG] = f2u(c->integ);
+    q[RK_VC_LPF_Y] = f2u(c->lpf_y), q[RK_VC_LPF_X] = f2u(c->lpf_x);
+    q[RK_VC_NOW_TGT] = f2u(c->now_tgt), q[RK_VC_NOW_ERR] = f2u(c->now_err), q[RK_VC_NOW_CTRL] = f2u(c->now_ctrl);
+  }
+  for(k = 0; k < 4; k++) {
+    uint32_t      *q = w + RK_VS_MOTOR0 + 8 * k;
+    const motor_t *m = &v->m[k];
+    q[RK_VM_SUM_LO]  = (uint32_t)(uint64_t)m->sum;
+    q[RK_VM_SUM_HI]  = (uint32_t)((uint64_t)m->sum >> 32);
+    q[RK_VM_PREV_LO] = (uint32_t)(uint64_t)m->prev;
+    q[RK_VM_PREV_HI] = (uint32_t)((uint64_t)m->prev >> 32);
+    q[RK_VM_ANG_RPM] = pack16(m->ang, m->rpm);
+    q[RK_VM_CUR_TGT] = pack16(m->cur, m->cur_tgt);
+    q[RK_VM_USEC]    = pack16(m->usec, m->head);
+    q[RK_VM_PLANT]   = pack16(m->p_ang, m->p_rpm);
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* CMSIS-DSP sin/cos restatement (un-vendored dependency; see oracle/cmsis_shim.c)       */
+static const float sin_table[513] = {
+#include "cmsis_sin_table.inc"
+};
+static float table_lerp(float in) {
+  int32_t  n = (int32_t)in;
+  float    findex, fract;
+  uint16_t index;
+  if(in < 0.0f) n--;
+  in     = in - (float)n;
+  findex = 512.0f * in;
+  index  = (uint16_t)findex;
+  if(index >= 512) {
+    index = 0;
+    findex -= 512.0f;
+  }
+  fract = findex - (float)index;
+  return (1.0f - fract) * sin_table[index] + fract * sin_table[index + 1];
+}
+float orc_sin(float x) { return table_lerp(x * 0.159154943092f); }
+float orc_cos(float x) { return table_lerp(x * 0.159154943092f + 0.25f); }
+/* arm_sqrt_f32 on an FPU core: IEEE sqrt, negative -> 0 (util_vel_interp.hpp:90) */
+static float orc_sqrt(float x) { return (x >= 0.0f) ? sqrtf(x) : 0.0f; }
+
+/* util_mymath.hpp:18-25 */
+float orc_normalize_rad_0to2pi(float d) {
+  if(d < 0.0f || d >= 2.0f * ORC_PI) {
+    int mod = (int)(d / (2.0f * ORC_PI));
+    d -= (mod * 2.0f * ORC_PI);
+    if(d < 0.0f) d = d + 2.0f * ORC_PI;
+  }
+  return d;
+}
+/* util_mymath.hpp:27-34 */
+float orc_normalize_deg_0to360(float d) {
+  if(d < 0.0f || d >= 360.0f) {
+    int mod = (int)(d / (360.0f));
+    d -= (mod * 360.0f);
+    if(d < 0.0f) d = d + 360.0f;
+  }
+  return d;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* VelInterpConstJerk::set_target_params   util_vel_interp.hpp:53-108 (writes the other page
+ * and flips; only the page that becomes active is state)                                 */
+static void interp_set(interp_t *t, float v_t, float a_m, float jrk) {
+  float vel_tgt = v_t, acl_max = a_m, vel_ini = t->vel, acl_ini = t->acl;
+  float jerk_m, jerk_p, jm_inv, jp_inv, dt1, dt2, dt3;
+  if((vel_tgt - vel_ini) < 0) acl_max = -a_m;
+  jerk_m = (acl_max >= 0) ? -jrk : jrk;
+  jm_inv = 1.0f / jerk_m;
+  jerk_p = (acl_max - acl_ini >= 0) ? jrk : -jrk;
+  jp_inv = 1.0f / jerk_p;
+  dt1    = (acl_max - acl_ini) * jp_inv;
+  dt3    = acl_max * (-jm_inv);
+  dt2    = 1.0f / acl_max * (vel_tgt - vel_ini - acl_ini * dt1 * 0.5f - acl_max * (dt1 + dt3) * 0.5f);
+  if(dt2 < 0.0f) {
+    float sq_in = (acl_ini * jp_inv) * (acl_ini * jp_inv) * 0.5f + (vel_tgt - vel_ini) * jp_inv;
+    float sq    = orc_sqrt(sq_in);
+    dt1         = sq - acl_ini * jp_inv;
+    acl_max     = acl_ini + jerk_p * dt1;
+    dt2         = 0.0f;
+    dt3         = acl_max * (-jm_inv);
+  }
+  dt1 = (dt1 < 0.0f) ? 0.0f : dt1;
+  dt3 = (dt3 < 0.0f) ? 0.0f : dt3;
+  t->vel_tgt = vel_tgt, t->acl_max = acl_max, t->jerk_p = jerk_p, t->jerk_m = jerk_m;
+  t->dt1 = dt1, t->dt2 = dt2, t->dt3 = dt3, t->vel_ini = vel_ini, t->acl_ini = acl_ini, t->dt = 0.0f;
+}
+/* VelInterpConstJerk::update   util_vel_interp.hpp:110-136 */
+static float interp_update(interp_t *t, float ts) {
+  if(t->dt <= t->dt1 + ts) {
+    t->acl = t->acl_ini + t->jerk_p * t->dt;
+    t->vel = t->vel_ini + (t->acl_ini + t->acl) * t->dt * 0.5f;
+    t->dt  = t->dt + ts;
+  } else if(t->dt <= t->dt1 + t->dt2 + ts) {
+    t->acl = t->acl_max;
+    t->vel = t->vel + t->acl * ts;
+    t->dt  = t->dt + ts;
+  } else if(t->dt <= t->dt1 + t->dt2 + t->dt3 + ts) {
+    t->acl = t->acl_max + t->jerk_m * (t->dt - t->dt1 - t->dt2);
+    t->vel = t->vel + t->acl * ts;
+    t->dt  = t->dt + ts;
+  } else {
+    t->acl = 0.0f;
+    t->vel = t->vel_tgt;
+  }
+  return t->vel;
+}
+/* VelInterpConstJerk::reset   util_vel_interp.hpp:138-143 */
+static void interp_reset(interp_t *t) { memset(t, 0, sizeof(*t)); }
+
+/* FF_PI_D::update -> PI_D::update -> IIR1::update
+ * util_controller.hpp:159-165, :94-110, ctor :90-92 ; util_iir.hpp:39-45 */
+static float ctrl_update(ctrl_t *c, const rk_vdt_params_t *p, float nowval) {
+  const float freq = p->ctrl_freq, dt = 1.0f / p->ctrl_freq, lpf = p->lpf_freq;
+  const float A1 = (2.0f * freq - lpf) / (2.0f * freq + lpf);
+  const float B0 = lpf / (2.0f * freq + lpf), B1 = lpf / (2.0f * freq + lpf);
+  float       now_val = nowval, err, x, y, ctrl, ff;
+  err       = c->now_tgt - now_val;
+  x         = (now_val - c->prev_val) * freq;
+  y         = A1 * c->lpf_y + B0 * x + B1 * c->lpf_x;
+  c->lpf_y  = y;
+  c->lpf_x  = x;
+  c->integ += p->ki * dt * err;
+  c->integ  = (c->integ >= p->i_limit) ? p->i_limit : ((c->integ <= -p->i_limit) ? -p->i_limit : c->integ);
+  ctrl      = p->kp * err + c->integ - p->kd * y;
+  c->prev_val = now_val;
+  c->now_err  = err;
+  ff          = c->now_tgt * p->kff;
+  ff          = (ff >= p->ff_limit) ? p->ff_limit : ((ff <= -p->ff_limit) ? -p->ff_limit : ff);
+  ctrl        = ctrl + ff;
+  c->now_ctrl = ctrl;
+  return ctrl;
+}
+/* PI_D::reset  util_controller.hpp:112-124 */
+static void ctrl_reset(ctrl_t *c) { memset(c, 0, sizeof(*c)); }
+
+/* MOTOR_IF_M2006::set_CurrA_tgt -> set_rawCurr_tgt -> sat_curr  VD_motor_if_m2006.hpp:36-37,57
+ * (int16_t)(float) is done as x86 does it: cvttss2si to 32 bits, keep the low 16. */
+static void motor_set_curr(motor_t *m, int dir, int lim, float amp) {
+  int16_t t  = (int16_t)(int32_t)(amp * AMPERE_TO_RAW_CURR);
+  int16_t c  = (int16_t)(t * dir);
+  int16_t l  = (int16_t)lim;
+  m->cur_tgt = (c > l) ? l : ((c < -l) ? (int16_t)-l : c);
+}
+
+/* MOTOR_IF_M2006::rx_callback  VD_motor_if_m2006.cpp:32-72 (integer part; the float fields
+ * flt_SpeedRadPS / flt_dltOutAngle_rad are dead: VD_vehicle_controller.cpp:20-24 `#if 1`) */
+static void motor_rx(motor_t *m, int dir, const uint8_t f[8], int16_t usec) {
+  uint8_t w = (uint8_t)(m->head + 1);
+  int16_t a, raw_ang, d;
+  if(w >= 3) w = 0;
+  a = (int16_t)((f[0] << 8) | f[1]);
+  if(dir == 1)
+    raw_ang = a;
+  else
+    raw_ang = (int16_t)(8192 - a);
+  d       = (int16_t)(raw_ang - m->ang);
+  d       = (d > 4096) ? (int16_t)(d - 8192) : ((d < -4096) ? (int16_t)(d + 8192) : d);
+  m->sum  = m->sum + d;
+  m->ang  = raw_ang;
+  m->rpm  = (int16_t)((int16_t)((f[2] << 8) | f[3]) * dir);
+  m->cur  = (int16_t)((int16_t)((f[4] << 8) | f[5]) * dir);
+  m->usec = usec;
+  m->head = w;
+}
+
+/* VEHICLE_CTRL::conv_Mdir_to_Vdir  VD_vehicle_controller.cpp:126-130 */
+static void fk(const rk_vdt_params_t *p, const float M[4], float V[3]) {
+  const float R = p->wheel_radius_mm, L = p->wheel_l_mm, S2 = p->sqrtf2;
+  V[0] = (M[0] + M[1] + M[2] + M[3]) * 0.25f * R;
+  V[1] = (-M[0] + M[1] - M[2] + M[3]) * 0.25f * R;
+  V[2] = (-M[0] - M[1] + M[2] + M[3]) * 0.25f / S2 / L * R;
+}
+/* VEHICLE_CTRL::conv_Vdir_to_Mdir  VD_vehicle_controller.cpp:113-118 */
+static void ik(const rk_vdt_params_t *p, const float V[3], float M[4]) {
+  const float R = p->wheel_radius_mm, L = p->wheel_l_mm, S2 = p->sqrtf2;
+  M[0] = (V[0] - V[1] - S2 * L * V[2] * 4.0f) / R;
+  M[1] = (V[0] + V[1] - S2 * L * V[2] * 4.0f) / R;
+  M[2] = (V[0] - V[1] + S2 * L * V[2] * 4.0f) / R;
+  M[3] = (V[0] + V[1] + S2 * L * V[2] * 4.0f) / R;
+}
+
+/* VEHICLE_CTRL::update  VD_vehicle_controller.cpp:6-99 */
+static void veh_update(veh_t *v, const rk_vdt_params_t *p) {
+  float Mvel[4], Mrad[4], loc[3], Mtgt[4], rad, c, s;
+  int   k;
+  for(k = 0; k < 4; k++) Mvel[k] = (float)v->m[k].rpm * RPM_TO_RADPS * GEAR_RATIO_INV;
+  fk(p, Mvel, v->vel);
+  for(k = 0; k < 4; k++) {
+    Mrad[k]      = (float)((double)(v->m[k].sum - v->m[k].prev) * OUT_RAD_PER_RAW_ANGLE * GEAR_RATIO_INV);
+    v->m[k].prev = v->m[k].sum;
+  }
+  fk(p, Mrad, loc);
+  rad       = orc_normalize_rad_0to2pi(v->pos[2]);
+  c         = orc_cos(rad);
+  s         = orc_sin(rad);
+  v->pos[0] = v->pos[0] + (loc[0] * c - loc[1] * s) * 0.001f;
+  v->pos[1] = v->pos[1] + (loc[0] * s + loc[1] * c) * 0.001f;
+  for(k = 0; k < 3; k++) v->tgt[k] = interp_update(&v->it[k], p->ts);
+  ik(p, v->tgt, Mtgt);
+  if(v->power) {
+    for(k = 0; k < 4; k++) v->c[k].now_tgt = Mtgt[k] * GEAR_RATIO;
+    for(k = 0; k < 4; k++) motor_set_curr(&v->m[k], p->motor_dir[k], p->raw_curr_lim, ctrl_update(&v->c[k], p, Mvel[k] * GEAR_RATIO));
+  } else {
+    for(k = 0; k < 3; k++) interp_reset(&v->it[k]);
+    for(k = 0; k < 4; k++) ctrl_reset(&v->c[k]);
+    for(k = 0; k < 4; k++) motor_set_curr(&v->m[k], p->motor_dir[k], p->raw_curr_lim, 0.0f);
+  }
+}
+
+/* synthetic plant of robotick.h (RK_SENSOR_PLANT) -- not part of the reference */
+static void plant_frame(motor_t *m, uint8_t f[8]) {
+  int32_t cur = m->cur_tgt, rpm = m->p_rpm, ang = m->p_ang;
+  rpm += ((cur * 4 - rpm) >> 4);
+  ang      = (ang + rpm * 8192 / 60000) & 8191;
+  m->p_rpm = rpm, m->p_ang = ang;
+  f[0] = (uint8_t)(ang >> 8), f[1] = (uint8_t)ang, f[2] = (uint8_t)(rpm >> 8), f[3] = (uint8_t)rpm;
+  f[4] = (uint8_t)(cur >> 8), f[5] = (uint8_t)cur, f[6] = 0, f[7] = 0;
+}
+
+/* VEHICLE_CTRL::set_target_vel  VD_vehicle_controller.cpp:101-105 */
+static void veh_set_target(veh_t *v, const float vv[3], const float a[3], const float j[3]) {
+  int k;
+  for(k = 0; k < 3; k++) interp_set(&v->it[k], vv[k], a[k], j[k]);
+}
+
+static void rollout_one(veh_t *v, const rk_vdt_params_t *p, int64_t n, int64_t i, const rk_vdt_rollout_t *a) {
+  int t, k, j;
+  for(t = 0; t < a->steps; t++) {
+    int16_t us;
+    if(a->d_cmd && a->seg_len > 0 && (t % a->seg_len) == 0 && (t / a->seg_len) < a->n_seg) {
+      const rk_vdt_cmd_t *c = &a->d_cmd[(int64_t)(t / a->seg_len) * n + i];
+      if(c->kind != RK_CMD_NONE) {
+        float vv[3] = {c->vx, c->vy, c->vth};
+        v->power    = 1; /* VEHICLE_CTRL::start()  VD_vehicle_controller.hpp:54 */
+        if(c->kind == RK_CMD_STOP)
+          veh_set_target(v, vv, p->accel_stop, p->jerk_stop);
+        else
+          veh_set_target(v, vv, p->accel_move, p->jerk_move);
+      }
+    }
+    if(a->d_yaw && a->yaw_period > 0 && (t % a->yaw_period) == 0 && (t / a->yaw_period) < a->n_yaw)
+      v->pos[2] = a->d_yaw[(int64_t)(t / a->yaw_period) * n + i]; /* set_now_yaw_world :57 */
+    us = (int16_t)(((t + 1) * 1000) & 0x7FFF);
+    if(a->sensor_mode == RK_SENSOR_PLANT) {
+      for(k = 0; k < 4; k++) {
+        uint8_t f[8];
+        plant_frame(&v->m[k], f);
+        motor_rx(&v->m[k], p->motor_dir[k], f, us);
+      }
+    } else if(a->sensor_mode == RK_SENSOR_STREAM) {
+      for(k = 0; k < 4; k++) {
+        uint8_t f[8];
+        memcpy(f, &a->d_frames[((int64_t)t * 4 + k) * n + i], 8);
+        motor_rx(&v->m[k], p->motor_dir[k], f, us);
+      }
+    }
+    veh_update(v, p);
+    if(a->d_trace) {
+      uint32_t *tr = a->d_trace + (int64_t)t * RK_VDT_TRACE_WORDS * n + i;
+      for(j = 0; j < 3; j++) {
+        tr[(int64_t)j * n]       = f2u(v->pos[j]);
+        tr[(int64_t)(3 + j) * n] = f2u(v->vel[j]);
+        tr[(int64_t)(6 + j) * n] = f2u(v->tgt[j]);
+      }
+      for(k = 0; k < 4; k++) tr[(int64_t)(9 + k) * n] = (uint32_t)(int32_t)v->m[k].cur_tgt;
+      for(j = 13; j < 16; j++) tr[(int64_t)j * n] = 0;
+    }
+  }
+  if(a->d_cost && a->d_goal) {
+    float dx = v->pos[0] - a->d_goal[2 * i], dy = v->pos[1] - a->d_goal[2 * i + 1];
+    a->d_cost[i] = dx * dx + dy * dy;
+  }
+}
+
+static uint32_t *soa(uint32_t *blk, int64_t n, int64_t i, int w) { return &blk[((int64_t)(w / 4) * n + i) * 4 + (w % 4)]; }
+
+typedef struct {
+  const rk_vdt_params_t  *p;
+  uint32_t               *state;
+  int64_t                 n, i0, i1;
+  const rk_vdt_rollout_t *args;
+  int                     tid, nthreads;
+} job_t;
+
+static void *job_main(void *arg) {
+  job_t   *jb = (job_t *)arg;
+  uint32_t w[RK_VS_WORDS];
+  veh_t    v;
+  int64_t  i;
+  int      k;
+  for(i = jb->i0 + jb->tid; i < jb->i1; i += jb->nthreads) {
+    if(jb->state) {
+      for(k = 0; k < RK_VS_WORDS; k++) w[k] = *soa(jb->state, jb->n, i, k);
+    } else {
+      memset(w, 0, sizeof(w));
+    }
+    unpack(&v, w);
+    rollout_one(&v, jb->p, jb->n, i, jb->args);
+    if(jb->state) {
+      pack(&v, w);
+      for(k = 0; k < RK_VS_WORDS; k++) *soa(jb->state, jb->n, i, k) = w[k];
+    }
+  }
+  return NULL;
+}
+
+void orc_vdt_rollout(const rk_vdt_params_t *p, uint32_t *state, int64_t n, int64_t i0, int64_t i1,
+                     const rk_vdt_rollout_t *args, int nthreads) {
+  job_t     jobs[256];
+  pthread_t th[256];
+  int       t;
+  if(nthreads < 1) nthreads = 1;
+  if(nthreads > 256) nthreads = 256;
+  for(t = 0; t < nthreads; t++) {
+    jobs[t].p = p, jobs[t].state = state, jobs[t].n = n, jobs[t].i0 = i0, jobs[t].i1 = i1;
+    jobs[t].args = args, jobs[t].tid = t, jobs[t].nthreads = nthreads;
+  }
+  if(nthreads == 1) {
+    job_main(&jobs[0]);
+    return;
+  }
+  for(t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, job_main, &jobs[t]);
+  for(t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+}
+
+void orc_vdt_set_target(const rk_vdt_params_t *p, uint32_t *words, const float v[3], const float a[3], const float j[3]) {
+  veh_t s;
+  (void)p;
+  unpack(&s, words);
+  veh_set_target(&s, v, a, j);
+  pack(&s, words);
+}
+void orc_vdt_rx(const rk_vdt_params_t *p, uint32_t *words, int wheel, const uint8_t frame[8], int16_t usec_id) {
+  veh_t s;
+  unpack(&s, words);
+  motor_rx(&s.m[wheel], p->motor_dir[wheel], frame, usec_id);
+  pack(&s, words);
+}
+void orc_vdt_update(const rk_vdt_params_t *p, uint32_t *words) {
+  veh_t s;
+  unpack(&s, words);
+  veh_update(&s, p);
+  pack(&s, words);
+}

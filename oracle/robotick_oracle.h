@@ -1,0 +1,37 @@
+/* TEST INFRASTRUCTURE (oracle) -- never linked into the product library.
+ *
+ * Plain-C restatement of the reference's numeric control tick; see robotick_oracle.c.
+ * Pinned against oracle/_ref (the unmodified reference compiled for x86) by
+ * tests/test_oracle_pin.py and against the golden fixtures in tests/golden/.
+ */
+#ifndef ROBOTICK_ORACLE_H_
+#define ROBOTICK_ORACLE_H_
+
+#include "robotick.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same contract as rk_vdt_rollout() on HOST arrays (same SoA indexing with pitch n), for
+ * instances [i0, i1) on nthreads host threads.  state == NULL: power-on state, results
+ * discarded (throughput runs). */
+void orc_vdt_rollout(const rk_vdt_params_t *p, uint32_t *state, int64_t n, int64_t i0, int64_t i1,
+                     const rk_vdt_rollout_t *args, int nthreads);
+/* VEHICLE_CTRL::set_target_vel on one AoS state (RK_VS_WORDS words) */
+void orc_vdt_set_target(const rk_vdt_params_t *p, uint32_t *words, const float v[3], const float a[3],
+                        const float j[3]);
+/* MOTOR_IF_M2006::rx_callback on one AoS state */
+void orc_vdt_rx(const rk_vdt_params_t *p, uint32_t *words, int wheel, const uint8_t frame[8], int16_t usec_id);
+/* VEHICLE_CTRL::update on one AoS state */
+void orc_vdt_update(const rk_vdt_params_t *p, uint32_t *words);
+
+float orc_sin(float x);
+float orc_cos(float x);
+float orc_normalize_rad_0to2pi(float x);
+float orc_normalize_deg_0to360(float x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,147 @@
+"""ctypes view of include/robotick.h -- the C-ABI of librobotick_b200.so.
+
+The library is the product: hand-written CUDA for sm_100a behind plain-C entry points.
+There is no Python/CPU fallback; `load()` raises when the library has not been built.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librobotick_b200.so")
+
+RK_OK = 0
+
+# ---- enums of robotick.h -------------------------------------------------------------
+RK_SENSOR_HOLD, RK_SENSOR_PLANT, RK_SENSOR_STREAM = 0, 1, 2
+RK_CMD_NONE, RK_CMD_MOVE, RK_CMD_STOP = 0, 1, 2
+RK_VDT_TRACE_WORDS = 16
+
+
+class VdtParams(C.Structure):
+    """rk_vdt_params_t"""
+
+    _fields_ = [
+        ("wheel_radius_mm", C.c_float),
+        ("wheel_l_mm", C.c_float),
+        ("sqrtf2", C.c_float),
+        ("ts", C.c_float),
+        ("ctrl_freq", C.c_float),
+        ("kff", C.c_float),
+        ("kp", C.c_float),
+        ("ki", C.c_float),
+        ("kd", C.c_float),
+        ("i_limit", C.c_float),
+        ("lpf_freq", C.c_float),
+        ("ff_limit", C.c_float),
+        ("accel_move", C.c_float * 3),
+        ("jerk_move", C.c_float * 3),
+        ("accel_stop", C.c_float * 3),
+        ("jerk_stop", C.c_float * 3),
+        ("motor_dir", C.c_int32 * 4),
+        ("raw_curr_lim", C.c_int32),
+    ]
+
+
+class VdtCmd(C.Structure):
+    """rk_vdt_cmd_t"""
+
+    _fields_ = [("vx", C.c_float), ("vy", C.c_float), ("vth", C.c_float), ("kind", C.c_int32)]
+
+
+class VdtRollout(C.Structure):
+    """rk_vdt_rollout_t (pointers are device pointers for the library, host for the oracle)"""
+
+    _fields_ = [
+        ("steps", C.c_int32),
+        ("sensor_mode", C.c_int32),
+        ("d_cmd", C.c_void_p),
+        ("n_seg", C.c_int32),
+        ("seg_len", C.c_int32),
+        ("d_yaw", C.c_void_p),
+        ("n_yaw", C.c_int32),
+        ("yaw_period", C.c_int32),
+        ("d_frames", C.c_void_p),
+        ("d_trace", C.c_void_p),
+        ("d_goal", C.c_void_p),
+        ("d_cost", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+class RobotickError(RuntimeError):
+    pass
+
+
+def _proto(lib):
+    vp = C.c_void_p
+    lib.rk_version.restype = C.c_int
+    lib.rk_last_error.restype = C.c_char_p
+    lib.rk_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+    lib.rk_vdt_default_params.argtypes = [C.POINTER(VdtParams)]
+    lib.rk_vdt_default_params.restype = None
+    lib.rk_vdt_state_words.restype = C.c_size_t
+    lib.rk_vdt_state_bytes.argtypes = [C.c_int64]
+    lib.rk_vdt_state_bytes.restype = C.c_size_t
+    lib.rk_vdt_rollout.argtypes = [C.POINTER(VdtParams), vp, C.c_int64, C.POINTER(VdtRollout), vp]
+    lib.rk_vdt_set_power.argtypes = [vp, C.c_int64, vp, vp]
+    lib.rk_vdt_set_target_vel.argtypes = [C.POINTER(VdtParams), vp, C.c_int64, vp, vp, vp, vp]
+    lib.rk_vdt_motor_rx.argtypes = [C.POINTER(VdtParams), vp, C.c_int64, C.c_int, vp, vp, vp]
+    lib.rk_vdt_create.argtypes = [C.POINTER(vp), C.POINTER(VdtParams)]
+    lib.rk_vdt_destroy.argtypes = [vp]
+    lib.rk_vdt_destroy.restype = None
+    for name in ("rk_vdt_update", "rk_vdt_start", "rk_vdt_stop"):
+        getattr(lib, name).argtypes = [vp]
+    f3 = C.POINTER(C.c_float)
+    lib.rk_vdt_set_target.argtypes = [vp, f3, f3, f3]
+    lib.rk_vdt_set_yaw.argtypes = [vp, C.c_float]
+    lib.rk_vdt_rx.argtypes = [vp, C.c_int, C.c_char_p, C.c_int16]
+    for name in ("rk_vdt_get_pos", "rk_vdt_get_vel", "rk_vdt_get_vel_tgt"):
+        getattr(lib, name).argtypes = [vp, f3]
+    lib.rk_vdt_get_raw_current.argtypes = [vp, C.POINTER(C.c_int16)]
+    lib.rk_vdt_get_angle_sum.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.rk_vdt_get_state.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.rk_vdt_set_state.argtypes = [vp, C.POINTER(C.c_uint32)]
+    return lib
+
+
+def load():
+    """dlopen librobotick_b200.so (built by `python -m ...build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RobotickError(
+                f"{LIB_PATH} is not built: run __graft_entry__.build() (nvcc, sm_100a). "
+                "There is no CPU fallback."
+            )
+        _lib = _proto(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(rc):
+    if rc != RK_OK:
+        msg = load().rk_last_error()
+        raise RobotickError(f"robotick call failed rc={rc}: {msg.decode() if msg else ''}")
+
+
+def default_params():
+    """The firmware constants (VD_task_main.cpp:22-48,75-108,157-160); must equal
+    rk_vdt_default_params() -- tests/test_cabi_cpu.py checks that."""
+    p = VdtParams()
+    p.wheel_radius_mm = 37.5
+    p.wheel_l_mm = 13.08148
+    p.sqrtf2 = 1.41421356
+    p.ts = 0.001  # float(1.0f/1000.0f) == float(0.001)
+    p.ctrl_freq = 100.0
+    p.kff, p.kp, p.ki, p.kd = 0.0075, 0.02, 0.01, 0.0
+    p.i_limit = 0.5
+    p.lpf_freq = 10.0
+    p.ff_limit = 1.0
+    p.accel_move[:] = [1000.0, 1000.0, 30.0]
+    p.jerk_move[:] = [10000.0, 10000.0, 300.0]
+    p.accel_stop[:] = [2000.0, 2000.0, 70.0]
+    p.jerk_stop[:] = [30000.0, 30000.0, 1000.0]
+    p.motor_dir[:] = [1, 1, -1, -1]
+    p.raw_curr_lim = 3000
+    return p

@@ -1,0 +1,73 @@
+"""State-block layout of include/robotick.h ("SoA of 128-bit planes") for host code.
+
+word w of instance i of an n-instance block lives at  u32[((w // 4) * n + i) * 4 + (w % 4)].
+AoS views ([n, WORDS] uint32) are for tests and host tooling only.
+"""
+import numpy as np
+
+# ---- vehicle (RK_VS_*) ----------------------------------------------------------------
+VS_POS_X, VS_POS_Y, VS_POS_TH, VS_FLAGS = 0, 1, 2, 3
+VS_VEL_X, VS_VEL_Y, VS_VEL_TH, VS_TGT_X = 4, 5, 6, 7
+VS_TGT_Y, VS_TGT_TH = 8, 9
+VS_INTERP0 = 12
+VS_CTRL0 = VS_INTERP0 + 3 * 12
+VS_MOTOR0 = VS_CTRL0 + 4 * 8
+VS_WORDS = VS_MOTOR0 + 4 * 8
+VS_FLAG_POWER_ON = 1
+
+VI_VEL_NOW, VI_ACL_NOW, VI_VEL_TGT, VI_ACL_MAX = 0, 1, 2, 3
+VI_JERK_P, VI_JERK_M, VI_DT1, VI_DT2 = 4, 5, 6, 7
+VI_DT3, VI_VEL_INI, VI_ACL_INI, VI_DT = 8, 9, 10, 11
+
+VC_PREV_VAL, VC_INTEG, VC_LPF_Y, VC_LPF_X = 0, 1, 2, 3
+VC_NOW_TGT, VC_NOW_ERR, VC_NOW_CTRL = 4, 5, 6
+
+VM_SUM_LO, VM_SUM_HI, VM_PREV_LO, VM_PREV_HI = 0, 1, 2, 3
+VM_ANG_RPM, VM_CUR_TGT, VM_USEC, VM_PLANT = 4, 5, 6, 7
+
+assert VS_WORDS == 112
+
+
+def soa_to_aos(block, n, words):
+    """[planes, n, 4] SoA block (any uint32 array of words*n elements) -> [n, words]."""
+    b = np.asarray(block, dtype=np.uint32).reshape(words // 4, n, 4)
+    return np.ascontiguousarray(b.transpose(1, 0, 2)).reshape(n, words)
+
+
+def aos_to_soa(aos):
+    """[n, words] -> flat SoA block (uint32, words*n)."""
+    a = np.asarray(aos, dtype=np.uint32)
+    n, words = a.shape
+    return np.ascontiguousarray(a.reshape(n, words // 4, 4).transpose(1, 0, 2)).reshape(-1)
+
+
+def f32(words):
+    return np.asarray(words, dtype=np.uint32).view(np.float32)
+
+
+def s16_lo(words):
+    return (np.asarray(words, dtype=np.uint32) & 0xFFFF).astype(np.uint16).view(np.int16)
+
+
+def s16_hi(words):
+    return (np.asarray(words, dtype=np.uint32) >> 16).astype(np.uint16).view(np.int16)
+
+
+def vehicle_view(aos):
+    """Decode an [n, VS_WORDS] AoS vehicle state into named numpy arrays (copies)."""
+    a = np.asarray(aos, dtype=np.uint32)
+    out = {
+        "pos": f32(a[:, VS_POS_X : VS_POS_X + 3]),
+        "power_on": (a[:, VS_FLAGS] & VS_FLAG_POWER_ON) != 0,
+        "vel": f32(a[:, VS_VEL_X : VS_VEL_X + 3]),
+        "vel_tgt": f32(a[:, VS_TGT_X : VS_TGT_X + 3]),
+    }
+    m = a[:, VS_MOTOR0:VS_WORDS].reshape(-1, 4, 8)
+    lo = m[:, :, VM_SUM_LO].astype(np.uint64)
+    hi = m[:, :, VM_SUM_HI].astype(np.uint64)
+    out["angle_sum"] = ((hi << np.uint64(32)) | lo).view(np.int64)
+    out["raw_angle"] = s16_lo(m[:, :, VM_ANG_RPM])
+    out["raw_rpm"] = s16_hi(m[:, :, VM_ANG_RPM])
+    out["raw_cur"] = s16_lo(m[:, :, VM_CUR_TGT])
+    out["cur_tgt"] = s16_hi(m[:, :, VM_CUR_TGT])
+    return out

@@ -1,0 +1,100 @@
+"""Seeded synthetic command / sensor streams.
+
+Everything here is host-side input generation: counter-based (splitmix64 of
+(seed, stream, instance, index)), vectorised numpy, float32 results produced only from
+exactly-representable integer arithmetic or IEEE float32 ops, so the SAME arrays feed the
+CUDA engine, the C port and the compiled reference.
+"""
+import numpy as np
+
+from . import _cabi
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    x = (np.asarray(x, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15)) & _M64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+    return z ^ (z >> np.uint64(31))
+
+
+def _hash(seed, stream, inst, idx):
+    with np.errstate(over="ignore"):
+        h = splitmix64(np.uint64(seed) ^ (np.uint64(stream) * np.uint64(0xD6E8FEB86659FD93)))
+        h = splitmix64(h ^ np.asarray(inst, dtype=np.uint64))
+        h = splitmix64(h ^ (np.asarray(idx, dtype=np.uint64) * np.uint64(0xA0761D6478BD642F)))
+    return h
+
+
+def _u01(h):
+    """24-bit uniform in [0,1) as exact float32."""
+    return (h >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def vehicle_commands(n, n_seg, seed=0x5EED, first=0, stop_every=8):
+    """C2 command schedule: [n_seg, n] rk_vdt_cmd_t records (structured array).
+
+    vx, vy ~ U[-400, 400] mm/s norm-clamped to 400 exactly as speed_limit_xy() does
+    (VD_task_main.cpp:127-137); vth ~ U[-2*pi, 2*pi] clamped by speed_limit_rot() (:139-142);
+    one segment in `stop_every` is a MOVE_STOP (zero target, STOP accel/jerk tables).
+    """
+    inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[None, :]
+    seg = np.arange(n_seg, dtype=np.uint64)[:, None]
+    f32 = np.float32
+    vx = _u01(_hash(seed, 1, inst, seg)) * f32(800.0) - f32(400.0)
+    vy = _u01(_hash(seed, 2, inst, seg)) * f32(800.0) - f32(400.0)
+    vth = _u01(_hash(seed, 3, inst, seg)) * f32(4.0 * np.pi) - f32(2.0 * np.pi)
+    # speed_limit_xy: sqrt, clamp, x*lim/len  (all IEEE float32, left to right)
+    ln = np.sqrt(vx * vx + vy * vy, dtype=np.float32)
+    lim = np.minimum(ln, f32(400.0))
+    nz = ln != 0
+    safe = np.where(nz, ln, f32(1.0))
+    vx = np.where(nz, (vx * lim) / safe, f32(0.0)).astype(np.float32)
+    vy = np.where(nz, (vy * lim) / safe, f32(0.0)).astype(np.float32)
+    rl = f32(6.0 * np.pi)
+    vth = np.clip(vth, -rl, rl).astype(np.float32)
+    stop = (_hash(seed, 4, inst, seg) % np.uint64(stop_every)) == 0
+    cmd = np.zeros((n_seg, n), dtype=np.dtype([("vx", "<f4"), ("vy", "<f4"), ("vth", "<f4"), ("kind", "<i4")]))
+    cmd["vx"] = np.where(stop, f32(0), vx)
+    cmd["vy"] = np.where(stop, f32(0), vy)
+    cmd["vth"] = np.where(stop, f32(0), vth)
+    cmd["kind"] = np.where(stop, _cabi.RK_CMD_STOP, _cabi.RK_CMD_MOVE)
+    return cmd
+
+
+DEG2RAD = np.float32(np.float32(3.14159265358979) / np.float32(180.0))  # util_mymath.hpp:13
+
+
+def vehicle_yaw(n, n_yaw, seed=0x5EED, first=0):
+    """Yaw stream at the IMU rate: integer-stepped triangle wave in whole degrees in
+    [-180, 180), converted with mymath::deg2rad (util_mymath.hpp:16).  [n_yaw, n] float32."""
+    inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[None, :]
+    k = np.arange(n_yaw, dtype=np.int64)[:, None]
+    phase = (_hash(seed, 5, inst, 0) % np.uint64(720)).astype(np.int64)
+    rate = (_hash(seed, 6, inst, 0) % np.uint64(5)).astype(np.int64) + 1  # deg per IMU sample
+    u = (phase + rate * k) % 720
+    deg = np.where(u < 360, u - 180, 539 - u)  # -180..179 then 179..-180
+    return (deg.astype(np.float32) * DEG2RAD).astype(np.float32)
+
+
+def vehicle_frames(n, steps, seed=0x5EED, first=0):
+    """RK_SENSOR_STREAM input: [steps, 4, n] uint64 M2006 feedback frames
+    (VD_motor_if_m2006.hpp:13-21, big-endian angle/speed/current) from a per-wheel random
+    walk: rpm wanders within +-8000, the angle integrates it and wraps at 8192."""
+    inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[None, None, :]
+    w = np.arange(4, dtype=np.uint64)[None, :, None]
+    t = np.arange(steps, dtype=np.uint64)[:, None, None]
+    dr = (_hash(seed, 7, inst * np.uint64(4) + w, t) % np.uint64(401)).astype(np.int64) - 200
+    rpm = np.clip(np.cumsum(dr, axis=0), -8000, 8000)
+    ang = np.cumsum((rpm * 8192) // 60000, axis=0) % 8192
+    cur = (_hash(seed, 8, inst * np.uint64(4) + w, t) % np.uint64(6001)).astype(np.int64) - 3000
+    b = np.zeros((steps, 4, n, 8), dtype=np.uint8)
+    b[..., 0] = (ang >> 8) & 255
+    b[..., 1] = ang & 255
+    b[..., 2] = (rpm >> 8) & 255
+    b[..., 3] = rpm & 255
+    b[..., 4] = (cur >> 8) & 255
+    b[..., 5] = cur & 255
+    return b.view(np.uint64).reshape(steps, 4, n)

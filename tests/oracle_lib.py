@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE: ctypes loaders for the oracles.
+
+  port()  -> oracle/liboracle_port.so   plain-C restatement (always available; built by
+             oracle/Makefile / __graft_entry__.build())
+  ref()   -> oracle/_ref/libref_vdt.so  the UNMODIFIED reference compiled for x86 (built
+             where /root/reference exists; the prebuilt .so travels to the GPU box)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import roboken_fmskf_robot_controller_b200 as rk
+from roboken_fmskf_robot_controller_b200 import _cabi, layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE = os.path.join(ROOT, "oracle")
+
+_cache = {}
+
+
+def _build(target):
+    subprocess.run(["make", "-s", "-C", ORACLE, target], check=True, capture_output=True)
+
+
+def port():
+    if "port" not in _cache:
+        path = os.path.join(ORACLE, "liboracle_port.so")
+        if not os.path.exists(path):
+            _build("port")
+        lib = C.CDLL(path)
+        vp = C.c_void_p
+        lib.orc_vdt_rollout.argtypes = [C.POINTER(_cabi.VdtParams), vp, C.c_int64, C.c_int64, C.c_int64,
+                                        C.POINTER(_cabi.VdtRollout), C.c_int]
+        lib.orc_vdt_rollout.restype = None
+        f3 = C.POINTER(C.c_float)
+        lib.orc_vdt_set_target.argtypes = [C.POINTER(_cabi.VdtParams), vp, f3, f3, f3]
+        lib.orc_vdt_rx.argtypes = [C.POINTER(_cabi.VdtParams), vp, C.c_int, C.c_char_p, C.c_int16]
+        lib.orc_vdt_update.argtypes = [C.POINTER(_cabi.VdtParams), vp]
+        for nm in ("orc_sin", "orc_cos", "orc_normalize_rad_0to2pi", "orc_normalize_deg_0to360"):
+            getattr(lib, nm).argtypes = [C.c_float]
+            getattr(lib, nm).restype = C.c_float
+        _cache["port"] = lib
+    return _cache["port"]
+
+
+def have_ref(name="libref_vdt.so"):
+    return os.path.exists(os.path.join(ORACLE, "_ref", name)) or os.path.isdir("/root/reference/src")
+
+
+def ref(name="libref_vdt.so"):
+    if name not in _cache:
+        path = os.path.join(ORACLE, "_ref", name)
+        if not os.path.exists(path):
+            _build("ref")
+        lib = C.CDLL(path)
+        vp = C.c_void_p
+        if name.startswith("libref_vdt"):
+            lib.ref_vdt_create.restype = vp
+            lib.ref_vdt_destroy.argtypes = [vp]
+            lib.ref_vdt_start.argtypes = [vp]
+            lib.ref_vdt_stop.argtypes = [vp]
+            f3 = C.POINTER(C.c_float)
+            lib.ref_vdt_set_target.argtypes = [vp, f3, f3, f3]
+            lib.ref_vdt_set_yaw.argtypes = [vp, C.c_float]
+            lib.ref_vdt_rx.argtypes = [vp, C.c_int, C.c_char_p, C.c_int16]
+            lib.ref_vdt_update.argtypes = [vp]
+            lib.ref_vdt_export.argtypes = [vp, vp]
+            lib.ref_vdt_import.argtypes = [vp, vp]
+            lib.ref_vdt_get.argtypes = [vp, f3, f3, f3, C.POINTER(C.c_int16)]
+            lib.ref_vdt_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_cabi.VdtRollout), C.c_int]
+            lib.ref_vdt_rollout.restype = None
+            for nm in ("ref_normalize_rad_0to2pi", "ref_normalize_deg_0to360", "ref_atanf", "ref_sinf",
+                       "ref_cosf", "ref_sqrtf"):
+                getattr(lib, nm).argtypes = [C.c_float]
+                getattr(lib, nm).restype = C.c_float
+            lib.ref_atan2f.argtypes = [C.c_float, C.c_float]
+            lib.ref_atan2f.restype = C.c_float
+        _cache[name] = lib
+    return _cache[name]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HostRollout:
+    """Builds an rk_vdt_rollout_t over HOST numpy arrays and keeps them alive."""
+
+    def __init__(self, n, steps, sensor_mode, cmd=None, seg_len=0, yaw=None, yaw_period=0, frames=None,
+                 trace=False, goal=None):
+        self.n = n
+        self.keep = [cmd, yaw, frames, goal]
+        self.trace = np.zeros((steps, _cabi.RK_VDT_TRACE_WORDS, n), dtype=np.uint32) if trace else None
+        self.cost = np.zeros(n, dtype=np.float32) if goal is not None else None
+        a = _cabi.VdtRollout()
+        a.steps, a.sensor_mode = steps, sensor_mode
+        a.d_cmd, a.n_seg, a.seg_len = _ptr(cmd), (0 if cmd is None else cmd.shape[0]), seg_len
+        a.d_yaw, a.n_yaw, a.yaw_period = _ptr(yaw), (0 if yaw is None else yaw.shape[0]), yaw_period
+        a.d_frames = _ptr(frames)
+        a.d_trace = _ptr(self.trace)
+        a.d_goal, a.d_cost = _ptr(goal), _ptr(self.cost)
+        self.args = a
+
+
+def run_port(state_soa, n, ro, params=None, nthreads=1):
+    p = params or rk.default_params()
+    port().orc_vdt_rollout(C.byref(p), _ptr(state_soa), n, 0, n, C.byref(ro.args), nthreads)
+
+
+def run_ref(state_soa, n, ro, nthreads=1, name="libref_vdt.so"):
+    ref(name).ref_vdt_rollout(_ptr(state_soa), n, 0, n, C.byref(ro.args), nthreads)
