@@ -49,6 +49,9 @@ int         rk_version(void);
 const char *rk_last_error(void); /* thread-local message of the last failing call */
 /* device properties the bench needs for its roofline (SM count, SM clock in kHz) */
 int rk_device_info(int device, int *sm_count, int *sm_clock_khz, size_t *hbm_bytes);
+/* Selects the CUDA device for subsequent calls of the calling thread (the library links its
+ * own static CUDA runtime; one process per GPU calls this once with LOCAL_RANK). */
+int rk_set_device(int device);
 
 /* =====================================================================================
  * Vehicle (src/VehicleDrive + the src/Utility math it calls)

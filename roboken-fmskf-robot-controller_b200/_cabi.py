@@ -79,6 +79,7 @@ def _proto(lib):
     lib.rk_version.restype = C.c_int
     lib.rk_last_error.restype = C.c_char_p
     lib.rk_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+    lib.rk_set_device.argtypes = [C.c_int]
     lib.rk_vdt_default_params.argtypes = [C.POINTER(VdtParams)]
     lib.rk_vdt_default_params.restype = None
     lib.rk_vdt_state_words.restype = C.c_size_t

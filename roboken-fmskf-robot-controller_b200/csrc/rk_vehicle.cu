@@ -1,0 +1,443 @@
+// rk_vehicle.cu -- vehicle kernels + their C-ABI entry points (include/robotick.h).
+#include <limits.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "rk_vehicle.cuh"
+
+namespace rk {
+
+// -----------------------------------------------------------------------------------------
+// Fused rollout: K ticks of VEHICLE_CTRL::update() per launch, one thread per robot, state
+// loaded once with 128-bit loads, held in registers for all K ticks, stored once.
+// MODE = RK_SENSOR_* ; TRACE writes the per-tick record (tests only).
+// -----------------------------------------------------------------------------------------
+constexpr int kRolloutThreads = 128;
+
+template <int MODE, bool TRACE>
+__global__ void __launch_bounds__(kRolloutThreads)
+vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
+  __shared__ float s_tab[513];
+  stage_sin_table(s_tab);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+
+  Veh v;
+  load_veh(state, n, i, v);
+  const Derived d = derive(p);
+  float         cth, sth;
+  yaw_trig(s_tab, v.pos[2], cth, sth);
+
+  const bool has_cmd  = a.d_cmd != nullptr && a.seg_len > 0 && a.n_seg > 0;
+  const bool has_yaw  = a.d_yaw != nullptr && a.yaw_period > 0 && a.n_yaw > 0;
+  int        next_cmd = has_cmd ? 0 : INT_MAX, seg = 0;
+  int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
+
+  for(int t = 0; t < a.steps; t++) {
+    if(t == next_cmd) { // VDT::main -> start(); set_target_vel()   VD_task_main.cpp:280-281,294-295
+      const uint4 cq = __ldcs(reinterpret_cast<const uint4 *>(a.d_cmd) + (int64_t)seg * n + i);
+      const int   kind = (int)cq.w;
+      if(kind != RK_CMD_NONE) {
+        const float vv[3] = {u2f(cq.x), u2f(cq.y), u2f(cq.z)};
+        v.flags |= RK_VS_FLAG_POWER_ON;
+        if(kind == RK_CMD_STOP)
+          veh_set_target(v, vv, p.accel_stop, p.jerk_stop);
+        else
+          veh_set_target(v, vv, p.accel_move, p.jerk_move);
+      }
+      seg++;
+      next_cmd = (seg < a.n_seg) ? next_cmd + a.seg_len : INT_MAX;
+    }
+    if(t == next_yaw) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
+      v.pos[2] = __ldcs(a.d_yaw + (int64_t)yk * n + i);
+      yaw_trig(s_tab, v.pos[2], cth, sth);
+      yk++;
+      next_yaw = (yk < a.n_yaw) ? next_yaw + a.yaw_period : INT_MAX;
+    }
+    if(MODE != RK_SENSOR_HOLD) {
+      const int32_t us = ((t + 1) * 1000) & 0x7FFF;
+#pragma unroll
+      for(int k = 0; k < 4; k++) {
+        uint64_t f;
+        if(MODE == RK_SENSOR_PLANT)
+          f = plant_frame(v.m[k]);
+        else
+          f = __ldcs(reinterpret_cast<const unsigned long long *>(a.d_frames) + ((int64_t)t * 4 + k) * n + i);
+        motor_rx(v.m[k], p.motor_dir[k], f, us);
+      }
+    }
+    veh_update(v, p, d, cth, sth);
+    if(TRACE) {
+      uint32_t *tr = a.d_trace + (int64_t)t * RK_VDT_TRACE_WORDS * n + i;
+#pragma unroll
+      for(int j = 0; j < 3; j++) {
+        tr[(int64_t)j * n]       = f2u(v.pos[j]);
+        tr[(int64_t)(3 + j) * n] = f2u(v.vel[j]);
+        tr[(int64_t)(6 + j) * n] = f2u(v.tgt[j]);
+      }
+#pragma unroll
+      for(int k = 0; k < 4; k++) tr[(int64_t)(9 + k) * n] = (uint32_t)v.m[k].cur_tgt;
+#pragma unroll
+      for(int j = 13; j < 16; j++) tr[(int64_t)j * n] = 0u;
+    }
+  }
+  store_veh(state, n, i, v);
+  if(a.d_cost != nullptr && a.d_goal != nullptr) {
+    const float2 g  = reinterpret_cast<const float2 *>(a.d_goal)[i];
+    const float  dx = fsub(v.pos[0], g.x), dy = fsub(v.pos[1], g.y);
+    a.d_cost[i]     = fadd(fmul(dx, dx), fmul(dy, dy));
+  }
+}
+
+// ---- small batched setters ------------------------------------------------------------
+__global__ void vdt_set_power_kernel(uint4 *state, int64_t n, const uint8_t *on) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  uint4 q = state[i]; // plane 0
+  bool  b = on ? (on[i] != 0) : true;
+  q.w     = b ? (q.w | RK_VS_FLAG_POWER_ON) : (q.w & ~RK_VS_FLAG_POWER_ON);
+  state[i] = q;
+}
+
+__global__ void vdt_set_target_kernel(uint4 *state, int64_t n, const float *v, const float *a, const float *j) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+#pragma unroll
+  for(int k = 0; k < 3; k++) {
+    Interp t;
+    load_interp(state, n, i, k, t);
+    interp_set(t, v[(int64_t)k * n + i], a[(int64_t)k * n + i], j[(int64_t)k * n + i]);
+    store_interp(state, n, i, k, t);
+  }
+}
+
+__global__ void vdt_motor_rx_kernel(const rk_vdt_params_t p, uint4 *state, int64_t n, int wheel,
+                                    const unsigned long long *frames, const int16_t *usec) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  Motor m;
+  load_motor(state, n, i, wheel, m);
+  motor_rx(m, p.motor_dir[wheel], frames[i], usec ? (int32_t)usec[i] : 0);
+  store_motor(state, n, i, wheel, m);
+}
+
+// single-instance pokes used by the handle API (arguments by value, one thread)
+__global__ void vdt_poke_word_kernel(uint32_t *state, int64_t idx, uint32_t val) { state[idx] = val; }
+__global__ void vdt_set_target1_kernel(uint4 *state, float v0, float v1, float v2, float a0, float a1, float a2,
+                                       float j0, float j1, float j2) {
+  const float v[3] = {v0, v1, v2}, a[3] = {a0, a1, a2}, j[3] = {j0, j1, j2};
+#pragma unroll
+  for(int k = 0; k < 3; k++) {
+    Interp t;
+    load_interp(state, 1, 0, k, t);
+    interp_set(t, v[k], a[k], j[k]);
+    store_interp(state, 1, 0, k, t);
+  }
+}
+__global__ void vdt_rx1_kernel(const rk_vdt_params_t p, uint4 *state, int wheel, unsigned long long frame, int usec) {
+  Motor m;
+  load_motor(state, 1, 0, wheel, m);
+  motor_rx(m, p.motor_dir[wheel], frame, usec);
+  store_motor(state, 1, 0, wheel, m);
+}
+
+// -----------------------------------------------------------------------------------------
+// host side
+// -----------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return RK_ERR_CUDA;
+}
+int require_device() {
+  int         cnt = 0;
+  cudaError_t e   = cudaGetDeviceCount(&cnt);
+  if(e != cudaSuccess || cnt == 0) {
+    set_error("no CUDA device (%s): librobotick_b200 has no CPU fallback", cudaGetErrorString(e));
+    cudaGetLastError();
+    return RK_ERR_CUDA;
+  }
+  return RK_OK;
+}
+
+static int check_block(const void *p, const char *name) {
+  if(p == nullptr || ((uintptr_t)p & 15u) != 0) {
+    set_error("%s must be a non-NULL 16-byte aligned device pointer", name);
+    return RK_ERR_ARG;
+  }
+  return RK_OK;
+}
+
+template <int MODE>
+static cudaError_t launch_rollout(const rk_vdt_params_t &p, void *d_state, int64_t n, const rk_vdt_rollout_t &a,
+                                  cudaStream_t st) {
+  const unsigned grid = (unsigned)((n + kRolloutThreads - 1) / kRolloutThreads);
+  if(a.d_trace)
+    vdt_rollout_kernel<MODE, true><<<grid, kRolloutThreads, 0, st>>>(p, (uint4 *)d_state, n, a);
+  else
+    vdt_rollout_kernel<MODE, false><<<grid, kRolloutThreads, 0, st>>>(p, (uint4 *)d_state, n, a);
+  return cudaGetLastError();
+}
+
+} // namespace rk
+
+using namespace rk;
+
+extern "C" {
+
+int         rk_version(void) { return RK_VERSION; }
+const char *rk_last_error(void) { return rk::g_err; }
+
+int rk_device_info(int device, int *sm_count, int *sm_clock_khz, size_t *hbm_bytes) {
+  if(int rc = require_device()) return rc;
+  cudaDeviceProp prop;
+  RK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if(sm_count) *sm_count = prop.multiProcessorCount;
+  if(sm_clock_khz) {
+    int khz = 0;
+    RK_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    *sm_clock_khz = khz;
+  }
+  if(hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+  return RK_OK;
+}
+
+int rk_set_device(int device) {
+  if(int rc = require_device()) return rc;
+  RK_CUDA(cudaSetDevice(device));
+  return RK_OK;
+}
+
+void rk_vdt_default_params(rk_vdt_params_t *p) {
+  if(!p) return;
+  memset(p, 0, sizeof(*p));
+  p->wheel_radius_mm = 37.5f;
+  p->wheel_l_mm      = 13.08148f;
+  p->sqrtf2          = 1.41421356f;
+  p->ts              = 1.0f / (float)1000;
+  p->ctrl_freq       = (float)100;
+  p->kff = 0.0075f, p->kp = 0.02f, p->ki = 0.01f, p->kd = 0.0f;
+  p->i_limit  = 0.5f;
+  p->lpf_freq = 10.0f;
+  p->ff_limit = 1.0f;
+  const float am[3] = {1000.0f, 1000.0f, 30.0f}, jm[3] = {10000.0f, 10000.0f, 300.0f};
+  const float as[3] = {2000.0f, 2000.0f, 70.0f}, js[3] = {30000.0f, 30000.0f, 1000.0f};
+  for(int k = 0; k < 3; k++) p->accel_move[k] = am[k], p->jerk_move[k] = jm[k], p->accel_stop[k] = as[k], p->jerk_stop[k] = js[k];
+  p->motor_dir[0] = 1, p->motor_dir[1] = 1, p->motor_dir[2] = -1, p->motor_dir[3] = -1;
+  p->raw_curr_lim = 3000;
+}
+
+size_t rk_vdt_state_words(void) { return RK_VS_WORDS; }
+size_t rk_vdt_state_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_VS_WORDS * 4u; }
+
+int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_vdt_rollout_t *args, void *stream) {
+  if(!p || !args) {
+    set_error("rk_vdt_rollout: NULL params/args");
+    return RK_ERR_ARG;
+  }
+  if(n == 0 || args->steps == 0) return RK_OK;
+  if(n < 0 || args->steps < 0) {
+    set_error("rk_vdt_rollout: negative n or steps");
+    return RK_ERR_ARG;
+  }
+  if(int rc = check_block(d_state, "d_state")) return rc;
+  if(args->d_cmd && (((uintptr_t)args->d_cmd & 15u) != 0)) {
+    set_error("rk_vdt_rollout: d_cmd must be 16-byte aligned");
+    return RK_ERR_ARG;
+  }
+  if(args->sensor_mode == RK_SENSOR_STREAM && (!args->d_frames || ((uintptr_t)args->d_frames & 7u) != 0)) {
+    set_error("rk_vdt_rollout: RK_SENSOR_STREAM needs 8-byte aligned d_frames");
+    return RK_ERR_ARG;
+  }
+  if(int rc = require_device()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t  e;
+  switch(args->sensor_mode) {
+  case RK_SENSOR_HOLD: e = launch_rollout<RK_SENSOR_HOLD>(*p, d_state, n, *args, st); break;
+  case RK_SENSOR_PLANT: e = launch_rollout<RK_SENSOR_PLANT>(*p, d_state, n, *args, st); break;
+  case RK_SENSOR_STREAM: e = launch_rollout<RK_SENSOR_STREAM>(*p, d_state, n, *args, st); break;
+  default: set_error("rk_vdt_rollout: bad sensor_mode %d", args->sensor_mode); return RK_ERR_ARG;
+  }
+  if(e != cudaSuccess) return cuda_fail(e, "vdt_rollout_kernel launch");
+  return RK_OK;
+}
+
+int rk_vdt_set_power(void *d_state, int64_t n, const uint8_t *d_on, void *stream) {
+  if(n <= 0) return RK_OK;
+  if(int rc = check_block(d_state, "d_state")) return rc;
+  if(int rc = require_device()) return rc;
+  vdt_set_power_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint4 *)d_state, n, d_on);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_vdt_set_target_vel(const rk_vdt_params_t *p, void *d_state, int64_t n, const float *d_v, const float *d_a,
+                          const float *d_j, void *stream) {
+  (void)p;
+  if(n <= 0) return RK_OK;
+  if(!d_v || !d_a || !d_j) {
+    set_error("rk_vdt_set_target_vel: NULL v/a/j");
+    return RK_ERR_ARG;
+  }
+  if(int rc = check_block(d_state, "d_state")) return rc;
+  if(int rc = require_device()) return rc;
+  vdt_set_target_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_state, n, d_v, d_a, d_j);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_vdt_motor_rx(const rk_vdt_params_t *p, void *d_state, int64_t n, int wheel, const uint64_t *d_frames,
+                    const int16_t *d_usec, void *stream) {
+  if(n <= 0) return RK_OK;
+  if(!p || !d_frames || wheel < 0 || wheel > 3) {
+    set_error("rk_vdt_motor_rx: bad arguments");
+    return RK_ERR_ARG;
+  }
+  if(int rc = check_block(d_state, "d_state")) return rc;
+  if(int rc = require_device()) return rc;
+  vdt_motor_rx_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      *p, (uint4 *)d_state, n, wheel, (const unsigned long long *)d_frames, d_usec);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+// ---- single-instance handle: a batch of one on the same kernels -------------------------
+struct rk_vdt {
+  rk_vdt_params_t p;
+  uint32_t       *d_state; // RK_VS_WORDS words, n = 1
+  uint32_t       *h_stage; // pinned
+  cudaStream_t    st;
+};
+
+int rk_vdt_create(rk_vdt_t **out, const rk_vdt_params_t *p) {
+  if(!out) {
+    set_error("rk_vdt_create: NULL out");
+    return RK_ERR_ARG;
+  }
+  *out = nullptr;
+  if(int rc = require_device()) return rc;
+  rk_vdt *h = new rk_vdt();
+  if(p)
+    h->p = *p;
+  else
+    rk_vdt_default_params(&h->p);
+  cudaError_t e = cudaMalloc((void **)&h->d_state, RK_VS_WORDS * 4);
+  if(e == cudaSuccess) e = cudaMallocHost((void **)&h->h_stage, RK_VS_WORDS * 4);
+  if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  if(e == cudaSuccess) e = cudaMemsetAsync(h->d_state, 0, RK_VS_WORDS * 4, h->st); // power-on = zero-initialised statics
+  if(e != cudaSuccess) {
+    int rc = cuda_fail(e, "rk_vdt_create");
+    rk_vdt_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return RK_OK;
+}
+
+void rk_vdt_destroy(rk_vdt_t *h) {
+  if(!h) return;
+  if(h->st) {
+    cudaStreamSynchronize(h->st);
+    cudaStreamDestroy(h->st);
+  }
+  if(h->d_state) cudaFree(h->d_state);
+  if(h->h_stage) cudaFreeHost(h->h_stage);
+  delete h;
+}
+
+int rk_vdt_update(rk_vdt_t *h) {
+  if(!h) return RK_ERR_ARG;
+  rk_vdt_rollout_t a;
+  memset(&a, 0, sizeof(a));
+  a.steps       = 1;
+  a.sensor_mode = RK_SENSOR_HOLD;
+  return rk_vdt_rollout(&h->p, h->d_state, 1, &a, h->st);
+}
+
+static int poke(rk_vdt_t *h, int word, uint32_t val) {
+  vdt_poke_word_kernel<<<1, 1, 0, h->st>>>(h->d_state, (int64_t)word, val); // n = 1: SoA index == word
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_vdt_start(rk_vdt_t *h) {
+  if(!h) return RK_ERR_ARG;
+  return rk_vdt_set_power(h->d_state, 1, nullptr, h->st);
+}
+int rk_vdt_stop(rk_vdt_t *h) {
+  if(!h) return RK_ERR_ARG;
+  // flags word only carries isPowerOn
+  return poke(h, RK_VS_FLAGS, 0u);
+}
+int rk_vdt_set_target(rk_vdt_t *h, const float v[3], const float a[3], const float j[3]) {
+  if(!h || !v || !a || !j) return RK_ERR_ARG;
+  vdt_set_target1_kernel<<<1, 1, 0, h->st>>>((uint4 *)h->d_state, v[0], v[1], v[2], a[0], a[1], a[2], j[0], j[1], j[2]);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+int rk_vdt_set_yaw(rk_vdt_t *h, float yaw_rad) {
+  if(!h) return RK_ERR_ARG;
+  uint32_t u;
+  memcpy(&u, &yaw_rad, 4);
+  return poke(h, RK_VS_POS_TH, u);
+}
+int rk_vdt_rx(rk_vdt_t *h, int wheel, const uint8_t frame[8], int16_t usec_id) {
+  if(!h || !frame || wheel < 0 || wheel > 3) return RK_ERR_ARG;
+  unsigned long long f;
+  memcpy(&f, frame, 8);
+  vdt_rx1_kernel<<<1, 1, 0, h->st>>>(h->p, (uint4 *)h->d_state, wheel, f, (int)usec_id);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_vdt_get_state(rk_vdt_t *h, uint32_t words[RK_VS_WORDS]) {
+  if(!h || !words) return RK_ERR_ARG;
+  RK_CUDA(cudaMemcpyAsync(h->h_stage, h->d_state, RK_VS_WORDS * 4, cudaMemcpyDeviceToHost, h->st));
+  RK_CUDA(cudaStreamSynchronize(h->st));
+  memcpy(words, h->h_stage, RK_VS_WORDS * 4); // n = 1: SoA == AoS
+  return RK_OK;
+}
+int rk_vdt_set_state(rk_vdt_t *h, const uint32_t words[RK_VS_WORDS]) {
+  if(!h || !words) return RK_ERR_ARG;
+  RK_CUDA(cudaStreamSynchronize(h->st));
+  memcpy(h->h_stage, words, RK_VS_WORDS * 4);
+  RK_CUDA(cudaMemcpyAsync(h->d_state, h->h_stage, RK_VS_WORDS * 4, cudaMemcpyHostToDevice, h->st));
+  RK_CUDA(cudaStreamSynchronize(h->st));
+  return RK_OK;
+}
+static int get3(rk_vdt_t *h, int word0, float out[3]) {
+  uint32_t w[RK_VS_WORDS];
+  if(int rc = rk_vdt_get_state(h, w)) return rc;
+  memcpy(out, &w[word0], 12);
+  return RK_OK;
+}
+int rk_vdt_get_pos(rk_vdt_t *h, float out[3]) { return (h && out) ? get3(h, RK_VS_POS_X, out) : RK_ERR_ARG; }
+int rk_vdt_get_vel(rk_vdt_t *h, float out[3]) { return (h && out) ? get3(h, RK_VS_VEL_X, out) : RK_ERR_ARG; }
+int rk_vdt_get_vel_tgt(rk_vdt_t *h, float out[3]) { return (h && out) ? get3(h, RK_VS_TGT_X, out) : RK_ERR_ARG; }
+int rk_vdt_get_raw_current(rk_vdt_t *h, int16_t out[4]) {
+  if(!h || !out) return RK_ERR_ARG;
+  uint32_t w[RK_VS_WORDS];
+  if(int rc = rk_vdt_get_state(h, w)) return rc;
+  for(int k = 0; k < 4; k++) out[k] = (int16_t)(w[RK_VS_MOTOR0 + 8 * k + RK_VM_CUR_TGT] >> 16);
+  return RK_OK;
+}
+int rk_vdt_get_angle_sum(rk_vdt_t *h, int64_t out[4]) {
+  if(!h || !out) return RK_ERR_ARG;
+  uint32_t w[RK_VS_WORDS];
+  if(int rc = rk_vdt_get_state(h, w)) return rc;
+  for(int k = 0; k < 4; k++) {
+    const uint32_t *q = &w[RK_VS_MOTOR0 + 8 * k];
+    out[k]            = (int64_t)(((uint64_t)q[RK_VM_SUM_HI] << 32) | q[RK_VM_SUM_LO]);
+  }
+  return RK_OK;
+}
+
+} // extern "C"

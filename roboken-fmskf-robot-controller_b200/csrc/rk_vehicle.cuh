@@ -1,0 +1,321 @@
+// rk_vehicle.cuh -- device-side vehicle tick: VEHICLE_CTRL::update() and the src/Utility /
+// MOTOR_IF_M2006 pieces it calls, one thread per robot, state in registers.
+//
+// Reference (paths relative to the reference tree):
+//   src/VehicleDrive/VD_vehicle_controller.cpp:6-99,101-105,113-118,126-130
+//   src/VehicleDrive/VD_motor_if_m2006.hpp:36-37,44-47,57 ; VD_motor_if_m2006.cpp:32-72
+//   src/Utility/util_vel_interp.hpp:53-143 ; util_controller.hpp:90-124,156-165 ; util_iir.hpp:39-45
+// Evaluation order is the C++ left-to-right order of those expressions, one rounding per
+// operation.
+#pragma once
+#include "rk_common.cuh"
+#include "rk_math.cuh"
+
+namespace rk {
+
+// VD_motor_if_m2006.hpp:76-82 (constexpr float arithmetic, folded identically by nvcc's
+// front end: single IEEE operations on literals)
+#define RK_RPM_TO_RADPS (2.0f * 3.1415926f / 60.0f)
+#define RK_AMPERE_TO_RAW_CURR 1000.0f
+#define RK_GEAR_RATIO 36.0f
+#define RK_GEAR_RATIO_INV (1.0f / 36.0f)
+#define RK_OUT_RAD_PER_RAW_ANGLE (2.0f * 3.1415926f / 8191.0f)
+
+struct Interp { // VelInterpConstJerk: vel_now_/acl_now_ + active StatusBuf page
+  float vel, acl, vel_tgt, acl_max, jerk_p, jerk_m, dt1, dt2, dt3, vel_ini, acl_ini, dt;
+};
+struct Ctrl { // FF_PI_D
+  float prev_val, integ, lpf_y, lpf_x, now_tgt, now_err, now_ctrl;
+};
+struct Motor { // MOTOR_IF_M2006 head Status + sums + synthetic plant
+  int64_t sum, prev;
+  int32_t ang, rpm, cur, cur_tgt, usec, head, p_ang, p_rpm;
+};
+struct Veh {
+  float    pos[3], vel[3], tgt[3];
+  uint32_t flags;
+  Interp   it[3];
+  Ctrl     c[4];
+  Motor    m[4];
+};
+
+// Values derived from rk_vdt_params_t once per thread, with the same float operations the
+// reference constructors perform (util_controller.hpp:10,90-92).
+struct Derived {
+  float A1, B0, B1; // IIR1 coefficients of PI_D::velLpf_
+  float ki_dt;      // Igain_ * dt_
+  float s2l;        // SQRTF2 * WHEEL_L_MM
+};
+RK_DEV Derived derive(const rk_vdt_params_t &p) {
+  Derived d;
+  float   two_f = fmul(2.0f, p.ctrl_freq);
+  float   den   = fadd(two_f, p.lpf_freq);
+  d.A1          = fdiv(fsub(two_f, p.lpf_freq), den);
+  d.B0          = fdiv(p.lpf_freq, den);
+  d.B1          = d.B0;
+  d.ki_dt       = fmul(p.ki, fdiv(1.0f, p.ctrl_freq));
+  d.s2l         = fmul(p.sqrtf2, p.wheel_l_mm);
+  return d;
+}
+
+// ---- state block <-> registers --------------------------------------------------------
+RK_DEV void load_interp(const uint4 *blk, int64_t n, int64_t i, int a, Interp &t) {
+  uint4 q0 = ld_plane(blk, n, RK_VS_INTERP0 / 4 + 3 * a + 0, i);
+  uint4 q1 = ld_plane(blk, n, RK_VS_INTERP0 / 4 + 3 * a + 1, i);
+  uint4 q2 = ld_plane(blk, n, RK_VS_INTERP0 / 4 + 3 * a + 2, i);
+  t.vel = u2f(q0.x), t.acl = u2f(q0.y), t.vel_tgt = u2f(q0.z), t.acl_max = u2f(q0.w);
+  t.jerk_p = u2f(q1.x), t.jerk_m = u2f(q1.y), t.dt1 = u2f(q1.z), t.dt2 = u2f(q1.w);
+  t.dt3 = u2f(q2.x), t.vel_ini = u2f(q2.y), t.acl_ini = u2f(q2.z), t.dt = u2f(q2.w);
+}
+RK_DEV void store_interp(uint4 *blk, int64_t n, int64_t i, int a, const Interp &t) {
+  st_plane(blk, n, RK_VS_INTERP0 / 4 + 3 * a + 0, i, make_uint4(f2u(t.vel), f2u(t.acl), f2u(t.vel_tgt), f2u(t.acl_max)));
+  st_plane(blk, n, RK_VS_INTERP0 / 4 + 3 * a + 1, i, make_uint4(f2u(t.jerk_p), f2u(t.jerk_m), f2u(t.dt1), f2u(t.dt2)));
+  st_plane(blk, n, RK_VS_INTERP0 / 4 + 3 * a + 2, i, make_uint4(f2u(t.dt3), f2u(t.vel_ini), f2u(t.acl_ini), f2u(t.dt)));
+}
+RK_DEV void load_ctrl(const uint4 *blk, int64_t n, int64_t i, int w, Ctrl &c) {
+  uint4 q0 = ld_plane(blk, n, RK_VS_CTRL0 / 4 + 2 * w + 0, i);
+  uint4 q1 = ld_plane(blk, n, RK_VS_CTRL0 / 4 + 2 * w + 1, i);
+  c.prev_val = u2f(q0.x), c.integ = u2f(q0.y), c.lpf_y = u2f(q0.z), c.lpf_x = u2f(q0.w);
+  c.now_tgt = u2f(q1.x), c.now_err = u2f(q1.y), c.now_ctrl = u2f(q1.z);
+}
+RK_DEV void store_ctrl(uint4 *blk, int64_t n, int64_t i, int w, const Ctrl &c) {
+  st_plane(blk, n, RK_VS_CTRL0 / 4 + 2 * w + 0, i, make_uint4(f2u(c.prev_val), f2u(c.integ), f2u(c.lpf_y), f2u(c.lpf_x)));
+  st_plane(blk, n, RK_VS_CTRL0 / 4 + 2 * w + 1, i, make_uint4(f2u(c.now_tgt), f2u(c.now_err), f2u(c.now_ctrl), 0u));
+}
+RK_DEV void load_motor(const uint4 *blk, int64_t n, int64_t i, int w, Motor &m) {
+  uint4 q0 = ld_plane(blk, n, RK_VS_MOTOR0 / 4 + 2 * w + 0, i);
+  uint4 q1 = ld_plane(blk, n, RK_VS_MOTOR0 / 4 + 2 * w + 1, i);
+  m.sum     = (int64_t)(((uint64_t)q0.y << 32) | q0.x);
+  m.prev    = (int64_t)(((uint64_t)q0.w << 32) | q0.z);
+  m.ang     = lo16(q1.x);
+  m.rpm     = hi16(q1.x);
+  m.cur     = lo16(q1.y);
+  m.cur_tgt = hi16(q1.y);
+  m.usec    = lo16(q1.z);
+  m.head    = hi16(q1.z) % 3;
+  m.p_ang   = lo16(q1.w);
+  m.p_rpm   = hi16(q1.w);
+}
+RK_DEV void store_motor(uint4 *blk, int64_t n, int64_t i, int w, const Motor &m) {
+  uint64_t s = (uint64_t)m.sum, p = (uint64_t)m.prev;
+  st_plane(blk, n, RK_VS_MOTOR0 / 4 + 2 * w + 0, i,
+           make_uint4((uint32_t)s, (uint32_t)(s >> 32), (uint32_t)p, (uint32_t)(p >> 32)));
+  st_plane(blk, n, RK_VS_MOTOR0 / 4 + 2 * w + 1, i,
+           make_uint4(pack16(m.ang, m.rpm), pack16(m.cur, m.cur_tgt), pack16(m.usec, m.head), pack16(m.p_ang, m.p_rpm)));
+}
+RK_DEV void load_veh(const uint4 *blk, int64_t n, int64_t i, Veh &v) {
+  uint4 q0 = ld_plane(blk, n, 0, i), q1 = ld_plane(blk, n, 1, i), q2 = ld_plane(blk, n, 2, i);
+  v.pos[0] = u2f(q0.x), v.pos[1] = u2f(q0.y), v.pos[2] = u2f(q0.z), v.flags = q0.w;
+  v.vel[0] = u2f(q1.x), v.vel[1] = u2f(q1.y), v.vel[2] = u2f(q1.z), v.tgt[0] = u2f(q1.w);
+  v.tgt[1] = u2f(q2.x), v.tgt[2] = u2f(q2.y);
+#pragma unroll
+  for(int a = 0; a < 3; a++) load_interp(blk, n, i, a, v.it[a]);
+#pragma unroll
+  for(int w = 0; w < 4; w++) load_ctrl(blk, n, i, w, v.c[w]);
+#pragma unroll
+  for(int w = 0; w < 4; w++) load_motor(blk, n, i, w, v.m[w]);
+}
+RK_DEV void store_veh(uint4 *blk, int64_t n, int64_t i, const Veh &v) {
+  st_plane(blk, n, 0, i, make_uint4(f2u(v.pos[0]), f2u(v.pos[1]), f2u(v.pos[2]), v.flags));
+  st_plane(blk, n, 1, i, make_uint4(f2u(v.vel[0]), f2u(v.vel[1]), f2u(v.vel[2]), f2u(v.tgt[0])));
+  st_plane(blk, n, 2, i, make_uint4(f2u(v.tgt[1]), f2u(v.tgt[2]), 0u, 0u));
+#pragma unroll
+  for(int a = 0; a < 3; a++) store_interp(blk, n, i, a, v.it[a]);
+#pragma unroll
+  for(int w = 0; w < 4; w++) store_ctrl(blk, n, i, w, v.c[w]);
+#pragma unroll
+  for(int w = 0; w < 4; w++) store_motor(blk, n, i, w, v.m[w]);
+}
+
+// ---- VelInterpConstJerk ---------------------------------------------------------------
+// set_target_params  util_vel_interp.hpp:53-108.  Writes the inactive page and flips to it;
+// only the page that becomes active is state, so it is written in place.
+RK_DEV void interp_set(Interp &t, float v_t, float a_m, float jrk) {
+  float vel_tgt = v_t, acl_max = a_m, vel_ini = t.vel, acl_ini = t.acl;
+  if(fsub(vel_tgt, vel_ini) < 0.0f) acl_max = -a_m;
+  float jerk_m = (acl_max >= 0.0f) ? -jrk : jrk;
+  float jm_inv = fdiv(1.0f, jerk_m);
+  float jerk_p = (fsub(acl_max, acl_ini) >= 0.0f) ? jrk : -jrk;
+  float jp_inv = fdiv(1.0f, jerk_p);
+  float dt1    = fmul(fsub(acl_max, acl_ini), jp_inv);
+  float dt3    = fmul(acl_max, -jm_inv);
+  //   1.0f / acl_max * (vel_tgt - vel_ini - acl_ini*dt1*0.5f - acl_max*(dt1+dt3)*0.5f)
+  float inner = fsub(fsub(fsub(vel_tgt, vel_ini), fmul(fmul(acl_ini, dt1), 0.5f)),
+                     fmul(fmul(acl_max, fadd(dt1, dt3)), 0.5f));
+  float dt2   = fmul(fdiv(1.0f, acl_max), inner);
+  if(dt2 < 0.0f) {
+    float q     = fmul(acl_ini, jp_inv);
+    float sq_in = fadd(fmul(fmul(q, q), 0.5f), fmul(fsub(vel_tgt, vel_ini), jp_inv));
+    float sq    = arm_sqrt(sq_in);
+    dt1         = fsub(sq, fmul(acl_ini, jp_inv));
+    acl_max     = fadd(acl_ini, fmul(jerk_p, dt1));
+    dt2         = 0.0f;
+    dt3         = fmul(acl_max, -jm_inv);
+  }
+  dt1 = (dt1 < 0.0f) ? 0.0f : dt1;
+  dt3 = (dt3 < 0.0f) ? 0.0f : dt3;
+  t.vel_tgt = vel_tgt, t.acl_max = acl_max, t.jerk_p = jerk_p, t.jerk_m = jerk_m;
+  t.dt1 = dt1, t.dt2 = dt2, t.dt3 = dt3, t.vel_ini = vel_ini, t.acl_ini = acl_ini, t.dt = 0.0f;
+}
+// update  util_vel_interp.hpp:110-136
+RK_DEV float interp_update(Interp &t, float ts) {
+  float t1 = fadd(t.dt1, ts);
+  float t2 = fadd(fadd(t.dt1, t.dt2), ts);
+  float t3 = fadd(fadd(fadd(t.dt1, t.dt2), t.dt3), ts);
+  if(t.dt <= t1) {
+    t.acl = fadd(t.acl_ini, fmul(t.jerk_p, t.dt));
+    t.vel = fadd(t.vel_ini, fmul(fmul(fadd(t.acl_ini, t.acl), t.dt), 0.5f));
+    t.dt  = fadd(t.dt, ts);
+  } else if(t.dt <= t2) {
+    t.acl = t.acl_max;
+    t.vel = fadd(t.vel, fmul(t.acl, ts));
+    t.dt  = fadd(t.dt, ts);
+  } else if(t.dt <= t3) {
+    t.acl = fadd(t.acl_max, fmul(t.jerk_m, fsub(fsub(t.dt, t.dt1), t.dt2)));
+    t.vel = fadd(t.vel, fmul(t.acl, ts));
+    t.dt  = fadd(t.dt, ts);
+  } else {
+    t.acl = 0.0f;
+    t.vel = t.vel_tgt;
+  }
+  return t.vel;
+}
+// reset  util_vel_interp.hpp:138-143
+RK_DEV void interp_reset(Interp &t) {
+  t.vel = t.acl = t.vel_tgt = t.acl_max = t.jerk_p = t.jerk_m = 0.0f;
+  t.dt1 = t.dt2 = t.dt3 = t.vel_ini = t.acl_ini = t.dt = 0.0f;
+}
+
+// ---- FF_PI_D::update -> PI_D::update -> IIR1::update ----------------------------------
+// util_controller.hpp:159-165, :94-110 ; util_iir.hpp:39-45
+RK_DEV float ctrl_update(Ctrl &c, const rk_vdt_params_t &p, const Derived &d, float now_val) {
+  float err = fsub(c.now_tgt, now_val);
+  float x   = fmul(fsub(now_val, c.prev_val), p.ctrl_freq);
+  float y   = fadd(fadd(fmul(d.A1, c.lpf_y), fmul(d.B0, x)), fmul(d.B1, c.lpf_x));
+  c.lpf_y   = y;
+  c.lpf_x   = x;
+  float I   = fadd(c.integ, fmul(d.ki_dt, err));
+  I         = (I >= p.i_limit) ? p.i_limit : ((I <= -p.i_limit) ? -p.i_limit : I);
+  c.integ   = I;
+  float u   = fsub(fadd(fmul(p.kp, err), I), fmul(p.kd, y));
+  c.prev_val = now_val;
+  c.now_err  = err;
+  float ff   = fmul(c.now_tgt, p.kff);
+  ff         = (ff >= p.ff_limit) ? p.ff_limit : ((ff <= -p.ff_limit) ? -p.ff_limit : ff);
+  u          = fadd(u, ff);
+  c.now_ctrl = u;
+  return u;
+}
+// PI_D::reset  util_controller.hpp:112-124
+RK_DEV void ctrl_reset(Ctrl &c) { c.prev_val = c.integ = c.lpf_y = c.lpf_x = c.now_tgt = c.now_err = c.now_ctrl = 0.0f; }
+
+// ---- MOTOR_IF_M2006 ---------------------------------------------------------------------
+// set_CurrA_tgt -> set_rawCurr_tgt -> sat_curr  VD_motor_if_m2006.hpp:36-37,57
+RK_DEV void motor_set_curr(Motor &m, int dir, int lim, float amp) {
+  int32_t t = f2s16(fmul(amp, RK_AMPERE_TO_RAW_CURR));
+  int32_t c = sext16(t * dir);
+  int32_t l = sext16(lim);
+  m.cur_tgt = (c > l) ? l : ((c < -l) ? sext16(-l) : c);
+}
+// rx_callback  VD_motor_if_m2006.cpp:32-72, integer part.  (flt_SpeedRadPS and
+// flt_dltOutAngle_rad are never consumed: VD_vehicle_controller.cpp:20-24 takes `#if 1`.)
+// frame bytes: [0..1] angle BE, [2..3] speed BE, [4..5] current BE (little-endian uint64 load).
+RK_DEV void motor_rx(Motor &m, int dir, uint64_t frame, int32_t usec) {
+  uint32_t lo = (uint32_t)frame, hi = (uint32_t)(frame >> 32);
+  int32_t  a  = sext16((int32_t)(__byte_perm(lo, 0, 0x4401)));   // (b0<<8)|b1
+  int32_t  r  = sext16((int32_t)(__byte_perm(lo, 0, 0x4423)));   // (b2<<8)|b3
+  int32_t  c  = sext16((int32_t)(__byte_perm(hi, 0, 0x4401)));   // (b4<<8)|b5
+  int32_t  raw_ang = (dir == 1) ? a : sext16(8192 - a);
+  int32_t  d       = sext16(raw_ang - m.ang);
+  d                = (d > 4096) ? sext16(d - 8192) : ((d < -4096) ? sext16(d + 8192) : d);
+  m.sum            = m.sum + (int64_t)d;
+  m.ang            = raw_ang;
+  m.rpm            = sext16(r * dir);
+  m.cur            = sext16(c * dir);
+  m.usec           = sext16(usec);
+  m.head           = (m.head + 1 >= 3) ? 0 : m.head + 1;
+}
+
+// The synthetic plant of RK_SENSOR_PLANT (robotick.h): first-order integer motor model in
+// the motor's own frame; emits the C610 feedback frame.  Not part of the reference.
+RK_DEV uint64_t plant_frame(Motor &m) {
+  int32_t cur = m.cur_tgt, rpm = m.p_rpm, ang = m.p_ang;
+  rpm += ((cur * 4 - rpm) >> 4);
+  ang     = (ang + rpm * 8192 / 60000) & 8191;
+  m.p_rpm = rpm, m.p_ang = ang;
+  uint32_t lo = __byte_perm((uint32_t)ang, (uint32_t)rpm, 0x4501); // b0=ang>>8 b1=ang b2=rpm>>8 b3=rpm
+  uint32_t hi = __byte_perm((uint32_t)cur, 0, 0x4401);             // b4=cur>>8 b5=cur
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// ---- kinematics  VD_vehicle_controller.cpp:113-118,126-130 -----------------------------
+RK_DEV void fk_xy(const rk_vdt_params_t &p, const float M[4], float &x, float &y) {
+  x = fmul(fmul(fadd(fadd(fadd(M[0], M[1]), M[2]), M[3]), 0.25f), p.wheel_radius_mm);
+  y = fmul(fmul(fadd(fsub(fadd(-M[0], M[1]), M[2]), M[3]), 0.25f), p.wheel_radius_mm);
+}
+RK_DEV float fk_th(const rk_vdt_params_t &p, const float M[4]) {
+  float s = fadd(fadd(fsub(-M[0], M[1]), M[2]), M[3]);
+  return fmul(fdiv(fdiv(fmul(s, 0.25f), p.sqrtf2), p.wheel_l_mm), p.wheel_radius_mm);
+}
+RK_DEV void ik(const rk_vdt_params_t &p, const Derived &d, const float V[3], float M[4]) {
+  float T   = fmul(fmul(d.s2l, V[2]), 4.0f);
+  float xmy = fsub(V[0], V[1]), xpy = fadd(V[0], V[1]);
+  M[0]      = fdiv(fsub(xmy, T), p.wheel_radius_mm);
+  M[1]      = fdiv(fsub(xpy, T), p.wheel_radius_mm);
+  M[2]      = fdiv(fadd(xmy, T), p.wheel_radius_mm);
+  M[3]      = fdiv(fadd(xpy, T), p.wheel_radius_mm);
+}
+
+// cos/sin of the world yaw, hoisted: pos.th only changes through set_now_yaw_world(), so
+// VD_vehicle_controller.cpp:47-49 is re-evaluated only when the yaw word changes.
+RK_DEV void yaw_trig(const float *s_tab, float th, float &c, float &s) {
+  float rad = normalize_rad_0to2pi(th);
+  c         = arm_cos(s_tab, rad);
+  s         = arm_sin(s_tab, rad);
+}
+
+// ---- VEHICLE_CTRL::update()  VD_vehicle_controller.cpp:6-99 ------------------------------
+RK_DEV void veh_update(Veh &v, const rk_vdt_params_t &p, const Derived &d, float cth, float sth) {
+  float Mvel[4], Mrad[4], Mtgt[4];
+#pragma unroll
+  for(int k = 0; k < 4; k++) Mvel[k] = fmul(fmul((float)v.m[k].rpm, RK_RPM_TO_RADPS), RK_GEAR_RATIO_INV);
+  fk_xy(p, Mvel, v.vel[0], v.vel[1]);
+  v.vel[2] = fk_th(p, Mvel);
+#pragma unroll
+  for(int k = 0; k < 4; k++) {
+    double dd   = (double)(v.m[k].sum - v.m[k].prev);
+    Mrad[k]     = __double2float_rn(__dmul_rn(__dmul_rn(dd, (double)RK_OUT_RAD_PER_RAW_ANGLE), (double)RK_GEAR_RATIO_INV));
+    v.m[k].prev = v.m[k].sum;
+  }
+  float lx, ly;
+  fk_xy(p, Mrad, lx, ly); // .th of the odometry increment is never used (:45-51)
+  v.pos[0] = fadd(v.pos[0], fmul(fsub(fmul(lx, cth), fmul(ly, sth)), 0.001f));
+  v.pos[1] = fadd(v.pos[1], fmul(fadd(fmul(lx, sth), fmul(ly, cth)), 0.001f));
+#pragma unroll
+  for(int a = 0; a < 3; a++) v.tgt[a] = interp_update(v.it[a], p.ts);
+  ik(p, d, v.tgt, Mtgt);
+  if(v.flags & RK_VS_FLAG_POWER_ON) {
+#pragma unroll
+    for(int k = 0; k < 4; k++) {
+      v.c[k].now_tgt = fmul(Mtgt[k], RK_GEAR_RATIO);
+      float u        = ctrl_update(v.c[k], p, d, fmul(Mvel[k], RK_GEAR_RATIO));
+      motor_set_curr(v.m[k], p.motor_dir[k], p.raw_curr_lim, u);
+    }
+  } else {
+#pragma unroll
+    for(int a = 0; a < 3; a++) interp_reset(v.it[a]);
+#pragma unroll
+    for(int k = 0; k < 4; k++) {
+      ctrl_reset(v.c[k]);
+      motor_set_curr(v.m[k], p.motor_dir[k], p.raw_curr_lim, 0.0f);
+    }
+  }
+}
+
+// VEHICLE_CTRL::set_target_vel  VD_vehicle_controller.cpp:101-105
+RK_DEV void veh_set_target(Veh &v, const float vv[3], const float a[3], const float j[3]) {
+#pragma unroll
+  for(int k = 0; k < 3; k++) interp_set(v.it[k], vv[k], a[k], j[k]);
+}
+
+} // namespace rk

@@ -1,0 +1,82 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/robotick.h declares,
+and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import roboken_fmskf_robot_controller_b200 as rk
+from roboken_fmskf_robot_controller_b200 import _cabi, build, layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return rk.load()
+
+
+def _declared_symbols():
+    syms = set()
+    for hdr in os.listdir(os.path.join(ROOT, "include")):
+        if not hdr.endswith(".h"):
+            continue
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        syms |= set(re.findall(r"\b(rk_[a-z0-9_]+)\s*\(", text))
+    return syms
+
+
+def test_exports_every_declared_symbol(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 25
+    for s in sorted(syms):
+        assert hasattr(lib, s), f"librobotick_b200.so does not export {s}"
+
+
+def test_version_and_layout(lib):
+    assert lib.rk_version() == 100
+    assert lib.rk_vdt_state_words() == layout.VS_WORDS == 112
+    assert lib.rk_vdt_state_bytes(10) == 10 * 448
+
+
+def test_default_params_match(lib):
+    p = _cabi.VdtParams()
+    lib.rk_vdt_default_params(C.byref(p))
+    assert bytes(p) == bytes(rk.default_params())
+
+
+def test_header_enums_match_python_layout():
+    text = open(os.path.join(ROOT, "include", "robotick.h")).read()
+    assert "RK_VS_INTERP0 = 12" in text
+    assert layout.VS_CTRL0 == 48 and layout.VS_MOTOR0 == 80
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.rk_vdt_create(C.byref(h), None)
+    assert rc == 2  # RK_ERR_CUDA
+    assert b"no CPU fallback" in lib.rk_last_error()
+    a = _cabi.VdtRollout()
+    a.steps = 1
+    buf = (C.c_uint32 * 448)()
+    addr = (C.addressof(buf) + 15) & ~15
+    rc = lib.rk_vdt_rollout(C.byref(rk.default_params()), C.c_void_p(addr), 1, C.byref(a), None)
+    assert rc == 2
+
+
+def test_argument_errors(lib):
+    a = _cabi.VdtRollout()
+    a.steps = 1
+    rc = lib.rk_vdt_rollout(C.byref(rk.default_params()), C.c_void_p(8), 1, C.byref(a), None)
+    assert rc == 1 and b"16-byte aligned" in lib.rk_last_error()
+    rc = lib.rk_vdt_rollout(C.byref(rk.default_params()), None, -1, C.byref(a), None)
+    assert rc == 1
+    # empty batch / zero steps are no-ops
+    assert lib.rk_vdt_rollout(C.byref(rk.default_params()), None, 0, C.byref(a), None) == 0

@@ -1,0 +1,327 @@
+"""GPU parity tests (the first gate): the CUDA path, called through the C-ABI, against the
+oracles on the same seeded inputs -- bit-exact on every state word and trace word.
+
+Tolerances: BASELINE.json asks for <=1e-5 relative per step on floats and bit-exact integer
+/ mode logic.  The kernels use no FMA contraction and IEEE div/sqrt, so these tests assert
+the stronger property: every 32-bit word identical (0 ulp), which implies both.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as ol
+import workloads as wl
+import roboken_fmskf_robot_controller_b200 as rk
+from roboken_fmskf_robot_controller_b200 import _cabi, layout, streams
+from roboken_fmskf_robot_controller_b200.vehicle import Vehicle, VehicleBatch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "vdt_golden.npz"))
+
+
+def _dev(a, dtype=None):
+    if a is None:
+        return None
+    t = torch.from_numpy(np.ascontiguousarray(a).view(dtype) if dtype is not None else np.ascontiguousarray(a))
+    return t.to(DEV)
+
+
+def gpu_run(inp, sensor=_cabi.RK_SENSOR_PLANT, frames=None, state=None, trace=True, chunks=None):
+    n, steps = inp["n"], inp["steps"]
+    vb = VehicleBatch(n, DEV)
+    if state is not None:
+        vb.load_state_soa(state)
+    cmd = _dev(inp.get("cmd"), np.int32)
+    if cmd is not None:
+        cmd = cmd.reshape(-1, n, 4)
+    yaw = _dev(inp.get("yaw"))
+    fr = _dev(frames, np.int64)
+    tr = torch.zeros((steps, 16, n), dtype=torch.int32, device=DEV) if trace else None
+    if chunks is None:
+        vb.rollout(steps, sensor_mode=sensor, cmd=cmd, seg_len=inp.get("seg_len", 0), yaw=yaw,
+                   yaw_period=inp.get("yaw_period", 0), frames=fr, trace=tr)
+    else:
+        # resume: K ticks as several launches, each taking its slice of the input tables
+        seg_len, yp = inp.get("seg_len", 0), inp.get("yaw_period", 0)
+        assert steps % chunks == 0
+        k = steps // chunks
+        assert (seg_len == 0 or k % seg_len == 0) and (yp == 0 or k % yp == 0)
+        for c in range(chunks):
+            vb.rollout(k, sensor_mode=sensor,
+                       cmd=None if cmd is None else cmd[c * k // seg_len:(c + 1) * k // seg_len].contiguous(),
+                       seg_len=seg_len,
+                       yaw=None if yaw is None else yaw[c * k // yp:(c + 1) * k // yp].contiguous(), yaw_period=yp,
+                       frames=None if fr is None else fr[c * k:(c + 1) * k].contiguous(),
+                       trace=None if tr is None else tr[c * k:(c + 1) * k])
+    torch.cuda.synchronize()
+    st = vb.state.cpu().numpy().view(np.uint32)
+    return st, (tr.cpu().numpy().view(np.uint32) if trace else None)
+
+
+def port_run(inp, sensor=_cabi.RK_SENSOR_PLANT, frames=None, state=None, trace=True, nthreads=1):
+    n = inp["n"]
+    st = np.zeros(layout.VS_WORDS * n, dtype=np.uint32) if state is None else state.copy()
+    ro = ol.HostRollout(n, inp["steps"], sensor, inp.get("cmd"), inp.get("seg_len", 0), inp.get("yaw"),
+                        inp.get("yaw_period", 0), frames=frames, trace=trace)
+    ol.run_port(st, n, ro, nthreads=nthreads)
+    return st, ro.trace
+
+
+def ref_run(inp, sensor=_cabi.RK_SENSOR_PLANT, frames=None, state=None):
+    n = inp["n"]
+    st = np.zeros(layout.VS_WORDS * n, dtype=np.uint32) if state is None else state.copy()
+    ro = ol.HostRollout(n, inp["steps"], sensor, inp.get("cmd"), inp.get("seg_len", 0), inp.get("yaw"),
+                        inp.get("yaw_period", 0), frames=frames, trace=True)
+    ol.run_ref(st, n, ro)
+    return st, ro.trace
+
+
+def assert_same(a, b, what):
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} words differ, first at {bad[0]}: {a[tuple(bad[0])]:#x} vs {b[tuple(bad[0])]:#x}")
+
+
+# ---- configs[0]: the reference's own CPU-runnable case -------------------------------------
+def test_c1_trace_bit_exact_vs_port_and_golden():
+    st, tr = gpu_run(wl.c1_inputs())
+    pst, ptr = port_run(wl.c1_inputs())
+    assert_same(tr, ptr, "C1 trace vs port")
+    assert_same(st, pst, "C1 final state vs port")
+    assert_same(tr[G["c1_rows"]], G["c1_trace"], "C1 trace vs golden (unmodified reference)")
+    assert_same(st, G["c1_state"], "C1 state vs golden")
+    # SURVEY.md Appendix D known answers
+    f = tr.view(np.float32)
+    for step, (tgt, vel, cur) in wl.APPENDIX_D.items():
+        np.testing.assert_allclose(f[step, 6:9, 0], np.float32(tgt), rtol=2e-7)
+        np.testing.assert_allclose(f[step, 3:6, 0], np.float32(vel), rtol=2e-7)
+        assert tuple(tr[step, 9:13, 0].view(np.int32)) == cur
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ol.ORACLE, "_ref", "libref_vdt.so")), reason="no prebuilt oracle/_ref")
+def test_plant_rollout_bit_exact_vs_compiled_reference():
+    inp = wl.plant_inputs(64, 1500, seed=3)
+    st, tr = gpu_run(inp)
+    rst, rtr = ref_run(inp)
+    assert_same(tr, rtr, "plant trace vs compiled reference")
+    assert_same(st, rst, "plant state vs compiled reference")
+
+
+@pytest.mark.parametrize("seed,n,steps", [(0x5EED, 256, 1000), (7, 33, 2000), (99, 1, 500)])
+def test_plant_rollout_bit_exact_vs_port(seed, n, steps):
+    inp = wl.plant_inputs(n, steps, seed=seed)
+    st, tr = gpu_run(inp)
+    pst, ptr = port_run(inp, nthreads=8)
+    assert_same(tr, ptr, "plant trace")
+    assert_same(st, pst, "plant state")
+
+
+def test_golden_plant_and_stream_and_random():
+    st, tr = gpu_run(wl.plant_inputs(16, 1000, seed=0x5EED))
+    assert_same(tr[::100], G["plant_trace"], "golden plant trace")
+    assert_same(st, G["plant_state"], "golden plant state")
+    fr = streams.vehicle_frames(8, 300, seed=21)
+    st, tr = gpu_run(wl.plant_inputs(8, 300, seed=21), sensor=_cabi.RK_SENSOR_STREAM, frames=fr)
+    assert_same(tr[::30], G["stream_trace"], "golden stream trace")
+    assert_same(st, G["stream_state"], "golden stream state")
+    st0 = layout.aos_to_soa(wl.random_states(64, seed=9))
+    st, tr = gpu_run(wl.plant_inputs(64, 24, seed=9, seg_len=6, yaw_period=3), state=st0)
+    assert_same(tr[::6], G["rand_trace"], "golden random-state trace")
+    assert_same(st, G["rand_state"], "golden random-state state")
+
+
+def test_stream_mode_bit_exact():
+    n, steps = 96, 700
+    inp = wl.plant_inputs(n, steps, seed=12)
+    fr = streams.vehicle_frames(n, steps, seed=12)
+    st, tr = gpu_run(inp, sensor=_cabi.RK_SENSOR_STREAM, frames=fr)
+    pst, ptr = port_run(inp, sensor=_cabi.RK_SENSOR_STREAM, frames=fr, nthreads=8)
+    assert_same(tr, ptr, "stream trace")
+    assert_same(st, pst, "stream state")
+
+
+def test_stream_mode_adversarial_frames():
+    """Frames with arbitrary 16-bit fields: exercises the int16 wrap / +-4096 unwrap edges of
+    rx_callback (VD_motor_if_m2006.cpp:40-69) far outside what a real C610 sends."""
+    n, steps = 128, 64
+    rng = np.random.default_rng(5)
+    fr = rng.integers(0, 1 << 63, size=(steps, 4, n), dtype=np.int64).view(np.uint64)
+    edge = np.array([0, 4096, 4097, 8191, 8192, 0x7FFF, 0x8000, 0xFFFF, 4095, 12288], dtype=np.uint64)
+    ang = edge[rng.integers(0, len(edge), size=(steps, 4, n))]
+    be = ((ang >> np.uint64(8)) & np.uint64(0xFF)) | ((ang & np.uint64(0xFF)) << np.uint64(8))
+    fr = np.where(rng.random((steps, 4, n)) < 0.5, (fr & ~np.uint64(0xFFFF)) | be, fr)
+    # keep |rpm| small enough that u*1000 stays inside int16 (C++ UB beyond)
+    fr = fr & ~np.uint64(0x00000000FFFF0000)
+    inp = dict(n=n, steps=steps)
+    st, tr = gpu_run(inp, sensor=_cabi.RK_SENSOR_STREAM, frames=fr)
+    pst, ptr = port_run(inp, sensor=_cabi.RK_SENSOR_STREAM, frames=fr)
+    assert_same(tr, ptr, "adversarial stream trace")
+    assert_same(st, pst, "adversarial stream state")
+
+
+def test_random_initial_states_and_hold_mode():
+    n = 2048
+    st0 = layout.aos_to_soa(wl.random_states(n, seed=3))
+    inp = wl.plant_inputs(n, 40, seed=5, seg_len=8, yaw_period=4)
+    for sensor in (_cabi.RK_SENSOR_PLANT, _cabi.RK_SENSOR_HOLD):
+        st, tr = gpu_run(inp, sensor=sensor, state=st0)
+        pst, ptr = port_run(inp, sensor=sensor, state=st0, nthreads=8)
+        assert_same(tr, ptr, f"random-state trace mode {sensor}")
+        assert_same(st, pst, f"random-state state mode {sensor}")
+
+
+def test_power_off_resets():
+    """isPowerOn false: interpolators and controllers reset each tick, current 0
+    (VD_vehicle_controller.cpp:81-98).  No command table -> power stays off."""
+    n = 64
+    aos = wl.random_states(n, seed=8)
+    aos[:, layout.VS_FLAGS] = 0
+    st0 = layout.aos_to_soa(aos)
+    inp = dict(n=n, steps=5)
+    st, tr = gpu_run(inp, state=st0)
+    pst, ptr = port_run(inp, state=st0)
+    assert_same(tr, ptr, "power-off trace")
+    assert_same(st, pst, "power-off state")
+    assert np.all(tr[1:, 9:13, :] == 0)
+
+
+def test_resume_chunked_equals_one_launch():
+    inp = wl.plant_inputs(300, 1000, seed=44, seg_len=125, yaw_period=10)
+    st1, tr1 = gpu_run(inp)
+    st2, tr2 = gpu_run(inp, chunks=4)
+    # microsecond ids restart per launch (dead telemetry word); mask it out of the compare
+    a1, a2 = layout.soa_to_aos(st1, 300, layout.VS_WORDS), layout.soa_to_aos(st2, 300, layout.VS_WORDS)
+    for w in range(4):
+        a1[:, layout.VS_MOTOR0 + 8 * w + layout.VM_USEC] &= 0xFFFF0000
+        a2[:, layout.VS_MOTOR0 + 8 * w + layout.VM_USEC] &= 0xFFFF0000
+    assert_same(tr2, tr1, "chunked trace")
+    assert_same(a2, a1, "chunked state")
+
+
+def test_trace_off_gives_same_state():
+    inp = wl.plant_inputs(500, 600, seed=45)
+    st1, _ = gpu_run(inp, trace=True)
+    st2, _ = gpu_run(inp, trace=False)
+    assert_same(st2, st1, "trace-off state")
+
+
+def test_full_size_c2_sampled_parity_and_slice_invariance():
+    """BASELINE.json configs[1]: 2^20 vehicles x 1000 fused ticks.  Size-independent checks:
+    (a) a seeded sample of instances equals the oracle run on those instances alone,
+    (b) instances are independent: a contiguous slice run as its own batch is identical."""
+    n, steps = 1 << 20, 1000
+    inp = wl.plant_inputs(n, steps, seed=0x5EED)
+    st, _ = gpu_run(inp, trace=False)
+    aos = layout.soa_to_aos(st, n, layout.VS_WORDS)
+    rng = np.random.default_rng(1)
+    idx = np.unique(np.concatenate([[0, 1, n - 1, n - 2, 127, 128], rng.integers(0, n, 90)]))
+    sub = dict(n=len(idx), steps=steps, cmd=np.ascontiguousarray(inp["cmd"][:, idx]), seg_len=inp["seg_len"],
+               yaw=np.ascontiguousarray(inp["yaw"][:, idx]), yaw_period=inp["yaw_period"])
+    pst, _ = port_run(sub, trace=False, nthreads=8)
+    assert_same(aos[idx], layout.soa_to_aos(pst, len(idx), layout.VS_WORDS), "sampled instances vs port")
+    lo, hi = 500_000, 500_000 + 4096 + 17
+    sl = dict(n=hi - lo, steps=steps, cmd=np.ascontiguousarray(inp["cmd"][:, lo:hi]), seg_len=inp["seg_len"],
+              yaw=np.ascontiguousarray(inp["yaw"][:, lo:hi]), yaw_period=inp["yaw_period"])
+    sst, _ = gpu_run(sl, trace=False)
+    assert_same(layout.soa_to_aos(sst, hi - lo, layout.VS_WORDS), aos[lo:hi], "slice invariance")
+    # physical sanity at full size: saturation respected everywhere, finite positions
+    v = layout.vehicle_view(aos)
+    assert np.all(np.abs(v["cur_tgt"]) <= 3000)
+    assert np.all(np.isfinite(v["pos"]))
+
+
+def test_bounded_drift_10k_steps():
+    """BASELINE.json: bounded-drift check after 10k steps.  Bit-exact state after 10 000
+    closed-loop ticks implies zero drift; also check it against the <=1e-5 formal bound."""
+    inp = wl.plant_inputs(128, 10000, seed=77)
+    st, _ = gpu_run(inp, trace=False)
+    pst, _ = port_run(inp, trace=False, nthreads=8)
+    a, b = layout.soa_to_aos(st, 128, layout.VS_WORDS), layout.soa_to_aos(pst, 128, layout.VS_WORDS)
+    pa, pb = layout.vehicle_view(a)["pos"], layout.vehicle_view(b)["pos"]
+    np.testing.assert_allclose(pa, pb, rtol=1e-5, atol=0)
+    assert_same(a, b, "10k-step state")
+
+
+def test_batched_setters_match_oracle():
+    import ctypes as C
+
+    n = 257
+    aos = wl.random_states(n, seed=12)
+    vb = VehicleBatch(n, DEV)
+    vb.load_state_aos(aos)
+    rng = np.random.default_rng(2)
+    v = rng.uniform(-400, 400, (3, n)).astype(np.float32)
+    a = rng.uniform(10, 2000, (3, n)).astype(np.float32)
+    j = rng.uniform(100, 30000, (3, n)).astype(np.float32)
+    vb.set_target_vel(_dev(v), _dev(a), _dev(j))
+    fr = streams.vehicle_frames(n, 1, seed=3)[0]
+    us = rng.integers(0, 0x7FFF, n).astype(np.int16)
+    for w in range(4):
+        vb.motor_rx(w, _dev(fr[w], np.int64), _dev(us))
+    vb.set_power()
+    torch.cuda.synchronize()
+    got = vb.state_aos()
+    p = rk.default_params()
+    lib = ol.port()
+    F3 = C.c_float * 3
+    exp = aos.copy()
+    for i in range(n):
+        row = np.ascontiguousarray(exp[i])
+        ptr = row.ctypes.data_as(C.c_void_p)
+        lib.orc_vdt_set_target(C.byref(p), ptr, F3(*v[:, i]), F3(*a[:, i]), F3(*j[:, i]))
+        for w in range(4):
+            lib.orc_vdt_rx(C.byref(p), ptr, w, fr[w, i].tobytes(), int(us[i]))
+        row[layout.VS_FLAGS] |= 1
+        exp[i] = row
+    assert_same(got, exp, "batched setters")
+
+
+def test_single_instance_handle_c1_prefix():
+    """The drop-in handle (rk_vdt_t): drive it exactly as the firmware drives its statics --
+    set_now_yaw_world + rx_callback x4 + update per tick -- and compare with the oracle."""
+    import ctypes as C
+
+    steps = 300
+    inp = wl.c1_inputs()
+    _, ptr = port_run(dict(inp, steps=steps))
+    veh = Vehicle()
+    rpm, ang = [0] * 4, [0] * 4
+    for t in range(steps):
+        if t == 0:
+            veh.start()
+            veh.set_target_vel((200.0, 100.0, 1.0), (1000.0, 1000.0, 30.0), (10000.0, 10000.0, 300.0))
+        veh.set_now_yaw_world(float(inp["yaw"][t // 10, 0]))
+        cur = veh.get_rawCurr_tgt()
+        for k in range(4):
+            c = cur[k]
+            rpm[k] += (c * 4 - rpm[k]) >> 4
+            q = abs(rpm[k] * 8192) // 60000
+            ang[k] = (ang[k] + (q if rpm[k] >= 0 else -q)) & 8191
+            fr = bytes([(ang[k] >> 8) & 255, ang[k] & 255, (rpm[k] >> 8) & 255, rpm[k] & 255, (c >> 8) & 255, c & 255, 0, 0])
+            veh.rx_callback(k, fr, ((t + 1) * 1000) & 0x7FFF)
+        veh.update()
+        if t % 25 == 0 or t == steps - 1:
+            row = ptr[t, :, 0]
+            np.testing.assert_array_equal(veh.get_vehicle_pos_m_latest().view(np.uint32), row[0:3])
+            np.testing.assert_array_equal(veh.get_vehicle_vel_mmps_latest().view(np.uint32), row[3:6])
+            np.testing.assert_array_equal(veh.get_vehicle_vel_tgt_mmps_latest().view(np.uint32), row[6:9])
+            assert veh.get_rawCurr_tgt() == list(row[9:13].view(np.int32))
+    veh.close()
+
+
+def test_cost_epilogue():
+    n = 100
+    inp = wl.plant_inputs(n, 500, seed=6)
+    goal = np.random.default_rng(0).uniform(-1, 1, (n, 2)).astype(np.float32)
+    vb = VehicleBatch(n, DEV)
+    cost = torch.zeros(n, dtype=torch.float32, device=DEV)
+    cmd = _dev(inp["cmd"], np.int32).reshape(-1, n, 4)
+    vb.rollout(500, cmd=cmd, seg_len=inp["seg_len"], yaw=_dev(inp["yaw"]), yaw_period=inp["yaw_period"],
+               goal=_dev(goal), cost=cost)
+    torch.cuda.synchronize()
+    pos = layout.vehicle_view(vb.state_aos())["pos"]
+    dx, dy = pos[:, 0] - goal[:, 0], pos[:, 1] - goal[:, 1]
+    np.testing.assert_array_equal(cost.cpu().numpy(), dx * dx + dy * dy)
