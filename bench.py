@@ -1,0 +1,439 @@
+#!/usr/bin/env python3
+"""bench.py -- robot-instance control steps/s of the fused vehicle rollout on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: one launch of the fused rollout kernel
+over `--instances` vehicles per GPU x `--ticks` 1 kHz control ticks (default: BASELINE.json
+configs[1], 2^20 vehicles x 1000 fused ticks, closed loop through the integer motor plant).
+Rank 0 prints ONE JSON line (see DESIGN.md "Measurement").
+
+  value        whole-job instance-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          the same metric through the C-ABI with HOST (pinned) command/yaw tables copied
+               H2D and the per-instance cost vector copied D2H inside the timed region
+  roofline     algorithmic FP32 flops (183 per tick) / launch duration against
+               the FP32 FFMA peak measured live by rk_probe_fp32 (MEASURED_PEAKS.json carries no
+               FP32 entry); the HBM side of the same launch is reported under roofline["hbm"]
+  cpu_baseline the reference's own sources compiled for x86 (oracle/_ref) -- or the plain-C port
+               if the prebuilt .so is absent -- on the box's host cores, bounded sample
+  --impl reference   times only that CPU implementation and prints the same JSON shape
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+FLOP_PER_TICK = 183        # SURVEY.md Appendix B (83 add/sub + 93 mul + 7 div), + 8 FP64 mul
+STATE_BYTES = 448          # include/robotick.h RK_VS_WORDS * 4
+METRIC = "robot-instance control steps/sec"
+UNIT = "instance-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=1 << 20, help="vehicles per GPU")
+    ap.add_argument("--ticks", type=int, default=1000, help="fused control ticks per launch")
+    ap.add_argument("--seg-len", type=int, default=125)
+    ap.add_argument("--yaw-period", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall budget of the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"configs[1]: {a.instances} mecanum vehicles/GPU x {a.ticks} fused 1 kHz ticks "
+            f"(rx_callback + FK/odometry + 3x const-jerk target + IK + 4x FF_PI_D + current saturation), "
+            f"closed loop through the integer motor plant, command every {a.seg_len} ticks, yaw every {a.yaw_period}")
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own code (oracle/_ref) or the C port, all host threads
+# ------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuArm:
+    def __init__(self, a):
+        import oracle_lib as ol
+        import workloads as wl
+        from roboken_fmskf_robot_controller_b200 import _cabi
+
+        self.ol, self.wl, self._cabi = ol, wl, _cabi
+        self.a = a
+        self.threads = host_threads()
+        self.kind = "reference" if os.path.exists(os.path.join(ol.ORACLE, "_ref", "libref_vdt.so")) else "port"
+        self._inp = {}
+
+    def _run(self, n):
+        a = self.a
+        if n not in self._inp:
+            inp = self.wl.plant_inputs(n, a.ticks, seed=0x5EED, seg_len=a.seg_len, yaw_period=a.yaw_period)
+            ro = self.ol.HostRollout(n, a.ticks, self._cabi.RK_SENSOR_PLANT, inp["cmd"], inp["seg_len"], inp["yaw"],
+                                     inp["yaw_period"])
+            self._inp[n] = (inp, ro)
+        _, ro = self._inp[n]
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            self.ol.run_ref(None, n, ro, nthreads=self.threads)
+        else:
+            self.ol.run_port(None, n, ro, nthreads=self.threads)
+        return time.perf_counter() - t0
+
+    def calibrate(self, step_budget_s):
+        """Pick the per-step sample (instances) so that one step takes about step_budget_s."""
+        n0 = 64 * self.threads
+        self._run(n0)  # warm caches / page in
+        dt = self._run(n0)
+        rate = n0 * self.a.ticks / dt
+        n = int(rate * step_budget_s / self.a.ticks)
+        n = max(self.threads * 16, min(n, self.a.instances))
+        return (n // self.threads) * self.threads
+
+    def sample_desc(self, n):
+        return (f"{n} of {self.a.instances} instances x {self.a.ticks} ticks per step, same seeded command/yaw "
+                f"streams and plant, {self.threads} host threads over instances")
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    arm = CpuArm(a)
+    budget = min(2.0, 90.0 / max(1, a.steps + a.warmup))
+    n = arm.calibrate(budget)
+    for _ in range(a.warmup):
+        arm._run(n)
+    t = 0.0
+    for _ in range(a.steps):
+        t += arm._run(n)
+    value = n * a.ticks * a.steps / t
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "instances_per_step": n, "ticks_per_launch": a.ticks},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "sample": arm.sample_desc(n)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs DURING the timed regions
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        if self.ok:
+            self.th.start()
+
+    def _loop(self):
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit and name != "gpu_idle":
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.02)
+
+    def start(self):
+        self._active.set()
+
+    def pause(self):
+        self._active.clear()
+
+    def result(self):
+        self._stop.set()
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+
+    import roboken_fmskf_robot_controller_b200 as rk
+    from roboken_fmskf_robot_controller_b200 import _cabi, layout, sharding, streams
+    from roboken_fmskf_robot_controller_b200.vehicle import VehicleBatch
+
+    lib = rk.load()  # raises if the CUDA library is not built: no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    rank, local_rank, world = sharding.init("nccl")
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _cabi.check(lib.rk_set_device(local_rank))
+    n, K, W, T = a.instances, a.steps, a.warmup, a.ticks
+    first = rank * n  # contiguous slice of the global instance index space
+    n_seg = (T + a.seg_len - 1) // a.seg_len
+    n_yaw = (T + a.yaw_period - 1) // a.yaw_period
+
+    # ---- synthetic inputs, generated on the host (pinned) ---------------------------------
+    cmd_h = torch.from_numpy(streams.vehicle_commands(n, n_seg, 0x5EED, first).view(np.int32).reshape(n_seg, n, 4)).pin_memory()
+    yaw_h = torch.from_numpy(streams.vehicle_yaw(n, n_yaw, 0x5EED, first)).pin_memory()
+    goal_h = torch.zeros((n, 2), dtype=torch.float32).pin_memory()
+    cmd_d, yaw_d, goal_d = cmd_h.to(dev), yaw_h.to(dev), goal_h.to(dev)
+    cost_d = torch.zeros(n, dtype=torch.float32, device=dev)
+    vb = VehicleBatch(n, dev)
+    args = vb.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=cmd_d, seg_len=a.seg_len, yaw=yaw_d,
+                        yaw_period=a.yaw_period, goal=goal_d, cost=cost_d)
+    keep = [cmd_d, yaw_d, goal_d, cost_d]
+    stream = torch.cuda.current_stream(dev)
+    clocks = ClockSampler(local_rank)
+
+    # ---- parity spot check of the exact bench launch (first pass, power-on state) ----------
+    vb.rollout_args(args)
+    torch.cuda.synchronize()
+    spot = None
+    if rank == 0:
+        import oracle_lib as ol
+
+        idx = np.unique(np.concatenate([[0, n - 1], np.random.default_rng(0).integers(0, n, 62)]))
+        cmd_np = cmd_h.numpy().view(streams.vehicle_commands(1, 1).dtype).reshape(n_seg, n)
+        ro = ol.HostRollout(len(idx), T, _cabi.RK_SENSOR_PLANT, np.ascontiguousarray(cmd_np[:, idx]), a.seg_len,
+                            np.ascontiguousarray(yaw_h.numpy()[:, idx]), a.yaw_period)
+        exp = np.zeros(layout.VS_WORDS * len(idx), dtype=np.uint32)
+        ol.run_port(exp, len(idx), ro, nthreads=min(8, host_threads()))
+        got = layout.soa_to_aos(vb.state.cpu().numpy().view(np.uint32), n, layout.VS_WORDS)[idx]
+        same = np.array_equal(got, layout.soa_to_aos(exp, len(idx), layout.VS_WORDS))
+        spot = f"{len(idx)} sampled instances x {T} ticks {'bit-exact' if same else 'MISMATCH'} vs oracle"
+        if not same:
+            raise SystemExit("bench parity spot check failed: " + spot)
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------
+    for _ in range(max(W - 1, 0)):
+        vb.rollout_args(args)
+    torch.cuda.synchronize()
+    sharding.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.start()
+    ev0.record(stream)
+    for _ in range(K):
+        vb.rollout_args(args)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks.pause()
+    sharding.barrier()
+    ms_local = ev0.elapsed_time(ev1)
+    ms = sharding.max_over_ranks(ms_local, dev)
+    value = world * n * T * K / (ms * 1e-3)
+    launches = K
+
+    # ---- FP32 peak probes (live; no FP32 entry in MEASURED_PEAKS.json) ---------------------
+    sm = C.c_int()
+    khz = C.c_int()
+    _cabi.check(lib.rk_device_info(local_rank, C.byref(sm), C.byref(khz), None))
+    probe_out = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def probe(fused):
+        fl = C.c_double()
+        best = 0.0
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _cabi.check(lib.rk_probe_fp32(fused, sm.value * 32, 4096, probe_out.data_ptr(), C.byref(fl), C.c_void_p(stream.cuda_stream)))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if it:
+                best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3))
+        return best / 1e12
+
+    ffma_tflops = probe(1)
+    issue_tflops = probe(0)
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        try:
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+
+    launch_s = ms_local * 1e-3 / K
+    achieved_tflops = FLOP_PER_TICK * n * T / launch_s / 1e12
+    alg_bytes = n * (2 * STATE_BYTES + n_seg * 16 + n_yaw * 4 + 8 + 4)  # state ld+st, cmd, yaw, goal, cost
+    roofline = {
+        "bound": "fp32",
+        "achieved": achieved_tflops, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / ffma_tflops,
+        "peak_source": "rk_probe_fp32 FFMA chains, measured live in this run (no FP32 entry in MEASURED_PEAKS.json)",
+        "nonfused_issue_peak": issue_tflops,
+        "frac_of_nonfused_issue_peak": achieved_tflops / issue_tflops,
+        "algorithmic_flop_per_tick": FLOP_PER_TICK,
+        "kernel": "rk::vdt_rollout_kernel<RK_SENSOR_PLANT,false>",
+        "launch_ms": launch_s * 1e3,
+        "traffic": None,
+        "hbm": {"achieved": alg_bytes / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / launch_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": alg_bytes},
+        "sm_count": sm.value,
+    }
+    traffic_note = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_note):
+        try:
+            roofline["traffic"] = json.load(open(traffic_note)).get("vdt_rollout_plant_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host tables in, costs out, through the same C-ABI call ------------------------
+    e2e = None
+    if not a.no_e2e:
+        copy_s = torch.cuda.Stream(dev)
+        comp_s = torch.cuda.Stream(dev)
+        bufs = []
+        for b in range(2):
+            c, y = torch.empty_like(cmd_d), torch.empty_like(yaw_d)
+            co = torch.zeros(n, dtype=torch.float32, device=dev)
+            bufs.append(dict(cmd=c, yaw=y, cost=co, cost_h=torch.empty(n, dtype=torch.float32).pin_memory(),
+                             args=vb.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=c, seg_len=a.seg_len, yaw=y,
+                                               yaw_period=a.yaw_period, goal=goal_d, cost=co),
+                             up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event()))
+            keep += [c, y, co]
+        h2d = cmd_h.numel() * 4 + yaw_h.numel() * 4
+        d2h = n * 4
+
+        def e2e_pass(s):
+            b = bufs[s % 2]
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(b["done"])  # buffer free again (previous use computed)
+                b["cmd"].copy_(cmd_h, non_blocking=True)
+                b["yaw"].copy_(yaw_h, non_blocking=True)
+                b["up"].record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(b["up"])
+                comp_s.wait_event(b["down"])  # cost buffer drained
+                vb.state.zero_()  # every rollout starts from the power-on state
+                vb.rollout_args(b["args"], stream=comp_s)
+                b["done"].record(comp_s)
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(b["done"])
+                b["cost_h"].copy_(b["cost"], non_blocking=True)
+                b["down"].record(copy_s)
+
+        for s in range(max(W, 2)):
+            e2e_pass(s)
+        torch.cuda.synchronize()
+        sharding.barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.start()
+        t0e.record(stream)
+        copy_s.wait_stream(stream)
+        comp_s.wait_stream(stream)
+        for s in range(K):
+            e2e_pass(s)
+        stream.wait_stream(copy_s)
+        stream.wait_stream(comp_s)
+        t1e.record(stream)
+        torch.cuda.synchronize()
+        clocks.pause()
+        sharding.barrier()
+        ms_e = sharding.max_over_ranks(t0e.elapsed_time(t1e), dev)
+        e2e = {"value": world * n * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / K,
+               "path": "rk_vdt_rollout() via ctypes; pinned host cmd+yaw tables H2D, state reset to power-on, "
+                       "cost vector D2H, double-buffered on a copy stream"}
+        launches += 0  # e2e launches are outside the `value` region; gpu_launches counts that region
+
+    # ---- optional NCCL gather of the summary costs (outside the timed regions) --------------
+    gather_ms = None
+    if world > 1:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sharding.gather_costs(cost_d)
+        torch.cuda.synchronize()
+        g0.record(stream)
+        allc = sharding.gather_costs(cost_d)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        gather_ms = sharding.max_over_ranks(g0.elapsed_time(g1), dev)
+        assert allc.numel() == world * n
+
+    clk = clocks.result()
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        arm = CpuArm(a)
+        nc = arm.calibrate(a.cpu_seconds / 3.0)
+        t = min(arm._run(nc) for _ in range(2))
+        cpu = {"value": nc * T / t, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "sample": arm.sample_desc(nc)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "instances_per_gpu": n, "ticks_per_launch": T,
+                       "l2": f"inputs larger than L2: {n * STATE_BYTES >> 20} MiB state + "
+                             f"{(cmd_h.numel() + yaw_h.numel()) * 4 >> 20} MiB tables per pass vs 126 MB L2",
+                       "parity_spot_check": spot},
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        if gather_ms is not None:
+            line["cost_gather_ms"] = gather_ms
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

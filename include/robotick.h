@@ -52,6 +52,19 @@ int rk_device_info(int device, int *sm_count, int *sm_clock_khz, size_t *hbm_byt
 /* Selects the CUDA device for subsequent calls of the calling thread (the library links its
  * own static CUDA runtime; one process per GPU calls this once with LOCAL_RANK). */
 int rk_set_device(int device);
+/* Library options (process-wide).  RK_OPT_FORCE_TRANSCRIPTION = 1 makes RK_SENSOR_PLANT
+ * rollouts use the direct transcription kernel instead of the issue-optimised one (the two
+ * are bit-identical; the tests compare them). */
+enum { RK_OPT_FORCE_TRANSCRIPTION = 1 };
+int rk_set_option(int option, int value);
+/* 1 if the exhaustive on-device proofs that gate the issue-optimised kernel hold for these
+ * parameters on the current device (csrc/rk_exact.cu), 0 if not, < 0 on error. */
+struct rk_vdt_params;
+int rk_vdt_fast_path_proven(const struct rk_vdt_params *p);
+/* Roofline probe (bench.py): launches a dense FP32 kernel on `stream` -- FFMA chains when
+ * fused != 0, alternating FMUL/FADD otherwise -- and reports its flop count; the caller
+ * times it with CUDA events.  d_out: >= 4 bytes of device memory. */
+int rk_probe_fp32(int fused, int blocks, int iters, float *d_out, double *flops, void *stream);
 
 /* =====================================================================================
  * Vehicle (src/VehicleDrive + the src/Utility math it calls)

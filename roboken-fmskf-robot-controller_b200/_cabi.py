@@ -15,6 +15,7 @@ RK_OK = 0
 RK_SENSOR_HOLD, RK_SENSOR_PLANT, RK_SENSOR_STREAM = 0, 1, 2
 RK_CMD_NONE, RK_CMD_MOVE, RK_CMD_STOP = 0, 1, 2
 RK_VDT_TRACE_WORDS = 16
+RK_OPT_FORCE_TRANSCRIPTION = 1
 
 
 class VdtParams(C.Structure):
@@ -80,6 +81,9 @@ def _proto(lib):
     lib.rk_last_error.restype = C.c_char_p
     lib.rk_device_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
     lib.rk_set_device.argtypes = [C.c_int]
+    lib.rk_set_option.argtypes = [C.c_int, C.c_int]
+    lib.rk_vdt_fast_path_proven.argtypes = [C.POINTER(VdtParams)]
+    lib.rk_probe_fp32.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_double), vp]
     lib.rk_vdt_default_params.argtypes = [C.POINTER(VdtParams)]
     lib.rk_vdt_default_params.restype = None
     lib.rk_vdt_state_words.restype = C.c_size_t

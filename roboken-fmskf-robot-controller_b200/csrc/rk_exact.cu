@@ -1,0 +1,117 @@
+// rk_exact.cu -- exhaustive on-device proofs that gate the fast path (rk_vehicle_fast.cuh).
+//
+// Run once per parameter set (a few milliseconds on a B200) by rk_vdt_rollout() before the
+// fast kernel is first used; results are cached.  If any proof fails for the given constants
+// the library silently uses the transcription kernel -- results are identical either way.
+//   1. div_const(x, c, RN(1/c)) == x / c bit for bit, for every finite float x (2^32 cases),
+//      c = wheel radius; for c = SQRTF2 and WHEEL_L_MM the sequence must be exact for
+//      x == 0 and |x| >= 2^-40 (their operand is a sum of wheel speeds derived from int16 rpm,
+//      which is 0 or >= 2^-34 in magnitude).
+//   2. fma(d, K_hi, d*K_lo) == (float)((double)d * OUT_RAD_PER_RAW_ANGLE * GEAR_RATIO_INV)
+//      for every integer |d| <= 8192.
+//   3. plant_dang(r) == r * 8192 / 60000 (C truncation) for every int16 r.
+#include <mutex>
+#include <string.h>
+
+#include "rk_vehicle_fast.cuh"
+
+namespace rk {
+
+struct ProofOut {
+  unsigned int div_fail_lo_max; // largest |x| bits < 1.0f that failed
+  unsigned int div_fail_hi_min; // smallest |x| bits >= 1.0f that failed
+  unsigned int mrad_fail, dang_fail;
+};
+
+__global__ void proof_div_kernel(float c, ProofOut *out) {
+  const float    rcp    = fdiv(1.0f, c);
+  unsigned int   lo_max = 0, hi_min = 0x7f800000u;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for(uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < 0x100000000ull; b += stride) {
+    const unsigned int u = (unsigned int)b, au = u & 0x7fffffffu;
+    if(au >= 0x7f800000u) continue; // NaN / Inf are outside the fast path's domain
+    const float x = u2f(u);
+    if(f2u(div_const(x, c, rcp)) != f2u(fdiv(x, c))) {
+      if(au < 0x3f800000u)
+        lo_max = max(lo_max, au);
+      else
+        hi_min = min(hi_min, au);
+    }
+  }
+  if(lo_max) atomicMax(&out->div_fail_lo_max, lo_max);
+  if(hi_min != 0x7f800000u) atomicMin(&out->div_fail_hi_min, hi_min);
+}
+
+__global__ void proof_small_kernel(ProofOut *out) {
+  const int  i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double K    = (double)RK_OUT_RAD_PER_RAW_ANGLE * (double)RK_GEAR_RATIO_INV;
+  const float  k_hi = __double2float_rn(K);
+  const float  k_lo = __double2float_rn(K - (double)k_hi);
+  if(i <= 2 * 8192) {
+    const int   d   = i - 8192;
+    const float ref = __double2float_rn(__dmul_rn(__dmul_rn((double)d, (double)RK_OUT_RAD_PER_RAW_ANGLE), (double)RK_GEAR_RATIO_INV));
+    const float df  = (float)d;
+    if(f2u(ref) != f2u(__fmaf_rn(df, k_hi, fmul(df, k_lo)))) atomicAdd(&out->mrad_fail, 1u);
+  }
+  if(i < 65536) {
+    const int r = i - 32768;
+    if(plant_dang(r) != r * 8192 / 60000) atomicAdd(&out->dang_fail, 1u);
+  }
+}
+
+struct ProofCache {
+  bool  valid = false, ok = false;
+  float r = 0, s2 = 0, l = 0;
+  int   device = -1;
+};
+static ProofCache g_proof;
+static std::mutex g_proof_mu;
+
+// true iff the fast path may be used with these divisors on the current device
+bool fast_path_proven(const rk_vdt_params_t &p) {
+  std::lock_guard<std::mutex> lk(g_proof_mu);
+  int dev = -1;
+  if(cudaGetDevice(&dev) != cudaSuccess) return false;
+  if(g_proof.valid && g_proof.device == dev && g_proof.r == p.wheel_radius_mm && g_proof.s2 == p.sqrtf2 &&
+     g_proof.l == p.wheel_l_mm)
+    return g_proof.ok;
+  g_proof.valid = true, g_proof.ok = false, g_proof.device = dev;
+  g_proof.r = p.wheel_radius_mm, g_proof.s2 = p.sqrtf2, g_proof.l = p.wheel_l_mm;
+  if(!(p.wheel_radius_mm > 0.0f) || !(p.sqrtf2 > 0.0f) || !(p.wheel_l_mm > 0.0f)) return false;
+  ProofOut *d_out = nullptr, h[4];
+  if(cudaMalloc((void **)&d_out, 4 * sizeof(ProofOut)) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  for(int k = 0; k < 4; k++) h[k] = ProofOut{0u, 0x7f800000u, 0u, 0u};
+  cudaMemcpy(d_out, h, sizeof(h), cudaMemcpyHostToDevice);
+  const float cs[3] = {p.wheel_radius_mm, p.sqrtf2, p.wheel_l_mm};
+  for(int k = 0; k < 3; k++) proof_div_kernel<<<148 * 16, 256>>>(cs[k], d_out + k);
+  proof_small_kernel<<<256, 256>>>(d_out + 3);
+  cudaError_t e = cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost); // synchronises
+  cudaFree(d_out);
+  if(e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const unsigned int two_m40 = 0x2b800000u; // 2^-40
+  bool ok = true;
+  ok &= (h[0].div_fail_lo_max == 0u) && (h[0].div_fail_hi_min == 0x7f800000u); // radius: all floats
+  for(int k = 1; k < 3; k++) ok &= (h[k].div_fail_lo_max < two_m40) && (h[k].div_fail_hi_min == 0x7f800000u);
+  ok &= (h[3].mrad_fail == 0u) && (h[3].dang_fail == 0u);
+  g_proof.ok = ok;
+  return ok;
+}
+
+} // namespace rk
+
+extern "C" {
+/* Test / diagnostics hook: runs (or returns the cached result of) the fast-path proofs for
+ * the given parameters on the current device.  1 = proven, 0 = not proven (transcription
+ * kernel is used), <0 = error. */
+int rk_vdt_fast_path_proven(const rk_vdt_params_t *p) {
+  if(!p) return -RK_ERR_ARG;
+  if(rk::require_device() != RK_OK) return -RK_ERR_CUDA;
+  return rk::fast_path_proven(*p) ? 1 : 0;
+}
+}

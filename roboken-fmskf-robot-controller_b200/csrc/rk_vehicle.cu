@@ -4,7 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "rk_vehicle.cuh"
+#include "rk_vehicle_fast.cuh"
 
 namespace rk {
 
@@ -80,6 +80,115 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
       for(int k = 0; k < 4; k++) tr[(int64_t)(9 + k) * n] = (uint32_t)v.m[k].cur_tgt;
 #pragma unroll
       for(int j = 13; j < 16; j++) tr[(int64_t)j * n] = 0u;
+    }
+  }
+  store_veh(state, n, i, v);
+  if(a.d_cost != nullptr && a.d_goal != nullptr) {
+    const float2 g  = reinterpret_cast<const float2 *>(a.d_goal)[i];
+    const float  dx = fsub(v.pos[0], g.x), dy = fsub(v.pos[1], g.y);
+    a.d_cost[i]     = fadd(fmul(dx, dx), fmul(dy, dy));
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// Closed-loop rollout, issue-optimised (rk_vehicle_fast.cuh).  Ticks between two command
+// boundaries ("chunks") run on the fast tick when the thread's state satisfies fast_ok();
+// command application, the last tick of the launch and any thread outside the fast path's
+// domain run the transcription (veh_update), so the stored state is complete and identical.
+// -----------------------------------------------------------------------------------------
+constexpr int kFastThreads = 128;
+
+template <bool TRACE>
+RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, float py, float pth, const float vel[3],
+                      const float tgt[3], int c0, int c1, int c2, int c3) {
+  if(!TRACE) return;
+  uint32_t *tr = d_trace + (int64_t)t * RK_VDT_TRACE_WORDS * n + i;
+  tr[0] = f2u(px), tr[n] = f2u(py), tr[2 * n] = f2u(pth);
+#pragma unroll
+  for(int j = 0; j < 3; j++) tr[(int64_t)(3 + j) * n] = f2u(vel[j]), tr[(int64_t)(6 + j) * n] = f2u(tgt[j]);
+  tr[9 * n] = (uint32_t)c0, tr[10 * n] = (uint32_t)c1, tr[11 * n] = (uint32_t)c2, tr[12 * n] = (uint32_t)c3;
+  tr[13 * n] = 0u, tr[14 * n] = 0u, tr[15 * n] = 0u;
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(kFastThreads, 4)
+vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
+  constexpr int D0 = 1, D1 = 1, D2 = -1, D3 = -1; // VD_task_main.cpp:75-78 (host checks params match)
+  __shared__ float s_tab[513];
+  stage_sin_table(s_tab);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+
+  Veh v;
+  load_veh(state, n, i, v);
+  const Derived d = derive(p);
+  FastConsts    fc;
+  {
+    fc.rcp_r = fdiv(1.0f, p.wheel_radius_mm), fc.rcp_s2 = fdiv(1.0f, p.sqrtf2), fc.rcp_l = fdiv(1.0f, p.wheel_l_mm);
+    const double K = (double)RK_OUT_RAD_PER_RAW_ANGLE * (double)RK_GEAR_RATIO_INV;
+    fc.k_hi        = __double2float_rn(K);
+    fc.k_lo        = __double2float_rn(K - (double)fc.k_hi);
+    fc.A1 = d.A1, fc.B0 = d.B0, fc.ki_dt = d.ki_dt, fc.s2l = d.s2l;
+    fc.neg_i_limit = -p.i_limit, fc.neg_ff_limit = -p.ff_limit;
+  }
+  float cth, sth;
+  yaw_trig(s_tab, v.pos[2], cth, sth);
+
+  const bool has_cmd  = a.d_cmd != nullptr && a.seg_len > 0 && a.n_seg > 0;
+  const bool has_yaw  = a.d_yaw != nullptr && a.yaw_period > 0 && a.n_yaw > 0;
+  int        next_cmd = has_cmd ? 0 : INT_MAX, seg = 0;
+  int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
+  const int  K        = a.steps;
+
+  int t = 0;
+  while(t < K) {
+    if(t == next_cmd) { // VDT::main -> start(); set_target_vel()   VD_task_main.cpp:280-281,294-295
+      const uint4 cq   = __ldcs(reinterpret_cast<const uint4 *>(a.d_cmd) + (int64_t)seg * n + i);
+      const int   kind = (int)cq.w;
+      if(kind != RK_CMD_NONE) {
+        const float vv[3] = {u2f(cq.x), u2f(cq.y), u2f(cq.z)};
+        v.flags |= RK_VS_FLAG_POWER_ON;
+        if(kind == RK_CMD_STOP)
+          veh_set_target(v, vv, p.accel_stop, p.jerk_stop);
+        else
+          veh_set_target(v, vv, p.accel_move, p.jerk_move);
+      }
+      seg++;
+      next_cmd = (seg < a.n_seg) ? next_cmd + a.seg_len : INT_MAX;
+    }
+    const int t_end = min(next_cmd, K - 1); // the last tick of the launch is a transcription tick
+    if(t < t_end && fast_ok<D0, D1, D2, D3>(v, p)) {
+      FastVeh f;
+      to_fast<D0, D1, D2, D3>(v, f, p.ts);
+      const int t0  = t;
+      float     pth = v.pos[2];
+      for(; t < t_end; t++) {
+        if(t == next_yaw) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
+          pth = __ldcs(a.d_yaw + (int64_t)yk * n + i);
+          yaw_trig(s_tab, pth, cth, sth);
+          yk++;
+          next_yaw = (yk < a.n_yaw) ? next_yaw + a.yaw_period : INT_MAX;
+        }
+        float vel[3], tgt[3];
+        fast_tick<D0, D1, D2, D3>(f, p, fc, cth, sth, vel, tgt);
+        trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur);
+      }
+      v.pos[2] = pth;
+      from_fast<D0, D1, D2, D3>(v, f, t - t0);
+    } else {
+      if(t == next_yaw) {
+        v.pos[2] = __ldcs(a.d_yaw + (int64_t)yk * n + i);
+        yaw_trig(s_tab, v.pos[2], cth, sth);
+        yk++;
+        next_yaw = (yk < a.n_yaw) ? next_yaw + a.yaw_period : INT_MAX;
+      }
+      const int32_t us = ((t + 1) * 1000) & 0x7FFF;
+#pragma unroll
+      for(int k = 0; k < 4; k++) motor_rx(v.m[k], p.motor_dir[k], plant_frame(v.m[k]), us);
+      veh_update(v, p, d, cth, sth);
+      trace_row<TRACE>(a.d_trace, n, i, t, v.pos[0], v.pos[1], v.pos[2], v.vel, v.tgt, v.m[0].cur_tgt, v.m[1].cur_tgt,
+                       v.m[2].cur_tgt, v.m[3].cur_tgt);
+      t++;
     }
   }
   store_veh(state, n, i, v);
@@ -187,6 +296,26 @@ static cudaError_t launch_rollout(const rk_vdt_params_t &p, void *d_state, int64
   return cudaGetLastError();
 }
 
+bool fast_path_proven(const rk_vdt_params_t &p); // rk_exact.cu
+
+static int g_force_transcription = 0; // rk_vdt_set_option(RK_OPT_FORCE_TRANSCRIPTION, 1): tests
+
+// The fast kernel is compiled for the firmware's wiring (directions +,+,-,-) and needs
+// positive finite limits / profile tables and proven exact-division constants; anything else
+// runs the transcription kernel.
+static bool fast_path_usable(const rk_vdt_params_t &p) {
+  if(g_force_transcription) return false;
+  if(!(p.motor_dir[0] == 1 && p.motor_dir[1] == 1 && p.motor_dir[2] == -1 && p.motor_dir[3] == -1)) return false;
+  if(!(p.raw_curr_lim >= 0 && p.raw_curr_lim <= 7000)) return false;
+  auto pos = [](float x) { return x > 0.0f && x <= 1.0e9f; };
+  auto fin = [](float x) { return x >= -1.0e9f && x <= 1.0e9f; };
+  if(!(pos(p.i_limit) && pos(p.ff_limit) && pos(p.ts) && pos(p.ctrl_freq) && pos(p.lpf_freq))) return false;
+  if(!(fin(p.kff) && fin(p.kp) && fin(p.ki) && fin(p.kd))) return false;
+  for(int k = 0; k < 3; k++)
+    if(!(pos(p.accel_move[k]) && pos(p.jerk_move[k]) && pos(p.accel_stop[k]) && pos(p.jerk_stop[k]))) return false;
+  return fast_path_proven(p);
+}
+
 } // namespace rk
 
 using namespace rk;
@@ -208,6 +337,15 @@ int rk_device_info(int device, int *sm_count, int *sm_clock_khz, size_t *hbm_byt
   }
   if(hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
   return RK_OK;
+}
+
+int rk_set_option(int option, int value) {
+  if(option == RK_OPT_FORCE_TRANSCRIPTION) {
+    rk::g_force_transcription = value;
+    return RK_OK;
+  }
+  set_error("rk_set_option: unknown option %d", option);
+  return RK_ERR_ARG;
 }
 
 int rk_set_device(int device) {
@@ -262,7 +400,18 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
   cudaError_t  e;
   switch(args->sensor_mode) {
   case RK_SENSOR_HOLD: e = launch_rollout<RK_SENSOR_HOLD>(*p, d_state, n, *args, st); break;
-  case RK_SENSOR_PLANT: e = launch_rollout<RK_SENSOR_PLANT>(*p, d_state, n, *args, st); break;
+  case RK_SENSOR_PLANT:
+    if(fast_path_usable(*p)) {
+      const unsigned grid = (unsigned)((n + kFastThreads - 1) / kFastThreads);
+      if(args->d_trace)
+        vdt_rollout_fast_kernel<true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+      else
+        vdt_rollout_fast_kernel<false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+      e = cudaGetLastError();
+    } else {
+      e = launch_rollout<RK_SENSOR_PLANT>(*p, d_state, n, *args, st);
+    }
+    break;
   case RK_SENSOR_STREAM: e = launch_rollout<RK_SENSOR_STREAM>(*p, d_state, n, *args, st); break;
   default: set_error("rk_vdt_rollout: bad sensor_mode %d", args->sensor_mode); return RK_ERR_ARG;
   }

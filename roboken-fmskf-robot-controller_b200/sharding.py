@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing: contiguous batch slices, no data-path collective.
+
+Robot instances are independent (the only cross-talk in the firmware is inside one robot:
+IMU yaw -> vehicle, VD_task_main.cpp:368), so G GPUs run G disjoint contiguous slices of the
+instance index space, one process per GPU.  torch.distributed is used for exactly three
+things: the start barrier, the max-over-ranks of the device-timed duration, and the optional
+end-of-rollout gather of one cost scalar per instance (NCCL all_gather over NVLink on GPU,
+gloo in the CPU tests).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    """(rank, local_rank, world_size) from the torchrun environment (1 process = 1 GPU)."""
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def shard_range(n_total, rank, world):
+    """Contiguous slice [lo, hi) of rank `rank`; the first n_total % world ranks get one more."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init(backend=None):
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {}
+        if (backend or "nccl") == "nccl":
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend or "nccl", rank=rank, world_size=world, **kw)
+    return rank, local_rank, world
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value, device="cpu"):
+    """Max of a python float over all ranks (the job's duration is its slowest rank's)."""
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device="cpu"):
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_costs(cost):
+    """All ranks' per-instance cost vectors concatenated in rank order (equal-size slices)."""
+    if not dist.is_initialized():
+        return cost
+    world = dist.get_world_size()
+    out = torch.empty(world * cost.numel(), dtype=cost.dtype, device=cost.device)
+    dist.all_gather_into_tensor(out, cost.contiguous())
+    return out
