@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--seg-len", type=int, default=125)
     ap.add_argument("--yaw-period", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall budget of the cpu_baseline leg")
+    ap.add_argument("--occupancy", type=int, default=0, help="RK_OPT_FAST_OCCUPANCY override (tuning)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -213,6 +214,8 @@ def run_ours(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _cabi.check(lib.rk_set_device(local_rank))
+    if a.occupancy:
+        _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_OCCUPANCY, a.occupancy))
     n, K, W, T = a.instances, a.steps, a.warmup, a.ticks
     first = rank * n  # contiguous slice of the global instance index space
     n_seg = (T + a.seg_len - 1) // a.seg_len
@@ -309,7 +312,7 @@ def run_ours(a):
         "nonfused_issue_peak": issue_tflops,
         "frac_of_nonfused_issue_peak": achieved_tflops / issue_tflops,
         "algorithmic_flop_per_tick": FLOP_PER_TICK,
-        "kernel": "rk::vdt_rollout_kernel<RK_SENSOR_PLANT,false>",
+        "kernel": "rk::vdt_rollout_fast_kernel<false,OCC>",
         "launch_ms": launch_s * 1e3,
         "traffic": None,
         "hbm": {"achieved": alg_bytes / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -55,7 +55,10 @@ int rk_set_device(int device);
 /* Library options (process-wide).  RK_OPT_FORCE_TRANSCRIPTION = 1 makes RK_SENSOR_PLANT
  * rollouts use the direct transcription kernel instead of the issue-optimised one (the two
  * are bit-identical; the tests compare them). */
-enum { RK_OPT_FORCE_TRANSCRIPTION = 1 };
+enum {
+  RK_OPT_FORCE_TRANSCRIPTION = 1,
+  RK_OPT_FAST_OCCUPANCY = 2 /* 3, 4 (default) or 5 resident CTAs/SM: register budget of the rollout kernel */
+};
 int rk_set_option(int option, int value);
 /* 1 if the exhaustive on-device proofs that gate the issue-optimised kernel hold for these
  * parameters on the current device (csrc/rk_exact.cu), 0 if not, < 0 on error. */

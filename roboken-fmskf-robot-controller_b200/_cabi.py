@@ -16,6 +16,7 @@ RK_SENSOR_HOLD, RK_SENSOR_PLANT, RK_SENSOR_STREAM = 0, 1, 2
 RK_CMD_NONE, RK_CMD_MOVE, RK_CMD_STOP = 0, 1, 2
 RK_VDT_TRACE_WORDS = 16
 RK_OPT_FORCE_TRANSCRIPTION = 1
+RK_OPT_FAST_OCCUPANCY = 2
 
 
 class VdtParams(C.Structure):

@@ -110,8 +110,8 @@ RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, 
   tr[13 * n] = 0u, tr[14 * n] = 0u, tr[15 * n] = 0u;
 }
 
-template <bool TRACE>
-__global__ void __launch_bounds__(kFastThreads, 4)
+template <bool TRACE, int OCC, bool FFSAT>
+__global__ void __launch_bounds__(kFastThreads, OCC)
 vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
   constexpr int D0 = 1, D1 = 1, D2 = -1, D3 = -1; // VD_task_main.cpp:75-78 (host checks params match)
   __shared__ float s_tab[513];
@@ -139,6 +139,20 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
   int        next_cmd = has_cmd ? 0 : INT_MAX, seg = 0;
   int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
   const int  K        = a.steps;
+  // The yaw sample for the next boundary is fetched one period ahead, so its HBM latency
+  // hides behind yaw_period ticks of arithmetic instead of stalling every warp at once.
+  float yaw_pf = has_yaw ? __ldcs(a.d_yaw + i) : 0.0f;
+  auto  take_yaw = [&](float &pth) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
+    pth = yaw_pf;
+    yaw_trig(s_tab, pth, cth, sth);
+    yk++;
+    if(yk < a.n_yaw) {
+      next_yaw += a.yaw_period;
+      yaw_pf = __ldcs(a.d_yaw + (int64_t)yk * n + i);
+    } else {
+      next_yaw = INT_MAX;
+    }
+  };
 
   int t = 0;
   while(t < K) {
@@ -159,29 +173,23 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
     const int t_end = min(next_cmd, K - 1); // the last tick of the launch is a transcription tick
     if(t < t_end && fast_ok<D0, D1, D2, D3>(v, p)) {
       FastVeh f;
-      to_fast<D0, D1, D2, D3>(v, f, p.ts);
+      to_fast<D0, D1, D2, D3>(v, f, p.ts, fc.B0);
       const int t0  = t;
       float     pth = v.pos[2];
-      for(; t < t_end; t++) {
-        if(t == next_yaw) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
-          pth = __ldcs(a.d_yaw + (int64_t)yk * n + i);
-          yaw_trig(s_tab, pth, cth, sth);
-          yk++;
-          next_yaw = (yk < a.n_yaw) ? next_yaw + a.yaw_period : INT_MAX;
+      while(t < t_end) {
+        if(t == next_yaw) take_yaw(pth);
+        const int t_stop = min(t_end, next_yaw);
+#pragma unroll 2
+        for(; t < t_stop; t++) {
+          float vel[3], tgt[3];
+          fast_tick<D0, D1, D2, D3, FFSAT>(f, p, fc, cth, sth, vel, tgt);
+          trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur);
         }
-        float vel[3], tgt[3];
-        fast_tick<D0, D1, D2, D3>(f, p, fc, cth, sth, vel, tgt);
-        trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur);
       }
       v.pos[2] = pth;
       from_fast<D0, D1, D2, D3>(v, f, t - t0);
     } else {
-      if(t == next_yaw) {
-        v.pos[2] = __ldcs(a.d_yaw + (int64_t)yk * n + i);
-        yaw_trig(s_tab, v.pos[2], cth, sth);
-        yk++;
-        next_yaw = (yk < a.n_yaw) ? next_yaw + a.yaw_period : INT_MAX;
-      }
+      if(t == next_yaw) take_yaw(v.pos[2]);
       const int32_t us = ((t + 1) * 1000) & 0x7FFF;
 #pragma unroll
       for(int k = 0; k < 4; k++) motor_rx(v.m[k], p.motor_dir[k], plant_frame(v.m[k]), us);
@@ -298,6 +306,7 @@ static cudaError_t launch_rollout(const rk_vdt_params_t &p, void *d_state, int64
 
 bool fast_path_proven(const rk_vdt_params_t &p); // rk_exact.cu
 
+static int g_fast_occupancy = 4;       // rk_set_option(RK_OPT_FAST_OCCUPANCY, 3|4|5): tuning
 static int g_force_transcription = 0; // rk_vdt_set_option(RK_OPT_FORCE_TRANSCRIPTION, 1): tests
 
 // The fast kernel is compiled for the firmware's wiring (directions +,+,-,-) and needs
@@ -344,7 +353,11 @@ int rk_set_option(int option, int value) {
     rk::g_force_transcription = value;
     return RK_OK;
   }
-  set_error("rk_set_option: unknown option %d", option);
+  if(option == RK_OPT_FAST_OCCUPANCY && (value >= 3 && value <= 5)) {
+    rk::g_fast_occupancy = value;
+    return RK_OK;
+  }
+  set_error("rk_set_option: unknown option %d / bad value %d", option, value);
   return RK_ERR_ARG;
 }
 
@@ -403,10 +416,24 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
   case RK_SENSOR_PLANT:
     if(fast_path_usable(*p)) {
       const unsigned grid = (unsigned)((n + kFastThreads - 1) / kFastThreads);
-      if(args->d_trace)
-        vdt_rollout_fast_kernel<true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
-      else
-        vdt_rollout_fast_kernel<false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+      const bool ffsat = (p->ff_limit == 1.0f);
+#define RK_LAUNCH_FAST(TR, OCC)                                                                                    \
+  do {                                                                                                             \
+    if(ffsat)                                                                                                      \
+      vdt_rollout_fast_kernel<TR, OCC, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);     \
+    else                                                                                                           \
+      vdt_rollout_fast_kernel<TR, OCC, false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);    \
+  } while(0)
+      if(args->d_trace) {
+        RK_LAUNCH_FAST(true, 4);
+      } else {
+        switch(g_fast_occupancy) { // resident CTAs per SM the kernel is compiled for (register budget)
+        case 3: RK_LAUNCH_FAST(false, 3); break;
+        case 5: RK_LAUNCH_FAST(false, 5); break;
+        default: RK_LAUNCH_FAST(false, 4); break;
+        }
+      }
+#undef RK_LAUNCH_FAST
       e = cudaGetLastError();
     } else {
       e = launch_rollout<RK_SENSOR_PLANT>(*p, d_state, n, *args, st);

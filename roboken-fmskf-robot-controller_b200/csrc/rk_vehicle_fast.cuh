@@ -6,8 +6,8 @@
 //     per-tick angle step |dang| < 4096, so the +-4096 unwrap of rx_callback
 //     (VD_motor_if_m2006.cpp:66-69) returns exactly dir*dang; no byte frame is built and the
 //     s64 angle sum is carried as a 32-bit per-launch delta;
-//   * every x / c with a launch-constant divisor uses q = x*rcp; r = fma(-q,c,x);
-//     q' = fma(r,rcp,q) | sign(x), which rk_exact.cu proves bit-identical to IEEE x / c by
+//   * every x / c with a launch-constant divisor uses q = x*rcp; e = fma(q,c,-x);
+//     q' = fma(-(q*c-x),rcp,q), which rk_exact.cu proves bit-identical to IEEE x / c by
 //     exhaustive search over all 2^32 inputs before the fast path is enabled;
 //   * the odometry product (double)d * OUT_RAD_PER_RAW_ANGLE * GEAR_RATIO_INV -> float
 //     (VD_vehicle_controller.cpp:37-41) is fma(d, K_hi, d*K_lo) in FP32, verified against the
@@ -30,17 +30,19 @@ struct FastConsts {
   float neg_i_limit, neg_ff_limit;
 };
 
-// exact x / c for launch-constant c > 0 (see header comment); rcp = RN(1/c)
+// exact x / c for launch-constant c > 0 (see header comment); rcp = RN(1/c).
+// e = q*c - x is exact; writing the correction as fma(-e, rcp, q) (rather than r = x - q*c,
+// fma(r, rcp, q)) also returns the IEEE sign for x = +-0, with no fix-up instruction.
 RK_DEV float div_const(float x, float c, float rcp) {
-  float q  = fmul(x, rcp);
-  float r  = __fmaf_rn(-q, c, x);
-  float q2 = __fmaf_rn(r, rcp, q);
-  return u2f(f2u(q2) | (f2u(x) & 0x80000000u));
+  const float q = fmul(x, rcp);
+  const float e = __fmaf_rn(q, c, -x);
+  return __fmaf_rn(-e, rcp, q);
 }
 
-// rpm * 8192 / 60000 (C truncating division) for |rpm| <= 32768: signed magic multiply,
-// verified exhaustively by rk_exact.cu.
-RK_DEV int32_t plant_dang(int32_t rpm) { return (__mulhi(rpm, 1172812403) >> 1) + (int32_t)((uint32_t)rpm >> 31); }
+// rpm * 8192 / 60000 (C truncating division) for |rpm| <= 32768: one signed high multiply by
+// ceil(2^32 * 8192 / 60000) gives the floor; adding the sign bit turns it into truncation.
+// Verified for every int16 by rk_exact.cu.
+RK_DEV int32_t plant_dang(int32_t rpm) { return __mulhi(rpm, 586406202) + (int32_t)((uint32_t)rpm >> 31); }
 
 struct FastInterp { // VelInterpConstJerk with the phase thresholds hoisted out of the tick
   float vel, acl, dt;
@@ -51,6 +53,7 @@ struct FastWheel {
   int32_t rpm, cur;  // plant rpm and s16_rawCurr_tgt, motor frame
   int32_t dsum;      // sum over this chunk of the WHEEL-frame angle steps (= the s16 deltas rx_callback adds)
   float   prev_val, integ, lpf_y, lpf_x; // FF_PI_D state
+  float   b0x;                           // B0 * lpf_x, carried so the product is formed once (B1 == B0)
 };
 struct FastVeh {
   float      px, py;
@@ -65,6 +68,9 @@ RK_DEV void fast_interp_load(FastInterp &f, const Interp &t, float ts) {
   f.t1 = fadd(t.dt1, ts);
   f.t2 = fadd(fadd(t.dt1, t.dt2), ts);
   f.t3 = fadd(fadd(fadd(t.dt1, t.dt2), t.dt3), ts);
+  // keep the thresholds in registers: without this ptxas rematerialises the six adds per
+  // interpolator every tick
+  asm volatile("" : "+f"(f.t1), "+f"(f.t2), "+f"(f.t3));
 }
 RK_DEV void fast_interp_store(const FastInterp &f, Interp &t) {
   t.vel = f.vel, t.acl = f.acl, t.dt = f.dt;
@@ -125,7 +131,7 @@ RK_DEV bool fast_ok(const Veh &v, const rk_vdt_params_t &p) {
 }
 
 template <int D0, int D1, int D2, int D3>
-RK_DEV void to_fast(const Veh &v, FastVeh &f, float ts) {
+RK_DEV void to_fast(const Veh &v, FastVeh &f, float ts, float b0) {
   f.px = v.pos[0], f.py = v.pos[1];
 #pragma unroll
   for(int a = 0; a < 3; a++) fast_interp_load(f.it[a], v.it[a], ts);
@@ -133,6 +139,7 @@ RK_DEV void to_fast(const Veh &v, FastVeh &f, float ts) {
   for(int k = 0; k < 4; k++) {
     f.w[k].rpm = v.m[k].p_rpm, f.w[k].cur = v.m[k].cur_tgt, f.w[k].dsum = 0;
     f.w[k].prev_val = v.c[k].prev_val, f.w[k].integ = v.c[k].integ, f.w[k].lpf_y = v.c[k].lpf_y, f.w[k].lpf_x = v.c[k].lpf_x;
+    f.w[k].b0x = fmul(b0, v.c[k].lpf_x);
   }
 }
 
@@ -182,28 +189,37 @@ RK_DEV void fast_wheel_sense(FastWheel &w, const FastConsts &fc, float &mvel, fl
 }
 
 // FF_PI_D::update + set_CurrA_tgt for one wheel (util_controller.hpp:94-110,159-165;
-// VD_motor_if_m2006.hpp:36-37,57)
-template <int DIR>
+// VD_motor_if_m2006.hpp:36-37,57).  FFSAT: ff_limit == 1.0f, so the feed-forward clamp
+// clamp(t, -1, 1) is sat(t) - sat(-t) with sat = clamp to [0,1] -- two FMUL.SAT on the FMA
+// pipe instead of two half-rate FMNMX.  (It returns +0 for t = -0; u only feeds the integer
+// conversion here, so the sign of a zero feed-forward is immaterial.)
+template <int DIR, bool FFSAT>
 RK_DEV void fast_wheel_ctrl(FastWheel &w, const rk_vdt_params_t &p, const FastConsts &fc, float mtgt, float mvel) {
   const float tgt = fmul(mtgt, RK_GEAR_RATIO);
   const float now = fmul(mvel, RK_GEAR_RATIO);
   const float err = fsub(tgt, now);
   const float x   = fmul(fsub(now, w.prev_val), p.ctrl_freq);
-  const float y   = fadd(fadd(fmul(fc.A1, w.lpf_y), fmul(fc.B0, x)), fmul(fc.B0, w.lpf_x));
+  const float b0x = fmul(fc.B0, x);
+  const float y   = fadd(fadd(fmul(fc.A1, w.lpf_y), b0x), w.b0x); // B1 * prev_X_ with B1 == B0
   w.lpf_y         = y;
   w.lpf_x         = x;
+  w.b0x           = b0x;
   w.integ         = clamp_sym(fadd(w.integ, fmul(fc.ki_dt, err)), p.i_limit, fc.neg_i_limit);
   float u         = fsub(fadd(fmul(p.kp, err), w.integ), fmul(p.kd, y));
   w.prev_val      = now;
-  const float ff  = clamp_sym(fmul(tgt, p.kff), p.ff_limit, fc.neg_ff_limit);
-  u               = fadd(u, ff);
-  int32_t t       = __float2int_rz(fmul(u, RK_AMPERE_TO_RAW_CURR));
-  t               = sext16(DIR > 0 ? t : -t);
-  w.cur           = min(max(t, -p.raw_curr_lim), p.raw_curr_lim);
+  float ff;
+  if(FFSAT)
+    ff = fsub(__saturatef(fmul(tgt, p.kff)), __saturatef(fmul(tgt, -p.kff)));
+  else
+    ff = clamp_sym(fmul(tgt, p.kff), p.ff_limit, fc.neg_ff_limit);
+  u         = fadd(u, ff);
+  int32_t t = __float2int_rz(fmul(u, RK_AMPERE_TO_RAW_CURR));
+  t         = sext16(DIR > 0 ? t : -t);
+  w.cur     = min(max(t, -p.raw_curr_lim), p.raw_curr_lim);
 }
 
 // One fast tick = plant + rx_callback x4 + VEHICLE_CTRL::update()
-template <int D0, int D1, int D2, int D3>
+template <int D0, int D1, int D2, int D3, bool FFSAT>
 RK_DEV void fast_tick(FastVeh &f, const rk_vdt_params_t &p, const FastConsts &fc, float cth, float sth,
                       float vel[3], float tgt[3]) {
   float Mvel[4], Mrad[4], Mtgt[4];
@@ -232,10 +248,10 @@ RK_DEV void fast_tick(FastVeh &f, const rk_vdt_params_t &p, const FastConsts &fc
   Mtgt[1]         = div_const(fsub(xpy, T), R, fc.rcp_r);
   Mtgt[2]         = div_const(fadd(xmy, T), R, fc.rcp_r);
   Mtgt[3]         = div_const(fadd(xpy, T), R, fc.rcp_r);
-  fast_wheel_ctrl<D0>(f.w[0], p, fc, Mtgt[0], Mvel[0]);
-  fast_wheel_ctrl<D1>(f.w[1], p, fc, Mtgt[1], Mvel[1]);
-  fast_wheel_ctrl<D2>(f.w[2], p, fc, Mtgt[2], Mvel[2]);
-  fast_wheel_ctrl<D3>(f.w[3], p, fc, Mtgt[3], Mvel[3]);
+  fast_wheel_ctrl<D0, FFSAT>(f.w[0], p, fc, Mtgt[0], Mvel[0]);
+  fast_wheel_ctrl<D1, FFSAT>(f.w[1], p, fc, Mtgt[1], Mvel[1]);
+  fast_wheel_ctrl<D2, FFSAT>(f.w[2], p, fc, Mtgt[2], Mvel[2]);
+  fast_wheel_ctrl<D3, FFSAT>(f.w[3], p, fc, Mtgt[3], Mvel[3]);
 }
 
 // set_target_params on the fast state (shares interp_set with the transcription)
