@@ -210,6 +210,51 @@ int  rk_vdt_get_angle_sum(rk_vdt_t *h, int64_t out[4]);   /* MOTOR_IF_M2006::get
 int  rk_vdt_get_state(rk_vdt_t *h, uint32_t words[RK_VS_WORDS]);
 int  rk_vdt_set_state(rk_vdt_t *h, const uint32_t words[RK_VS_WORDS]);
 
+/* =====================================================================================
+ * IMU (src/Imu): the WT901C "state-estimation update".  The firmware contains no Kalman
+ * filter -- the sensor fuses on-chip; IMU_IF_WT901C::updateData() (imu_if_wt901c.cpp:91-129)
+ * scales 16 int16 registers, flips the Y/Z signs, re-wraps roll and re-references the
+ * quaternion against the boot-time quaternion q_init.
+ * ===================================================================================== */
+/* register order of one sample (the sReg[] entries updateData() reads; lib/wt901c/REG.h) */
+enum {
+  RK_IMT_REG_AX = 0, RK_IMT_REG_AY, RK_IMT_REG_AZ, RK_IMT_REG_GX, RK_IMT_REG_GY, RK_IMT_REG_GZ,
+  RK_IMT_REG_HX, RK_IMT_REG_HY, RK_IMT_REG_HZ, RK_IMT_REG_ROLL, RK_IMT_REG_PITCH, RK_IMT_REG_YAW,
+  RK_IMT_REG_Q0, RK_IMT_REG_Q1, RK_IMT_REG_Q2, RK_IMT_REG_Q3, RK_IMT_REGS
+};
+/* IMU state words: plane 0 q_init[4] (imu_if_wt901c.hpp:39); planes 1-4 the readable page of
+ * d_buf as IMU_IF::Data {accel[3], gyro[3], mag[3], angle[3], qut[4]} in struct order
+ * (imu_if_base.hpp:12-18); plane 5 flags. */
+enum { RK_IS_QINIT = 0, RK_IS_DATA = 4, RK_IS_FLAGS = 20, RK_IS_WORDS = 24 };
+enum { RK_IS_D_ACCEL = 0, RK_IS_D_GYRO = 3, RK_IS_D_MAG = 6, RK_IS_D_ANGLE = 9, RK_IS_D_QUT = 12 };
+#define RK_IS_FLAG_ERROR 1u /* IMU_IF_WT901C::is_error */
+
+size_t rk_imt_state_words(void);
+size_t rk_imt_state_bytes(int64_t n);
+
+/* K fused IMU_IF_WT901C::update() calls (imu_if_wt901c.cpp:83-89) for n instances.
+ *  d_regs      int16, sample u / register r / instance i at ((u*16)+r)*n + i  (16 SoA planes
+ *              per sample: the sReg[] snapshot at the time update() runs)
+ *  d_have_quat uint8 [K][n] or NULL (= all 1): whether a quaternion frame arrived since the
+ *              last call (isComComp(), :132-143); 0 -> is_error = true, data retained
+ *  d_out       optional getDataLatest() after each update, as 128-bit planes like the state:
+ *              word w of sample u, instance i at ((u*4 + w/4)*n + i)*4 + w%4 (16-byte aligned)
+ *  do_init     != 0: the first sample is consumed by IMU_IF_WT901C::init() (:63-77) instead:
+ *              updateData() against the current q_init, then q_init latched from q0..q3 */
+int rk_imt_update(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat,
+                  float *d_out, int do_init, void *stream);
+
+/* single-instance handle (drop-in for `static IMU_IF_WT901C imu_if`, imu_task_main.cpp:25) */
+typedef struct rk_imt rk_imt_t;
+int   rk_imt_create(rk_imt_t **out);
+void  rk_imt_destroy(rk_imt_t *h);
+int   rk_imt_init(rk_imt_t *h, const int16_t regs[RK_IMT_REGS]);                /* ::init()          */
+int   rk_imt_update1(rk_imt_t *h, const int16_t regs[RK_IMT_REGS], int have_quat); /* ::update()     */
+int   rk_imt_get(rk_imt_t *h, float data[16], int *is_error); /* ::getDataLatest() / ::isError()      */
+int   rk_imt_get_yaw(rk_imt_t *h, float *yaw_deg);            /* ::getYawDate()  :160-162             */
+int   rk_imt_get_state(rk_imt_t *h, uint32_t words[RK_IS_WORDS]);
+int   rk_imt_set_state(rk_imt_t *h, const uint32_t words[RK_IS_WORDS]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,166 @@
+/* TEST INFRASTRUCTURE (oracle) -- never linked into the product library.
+ *
+ * C-ABI harness around the UNMODIFIED reference IMU sources
+ *   src/Imu/imu_if_wt901c.{hpp,cpp}, src/Imu/imu_if_base.hpp, lib/wt901c/wit_c_sdk.{c,h}, REG.h
+ * compiled where they lie under /root/reference (oracle/Makefile -> oracle/_ref/libref_imu.so).
+ * Sensor samples enter exactly as on the robot: as WT901 serial frames (0x55, type, 4 x int16
+ * little-endian, 8-bit checksum -- lib/wt901c/wit_c_sdk.c:132-164) pushed into the fake
+ * Serial6 FIFO, drained by IMU_IF_WT901C::isComComp() through WitSerialDataIn().
+ *
+ * The WIT SDK keeps its register file and parser state in globals (sReg[], s_cDataUpdate),
+ * so this library holds ONE live IMU at a time; batches run instance after instance.
+ */
+#include <new>
+#include <stdlib.h>
+#include <string.h>
+
+#include "Imu/imu_if_wt901c.hpp"
+extern "C" {
+#include <wit_c_sdk.h>
+}
+#include "robotick.h"
+
+HardwareSerial Serial6;
+HardwareSerial Serial7;
+uint32_t       get_gptimer_cnt() { return 0; }
+namespace DEBUG {
+char EXT_PRINT_BUF[1024];
+void print(char *, uint32_t) {}
+void record_proc_load(uint8_t, uint8_t) {}
+} // namespace DEBUG
+namespace LGT {
+void push_buffer(char *, uint32_t) {}
+} // namespace LGT
+
+namespace {
+
+using IMT::IMU_IF_WT901C;
+
+void push_frame(uint8_t type, const int16_t w[4]) {
+  uint8_t f[11];
+  f[0] = 0x55, f[1] = type;
+  for(int k = 0; k < 4; k++) f[2 + 2 * k] = (uint8_t)(w[k] & 0xFF), f[3 + 2 * k] = (uint8_t)((w[k] >> 8) & 0xFF);
+  uint8_t s = 0;
+  for(int k = 0; k < 10; k++) s += f[k];
+  f[10] = s;
+  Serial6.feed(f, 11);
+}
+
+/* regs: AX AY AZ GX GY GZ HX HY HZ Roll Pitch Yaw q0 q1 q2 q3 (robotick.h RK_IMT_REG_*) */
+void push_sample(const int16_t r[16], int have_quat) {
+  const int16_t acc[4] = {r[0], r[1], r[2], 0}, gyr[4] = {r[3], r[4], r[5], 0}, mag[4] = {r[6], r[7], r[8], 0};
+  const int16_t ang[4] = {r[9], r[10], r[11], 0}, qut[4] = {r[12], r[13], r[14], r[15]};
+  push_frame(WIT_ACC, acc);
+  push_frame(WIT_GYRO, gyr);
+  push_frame(WIT_ANGLE, ang);
+  push_frame(WIT_MAGNETIC, mag);
+  if(have_quat) push_frame(WIT_QUATER, qut);
+}
+
+inline uint32_t f2u(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+inline float u2f(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+void export_state(IMU_IF_WT901C *m, uint32_t *w) {
+  memset(w, 0, 4 * RK_IS_WORDS);
+  for(int k = 0; k < 4; k++) w[RK_IS_QINIT + k] = f2u(m->q_init[k]);
+  const IMT::IMU_IF::Data &d = m->d_buf[m->u8_d_buf_read_page];
+  memcpy(&w[RK_IS_DATA], &d, 16 * 4);
+  w[RK_IS_FLAGS] = m->is_error ? RK_IS_FLAG_ERROR : 0u;
+}
+void import_state(IMU_IF_WT901C *m, const uint32_t *w) {
+  for(int k = 0; k < 4; k++) m->q_init[k] = u2f(w[RK_IS_QINIT + k]);
+  memset(m->d_buf, 0, sizeof(m->d_buf));
+  m->u8_d_buf_read_page = 0;
+  memcpy(&m->d_buf[0], &w[RK_IS_DATA], 16 * 4);
+  m->is_error = (w[RK_IS_FLAGS] & RK_IS_FLAG_ERROR) != 0;
+}
+
+IMU_IF_WT901C *make() {
+  void *mem = calloc(1, sizeof(IMU_IF_WT901C));
+  return new(mem) IMU_IF_WT901C();
+}
+
+inline uint32_t &soa(uint32_t *blk, int64_t n, int64_t i, int w) { return blk[((int64_t)(w / 4) * n + i) * 4 + (w % 4)]; }
+
+} // namespace
+
+extern "C" {
+
+void *ref_imt_create(void) {
+  memset(sReg, 0, sizeof(int16_t) * REGSIZE);
+  return make();
+}
+void ref_imt_destroy(void *h) {
+  if(!h) return;
+  ((IMU_IF_WT901C *)h)->~IMU_IF_WT901C();
+  free(h);
+}
+/* IMU_IF_WT901C::init()  imu_if_wt901c.cpp:63-77 with the boot-time sample already on the wire */
+void ref_imt_init(void *h, const int16_t regs[16]) {
+  push_sample(regs, 1);
+  ((IMU_IF_WT901C *)h)->init();
+}
+/* IMU_IF_WT901C::update()  :83-89 */
+void ref_imt_update(void *h, const int16_t regs[16], int have_quat) {
+  push_sample(regs, have_quat);
+  ((IMU_IF_WT901C *)h)->update();
+}
+float ref_imt_yaw(void *h) { return ((IMU_IF_WT901C *)h)->getYawDate(); }
+int   ref_imt_is_error(void *h) { return ((IMU_IF_WT901C *)h)->isError() ? 1 : 0; }
+void  ref_imt_get(void *h, float out[16]) {
+  IMT::IMU_IF::Data d;
+  ((IMU_IF_WT901C *)h)->getDataLatest(d);
+  memcpy(out, &d, 64);
+}
+void ref_imt_export(void *h, uint32_t *words) { export_state((IMU_IF_WT901C *)h, words); }
+void ref_imt_import(void *h, const uint32_t *words) { import_state((IMU_IF_WT901C *)h, words); }
+
+/* Same contract as rk_imt_update() on HOST arrays: K updates of instances [i0,i1).
+ * regs: int16 [K][16][n] (sample u, register r, instance i at ((u*16)+r)*n+i);
+ * have_quat: uint8 [K][n] or NULL; out: Data planes [K][4][n] float4 or NULL; do_init: run init() with the
+ * first sample instead of update(). */
+void ref_imt_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, const int16_t *regs,
+                     const uint8_t *have_quat, uint32_t *out, int do_init) {
+  for(int64_t i = i0; i < i1; i++) {
+    memset(sReg, 0, sizeof(int16_t) * REGSIZE);
+    IMU_IF_WT901C *m = make();
+    uint32_t       w[RK_IS_WORDS];
+    if(state) {
+      for(int k = 0; k < RK_IS_WORDS; k++) w[k] = soa(state, n, i, k);
+      import_state(m, w);
+    }
+    for(int u = 0; u < K; u++) {
+      int16_t r[16];
+      for(int k = 0; k < 16; k++) r[k] = regs[((int64_t)u * 16 + k) * n + i];
+      int hq = have_quat ? have_quat[(int64_t)u * n + i] : 1;
+      if(do_init && u == 0) {
+        push_sample(r, 1);
+        m->init();
+      } else {
+        push_sample(r, hq);
+        m->update();
+      }
+      if(out) {
+        IMT::IMU_IF::Data d;
+        m->getDataLatest(d);
+        const uint32_t *dw = (const uint32_t *)&d;
+        for(int k = 0; k < 16; k++) out[(((int64_t)u * 4 + k / 4) * n + i) * 4 + (k % 4)] = dw[k];
+      }
+    }
+    if(state) {
+      export_state(m, w);
+      for(int k = 0; k < RK_IS_WORDS; k++) soa(state, n, i, k) = w[k];
+    }
+    m->~IMU_IF_WT901C();
+    free(m);
+  }
+}
+}

@@ -474,3 +474,65 @@ void orc_vdt_update(const rk_vdt_params_t *p, uint32_t *words) {
   veh_update(&s, p);
   pack(&s, words);
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* IMU_IF_WT901C::updateData   src/Imu/imu_if_wt901c.cpp:91-129                           */
+static void imu_update_data(const float qi[4], const int16_t r[16], float d[16]) {
+  float a[3], g[3], m[3], e[3], q[4];
+  int   i;
+  for(i = 0; i < 3; i++) {
+    a[i] = (float)r[RK_IMT_REG_AX + i] / 32768.0f * 16.0f;
+    g[i] = (float)r[RK_IMT_REG_GX + i] / 32768.0f * 2000.0f;
+    m[i] = (float)r[RK_IMT_REG_HX + i];
+    e[i] = (float)r[RK_IMT_REG_ROLL + i] / 32768.0f * 180.0f;
+  }
+  for(i = 0; i < 4; i++) q[i] = r[RK_IMT_REG_Q0 + i] / 32768.0f;
+  d[0] = a[0], d[1] = -a[1], d[2] = -a[2];
+  d[3] = g[0], d[4] = -g[1], d[5] = -g[2];
+  d[6] = m[0], d[7] = -m[1], d[8] = -m[2];
+  d[9]  = orc_normalize_deg_0to360(e[0]) - 180.0f;
+  d[10] = e[1];
+  d[11] = e[2];
+  d[14] = -(qi[3] * q[0] + qi[2] * q[1] - qi[1] * q[2] - qi[0] * q[3]);
+  d[13] = (-qi[2] * q[0] + qi[3] * q[1] + qi[0] * q[2] - qi[1] * q[3]);
+  d[12] = -(qi[1] * q[0] - qi[0] * q[1] + qi[3] * q[2] - qi[2] * q[3]);
+  d[15] = (qi[0] * q[0] + qi[1] * q[1] + qi[2] * q[2] + qi[3] * q[3]);
+}
+
+void orc_imt_update(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, const int16_t *regs,
+                    const uint8_t *have_quat, uint32_t *out, int do_init) {
+  int64_t i;
+  int     u, k;
+  for(i = i0; i < i1; i++) {
+    float    qi[4] = {0, 0, 0, 0}, d[16];
+    uint32_t flags = 0;
+    memset(d, 0, sizeof(d));
+    if(state) {
+      for(k = 0; k < 4; k++) qi[k] = u2f(*soa(state, n, i, RK_IS_QINIT + k));
+      for(k = 0; k < 16; k++) d[k] = u2f(*soa(state, n, i, RK_IS_DATA + k));
+      flags = *soa(state, n, i, RK_IS_FLAGS);
+    }
+    for(u = 0; u < K; u++) {
+      int16_t r[16];
+      int     hq = have_quat ? have_quat[(int64_t)u * n + i] : 1;
+      for(k = 0; k < 16; k++) r[k] = regs[((int64_t)u * 16 + k) * n + i];
+      if(do_init && u == 0) { /* IMU_IF_WT901C::init  :63-77 (getDataImmediately -> updateData, then latch) */
+        imu_update_data(qi, r, d);
+        for(k = 0; k < 4; k++) qi[k] = r[RK_IMT_REG_Q0 + k] / 32768.0f;
+      } else if(hq) { /* ::update  :83-89 */
+        flags &= ~RK_IS_FLAG_ERROR;
+        imu_update_data(qi, r, d);
+      } else {
+        flags |= RK_IS_FLAG_ERROR;
+      }
+      if(out)
+        for(k = 0; k < 16; k++) out[(((int64_t)u * 4 + k / 4) * n + i) * 4 + (k % 4)] = f2u(d[k]);
+    }
+    if(state) {
+      for(k = 0; k < 4; k++) *soa(state, n, i, RK_IS_QINIT + k) = f2u(qi[k]);
+      for(k = 0; k < 16; k++) *soa(state, n, i, RK_IS_DATA + k) = f2u(d[k]);
+      *soa(state, n, i, RK_IS_FLAGS) = flags;
+      for(k = RK_IS_FLAGS + 1; k < RK_IS_WORDS; k++) *soa(state, n, i, k) = 0;
+    }
+  }
+}

@@ -26,6 +26,10 @@ void orc_vdt_rx(const rk_vdt_params_t *p, uint32_t *words, int wheel, const uint
 /* VEHICLE_CTRL::update on one AoS state */
 void orc_vdt_update(const rk_vdt_params_t *p, uint32_t *words);
 
+/* Same contract as rk_imt_update() on HOST arrays, instances [i0, i1). */
+void orc_imt_update(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, const int16_t *regs,
+                    const uint8_t *have_quat, uint32_t *out, int do_init);
+
 float orc_sin(float x);
 float orc_cos(float x);
 float orc_normalize_rad_0to2pi(float x);

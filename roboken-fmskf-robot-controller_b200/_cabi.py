@@ -94,6 +94,19 @@ def _proto(lib):
     lib.rk_vdt_set_power.argtypes = [vp, C.c_int64, vp, vp]
     lib.rk_vdt_set_target_vel.argtypes = [C.POINTER(VdtParams), vp, C.c_int64, vp, vp, vp, vp]
     lib.rk_vdt_motor_rx.argtypes = [C.POINTER(VdtParams), vp, C.c_int64, C.c_int, vp, vp, vp]
+    lib.rk_imt_state_words.restype = C.c_size_t
+    lib.rk_imt_state_bytes.argtypes = [C.c_int64]
+    lib.rk_imt_state_bytes.restype = C.c_size_t
+    lib.rk_imt_update.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, C.c_int, vp]
+    lib.rk_imt_create.argtypes = [C.POINTER(vp)]
+    lib.rk_imt_destroy.argtypes = [vp]
+    lib.rk_imt_destroy.restype = None
+    lib.rk_imt_init.argtypes = [vp, C.POINTER(C.c_int16)]
+    lib.rk_imt_update1.argtypes = [vp, C.POINTER(C.c_int16), C.c_int]
+    lib.rk_imt_get.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    lib.rk_imt_get_yaw.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.rk_imt_get_state.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.rk_imt_set_state.argtypes = [vp, C.POINTER(C.c_uint32)]
     lib.rk_vdt_create.argtypes = [C.POINTER(vp), C.POINTER(VdtParams)]
     lib.rk_vdt_destroy.argtypes = [vp]
     lib.rk_vdt_destroy.restype = None

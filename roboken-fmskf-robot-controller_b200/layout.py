@@ -27,6 +27,14 @@ VM_ANG_RPM, VM_CUR_TGT, VM_USEC, VM_PLANT = 4, 5, 6, 7
 
 assert VS_WORDS == 112
 
+# ---- IMU (RK_IS_*) ---------------------------------------------------------------------
+IS_QINIT, IS_DATA, IS_FLAGS, IS_WORDS = 0, 4, 20, 24
+IS_D_ACCEL, IS_D_GYRO, IS_D_MAG, IS_D_ANGLE, IS_D_QUT = 0, 3, 6, 9, 12
+IS_FLAG_ERROR = 1
+IMT_REGS = 16
+(REG_AX, REG_AY, REG_AZ, REG_GX, REG_GY, REG_GZ, REG_HX, REG_HY, REG_HZ, REG_ROLL, REG_PITCH, REG_YAW,
+ REG_Q0, REG_Q1, REG_Q2, REG_Q3) = range(16)
+
 
 def soa_to_aos(block, n, words):
     """[planes, n, 4] SoA block (any uint32 array of words*n elements) -> [n, words]."""

@@ -98,3 +98,21 @@ def vehicle_frames(n, steps, seed=0x5EED, first=0):
     b[..., 4] = (cur >> 8) & 255
     b[..., 5] = cur & 255
     return b.view(np.uint64).reshape(steps, 4, n)
+
+
+def imu_samples(n, n_upd, seed=0x5EED, first=0, drop_every=64):
+    """C3 stream: WT901 register snapshots, int16 [n_upd, 16, n] (+ have_quat uint8 [n_upd, n]).
+
+    AX..Yaw ~ U{-32768..32767}; q0..q3 a random unit quaternion x 32767 rounded; one update in
+    `drop_every` carries no quaternion frame (error / hold path, imu_if_wt901c.cpp:83-89)."""
+    inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[None, None, :]
+    u = np.arange(n_upd, dtype=np.uint64)[:, None, None]
+    r = np.arange(16, dtype=np.uint64)[None, :, None]
+    h = _hash(seed, 20, inst * np.uint64(16) + r, u)
+    regs = ((h >> np.uint64(13)) & np.uint64(0xFFFF)).astype(np.uint16).view(np.int16).copy()
+    g = _u01(_hash(seed, 21, inst * np.uint64(16) + r, u))[:, 12:16, :].astype(np.float64) * 2.0 - 1.0
+    nrm = np.sqrt((g * g).sum(axis=1, keepdims=True))
+    nrm[nrm == 0] = 1.0
+    regs[:, 12:16, :] = np.rint(g / nrm * 32767.0).astype(np.int16)
+    have = (_hash(seed, 22, inst[:, 0, :], u[:, 0, :]) % np.uint64(drop_every) != 0).astype(np.uint8)
+    return np.ascontiguousarray(regs), np.ascontiguousarray(have)

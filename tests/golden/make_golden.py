@@ -58,6 +58,14 @@ def main():
     path = os.path.join(HERE, "vdt_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
+    # IMU: compiled reference driven through WT901 serial frames
+    n, K = 64, 32
+    regs, have = streams.imu_samples(n, K, seed=0x5EED, drop_every=8)
+    st = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
+    o = ol.imu_ref(st, n, regs, have, want_out=True, do_init=True)
+    path = os.path.join(HERE, "imu_golden.npz")
+    np.savez_compressed(path, out=o, state=st)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

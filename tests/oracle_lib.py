@@ -38,6 +38,8 @@ def port():
         lib.orc_vdt_set_target.argtypes = [C.POINTER(_cabi.VdtParams), vp, f3, f3, f3]
         lib.orc_vdt_rx.argtypes = [C.POINTER(_cabi.VdtParams), vp, C.c_int, C.c_char_p, C.c_int16]
         lib.orc_vdt_update.argtypes = [C.POINTER(_cabi.VdtParams), vp]
+        lib.orc_imt_update.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int]
+        lib.orc_imt_update.restype = None
         for nm in ("orc_sin", "orc_cos", "orc_normalize_rad_0to2pi", "orc_normalize_deg_0to360"):
             getattr(lib, nm).argtypes = [C.c_float]
             getattr(lib, nm).restype = C.c_float
@@ -77,6 +79,20 @@ def ref(name="libref_vdt.so"):
                 getattr(lib, nm).restype = C.c_float
             lib.ref_atan2f.argtypes = [C.c_float, C.c_float]
             lib.ref_atan2f.restype = C.c_float
+        if name.startswith("libref_imu"):
+            lib.ref_imt_create.restype = vp
+            lib.ref_imt_destroy.argtypes = [vp]
+            R = C.POINTER(C.c_int16)
+            lib.ref_imt_init.argtypes = [vp, R]
+            lib.ref_imt_update.argtypes = [vp, R, C.c_int]
+            lib.ref_imt_yaw.argtypes = [vp]
+            lib.ref_imt_yaw.restype = C.c_float
+            lib.ref_imt_is_error.argtypes = [vp]
+            lib.ref_imt_get.argtypes = [vp, C.POINTER(C.c_float)]
+            lib.ref_imt_export.argtypes = [vp, vp]
+            lib.ref_imt_import.argtypes = [vp, vp]
+            lib.ref_imt_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int]
+            lib.ref_imt_rollout.restype = None
         _cache[name] = lib
     return _cache[name]
 
@@ -111,3 +127,17 @@ def run_port(state_soa, n, ro, params=None, nthreads=1):
 
 def run_ref(state_soa, n, ro, nthreads=1, name="libref_vdt.so"):
     ref(name).ref_vdt_rollout(_ptr(state_soa), n, 0, n, C.byref(ro.args), nthreads)
+
+
+def imu_port(state_soa, n, regs, have=None, want_out=False, do_init=False):
+    K = regs.shape[0]
+    out = np.zeros((K, 4, n, 4), dtype=np.uint32) if want_out else None
+    port().orc_imt_update(_ptr(state_soa), n, 0, n, K, _ptr(regs), _ptr(have), _ptr(out), int(do_init))
+    return out
+
+
+def imu_ref(state_soa, n, regs, have=None, want_out=False, do_init=False):
+    K = regs.shape[0]
+    out = np.zeros((K, 4, n, 4), dtype=np.uint32) if want_out else None
+    ref("libref_imu.so").ref_imt_rollout(_ptr(state_soa), n, 0, n, K, _ptr(regs), _ptr(have), _ptr(out), int(do_init))
+    return out
