@@ -255,6 +255,113 @@ int   rk_imt_get_yaw(rk_imt_t *h, float *yaw_deg);            /* ::getYawDate() 
 int   rk_imt_get_state(rk_imt_t *h, uint32_t words[RK_IS_WORDS]);
 int   rk_imt_set_state(rk_imt_t *h, const uint32_t words[RK_IS_WORDS]);
 
+/* =====================================================================================
+ * Arm (src/ArmDrive): 5-axis joint-command interpolation, ADTModePositioningSeq + the joint
+ * classes it drives, one 100 Hz tick = ADT::main's loop body (AD_task_main.cpp:208-229):
+ *   m_posseq.update(); j_P1.update(); j_DF_Left.update(); j_DF_Right.update(); j_P3.update();
+ *   [CAN tx]; j_Y0.update();
+ * Joint objects in this order everywhere: Y0 (ICS), P1 (MG), DF_Left, DF_Right (MyBldc),
+ * P2 (DfGearPitch), R0 (DfGearRoll), P3 (MyBldc); mode axes J0..J4 = Y0, P1, P2, R0, P3.
+ * ===================================================================================== */
+enum { RK_AJ_Y0 = 0, RK_AJ_P1, RK_AJ_DFL, RK_AJ_DFR, RK_AJ_P2, RK_AJ_R0, RK_AJ_P3, RK_AJ_NUM };
+
+/* JointBase::ConstParams of the seven joints (AD_task_main.cpp:38-107) + the mode cycle time */
+typedef struct rk_adt_params {
+  float ctrl_time_s[RK_AJ_NUM];  /* fl_ctrl_time_s  0.01f                       */
+  float gear_ratio[RK_AJ_NUM];   /* fl_gear_ratio   1,1,1,1,24/7,48/7,48/19      */
+  float motor_dir[RK_AJ_NUM];    /* fl_motor_dir    -1,1,1,1,1,1,-1              */
+  float curlim_default_A[RK_AJ_NUM];
+  float cycle_time_s;            /* ADTModeBase::FL_CYCLE_TIME_S 0.01f  AD_task_main.cpp:149 */
+} rk_adt_params_t;
+void rk_adt_default_params(rk_adt_params_t *p);
+
+/* arm state words (19 planes = 76 words = 304 B / arm) */
+enum {
+  /* ADTModePositioningSeq  AD_mode_positioning_seq.hpp:55-70 */
+  RK_AS_FSM = 0,        /* nowState | isModeFirstCall << 8 | is_comp << 9 */
+  RK_AS_SEQ_IDX,        /* u16_seq_exec_idx_ | u16_seq_write_head_ << 16 */
+  RK_AS_CMD_IDX,        /* u8_nowcmd_idx_ */
+  RK_AS_MOVE_CNT,       /* s32_move_cnt_ */
+  RK_AS_CYCLE,          /* s32_cycle_counter_ */
+  RK_AS_TOTAL_MS,       /* u32_total_move_ms_ */
+  RK_AS_NOW_DT,         /* now_cmd_.u32_dt_ms */
+  RK_AS_RSV0,
+  RK_AS_NOW_TGT = 8,    /* now_cmd_.fl_tgt_pos_deg[5] */
+  RK_AS_MOVE_DEG = 13,  /* fl_move_deg_[5] */
+  RK_AS_DFV_P = 18,     /* JointDfGearVirtual::fl_rawP_tgt_deg_  AD_joint_dfgear.hpp:35 */
+  RK_AS_DFV_R,          /* ::fl_rawR_tgt_deg_ */
+  /* 7 x JointBase {fl_out_ofs_deg, fl_raw_tgt_deg, fl_curlim_A, fl_raw_now_deg}  AD_joint_base.hpp:62-74 */
+  RK_AS_JOINT0 = 20,
+  RK_AS_JFLAGS = 48,    /* 4 bits per joint: connected | torque_on << 1 | initialized << 2 | torque_on_prev << 3 */
+  RK_AS_MG_PRE_TGT,     /* JointMgServo::fl_pre_raw_tgt_deg */
+  RK_AS_ICS_POS,        /* last position word handed to IcsBaseClass::setPos (-1: none) */
+  RK_AS_ICS_SERVO,      /* ideal-servo model of the stubbed UART: position the servo reports */
+  /* last transmitted servo commands */
+  RK_AS_MG_TX = 52,     /* tx1data[8] (2 words), word 2 = bytes valid, word 3 rsv     AD_joint_mg_servo.hpp:93 */
+  RK_AS_BLDC_TX0 = 56,  /* 3 x {txmsg[8] (2 words), u32_txcmdid, valid}: DF_Left, DF_Right, P3 */
+  RK_AS_MG_CTRL = 68,   /* JointMgServo::pos_ctrl_ (PI_D) -- torque-control branch (AD_joint_mg_servo.cpp:104-134,
+                         * joint not initialised or torque off): reserved, carried through unchanged; in that
+                         * branch no MG frame is produced (RK_AS_MG_TX + 2 == 0) */
+  RK_AS_WORDS = 76
+};
+enum { RK_AJ_OFS = 0, RK_AJ_RAW_TGT, RK_AJ_CURLIM, RK_AJ_RAW_NOW };
+enum { RK_ASTATE_STANDBY = 0, RK_ASTATE_MOVE_START, RK_ASTATE_MOVING, RK_ASTATE_COMPLETED };
+#define RK_AS_FSM_FIRSTCALL 0x100u
+#define RK_AS_FSM_IS_COMP 0x200u
+#define RK_AJF_CONNECTED 1u
+#define RK_AJF_TORQUE_ON 2u
+#define RK_AJF_INITIALIZED 4u
+#define RK_AJF_TORQUE_PREV 8u
+
+/* Command-sequence ring, CMD_SEQ_BUF_LEN = 4 slots of PosCmdSeq per arm
+ * (AD_mode_positioning_seq.hpp:11,15-24,59), in its own block so the 100 Hz state stays small:
+ * slot s = 260 words = 65 planes: word 0 u32_id, word 1 u8_cmd_seq_len, words 2-3 zero, then
+ * 32 waypoints of 8 words {u32_dt_ms, fl_tgt_pos_deg[5], 0, 0}.  Same plane indexing. */
+#define RK_ACMD_SLOTS 4
+#define RK_ACMD_MAX_LEN 32
+#define RK_ACMD_SLOT_WORDS 260
+#define RK_ACMD_WORDS (RK_ACMD_SLOTS * RK_ACMD_SLOT_WORDS)
+typedef struct rk_adt_poscmd { uint32_t dt_ms; float tgt_deg[5]; } rk_adt_poscmd_t;
+typedef struct rk_adt_poscmdseq { uint32_t id; uint8_t len; rk_adt_poscmd_t cmd[RK_ACMD_MAX_LEN]; } rk_adt_poscmdseq_t;
+
+size_t rk_adt_state_words(void);
+size_t rk_adt_state_bytes(int64_t n);
+size_t rk_adt_cmdtab_bytes(int64_t n);
+
+/* ADTModeBase::init() -> ADTModePositioningSeq::doInit()  (AD_mode_base.hpp:19-22,
+ * AD_mode_positioning_seq.cpp:5-11) for every arm, and the joint flags/limits a finished
+ * INIT mode leaves behind: connected, torque on, initialized, curlim = default
+ * (AD_mode_initialize.cpp:133-135).  Offsets / targets are left as they are. */
+int rk_adt_mode_init(const rk_adt_params_t *p, void *d_state, int64_t n, void *stream);
+/* ADTModePositioningSeq::push_cmdseq (AD_mode_positioning_seq.cpp:124-137): one sequence per
+ * arm from d_seq = n blocks of RK_ACMD_SLOT_WORDS words in plane order (pitch n); d_valid
+ * (uint8[n] or NULL) selects the arms that push.  A full ring drops the push silently. */
+int rk_adt_push_cmdseq(void *d_state, void *d_cmdtab, int64_t n, const void *d_seq, const uint8_t *d_valid, void *stream);
+/* K fused arm ticks.  d_trace (optional): per tick 16 words, word j of tick t, arm i at
+ * (t*16 + j)*n + i: 0-4 get_tgt_deg() of J0..J4; 5 MG u16_vel_lim; 6 MG s32_ang; 7-9 MyBldc
+ * s32_tgt_ang_deg_Q16 of DF_Left, DF_Right, P3; 10 ICS position word; 11 nowState;
+ * 12 u8_nowcmd_idx_; 13 MyBldc txcmdids packed (8 bits each, low byte of the id | 0x80 when
+ * the id is >= 0x8000); 14-15 zero. */
+#define RK_ADT_TRACE_WORDS 16
+int rk_adt_update(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab, int64_t n, int32_t K,
+                  uint32_t *d_trace, void *stream);
+/* ADTModePositioningSeq::get_q_cmdseq_status (AD_mode_positioning_seq.cpp:146-184):
+ * d_status[i] in {0 PROCESSING, 1 DONE, 99 NO_DATA} for command id d_id[i]. */
+int rk_adt_cmdseq_status(const void *d_state, const void *d_cmdtab, int64_t n, const uint32_t *d_id,
+                         int32_t *d_status, void *stream);
+
+/* single-instance handle (drop-in for the statics of AD_task_main.cpp:108-156) */
+typedef struct rk_adt rk_adt_t;
+int  rk_adt_create(rk_adt_t **out, const rk_adt_params_t *p /* NULL = defaults */);
+void rk_adt_destroy(rk_adt_t *h);
+int  rk_adt_init(rk_adt_t *h);                                    /* mode init, see rk_adt_mode_init */
+int  rk_adt_push(rk_adt_t *h, const rk_adt_poscmdseq_t *seq);     /* push_cmdseq                     */
+int  rk_adt_tick(rk_adt_t *h);                                    /* one ADT::main loop body         */
+int  rk_adt_status(rk_adt_t *h, uint32_t id, int32_t *status);    /* get_q_cmdseq_status             */
+int  rk_adt_get_targets_deg(rk_adt_t *h, float out[5]);           /* JointBase::get_tgt_deg x5       */
+int  rk_adt_get_state(rk_adt_t *h, uint32_t words[RK_AS_WORDS]);
+int  rk_adt_set_state(rk_adt_t *h, const uint32_t words[RK_AS_WORDS]);
+
 #ifdef __cplusplus
 }
 #endif

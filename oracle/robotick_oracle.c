@@ -536,3 +536,273 @@ void orc_imt_update(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, c
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* Arm: ADTModePositioningSeq + joint command packers (src/ArmDrive), on AoS state words   */
+/* (int32_t)(float) as the x86 build performs it: cvttss2si, out of range / NaN -> INT_MIN   */
+static int32_t f2i_x86(float f) {
+  if(!(fabsf(f) < 2147483648.0f)) return (int32_t)0x80000000u;
+  return (int32_t)f;
+}
+/* IcsBaseClass::degPos100 / posDeg100   lib/IcsClass_V210/src/IcsBaseClass.cpp:105-137 */
+static int ics_degPos100(int deg) {
+  long long a;
+  if(deg > 18000 || deg < -18000) return -1;
+  a = ((long long)deg * 2963) / 10000;
+  return (int)a + 7500;
+}
+static int ics_posDeg100(int pos) {
+  long long a   = (long long)pos - 7500;
+  int       deg = (int)((a * 1000) / 296);
+  if(deg > 18000) return 0x7FFF;
+  if(deg < -18000) return -0x7FFF;
+  return deg;
+}
+#define AJ(w, k, f) ((w)[RK_AS_JOINT0 + 4 * (k) + (f)])
+static float adt_get_tgt_deg(const uint32_t *w, int k) { /* JointBase::get_tgt_deg  AD_joint_base.hpp:47 */
+  return u2f(AJ(w, k, RK_AJ_RAW_TGT)) - u2f(AJ(w, k, RK_AJ_OFS));
+}
+static const int ADT_AXIS[5] = {RK_AJ_Y0, RK_AJ_P1, RK_AJ_P2, RK_AJ_R0, RK_AJ_P3}; /* AD_task_main.cpp:148 */
+
+/* JointBase::set_tgt_ang_deg (:42) and the DfGear overrides (AD_joint_dfgear.hpp:14-37,60-63,93-96) */
+static void adt_set_tgt(const rk_adt_params_t *p, uint32_t *w, int axis, float tgt) {
+  int   k   = ADT_AXIS[axis];
+  float raw = tgt + u2f(AJ(w, k, RK_AJ_OFS));
+  AJ(w, k, RK_AJ_RAW_TGT) = f2u(raw);
+  if(k == RK_AJ_P2 || k == RK_AJ_R0) {
+    float P, R;
+    if(k == RK_AJ_P2) w[RK_AS_DFV_P] = f2u(raw * p->gear_ratio[k]);
+    else w[RK_AS_DFV_R] = f2u(raw * p->gear_ratio[k]);
+    P = u2f(w[RK_AS_DFV_P]), R = u2f(w[RK_AS_DFV_R]);
+    AJ(w, RK_AJ_DFL, RK_AJ_RAW_TGT) = f2u((P - R) + u2f(AJ(w, RK_AJ_DFL, RK_AJ_OFS)));
+    AJ(w, RK_AJ_DFR, RK_AJ_RAW_TGT) = f2u(-(P + R) + u2f(AJ(w, RK_AJ_DFR, RK_AJ_OFS)));
+  }
+}
+
+/* ADTModePositioningSeq::update   AD_mode_positioning_seq.cpp:13-117 */
+static void adt_mode_update(const rk_adt_params_t *p, uint32_t *w, const uint32_t *tab, int64_t n, int64_t i) {
+  uint32_t fsm   = w[RK_AS_FSM];
+  uint32_t state = fsm & 0xFFu;
+  uint32_t exec = w[RK_AS_SEQ_IDX] & 0xFFFFu, head = w[RK_AS_SEQ_IDX] >> 16;
+  int      j;
+  if(state == RK_ASTATE_STANDBY) { /* exec_standby :24-42 */
+    fsm |= RK_AS_FSM_IS_COMP;
+    if(exec != head) {
+      exec = (exec + 1) & 0xFFFFu;
+      exec = (exec >= RK_ACMD_SLOTS) ? 0 : exec;
+      w[RK_AS_CMD_IDX]  = 0;
+      w[RK_AS_TOTAL_MS] = 0;
+      state             = RK_ASTATE_MOVE_START;
+      fsm &= ~RK_AS_FSM_FIRSTCALL;
+    }
+  }
+  if(state == RK_ASTATE_MOVE_START) { /* exec_move_start :48-83 */
+    /* cmd_seq_[exec] with exec > 3 is out of bounds in the reference; slots wrap here */
+    int      base = (int)(exec % RK_ACMD_SLOTS) * RK_ACMD_SLOT_WORDS;
+    uint32_t len  = *soa((uint32_t *)tab, n, i, base + 1) & 0xFFu;
+    uint32_t idx  = w[RK_AS_CMD_IDX] & 0xFFu;
+    if(idx >= len) {
+      state = RK_ASTATE_STANDBY;
+    } else {
+      int32_t cnt;
+      float   fc;
+      int     wb = base + 4 + 8 * (int)(idx % RK_ACMD_MAX_LEN);
+      w[RK_AS_NOW_DT] = *soa((uint32_t *)tab, n, i, wb);
+      for(j = 0; j < 5; j++) w[RK_AS_NOW_TGT + j] = *soa((uint32_t *)tab, n, i, wb + 1 + j);
+      cnt = f2i_x86((float)(uint32_t)(w[RK_AS_NOW_DT] - w[RK_AS_TOTAL_MS]) * 0.001f / p->cycle_time_s);
+      cnt = (cnt <= 0) ? 1 : cnt;
+      fc  = (float)cnt;
+      for(j = 0; j < 5; j++) w[RK_AS_MOVE_DEG + j] = f2u((u2f(w[RK_AS_NOW_TGT + j]) - adt_get_tgt_deg(w, ADT_AXIS[j])) / fc);
+      w[RK_AS_MOVE_CNT] = (uint32_t)cnt;
+      w[RK_AS_TOTAL_MS] = w[RK_AS_NOW_DT];
+      w[RK_AS_CYCLE]    = 0;
+      fsm &= ~RK_AS_FSM_IS_COMP;
+      state = RK_ASTATE_MOVING;
+    }
+  }
+  if(state == RK_ASTATE_MOVING) { /* exec_moving :89-117 */
+    int32_t cnt = (int32_t)w[RK_AS_MOVE_CNT], cyc = (int32_t)w[RK_AS_CYCLE];
+    float   rem = (float)(cnt - cyc);
+    for(j = 0; j < 5; j++) adt_set_tgt(p, w, j, u2f(w[RK_AS_NOW_TGT + j]) - u2f(w[RK_AS_MOVE_DEG + j]) * rem);
+    if(cnt <= cyc) {
+      w[RK_AS_CMD_IDX] = (w[RK_AS_CMD_IDX] + 1) & 0xFFu;
+      state            = RK_ASTATE_MOVE_START;
+    } else {
+      w[RK_AS_CYCLE] = (uint32_t)(cyc + 1);
+    }
+  }
+  w[RK_AS_FSM]     = (fsm & ~0xFFu) | state;
+  w[RK_AS_SEQ_IDX] = exec | (head << 16);
+}
+
+static uint32_t jflag(const uint32_t *w, int k) { return (w[RK_AS_JFLAGS] >> (4 * k)) & 0xFu; }
+static void     set_jflag(uint32_t *w, int k, uint32_t b) { w[RK_AS_JFLAGS] = (w[RK_AS_JFLAGS] & ~(0xFu << (4 * k))) | (b << (4 * k)); }
+
+/* JointMgServo::update -> subproc_posctrl   AD_joint_mg_servo.cpp:50-73,136-149.
+ * The torque-control branches (not initialised / torque off; :104-134) are SURVEY 8(f)4 "next":
+ * no MG frame is produced there (valid = 0), exactly what the C-ABI documents. */
+static void adt_mg_update(const rk_adt_params_t *p, uint32_t *w) {
+  uint32_t b    = jflag(w, RK_AJ_P1);
+  int      on   = (b & RK_AJF_TORQUE_ON) != 0, prev = (b & RK_AJF_TORQUE_PREV) != 0, ini = (b & RK_AJF_INITIALIZED) != 0;
+  float    tgt  = u2f(AJ(w, RK_AJ_P1, RK_AJ_RAW_TGT));
+  w[RK_AS_MG_TX + 2] = 0;
+  if(prev && !on) {
+    /* pos_ctrl_.reset() */
+  } else if(!ini && on) {
+    /* subproc_torquectrl: reserved */
+  } else if(on) {
+    float    v   = fabsf((tgt - u2f(w[RK_AS_MG_PRE_TGT])) / p->ctrl_time_s[RK_AJ_P1] * -10.0f);
+    uint32_t vl  = (uint32_t)f2i_x86((v > 1800) ? 1800 : v) & 0xFFFFu;
+    int32_t  ang = f2i_x86(tgt * (-100.0f * 10.0f));
+    w[RK_AS_MG_TX]     = 0xA4u | (vl << 16);
+    w[RK_AS_MG_TX + 1] = (uint32_t)ang;
+    w[RK_AS_MG_TX + 2] = 1;
+  }
+  set_jflag(w, RK_AJ_P1, (b & ~RK_AJF_TORQUE_PREV) | (on ? RK_AJF_TORQUE_PREV : 0u));
+  w[RK_AS_MG_PRE_TGT] = f2u(tgt);
+}
+
+/* JointMyBldcServo::update   AD_joint_mybldc_servo.cpp:7-36 ; slot 0..2 = DF_Left, DF_Right, P3 */
+static void adt_bldc_update(const rk_adt_params_t *p, uint32_t *w, int slot) {
+  static const int JK[3] = {RK_AJ_DFL, RK_AJ_DFR, RK_AJ_P3};
+  int       k  = JK[slot];
+  uint32_t  b  = jflag(w, k);
+  int       on = (b & RK_AJF_TORQUE_ON) != 0, prev = (b & RK_AJF_TORQUE_PREV) != 0;
+  uint32_t *q  = w + RK_AS_BLDC_TX0 + 4 * slot;
+  if(!on) {
+    q[0] = 0, q[1] = 0, q[2] = 0x8002u;
+  } else if(!prev) {
+    q[0] = 0, q[1] = 0, q[2] = 0x8001u;
+  } else {
+    int32_t  a  = f2i_x86(u2f(AJ(w, k, RK_AJ_RAW_TGT)) * p->gear_ratio[k] * p->motor_dir[k] * 65536.0f);
+    uint32_t ms = (uint32_t)f2i_x86(p->ctrl_time_s[k] * 1000.0f) & 0xFFFFu;
+    uint32_t cl = (uint32_t)f2i_x86(u2f(AJ(w, k, RK_AJ_CURLIM)) * 256.0f) & 0xFFFFu;
+    q[0] = (uint32_t)a, q[1] = ms | (cl << 16), q[2] = 0x8010u;
+  }
+  q[3] = 1;
+  set_jflag(w, k, (b & ~RK_AJF_TORQUE_PREV) | (on ? RK_AJF_TORQUE_PREV : 0u));
+}
+
+/* JointIcsServo::update   AD_joint_ics_servo.cpp:5-29 over the ideal servo of
+ * oracle/stubs/IcsHardSerialClass.h (echoes the commanded position) */
+static void adt_ics_update(const rk_adt_params_t *p, uint32_t *w) {
+  uint32_t b = jflag(w, RK_AJ_Y0);
+  int      tgt_pos, now_pos;
+  if(!(b & RK_AJF_CONNECTED)) return;
+  tgt_pos = ics_degPos100(f2i_x86(u2f(AJ(w, RK_AJ_Y0, RK_AJ_RAW_TGT)) * p->motor_dir[RK_AJ_Y0] * 100.0f));
+  if(tgt_pos == -1) return;
+  if(b & RK_AJF_TORQUE_ON) {
+    if(tgt_pos > 11500 || tgt_pos < 3500) { /* IcsBaseClass::setPos range check: nothing transmitted */
+      now_pos = -1;
+    } else {
+      w[RK_AS_ICS_POS]   = (uint32_t)tgt_pos;
+      w[RK_AS_ICS_SERVO] = (uint32_t)(tgt_pos - 7500);
+      now_pos            = tgt_pos;
+    }
+  } else { /* setFree: {0x80 + id, 0, 0} */
+    w[RK_AS_ICS_POS] = (uint32_t)-1;
+    now_pos          = (int)(int32_t)w[RK_AS_ICS_SERVO] + 7500;
+  }
+  AJ(w, RK_AJ_Y0, RK_AJ_RAW_NOW) = f2u((float)ics_posDeg100(now_pos) * 0.01f * p->motor_dir[RK_AJ_Y0]);
+}
+
+/* one ADT::main loop body   AD_task_main.cpp:208-229 */
+static void adt_tick(const rk_adt_params_t *p, uint32_t *w, const uint32_t *tab, int64_t n, int64_t i) {
+  adt_mode_update(p, w, tab, n, i);
+  adt_mg_update(p, w);
+  adt_bldc_update(p, w, 0);
+  adt_bldc_update(p, w, 1);
+  adt_bldc_update(p, w, 2);
+  adt_ics_update(p, w);
+}
+
+/* prepare_task + finished INIT mode + ADTModeBase::init (see oracle/ref_harness_arm.cpp bringup()) */
+static void adt_bringup(const rk_adt_params_t *p, uint32_t *w) {
+  float now = (float)ics_posDeg100((int)(int32_t)w[RK_AS_ICS_SERVO] + 7500) * 0.01f * p->motor_dir[RK_AJ_Y0];
+  AJ(w, RK_AJ_Y0, RK_AJ_RAW_NOW) = f2u(now);
+  AJ(w, RK_AJ_Y0, RK_AJ_RAW_TGT) = f2u(now);
+  w[RK_AS_ICS_POS]               = (uint32_t)-1;
+  set_jflag(w, RK_AJ_Y0, RK_AJF_CONNECTED | RK_AJF_TORQUE_ON | RK_AJF_INITIALIZED);
+  set_jflag(w, RK_AJ_P1, RK_AJF_CONNECTED | RK_AJF_TORQUE_ON | RK_AJF_INITIALIZED);
+  set_jflag(w, RK_AJ_DFL, jflag(w, RK_AJ_DFL) | RK_AJF_TORQUE_ON);
+  set_jflag(w, RK_AJ_DFR, jflag(w, RK_AJ_DFR) | RK_AJF_TORQUE_ON);
+  set_jflag(w, RK_AJ_P2, jflag(w, RK_AJ_P2) | RK_AJF_INITIALIZED);
+  set_jflag(w, RK_AJ_R0, jflag(w, RK_AJ_R0) | RK_AJF_INITIALIZED);
+  set_jflag(w, RK_AJ_P3, jflag(w, RK_AJ_P3) | RK_AJF_TORQUE_ON | RK_AJF_INITIALIZED);
+  AJ(w, RK_AJ_Y0, RK_AJ_CURLIM)  = f2u(p->curlim_default_A[RK_AJ_Y0]);
+  AJ(w, RK_AJ_P1, RK_AJ_CURLIM)  = f2u(p->curlim_default_A[RK_AJ_P1]);
+  AJ(w, RK_AJ_DFL, RK_AJ_CURLIM) = f2u(p->curlim_default_A[RK_AJ_R0]);
+  AJ(w, RK_AJ_DFR, RK_AJ_CURLIM) = f2u(p->curlim_default_A[RK_AJ_R0]);
+  AJ(w, RK_AJ_P3, RK_AJ_CURLIM)  = f2u(p->curlim_default_A[RK_AJ_P3]);
+  w[RK_AS_FSM]     = RK_ASTATE_STANDBY | RK_AS_FSM_FIRSTCALL;
+  w[RK_AS_SEQ_IDX] = (RK_ACMD_SLOTS - 1) | ((uint32_t)(RK_ACMD_SLOTS - 1) << 16);
+}
+
+/* ADTModePositioningSeq::push_cmdseq   AD_mode_positioning_seq.cpp:124-137 */
+static void adt_push(uint32_t *w, uint32_t *tab, int64_t n, int64_t i, const uint32_t *seq) {
+  uint32_t exec = w[RK_AS_SEQ_IDX] & 0xFFFFu, head = w[RK_AS_SEQ_IDX] >> 16;
+  uint32_t nw   = (head + 1) & 0xFFFFu;
+  int      k;
+  nw = (nw >= RK_ACMD_SLOTS) ? 0 : nw;
+  if(nw == exec) return;
+  for(k = 0; k < RK_ACMD_SLOT_WORDS; k++) *soa(tab, n, i, (int)nw * RK_ACMD_SLOT_WORDS + k) = *soa((uint32_t *)seq, n, i, k);
+  *soa(tab, n, i, (int)nw * RK_ACMD_SLOT_WORDS + 1) &= 0xFFu;
+  w[RK_AS_SEQ_IDX] = exec | (nw << 16);
+}
+
+/* ADTModePositioningSeq::get_q_cmdseq_status   AD_mode_positioning_seq.cpp:146-184 */
+static int32_t adt_status(const uint32_t *w, const uint32_t *tab, int64_t n, int64_t i, uint32_t id) {
+  uint32_t exec = w[RK_AS_SEQ_IDX] & 0xFFFFu, head = w[RK_AS_SEQ_IDX] >> 16;
+  int32_t  sts  = 99;
+  uint32_t s;
+  if((w[RK_AS_FSM] & RK_AS_FSM_FIRSTCALL) && id == 0) return 99;
+  for(s = 0; s < RK_ACMD_SLOTS; s++) {
+    if(*soa((uint32_t *)tab, n, i, (int)s * RK_ACMD_SLOT_WORDS) != id) continue;
+    if(exec == head) {
+      uint32_t len = *soa((uint32_t *)tab, n, i, (int)(exec % RK_ACMD_SLOTS) * RK_ACMD_SLOT_WORDS + 1) & 0xFFu;
+      sts          = ((w[RK_AS_CMD_IDX] & 0xFFu) >= len) ? 1 : 0;
+    } else if(exec < head) {
+      sts = (exec <= s && s <= head) ? 0 : 1;
+    } else {
+      sts = ((exec <= s && s < RK_ACMD_SLOTS) || s <= head) ? 0 : 1;
+    }
+  }
+  return sts;
+}
+
+static uint32_t bldc_id_byte(uint32_t id) { return (id & 0xFFu) | ((id & 0x8000u) ? 0x80u : 0u); }
+
+void orc_adt_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *cmdtab, int64_t n, int64_t i0, int64_t i1,
+                   int K, const uint32_t *seq, const uint8_t *valid, uint32_t *trace, const uint32_t *ids, int32_t *status) {
+  int64_t i;
+  int     k, t, j;
+  for(i = i0; i < i1; i++) {
+    uint32_t w[RK_AS_WORDS];
+    for(k = 0; k < RK_AS_WORDS; k++) w[k] = *soa(state, n, i, k);
+    if(op == 0) {
+      adt_bringup(p, w);
+    } else if(op == 1) {
+      if(!valid || valid[i]) adt_push(w, cmdtab, n, i, seq);
+    } else if(op == 2) {
+      for(t = 0; t < K; t++) {
+        adt_tick(p, w, cmdtab, n, i);
+        if(trace) {
+          uint32_t *tr = trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i;
+          for(j = 0; j < 5; j++) tr[(int64_t)j * n] = f2u(adt_get_tgt_deg(w, ADT_AXIS[j]));
+          tr[5 * n] = w[RK_AS_MG_TX] >> 16, tr[6 * n] = w[RK_AS_MG_TX + 1];
+          for(j = 0; j < 3; j++) tr[(int64_t)(7 + j) * n] = w[RK_AS_BLDC_TX0 + 4 * j];
+          tr[10 * n] = w[RK_AS_ICS_POS];
+          tr[11 * n] = w[RK_AS_FSM] & 0xFFu;
+          tr[12 * n] = w[RK_AS_CMD_IDX];
+          tr[13 * n] = bldc_id_byte(w[RK_AS_BLDC_TX0 + 2]) | (bldc_id_byte(w[RK_AS_BLDC_TX0 + 6]) << 8) |
+                       (bldc_id_byte(w[RK_AS_BLDC_TX0 + 10]) << 16);
+          tr[14 * n] = 0, tr[15 * n] = 0;
+        }
+      }
+    } else if(op == 3) {
+      status[i] = adt_status(w, cmdtab, n, i, ids[i]);
+    }
+    if(op != 3)
+      for(k = 0; k < RK_AS_WORDS; k++) *soa(state, n, i, k) = w[k];
+  }
+}

@@ -30,6 +30,12 @@ void orc_vdt_update(const rk_vdt_params_t *p, uint32_t *words);
 void orc_imt_update(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, const int16_t *regs,
                     const uint8_t *have_quat, uint32_t *out, int do_init);
 
+/* Arm batch driver on HOST arrays, same contracts as the rk_adt_* batch calls (see
+ * oracle/ref_harness_arm.cpp ref_adt_batch): op 0 = rk_adt_mode_init, 1 = rk_adt_push_cmdseq,
+ * 2 = rk_adt_update (K ticks, optional trace), 3 = rk_adt_cmdseq_status. */
+void orc_adt_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *cmdtab, int64_t n, int64_t i0, int64_t i1,
+                   int K, const uint32_t *seq, const uint8_t *valid, uint32_t *trace, const uint32_t *ids, int32_t *status);
+
 float orc_sin(float x);
 float orc_cos(float x);
 float orc_normalize_rad_0to2pi(float x);

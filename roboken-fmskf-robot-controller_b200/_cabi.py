@@ -69,6 +69,30 @@ class VdtRollout(C.Structure):
     ]
 
 
+class AdtParams(C.Structure):
+    """rk_adt_params_t"""
+
+    _fields_ = [
+        ("ctrl_time_s", C.c_float * 7),
+        ("gear_ratio", C.c_float * 7),
+        ("motor_dir", C.c_float * 7),
+        ("curlim_default_A", C.c_float * 7),
+        ("cycle_time_s", C.c_float),
+    ]
+
+
+class AdtPosCmd(C.Structure):
+    """rk_adt_poscmd_t == ADTModePositioningSeq::PosCmd (AD_mode_positioning_seq.hpp:15-18)"""
+
+    _fields_ = [("dt_ms", C.c_uint32), ("tgt_deg", C.c_float * 5)]
+
+
+class AdtPosCmdSeq(C.Structure):
+    """rk_adt_poscmdseq_t == ADTModePositioningSeq::PosCmdSeq (:20-24), 776 bytes"""
+
+    _fields_ = [("id", C.c_uint32), ("len", C.c_uint8), ("cmd", AdtPosCmd * 32)]
+
+
 _lib = None
 
 
@@ -107,6 +131,26 @@ def _proto(lib):
     lib.rk_imt_get_yaw.argtypes = [vp, C.POINTER(C.c_float)]
     lib.rk_imt_get_state.argtypes = [vp, C.POINTER(C.c_uint32)]
     lib.rk_imt_set_state.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.rk_adt_default_params.argtypes = [C.POINTER(AdtParams)]
+    lib.rk_adt_default_params.restype = None
+    for nm in ("rk_adt_state_bytes", "rk_adt_cmdtab_bytes"):
+        getattr(lib, nm).argtypes = [C.c_int64]
+        getattr(lib, nm).restype = C.c_size_t
+    lib.rk_adt_state_words.restype = C.c_size_t
+    lib.rk_adt_mode_init.argtypes = [C.POINTER(AdtParams), vp, C.c_int64, vp]
+    lib.rk_adt_push_cmdseq.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
+    lib.rk_adt_update.argtypes = [C.POINTER(AdtParams), vp, vp, C.c_int64, C.c_int32, vp, vp]
+    lib.rk_adt_cmdseq_status.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
+    lib.rk_adt_create.argtypes = [C.POINTER(vp), C.POINTER(AdtParams)]
+    lib.rk_adt_destroy.argtypes = [vp]
+    lib.rk_adt_destroy.restype = None
+    lib.rk_adt_init.argtypes = [vp]
+    lib.rk_adt_push.argtypes = [vp, C.POINTER(AdtPosCmdSeq)]
+    lib.rk_adt_tick.argtypes = [vp]
+    lib.rk_adt_status.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int32)]
+    lib.rk_adt_get_targets_deg.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.rk_adt_get_state.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.rk_adt_set_state.argtypes = [vp, C.POINTER(C.c_uint32)]
     lib.rk_vdt_create.argtypes = [C.POINTER(vp), C.POINTER(VdtParams)]
     lib.rk_vdt_destroy.argtypes = [vp]
     lib.rk_vdt_destroy.restype = None
@@ -163,4 +207,18 @@ def default_params():
     p.jerk_stop[:] = [30000.0, 30000.0, 1000.0]
     p.motor_dir[:] = [1, 1, -1, -1]
     p.raw_curr_lim = 3000
+    return p
+
+
+def default_arm_params():
+    """JointBase::ConstParams of AD_task_main.cpp:38-107 in RK_AJ_* order + FL_CYCLE_TIME_S (:149);
+    must equal rk_adt_default_params()."""
+    f = C.c_float
+    p = AdtParams()
+    p.ctrl_time_s[:] = [0.01] * 7
+    p.gear_ratio[:] = [1.0, 1.0, 1.0, 1.0, f(f(24.0).value / f(7.0).value).value, f(f(48.0).value / f(7.0).value).value,
+                       f(f(48.0).value / f(19.0).value).value]
+    p.motor_dir[:] = [-1.0, 1.0, 1.0, 1.0, 1.0, 1.0, -1.0]
+    p.curlim_default_A[:] = [3.0, 0.7, 0.5, 0.5, 1.0, 1.0, 0.8]
+    p.cycle_time_s = 0.01
     return p

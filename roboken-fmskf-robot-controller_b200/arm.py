@@ -1,0 +1,119 @@
+"""Host-side mirror of the arm entry points (src/ArmDrive) over the C-ABI; torch owns the HBM.
+
+ArmBatch  = N x {ADTModePositioningSeq + the seven joint objects of AD_task_main.cpp:108-116}
+Arm       = one arm behind an rk_adt_t handle, method names as in the reference
+            (push_cmdseq / update / get_q_cmdseq_status / get_tgt_deg).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi, layout
+
+PROCESSING, DONE, NO_DATA = 0, 1, 99  # ADTModePositioningSeq::CmdStatus  AD_mode_positioning_seq.hpp:36-40
+
+
+class ArmBatch:
+    def __init__(self, n, device="cuda:0", params=None):
+        self.lib = _cabi.load()
+        self.n = int(n)
+        self.device = torch.device(device)
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.params = params or _cabi.default_arm_params()
+        assert self.lib.rk_adt_state_words() == layout.AS_WORDS
+        with torch.cuda.device(self.dev_index):
+            self.state = torch.zeros(layout.AS_WORDS * self.n, dtype=torch.int32, device=self.device)
+            self.cmdtab = torch.zeros(layout.ACMD_WORDS * self.n, dtype=torch.int32, device=self.device)
+
+    def _st(self, stream):
+        _cabi.check(self.lib.rk_set_device(self.dev_index))
+        st = stream if stream is not None else torch.cuda.current_stream(self.dev_index)
+        return C.c_void_p(st.cuda_stream)
+
+    def mode_init(self, stream=None):
+        """ADTModeBase::init() after a finished INIT mode (rk_adt_mode_init)."""
+        _cabi.check(self.lib.rk_adt_mode_init(C.byref(self.params), self.state.data_ptr(), self.n, self._st(stream)))
+
+    def push_cmdseq(self, seq_soa, valid=None, stream=None):
+        """seq_soa: int32/uint32 device tensor, 260*n words in plane order; valid: uint8 [n] or None."""
+        assert seq_soa.is_cuda and seq_soa.numel() == layout.ACMD_SLOT_WORDS * self.n and seq_soa.element_size() == 4
+        if valid is not None:
+            assert valid.is_cuda and valid.dtype == torch.uint8 and valid.numel() == self.n
+        _cabi.check(self.lib.rk_adt_push_cmdseq(self.state.data_ptr(), self.cmdtab.data_ptr(), self.n, seq_soa.data_ptr(),
+                                                None if valid is None else valid.data_ptr(), self._st(stream)))
+
+    def update(self, K=1, trace=None, stream=None):
+        """K fused 100 Hz ticks; trace: int32 device tensor [K, 16, n] or None."""
+        if trace is not None:
+            assert trace.is_cuda and trace.element_size() == 4 and trace.numel() == K * layout.ADT_TRACE_WORDS * self.n
+        _cabi.check(self.lib.rk_adt_update(C.byref(self.params), self.state.data_ptr(), self.cmdtab.data_ptr(), self.n, int(K),
+                                           None if trace is None else trace.data_ptr(), self._st(stream)))
+
+    def cmdseq_status(self, ids, stream=None):
+        assert ids.is_cuda and ids.element_size() == 4 and ids.numel() == self.n
+        out = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        _cabi.check(self.lib.rk_adt_cmdseq_status(self.state.data_ptr(), self.cmdtab.data_ptr(), self.n, ids.data_ptr(),
+                                                  out.data_ptr(), self._st(stream)))
+        return out
+
+    def state_host(self):
+        return self.state.cpu().numpy().view(np.uint32)
+
+    def cmdtab_host(self):
+        return self.cmdtab.cpu().numpy().view(np.uint32)
+
+    def load_state_soa(self, soa_u32, tab_u32=None):
+        self.state.copy_(torch.from_numpy(np.asarray(soa_u32).view(np.int32)))
+        if tab_u32 is not None:
+            self.cmdtab.copy_(torch.from_numpy(np.asarray(tab_u32).view(np.int32)))
+
+
+class Arm:
+    """Single arm (rk_adt_t): the statics of AD_task_main.cpp:108-156 behind one handle."""
+
+    def __init__(self, params=None):
+        self.lib = _cabi.load()
+        self.h = C.c_void_p()
+        _cabi.check(self.lib.rk_adt_create(C.byref(self.h), None if params is None else C.byref(params)))
+
+    def close(self):
+        if self.h:
+            self.lib.rk_adt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self):
+        _cabi.check(self.lib.rk_adt_init(self.h))
+
+    def push_cmdseq(self, seq_id, waypoints):
+        """waypoints: [(dt_ms, (5 deg)), ...] (<= 32)."""
+        q = _cabi.AdtPosCmdSeq()
+        q.id, q.len = int(seq_id), len(waypoints)
+        for k, (dt, deg) in enumerate(waypoints):
+            q.cmd[k].dt_ms = int(dt)
+            q.cmd[k].tgt_deg[:] = [float(x) for x in deg]
+        _cabi.check(self.lib.rk_adt_push(self.h, C.byref(q)))
+
+    def update(self):
+        _cabi.check(self.lib.rk_adt_tick(self.h))
+
+    def get_q_cmdseq_status(self, seq_id):
+        s = C.c_int32()
+        _cabi.check(self.lib.rk_adt_status(self.h, int(seq_id), C.byref(s)))
+        return s.value
+
+    def get_tgt_deg(self):
+        out = (C.c_float * 5)()
+        _cabi.check(self.lib.rk_adt_get_targets_deg(self.h, out))
+        return np.array(out[:], dtype=np.float32)
+
+    def get_state(self):
+        w = (C.c_uint32 * layout.AS_WORDS)()
+        _cabi.check(self.lib.rk_adt_get_state(self.h, w))
+        return np.array(w[:], dtype=np.uint32)

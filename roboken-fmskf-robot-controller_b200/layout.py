@@ -35,6 +35,21 @@ IMT_REGS = 16
 (REG_AX, REG_AY, REG_AZ, REG_GX, REG_GY, REG_GZ, REG_HX, REG_HY, REG_HZ, REG_ROLL, REG_PITCH, REG_YAW,
  REG_Q0, REG_Q1, REG_Q2, REG_Q3) = range(16)
 
+# ---- arm (RK_AS_* / RK_ACMD_*) ------------------------------------------------------------
+AJ_Y0, AJ_P1, AJ_DFL, AJ_DFR, AJ_P2, AJ_R0, AJ_P3, AJ_NUM = range(8)
+AS_FSM, AS_SEQ_IDX, AS_CMD_IDX, AS_MOVE_CNT, AS_CYCLE, AS_TOTAL_MS, AS_NOW_DT = range(7)
+AS_NOW_TGT, AS_MOVE_DEG, AS_DFV_P, AS_DFV_R, AS_JOINT0 = 8, 13, 18, 19, 20
+AS_JFLAGS, AS_MG_PRE_TGT, AS_ICS_POS, AS_ICS_SERVO = 48, 49, 50, 51
+AS_MG_TX, AS_BLDC_TX0, AS_MG_CTRL, AS_WORDS = 52, 56, 68, 76
+AJ_OFS, AJ_RAW_TGT, AJ_CURLIM, AJ_RAW_NOW = range(4)
+ASTATE_STANDBY, ASTATE_MOVE_START, ASTATE_MOVING, ASTATE_COMPLETED = range(4)
+AS_FSM_FIRSTCALL, AS_FSM_IS_COMP = 0x100, 0x200
+AJF_CONNECTED, AJF_TORQUE_ON, AJF_INITIALIZED, AJF_TORQUE_PREV = 1, 2, 4, 8
+ACMD_SLOTS, ACMD_MAX_LEN, ACMD_SLOT_WORDS = 4, 32, 260
+ACMD_WORDS = ACMD_SLOTS * ACMD_SLOT_WORDS
+ADT_TRACE_WORDS = 16
+ADT_AXIS = (AJ_Y0, AJ_P1, AJ_P2, AJ_R0, AJ_P3)  # mode axes J0..J4 (AD_task_main.cpp:148)
+
 
 def soa_to_aos(block, n, words):
     """[planes, n, 4] SoA block (any uint32 array of words*n elements) -> [n, words]."""

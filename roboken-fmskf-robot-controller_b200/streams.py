@@ -116,3 +116,40 @@ def imu_samples(n, n_upd, seed=0x5EED, first=0, drop_every=64):
     regs[:, 12:16, :] = np.rint(g / nrm * 32767.0).astype(np.int16)
     have = (_hash(seed, 22, inst[:, 0, :], u[:, 0, :]) % np.uint64(drop_every) != 0).astype(np.uint8)
     return np.ascontiguousarray(regs), np.ascontiguousarray(have)
+
+
+def arm_sequences(n, seed=0x5EED, first=0, max_len=32, min_len=2, seq_id=1, dt_zero_every=4):
+    """C4 command sequences: one PosCmdSeq per arm as an AoS slot image, uint32 [n, 260]
+    (word 0 u32_id, 1 u8_cmd_seq_len, 2-3 zero, then 32 x {u32_dt_ms, fl_tgt_pos_deg[5], 0, 0};
+    AD_mode_positioning_seq.hpp:15-24).  len ~ U{min_len..max_len}; dt_ms absolute and
+    non-decreasing, increments ~ U{10..1000} (1 in 8 is 0: a zero-length segment, one cycle);
+    1 arm in `dt_zero_every` starts with dt=0 like POS_CMD_SEQ_DEBUG_2; angles ~ U[-150,150]
+    deg in whole 1/64 deg (exact float32).  Entries past len hold stale random waypoints, as a
+    reused firmware buffer would."""
+    inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[:, None]
+    k = np.arange(32, dtype=np.uint64)[None, :]
+    ln = (_hash(seed, 30, inst[:, 0], 0) % np.uint64(max_len - min_len + 1)).astype(np.int64) + min_len
+    inc = (_hash(seed, 31, inst, k) % np.uint64(991)).astype(np.int64) + 10
+    inc[(_hash(seed, 32, inst, k) % np.uint64(8)) == 0] = 0
+    z = (_hash(seed, 33, inst[:, 0], 0) % np.uint64(dt_zero_every)) == 0
+    inc[z, 0] = 0
+    dt = np.cumsum(inc, axis=1)
+    img = np.zeros((n, 260), dtype=np.uint32)
+    img[:, 0] = seq_id
+    img[:, 1] = ln
+    wp = img[:, 4:].reshape(n, 32, 8)
+    wp[:, :, 0] = dt.astype(np.uint32)
+    for j in range(5):
+        q = (_hash(seed, 34 + j, inst, k) % np.uint64(300 * 64 + 1)).astype(np.int64) - 150 * 64
+        wp[:, :, 1 + j] = (q.astype(np.float32) * np.float32(1.0 / 64.0)).view(np.uint32)
+    return img
+
+
+def arm_seq_image(seq_id, waypoints):
+    """One slot image (uint32 [260]) from [(dt_ms, (5 deg)), ...]."""
+    img = np.zeros(260, dtype=np.uint32)
+    img[0], img[1] = seq_id, len(waypoints)
+    for k, (dt, deg) in enumerate(waypoints):
+        img[4 + 8 * k] = dt
+        img[5 + 8 * k : 10 + 8 * k] = np.asarray(deg, dtype=np.float32).view(np.uint32)
+    return img

@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
-"""Generate tests/golden/vdt_golden.npz from oracle/_ref -- the reference's own sources
+"""Generate tests/golden/{vdt,imu,arm}_golden.npz from oracle/_ref -- the reference's own sources
 compiled unmodified for x86 (needs /root/reference or a prebuilt oracle/_ref).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [vdt] [imu] [arm]     (default: all)
 
 The fixtures hold OUTPUTS only (decimated traces + final state blocks); inputs are
 re-derived from seeds by tests/workloads.py, so the file stays small.
@@ -34,7 +34,45 @@ def c1_rows():
     return np.unique(np.concatenate([np.arange(10), np.arange(0, 10000, 50), [4999, 5000, 5001, 9999]]))
 
 
+def arm_golden():
+    """Arm: the reference's own POS_CMD_SEQ_DEBUG_0/1/2 (AD_mode_positioning_seq_debug_data.cpp)
+    on arms 0..2 + seeded random sequences, through the compiled reference.  Inputs are stored
+    too (they are small) so the fixture is self-contained."""
+    n, K = 24, 420
+    r = ol.ref("libref_arm.so")
+    seq_a = streams.arm_sequences(n, seed=0x5EED, seq_id=1, max_len=6)
+    seq_b = streams.arm_sequences(n, seed=0x5EED + 1, seq_id=2, max_len=4)
+    for w in range(3):
+        q = _cabi.AdtPosCmdSeq()
+        r.ref_adt_debug_seq(w, q)
+        seq_a[w] = ol.seq_struct_to_image(q)
+        seq_a[w, 0] = 1
+    valid_b = (np.arange(n) % 4 != 1).astype(np.uint8)
+    st = np.zeros(layout.AS_WORDS * n, dtype=np.uint32)
+    tb = np.zeros(layout.ACMD_WORDS * n, dtype=np.uint32)
+    ol.arm_batch("ref", "init", st, tb, n)
+    ol.arm_batch("ref", "push", st, tb, n, seq=layout.aos_to_soa(seq_a))
+    ol.arm_batch("ref", "push", st, tb, n, seq=layout.aos_to_soa(seq_b), valid=valid_b)
+    tr, _ = ol.arm_batch("ref", "update", st, tb, n, K=K, trace=True)
+    ids = (np.arange(n) % 3).astype(np.uint32)
+    _, status = ol.arm_batch("ref", "status", st, tb, n, ids=ids)
+    path = os.path.join(HERE, "arm_golden.npz")
+    np.savez_compressed(path, n=n, K=K, seq_a=seq_a, seq_b=seq_b, valid_b=valid_b, trace=tr, state=st, cmdtab=tb, ids=ids,
+                        status=status)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
+    which = set(sys.argv[1:]) or {"vdt", "imu", "arm"}
+    if "arm" in which:
+        arm_golden()
+    if "vdt" in which:
+        vdt_golden()
+    if "imu" in which:
+        imu_golden()
+
+
+def vdt_golden():
     out = {}
     st, tr = run_ref(wl.c1_inputs())
     out["c1_rows"] = c1_rows()
@@ -58,6 +96,9 @@ def main():
     path = os.path.join(HERE, "vdt_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def imu_golden():
     # IMU: compiled reference driven through WT901 serial frames
     n, K = 64, 32
     regs, have = streams.imu_samples(n, K, seed=0x5EED, drop_every=8)

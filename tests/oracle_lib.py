@@ -40,6 +40,9 @@ def port():
         lib.orc_vdt_update.argtypes = [C.POINTER(_cabi.VdtParams), vp]
         lib.orc_imt_update.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int]
         lib.orc_imt_update.restype = None
+        lib.orc_adt_batch.argtypes = [C.c_int, C.POINTER(_cabi.AdtParams), vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                      vp, vp, vp, vp, vp]
+        lib.orc_adt_batch.restype = None
         for nm in ("orc_sin", "orc_cos", "orc_normalize_rad_0to2pi", "orc_normalize_deg_0to360"):
             getattr(lib, nm).argtypes = [C.c_float]
             getattr(lib, nm).restype = C.c_float
@@ -93,6 +96,20 @@ def ref(name="libref_vdt.so"):
             lib.ref_imt_import.argtypes = [vp, vp]
             lib.ref_imt_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int]
             lib.ref_imt_rollout.restype = None
+        if name.startswith("libref_arm"):
+            lib.ref_adt_create.restype = vp
+            for nm in ("ref_adt_destroy", "ref_adt_bringup", "ref_adt_tick"):
+                getattr(lib, nm).argtypes = [vp]
+                getattr(lib, nm).restype = None
+            lib.ref_adt_push.argtypes = [vp, C.POINTER(_cabi.AdtPosCmdSeq)]
+            lib.ref_adt_status.argtypes = [vp, C.c_uint32]
+            lib.ref_adt_targets.argtypes = [vp, C.POINTER(C.c_float)]
+            lib.ref_adt_export.argtypes = [vp, vp]
+            lib.ref_adt_import.argtypes = [vp, vp]
+            lib.ref_adt_trace_row.argtypes = [vp, vp]
+            lib.ref_adt_debug_seq.argtypes = [C.c_int, C.POINTER(_cabi.AdtPosCmdSeq)]
+            lib.ref_adt_batch.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, vp, vp]
+            lib.ref_adt_batch.restype = None
         _cache[name] = lib
     return _cache[name]
 
@@ -141,3 +158,42 @@ def imu_ref(state_soa, n, regs, have=None, want_out=False, do_init=False):
     out = np.zeros((K, 4, n, 4), dtype=np.uint32) if want_out else None
     ref("libref_imu.so").ref_imt_rollout(_ptr(state_soa), n, 0, n, K, _ptr(regs), _ptr(have), _ptr(out), int(do_init))
     return out
+
+
+# ---- arm ---------------------------------------------------------------------------------
+ARM_OPS = {"init": 0, "push": 1, "update": 2, "status": 3}
+
+
+def arm_batch(kind, op, state, cmdtab, n, K=0, seq=None, valid=None, trace=False, ids=None, params=None):
+    """Runs one rk_adt_* batch op on HOST SoA arrays through the port ("port") or the compiled
+    reference ("ref").  Returns (trace or None, status or None); state/cmdtab updated in place."""
+    tr = np.zeros((K, layout.ADT_TRACE_WORDS, n), dtype=np.uint32) if (trace and op == "update") else None
+    status = np.zeros(n, dtype=np.int32) if op == "status" else None
+    if kind == "port":
+        p = params or _cabi.default_arm_params()
+        port().orc_adt_batch(ARM_OPS[op], C.byref(p), _ptr(state), _ptr(cmdtab), n, 0, n, K, _ptr(seq), _ptr(valid),
+                             _ptr(tr), _ptr(ids), _ptr(status))
+    else:
+        assert params is None, "the compiled reference has the firmware constants wired in"
+        ref("libref_arm.so").ref_adt_batch(ARM_OPS[op], _ptr(state), _ptr(cmdtab), n, 0, n, K, _ptr(seq), _ptr(valid),
+                                           _ptr(tr), _ptr(ids), _ptr(status))
+    return tr, status
+
+
+def seq_struct_to_image(q):
+    """rk_adt_poscmdseq_t -> uint32[260] slot image"""
+    img = np.zeros(layout.ACMD_SLOT_WORDS, dtype=np.uint32)
+    img[0], img[1] = q.id, q.len
+    for k in range(32):
+        img[4 + 8 * k] = q.cmd[k].dt_ms
+        img[5 + 8 * k : 10 + 8 * k] = np.array(q.cmd[k].tgt_deg[:], dtype=np.float32).view(np.uint32)
+    return img
+
+
+def image_to_seq_struct(img):
+    q = _cabi.AdtPosCmdSeq()
+    q.id, q.len = int(img[0]), int(img[1]) & 0xFF
+    for k in range(32):
+        q.cmd[k].dt_ms = int(img[4 + 8 * k])
+        q.cmd[k].tgt_deg[:] = [float(x) for x in np.asarray(img[5 + 8 * k : 10 + 8 * k], dtype=np.uint32).view(np.float32)]
+    return q

@@ -48,6 +48,28 @@ def test_default_params_match(lib):
     assert bytes(p) == bytes(rk.default_params())
 
 
+def test_arm_abi(lib):
+    p = _cabi.AdtParams()
+    lib.rk_adt_default_params(C.byref(p))
+    assert bytes(p) == bytes(_cabi.default_arm_params())
+    assert lib.rk_adt_state_words() == layout.AS_WORDS == 76
+    assert lib.rk_adt_state_bytes(3) == 3 * 304 and lib.rk_adt_cmdtab_bytes(2) == 2 * 4160
+    assert C.sizeof(_cabi.AdtPosCmdSeq) == 776  # sizeof(ADTModePositioningSeq::PosCmdSeq), SURVEY 8a
+    text = open(os.path.join(ROOT, "include", "robotick.h")).read()
+    for name, val in (("RK_AS_JOINT0", layout.AS_JOINT0), ("RK_AS_JFLAGS", layout.AS_JFLAGS), ("RK_AS_MG_TX", layout.AS_MG_TX),
+                      ("RK_AS_BLDC_TX0", layout.AS_BLDC_TX0), ("RK_AS_WORDS", layout.AS_WORDS)):
+        assert re.search(rf"{name}\s*=\s*{val}\b", text), name
+    import torch
+
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert lib.rk_adt_create(C.byref(h), None) == 2  # RK_ERR_CUDA: no CPU fallback
+        buf = (C.c_uint32 * 2048)()
+        addr = (C.addressof(buf) + 15) & ~15
+        assert lib.rk_adt_update(C.byref(p), C.c_void_p(addr), C.c_void_p(addr), 1, 1, None, None) == 2
+    assert lib.rk_adt_update(C.byref(p), C.c_void_p(8), C.c_void_p(16), 1, 1, None, None) == 1
+
+
 def test_header_enums_match_python_layout():
     text = open(os.path.join(ROOT, "include", "robotick.h")).read()
     assert "RK_VS_INTERP0 = 12" in text
