@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--yaw-period", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall budget of the cpu_baseline leg")
     ap.add_argument("--occupancy", type=int, default=0, help="RK_OPT_FAST_OCCUPANCY override (tuning)")
+    ap.add_argument("--packed", type=int, default=-1, help="RK_OPT_FAST_PACKED override (tuning; -1 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -216,6 +217,8 @@ def run_ours(a):
     _cabi.check(lib.rk_set_device(local_rank))
     if a.occupancy:
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_OCCUPANCY, a.occupancy))
+    if a.packed >= 0:
+        _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_PACKED, a.packed))
     n, K, W, T = a.instances, a.steps, a.warmup, a.ticks
     first = rank * n  # contiguous slice of the global instance index space
     n_seg = (T + a.seg_len - 1) // a.seg_len

@@ -57,7 +57,8 @@ int rk_set_device(int device);
  * are bit-identical; the tests compare them). */
 enum {
   RK_OPT_FORCE_TRANSCRIPTION = 1,
-  RK_OPT_FAST_OCCUPANCY = 2 /* 3, 4 (default) or 5 resident CTAs/SM: register budget of the rollout kernel */
+  RK_OPT_FAST_OCCUPANCY = 2, /* 3, 4 (default) or 5 resident CTAs/SM: register budget of the rollout kernel */
+  RK_OPT_FAST_PACKED = 3     /* 1 (default): packed FADD2/FFMA2 tick; 0: scalar tick.  Bit-identical; tests compare. */
 };
 int rk_set_option(int option, int value);
 /* 1 if the exhaustive on-device proofs that gate the issue-optimised kernel hold for these

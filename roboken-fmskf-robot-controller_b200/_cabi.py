@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librobotick_b200.so")
+LIB_PATH = os.environ.get("ROBOTICK_LIB") or os.path.join(_HERE, "librobotick_b200.so")  # env: tuning builds only
 
 RK_OK = 0
 
@@ -17,6 +17,7 @@ RK_CMD_NONE, RK_CMD_MOVE, RK_CMD_STOP = 0, 1, 2
 RK_VDT_TRACE_WORDS = 16
 RK_OPT_FORCE_TRANSCRIPTION = 1
 RK_OPT_FAST_OCCUPANCY = 2
+RK_OPT_FAST_PACKED = 3
 
 
 class VdtParams(C.Structure):

@@ -4,7 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "rk_vehicle_fast.cuh"
+#include "rk_vehicle_fast2.cuh"
 
 namespace rk {
 
@@ -96,7 +96,14 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
 // command application, the last tick of the launch and any thread outside the fast path's
 // domain run the transcription (veh_update), so the stored state is complete and identical.
 // -----------------------------------------------------------------------------------------
-constexpr int kFastThreads = 128;
+#ifndef RK_FAST_THREADS
+#define RK_FAST_THREADS 128
+#endif
+#ifndef RK_FAST_UNROLL
+#define RK_FAST_UNROLL 2
+#endif
+constexpr int kFastThreads = RK_FAST_THREADS;
+constexpr int kFastUnroll  = RK_FAST_UNROLL;
 
 template <bool TRACE>
 RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, float py, float pth, const float vel[3],
@@ -110,8 +117,8 @@ RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, 
   tr[13 * n] = 0u, tr[14 * n] = 0u, tr[15 * n] = 0u;
 }
 
-template <bool TRACE, int OCC, bool FFSAT>
-__global__ void __launch_bounds__(kFastThreads, OCC)
+template <bool TRACE, int OCC, bool FFSAT, bool PACKED>
+__global__ void __launch_bounds__(kFastThreads, OCC * 128 / kFastThreads)
 vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
   constexpr int D0 = 1, D1 = 1, D2 = -1, D3 = -1; // VD_task_main.cpp:75-78 (host checks params match)
   __shared__ float s_tab[513];
@@ -172,22 +179,41 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
     }
     const int t_end = min(next_cmd, K - 1); // the last tick of the launch is a transcription tick
     if(t < t_end && fast_ok<D0, D1, D2, D3>(v, p)) {
-      FastVeh f;
-      to_fast<D0, D1, D2, D3>(v, f, p.ts, fc.B0);
       const int t0  = t;
       float     pth = v.pos[2];
-      while(t < t_end) {
-        if(t == next_yaw) take_yaw(pth);
-        const int t_stop = min(t_end, next_yaw);
-#pragma unroll 2
-        for(; t < t_stop; t++) {
-          float vel[3], tgt[3];
-          fast_tick<D0, D1, D2, D3, FFSAT>(f, p, fc, cth, sth, vel, tgt);
-          trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur);
+      if(PACKED) { // FADD2 / FFMA2 form of the same tick (rk_vehicle_fast2.cuh)
+        FastVeh2 f;
+        to_fast2(v, f, p.ts, fc.B0);
+        const float nz = fmul(-0.0f, p.ts); // opaque -0.0f (p.ts > 0 is a fast-path precondition)
+        while(t < t_end) {
+          if(t == next_yaw) take_yaw(pth);
+          const int    t_stop = min(t_end, next_yaw);
+          const float2 cs = make_float2(cth, sth), sc = make_float2(sth, cth);
+#pragma unroll kFastUnroll
+          for(; t < t_stop; t++) {
+            float vel[3], tgt[3];
+            fast_tick2<FFSAT>(f, p, fc, cs, sc, nz, vel, tgt);
+            trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1]);
+          }
         }
+        v.pos[2] = pth;
+        from_fast2<D0, D1, D2, D3>(v, f, t - t0);
+      } else {
+        FastVeh f;
+        to_fast<D0, D1, D2, D3>(v, f, p.ts, fc.B0);
+        while(t < t_end) {
+          if(t == next_yaw) take_yaw(pth);
+          const int t_stop = min(t_end, next_yaw);
+#pragma unroll kFastUnroll
+          for(; t < t_stop; t++) {
+            float vel[3], tgt[3];
+            fast_tick<D0, D1, D2, D3, FFSAT>(f, p, fc, cth, sth, vel, tgt);
+            trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur);
+          }
+        }
+        v.pos[2] = pth;
+        from_fast<D0, D1, D2, D3>(v, f, t - t0);
       }
-      v.pos[2] = pth;
-      from_fast<D0, D1, D2, D3>(v, f, t - t0);
     } else {
       if(t == next_yaw) take_yaw(v.pos[2]);
       const int32_t us = ((t + 1) * 1000) & 0x7FFF;
@@ -307,6 +333,7 @@ static cudaError_t launch_rollout(const rk_vdt_params_t &p, void *d_state, int64
 bool fast_path_proven(const rk_vdt_params_t &p); // rk_exact.cu
 
 static int g_fast_occupancy = 4;       // rk_set_option(RK_OPT_FAST_OCCUPANCY, 3|4|5): tuning
+static int g_fast_packed = 1;          // rk_set_option(RK_OPT_FAST_PACKED, 0|1): packed FP32 tick (default) or scalar
 static int g_force_transcription = 0; // rk_vdt_set_option(RK_OPT_FORCE_TRANSCRIPTION, 1): tests
 
 // The fast kernel is compiled for the firmware's wiring (directions +,+,-,-) and needs
@@ -351,6 +378,10 @@ int rk_device_info(int device, int *sm_count, int *sm_clock_khz, size_t *hbm_byt
 int rk_set_option(int option, int value) {
   if(option == RK_OPT_FORCE_TRANSCRIPTION) {
     rk::g_force_transcription = value;
+    return RK_OK;
+  }
+  if(option == RK_OPT_FAST_PACKED) {
+    rk::g_fast_packed = value != 0;
     return RK_OK;
   }
   if(option == RK_OPT_FAST_OCCUPANCY && (value >= 3 && value <= 5)) {
@@ -417,12 +448,19 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
     if(fast_path_usable(*p)) {
       const unsigned grid = (unsigned)((n + kFastThreads - 1) / kFastThreads);
       const bool ffsat = (p->ff_limit == 1.0f);
+#define RK_LAUNCH_FAST2(TR, OCC, SAT)                                                                              \
+  do {                                                                                                             \
+    if(g_fast_packed)                                                                                              \
+      vdt_rollout_fast_kernel<TR, OCC, SAT, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); \
+    else                                                                                                           \
+      vdt_rollout_fast_kernel<TR, OCC, SAT, false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);\
+  } while(0)
 #define RK_LAUNCH_FAST(TR, OCC)                                                                                    \
   do {                                                                                                             \
     if(ffsat)                                                                                                      \
-      vdt_rollout_fast_kernel<TR, OCC, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);     \
+      RK_LAUNCH_FAST2(TR, OCC, true);                                                                              \
     else                                                                                                           \
-      vdt_rollout_fast_kernel<TR, OCC, false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);    \
+      RK_LAUNCH_FAST2(TR, OCC, false);                                                                             \
   } while(0)
       if(args->d_trace) {
         RK_LAUNCH_FAST(true, 4);
@@ -434,6 +472,7 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
         }
       }
 #undef RK_LAUNCH_FAST
+#undef RK_LAUNCH_FAST2
       e = cudaGetLastError();
     } else {
       e = launch_rollout<RK_SENSOR_PLANT>(*p, d_state, n, *args, st);

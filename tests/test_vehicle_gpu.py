@@ -358,6 +358,25 @@ def test_fast_kernel_equals_transcription_kernel():
     assert_same(fast_st, pst, "fast state vs port")
 
 
+def test_packed_and_scalar_fast_ticks_agree():
+    """The fast kernel has two bit-identical forms: packed FADD2/FFMA2 (default) and scalar
+    (RK_OPT_FAST_PACKED = 0).  Every other test here runs the packed one; this one runs both."""
+    lib = rk.load()
+    n = 2048 + 5
+    inp = wl.plant_inputs(n, 1000, seed=31, seg_len=125, yaw_period=10)
+    packed_st, packed_tr = gpu_run(inp)
+    lib.rk_set_option(_cabi.RK_OPT_FAST_PACKED, 0)
+    try:
+        scalar_st, scalar_tr = gpu_run(inp)
+    finally:
+        lib.rk_set_option(_cabi.RK_OPT_FAST_PACKED, 1)
+    assert_same(packed_tr, scalar_tr, "packed vs scalar trace")
+    assert_same(packed_st, scalar_st, "packed vs scalar state")
+    pst, ptr = port_run(inp, nthreads=8)
+    assert_same(packed_tr, ptr, "packed trace vs port")
+    assert_same(packed_st, pst, "packed state vs port")
+
+
 def test_non_finite_and_extreme_commands_fall_back_exactly():
     """Commands outside the fast path's domain (huge / tiny / NaN / Inf targets) must take the
     transcription path per thread and still match the oracle bit for bit."""
