@@ -245,6 +245,12 @@ size_t rk_imt_state_bytes(int64_t n);
 int rk_imt_update(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat,
                   float *d_out, int do_init, void *stream);
 
+/* Same, plus the value the vehicle ISR reads after each update: d_yaw_rad[u * n + i] =
+ * mymath::deg2rad(IMT::get_status_now_yaw())  (VD_task_main.cpp:368, imu_task_main.cpp:102-104,
+ * util_mymath.hpp:16) -- the 4-byte-per-update stream rk_vdt_rollout() consumes as d_yaw. */
+int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat,
+                      float *d_out, float *d_yaw_rad, int do_init, void *stream);
+
 /* single-instance handle (drop-in for `static IMU_IF_WT901C imu_if`, imu_task_main.cpp:25) */
 typedef struct rk_imt rk_imt_t;
 int   rk_imt_create(rk_imt_t **out);
@@ -362,6 +368,33 @@ int  rk_adt_status(rk_adt_t *h, uint32_t id, int32_t *status);    /* get_q_cmdse
 int  rk_adt_get_targets_deg(rk_adt_t *h, float out[5]);           /* JointBase::get_tgt_deg x5       */
 int  rk_adt_get_state(rk_adt_t *h, uint32_t words[RK_AS_WORDS]);
 int  rk_adt_set_state(rk_adt_t *h, const uint32_t words[RK_AS_WORDS]);
+
+/* =====================================================================================
+ * Full controller tick (BASELINE configs[4]): vehicle at 1 kHz, IMU update + arm tick every
+ * `slow_period` vehicle ticks (10: the tasks run at 100 Hz, imu_task_main.cpp:17,
+ * AD_task_main.cpp loop), coupled exactly as the firmware couples them: the vehicle ISR reads
+ * deg2rad(IMU yaw) before every update (VD_task_main.cpp:368).  Slow tick k runs before
+ * vehicle tick k * slow_period.  The three sub-systems are independent apart from that yaw
+ * stream, so the call runs the IMU kernel, then the vehicle rollout fed by the yaw stream it
+ * emitted, with the arm kernel concurrent on an internal side stream; it is asynchronous on
+ * `stream` like every other batch call.
+ * ===================================================================================== */
+typedef struct rk_tick_rollout {
+  int32_t steps;             /* K vehicle ticks */
+  int32_t slow_period;       /* vehicle ticks per IMU / arm tick (firmware: 10) */
+  const rk_vdt_cmd_t *d_cmd; /* vehicle commands, as rk_vdt_rollout_t */
+  int32_t n_seg, seg_len;
+  const int16_t *d_regs;     /* IMU samples [n_slow][16][n], n_slow = ceil(K / slow_period) */
+  const uint8_t *d_have_quat;/* [n_slow][n] or NULL */
+  float *d_yaw;              /* scratch, n_slow * n floats: the yaw stream (radians) */
+  const float *d_goal;       /* optional cost epilogue, as rk_vdt_rollout_t */
+  float *d_cost;
+  uint32_t *d_vdt_trace;     /* optional traces (tests) */
+  uint32_t *d_adt_trace;
+} rk_tick_rollout_t;
+
+int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t *ap, void *d_vdt_state, void *d_imt_state,
+                    void *d_adt_state, const void *d_adt_cmdtab, int64_t n, const rk_tick_rollout_t *args, void *stream);
 
 #ifdef __cplusplus
 }

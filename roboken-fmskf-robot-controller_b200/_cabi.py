@@ -94,6 +94,25 @@ class AdtPosCmdSeq(C.Structure):
     _fields_ = [("id", C.c_uint32), ("len", C.c_uint8), ("cmd", AdtPosCmd * 32)]
 
 
+class TickRollout(C.Structure):
+    """rk_tick_rollout_t"""
+
+    _fields_ = [
+        ("steps", C.c_int32),
+        ("slow_period", C.c_int32),
+        ("d_cmd", C.c_void_p),
+        ("n_seg", C.c_int32),
+        ("seg_len", C.c_int32),
+        ("d_regs", C.c_void_p),
+        ("d_have_quat", C.c_void_p),
+        ("d_yaw", C.c_void_p),
+        ("d_goal", C.c_void_p),
+        ("d_cost", C.c_void_p),
+        ("d_vdt_trace", C.c_void_p),
+        ("d_adt_trace", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -123,6 +142,9 @@ def _proto(lib):
     lib.rk_imt_state_bytes.argtypes = [C.c_int64]
     lib.rk_imt_state_bytes.restype = C.c_size_t
     lib.rk_imt_update.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, C.c_int, vp]
+    lib.rk_imt_update_yaw.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int, vp]
+    lib.rk_tick_rollout.argtypes = [C.POINTER(VdtParams), C.POINTER(AdtParams), vp, vp, vp, vp, C.c_int64,
+                                    C.POINTER(TickRollout), vp]
     lib.rk_imt_create.argtypes = [C.POINTER(vp)]
     lib.rk_imt_destroy.argtypes = [vp]
     lib.rk_imt_destroy.restype = None

@@ -43,7 +43,7 @@ RK_DEV void imu_update_data(const float qi[4], const int r[16], ImuData &o) {
 
 __global__ void __launch_bounds__(256)
 imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__restrict__ regs,
-                  const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, int do_init) {
+                  const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
   float   qi[4];
@@ -74,6 +74,9 @@ imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__
     } else {
       flags |= RK_IS_FLAG_ERROR; // previous page stays readable
     }
+    // what the vehicle ISR reads each tick: mymath::deg2rad(IMT::get_status_now_yaw())
+    // (VD_task_main.cpp:368, imu_task_main.cpp:102-104, util_mymath.hpp:13,16)
+    if(yaw_rad) __stcs(yaw_rad + (int64_t)u * n + i, fmul(cur.d[RK_IS_D_ANGLE + 2], RK_DEG2RAD));
     if(out) {
 #pragma unroll
       for(int pl = 0; pl < 4; pl++)
@@ -98,6 +101,11 @@ size_t rk_imt_state_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_IS_WORD
 
 int rk_imt_update(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
                   int do_init, void *stream) {
+  return rk_imt_update_yaw(d_state, n, K, d_regs, d_have_quat, d_out, nullptr, do_init, stream);
+}
+
+int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
+                      float *d_yaw_rad, int do_init, void *stream) {
   if(n == 0 || K == 0) return RK_OK;
   if(n < 0 || K < 0 || !d_regs) {
     set_error("rk_imt_update: bad n/K/regs");
@@ -109,7 +117,7 @@ int rk_imt_update(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, co
   }
   if(int rc = require_device()) return rc;
   imt_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint4 *)d_state, n, K, d_regs, d_have_quat,
-                                                                                  (float4 *)d_out, do_init);
+                                                                                  (float4 *)d_out, d_yaw_rad, do_init);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }

@@ -197,3 +197,25 @@ def image_to_seq_struct(img):
         q.cmd[k].dt_ms = int(img[4 + 8 * k])
         q.cmd[k].tgt_deg[:] = [float(x) for x in np.asarray(img[5 + 8 * k : 10 + 8 * k], dtype=np.uint32).view(np.float32)]
     return q
+
+
+# ---- full tick (vehicle + IMU + arm) ---------------------------------------------------------
+def full_tick(kind, n, steps, slow_period, cmd, seg_len, regs, have, vstate, istate, astate, atab, trace=False, goal=None,
+              nthreads=1):
+    """The firmware's coupling restated on the HOST from the per-module oracles: IMU update k runs
+    before vehicle tick k*slow_period and the vehicle ISR reads deg2rad(getYawDate())
+    (VD_task_main.cpp:368, util_mymath.hpp:13,16); the arm ticks at the IMU rate.  `kind` selects
+    the plain-C port or the compiled reference for every module.  States updated in place."""
+    from roboken_fmskf_robot_controller_b200 import streams
+
+    n_slow = (steps + slow_period - 1) // slow_period
+    out = (imu_port if kind == "port" else imu_ref)(istate, n, regs[:n_slow], None if have is None else have[:n_slow], want_out=True)
+    yaw_deg = np.ascontiguousarray(out[:, 2, :, 3]).view(np.float32)  # Data.angle[2] = word 11
+    yaw = (yaw_deg * streams.DEG2RAD).astype(np.float32)
+    ro = HostRollout(n, steps, _cabi.RK_SENSOR_PLANT, cmd, seg_len, yaw, slow_period, trace=trace, goal=goal)
+    if kind == "port":
+        run_port(vstate, n, ro, nthreads=nthreads)
+    else:
+        run_ref(vstate, n, ro, nthreads=nthreads)
+    atr, _ = arm_batch(kind, "update", astate, atab, n, K=n_slow, trace=trace)
+    return ro.trace, atr, yaw, ro.cost
