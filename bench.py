@@ -4,9 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one batch: one launch of the fused rollout kernel
-over `--instances` vehicles per GPU x `--ticks` 1 kHz control ticks (default: BASELINE.json
-configs[1], 2^20 vehicles x 1000 fused ticks, closed loop through the integer motor plant).
+A "step" is one pass of the hot path over one batch.
+  --workload vehicle (default; BASELINE.json configs[1]): one launch of the fused rollout kernel over
+      `--instances` vehicles per GPU x `--ticks` 1 kHz control ticks, closed loop through the
+      integer motor plant.  Weak scaling (per-GPU batch fixed).
+  --workload full (BASELINE.json configs[4]): the full controller tick -- vehicle at 1 kHz, IMU
+      update + arm tick at 100 Hz, coupled through the IMU yaw -- over `--total` robots (2^24)
+      batch-sharded across the GPUs (strong scaling), run in chunks of `--chunk` robots.
 Rank 0 prints ONE JSON line (see DESIGN.md "Measurement").
 
   value        whole-job instance-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
@@ -46,7 +50,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--instances", type=int, default=1 << 20, help="vehicles per GPU")
+    ap.add_argument("--workload", default="vehicle", choices=["vehicle", "full"])
+    ap.add_argument("--instances", type=int, default=1 << 20, help="vehicles per GPU (workload vehicle)")
+    ap.add_argument("--total", type=int, default=1 << 24, help="robots over all GPUs (workload full)")
+    ap.add_argument("--chunk", type=int, default=1 << 20, help="robots per rk_tick_rollout call (workload full)")
+    ap.add_argument("--slow-period", type=int, default=10, help="vehicle ticks per IMU/arm tick (workload full)")
     ap.add_argument("--ticks", type=int, default=1000, help="fused control ticks per launch")
     ap.add_argument("--seg-len", type=int, default=125)
     ap.add_argument("--yaw-period", type=int, default=10)
@@ -59,6 +67,11 @@ def parse():
 
 
 def workload_name(a):
+    if a.workload == "full":
+        return (f"configs[4]: full controller tick, {a.total} robots batch-sharded over {a.gpus} GPU(s) x {a.ticks} fused 1 kHz "
+                f"vehicle ticks (closed loop through the integer motor plant, command every {a.seg_len} ticks) + WT901 IMU "
+                f"update and 5-axis arm tick every {a.slow_period} ticks, IMU yaw -> vehicle as VD_task_main.cpp:368; "
+                f"chunks of {a.chunk} robots")
     return (f"configs[1]: {a.instances} mecanum vehicles/GPU x {a.ticks} fused 1 kHz ticks "
             f"(rx_callback + FK/odometry + 3x const-jerk target + IK + 4x FF_PI_D + current saturation), "
             f"closed loop through the integer motor plant, command every {a.seg_len} ticks, yaw every {a.yaw_period}")
@@ -116,11 +129,85 @@ class CpuArm:
                 f"streams and plant, {self.threads} host threads over instances")
 
 
+# ---- full tick on the CPU: per-module oracles composed exactly as tests/oracle_lib.full_tick ----
+_FULL_CACHE = {}
+
+
+def _full_cpu_worker(job):
+    """One host process = one slice of instances through vehicle + IMU + arm (the reference keeps its
+    IMU / arm objects in static storage, so parallelism is across processes, one per core)."""
+    kind, n, first, ticks, slow, seg_len, seed = job
+    import oracle_lib as ol
+    from roboken_fmskf_robot_controller_b200 import layout, streams
+
+    key = (n, first, ticks, slow, seg_len, seed)
+    if key not in _FULL_CACHE:
+        n_seg, n_slow = (ticks + seg_len - 1) // seg_len, (ticks + slow - 1) // slow
+        cmd = streams.vehicle_commands(n, n_seg, seed, first)
+        regs, have = streams.imu_samples(n, n_slow + 1, seed=seed, first=first, drop_every=64)
+        seq = layout.aos_to_soa(streams.arm_sequences(n, seed=seed, first=first, seq_id=1, max_len=32))
+        _FULL_CACHE.clear()
+        _FULL_CACHE[key] = (cmd, regs, have, seq)
+    cmd, regs, have, seq = _FULL_CACHE[key]
+    v = np.zeros(layout.VS_WORDS * n, dtype=np.uint32)
+    i = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
+    ar = np.zeros(layout.AS_WORDS * n, dtype=np.uint32)
+    tb = np.zeros(layout.ACMD_WORDS * n, dtype=np.uint32)
+    (ol.imu_port if kind == "port" else ol.imu_ref)(i, n, regs[:1], None, do_init=True)
+    t0 = time.perf_counter()
+    ol.arm_batch(kind, "init", ar, tb, n)
+    ol.arm_batch(kind, "push", ar, tb, n, seq=seq)
+    ol.full_tick(kind, n, ticks, slow, cmd, seg_len, regs[1:], have[1:], v, i, ar, tb)
+    return time.perf_counter() - t0
+
+
+class CpuArmFull:
+    def __init__(self, a):
+        import concurrent.futures as cf
+        import multiprocessing as mp
+
+        import oracle_lib as ol
+
+        self.a = a
+        self.threads = host_threads()
+        have = all(os.path.exists(os.path.join(ol.ORACLE, "_ref", f)) for f in ("libref_vdt.so", "libref_imu.so", "libref_arm.so"))
+        self.kind = "reference" if have else "port"
+        self.pool = cf.ProcessPoolExecutor(max_workers=self.threads, mp_context=mp.get_context("fork"))
+
+    def _run(self, n):
+        """n instances split over the worker processes; wall time of the whole pass."""
+        a, per = self.a, max(1, n // self.threads)
+        jobs = [("ref" if self.kind == "reference" else "port", per, w * per, a.ticks, a.slow_period, a.seg_len, 0x5EED)
+                for w in range(self.threads)]
+        t0 = time.perf_counter()
+        list(self.pool.map(_full_cpu_worker, jobs))
+        return time.perf_counter() - t0
+
+    def calibrate(self, step_budget_s):
+        n0 = 8 * self.threads
+        self._run(n0)
+        dt = self._run(n0)
+        n = int(n0 / dt * step_budget_s)
+        n = max(self.threads * 4, min(n, self.a.total))
+        return (n // self.threads) * self.threads
+
+    def sample_desc(self, n):
+        return (f"{n} of {self.a.total} robots x {self.a.ticks} vehicle ticks (+ IMU and arm every {self.a.slow_period}) per step, "
+                f"same seeded streams, {self.threads} host processes over instances (the reference keeps IMU/arm objects static)")
+
+    def close(self):
+        self.pool.shutdown()
+
+
+def make_cpu_arm(a):
+    return CpuArmFull(a) if a.workload == "full" else CpuArm(a)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    arm = CpuArm(a)
+    arm = make_cpu_arm(a)
     budget = min(2.0, 90.0 / max(1, a.steps + a.warmup))
     n = arm.calibrate(budget)
     for _ in range(a.warmup):
@@ -132,7 +219,8 @@ def run_reference(a):
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "strong" if a.workload == "full" else "weak",
+        "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "instances_per_step": n, "ticks_per_launch": a.ticks},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "sample": arm.sample_desc(n)},
@@ -195,6 +283,45 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"], "samples": 0}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# roofline denominators
+# ------------------------------------------------------------------------------------------
+def fp32_probes(lib, local_rank, dev, stream):
+    """FP32 peaks measured live (MEASURED_PEAKS.json has no FP32 entry): dense FFMA and dense
+    non-fused FMUL/FADD issue throughput, TFLOP/s, best of 3 after one warm-up."""
+    import torch
+
+    from roboken_fmskf_robot_controller_b200 import _cabi
+
+    sm, khz = C.c_int(), C.c_int()
+    _cabi.check(lib.rk_device_info(local_rank, C.byref(sm), C.byref(khz), None))
+    probe_out = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def probe(fused):
+        fl, best = C.c_double(), 0.0
+        for it in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _cabi.check(lib.rk_probe_fp32(fused, sm.value * 32, 4096, probe_out.data_ptr(), C.byref(fl), C.c_void_p(stream.cuda_stream)))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if it:
+                best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3))
+        return best / 1e12
+
+    return probe(1), probe(0), sm.value
+
+
+def hbm_peak_measured():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        try:
+            return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------
@@ -275,35 +402,8 @@ def run_ours(a):
     value = world * n * T * K / (ms * 1e-3)
     launches = K
 
-    # ---- FP32 peak probes (live; no FP32 entry in MEASURED_PEAKS.json) ---------------------
-    sm = C.c_int()
-    khz = C.c_int()
-    _cabi.check(lib.rk_device_info(local_rank, C.byref(sm), C.byref(khz), None))
-    probe_out = torch.zeros(4, dtype=torch.float32, device=dev)
-
-    def probe(fused):
-        fl = C.c_double()
-        best = 0.0
-        for it in range(4):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            _cabi.check(lib.rk_probe_fp32(fused, sm.value * 32, 4096, probe_out.data_ptr(), C.byref(fl), C.c_void_p(stream.cuda_stream)))
-            e1.record(stream)
-            torch.cuda.synchronize()
-            if it:
-                best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3))
-        return best / 1e12
-
-    ffma_tflops = probe(1)
-    issue_tflops = probe(0)
-
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-    if os.path.exists(peaks_path):
-        try:
-            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        except Exception:
-            pass
+    ffma_tflops, issue_tflops, sm_count = fp32_probes(lib, local_rank, dev, stream)
+    hbm_peak, hbm_src = hbm_peak_measured()
 
     launch_s = ms_local * 1e-3 / K
     achieved_tflops = FLOP_PER_TICK * n * T / launch_s / 1e12
@@ -321,7 +421,7 @@ def run_ours(a):
         "hbm": {"achieved": alg_bytes / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / launch_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": alg_bytes},
-        "sm_count": sm.value,
+        "sm_count": sm_count,
     }
     traffic_note = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_note):
@@ -433,10 +533,245 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------
+# GPU arm, workload "full" (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------
+FLOP_PER_FULL_STEP = 183 + 1 + (55 + 46) / 10.0  # vehicle + deg2rad + (IMU + arm) at 1/10 rate
+
+
+def run_ours_full(a):
+    import torch
+
+    import roboken_fmskf_robot_controller_b200 as rk
+    from roboken_fmskf_robot_controller_b200 import _cabi, layout, sharding, streams
+    from roboken_fmskf_robot_controller_b200.robot import RobotBatch
+
+    lib = rk.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    rank, local_rank, world = sharding.init("nccl")
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _cabi.check(lib.rk_set_device(local_rank))
+    K, W, T, slow = a.steps, a.warmup, a.ticks, a.slow_period
+    lo, hi = sharding.shard_range(a.total, rank, world)
+    n_rank = hi - lo
+    n = min(a.chunk, n_rank)
+    assert n_rank % n == 0, "--total / --gpus must be a multiple of --chunk"
+    n_chunks = n_rank // n
+    n_seg, n_slow = (T + a.seg_len - 1) // a.seg_len, (T + slow - 1) // slow
+    stream = torch.cuda.current_stream(dev)
+    clocks = ClockSampler(local_rank)
+
+    # ---- synthetic inputs of ONE chunk (every chunk replays them; states are per chunk) ----------
+    seed = 0x5EED
+    cmd_np = streams.vehicle_commands(n, n_seg, seed, lo)
+    # the IMU register stream is generated for 2^16 distinct robots and tiled over the chunk (hashing 1.7e9
+    # register words on the host would take minutes); commands and arm sequences are distinct per robot
+    uniq = min(n, 1 << 16)
+    assert n % uniq == 0
+    regs_np, have_np = streams.imu_samples(uniq, n_slow + 1, seed=seed, first=lo, drop_every=64)
+    regs_np, have_np = np.tile(regs_np, (1, 1, n // uniq)), np.tile(have_np, (1, n // uniq))
+    seq_np = streams.arm_sequences(n, seed=seed, first=lo, seq_id=1, max_len=32)
+    cmd_h = torch.from_numpy(cmd_np.view(np.int32).reshape(n_seg, n, 4)).pin_memory()
+    regs_h = torch.from_numpy(np.ascontiguousarray(regs_np[1:])).pin_memory()
+    have_h = torch.from_numpy(np.ascontiguousarray(have_np[1:])).pin_memory()
+    seq_h = torch.from_numpy(layout.aos_to_soa(seq_np).view(np.int32)).pin_memory()
+    goal_d = torch.zeros((n, 2), dtype=torch.float32, device=dev)
+    cmd_d, regs_d, have_d, seq_d = cmd_h.to(dev), regs_h.to(dev), have_h.to(dev), seq_h.to(dev)
+    yaw_d = torch.zeros((n_slow, n), dtype=torch.float32, device=dev)
+    ring = torch.zeros(layout.ACMD_WORDS * n, dtype=torch.int32, device=dev)  # shared: re-pushed before every chunk
+    boot = torch.from_numpy(np.ascontiguousarray(regs_np[:1])).to(dev)
+    chunks = []
+    for c in range(n_chunks):
+        rb = RobotBatch(n, dev, arm_cmdtab=ring)
+        rb.imu.update(boot, None, None, do_init=True)  # IMU_IF_WT901C::init() at boot
+        cost = torch.zeros(n, dtype=torch.float32, device=dev)
+        args = rb.make_args(T, slow, cmd=cmd_d, seg_len=a.seg_len, regs=regs_d, have_quat=have_d, yaw=yaw_d, goal=goal_d, cost=cost)
+        chunks.append((rb, cost, args))
+    torch.cuda.synchronize()
+
+    def one_pass(st=None):
+        """All chunks of this rank: arm bring-up + one command sequence pushed, then the fused tick."""
+        for rb, _, args in chunks:
+            rb.arm.mode_init(stream=st)
+            rb.arm.push_cmdseq(seq_d, stream=st)
+            rb.rollout_args(args, stream=st)
+
+    # ---- parity spot check of the exact bench launch (first pass of chunk 0) ---------------------
+    one_pass()
+    torch.cuda.synchronize()
+    spot = None
+    if rank == 0:
+        import oracle_lib as ol
+
+        rb0 = chunks[0][0]
+        idx = np.unique(np.concatenate([[0, n - 1], np.random.default_rng(0).integers(0, n, 46)]))
+        m = len(idx)
+        v, i_, ar, tb = (np.zeros(w * m, dtype=np.uint32) for w in (layout.VS_WORDS, layout.IS_WORDS, layout.AS_WORDS, layout.ACMD_WORDS))
+        sub = lambda x: np.ascontiguousarray(x[..., idx])
+        ol.imu_port(i_, m, sub(regs_np[:1]), None, do_init=True)
+        ol.arm_batch("port", "init", ar, tb, m)
+        ol.arm_batch("port", "push", ar, tb, m, seq=layout.aos_to_soa(seq_np[idx]))
+        ol.full_tick("port", m, T, slow, sub(cmd_np), a.seg_len, sub(regs_np[1:]), sub(have_np[1:]), v, i_, ar, tb, nthreads=min(8, host_threads()))
+        same = True
+        for got, exp, words in ((rb0.vehicle.state, v, layout.VS_WORDS), (rb0.imu.state, i_, layout.IS_WORDS), (rb0.arm.state, ar, layout.AS_WORDS)):
+            g = layout.soa_to_aos(got.cpu().numpy().view(np.uint32), n, words)[idx]
+            same &= np.array_equal(g, layout.soa_to_aos(exp, m, words))
+        spot = f"{m} sampled robots x {T} ticks (vehicle + IMU + arm state) {'bit-exact' if same else 'MISMATCH'} vs oracle"
+        if not same:
+            raise SystemExit("bench parity spot check failed: " + spot)
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------------
+    for _ in range(max(W - 1, 0)):
+        one_pass()
+    torch.cuda.synchronize()
+    sharding.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.start()
+    ev0.record(stream)
+    for _ in range(K):
+        one_pass()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks.pause()
+    sharding.barrier()
+    ms_local = ev0.elapsed_time(ev1)
+    ms = sharding.max_over_ranks(ms_local, dev)
+    value = a.total * T * K / (ms * 1e-3)
+    launches = K * n_chunks * 5  # mode_init, push, arm update, IMU update, vehicle rollout
+
+    # ---- dominant kernel alone (the vehicle rollout fed by the yaw stream), for the roofline -----
+    rb0 = chunks[0][0]
+    vargs = rb0.vehicle.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=cmd_d, seg_len=a.seg_len, yaw=yaw_d, yaw_period=slow,
+                                  goal=goal_d, cost=chunks[0][1])
+    rb0.vehicle.rollout_args(vargs)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(stream)
+    for _ in range(5):
+        rb0.vehicle.rollout_args(vargs)
+    k1.record(stream)
+    torch.cuda.synchronize()
+    launch_s = k0.elapsed_time(k1) * 1e-3 / 5
+    ffma_tflops, issue_tflops, sm_count = fp32_probes(lib, local_rank, dev, stream)
+    hbm_peak, hbm_src = hbm_peak_measured()
+    achieved = FLOP_PER_TICK * n * T / launch_s / 1e12
+    step_bytes = n_rank * (2 * (448 + 96 + 304) + n_seg * 16 + n_slow * (32 + 1 + 8) + 1040 * 2 + 8 + 4)
+    step_s = ms_local * 1e-3 / K
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
+        "peak_source": "rk_probe_fp32 FFMA chains, measured live in this run (no FP32 entry in MEASURED_PEAKS.json)",
+        "nonfused_issue_peak": issue_tflops, "frac_of_nonfused_issue_peak": achieved / issue_tflops,
+        "algorithmic_flop_per_tick": FLOP_PER_TICK, "kernel": "rk::vdt_rollout_fast_kernel (dominant kernel, timed alone on one chunk)",
+        "launch_ms": launch_s * 1e3, "traffic": None,
+        "step": {"algorithmic_flop_per_robot_step": FLOP_PER_FULL_STEP,
+                 "achieved_tflops": FLOP_PER_FULL_STEP * n_rank * T / step_s / 1e12,
+                 "frac_of_ffma_peak": FLOP_PER_FULL_STEP * n_rank * T / step_s / 1e12 / ffma_tflops,
+                 "algorithmic_bytes": step_bytes, "hbm_gbs": step_bytes / step_s / 1e9,
+                 "hbm_frac": step_bytes / step_s / 1e9 / hbm_peak, "hbm_peak_source": hbm_src},
+        "sm_count": sm_count,
+    }
+
+    # ---- e2e: host tables in, costs out, through rk_tick_rollout ----------------------------------
+    e2e = None
+    if not a.no_e2e:
+        copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        bufs = []
+        for b in range(2):
+            d = dict(cmd=torch.empty_like(cmd_d), regs=torch.empty_like(regs_d), have=torch.empty_like(have_d),
+                     seq=torch.empty_like(seq_d), cost=torch.zeros(n, dtype=torch.float32, device=dev),
+                     cost_h=torch.empty(n, dtype=torch.float32).pin_memory(), up=torch.cuda.Event(), done=torch.cuda.Event(),
+                     down=torch.cuda.Event())
+            bufs.append(d)
+        h2d = n_chunks * 4 * (cmd_h.numel() + seq_h.numel()) + n_chunks * (2 * regs_h.numel() + have_h.numel())
+        d2h = n_chunks * n * 4
+        argcache = {}
+
+        def e2e_pass(s):
+            for c, (rb, _, _) in enumerate(chunks):
+                b = bufs[(s * n_chunks + c) % 2]
+                with torch.cuda.stream(copy_s):
+                    copy_s.wait_event(b["done"])
+                    b["cmd"].copy_(cmd_h, non_blocking=True)
+                    b["regs"].copy_(regs_h, non_blocking=True)
+                    b["have"].copy_(have_h, non_blocking=True)
+                    b["seq"].copy_(seq_h, non_blocking=True)
+                    b["up"].record(copy_s)
+                with torch.cuda.stream(comp_s):
+                    comp_s.wait_event(b["up"])
+                    comp_s.wait_event(b["down"])
+                    rb.vehicle.state.zero_()  # every rollout starts from the power-on vehicle
+                    rb.arm.mode_init(stream=comp_s)
+                    rb.arm.push_cmdseq(b["seq"], stream=comp_s)
+                    key = (c, (s * n_chunks + c) % 2)
+                    if key not in argcache:
+                        argcache[key] = rb.make_args(T, slow, cmd=b["cmd"], seg_len=a.seg_len, regs=b["regs"], have_quat=b["have"],
+                                                     yaw=yaw_d, goal=goal_d, cost=b["cost"])
+                    rb.rollout_args(argcache[key], stream=comp_s)
+                    b["done"].record(comp_s)
+                with torch.cuda.stream(copy_s):
+                    copy_s.wait_event(b["done"])
+                    b["cost_h"].copy_(b["cost"], non_blocking=True)
+                    b["down"].record(copy_s)
+
+        for s in range(2):
+            e2e_pass(s)
+        torch.cuda.synchronize()
+        sharding.barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.start()
+        t0e.record(stream)
+        copy_s.wait_stream(stream)
+        comp_s.wait_stream(stream)
+        for s in range(K):
+            e2e_pass(s)
+        stream.wait_stream(copy_s)
+        stream.wait_stream(comp_s)
+        t1e.record(stream)
+        torch.cuda.synchronize()
+        clocks.pause()
+        sharding.barrier()
+        ms_e = sharding.max_over_ranks(t0e.elapsed_time(t1e), dev)
+        e2e = {"value": a.total * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e / K,
+               "path": "rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout via ctypes per chunk; pinned host command, IMU-register "
+                       "and arm-sequence tables H2D, vehicle reset to power-on, cost vector D2H, double-buffered on a copy stream"}
+
+    clk = clocks.result()
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        arm = CpuArmFull(a)
+        nc = arm.calibrate(a.cpu_seconds / 3.0)
+        t = min(arm._run(nc) for _ in range(2))
+        cpu = {"value": nc * T / t, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "sample": arm.sample_desc(nc)}
+        arm.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "robots_total": a.total, "robots_per_gpu": n_rank, "chunk": n, "ticks_per_launch": T,
+                       "l2": f"inputs larger than L2: {(cmd_h.numel() * 4 + regs_h.numel() * 2 + seq_h.numel() * 4) >> 20} MiB tables + "
+                             f"{n * 848 >> 20} MiB state per chunk vs 126 MB L2",
+                       "parity_spot_check": spot},
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "full":
+        run_ours_full(a)
     else:
         run_ours(a)
 

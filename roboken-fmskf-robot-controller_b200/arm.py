@@ -15,7 +15,9 @@ PROCESSING, DONE, NO_DATA = 0, 1, 99  # ADTModePositioningSeq::CmdStatus  AD_mod
 
 
 class ArmBatch:
-    def __init__(self, n, device="cuda:0", params=None):
+    def __init__(self, n, device="cuda:0", params=None, cmdtab=None):
+        """cmdtab: an existing command-ring tensor to use instead of allocating one (rollout drivers
+        that re-push every pass share one ring between batches they run back to back)."""
         self.lib = _cabi.load()
         self.n = int(n)
         self.device = torch.device(device)
@@ -24,7 +26,10 @@ class ArmBatch:
         assert self.lib.rk_adt_state_words() == layout.AS_WORDS
         with torch.cuda.device(self.dev_index):
             self.state = torch.zeros(layout.AS_WORDS * self.n, dtype=torch.int32, device=self.device)
-            self.cmdtab = torch.zeros(layout.ACMD_WORDS * self.n, dtype=torch.int32, device=self.device)
+            if cmdtab is None:
+                cmdtab = torch.zeros(layout.ACMD_WORDS * self.n, dtype=torch.int32, device=self.device)
+            assert cmdtab.is_cuda and cmdtab.numel() == layout.ACMD_WORDS * self.n and cmdtab.element_size() == 4
+            self.cmdtab = cmdtab
 
     def _st(self, stream):
         _cabi.check(self.lib.rk_set_device(self.dev_index))

@@ -12,13 +12,13 @@ from .vehicle import VehicleBatch
 
 
 class RobotBatch:
-    def __init__(self, n, device="cuda:0", vdt_params=None, adt_params=None):
+    def __init__(self, n, device="cuda:0", vdt_params=None, adt_params=None, arm_cmdtab=None):
         self.lib = _cabi.load()
         self.n = int(n)
         self.device = torch.device(device)
         self.vehicle = VehicleBatch(n, device, vdt_params)
         self.imu = ImuBatch(n, device)
-        self.arm = ArmBatch(n, device, adt_params)
+        self.arm = ArmBatch(n, device, adt_params, cmdtab=arm_cmdtab)
         self.dev_index = self.vehicle.dev_index
         self._keep = []
 
