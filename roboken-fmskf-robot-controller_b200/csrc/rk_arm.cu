@@ -8,9 +8,10 @@
 // the kernel is issue/latency bound, not bandwidth bound.
 #include <string.h>
 
-#include "rk_common.cuh"
+#include "rk_vehicle_fast.cuh" // div_const()
 
 namespace rk {
+int div_const_exact(float c); // rk_exact.cu: 2 = exact for all x, 1 = for x == 0 or |x| >= 2^-40, 0 = no
 
 // (int32_t)(float) as the x86 build of the firmware source performs it: cvttss2si, which
 // returns INT_MIN for NaN / out of range (F2I.TRUNC saturates instead).
@@ -26,8 +27,13 @@ RK_DEV int ics_degPos100(int deg) {
   return (deg * 2963) / 10000 + 7500;
 }
 RK_DEV int ics_posDeg100(int pos) {
-  const long long a   = (long long)pos - 7500;
-  const int       deg = (int)((a * 1000) / 296);
+  int deg;
+  if(pos >= -2000000 && pos <= 2000000) { // every position a 14-bit ICS frame can carry: 32-bit arithmetic
+    deg = ((pos - 7500) * 1000) / 296;
+  } else { // arbitrary state words: the reference's 64-bit `long` arithmetic
+    const long long a = (long long)pos - 7500;
+    deg               = (int)((a * 1000) / 296);
+  }
   if(deg > 18000) return 0x7FFF;
   if(deg < -18000) return -0x7FFF;
   return deg;
@@ -114,177 +120,334 @@ RK_DEV constexpr int axis_joint(int ax) { return ax == 0 ? RK_AJ_Y0 : ax == 1 ? 
 // JointBase::get_tgt_deg  AD_joint_base.hpp:47
 RK_DEV float get_tgt_deg(const Arm &a, int ax) { return fsub(a.j[axis_joint(ax)].raw_tgt, a.j[axis_joint(ax)].ofs); }
 
-// ADTModePositioningSeq::update   AD_mode_positioning_seq.cpp:13-117
-RK_DEV void mode_update(Arm &a, const rk_adt_params_t &p, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
-  uint32_t state = a.fsm & 0xFFu;
-  if(state == RK_ASTATE_STANDBY) { // exec_standby :24-42
-    a.fsm |= RK_AS_FSM_IS_COMP;
+RK_DEV uint32_t bldc_id_byte(uint32_t id) { return (id & 0xFFu) | ((id & 0x8000u) ? 0x80u : 0u); }
+
+// ---------------------------------------------------------------------------------------------
+// K fused ticks.  Only the words a tick reads or writes live in registers (ArmLoop); words that
+// are constant during update() -- unused offsets / limits / measured angles, the reserved
+// torque-control block -- stay in HBM and are merged back plane by plane at the end.  The tick
+// is straight-line predicated code apart from the two rare FSM transitions, so ptxas can
+// interleave its six independent chains (mode, MG, 3 x MyBldc, ICS) and their long-latency
+// conversions (F2I / I2FP ~12 cycles each).  DIVC: the MG velocity limit divides by a launch
+// constant through div_const() when rk_exact.cu has proven it exact for every finite input.
+// ---------------------------------------------------------------------------------------------
+struct ArmLoop {
+  uint32_t state, fsmflags, exec, head, cmd_idx;
+  int32_t  cnt, cyc;
+  uint32_t total_ms, now_dt;
+  float    now_tgt[5], move[5], dfv_p, dfv_r;
+  float    ofs[5], ofs_dfl, ofs_dfr; // offsets: mode axes J0..J4, DF_Left, DF_Right
+  float    tgt[5], tgt_dfl, tgt_dfr; // fl_raw_tgt_deg of the same
+  float    cl_dfl, cl_dfr, cl_p3;    // fl_curlim_A of the three MyBldc joints
+  float    now_y0, mg_pre;
+  uint32_t ics_pos, ics_servo, mg_tx0, mg_tx1, mg_valid;
+  uint32_t bl0[3], bl1[3], bl2[3];   // txmsg word 0, word 1, u32_txcmdid per MyBldc joint
+  bool     mg_prev, bl_prev[3];
+  // command-ring prefetch: the lengths of the four slots (8 bits each) and the waypoint the FSM
+  // will ask for next, fetched one segment ahead so its HBM latency never stalls a tick.  The
+  // ring is read-only while update() runs (push_cmdseq is a separate call), so reading early
+  // returns the same words.  Two register sets alternate (sel = the set holding the prefetched
+  // waypoint): a set is only ever written by a predicated load and read by a select, so no copy
+  // has to wait for a load in flight.
+  uint32_t lens, pf_key; // pf_key = slot * 32 + index of the prefetched waypoint, or ~0u
+  uint4    pa0, pb0;     // {u32_dt_ms, fl_tgt_pos_deg[0..2]}
+  uint2    pa1, pb1;     // fl_tgt_pos_deg[3..4]
+  bool     sel;
+};
+
+RK_DEV uint32_t ring_len(const ArmLoop &a, uint32_t slot) { return (a.lens >> (8 * (slot % RK_ACMD_SLOTS))) & 0xFFu; }
+RK_DEV uint32_t ring_key(uint32_t slot, uint32_t idx) { return (slot % RK_ACMD_SLOTS) * RK_ACMD_MAX_LEN + (idx % RK_ACMD_MAX_LEN); }
+
+// `if(pred) dst = *addr` as ONE predicated load into the registers dst already lives in.  The two
+// register sets use different load flavours (read-only path / L2-coherent path): ptxas otherwise
+// merges the complementary-predicate pair into one load plus moves that wait for it.
+template <bool NC> RK_DEV void ldg_if(uint4 &d, const uint4 *addr, bool pred) {
+  if(NC)
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4]; }"
+                 : "+r"(d.x), "+r"(d.y), "+r"(d.z), "+r"(d.w) : "l"(addr), "r"((uint32_t)pred));
+  else
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %5, 0; @p ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4]; }"
+                 : "+r"(d.x), "+r"(d.y), "+r"(d.z), "+r"(d.w) : "l"(addr), "r"((uint32_t)pred));
+}
+template <bool NC> RK_DEV void ldg_if(uint2 &d, const uint4 *addr, bool pred) {
+  if(NC)
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p ld.global.nc.v2.u32 {%0, %1}, [%2]; }" : "+r"(d.x), "+r"(d.y) : "l"(addr), "r"((uint32_t)pred));
+  else
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p ld.global.cg.v2.u32 {%0, %1}, [%2]; }" : "+r"(d.x), "+r"(d.y) : "l"(addr), "r"((uint32_t)pred));
+}
+// waypoint (slot, idx) -> register set B when `into_b`, else set A
+RK_DEV void ring_fetch(ArmLoop &a, const uint4 *__restrict__ tab, int64_t n, int64_t i, uint32_t slot, uint32_t idx, bool into_b) {
+  const int    pl = (int)(slot % RK_ACMD_SLOTS) * (RK_ACMD_SLOT_WORDS / 4) + 1 + 2 * (int)(idx % RK_ACMD_MAX_LEN);
+  const uint4 *p0 = &tab[(int64_t)pl * n + i], *p1 = &tab[(int64_t)(pl + 1) * n + i];
+  ldg_if<true>(a.pa0, p0, !into_b), ldg_if<true>(a.pa1, p1, !into_b);
+  ldg_if<false>(a.pb0, p0, into_b), ldg_if<false>(a.pb1, p1, into_b);
+}
+// what exec_move_start will read after the segment (slot, idx) that is starting now: the next waypoint
+// of the sequence, else waypoint 0 of the next queued sequence, else (nothing to come) the same entry
+RK_DEV void ring_next(const ArmLoop &a, uint32_t slot, uint32_t idx, uint32_t &nslot, uint32_t &nidx) {
+  const bool more = idx + 1 < ring_len(a, slot) && idx + 1 < RK_ACMD_MAX_LEN;
+  const bool next = !more && slot != a.head;
+  uint32_t   nx   = (slot + 1) & 0xFFFFu;
+  nx              = (nx >= RK_ACMD_SLOTS) ? 0u : nx;
+  nslot = next ? nx : slot, nidx = more ? idx + 1 : (next ? 0u : idx);
+}
+
+RK_DEV uint4 ldp(const uint4 *st, int64_t n, int64_t i, int word) { return ld_plane(st, n, word / 4, i); }
+
+RK_DEV void loop_load(const uint4 *st, int64_t n, int64_t i, ArmLoop &a, uint32_t &jflags) {
+  const uint4 f0 = ldp(st, n, i, RK_AS_FSM), f1 = ldp(st, n, i, RK_AS_CYCLE);
+  a.state = f0.x & 0xFFu, a.fsmflags = f0.x & ~0xFFu, a.exec = f0.y & 0xFFFFu, a.head = f0.y >> 16, a.cmd_idx = f0.z;
+  a.cnt = (int32_t)f0.w, a.cyc = (int32_t)f1.x, a.total_ms = f1.y, a.now_dt = f1.z;
+  const uint4 t0 = ldp(st, n, i, RK_AS_NOW_TGT), t1 = ldp(st, n, i, 12), t2 = ldp(st, n, i, 16);
+  a.now_tgt[0] = u2f(t0.x), a.now_tgt[1] = u2f(t0.y), a.now_tgt[2] = u2f(t0.z), a.now_tgt[3] = u2f(t0.w), a.now_tgt[4] = u2f(t1.x);
+  a.move[0] = u2f(t1.y), a.move[1] = u2f(t1.z), a.move[2] = u2f(t1.w), a.move[3] = u2f(t2.x), a.move[4] = u2f(t2.y);
+  a.dfv_p = u2f(t2.z), a.dfv_r = u2f(t2.w);
+#pragma unroll
+  for(int ax = 0; ax < 5; ax++) {
+    const uint4 j = ldp(st, n, i, RK_AS_JOINT0 + 4 * axis_joint(ax));
+    a.ofs[ax] = u2f(j.x), a.tgt[ax] = u2f(j.y);
+    if(ax == 0) a.now_y0 = u2f(j.w);
+    if(ax == 4) a.cl_p3 = u2f(j.z);
+  }
+  const uint4 l = ldp(st, n, i, RK_AS_JOINT0 + 4 * RK_AJ_DFL), r = ldp(st, n, i, RK_AS_JOINT0 + 4 * RK_AJ_DFR);
+  a.ofs_dfl = u2f(l.x), a.tgt_dfl = u2f(l.y), a.cl_dfl = u2f(l.z);
+  a.ofs_dfr = u2f(r.x), a.tgt_dfr = u2f(r.y), a.cl_dfr = u2f(r.z);
+  const uint4 m = ldp(st, n, i, RK_AS_JFLAGS), x = ldp(st, n, i, RK_AS_MG_TX);
+  jflags = m.x, a.mg_pre = u2f(m.y), a.ics_pos = m.z, a.ics_servo = m.w;
+  a.mg_tx0 = x.x, a.mg_tx1 = x.y, a.mg_valid = x.z;
+#pragma unroll
+  for(int s = 0; s < 3; s++) {
+    const uint4 b = ldp(st, n, i, RK_AS_BLDC_TX0 + 4 * s);
+    a.bl0[s] = b.x, a.bl1[s] = b.y, a.bl2[s] = b.z;
+  }
+  a.lens = 0u, a.pf_key = 0xFFFFFFFFu, a.sel = false;
+  a.pa0 = make_uint4(0u, 0u, 0u, 0u), a.pb0 = a.pa0, a.pa1 = make_uint2(0u, 0u), a.pb1 = a.pa1;
+  a.mg_prev    = ((jflags >> (4 * RK_AJ_P1)) & RK_AJF_TORQUE_PREV) != 0;
+  a.bl_prev[0] = ((jflags >> (4 * RK_AJ_DFL)) & RK_AJF_TORQUE_PREV) != 0;
+  a.bl_prev[1] = ((jflags >> (4 * RK_AJ_DFR)) & RK_AJF_TORQUE_PREV) != 0;
+  a.bl_prev[2] = ((jflags >> (4 * RK_AJ_P3)) & RK_AJF_TORQUE_PREV) != 0;
+}
+
+RK_DEV void loop_store(uint4 *st, int64_t n, int64_t i, const ArmLoop &a, uint32_t jflags, bool ticked) {
+  st_plane(st, n, 0, i, make_uint4(a.state | a.fsmflags, a.exec | (a.head << 16), a.cmd_idx, (uint32_t)a.cnt));
+  uint4 f1 = ldp(st, n, i, RK_AS_CYCLE);
+  f1.x = (uint32_t)a.cyc, f1.y = a.total_ms, f1.z = a.now_dt;
+  st_plane(st, n, 1, i, f1);
+  st_plane(st, n, 2, i, make_uint4(f2u(a.now_tgt[0]), f2u(a.now_tgt[1]), f2u(a.now_tgt[2]), f2u(a.now_tgt[3])));
+  st_plane(st, n, 3, i, make_uint4(f2u(a.now_tgt[4]), f2u(a.move[0]), f2u(a.move[1]), f2u(a.move[2])));
+  st_plane(st, n, 4, i, make_uint4(f2u(a.move[3]), f2u(a.move[4]), f2u(a.dfv_p), f2u(a.dfv_r)));
+#pragma unroll
+  for(int ax = 0; ax < 5; ax++) {
+    const int pl = (RK_AS_JOINT0 + 4 * axis_joint(ax)) / 4;
+    uint4     j  = ld_plane(st, n, pl, i);
+    j.y          = f2u(a.tgt[ax]);
+    if(ax == 0) j.w = f2u(a.now_y0);
+    st_plane(st, n, pl, i, j);
+  }
+  {
+    const int pl = (RK_AS_JOINT0 + 4 * RK_AJ_DFL) / 4;
+    uint4     l = ld_plane(st, n, pl, i), r = ld_plane(st, n, pl + 1, i);
+    l.y = f2u(a.tgt_dfl), r.y = f2u(a.tgt_dfr);
+    st_plane(st, n, pl, i, l);
+    st_plane(st, n, pl + 1, i, r);
+  }
+  if(ticked) { // is_torque_on_prev = is_torque_on after any tick
+    const uint32_t prevbits = ((uint32_t)RK_AJF_TORQUE_PREV << (4 * RK_AJ_P1)) | ((uint32_t)RK_AJF_TORQUE_PREV << (4 * RK_AJ_DFL)) |
+                              ((uint32_t)RK_AJF_TORQUE_PREV << (4 * RK_AJ_DFR)) | ((uint32_t)RK_AJF_TORQUE_PREV << (4 * RK_AJ_P3));
+    const uint32_t onbits   = ((uint32_t)RK_AJF_TORQUE_ON << (4 * RK_AJ_P1)) | ((uint32_t)RK_AJF_TORQUE_ON << (4 * RK_AJ_DFL)) |
+                            ((uint32_t)RK_AJF_TORQUE_ON << (4 * RK_AJ_DFR)) | ((uint32_t)RK_AJF_TORQUE_ON << (4 * RK_AJ_P3));
+    jflags = (jflags & ~prevbits) | ((jflags & onbits) << 2); // TORQUE_PREV = TORQUE_ON << 2
+  }
+  st_plane(st, n, RK_AS_JFLAGS / 4, i, make_uint4(jflags, f2u(a.mg_pre), a.ics_pos, a.ics_servo));
+  uint4 x = ldp(st, n, i, RK_AS_MG_TX);
+  x.x = a.mg_tx0, x.y = a.mg_tx1, x.z = a.mg_valid;
+  st_plane(st, n, RK_AS_MG_TX / 4, i, x);
+#pragma unroll
+  for(int s = 0; s < 3; s++) st_plane(st, n, (RK_AS_BLDC_TX0 + 4 * s) / 4, i, make_uint4(a.bl0[s], a.bl1[s], a.bl2[s], 1u));
+}
+
+struct ArmConsts { // loop invariants derived from params + flags once per launch
+  float    gear_p2, gear_r0, gear_dir[3], dir_y0, mg_ctrl_time, mg_rcp;
+  uint32_t bl_ms[3];
+  bool     y0_conn, y0_on, mg_pos, mg_on, bl_on[3];
+};
+
+// exec_standby + exec_move_start: the rare, divergent part of ADTModePositioningSeq::update
+RK_DEV void loop_fsm_transitions(ArmLoop &a, const rk_adt_params_t &p, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
+  if(a.state == RK_ASTATE_STANDBY) { // exec_standby :24-42
+    a.fsmflags |= RK_AS_FSM_IS_COMP;
     if(a.exec != a.head) {
       a.exec = (a.exec + 1) & 0xFFFFu;
       a.exec = (a.exec >= RK_ACMD_SLOTS) ? 0u : a.exec;
       a.cmd_idx  = 0;
       a.total_ms = 0;
-      state      = RK_ASTATE_MOVE_START;
-      a.fsm &= ~RK_AS_FSM_FIRSTCALL;
+      a.state    = RK_ASTATE_MOVE_START;
+      a.fsmflags &= ~RK_AS_FSM_FIRSTCALL;
     }
   }
-  if(state == RK_ASTATE_MOVE_START) { // exec_move_start :48-83
-    const int      base_pl = (int)(a.exec % RK_ACMD_SLOTS) * (RK_ACMD_SLOT_WORDS / 4);
-    const uint32_t len     = __ldg(&tab[(int64_t)base_pl * n + i]).y & 0xFFu;
-    const uint32_t idx     = a.cmd_idx & 0xFFu;
+  if(a.state == RK_ASTATE_MOVE_START) { // exec_move_start :48-83
+    const uint32_t len = ring_len(a, a.exec);
+    const uint32_t idx = a.cmd_idx & 0xFFu;
     if(idx >= len) {
-      state = RK_ASTATE_STANDBY;
+      a.state = RK_ASTATE_STANDBY;
     } else {
-      // now_cmd_ = cmd_seq_[exec].cmd_seq[idx]: one waypoint = two 128-bit planes
-      const int   pl = base_pl + 1 + 2 * (int)(idx % RK_ACMD_MAX_LEN);
-      const uint4 w0 = __ldg(&tab[(int64_t)pl * n + i]);
-      const uint4 w1 = __ldg(&tab[(int64_t)(pl + 1) * n + i]);
+      // now_cmd_ = cmd_seq_[exec].cmd_seq[idx]: one waypoint = two 128-bit planes, normally already prefetched
+      if(a.pf_key != ring_key(a.exec, idx)) ring_fetch(a, tab, n, i, a.exec, idx, a.sel);
+      const uint4 w0 = a.sel ? a.pb0 : a.pa0;
+      const uint2 w1 = a.sel ? a.pb1 : a.pa1;
+      uint32_t    ns, ni;
+      ring_next(a, a.exec, idx, ns, ni);
+      a.sel = !a.sel;
+      ring_fetch(a, tab, n, i, ns, ni, a.sel);
+      a.pf_key = ring_key(ns, ni);
       a.now_dt       = w0.x;
       a.now_tgt[0] = u2f(w0.y), a.now_tgt[1] = u2f(w0.z), a.now_tgt[2] = u2f(w0.w), a.now_tgt[3] = u2f(w1.x), a.now_tgt[4] = u2f(w1.y);
-      int32_t cnt = f2i_x86(fdiv(fmul(__uint2float_rn(a.now_dt - a.total_ms), 0.001f), p.cycle_time_s));
-      cnt         = (cnt <= 0) ? 1 : cnt;
-      const float fc = (float)cnt;
+      // a zero numerator (dt equal to the previous one; an axis that does not move) would send the
+      // IEEE division down its slow path: 0 / c = 0 with the numerator's sign for c > 0
+      const float span = fmul(__uint2float_rn(a.now_dt - a.total_ms), 0.001f);
+      int32_t     cnt  = f2i_x86((span == 0.0f && p.cycle_time_s > 0.0f) ? span : fdiv(span, p.cycle_time_s));
+      cnt              = (cnt <= 0) ? 1 : cnt;
+      const float fc   = (float)cnt; // >= 1
 #pragma unroll
-      for(int k = 0; k < 5; k++) a.move_deg[k] = fdiv(fsub(a.now_tgt[k], get_tgt_deg(a, k)), fc);
-      a.move_cnt = cnt;
+      for(int k = 0; k < 5; k++) {
+        const float d = fsub(a.now_tgt[k], fsub(a.tgt[k], a.ofs[k]));
+        a.move[k]     = (d == 0.0f) ? d : fdiv(d, fc);
+      }
+      a.cnt      = cnt;
       a.total_ms = a.now_dt;
-      a.cycle    = 0;
-      a.fsm &= ~RK_AS_FSM_IS_COMP;
-      state = RK_ASTATE_MOVING;
+      a.cyc      = 0;
+      a.fsmflags &= ~RK_AS_FSM_IS_COMP;
+      a.state = RK_ASTATE_MOVING;
     }
   }
-  if(state == RK_ASTATE_MOVING) { // exec_moving :89-117
-    const float rem = (float)(a.move_cnt - a.cycle);
-    float       raw[5];
+}
+
+template <int DIVC>
+RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
+  if(a.state != RK_ASTATE_MOVING) loop_fsm_transitions(a, p, tab, n, i);
+  // ---- exec_moving :89-117 + JointBase / DfGear set_tgt_ang_deg, predicated on `moving`
+  const bool  moving = a.state == RK_ASTATE_MOVING;
+  const float rem    = (float)(a.cnt - a.cyc);
+  float       raw[5];
 #pragma unroll
-    for(int k = 0; k < 5; k++) {
-      // JointBase::set_tgt_ang_deg :42 (and the first line of the DfGear overrides)
-      raw[k]                        = fadd(fsub(a.now_tgt[k], fmul(a.move_deg[k], rem)), a.j[axis_joint(k)].ofs);
-      a.j[axis_joint(k)].raw_tgt = raw[k];
-    }
-    // JointDfGearPitch/Roll::set_tgt_ang_deg -> JointDfGearVirtual::set_P/R_tgt_ang_deg
-    // (AD_joint_dfgear.hpp:19-29,60-63,93-96): the Pitch call's left/right targets are overwritten
-    // by the Roll call that follows it in the same tick, so only the final pair is formed.
-    a.dfv_p                 = fmul(raw[2], p.gear_ratio[RK_AJ_P2]);
-    a.dfv_r                 = fmul(raw[3], p.gear_ratio[RK_AJ_R0]);
-    a.j[RK_AJ_DFL].raw_tgt = fadd(fsub(a.dfv_p, a.dfv_r), a.j[RK_AJ_DFL].ofs);
-    a.j[RK_AJ_DFR].raw_tgt = fadd(-fadd(a.dfv_p, a.dfv_r), a.j[RK_AJ_DFR].ofs);
-    if(a.move_cnt <= a.cycle) {
-      a.cmd_idx = (a.cmd_idx + 1) & 0xFFu;
-      state     = RK_ASTATE_MOVE_START;
-    } else {
-      a.cycle++;
-    }
+  for(int k = 0; k < 5; k++) {
+    raw[k]   = fadd(fsub(a.now_tgt[k], fmul(a.move[k], rem)), a.ofs[k]);
+    a.tgt[k] = moving ? raw[k] : a.tgt[k];
   }
-  a.fsm = (a.fsm & ~0xFFu) | state;
-}
-
-RK_DEV uint32_t jflag(const Arm &a, int k) { return (a.jflags >> (4 * k)) & 0xFu; }
-RK_DEV void     set_prev(Arm &a, int k, bool on) {
-  a.jflags = (a.jflags & ~((uint32_t)RK_AJF_TORQUE_PREV << (4 * k))) | ((on ? (uint32_t)RK_AJF_TORQUE_PREV : 0u) << (4 * k));
-}
-
-// JointMgServo::update -> subproc_posctrl   AD_joint_mg_servo.cpp:50-73,136-149.  The
-// torque-control branches (:104-134; joint not initialised or torque off) are not part of this
-// path: no MG frame is produced there (valid word = 0).
-RK_DEV void mg_update(Arm &a, const rk_adt_params_t &p) {
-  const uint32_t b  = jflag(a, RK_AJ_P1);
-  const bool     on = (b & RK_AJF_TORQUE_ON) != 0, prev = (b & RK_AJF_TORQUE_PREV) != 0, ini = (b & RK_AJF_INITIALIZED) != 0;
-  const float    tgt = a.j[RK_AJ_P1].raw_tgt;
-  a.mg_tx[2]         = 0;
-  if(prev && !on) {
-  } else if(!ini && on) {
-  } else if(on) {
-    const float    v  = fabsf(fmul(fdiv(fsub(tgt, a.mg_pre), p.ctrl_time_s[RK_AJ_P1]), -10.0f));
+  {
+    const float P = fmul(raw[2], c.gear_p2), R = fmul(raw[3], c.gear_r0);
+    a.dfv_p = moving ? P : a.dfv_p, a.dfv_r = moving ? R : a.dfv_r;
+    a.tgt_dfl = moving ? fadd(fsub(P, R), a.ofs_dfl) : a.tgt_dfl;
+    a.tgt_dfr = moving ? fadd(-fadd(P, R), a.ofs_dfr) : a.tgt_dfr;
+    const bool fin = moving && (a.cnt <= a.cyc);
+    a.cmd_idx      = fin ? ((a.cmd_idx + 1) & 0xFFu) : a.cmd_idx;
+    a.state        = fin ? (uint32_t)RK_ASTATE_MOVE_START : a.state;
+    a.cyc          = (moving && !fin) ? a.cyc + 1 : a.cyc;
+  }
+  // ---- JointMgServo::update -> subproc_posctrl  AD_joint_mg_servo.cpp:50-73,136-149
+  {
+    const float tgt = a.tgt[1];
+    const float d   = fsub(tgt, a.mg_pre);
+    float q;
+    if(DIVC == 2) {
+      q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
+    } else if(DIVC == 1) { // proven for zero and |d| >= 2^-40; anything tinier takes the IEEE division
+      if(d == 0.0f || fabsf(d) >= 9.094947017729282e-13f) q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
+      else q = fdiv(d, c.mg_ctrl_time);
+    } else { // 0 / c = 0 with the numerator's sign for c > 0; keeps an idle joint off the division's slow path
+      q = (d == 0.0f && c.mg_ctrl_time > 0.0f) ? d : fdiv(d, c.mg_ctrl_time);
+    }
+    const float v   = fabsf(fmul(q, -10.0f));
     const uint32_t vl = (uint32_t)f2i_x86((v > 1800.0f) ? 1800.0f : v) & 0xFFFFu;
-    a.mg_tx[0]        = 0xA4u | (vl << 16);
-    a.mg_tx[1]        = (uint32_t)f2i_x86(fmul(tgt, -100.0f * 10.0f));
-    a.mg_tx[2]        = 1;
+    const uint32_t w1 = (uint32_t)f2i_x86(fmul(tgt, -100.0f * 10.0f));
+    a.mg_tx0   = c.mg_pos ? (0xA4u | (vl << 16)) : a.mg_tx0;
+    a.mg_tx1   = c.mg_pos ? w1 : a.mg_tx1;
+    a.mg_valid = c.mg_pos ? 1u : 0u;
+    a.mg_pre   = tgt;
   }
-  set_prev(a, RK_AJ_P1, on);
-  a.mg_pre = tgt;
-}
-
-// JointMyBldcServo::update   AD_joint_mybldc_servo.cpp:7-36 ; slot 0..2 = DF_Left, DF_Right, P3
-template <int SLOT>
-RK_DEV void bldc_update(Arm &a, const rk_adt_params_t &p) {
-  constexpr int  k  = SLOT == 0 ? RK_AJ_DFL : SLOT == 1 ? RK_AJ_DFR : RK_AJ_P3;
-  const uint32_t b  = jflag(a, k);
-  const bool     on = (b & RK_AJF_TORQUE_ON) != 0, prev = (b & RK_AJF_TORQUE_PREV) != 0;
-  uint32_t      *q  = a.bldc[SLOT];
-  if(!on) {
-    q[0] = 0, q[1] = 0, q[2] = 0x8002u;
-  } else if(!prev) {
-    q[0] = 0, q[1] = 0, q[2] = 0x8001u;
-  } else {
-    const int32_t  ang = f2i_x86(fmul(fmul(fmul(a.j[k].raw_tgt, p.gear_ratio[k]), p.motor_dir[k]), 65536.0f));
-    const uint32_t ms  = (uint32_t)f2i_x86(fmul(p.ctrl_time_s[k], 1000.0f)) & 0xFFFFu;
-    const uint32_t cl  = (uint32_t)f2i_x86(fmul(a.j[k].curlim, 256.0f)) & 0xFFFFu;
-    q[0] = (uint32_t)ang, q[1] = ms | (cl << 16), q[2] = 0x8010u;
+  // ---- JointMyBldcServo::update x3  AD_joint_mybldc_servo.cpp:7-36
+#pragma unroll
+  for(int s = 0; s < 3; s++) {
+    const float tg = s == 0 ? a.tgt_dfl : s == 1 ? a.tgt_dfr : a.tgt[4];
+    const float cl = s == 0 ? a.cl_dfl : s == 1 ? a.cl_dfr : a.cl_p3;
+    const int32_t  ang   = f2i_x86(fmul(fmul(fmul(tg, p.gear_ratio[s == 0 ? RK_AJ_DFL : s == 1 ? RK_AJ_DFR : RK_AJ_P3]),
+                                             p.motor_dir[s == 0 ? RK_AJ_DFL : s == 1 ? RK_AJ_DFR : RK_AJ_P3]), 65536.0f));
+    const uint32_t clq   = (uint32_t)f2i_x86(fmul(cl, 256.0f)) & 0xFFFFu;
+    const bool     drive = c.bl_on[s] && a.bl_prev[s];
+    a.bl0[s]     = drive ? (uint32_t)ang : 0u;
+    a.bl1[s]     = drive ? (c.bl_ms[s] | (clq << 16)) : 0u;
+    a.bl2[s]     = !c.bl_on[s] ? 0x8002u : (a.bl_prev[s] ? 0x8010u : 0x8001u);
+    a.bl_prev[s] = c.bl_on[s];
   }
-  q[3] = 1;
-  set_prev(a, k, on);
-}
-
-// JointIcsServo::update   AD_joint_ics_servo.cpp:5-29, the UART replaced by an ideal servo that
-// answers with the commanded position (a free command answers with the last one).
-RK_DEV void ics_update(Arm &a, const rk_adt_params_t &p) {
-  const uint32_t b = jflag(a, RK_AJ_Y0);
-  if(!(b & RK_AJF_CONNECTED)) return;
-  const int tgt_pos = ics_degPos100(f2i_x86(fmul(fmul(a.j[RK_AJ_Y0].raw_tgt, p.motor_dir[RK_AJ_Y0]), 100.0f)));
-  if(tgt_pos == -1) return;
-  int now_pos;
-  if(b & RK_AJF_TORQUE_ON) {
-    if(tgt_pos > 11500 || tgt_pos < 3500) { // IcsBaseClass::setPos range check: nothing is sent
-      now_pos = -1;
-    } else {
-      a.ics_pos   = (uint32_t)tgt_pos;
-      a.ics_servo = (uint32_t)(tgt_pos - 7500);
-      now_pos     = tgt_pos;
-    }
-  } else {
-    a.ics_pos = 0xFFFFFFFFu;
-    now_pos   = (int)(int32_t)a.ics_servo + 7500;
+  // ---- JointIcsServo::update  AD_joint_ics_servo.cpp:5-29 over the ideal servo
+  {
+    const int  deg100 = f2i_x86(fmul(fmul(a.tgt[0], c.dir_y0), 100.0f));
+    const bool in_deg = deg100 <= 18000 && deg100 >= -18000;
+    const int  tp     = (deg100 * 2963) / 10000 + 7500; // garbage when !in_deg, never used then
+    const bool active = c.y0_conn && in_deg;
+    const bool send   = active && c.y0_on && tp <= 11500 && tp >= 3500;
+    const bool fre    = active && !c.y0_on;
+    const int  now_pos = send ? tp : (fre ? (int)(int32_t)a.ics_servo + 7500 : -1);
+    a.ics_pos   = send ? (uint32_t)tp : (fre ? 0xFFFFFFFFu : a.ics_pos);
+    a.ics_servo = send ? (uint32_t)(tp - 7500) : a.ics_servo;
+    const float nn = fmul(fmul((float)ics_posDeg100(now_pos), 0.01f), c.dir_y0);
+    a.now_y0       = active ? nn : a.now_y0;
   }
-  a.j[RK_AJ_Y0].raw_now = fmul(fmul((float)ics_posDeg100(now_pos), 0.01f), p.motor_dir[RK_AJ_Y0]);
 }
 
-RK_DEV uint32_t bldc_id_byte(uint32_t id) { return (id & 0xFFu) | ((id & 0x8000u) ? 0x80u : 0u); }
-
-RK_DEV void arm_tick(Arm &a, const rk_adt_params_t &p, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
-  mode_update(a, p, tab, n, i);
-  mg_update(a, p);
-  bldc_update<0>(a, p);
-  bldc_update<1>(a, p);
-  bldc_update<2>(a, p);
-  ics_update(a, p);
-}
-
-template <bool TRACE>
+template <bool TRACE, int DIVC>
 __global__ void __launch_bounds__(128)
 adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
-                  uint32_t *__restrict__ trace) {
+                  uint32_t *__restrict__ trace, float mg_rcp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
-  Arm a;
-  load_arm(state, n, i, a);
+  ArmLoop  a;
+  uint32_t jflags;
+  loop_load(state, n, i, a, jflags);
+  ArmConsts c;
+  {
+    auto fl = [&](int k) { return (jflags >> (4 * k)) & 0xFu; };
+    c.gear_p2 = p.gear_ratio[RK_AJ_P2], c.gear_r0 = p.gear_ratio[RK_AJ_R0], c.dir_y0 = p.motor_dir[RK_AJ_Y0];
+    c.mg_ctrl_time = p.ctrl_time_s[RK_AJ_P1], c.mg_rcp = mg_rcp;
+    c.y0_conn = (fl(RK_AJ_Y0) & RK_AJF_CONNECTED) != 0, c.y0_on = (fl(RK_AJ_Y0) & RK_AJF_TORQUE_ON) != 0;
+    c.mg_on  = (fl(RK_AJ_P1) & RK_AJF_TORQUE_ON) != 0;
+    c.mg_pos = c.mg_on && (fl(RK_AJ_P1) & RK_AJF_INITIALIZED) != 0; // the only branch of update() that emits a frame here
+    const int jk[3] = {RK_AJ_DFL, RK_AJ_DFR, RK_AJ_P3};
+#pragma unroll
+    for(int s = 0; s < 3; s++) {
+      c.bl_on[s] = (fl(jk[s]) & RK_AJF_TORQUE_ON) != 0;
+      c.bl_ms[s] = (uint32_t)f2i_x86(fmul(p.ctrl_time_s[jk[s]], 1000.0f)) & 0xFFFFu;
+    }
+  }
+  {
+    uint32_t lens = 0;
+#pragma unroll
+    for(int sl = 0; sl < RK_ACMD_SLOTS; sl++) lens |= (__ldg(&tab[(int64_t)sl * (RK_ACMD_SLOT_WORDS / 4) * n + i]).y & 0xFFu) << (8 * sl);
+    a.lens = lens;
+    // what the FSM will read first: the waypoint of a pending MOVE_START, else the one after the running segment
+    uint32_t fs = a.exec, fi = a.cmd_idx & 0xFFu;
+    if(a.state == RK_ASTATE_MOVING) ring_next(a, a.exec, a.cmd_idx & 0xFFu, fs, fi);
+    else if(a.state != RK_ASTATE_MOVE_START) fs = (a.exec + 1 >= RK_ACMD_SLOTS) ? 0u : a.exec + 1, fi = 0u;
+    ring_fetch(a, tab, n, i, fs, fi, a.sel);
+    a.pf_key = ring_key(fs, fi);
+  }
   for(int t = 0; t < K; t++) {
-    arm_tick(a, p, tab, n, i);
+    loop_tick<DIVC>(a, p, c, tab, n, i);
     if(TRACE) {
       uint32_t *tr = trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i;
 #pragma unroll
-      for(int k = 0; k < 5; k++) tr[(int64_t)k * n] = f2u(get_tgt_deg(a, k));
-      tr[5 * n] = a.mg_tx[0] >> 16, tr[6 * n] = a.mg_tx[1];
+      for(int k = 0; k < 5; k++) tr[(int64_t)k * n] = f2u(fsub(a.tgt[k], a.ofs[k]));
+      tr[5 * n] = a.mg_tx0 >> 16, tr[6 * n] = a.mg_tx1;
 #pragma unroll
-      for(int s = 0; s < 3; s++) tr[(int64_t)(7 + s) * n] = a.bldc[s][0];
+      for(int s = 0; s < 3; s++) tr[(int64_t)(7 + s) * n] = a.bl0[s];
       tr[10 * n] = a.ics_pos;
-      tr[11 * n] = a.fsm & 0xFFu;
+      tr[11 * n] = a.state;
       tr[12 * n] = a.cmd_idx;
-      tr[13 * n] = bldc_id_byte(a.bldc[0][2]) | (bldc_id_byte(a.bldc[1][2]) << 8) | (bldc_id_byte(a.bldc[2][2]) << 16);
+      tr[13 * n] = bldc_id_byte(a.bl2[0]) | (bldc_id_byte(a.bl2[1]) << 8) | (bldc_id_byte(a.bl2[2]) << 16);
       tr[14 * n] = 0u, tr[15 * n] = 0u;
     }
   }
-  store_arm(state, n, i, a);
+  loop_store(state, n, i, a, jflags, K > 0);
 }
 
 // prepare_task() + a finished INIT mode + ADTModeBase::init() -> doInit()
@@ -439,10 +602,22 @@ int rk_adt_update(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab,
     return RK_ERR_ARG;
   }
   if(int rc = adt_check("rk_adt_update", d_state, d_cmdtab, n)) return rc;
-  if(d_trace)
-    adt_update_kernel<true><<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>(*p, (uint4 *)d_state, (const uint4 *)d_cmdtab, n, K, d_trace);
-  else
-    adt_update_kernel<false><<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>(*p, (uint4 *)d_state, (const uint4 *)d_cmdtab, n, K, nullptr);
+  const float ct   = p->ctrl_time_s[RK_AJ_P1];
+  const int   divc = div_const_exact(ct); // exhaustive on-device proof, cached per constant
+  const float rcp  = divc ? 1.0f / ct : 0.0f; // one correctly rounded host division: RN(1/c)
+  cudaStream_t st  = (cudaStream_t)stream;
+#define RK_LAUNCH_ADT(TR, DV) \
+  adt_update_kernel<TR, DV><<<adt_grid(n), 128, 0, st>>>(*p, (uint4 *)d_state, (const uint4 *)d_cmdtab, n, K, d_trace, rcp)
+  if(d_trace) {
+    if(divc == 2) RK_LAUNCH_ADT(true, 2);
+    else if(divc == 1) RK_LAUNCH_ADT(true, 1);
+    else RK_LAUNCH_ADT(true, 0);
+  } else {
+    if(divc == 2) RK_LAUNCH_ADT(false, 2);
+    else if(divc == 1) RK_LAUNCH_ADT(false, 1);
+    else RK_LAUNCH_ADT(false, 0);
+  }
+#undef RK_LAUNCH_ADT
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }

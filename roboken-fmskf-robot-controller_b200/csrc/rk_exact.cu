@@ -100,6 +100,41 @@ bool fast_path_proven(const rk_vdt_params_t &p) {
   return ok;
 }
 
+// Exhaustive check of div_const(x, c, RN(1/c)) == x / c (bit for bit) over every finite float x on
+// the current device (one pass, ~4 ms, cached per (device, c)):  2 = exact for every x,
+// 1 = exact for x == +-0 and |x| >= 2^-40 (the tiny-quotient range underflows), 0 = not usable.
+// Used by kernels that divide by a launch constant every tick (e.g. the MG joint's velocity
+// limit, AD_joint_mg_servo.cpp:140).
+int div_const_exact(float c) {
+  static std::mutex mu;
+  static struct { int dev; uint32_t bits; int ok; } cache[16];
+  static int n_cache = 0;
+  if(!(c > 0.0f) || !(c < 3.0e38f)) return 0;
+  int dev = -1;
+  if(cudaGetDevice(&dev) != cudaSuccess) return 0;
+  uint32_t bits;
+  memcpy(&bits, &c, 4);
+  std::lock_guard<std::mutex> lk(mu);
+  for(int k = 0; k < n_cache; k++)
+    if(cache[k].dev == dev && cache[k].bits == bits) return cache[k].ok;
+  ProofOut *d_out = nullptr, h = ProofOut{0u, 0u, 0u, 0u};
+  if(cudaMalloc((void **)&d_out, sizeof(ProofOut)) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaMemcpy(d_out, &h, sizeof(h), cudaMemcpyHostToDevice);
+  proof_div_kernel<<<148 * 16, 256>>>(c, d_out);
+  cudaError_t e = cudaMemcpy(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d_out);
+  if(e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  const int ok = (h.div_fail_any == 0u) ? 2 : (h.div_fail_outside == 0u) ? 1 : 0;
+  if(n_cache < 16) cache[n_cache].dev = dev, cache[n_cache].bits = bits, cache[n_cache].ok = ok, n_cache++;
+  return ok;
+}
+
 } // namespace rk
 
 extern "C" {
