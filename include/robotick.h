@@ -357,6 +357,35 @@ int rk_adt_update(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab,
 int rk_adt_cmdseq_status(const void *d_state, const void *d_cmdtab, int64_t n, const uint32_t *d_id,
                          int32_t *d_status, void *stream);
 
+/* ---- ADTModePositioning (src/ArmDrive/AD_mode_positioning.{hpp,cpp}): the single-command mode behind
+ * REQ_MOVE_POS (AD_task_main.cpp:260-272).  Same joints (the RK_AS_* block), its own mode block:
+ * a FIFO of at most four commands (std::deque, push drops the OLDEST when full, :118-124), the
+ * move measured from get_now_deg() (:42-46), one state handler per update (:9-20). */
+enum {
+  RK_PS_STATE = 0,     /* nowState (0 STANDBY, 1 MOVING, 2 COMPLETED) | is_comp << 9 */
+  RK_PS_MOVE_CNT,      /* u32_move_cnt_ */
+  RK_PS_CYCLE,         /* u32_cycle_counter_ */
+  RK_PS_QSIZE,         /* cmd_q_.size() */
+  RK_PS_PREV_ID0 = 4,  /* u32_prev_cmd_id_[0], [1] */
+  RK_PS_PREV_ID1,
+  RK_PS_NOW_CMD = 8,   /* now_cmd_: u32_id, u32_dt_ms, fl_tgt_pos_deg[5], 0 */
+  RK_PS_MOVE_DEG = 16, /* fl_move_deg_[5], 0, 0, 0 */
+  RK_PS_QUEUE = 24,    /* cmd_q_ front first: 4 x {u32_id, u32_dt_ms, fl_tgt_pos_deg[5], 0} */
+  RK_PS_WORDS = 56     /* 14 planes = 224 B */
+};
+typedef struct rk_adp_poscmd { uint32_t id, dt_ms; float tgt_deg[5]; } rk_adp_poscmd_t; /* == ADTModePositioning::PosCmd */
+size_t rk_adp_state_words(void);
+size_t rk_adp_state_bytes(int64_t n);
+/* ADTModeBase::init() -> ADTModePositioning::doInit()  (AD_mode_base.hpp:19-22, AD_mode_positioning.cpp:5-7) */
+int rk_adp_mode_init(void *d_pstate, int64_t n, void *stream);
+/* ::push_cmd (:118-124).  d_cmd: two planes per arm, {id, dt_ms, tgt0, tgt1} and {tgt2, tgt3, tgt4, 0} (pitch n) */
+int rk_adp_push_cmd(void *d_pstate, int64_t n, const void *d_cmd, const uint8_t *d_valid, void *stream);
+/* K fused ticks of ADT::main's loop body with this mode active; trace as rk_adt_update (word 11 = nowState,
+ * word 12 = queue size) */
+int rk_adp_update(const rk_adt_params_t *p, void *d_state, void *d_pstate, int64_t n, int32_t K, uint32_t *d_trace, void *stream);
+/* ::get_q_cmd_status (:134-148): 0 PROCESSING (queued), 1 DONE (one of the last two finished), 99 NO_DATA */
+int rk_adp_cmd_status(const void *d_pstate, int64_t n, const uint32_t *d_id, int32_t *d_status, void *stream);
+
 /* single-instance handle (drop-in for the statics of AD_task_main.cpp:108-156) */
 typedef struct rk_adt rk_adt_t;
 int  rk_adt_create(rk_adt_t **out, const rk_adt_params_t *p /* NULL = defaults */);

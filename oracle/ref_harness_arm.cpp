@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE (oracle) -- never linked into the product library.
  *
  * C-ABI harness around the UNMODIFIED reference arm sources
- *   src/ArmDrive/AD_mode_positioning_seq.{hpp,cpp}, AD_mode_base.hpp, AD_joint_base.hpp,
+ *   src/ArmDrive/AD_mode_positioning_seq.{hpp,cpp}, AD_mode_positioning.{hpp,cpp}, AD_mode_base.hpp, AD_joint_base.hpp,
  *   AD_joint_dfgear.hpp, AD_joint_mybldc_servo.{hpp,cpp}, AD_joint_mg_servo.{hpp,cpp},
  *   AD_joint_ics_servo.{hpp,cpp}, lib/IcsClass_V210/src/IcsBaseClass.{h,cpp}
  * compiled where they lie (oracle/Makefile -> oracle/_ref/libref_arm.so).  Joint objects are
@@ -19,6 +19,7 @@
 #include "ArmDrive/AD_joint_ics_servo.hpp"
 #include "ArmDrive/AD_joint_mg_servo.hpp"
 #include "ArmDrive/AD_joint_mybldc_servo.hpp"
+#include "ArmDrive/AD_mode_positioning.hpp"
 #include "ArmDrive/AD_mode_positioning_seq.hpp"
 /* the three in-tree command sequences (POS_CMD_SEQ_DEBUG_0/1/2 have internal linkage, so the
  * reference translation unit is included where it lies -- nothing is copied) */
@@ -74,6 +75,7 @@ struct ArmSet {
   JointDfGearRoll        j_R0;
   JointMyBldcServo       j_P3;
   ADTModePositioningSeq  posseq;
+  ADTModePositioning     pos; /* the single-command mode (REQ_MOVE_POS) on the same joints */
   /* what the CAN tx routines / the UART took this tick */
   uint8_t  mg_tx[8];
   int      mg_valid;
@@ -123,9 +125,10 @@ void bringup(ArmSet *s) {
   s->posseq.init();
 }
 
-/* ADT::main loop body  AD_task_main.cpp:208-229 */
-void tick(ArmSet *s) {
-  s->posseq.update();
+/* ADT::main loop body  AD_task_main.cpp:208-229 ; which = the active mode object */
+void tick(ArmSet *s, int which = 0) {
+  if(which == 0) s->posseq.update();
+  else s->pos.update();
   s->j_P1.update();
   s->j_DFL.update();
   s->j_DFR.update();
@@ -248,6 +251,39 @@ void import_state(ArmSet *s, const uint32_t *w) {
   }
 }
 
+void export_pstate(ArmSet *s, uint32_t *w) {
+  memset(w, 0, 4 * RK_PS_WORDS);
+  auto &m = s->pos;
+  w[RK_PS_STATE]    = (uint32_t)m.nowState | (m.is_comp ? RK_AS_FSM_IS_COMP : 0u);
+  w[RK_PS_MOVE_CNT] = m.u32_move_cnt_, w[RK_PS_CYCLE] = m.u32_cycle_counter_, w[RK_PS_QSIZE] = (uint32_t)m.cmd_q_.size();
+  w[RK_PS_PREV_ID0] = m.u32_prev_cmd_id_[0], w[RK_PS_PREV_ID1] = m.u32_prev_cmd_id_[1];
+  w[RK_PS_NOW_CMD] = m.now_cmd_.u32_id, w[RK_PS_NOW_CMD + 1] = m.now_cmd_.u32_dt_ms;
+  for(int j = 0; j < 5; j++) w[RK_PS_NOW_CMD + 2 + j] = f2u(m.now_cmd_.fl_tgt_pos_deg[j]), w[RK_PS_MOVE_DEG + j] = f2u(m.fl_move_deg_[j]);
+  int e = 0;
+  for(auto it = m.cmd_q_.cbegin(); it != m.cmd_q_.cend() && e < 4; ++it, ++e) {
+    uint32_t *q = w + RK_PS_QUEUE + 8 * e;
+    q[0] = it->u32_id, q[1] = it->u32_dt_ms;
+    for(int j = 0; j < 5; j++) q[2 + j] = f2u(it->fl_tgt_pos_deg[j]);
+  }
+}
+void import_pstate(ArmSet *s, const uint32_t *w) {
+  auto &m    = s->pos;
+  m.nowState = (ADTModePositioning::State)(w[RK_PS_STATE] & 0xFF);
+  m.is_comp  = (w[RK_PS_STATE] & RK_AS_FSM_IS_COMP) != 0;
+  m.u32_move_cnt_ = w[RK_PS_MOVE_CNT], m.u32_cycle_counter_ = w[RK_PS_CYCLE];
+  m.u32_prev_cmd_id_[0] = w[RK_PS_PREV_ID0], m.u32_prev_cmd_id_[1] = w[RK_PS_PREV_ID1];
+  m.now_cmd_.u32_id = w[RK_PS_NOW_CMD], m.now_cmd_.u32_dt_ms = w[RK_PS_NOW_CMD + 1];
+  for(int j = 0; j < 5; j++) m.now_cmd_.fl_tgt_pos_deg[j] = u2f(w[RK_PS_NOW_CMD + 2 + j]), m.fl_move_deg_[j] = u2f(w[RK_PS_MOVE_DEG + j]);
+  m.cmd_q_.clear();
+  for(uint32_t e = 0; e < w[RK_PS_QSIZE] && e < 4; e++) {
+    ADTModePositioning::PosCmd c;
+    const uint32_t            *q = w + RK_PS_QUEUE + 8 * e;
+    c.u32_id = q[0], c.u32_dt_ms = q[1];
+    for(int j = 0; j < 5; j++) c.fl_tgt_pos_deg[j] = u2f(q[2 + j]);
+    m.cmd_q_.push_back(c);
+  }
+}
+
 inline uint32_t &soa(uint32_t *blk, int64_t n, int64_t i, int w) { return blk[((int64_t)(w / 4) * n + i) * 4 + (w % 4)]; }
 
 void load_cmdtab(ArmSet *s, const uint32_t *tab, int64_t n, int64_t i) {
@@ -277,7 +313,7 @@ void store_cmdtab(ArmSet *s, uint32_t *tab, int64_t n, int64_t i) {
 
 uint32_t bldc_id_byte(uint32_t id) { return (id & 0xFF) | ((id & 0x8000) ? 0x80u : 0u); }
 
-void trace_row(ArmSet *s, uint32_t *tr, int64_t n) {
+void trace_row(ArmSet *s, uint32_t *tr, int64_t n, int which = 0) {
   for(int j = 0; j < 5; j++) tr[(int64_t)j * n] = f2u(ADTModeBase::P_JOINT_[j]->get_tgt_deg());
   uint16_t vl;
   int32_t  ang;
@@ -285,8 +321,8 @@ void trace_row(ArmSet *s, uint32_t *tr, int64_t n) {
   tr[5 * n] = vl, tr[6 * n] = (uint32_t)ang;
   for(int k = 0; k < 3; k++) tr[(int64_t)(7 + k) * n] = ld32(s->bldc_tx[k]);
   tr[10 * n] = (uint32_t)ics_pos_word(s);
-  tr[11 * n] = (uint32_t)s->posseq.nowState;
-  tr[12 * n] = s->posseq.u8_nowcmd_idx_;
+  tr[11 * n] = which == 0 ? (uint32_t)s->posseq.nowState : (uint32_t)s->pos.nowState;
+  tr[12 * n] = which == 0 ? (uint32_t)s->posseq.u8_nowcmd_idx_ : (uint32_t)s->pos.cmd_q_.size();
   tr[13 * n] = bldc_id_byte(s->bl(0)->u32_txcmdid) | (bldc_id_byte(s->bl(1)->u32_txcmdid) << 8) | (bldc_id_byte(s->bl(2)->u32_txcmdid) << 16);
   tr[14 * n] = 0, tr[15 * n] = 0;
 }
@@ -378,6 +414,46 @@ void ref_adt_batch(int op, uint32_t *state, uint32_t *cmdtab, int64_t n, int64_t
       export_state(s, w);
       for(int k = 0; k < RK_AS_WORDS; k++) soa(state, n, i, k) = w[k];
       if(cmdtab && op == 1) store_cmdtab(s, cmdtab, n, i);
+    }
+    s->~ArmSet();
+    free(s);
+  }
+}
+
+/* ADTModePositioning batch driver on HOST arrays, same contracts as the rk_adp_* calls:
+ * op 0 = rk_adp_mode_init, 1 = rk_adp_push_cmd (cmd: two planes per arm), 2 = K ticks (+trace), 3 = status */
+void ref_adp_batch(int op, uint32_t *state, uint32_t *pstate, int64_t n, int64_t i0, int64_t i1, int K, const uint32_t *cmd,
+                   const uint8_t *valid, uint32_t *trace, const uint32_t *ids, int32_t *status) {
+  for(int64_t i = i0; i < i1; i++) {
+    ArmSet  *s = make();
+    uint32_t w[RK_AS_WORDS], pw[RK_PS_WORDS];
+    for(int k = 0; k < RK_AS_WORDS; k++) w[k] = soa(state, n, i, k);
+    for(int k = 0; k < RK_PS_WORDS; k++) pw[k] = soa(pstate, n, i, k);
+    import_state(s, w);
+    import_pstate(s, pw);
+    if(op == 0) {
+      s->pos.init();
+    } else if(op == 1) {
+      if(!valid || valid[i]) {
+        ADTModePositioning::PosCmd c;
+        c.u32_id = soa((uint32_t *)cmd, n, i, 0), c.u32_dt_ms = soa((uint32_t *)cmd, n, i, 1);
+        for(int j = 0; j < 5; j++) c.fl_tgt_pos_deg[j] = u2f(soa((uint32_t *)cmd, n, i, 2 + j));
+        s->pos.push_cmd(c);
+      }
+    } else if(op == 2) {
+      for(int t = 0; t < K; t++) {
+        tick(s, 1);
+        if(trace) trace_row(s, trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, 1);
+      }
+    } else if(op == 3) {
+      status[i] = s->pos.get_q_cmd_status(ids[i]);
+    }
+    if(op != 3) {
+      export_state(s, w);
+      export_pstate(s, pw);
+      if(op == 2)
+        for(int k = 0; k < RK_AS_WORDS; k++) soa(state, n, i, k) = w[k];
+      for(int k = 0; k < RK_PS_WORDS; k++) soa(pstate, n, i, k) = pw[k];
     }
     s->~ArmSet();
     free(s);

@@ -806,3 +806,111 @@ void orc_adt_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *
       for(k = 0; k < RK_AS_WORDS; k++) *soa(state, n, i, k) = w[k];
   }
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* ADTModePositioning   src/ArmDrive/AD_mode_positioning.cpp (single-command FIFO mode)    */
+static float adt_get_now_deg(const rk_adt_params_t *p, const uint32_t *w, int axis) {
+  /* JointBase::get_now_deg (AD_joint_base.hpp:48); DfGear overrides (AD_joint_dfgear.hpp:76-77,98) */
+  float ln = u2f(AJ(w, RK_AJ_DFL, RK_AJ_RAW_NOW)) - u2f(AJ(w, RK_AJ_DFL, RK_AJ_OFS));
+  float rn = u2f(AJ(w, RK_AJ_DFR, RK_AJ_RAW_NOW)) - u2f(AJ(w, RK_AJ_DFR, RK_AJ_OFS));
+  int   k  = ADT_AXIS[axis];
+  if(k == RK_AJ_P2) return (ln - rn) * 0.5f / p->gear_ratio[k] - u2f(AJ(w, k, RK_AJ_OFS));
+  if(k == RK_AJ_R0) return -(ln + rn) * 0.5f / p->gear_ratio[k] - u2f(AJ(w, k, RK_AJ_OFS));
+  return u2f(AJ(w, k, RK_AJ_RAW_NOW)) - u2f(AJ(w, k, RK_AJ_OFS));
+}
+
+static void adp_mode_update(const rk_adt_params_t *p, uint32_t *w, uint32_t *pw) {
+  uint32_t state = pw[RK_PS_STATE] & 0xFFu, flags = pw[RK_PS_STATE] & ~0xFFu;
+  int      j, e;
+  if(state == 0) { /* exec_standby :27-58 */
+    flags |= RK_AS_FSM_IS_COMP;
+    if(pw[RK_PS_QSIZE] > 0) {
+      uint32_t cnt, qs = pw[RK_PS_QSIZE] > 4 ? 4 : pw[RK_PS_QSIZE];
+      float    fc;
+      for(j = 0; j < 8; j++) pw[RK_PS_NOW_CMD + j] = pw[RK_PS_QUEUE + j];
+      for(e = 1; e < (int)qs; e++)
+        for(j = 0; j < 8; j++) pw[RK_PS_QUEUE + 8 * (e - 1) + j] = pw[RK_PS_QUEUE + 8 * e + j];
+      for(j = 0; j < 8; j++) pw[RK_PS_QUEUE + 8 * (qs - 1) + j] = 0; /* entries past size() are kept zero */
+      pw[RK_PS_QSIZE] = qs - 1;
+      cnt = (uint32_t)f2i_x86((float)pw[RK_PS_NOW_CMD + 1] * 0.001f / p->cycle_time_s);
+      cnt = (cnt == 0) ? 1 : cnt;
+      fc  = (float)cnt;
+      for(j = 0; j < 5; j++) pw[RK_PS_MOVE_DEG + j] = f2u((u2f(pw[RK_PS_NOW_CMD + 2 + j]) - adt_get_now_deg(p, w, j)) / fc);
+      pw[RK_PS_MOVE_CNT] = cnt;
+      pw[RK_PS_CYCLE]    = 0;
+      flags &= ~RK_AS_FSM_IS_COMP;
+      state = 1;
+    }
+  } else if(state == 1) { /* exec_moving :64-110 */
+    uint32_t cnt = pw[RK_PS_MOVE_CNT], cyc = pw[RK_PS_CYCLE];
+    float    rem = (float)(uint32_t)(cnt - cyc);
+    for(j = 0; j < 5; j++) adt_set_tgt(p, w, j, u2f(pw[RK_PS_NOW_CMD + 2 + j]) - u2f(pw[RK_PS_MOVE_DEG + j]) * rem);
+    if(cnt <= cyc) {
+      pw[RK_PS_PREV_ID1] = pw[RK_PS_PREV_ID0];
+      pw[RK_PS_PREV_ID0] = pw[RK_PS_NOW_CMD];
+      state              = 0;
+    } else {
+      pw[RK_PS_CYCLE] = cyc + 1;
+    }
+  }
+  pw[RK_PS_STATE] = flags | state;
+}
+
+void orc_adp_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *pstate, int64_t n, int64_t i0, int64_t i1, int K,
+                   const uint32_t *cmd, const uint8_t *valid, uint32_t *trace, const uint32_t *ids, int32_t *status) {
+  int64_t i;
+  int     k, t, j, e;
+  for(i = i0; i < i1; i++) {
+    uint32_t w[RK_AS_WORDS], pw[RK_PS_WORDS];
+    for(k = 0; k < RK_AS_WORDS; k++) w[k] = *soa(state, n, i, k);
+    for(k = 0; k < RK_PS_WORDS; k++) pw[k] = *soa(pstate, n, i, k);
+    if(op == 0) { /* ADTModeBase::init -> doInit */
+      pw[RK_PS_STATE] = 0;
+    } else if(op == 1) { /* push_cmd :118-124 */
+      if(!valid || valid[i]) {
+        uint32_t qs = pw[RK_PS_QSIZE] > 4 ? 4 : pw[RK_PS_QSIZE];
+        if(qs >= 4) {
+          for(e = 1; e < 4; e++)
+            for(j = 0; j < 8; j++) pw[RK_PS_QUEUE + 8 * (e - 1) + j] = pw[RK_PS_QUEUE + 8 * e + j];
+          qs = 3;
+        }
+        for(j = 0; j < 7; j++) pw[RK_PS_QUEUE + 8 * qs + j] = *soa((uint32_t *)cmd, n, i, j);
+        pw[RK_PS_QUEUE + 8 * qs + 7] = 0;
+        pw[RK_PS_QSIZE]              = qs + 1;
+      }
+    } else if(op == 2) {
+      for(t = 0; t < K; t++) {
+        adp_mode_update(p, w, pw);
+        adt_mg_update(p, w);
+        adt_bldc_update(p, w, 0);
+        adt_bldc_update(p, w, 1);
+        adt_bldc_update(p, w, 2);
+        adt_ics_update(p, w);
+        if(trace) {
+          uint32_t *tr = trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i;
+          for(j = 0; j < 5; j++) tr[(int64_t)j * n] = f2u(adt_get_tgt_deg(w, ADT_AXIS[j]));
+          tr[5 * n] = w[RK_AS_MG_TX] >> 16, tr[6 * n] = w[RK_AS_MG_TX + 1];
+          for(j = 0; j < 3; j++) tr[(int64_t)(7 + j) * n] = w[RK_AS_BLDC_TX0 + 4 * j];
+          tr[10 * n] = w[RK_AS_ICS_POS];
+          tr[11 * n] = pw[RK_PS_STATE] & 0xFFu;
+          tr[12 * n] = pw[RK_PS_QSIZE];
+          tr[13 * n] = bldc_id_byte(w[RK_AS_BLDC_TX0 + 2]) | (bldc_id_byte(w[RK_AS_BLDC_TX0 + 6]) << 8) |
+                       (bldc_id_byte(w[RK_AS_BLDC_TX0 + 10]) << 16);
+          tr[14 * n] = 0, tr[15 * n] = 0;
+        }
+      }
+    } else if(op == 3) { /* get_q_cmd_status :134-148 */
+      int32_t  sts = 0x63;
+      uint32_t qs  = pw[RK_PS_QSIZE] > 4 ? 4 : pw[RK_PS_QSIZE];
+      for(e = 0; e < (int)qs; e++)
+        if(pw[RK_PS_QUEUE + 8 * e] == ids[i]) sts = 0;
+      if(pw[RK_PS_PREV_ID0] == ids[i] || pw[RK_PS_PREV_ID1] == ids[i]) sts = 1;
+      status[i] = sts;
+    }
+    if(op != 3) {
+      if(op == 2)
+        for(k = 0; k < RK_AS_WORDS; k++) *soa(state, n, i, k) = w[k];
+      for(k = 0; k < RK_PS_WORDS; k++) *soa(pstate, n, i, k) = pw[k];
+    }
+  }
+}

@@ -36,6 +36,10 @@ void orc_imt_update(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, c
 void orc_adt_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *cmdtab, int64_t n, int64_t i0, int64_t i1,
                    int K, const uint32_t *seq, const uint8_t *valid, uint32_t *trace, const uint32_t *ids, int32_t *status);
 
+/* ADTModePositioning batch driver (ref_adp_batch's contract): op 0 init, 1 push_cmd, 2 K ticks, 3 status */
+void orc_adp_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *pstate, int64_t n, int64_t i0, int64_t i1, int K,
+                   const uint32_t *cmd, const uint8_t *valid, uint32_t *trace, const uint32_t *ids, int32_t *status);
+
 float orc_sin(float x);
 float orc_cos(float x);
 float orc_normalize_rad_0to2pi(float x);

@@ -164,6 +164,13 @@ def _proto(lib):
     lib.rk_adt_push_cmdseq.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
     lib.rk_adt_update.argtypes = [C.POINTER(AdtParams), vp, vp, C.c_int64, C.c_int32, vp, vp]
     lib.rk_adt_cmdseq_status.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
+    lib.rk_adp_state_words.restype = C.c_size_t
+    lib.rk_adp_state_bytes.argtypes = [C.c_int64]
+    lib.rk_adp_state_bytes.restype = C.c_size_t
+    lib.rk_adp_mode_init.argtypes = [vp, C.c_int64, vp]
+    lib.rk_adp_push_cmd.argtypes = [vp, C.c_int64, vp, vp, vp]
+    lib.rk_adp_update.argtypes = [C.POINTER(AdtParams), vp, vp, C.c_int64, C.c_int32, vp, vp]
+    lib.rk_adp_cmd_status.argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.rk_adt_create.argtypes = [C.POINTER(vp), C.POINTER(AdtParams)]
     lib.rk_adt_destroy.argtypes = [vp]
     lib.rk_adt_destroy.restype = None

@@ -74,6 +74,35 @@ class ArmBatch:
             self.cmdtab.copy_(torch.from_numpy(np.asarray(tab_u32).view(np.int32)))
 
 
+class ArmPositioningBatch:
+    """ADTModePositioning (the single-command mode behind REQ_MOVE_POS) for the arms of an ArmBatch:
+    the joints are the ArmBatch's, the mode block (FIFO of <= 4 commands) lives here."""
+
+    def __init__(self, arms):
+        self.arms, self.lib, self.n = arms, arms.lib, arms.n
+        assert self.lib.rk_adp_state_words() == layout.PS_WORDS
+        with torch.cuda.device(arms.dev_index):
+            self.pstate = torch.zeros(layout.PS_WORDS * self.n, dtype=torch.int32, device=arms.device)
+
+    def mode_init(self, stream=None):
+        _cabi.check(self.lib.rk_adp_mode_init(self.pstate.data_ptr(), self.n, self.arms._st(stream)))
+
+    def push_cmd(self, cmd, valid=None, stream=None):
+        """cmd: int32/uint32 device tensor [2, n, 4]: {id, dt_ms, tgt0, tgt1}, {tgt2, tgt3, tgt4, 0} per arm."""
+        assert cmd.is_cuda and cmd.numel() == 8 * self.n and cmd.element_size() == 4 and cmd.is_contiguous()
+        _cabi.check(self.lib.rk_adp_push_cmd(self.pstate.data_ptr(), self.n, cmd.data_ptr(),
+                                             None if valid is None else valid.data_ptr(), self.arms._st(stream)))
+
+    def update(self, K=1, trace=None, stream=None):
+        _cabi.check(self.lib.rk_adp_update(C.byref(self.arms.params), self.arms.state.data_ptr(), self.pstate.data_ptr(), self.n,
+                                           int(K), None if trace is None else trace.data_ptr(), self.arms._st(stream)))
+
+    def cmd_status(self, ids, stream=None):
+        out = torch.empty(self.n, dtype=torch.int32, device=self.arms.device)
+        _cabi.check(self.lib.rk_adp_cmd_status(self.pstate.data_ptr(), self.n, ids.data_ptr(), out.data_ptr(), self.arms._st(stream)))
+        return out
+
+
 class Arm:
     """Single arm (rk_adt_t): the statics of AD_task_main.cpp:108-156 behind one handle."""
 

@@ -322,28 +322,38 @@ RK_DEV void loop_fsm_transitions(ArmLoop &a, const rk_adt_params_t &p, const uin
   }
 }
 
+// the five set_tgt_ang_deg() calls of exec_moving (JointBase :42, DfGear overrides), predicated on `moving`
+RK_DEV void loop_set_targets(ArmLoop &a, const ArmConsts &c, bool moving, float rem, const float now_tgt[5], const float move[5]) {
+  float raw[5];
+#pragma unroll
+  for(int k = 0; k < 5; k++) {
+    raw[k]   = fadd(fsub(now_tgt[k], fmul(move[k], rem)), a.ofs[k]);
+    a.tgt[k] = moving ? raw[k] : a.tgt[k];
+  }
+  const float P = fmul(raw[2], c.gear_p2), R = fmul(raw[3], c.gear_r0);
+  a.dfv_p = moving ? P : a.dfv_p, a.dfv_r = moving ? R : a.dfv_r;
+  a.tgt_dfl = moving ? fadd(fsub(P, R), a.ofs_dfl) : a.tgt_dfl;
+  a.tgt_dfr = moving ? fadd(-fadd(P, R), a.ofs_dfr) : a.tgt_dfr;
+}
+
+template <int DIVC> RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c);
+
 template <int DIVC>
 RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
   if(a.state != RK_ASTATE_MOVING) loop_fsm_transitions(a, p, tab, n, i);
-  // ---- exec_moving :89-117 + JointBase / DfGear set_tgt_ang_deg, predicated on `moving`
-  const bool  moving = a.state == RK_ASTATE_MOVING;
-  const float rem    = (float)(a.cnt - a.cyc);
-  float       raw[5];
-#pragma unroll
-  for(int k = 0; k < 5; k++) {
-    raw[k]   = fadd(fsub(a.now_tgt[k], fmul(a.move[k], rem)), a.ofs[k]);
-    a.tgt[k] = moving ? raw[k] : a.tgt[k];
-  }
-  {
-    const float P = fmul(raw[2], c.gear_p2), R = fmul(raw[3], c.gear_r0);
-    a.dfv_p = moving ? P : a.dfv_p, a.dfv_r = moving ? R : a.dfv_r;
-    a.tgt_dfl = moving ? fadd(fsub(P, R), a.ofs_dfl) : a.tgt_dfl;
-    a.tgt_dfr = moving ? fadd(-fadd(P, R), a.ofs_dfr) : a.tgt_dfr;
-    const bool fin = moving && (a.cnt <= a.cyc);
-    a.cmd_idx      = fin ? ((a.cmd_idx + 1) & 0xFFu) : a.cmd_idx;
-    a.state        = fin ? (uint32_t)RK_ASTATE_MOVE_START : a.state;
-    a.cyc          = (moving && !fin) ? a.cyc + 1 : a.cyc;
-  }
+  // ---- exec_moving :89-117
+  const bool moving = a.state == RK_ASTATE_MOVING;
+  loop_set_targets(a, c, moving, (float)(a.cnt - a.cyc), a.now_tgt, a.move);
+  const bool fin = moving && (a.cnt <= a.cyc);
+  a.cmd_idx      = fin ? ((a.cmd_idx + 1) & 0xFFu) : a.cmd_idx;
+  a.state        = fin ? (uint32_t)RK_ASTATE_MOVE_START : a.state;
+  a.cyc          = (moving && !fin) ? a.cyc + 1 : a.cyc;
+  loop_joints<DIVC>(a, p, c);
+}
+
+// ADT::main's joint updates (AD_task_main.cpp:213-228): j_P1, j_DF_Left, j_DF_Right, j_P3, [CAN tx], j_Y0
+template <int DIVC>
+RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c) {
   // ---- JointMgServo::update -> subproc_posctrl  AD_joint_mg_servo.cpp:50-73,136-149
   {
     const float tgt = a.tgt[1];
@@ -395,6 +405,36 @@ RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, 
   }
 }
 
+RK_DEV ArmConsts make_consts(const rk_adt_params_t &p, uint32_t jflags, float mg_rcp) {
+  ArmConsts c;
+  auto      fl = [&](int k) { return (jflags >> (4 * k)) & 0xFu; };
+  c.gear_p2 = p.gear_ratio[RK_AJ_P2], c.gear_r0 = p.gear_ratio[RK_AJ_R0], c.dir_y0 = p.motor_dir[RK_AJ_Y0];
+  c.mg_ctrl_time = p.ctrl_time_s[RK_AJ_P1], c.mg_rcp = mg_rcp;
+  c.y0_conn = (fl(RK_AJ_Y0) & RK_AJF_CONNECTED) != 0, c.y0_on = (fl(RK_AJ_Y0) & RK_AJF_TORQUE_ON) != 0;
+  c.mg_on  = (fl(RK_AJ_P1) & RK_AJF_TORQUE_ON) != 0;
+  c.mg_pos = c.mg_on && (fl(RK_AJ_P1) & RK_AJF_INITIALIZED) != 0; // the only branch of update() that emits a frame here
+  const int jk[3] = {RK_AJ_DFL, RK_AJ_DFR, RK_AJ_P3};
+#pragma unroll
+  for(int s = 0; s < 3; s++) {
+    c.bl_on[s] = (fl(jk[s]) & RK_AJF_TORQUE_ON) != 0;
+    c.bl_ms[s] = (uint32_t)f2i_x86(fmul(p.ctrl_time_s[jk[s]], 1000.0f)) & 0xFFFFu;
+  }
+  return c;
+}
+
+RK_DEV void arm_trace_row(uint32_t *tr, int64_t n, const ArmLoop &a, uint32_t w11, uint32_t w12) {
+#pragma unroll
+  for(int k = 0; k < 5; k++) tr[(int64_t)k * n] = f2u(fsub(a.tgt[k], a.ofs[k]));
+  tr[5 * n] = a.mg_tx0 >> 16, tr[6 * n] = a.mg_tx1;
+#pragma unroll
+  for(int s = 0; s < 3; s++) tr[(int64_t)(7 + s) * n] = a.bl0[s];
+  tr[10 * n] = a.ics_pos;
+  tr[11 * n] = w11;
+  tr[12 * n] = w12;
+  tr[13 * n] = bldc_id_byte(a.bl2[0]) | (bldc_id_byte(a.bl2[1]) << 8) | (bldc_id_byte(a.bl2[2]) << 16);
+  tr[14 * n] = 0u, tr[15 * n] = 0u;
+}
+
 template <bool TRACE, int DIVC>
 __global__ void __launch_bounds__(128)
 adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
@@ -404,21 +444,7 @@ adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint
   ArmLoop  a;
   uint32_t jflags;
   loop_load(state, n, i, a, jflags);
-  ArmConsts c;
-  {
-    auto fl = [&](int k) { return (jflags >> (4 * k)) & 0xFu; };
-    c.gear_p2 = p.gear_ratio[RK_AJ_P2], c.gear_r0 = p.gear_ratio[RK_AJ_R0], c.dir_y0 = p.motor_dir[RK_AJ_Y0];
-    c.mg_ctrl_time = p.ctrl_time_s[RK_AJ_P1], c.mg_rcp = mg_rcp;
-    c.y0_conn = (fl(RK_AJ_Y0) & RK_AJF_CONNECTED) != 0, c.y0_on = (fl(RK_AJ_Y0) & RK_AJF_TORQUE_ON) != 0;
-    c.mg_on  = (fl(RK_AJ_P1) & RK_AJF_TORQUE_ON) != 0;
-    c.mg_pos = c.mg_on && (fl(RK_AJ_P1) & RK_AJF_INITIALIZED) != 0; // the only branch of update() that emits a frame here
-    const int jk[3] = {RK_AJ_DFL, RK_AJ_DFR, RK_AJ_P3};
-#pragma unroll
-    for(int s = 0; s < 3; s++) {
-      c.bl_on[s] = (fl(jk[s]) & RK_AJF_TORQUE_ON) != 0;
-      c.bl_ms[s] = (uint32_t)f2i_x86(fmul(p.ctrl_time_s[jk[s]], 1000.0f)) & 0xFFFFu;
-    }
-  }
+  const ArmConsts c = make_consts(p, jflags, mg_rcp);
   {
     uint32_t lens = 0;
 #pragma unroll
@@ -433,21 +459,134 @@ adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint
   }
   for(int t = 0; t < K; t++) {
     loop_tick<DIVC>(a, p, c, tab, n, i);
-    if(TRACE) {
-      uint32_t *tr = trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i;
-#pragma unroll
-      for(int k = 0; k < 5; k++) tr[(int64_t)k * n] = f2u(fsub(a.tgt[k], a.ofs[k]));
-      tr[5 * n] = a.mg_tx0 >> 16, tr[6 * n] = a.mg_tx1;
-#pragma unroll
-      for(int s = 0; s < 3; s++) tr[(int64_t)(7 + s) * n] = a.bl0[s];
-      tr[10 * n] = a.ics_pos;
-      tr[11 * n] = a.state;
-      tr[12 * n] = a.cmd_idx;
-      tr[13 * n] = bldc_id_byte(a.bl2[0]) | (bldc_id_byte(a.bl2[1]) << 8) | (bldc_id_byte(a.bl2[2]) << 16);
-      tr[14 * n] = 0u, tr[15 * n] = 0u;
-    }
+    if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, a.state, a.cmd_idx);
   }
   loop_store(state, n, i, a, jflags, K > 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ADTModePositioning (AD_mode_positioning.cpp): same joints, single-command FIFO mode.
+// The FIFO (front first) stays in HBM; a command start (rare) pops it there.
+// ---------------------------------------------------------------------------------------------
+RK_DEV float joint_now_deg(const uint4 *st, int64_t n, int64_t i, int k) { // JointBase::get_now_deg  AD_joint_base.hpp:48
+  const uint4 j = ld_plane(st, n, (RK_AS_JOINT0 + 4 * k) / 4, i);
+  return fsub(u2f(j.w), u2f(j.x));
+}
+
+template <bool TRACE, int DIVC>
+__global__ void __launch_bounds__(128)
+adp_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, uint4 *__restrict__ ps, int64_t n, int K,
+                  uint32_t *__restrict__ trace, float mg_rcp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  ArmLoop  a;
+  uint32_t jflags;
+  loop_load(state, n, i, a, jflags);
+  const ArmConsts c = make_consts(p, jflags, mg_rcp);
+  uint4    h0 = ld_plane(ps, n, 0, i), h1 = ld_plane(ps, n, 1, i);
+  uint32_t pstate = h0.x & 0xFFu, pflags = h0.x & ~0xFFu, cnt = h0.y, cyc = h0.z, qsize = h0.w;
+  uint4    c0 = ld_plane(ps, n, 2, i), c1 = ld_plane(ps, n, 3, i);
+  const uint4 m0 = ld_plane(ps, n, 4, i), m1 = ld_plane(ps, n, 5, i);
+  uint32_t now_id = c0.x, now_dt = c0.y;
+  float    now_tgt[5] = {u2f(c0.z), u2f(c0.w), u2f(c1.x), u2f(c1.y), u2f(c1.z)};
+  float    move[5]    = {u2f(m0.x), u2f(m0.y), u2f(m0.z), u2f(m0.w), u2f(m1.x)};
+  for(int t = 0; t < K; t++) {
+    const bool was_moving = pstate == 1u; // switch(nowState): ONE handler per update  :9-20
+    if(pstate == 0u) {                    // exec_standby :27-58
+      pflags |= RK_AS_FSM_IS_COMP;
+      if(qsize > 0) {
+        c0 = ld_plane(ps, n, RK_PS_QUEUE / 4, i), c1 = ld_plane(ps, n, RK_PS_QUEUE / 4 + 1, i); // cmd_q_.front()
+        for(uint32_t e = 1; e < qsize && e < 4; e++) {                                          // pop_front()
+          st_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (e - 1), i, ld_plane(ps, n, RK_PS_QUEUE / 4 + 2 * e, i));
+          st_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (e - 1) + 1, i, ld_plane(ps, n, RK_PS_QUEUE / 4 + 2 * e + 1, i));
+        }
+        qsize = (qsize > 4u ? 4u : qsize) - 1u;
+        st_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (int)qsize, i, make_uint4(0u, 0u, 0u, 0u)); // entries past size() are kept zero
+        st_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (int)qsize + 1, i, make_uint4(0u, 0u, 0u, 0u));
+        now_id = c0.x, now_dt = c0.y;
+        now_tgt[0] = u2f(c0.z), now_tgt[1] = u2f(c0.w), now_tgt[2] = u2f(c1.x), now_tgt[3] = u2f(c1.y), now_tgt[4] = u2f(c1.z);
+        cnt = (uint32_t)f2i_x86(fdiv(fmul(__uint2float_rn(now_dt), 0.001f), p.cycle_time_s));
+        cnt = (cnt == 0u) ? 1u : cnt;
+        const float fc = __uint2float_rn(cnt);
+        // get_now_deg() of the five axes; J2 / J3 through the differential (AD_joint_dfgear.hpp:76-77,98)
+        const float ln = joint_now_deg(state, n, i, RK_AJ_DFL), rn = joint_now_deg(state, n, i, RK_AJ_DFR);
+        const float ofs_p2 = a.ofs[2], ofs_r0 = a.ofs[3];
+        float       now[5];
+        now[0] = fsub(a.now_y0, a.ofs[0]);
+        now[1] = joint_now_deg(state, n, i, RK_AJ_P1);
+        now[2] = fsub(fdiv(fmul(fsub(ln, rn), 0.5f), p.gear_ratio[RK_AJ_P2]), ofs_p2);
+        now[3] = fsub(fdiv(fmul(-fadd(ln, rn), 0.5f), p.gear_ratio[RK_AJ_R0]), ofs_r0);
+        now[4] = joint_now_deg(state, n, i, RK_AJ_P3);
+#pragma unroll
+        for(int k = 0; k < 5; k++) move[k] = fdiv(fsub(now_tgt[k], now[k]), fc);
+        cyc = 0;
+        pflags &= ~RK_AS_FSM_IS_COMP;
+        pstate = 1u;
+      }
+    }
+    // exec_moving :64-110 (only when the update STARTED in MOVING)
+    loop_set_targets(a, c, was_moving, __uint2float_rn(cnt - cyc), now_tgt, move);
+    if(was_moving) {
+      if(cnt <= cyc) {
+        h1.y = h1.x, h1.x = now_id; // u32_prev_cmd_id_
+        pstate = 0u;
+      } else {
+        cyc++;
+      }
+    }
+    loop_joints<DIVC>(a, p, c);
+    if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, pstate, qsize);
+  }
+  loop_store(state, n, i, a, jflags, K > 0);
+  st_plane(ps, n, 0, i, make_uint4(pstate | pflags, cnt, cyc, qsize));
+  st_plane(ps, n, 1, i, h1);
+  st_plane(ps, n, 2, i, make_uint4(now_id, now_dt, f2u(now_tgt[0]), f2u(now_tgt[1])));
+  st_plane(ps, n, 3, i, make_uint4(f2u(now_tgt[2]), f2u(now_tgt[3]), f2u(now_tgt[4]), c1.w));
+  st_plane(ps, n, 4, i, make_uint4(f2u(move[0]), f2u(move[1]), f2u(move[2]), f2u(move[3])));
+  st_plane(ps, n, 5, i, make_uint4(f2u(move[4]), m1.y, m1.z, m1.w));
+}
+
+__global__ void __launch_bounds__(128) adp_mode_init_kernel(uint4 *__restrict__ ps, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  uint4 h = ld_plane(ps, n, 0, i);
+  h.x     = 0u; // is_comp = false; nowState = STANDBY
+  st_plane(ps, n, 0, i, h);
+}
+
+// ADTModePositioning::push_cmd :118-124
+__global__ void __launch_bounds__(128) adp_push_kernel(uint4 *__restrict__ ps, int64_t n, const uint4 *__restrict__ cmd, const uint8_t *__restrict__ valid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  if(valid && !valid[i]) return;
+  uint4    h     = ld_plane(ps, n, 0, i);
+  uint32_t qsize = h.w > 4u ? 4u : h.w;
+  if(qsize >= 4u) { // pop_front()
+    for(int e = 1; e < 4; e++) {
+      st_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (e - 1), i, ld_plane(ps, n, RK_PS_QUEUE / 4 + 2 * e, i));
+      st_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (e - 1) + 1, i, ld_plane(ps, n, RK_PS_QUEUE / 4 + 2 * e + 1, i));
+    }
+    qsize = 3u;
+  }
+  uint4 c1 = __ldcs(cmd + n + i);
+  c1.w     = 0u;
+  st_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (int)qsize, i, __ldcs(cmd + i));
+  st_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (int)qsize + 1, i, c1);
+  h.w = qsize + 1u;
+  st_plane(ps, n, 0, i, h);
+}
+
+// ADTModePositioning::get_q_cmd_status :134-148
+__global__ void __launch_bounds__(128) adp_status_kernel(const uint4 *__restrict__ ps, int64_t n, const uint32_t *__restrict__ ids, int32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const uint4    h = ld_plane(ps, n, 0, i), h1 = ld_plane(ps, n, 1, i);
+  const uint32_t id = ids[i], qsize = h.w > 4u ? 4u : h.w;
+  int32_t        sts = 0x63;
+  for(uint32_t e = 0; e < qsize; e++)
+    if(ld_plane(ps, n, RK_PS_QUEUE / 4 + 2 * (int)e, i).x == id) sts = 0;
+  if(h1.x == id || h1.y == id) sts = 1;
+  out[i] = sts;
 }
 
 // prepare_task() + a finished INIT mode + ADTModeBase::init() -> doInit()
@@ -630,6 +769,71 @@ int rk_adt_cmdseq_status(const void *d_state, const void *d_cmdtab, int64_t n, c
   }
   if(int rc = adt_check("rk_adt_cmdseq_status", d_state, d_cmdtab, n)) return rc;
   adt_status_kernel<<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>((const uint4 *)d_state, (const uint4 *)d_cmdtab, n, d_id, d_status);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+size_t rk_adp_state_words(void) { return RK_PS_WORDS; }
+size_t rk_adp_state_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_PS_WORDS * 4u; }
+
+int rk_adp_mode_init(void *d_pstate, int64_t n, void *stream) {
+  if(n == 0) return RK_OK;
+  if(int rc = adt_check("rk_adp_mode_init", d_pstate, nullptr, n)) return rc;
+  adp_mode_init_kernel<<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_pstate, n);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_adp_push_cmd(void *d_pstate, int64_t n, const void *d_cmd, const uint8_t *d_valid, void *stream) {
+  if(n == 0) return RK_OK;
+  if(!d_cmd || ((uintptr_t)d_cmd & 15u)) {
+    set_error("rk_adp_push_cmd: d_cmd must be non-NULL and 16-byte aligned");
+    return RK_ERR_ARG;
+  }
+  if(int rc = adt_check("rk_adp_push_cmd", d_pstate, nullptr, n)) return rc;
+  adp_push_kernel<<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_pstate, n, (const uint4 *)d_cmd, d_valid);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_adp_update(const rk_adt_params_t *p, void *d_state, void *d_pstate, int64_t n, int32_t K, uint32_t *d_trace, void *stream) {
+  if(n == 0 || K == 0) return RK_OK;
+  if(!p || K < 0) {
+    set_error("rk_adp_update: params NULL or K < 0");
+    return RK_ERR_ARG;
+  }
+  if(int rc = adt_check("rk_adp_update", d_state, d_pstate, n)) return rc;
+  if(!d_pstate) {
+    set_error("rk_adp_update: d_pstate NULL");
+    return RK_ERR_ARG;
+  }
+  const float ct   = p->ctrl_time_s[RK_AJ_P1];
+  const int   divc = div_const_exact(ct);
+  const float rcp  = divc ? 1.0f / ct : 0.0f;
+  cudaStream_t st  = (cudaStream_t)stream;
+#define RK_LAUNCH_ADP(TR, DV) adp_update_kernel<TR, DV><<<adt_grid(n), 128, 0, st>>>(*p, (uint4 *)d_state, (uint4 *)d_pstate, n, K, d_trace, rcp)
+  if(d_trace) {
+    if(divc == 2) RK_LAUNCH_ADP(true, 2);
+    else if(divc == 1) RK_LAUNCH_ADP(true, 1);
+    else RK_LAUNCH_ADP(true, 0);
+  } else {
+    if(divc == 2) RK_LAUNCH_ADP(false, 2);
+    else if(divc == 1) RK_LAUNCH_ADP(false, 1);
+    else RK_LAUNCH_ADP(false, 0);
+  }
+#undef RK_LAUNCH_ADP
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_adp_cmd_status(const void *d_pstate, int64_t n, const uint32_t *d_id, int32_t *d_status, void *stream) {
+  if(n == 0) return RK_OK;
+  if(!d_id || !d_status) {
+    set_error("rk_adp_cmd_status: NULL argument");
+    return RK_ERR_ARG;
+  }
+  if(int rc = adt_check("rk_adp_cmd_status", d_pstate, nullptr, n)) return rc;
+  adp_status_kernel<<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>((const uint4 *)d_pstate, n, d_id, d_status);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }

@@ -48,6 +48,9 @@ AJF_CONNECTED, AJF_TORQUE_ON, AJF_INITIALIZED, AJF_TORQUE_PREV = 1, 2, 4, 8
 ACMD_SLOTS, ACMD_MAX_LEN, ACMD_SLOT_WORDS = 4, 32, 260
 ACMD_WORDS = ACMD_SLOTS * ACMD_SLOT_WORDS
 ADT_TRACE_WORDS = 16
+# ADTModePositioning mode block (RK_PS_*)
+PS_STATE, PS_MOVE_CNT, PS_CYCLE, PS_QSIZE, PS_PREV_ID0, PS_PREV_ID1 = 0, 1, 2, 3, 4, 5
+PS_NOW_CMD, PS_MOVE_DEG, PS_QUEUE, PS_WORDS = 8, 16, 24, 56
 ADT_AXIS = (AJ_Y0, AJ_P1, AJ_P2, AJ_R0, AJ_P3)  # mode axes J0..J4 (AD_task_main.cpp:148)
 
 

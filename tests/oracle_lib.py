@@ -43,6 +43,8 @@ def port():
         lib.orc_adt_batch.argtypes = [C.c_int, C.POINTER(_cabi.AdtParams), vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                       vp, vp, vp, vp, vp]
         lib.orc_adt_batch.restype = None
+        lib.orc_adp_batch.argtypes = lib.orc_adt_batch.argtypes
+        lib.orc_adp_batch.restype = None
         for nm in ("orc_sin", "orc_cos", "orc_normalize_rad_0to2pi", "orc_normalize_deg_0to360"):
             getattr(lib, nm).argtypes = [C.c_float]
             getattr(lib, nm).restype = C.c_float
@@ -110,6 +112,8 @@ def ref(name="libref_vdt.so"):
             lib.ref_adt_debug_seq.argtypes = [C.c_int, C.POINTER(_cabi.AdtPosCmdSeq)]
             lib.ref_adt_batch.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, vp, vp]
             lib.ref_adt_batch.restype = None
+            lib.ref_adp_batch.argtypes = lib.ref_adt_batch.argtypes
+            lib.ref_adp_batch.restype = None
         _cache[name] = lib
     return _cache[name]
 
@@ -177,6 +181,20 @@ def arm_batch(kind, op, state, cmdtab, n, K=0, seq=None, valid=None, trace=False
         assert params is None, "the compiled reference has the firmware constants wired in"
         ref("libref_arm.so").ref_adt_batch(ARM_OPS[op], _ptr(state), _ptr(cmdtab), n, 0, n, K, _ptr(seq), _ptr(valid),
                                            _ptr(tr), _ptr(ids), _ptr(status))
+    return tr, status
+
+
+def armpos_batch(kind, op, state, pstate, n, K=0, cmd=None, valid=None, trace=False, ids=None, params=None):
+    """ADTModePositioning (single-command mode) batch op on HOST SoA arrays; cmd = uint32 [2, n, 4] planes."""
+    tr = np.zeros((K, layout.ADT_TRACE_WORDS, n), dtype=np.uint32) if (trace and op == "update") else None
+    status = np.zeros(n, dtype=np.int32) if op == "status" else None
+    if kind == "port":
+        p = params or _cabi.default_arm_params()
+        port().orc_adp_batch(ARM_OPS[op], C.byref(p), _ptr(state), _ptr(pstate), n, 0, n, K, _ptr(cmd), _ptr(valid), _ptr(tr),
+                             _ptr(ids), _ptr(status))
+    else:
+        ref("libref_arm.so").ref_adp_batch(ARM_OPS[op], _ptr(state), _ptr(pstate), n, 0, n, K, _ptr(cmd), _ptr(valid), _ptr(tr),
+                                           _ptr(ids), _ptr(status))
     return tr, status
 
 
