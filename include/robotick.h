@@ -306,9 +306,8 @@ enum {
   /* last transmitted servo commands */
   RK_AS_MG_TX = 52,     /* tx1data[8] (2 words), word 2 = bytes valid, word 3 rsv     AD_joint_mg_servo.hpp:93 */
   RK_AS_BLDC_TX0 = 56,  /* 3 x {txmsg[8] (2 words), u32_txcmdid, valid}: DF_Left, DF_Right, P3 */
-  RK_AS_MG_CTRL = 68,   /* JointMgServo::pos_ctrl_ (PI_D) -- torque-control branch (AD_joint_mg_servo.cpp:104-134,
-                         * joint not initialised or torque off): reserved, carried through unchanged; in that
-                         * branch no MG frame is produced (RK_AS_MG_TX + 2 == 0) */
+  RK_AS_MG_CTRL = 68,   /* JointMgServo::pos_ctrl_ (UTIL::PI_D, the torque-control branches AD_joint_mg_servo.cpp:104-134):
+                         * prev_val_, Integ_, velLpf_ y, velLpf_ x, now_tgt_, now_error_, now_ctrl_, "InitGain applied" */
   RK_AS_WORDS = 76
 };
 enum { RK_AJ_OFS = 0, RK_AJ_RAW_TGT, RK_AJ_CURLIM, RK_AJ_RAW_NOW };

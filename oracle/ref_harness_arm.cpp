@@ -195,6 +195,12 @@ void export_state(ArmSet *s, uint32_t *w) {
   w[RK_AS_ICS_POS]    = (uint32_t)ics_pos_word(s);
   w[RK_AS_ICS_SERVO]  = (uint32_t)((((int)s->ics.pos_h << 7) | s->ics.pos_l) - 7500);
   w[RK_AS_MG_TX] = ld32(s->mg_tx), w[RK_AS_MG_TX + 1] = ld32(s->mg_tx + 4), w[RK_AS_MG_TX + 2] = (uint32_t)s->mg_valid;
+  { /* JointMgServo::pos_ctrl_ (UTIL::PI_D); word 7 = "InitGain applied" (the only gain set the firmware ever loads) */
+    auto     &c = s->j_P1.pos_ctrl_;
+    uint32_t *q = w + RK_AS_MG_CTRL;
+    q[0] = f2u(c.prev_val_), q[1] = f2u(c.Integ_), q[2] = f2u(c.velLpf_.now_Y_), q[3] = f2u(c.velLpf_.prev_X_);
+    q[4] = f2u(c.now_tgt_), q[5] = f2u(c.now_error_), q[6] = f2u(c.now_ctrl_), q[7] = (c.Pgain_ != 0.0f) ? 1u : 0u;
+  }
   for(int k = 0; k < 3; k++) {
     uint32_t *q = w + RK_AS_BLDC_TX0 + 4 * k;
     q[0] = ld32(s->bldc_tx[k]), q[1] = ld32(s->bldc_tx[k] + 4), q[2] = s->bl(k)->u32_txcmdid, q[3] = (uint32_t)s->bldc_valid[k];
@@ -232,6 +238,14 @@ void import_state(ArmSet *s, const uint32_t *w) {
     if(k == RK_AJ_P3) s->j_P3.is_torque_on_prev = prev;
   }
   s->j_P1.fl_pre_raw_tgt_deg = u2f(w[RK_AS_MG_PRE_TGT]);
+  {
+    auto           &c = s->j_P1.pos_ctrl_;
+    const uint32_t *q = w + RK_AS_MG_CTRL;
+    c.prev_val_ = c.now_val_ = u2f(q[0]), c.Integ_ = u2f(q[1]);
+    c.velLpf_.now_Y_ = c.velLpf_.prev_Y_ = u2f(q[2]), c.velLpf_.prev_X_ = u2f(q[3]);
+    c.now_tgt_ = u2f(q[4]), c.now_error_ = c.prev_error_ = u2f(q[5]), c.now_ctrl_ = u2f(q[6]);
+    c.Pgain_ = q[7] ? 0.01f : 0.0f, c.Igain_ = 0.0f, c.Dgain_ = 0.0f, c.I_limit_ = 0.0f;
+  }
   int sp                     = (int)(int32_t)w[RK_AS_ICS_SERVO] + 7500;
   s->ics.pos_h = (byte)((sp >> 7) & 0x7F), s->ics.pos_l = (byte)(sp & 0x7F);
   s->j_Y0.p_ics_serial = &s->ics;

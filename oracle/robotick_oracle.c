@@ -638,25 +638,67 @@ static void adt_mode_update(const rk_adt_params_t *p, uint32_t *w, const uint32_
 static uint32_t jflag(const uint32_t *w, int k) { return (w[RK_AS_JFLAGS] >> (4 * k)) & 0xFu; }
 static void     set_jflag(uint32_t *w, int k, uint32_t b) { w[RK_AS_JFLAGS] = (w[RK_AS_JFLAGS] & ~(0xFu << (4 * k))) | (b << (4 * k)); }
 
-/* JointMgServo::update -> subproc_posctrl   AD_joint_mg_servo.cpp:50-73,136-149.
- * The torque-control branches (not initialised / torque off; :104-134) are SURVEY 8(f)4 "next":
- * no MG frame is produced there (valid = 0), exactly what the C-ABI documents. */
+/* JointMgServo::subproc_torquectrl   AD_joint_mg_servo.cpp:104-134 with UTIL::PI_D pos_ctrl_
+ * (util_controller.hpp:86-153; constructed as PI_D(1/ctrl_time, 0, 0, 0, 0, 10), AD_joint_mg_servo.hpp:69)
+ * and the double-precision current -> raw map (AD_joint_mg_servo.hpp:120-136). */
+enum { MGC_PREV_VAL = 0, MGC_INTEG, MGC_LPF_Y, MGC_LPF_X, MGC_NOW_TGT, MGC_NOW_ERR, MGC_NOW_CTRL, MGC_GAINSET };
+static int32_t d2i_x86(double d) { /* cvttsd2si */
+  if(!(fabs(d) < 2147483648.0)) return (int32_t)0x80000000u;
+  return (int32_t)d;
+}
+static void adt_mg_torquectrl(const rk_adt_params_t *p, uint32_t *w, int ini) {
+  uint32_t *c    = w + RK_AS_MG_CTRL;
+  float     freq = 1.0f / p->ctrl_time_s[RK_AJ_P1], dt = 1.0f / freq, lpf = 10.0f;
+  float     A1 = (2.0f * freq - lpf) / (2.0f * freq + lpf), B0 = lpf / (2.0f * freq + lpf), B1 = B0;
+  float     pg = c[MGC_GAINSET] ? 0.01f : 0.0f, ig = 0.0f, dg = 0.0f, ilim = 0.0f; /* InitGain  .cpp:25-31 */
+  float     tgt = u2f(AJ(w, RK_AJ_P1, RK_AJ_RAW_TGT)), now = u2f(AJ(w, RK_AJ_P1, RK_AJ_RAW_NOW));
+  float     curlim = u2f(AJ(w, RK_AJ_P1, RK_AJ_CURLIM));
+  float     err, x, y, integ, iq;
+  double    raw;
+  const double C_A = 0.0000057204, C_B = -0.0000485371;
+  int32_t   s;
+  err   = tgt - now;
+  x     = (now - u2f(c[MGC_PREV_VAL])) * freq;
+  y     = A1 * u2f(c[MGC_LPF_Y]) + B0 * x + B1 * u2f(c[MGC_LPF_X]);
+  integ = u2f(c[MGC_INTEG]);
+  integ += ig * dt * err;
+  integ = (integ >= ilim) ? ilim : ((integ <= -ilim) ? -ilim : integ);
+  iq    = pg * err + integ - dg * y;
+  c[MGC_PREV_VAL] = f2u(now), c[MGC_INTEG] = f2u(integ), c[MGC_LPF_Y] = f2u(y), c[MGC_LPF_X] = f2u(x);
+  c[MGC_NOW_TGT] = f2u(tgt), c[MGC_NOW_ERR] = f2u(err), c[MGC_NOW_CTRL] = f2u(iq);
+  if(ini) iq -= 0.05f * orc_sin((now - u2f(AJ(w, RK_AJ_P1, RK_AJ_OFS))) * (ORC_PI / 180.0f));
+  iq = (iq > curlim) ? curlim : ((iq < -curlim) ? -curlim : iq);
+  if((double)iq >= 0) raw = (-C_B + orc_sqrt((float)(C_B * C_B + 4.0 * C_A * (double)iq))) / (2.0 * C_A);
+  else raw = (C_B - orc_sqrt((float)(C_B * C_B - 4.0 * C_A * (double)iq))) / (2.0 * C_A);
+  s = (int32_t)(int16_t)d2i_x86(-1.0f * raw);
+  s = (s > 450) ? 450 : ((s < -450) ? -450 : s);
+  w[RK_AS_MG_TX]     = 0xA1u;
+  w[RK_AS_MG_TX + 1] = (uint32_t)s & 0xFFFFu;
+  w[RK_AS_MG_TX + 2] = 1;
+}
+
+/* JointMgServo::update   AD_joint_mg_servo.cpp:50-73 */
 static void adt_mg_update(const rk_adt_params_t *p, uint32_t *w) {
   uint32_t b    = jflag(w, RK_AJ_P1);
   int      on   = (b & RK_AJF_TORQUE_ON) != 0, prev = (b & RK_AJF_TORQUE_PREV) != 0, ini = (b & RK_AJF_INITIALIZED) != 0;
   float    tgt  = u2f(AJ(w, RK_AJ_P1, RK_AJ_RAW_TGT));
+  int      k;
   w[RK_AS_MG_TX + 2] = 0;
-  if(prev && !on) {
-    /* pos_ctrl_.reset() */
+  if(prev && !on) { /* pos_ctrl_.reset()  util_controller.hpp:112-124: everything but the gains */
+    for(k = MGC_PREV_VAL; k <= MGC_NOW_CTRL; k++) w[RK_AS_MG_CTRL + k] = 0;
   } else if(!ini && on) {
-    /* subproc_torquectrl: reserved */
-  } else if(on) {
+    adt_mg_torquectrl(p, w, ini);
+  } else if(on) { /* subproc_posctrl :136-149 */
     float    v   = fabsf((tgt - u2f(w[RK_AS_MG_PRE_TGT])) / p->ctrl_time_s[RK_AJ_P1] * -10.0f);
     uint32_t vl  = (uint32_t)f2i_x86((v > 1800) ? 1800 : v) & 0xFFFFu;
     int32_t  ang = f2i_x86(tgt * (-100.0f * 10.0f));
     w[RK_AS_MG_TX]     = 0xA4u | (vl << 16);
     w[RK_AS_MG_TX + 1] = (uint32_t)ang;
     w[RK_AS_MG_TX + 2] = 1;
+  } else { /* torque off: set_myctrl_gain_params(InitGain) -- set_VelLpf_CutOff resets the IIR -- then torque control */
+    w[RK_AS_MG_CTRL + MGC_GAINSET] = 1;
+    w[RK_AS_MG_CTRL + MGC_LPF_Y] = 0, w[RK_AS_MG_CTRL + MGC_LPF_X] = 0;
+    adt_mg_torquectrl(p, w, ini);
   }
   set_jflag(w, RK_AJ_P1, (b & ~RK_AJF_TORQUE_PREV) | (on ? RK_AJF_TORQUE_PREV : 0u));
   w[RK_AS_MG_PRE_TGT] = f2u(tgt);
@@ -734,6 +776,8 @@ static void adt_bringup(const rk_adt_params_t *p, uint32_t *w) {
   AJ(w, RK_AJ_DFL, RK_AJ_CURLIM) = f2u(p->curlim_default_A[RK_AJ_R0]);
   AJ(w, RK_AJ_DFR, RK_AJ_CURLIM) = f2u(p->curlim_default_A[RK_AJ_R0]);
   AJ(w, RK_AJ_P3, RK_AJ_CURLIM)  = f2u(p->curlim_default_A[RK_AJ_P3]);
+  w[RK_AS_MG_CTRL + 7] = 1; /* JointMgServo::init(): set_myctrl_gain_params(InitGain), IIR reset */
+  w[RK_AS_MG_CTRL + 2] = 0, w[RK_AS_MG_CTRL + 3] = 0;
   w[RK_AS_FSM]     = RK_ASTATE_STANDBY | RK_AS_FSM_FIRSTCALL;
   w[RK_AS_SEQ_IDX] = (RK_ACMD_SLOTS - 1) | ((uint32_t)(RK_ACMD_SLOTS - 1) << 16);
 }

@@ -8,7 +8,7 @@
 // the kernel is issue/latency bound, not bandwidth bound.
 #include <string.h>
 
-#include "rk_vehicle_fast.cuh" // div_const()
+#include "rk_vehicle_fast.cuh" // div_const(), rk_math.cuh
 
 namespace rk {
 int div_const_exact(float c); // rk_exact.cu: 2 = exact for all x, 1 = for x == 0 or |x| >= 2^-40, 0 = no
@@ -269,7 +269,7 @@ RK_DEV void loop_store(uint4 *st, int64_t n, int64_t i, const ArmLoop &a, uint32
 struct ArmConsts { // loop invariants derived from params + flags once per launch
   float    gear_p2, gear_r0, gear_dir[3], dir_y0, mg_ctrl_time, mg_rcp;
   uint32_t bl_ms[3];
-  bool     y0_conn, y0_on, mg_pos, mg_on, bl_on[3];
+  bool     y0_conn, y0_on, mg_pos, mg_on, mg_ini, bl_on[3];
 };
 
 // exec_standby + exec_move_start: the rare, divergent part of ADTModePositioningSeq::update
@@ -336,10 +336,62 @@ RK_DEV void loop_set_targets(ArmLoop &a, const ArmConsts &c, bool moving, float 
   a.tgt_dfr = moving ? fadd(-fadd(P, R), a.ofs_dfr) : a.tgt_dfr;
 }
 
-template <int DIVC> RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c);
+// (int32_t)(double) as cvttsd2si
+RK_DEV int32_t d2i_x86(double d) { return (fabs(d) < 2147483648.0) ? __double2int_rz(d) : (int32_t)0x80000000u; }
 
-template <int DIVC>
-RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
+// The three branches of JointMgServo::update() other than position control (AD_joint_mg_servo.cpp:50-73):
+// PI_D reset on the torque on->off edge, torque control while not initialised, InitGain + torque
+// control while torque is off (subproc_torquectrl :104-134, UTIL::PI_D util_controller.hpp:86-153, the
+// double-precision current->raw map AD_joint_mg_servo.hpp:120-136).  Rare (an arm that is being homed
+// or is limp), so the PI_D block is read and written in HBM and the function is kept out of line.
+struct MgFrame {
+  uint32_t tx0, tx1, valid;
+};
+__device__ __noinline__ MgFrame mg_update_slow(MgFrame f, float tgt, float ctrl_time_s, bool prev, bool on, bool ini, uint4 *st,
+                                               int64_t n, int64_t i) {
+  uint4       q0 = ld_plane(st, n, RK_AS_MG_CTRL / 4, i), q1 = ld_plane(st, n, RK_AS_MG_CTRL / 4 + 1, i);
+  const uint4 jp = ld_plane(st, n, (RK_AS_JOINT0 + 4 * RK_AJ_P1) / 4, i); // {ofs, raw_tgt (stale), curlim, raw_now}
+  f.valid        = 0u;
+  if(prev && !on) { // pos_ctrl_.reset(): everything but the gains
+    q0 = make_uint4(0u, 0u, 0u, 0u);
+    q1.x = 0u, q1.y = 0u, q1.z = 0u;
+  } else {
+    if(!on) { // set_myctrl_gain_params(InitGain): gains + set_VelLpf_CutOff -> IIR reset
+      q1.w = 1u;
+      q0.z = 0u, q0.w = 0u;
+    }
+    const float freq = fdiv(1.0f, ctrl_time_s), dt = fdiv(1.0f, freq), lpf = 10.0f;
+    const float den  = fadd(fmul(2.0f, freq), lpf);
+    const float A1 = fdiv(fsub(fmul(2.0f, freq), lpf), den), B0 = fdiv(lpf, den);
+    const float pg = q1.w ? 0.01f : 0.0f, ig = 0.0f, dg = 0.0f, ilim = 0.0f;
+    const float now = u2f(jp.w), curlim = u2f(jp.z);
+    const float err = fsub(tgt, now);
+    const float x   = fmul(fsub(now, u2f(q0.x)), freq);
+    const float y   = fadd(fadd(fmul(A1, u2f(q0.z)), fmul(B0, x)), fmul(B0, u2f(q0.w)));
+    float integ     = fadd(u2f(q0.y), fmul(fmul(ig, dt), err));
+    integ           = (integ >= ilim) ? ilim : ((integ <= -ilim) ? -ilim : integ);
+    float iq        = fsub(fadd(fmul(pg, err), integ), fmul(dg, y));
+    q0 = make_uint4(f2u(now), f2u(integ), f2u(y), f2u(x));
+    q1.x = f2u(tgt), q1.y = f2u(err), q1.z = f2u(iq);
+    if(ini) iq = fsub(iq, fmul(0.05f, arm_sin(g_sin_table, fmul(fsub(now, u2f(jp.x)), RK_DEG2RAD))));
+    iq = (iq > curlim) ? curlim : ((iq < -curlim) ? -curlim : iq);
+    const double C_A = 0.0000057204, C_B = -0.0000485371, d = (double)iq;
+    double       raw;
+    if(d >= 0) raw = __ddiv_rn(__dadd_rn(-C_B, (double)arm_sqrt(__double2float_rn(__dadd_rn(C_B * C_B, __dmul_rn(4.0 * C_A, d))))), 2.0 * C_A);
+    else raw = __ddiv_rn(__dsub_rn(C_B, (double)arm_sqrt(__double2float_rn(__dsub_rn(C_B * C_B, __dmul_rn(4.0 * C_A, d))))), 2.0 * C_A);
+    int32_t s = sext16(d2i_x86(__dmul_rn(-1.0, raw)));
+    s         = (s > 450) ? 450 : ((s < -450) ? -450 : s);
+    f.tx0 = 0xA1u, f.tx1 = (uint32_t)s & 0xFFFFu, f.valid = 1u;
+  }
+  st_plane(st, n, RK_AS_MG_CTRL / 4, i, q0);
+  st_plane(st, n, RK_AS_MG_CTRL / 4 + 1, i, q1);
+  return f;
+}
+
+template <int DIVC, bool MGSLOW> RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i);
+
+template <int DIVC, bool MGSLOW>
+RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
   if(a.state != RK_ASTATE_MOVING) loop_fsm_transitions(a, p, tab, n, i);
   // ---- exec_moving :89-117
   const bool moving = a.state == RK_ASTATE_MOVING;
@@ -348,14 +400,23 @@ RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, 
   a.cmd_idx      = fin ? ((a.cmd_idx + 1) & 0xFFu) : a.cmd_idx;
   a.state        = fin ? (uint32_t)RK_ASTATE_MOVE_START : a.state;
   a.cyc          = (moving && !fin) ? a.cyc + 1 : a.cyc;
-  loop_joints<DIVC>(a, p, c);
+  loop_joints<DIVC, MGSLOW>(a, p, c, st, n, i);
 }
 
 // ADT::main's joint updates (AD_task_main.cpp:213-228): j_P1, j_DF_Left, j_DF_Right, j_P3, [CAN tx], j_Y0
-template <int DIVC>
-RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c) {
+// MGSLOW: the thread's MG joint is NOT in position control (c.mg_pos is invariant over the launch); the
+// kernel runs such threads through a separate instantiation of the tick loop so that the common loop
+// carries none of the torque-control code.
+template <int DIVC, bool MGSLOW>
+RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i) {
   // ---- JointMgServo::update -> subproc_posctrl  AD_joint_mg_servo.cpp:50-73,136-149
-  {
+  if(MGSLOW) {
+    MgFrame f = {a.mg_tx0, a.mg_tx1, a.mg_valid};
+    f         = mg_update_slow(f, a.tgt[1], c.mg_ctrl_time, a.mg_prev, c.mg_on, c.mg_ini, st, n, i);
+    a.mg_tx0 = f.tx0, a.mg_tx1 = f.tx1, a.mg_valid = f.valid;
+    a.mg_prev = c.mg_on;
+    a.mg_pre  = a.tgt[1];
+  } else {
     const float tgt = a.tgt[1];
     const float d   = fsub(tgt, a.mg_pre);
     float q;
@@ -370,9 +431,9 @@ RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c
     const float v   = fabsf(fmul(q, -10.0f));
     const uint32_t vl = (uint32_t)f2i_x86((v > 1800.0f) ? 1800.0f : v) & 0xFFFFu;
     const uint32_t w1 = (uint32_t)f2i_x86(fmul(tgt, -100.0f * 10.0f));
-    a.mg_tx0   = c.mg_pos ? (0xA4u | (vl << 16)) : a.mg_tx0;
-    a.mg_tx1   = c.mg_pos ? w1 : a.mg_tx1;
-    a.mg_valid = c.mg_pos ? 1u : 0u;
+    a.mg_tx0   = 0xA4u | (vl << 16);
+    a.mg_tx1   = w1;
+    a.mg_valid = 1u;
     a.mg_pre   = tgt;
   }
   // ---- JointMyBldcServo::update x3  AD_joint_mybldc_servo.cpp:7-36
@@ -412,7 +473,8 @@ RK_DEV ArmConsts make_consts(const rk_adt_params_t &p, uint32_t jflags, float mg
   c.mg_ctrl_time = p.ctrl_time_s[RK_AJ_P1], c.mg_rcp = mg_rcp;
   c.y0_conn = (fl(RK_AJ_Y0) & RK_AJF_CONNECTED) != 0, c.y0_on = (fl(RK_AJ_Y0) & RK_AJF_TORQUE_ON) != 0;
   c.mg_on  = (fl(RK_AJ_P1) & RK_AJF_TORQUE_ON) != 0;
-  c.mg_pos = c.mg_on && (fl(RK_AJ_P1) & RK_AJF_INITIALIZED) != 0; // the only branch of update() that emits a frame here
+  c.mg_ini = (fl(RK_AJ_P1) & RK_AJF_INITIALIZED) != 0;
+  c.mg_pos = c.mg_on && c.mg_ini; // position control on every tick (the branch a running arm is in)
   const int jk[3] = {RK_AJ_DFL, RK_AJ_DFR, RK_AJ_P3};
 #pragma unroll
   for(int s = 0; s < 3; s++) {
@@ -436,7 +498,7 @@ RK_DEV void arm_trace_row(uint32_t *tr, int64_t n, const ArmLoop &a, uint32_t w1
 }
 
 template <bool TRACE, int DIVC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
                   uint32_t *__restrict__ trace, float mg_rcp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,9 +519,17 @@ adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint
     ring_fetch(a, tab, n, i, fs, fi, a.sel);
     a.pf_key = ring_key(fs, fi);
   }
-  for(int t = 0; t < K; t++) {
-    loop_tick<DIVC>(a, p, c, tab, n, i);
-    if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, a.state, a.cmd_idx);
+  if(c.mg_pos) {
+    for(int t = 0; t < K; t++) {
+      loop_tick<DIVC, false>(a, p, c, state, tab, n, i);
+      if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, a.state, a.cmd_idx);
+    }
+  } else {
+#pragma unroll 1
+    for(int t = 0; t < K; t++) {
+      loop_tick<DIVC, true>(a, p, c, state, tab, n, i);
+      if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, a.state, a.cmd_idx);
+    }
   }
   loop_store(state, n, i, a, jflags, K > 0);
 }
@@ -534,7 +604,8 @@ adp_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, uint4 *__r
         cyc++;
       }
     }
-    loop_joints<DIVC>(a, p, c);
+    if(c.mg_pos) loop_joints<DIVC, false>(a, p, c, state, n, i);
+    else loop_joints<DIVC, true>(a, p, c, state, n, i);
     if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, pstate, qsize);
   }
   loop_store(state, n, i, a, jflags, K > 0);
@@ -615,6 +686,8 @@ __global__ void __launch_bounds__(128) adt_mode_init_kernel(const rk_adt_params_
   a.j[RK_AJ_DFL].curlim = p.curlim_default_A[RK_AJ_R0]; // J3 (Roll) is the last to set both motors
   a.j[RK_AJ_DFR].curlim = p.curlim_default_A[RK_AJ_R0];
   a.j[RK_AJ_P3].curlim  = p.curlim_default_A[RK_AJ_P3];
+  a.mg_ctrl[7] = 1u;                     // JointMgServo::init(): set_myctrl_gain_params(InitGain) ...
+  a.mg_ctrl[2] = 0u, a.mg_ctrl[3] = 0u;  // ... whose set_VelLpf_CutOff() resets the IIR
   a.fsm  = RK_ASTATE_STANDBY | RK_AS_FSM_FIRSTCALL;
   a.exec = RK_ACMD_SLOTS - 1, a.head = RK_ACMD_SLOTS - 1;
   store_arm(state, n, i, a);

@@ -50,9 +50,10 @@ def assert_same(a, b):
     np.testing.assert_array_equal(a[1], b[1])
 
 
-def random_arm_states(n, seed):
-    """Random but valid arm states: offsets, targets, flags (MG joint kept in its position-control
-    branch: torque on + initialised), ring indices, mid-move FSM."""
+def random_arm_states(n, seed, mg_any_branch=False):
+    """Random but valid arm states: offsets, targets, flags, ring indices, mid-move FSM.  The MG joint
+    is kept in its position-control branch (torque on + initialised) unless mg_any_branch, which also
+    randomises its PI_D state so that every branch of JointMgServo::update runs."""
     rng = np.random.default_rng(seed)
     a = np.zeros((n, layout.AS_WORDS), dtype=np.uint32)
     f = lambda lo, hi, shape: (rng.integers(int(lo * 64), int(hi * 64) + 1, shape).astype(np.float32) / np.float32(64)).view(np.uint32)
@@ -64,7 +65,11 @@ def random_arm_states(n, seed):
     a[:, layout.AS_DFV_P] = f(-300, 300, n)
     a[:, layout.AS_DFV_R] = f(-300, 300, n)
     fl = rng.integers(0, 16, (n, 7)).astype(np.uint32)
-    fl[:, layout.AJ_P1] = (fl[:, layout.AJ_P1] & 8) | 7
+    if not mg_any_branch:
+        fl[:, layout.AJ_P1] = (fl[:, layout.AJ_P1] & 8) | 7
+    else:
+        a[:, layout.AS_MG_CTRL : layout.AS_MG_CTRL + 7] = f(-2, 2, (n, 7))
+        a[:, layout.AS_MG_CTRL + 7] = rng.integers(0, 2, n)
     fl[:, [layout.AJ_Y0, layout.AJ_P2, layout.AJ_R0]] &= 7
     a[:, layout.AS_JFLAGS] = sum(fl[:, k] << np.uint32(4 * k) for k in range(7))
     a[:, layout.AS_MG_PRE_TGT] = f(-150, 150, n)
@@ -145,6 +150,27 @@ def test_random_states_port_equals_ref():
     tab[:] = layout.aos_to_soa(taos)
     script = [("update", 3), ("status", np.full(n, 2)), ("update", 120)]
     assert_same(run_script("ref", n, script, st0, tab), run_script("port", n, script, st0, tab))
+
+
+@needs_ref
+def test_mg_torque_control_branches_port_equals_ref():
+    """JointMgServo::update, all four branches (AD_joint_mg_servo.cpp:50-73): torque on->off edge
+    (PI_D reset), not initialised + torque on (torque control), position control, torque off
+    (InitGain + torque control incl. the gravity feed-forward through the CMSIS sine and the
+    double-precision current -> raw map)."""
+    n = 512
+    st0 = random_arm_states(n, seed=6, mg_any_branch=True)
+    taos = np.zeros((n, layout.ACMD_WORDS), dtype=np.uint32)
+    for s in range(4):
+        taos[:, s * 260 : (s + 1) * 260] = streams.arm_sequences(n, seed=30 + s, seq_id=s + 1, max_len=4)
+    tab = layout.aos_to_soa(taos)
+    script = [("update", 1), ("update", 2), ("update", 60)]
+    a, b = run_script("ref", n, script, st0, tab), run_script("port", n, script, st0, tab)
+    assert_same(a, b)
+    fl = (layout.soa_to_aos(st0, n, layout.AS_WORDS)[:, layout.AS_JFLAGS] >> 4) & 0xF
+    assert len(np.unique(fl)) == 16  # every flag combination of the MG joint occurred
+    tr = a[2][0]
+    assert set(np.unique(tr[0, 5, :] * 0 + (layout.soa_to_aos(a[2][1], n, layout.AS_WORDS)[:, layout.AS_MG_TX] & 0xFF))) >= {0xA1, 0xA4}
 
 
 @needs_ref

@@ -91,6 +91,19 @@ def test_arm_random_states_vs_port():
     assert_same(gpu_script(n, script, st0, tab), run_script("port", n, script, st0, tab))
 
 
+def test_mg_torque_control_branches_vs_port():
+    """Every flag combination of the MG joint: PI_D reset on the torque-off edge, torque control while not
+    initialised / limp (CMSIS sine, double-precision current->raw map), position control."""
+    n = 2048
+    st0 = random_arm_states(n, seed=6, mg_any_branch=True)
+    taos = np.zeros((n, layout.ACMD_WORDS), dtype=np.uint32)
+    for s in range(4):
+        taos[:, s * 260 : (s + 1) * 260] = streams.arm_sequences(n, seed=30 + s, seq_id=s + 1, max_len=4)
+    tab = layout.aos_to_soa(taos)
+    script = [("update", 1), ("update", 2), ("update", 60)]
+    assert_same(gpu_script(n, script, st0, tab), run_script("port", n, script, st0, tab))
+
+
 def test_arm_extreme_waypoints_vs_port():
     wp = [(0, (170, 10, 10, 10, 10)), (50, (-190, 20, -20, 5, 5)), (50, (140, 0, 0, 0, 0)), (40, (0, 0, 0, 0, 0)),
           (45, (100, -100, 100, -100, 100))]
