@@ -183,12 +183,15 @@ RK_DEV void fast_tick2(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &
   const float2 m2 = fast_wheel_sense2<-1>(f.w23.rpm[0], f.w23.cur[0], f.w23.dsum[0], fc);
   const float2 m3 = fast_wheel_sense2<-1>(f.w23.rpm[1], f.w23.cur[1], f.w23.dsum[1], fc);
   // conv_Mdir_to_Vdir on both paths at once  VD_vehicle_controller.cpp:126-130 (called at :26 and :42)
-  const float  R  = p.wheel_radius_mm;
-  const float2 vx = mul2(mul2(add2(add2(add2(m0, m1), m2), m3), bc2(0.25f), nz), bc2(R), nz);       // {vel.x, local dx}
-  const float2 vy = mul2(mul2(add2(sub2(add2(neg2(m0), m1), m2), m3), bc2(0.25f), nz), bc2(R), nz); // {vel.y, local dy}
+  // (sum * 0.25f) * R == sum * (0.25f * R) bit for bit: scaling by 2^-2 is exact in both places as long as
+  // nothing underflows, and a sum of wheel speeds / angle steps is 0 or >= 2^-40 in magnitude (they derive
+  // from int16 rpm and integer encoder steps).  The same scaling commutes with the two exact divisions.
+  const float  R = p.wheel_radius_mm, qR = fmul(0.25f, R);
+  const float2 vx = mul2(add2(add2(add2(m0, m1), m2), m3), bc2(qR), nz);       // {vel.x, local dx}
+  const float2 vy = mul2(add2(sub2(add2(neg2(m0), m1), m2), m3), bc2(qR), nz); // {vel.y, local dy}
   {
-    const float s = fmul(fadd(fadd(fsub(-m0.x, m1.x), m2.x), m3.x), 0.25f);
-    vel[2]        = fmul(div_const(div_const(s, p.sqrtf2, fc.rcp_s2), p.wheel_l_mm, fc.rcp_l), R);
+    const float s = fadd(fadd(fsub(-m0.x, m1.x), m2.x), m3.x);
+    vel[2]        = fmul(div_const(div_const(s, p.sqrtf2, fc.rcp_s2), p.wheel_l_mm, fc.rcp_l), qR);
   }
   vel[0] = vx.x, vel[1] = vy.x;
   // pos += (R(yaw) * local) * 0.001   :50-51 ; {lx*c - ly*s, lx*s + ly*c}
@@ -199,7 +202,7 @@ RK_DEV void fast_tick2(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &
   tgt[0] = txy.x, tgt[1] = txy.y;
   tgt[2] = fast_interp_update(f.th, p.ts);
   // conv_Vdir_to_Mdir  :113-118
-  const float  T  = fmul(fmul(fc.s2l, tgt[2]), 4.0f);
+  const float  T  = fmul(fmul(fc.s2l, tgt[2]), 4.0f); // (not folded: a denormal-range target would round differently)
   const float2 xy = make_float2(fsub(tgt[0], tgt[1]), fadd(tgt[0], tgt[1]));
   const float2 M01 = div_const2(sub2(xy, bc2(T)), R, fc.rcp_r, nz);
   const float2 M23 = div_const2(add2(xy, bc2(T)), R, fc.rcp_r, nz);
