@@ -92,6 +92,12 @@ typedef struct rk_vdt_params {
   float   jerk_stop[3];      /* C_JERK_MAX_STOP  {30000,30000,1000}  :44-48 */
   int32_t motor_dir[4];      /* FL,BL,BR,FR = +1,+1,-1,-1            :75-78 */
   int32_t raw_curr_lim;      /* s16_rawCurr_lim 3000          VD_motor_if_m2006.hpp:64 */
+  /* VDT::main limiters  VD_task_main.cpp:24-27 */
+  float   default_speed_mmps;  /* FL_VEHICLE_DEFAULT_SPEED_MMPS      200 */
+  float   limit_speed_mmps;    /* FL_VEHICLE_LIMIT_SPEED_MMPS        400 */
+  float   default_rot_radps;   /* FL_VEHICLE_DEFAULT_ROT_SPEED_RADPS (float)(2.0f * M_PI / 1.0f) */
+  float   limit_rot_radps;     /* FL_VEHICLE_LIMIT_ROT_SPEED_RADPS   (float)(6.0f * M_PI / 1.0f) */
+  uint32_t task_freq_hz;       /* U32_VD_TASK_CTRL_FREQ_HZ 100: move-time count = time_ms * freq / 1000 + 1  :186 */
 } rk_vdt_params_t;
 
 void rk_vdt_default_params(rk_vdt_params_t *p);
@@ -102,7 +108,7 @@ enum {
   RK_VS_POS_X = 0, RK_VS_POS_Y, RK_VS_POS_TH, RK_VS_FLAGS,
   /* plane 1-2 : now_vhcl_vel_mmps, now_vhcl_vel_tgt_mmps  (:74-75) */
   RK_VS_VEL_X, RK_VS_VEL_Y, RK_VS_VEL_TH, RK_VS_TGT_X,
-  RK_VS_TGT_Y, RK_VS_TGT_TH, RK_VS_RSV0, RK_VS_RSV1,
+  RK_VS_TGT_Y, RK_VS_TGT_TH, RK_VS_MOVE_CNT /* VDT::U32_MOVE_TIME_CNT_ORDER  VD_task_main.cpp:115 */, RK_VS_RSV1,
   /* planes 3..11 : three VelInterpConstJerk (x, y, th), 12 words each: vel_now_/acl_now_ and
    * the ACTIVE StatusBuf page (util_vel_interp.hpp:20-21,27-39).  The inactive page is fully
    * overwritten by set_target_params() before it can be read, so it carries no state. */
@@ -150,12 +156,24 @@ enum {
 enum {
   RK_CMD_NONE = 0, /* no message this segment                                    */
   RK_CMD_MOVE = 1, /* start(); set_target_vel(v, C_ACCEL_MAX_MOVE, C_JERK_MAX_MOVE)  :294-295 */
-  RK_CMD_STOP = 2  /* start(); set_target_vel(v, C_ACCEL_MAX_STOP, C_JERK_MAX_STOP)  :271-281,305-319 */
+  RK_CMD_STOP = 2, /* start(); set_target_vel(v, C_ACCEL_MAX_STOP, C_JERK_MAX_STOP)  :271-281,305-319 */
+  /* VDT::main's own message vocabulary (VD_task_main.hpp:8-60, VD_task_main.cpp:178-296): speed limiters,
+   * direction table and the move-time countdown included.  kind = id | u32_time_ms << 8 (time_ms < 2^24).
+   * Messages are taken at task-period boundaries only (seg_len must be a multiple of task_period). */
+  RK_CMD_MSG_MOVE_DIR = 3,      /* REQ_MOVE_DIR: the vx / vy slots carry u32_cmd / u32_speed as raw uint32 */
+  RK_CMD_MSG_MOVE_CONT_DIR = 4, /* REQ_MOVE_CONT_DIR: vx, vy, vth = fl_vel_x_mmps, fl_vel_y_mmps, fl_vel_th_radps */
+  RK_CMD_MSG_UNKNOWN = 5        /* a MsgId the task ignores */
+};
+/* REQ_MOVE_DIR_CMD  VD_task_main.hpp:37-49 */
+enum {
+  RK_DIR_MOVE_STOP = 0, RK_DIR_GO_FORWARD, RK_DIR_GO_BACK, RK_DIR_GO_RIGHT, RK_DIR_GO_LEFT, RK_DIR_GO_RIGHT_FORWARD,
+  RK_DIR_GO_LEFT_FORWARD, RK_DIR_GO_RIGHT_BACK, RK_DIR_GO_LEFT_BACK, RK_DIR_ROT_RIGHT, RK_DIR_ROT_LEFT
 };
 typedef struct rk_vdt_cmd { float vx, vy, vth; int32_t kind; } rk_vdt_cmd_t; /* 16 B */
 
 /* Trace record written per tick when d_trace != NULL (tests / small N only):
- * word 0-2 pos, 3-5 vel, 6-8 vel_tgt, 9-12 s16_rawCurr_tgt (sign-extended), 13-15 zero. */
+ * word 0-2 pos, 3-5 vel, 6-8 vel_tgt, 9-12 s16_rawCurr_tgt (sign-extended), 13 the move-time countdown
+ * (task_period > 0, else zero), 14-15 zero. */
 #define RK_VDT_TRACE_WORDS 16
 
 typedef struct rk_vdt_rollout {
@@ -175,6 +193,10 @@ typedef struct rk_vdt_rollout {
   /* optional rollout cost: (pos.x-gx)^2 + (pos.y-gy)^2 at the end; d_goal = float2[n] */
   const float *d_goal;
   float *d_cost;
+  /* > 0: VDT::main runs every task_period ticks (firmware: 10 = 1 kHz / 100 Hz, VD_task_main.cpp:21-22):
+   * RK_CMD_MSG_* records are decoded and the move-time countdown (U32_MOVE_TIME_CNT_ORDER, :298-316) issues
+   * the automatic stop.  0: no task loop (RK_CMD_MOVE / RK_CMD_STOP records only). */
+  int32_t task_period;
 } rk_vdt_rollout_t;
 
 /* VEHICLE_CTRL::update() x steps   (VD_vehicle_controller.cpp:6-99), fused with the callers

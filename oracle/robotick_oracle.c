@@ -47,6 +47,7 @@ typedef struct {
 typedef struct {
   float    pos[3], vel[3], tgt[3];
   int      power;
+  uint32_t move_cnt; /* VDT::U32_MOVE_TIME_CNT_ORDER */
   interp_t it[3];
   ctrl_t   c[4];
   motor_t  m[4];
@@ -74,6 +75,7 @@ static void unpack(veh_t *v, const uint32_t *w) {
     v->tgt[a] = u2f(w[RK_VS_TGT_X + a]);
   }
   v->power = (w[RK_VS_FLAGS] & RK_VS_FLAG_POWER_ON) != 0;
+  v->move_cnt = w[RK_VS_MOVE_CNT];
   for(a = 0; a < 3; a++) {
     const uint32_t *q = w + RK_VS_INTERP0 + 12 * a;
     interp_t       *t = &v->it[a];
@@ -115,6 +117,7 @@ static void pack(const veh_t *v, uint32_t *w) {
     w[RK_VS_TGT_X + a] = f2u(v->tgt[a]);
   }
   w[RK_VS_FLAGS] = v->power ? RK_VS_FLAG_POWER_ON : 0u;
+  w[RK_VS_MOVE_CNT] = v->move_cnt;
   for(a = 0; a < 3; a++) {
     uint32_t       *q = w + RK_VS_INTERP0 + 12 * a;
     const interp_t *t = &v->it[a];
@@ -355,20 +358,91 @@ static void veh_set_target(veh_t *v, const float vv[3], const float a[3], const 
   for(k = 0; k < 3; k++) interp_set(&v->it[k], vv[k], a[k], j[k]);
 }
 
+/* VDT::main's limiters  VD_task_main.cpp:119-151 */
+static float vdt_speed_limit(const rk_vdt_params_t *p, uint32_t spd) {
+  if(spd == 0) return p->default_speed_mmps;
+  return ((float)spd > p->limit_speed_mmps) ? p->limit_speed_mmps : (float)spd;
+}
+static float vdt_rot_speed_limit(const rk_vdt_params_t *p, uint32_t spd) {
+  float fl;
+  if(spd == 0) return p->default_rot_radps;
+  fl = (float)((double)(float)spd * 0.1); /* `(float)u32_spd * 0.1` is a double product, :146 */
+  return (fl > p->limit_rot_radps) ? p->limit_rot_radps : fl;
+}
+/* one received MSG_REQ: the switch of VDT::main  VD_task_main.cpp:178-296 */
+static void vdt_task_message(veh_t *v, const rk_vdt_params_t *p, const rk_vdt_cmd_t *c) {
+  uint32_t kind = (uint32_t)c->kind & 0xFFu, time_ms = (uint32_t)c->kind >> 8;
+  float    mv[3] = {0.0f, 0.0f, 0.0f};
+  const float *acl = p->accel_move, *jrk = p->jerk_move;
+  if(kind == RK_CMD_MSG_MOVE_DIR) {
+    uint32_t u[2];
+    float    speed, diag;
+    memcpy(u, &c->vx, 8);
+    v->move_cnt = time_ms * p->task_freq_hz / 1000u + 1u;
+    switch(u[0]) {
+    case RK_DIR_GO_FORWARD: mv[0] = vdt_speed_limit(p, u[1]); break;
+    case RK_DIR_GO_BACK: mv[0] = -vdt_speed_limit(p, u[1]); break;
+    case RK_DIR_GO_RIGHT: mv[1] = -vdt_speed_limit(p, u[1]); break;
+    case RK_DIR_GO_LEFT: mv[1] = vdt_speed_limit(p, u[1]); break;
+    case RK_DIR_GO_RIGHT_FORWARD:
+    case RK_DIR_GO_LEFT_FORWARD:
+    case RK_DIR_GO_RIGHT_BACK:
+    case RK_DIR_GO_LEFT_BACK:
+      speed = vdt_speed_limit(p, u[1]);
+      diag  = speed * sqrtf(2) * 0.5f; /* (+-(float)speed * sqrtf(2)) * 0.5f: the sign commutes with both products */
+      mv[0] = (u[0] == RK_DIR_GO_RIGHT_FORWARD || u[0] == RK_DIR_GO_LEFT_FORWARD) ? diag : -diag;
+      mv[1] = (u[0] == RK_DIR_GO_LEFT_FORWARD || u[0] == RK_DIR_GO_LEFT_BACK) ? diag : -diag;
+      break;
+    case RK_DIR_ROT_RIGHT: mv[2] = -vdt_rot_speed_limit(p, u[1]); break;
+    case RK_DIR_ROT_LEFT: mv[2] = vdt_rot_speed_limit(p, u[1]); break;
+    default: acl = p->accel_stop, jrk = p->jerk_stop; break; /* MOVE_STOP and anything else */
+    }
+    v->power = 1;
+    veh_set_target(v, mv, acl, jrk);
+  } else if(kind == RK_CMD_MSG_MOVE_CONT_DIR) {
+    float len, lim;
+    v->move_cnt = time_ms * p->task_freq_hz / 1000u + 1u;
+    len = orc_sqrt(c->vx * c->vx + c->vy * c->vy); /* speed_limit_xy :127-137 */
+    lim = (len > p->limit_speed_mmps) ? p->limit_speed_mmps : len;
+    if(len == 0) {
+      mv[0] = 0, mv[1] = 0;
+    } else {
+      mv[0] = c->vx * lim / len, mv[1] = c->vy * lim / len;
+    }
+    mv[2] = (c->vth > p->limit_rot_radps) ? p->limit_rot_radps : ((c->vth < -p->limit_rot_radps) ? -p->limit_rot_radps : c->vth);
+    v->power = 1;
+    veh_set_target(v, mv, p->accel_move, p->jerk_move);
+  }
+}
+/* the move-time countdown at the end of every VDT::main iteration  :298-316 */
+static void vdt_task_countdown(veh_t *v, const rk_vdt_params_t *p) {
+  if(v->move_cnt > 1) {
+    v->move_cnt--;
+  } else if(v->move_cnt == 1) {
+    float z[3] = {0.0f, 0.0f, 0.0f};
+    v->power   = 1;
+    veh_set_target(v, z, p->accel_stop, p->jerk_stop);
+    v->move_cnt = 0;
+  }
+}
+
 static void rollout_one(veh_t *v, const rk_vdt_params_t *p, int64_t n, int64_t i, const rk_vdt_rollout_t *a) {
   int t, k, j;
   for(t = 0; t < a->steps; t++) {
     int16_t us;
-    if(a->d_cmd && a->seg_len > 0 && (t % a->seg_len) == 0 && (t / a->seg_len) < a->n_seg) {
-      const rk_vdt_cmd_t *c = &a->d_cmd[(int64_t)(t / a->seg_len) * n + i];
-      if(c->kind != RK_CMD_NONE) {
-        float vv[3] = {c->vx, c->vy, c->vth};
-        v->power    = 1; /* VEHICLE_CTRL::start()  VD_vehicle_controller.hpp:54 */
-        if(c->kind == RK_CMD_STOP)
-          veh_set_target(v, vv, p->accel_stop, p->jerk_stop);
-        else
-          veh_set_target(v, vv, p->accel_move, p->jerk_move);
-      }
+    const rk_vdt_cmd_t *c = NULL;
+    if(a->d_cmd && a->seg_len > 0 && (t % a->seg_len) == 0 && (t / a->seg_len) < a->n_seg) c = &a->d_cmd[(int64_t)(t / a->seg_len) * n + i];
+    if(c && ((uint32_t)c->kind & 0xFFu) != RK_CMD_NONE && ((uint32_t)c->kind & 0xFFu) < RK_CMD_MSG_MOVE_DIR) {
+      float vv[3] = {c->vx, c->vy, c->vth};
+      v->power    = 1; /* VEHICLE_CTRL::start()  VD_vehicle_controller.hpp:54 */
+      if(c->kind == RK_CMD_STOP)
+        veh_set_target(v, vv, p->accel_stop, p->jerk_stop);
+      else
+        veh_set_target(v, vv, p->accel_move, p->jerk_move);
+    }
+    if(a->task_period > 0 && (t % a->task_period) == 0) { /* one VDT::main iteration */
+      if(c) vdt_task_message(v, p, c);
+      vdt_task_countdown(v, p);
     }
     if(a->d_yaw && a->yaw_period > 0 && (t % a->yaw_period) == 0 && (t / a->yaw_period) < a->n_yaw)
       v->pos[2] = a->d_yaw[(int64_t)(t / a->yaw_period) * n + i]; /* set_now_yaw_world :57 */
@@ -395,7 +469,8 @@ static void rollout_one(veh_t *v, const rk_vdt_params_t *p, int64_t n, int64_t i
         tr[(int64_t)(6 + j) * n] = f2u(v->tgt[j]);
       }
       for(k = 0; k < 4; k++) tr[(int64_t)(9 + k) * n] = (uint32_t)(int32_t)v->m[k].cur_tgt;
-      for(j = 13; j < 16; j++) tr[(int64_t)j * n] = 0;
+      tr[(int64_t)13 * n] = (a->task_period > 0) ? v->move_cnt : 0u;
+      for(j = 14; j < 16; j++) tr[(int64_t)j * n] = 0;
     }
   }
   if(a->d_cost && a->d_goal) {

@@ -26,7 +26,12 @@ typedef bool    boolean;
 
 static inline void     pinMode(int, int) {}
 static inline void     digitalWrite(int, int) {}
+/* micros(): a harness that needs a running clock defines ORACLE_MICROS_EXTERN before including this header */
+#ifdef ORACLE_MICROS_EXTERN
+uint32_t micros();
+#else
 static inline uint32_t micros() { return 0; }
+#endif
 static inline uint32_t millis() { return 0; }
 static inline void     delay(uint32_t) {}
 
@@ -56,6 +61,17 @@ public:
 private:
   uint8_t buf_[512];
   size_t  n_ = 0, pos_ = 0;
+};
+
+/* Teensy IntervalTimer: keeps the callback so the harness can fire the 1 kHz ISR itself */
+class IntervalTimer {
+public:
+  bool begin(void (*fn)(), uint32_t period) {
+    isr = fn, arg = period;
+    return true;
+  }
+  void (*isr)() = nullptr;
+  uint32_t arg  = 0;
 };
 
 extern HardwareSerial Serial6;

@@ -14,6 +14,9 @@ RK_OK = 0
 # ---- enums of robotick.h -------------------------------------------------------------
 RK_SENSOR_HOLD, RK_SENSOR_PLANT, RK_SENSOR_STREAM = 0, 1, 2
 RK_CMD_NONE, RK_CMD_MOVE, RK_CMD_STOP = 0, 1, 2
+RK_CMD_MSG_MOVE_DIR, RK_CMD_MSG_MOVE_CONT_DIR, RK_CMD_MSG_UNKNOWN = 3, 4, 5
+(RK_DIR_MOVE_STOP, RK_DIR_GO_FORWARD, RK_DIR_GO_BACK, RK_DIR_GO_RIGHT, RK_DIR_GO_LEFT, RK_DIR_GO_RIGHT_FORWARD,
+ RK_DIR_GO_LEFT_FORWARD, RK_DIR_GO_RIGHT_BACK, RK_DIR_GO_LEFT_BACK, RK_DIR_ROT_RIGHT, RK_DIR_ROT_LEFT) = range(11)
 RK_VDT_TRACE_WORDS = 16
 RK_OPT_FORCE_TRANSCRIPTION = 1
 RK_OPT_FAST_OCCUPANCY = 2
@@ -42,6 +45,11 @@ class VdtParams(C.Structure):
         ("jerk_stop", C.c_float * 3),
         ("motor_dir", C.c_int32 * 4),
         ("raw_curr_lim", C.c_int32),
+        ("default_speed_mmps", C.c_float),
+        ("limit_speed_mmps", C.c_float),
+        ("default_rot_radps", C.c_float),
+        ("limit_rot_radps", C.c_float),
+        ("task_freq_hz", C.c_uint32),
     ]
 
 
@@ -66,7 +74,7 @@ class VdtRollout(C.Structure):
         ("d_frames", C.c_void_p),
         ("d_trace", C.c_void_p),
         ("d_goal", C.c_void_p),
-        ("d_cost", C.c_void_p),
+        ("d_cost", C.c_void_p),        ("task_period", C.c_int32),
     ]
 
 
@@ -237,6 +245,11 @@ def default_params():
     p.jerk_stop[:] = [30000.0, 30000.0, 1000.0]
     p.motor_dir[:] = [1, 1, -1, -1]
     p.raw_curr_lim = 3000
+    import math
+
+    p.default_speed_mmps, p.limit_speed_mmps = 200.0, 400.0
+    p.default_rot_radps, p.limit_rot_radps = 2.0 * math.pi, 6.0 * math.pi  # double expressions stored as float (:25,:27)
+    p.task_freq_hz = 100
     return p
 
 

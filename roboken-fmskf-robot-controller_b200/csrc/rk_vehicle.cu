@@ -1,5 +1,6 @@
 // rk_vehicle.cu -- vehicle kernels + their C-ABI entry points (include/robotick.h).
 #include <limits.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -29,26 +30,13 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
   float         cth, sth;
   yaw_trig(s_tab, v.pos[2], cth, sth);
 
-  const bool has_cmd  = a.d_cmd != nullptr && a.seg_len > 0 && a.n_seg > 0;
   const bool has_yaw  = a.d_yaw != nullptr && a.yaw_period > 0 && a.n_yaw > 0;
-  int        next_cmd = has_cmd ? 0 : INT_MAX, seg = 0;
   int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
+  Sched      sc;
+  sched_init(sc, a);
 
   for(int t = 0; t < a.steps; t++) {
-    if(t == next_cmd) { // VDT::main -> start(); set_target_vel()   VD_task_main.cpp:280-281,294-295
-      const uint4 cq = __ldcs(reinterpret_cast<const uint4 *>(a.d_cmd) + (int64_t)seg * n + i);
-      const int   kind = (int)cq.w;
-      if(kind != RK_CMD_NONE) {
-        const float vv[3] = {u2f(cq.x), u2f(cq.y), u2f(cq.z)};
-        v.flags |= RK_VS_FLAG_POWER_ON;
-        if(kind == RK_CMD_STOP)
-          veh_set_target(v, vv, p.accel_stop, p.jerk_stop);
-        else
-          veh_set_target(v, vv, p.accel_move, p.jerk_move);
-      }
-      seg++;
-      next_cmd = (seg < a.n_seg) ? next_cmd + a.seg_len : INT_MAX;
-    }
+    sched_events(v, p, a, n, i, t, sc);
     if(t == next_yaw) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
       v.pos[2] = __ldcs(a.d_yaw + (int64_t)yk * n + i);
       yaw_trig(s_tab, v.pos[2], cth, sth);
@@ -78,8 +66,8 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
       }
 #pragma unroll
       for(int k = 0; k < 4; k++) tr[(int64_t)(9 + k) * n] = (uint32_t)v.m[k].cur_tgt;
-#pragma unroll
-      for(int j = 13; j < 16; j++) tr[(int64_t)j * n] = 0u;
+      tr[(int64_t)13 * n] = (a.task_period > 0) ? v.move_cnt : 0u;
+      tr[(int64_t)14 * n] = 0u, tr[(int64_t)15 * n] = 0u;
     }
   }
   store_veh(state, n, i, v);
@@ -107,14 +95,14 @@ constexpr int kFastUnroll  = RK_FAST_UNROLL;
 
 template <bool TRACE>
 RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, float py, float pth, const float vel[3],
-                      const float tgt[3], int c0, int c1, int c2, int c3) {
+                      const float tgt[3], int c0, int c1, int c2, int c3, uint32_t cnt) {
   if(!TRACE) return;
   uint32_t *tr = d_trace + (int64_t)t * RK_VDT_TRACE_WORDS * n + i;
   tr[0] = f2u(px), tr[n] = f2u(py), tr[2 * n] = f2u(pth);
 #pragma unroll
   for(int j = 0; j < 3; j++) tr[(int64_t)(3 + j) * n] = f2u(vel[j]), tr[(int64_t)(6 + j) * n] = f2u(tgt[j]);
   tr[9 * n] = (uint32_t)c0, tr[10 * n] = (uint32_t)c1, tr[11 * n] = (uint32_t)c2, tr[12 * n] = (uint32_t)c3;
-  tr[13 * n] = 0u, tr[14 * n] = 0u, tr[15 * n] = 0u;
+  tr[13 * n] = cnt, tr[14 * n] = 0u, tr[15 * n] = 0u;
 }
 
 template <bool TRACE, int OCC, bool FFSAT, bool PACKED>
@@ -141,11 +129,11 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
   float cth, sth;
   yaw_trig(s_tab, v.pos[2], cth, sth);
 
-  const bool has_cmd  = a.d_cmd != nullptr && a.seg_len > 0 && a.n_seg > 0;
   const bool has_yaw  = a.d_yaw != nullptr && a.yaw_period > 0 && a.n_yaw > 0;
-  int        next_cmd = has_cmd ? 0 : INT_MAX, seg = 0;
   int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
   const int  K        = a.steps;
+  Sched      sch;
+  sched_init(sch, a);
   // The yaw sample for the next boundary is fetched one period ahead, so its HBM latency
   // hides behind yaw_period ticks of arithmetic instead of stalling every warp at once.
   float yaw_pf = has_yaw ? __ldcs(a.d_yaw + i) : 0.0f;
@@ -163,21 +151,11 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
 
   int t = 0;
   while(t < K) {
-    if(t == next_cmd) { // VDT::main -> start(); set_target_vel()   VD_task_main.cpp:280-281,294-295
-      const uint4 cq   = __ldcs(reinterpret_cast<const uint4 *>(a.d_cmd) + (int64_t)seg * n + i);
-      const int   kind = (int)cq.w;
-      if(kind != RK_CMD_NONE) {
-        const float vv[3] = {u2f(cq.x), u2f(cq.y), u2f(cq.z)};
-        v.flags |= RK_VS_FLAG_POWER_ON;
-        if(kind == RK_CMD_STOP)
-          veh_set_target(v, vv, p.accel_stop, p.jerk_stop);
-        else
-          veh_set_target(v, vv, p.accel_move, p.jerk_move);
-      }
-      seg++;
-      next_cmd = (seg < a.n_seg) ? next_cmd + a.seg_len : INT_MAX;
-    }
-    const int t_end = min(next_cmd, K - 1); // the last tick of the launch is a transcription tick
+    sched_events(v, p, a, n, i, t, sch); // commands, VDT::main messages and the move-time countdown due at this tick
+    // run to the next event: a command, the countdown's automatic stop, or the last tick of the launch
+    // (always a transcription tick).  Lanes of a warp whose countdowns fire at different ticks leave
+    // the fast loop at different times; results do not depend on it.
+    const int t_end = min(min(sch.next_cmd, sched_fire_tick(v, a, sch)), K - 1);
     if(t < t_end && fast_ok<D0, D1, D2, D3>(v, p)) {
       const int t0  = t;
       float     pth = v.pos[2];
@@ -193,11 +171,13 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
           for(; t < t_stop; t++) {
             float vel[3], tgt[3];
             fast_tick2<FFSAT>(f, p, fc, cs, sc, nz, vel, tgt);
-            trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1]);
+            trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1],
+                             TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
           }
         }
         v.pos[2] = pth;
         from_fast2<D0, D1, D2, D3>(v, f, t - t0);
+        sched_skip_to(v, a, sch, t);
       } else {
         FastVeh f;
         to_fast<D0, D1, D2, D3>(v, f, p.ts, fc.B0);
@@ -208,11 +188,13 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
           for(; t < t_stop; t++) {
             float vel[3], tgt[3];
             fast_tick<D0, D1, D2, D3, FFSAT>(f, p, fc, cth, sth, vel, tgt);
-            trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur);
+            trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur,
+                             TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
           }
         }
         v.pos[2] = pth;
         from_fast<D0, D1, D2, D3>(v, f, t - t0);
+        sched_skip_to(v, a, sch, t);
       }
     } else {
       if(t == next_yaw) take_yaw(v.pos[2]);
@@ -221,7 +203,7 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
       for(int k = 0; k < 4; k++) motor_rx(v.m[k], p.motor_dir[k], plant_frame(v.m[k]), us);
       veh_update(v, p, d, cth, sth);
       trace_row<TRACE>(a.d_trace, n, i, t, v.pos[0], v.pos[1], v.pos[2], v.vel, v.tgt, v.m[0].cur_tgt, v.m[1].cur_tgt,
-                       v.m[2].cur_tgt, v.m[3].cur_tgt);
+                       v.m[2].cur_tgt, v.m[3].cur_tgt, (a.task_period > 0) ? v.move_cnt : 0u);
       t++;
     }
   }
@@ -415,6 +397,9 @@ void rk_vdt_default_params(rk_vdt_params_t *p) {
   for(int k = 0; k < 3; k++) p->accel_move[k] = am[k], p->jerk_move[k] = jm[k], p->accel_stop[k] = as[k], p->jerk_stop[k] = js[k];
   p->motor_dir[0] = 1, p->motor_dir[1] = 1, p->motor_dir[2] = -1, p->motor_dir[3] = -1;
   p->raw_curr_lim = 3000;
+  p->default_speed_mmps = 200.0f, p->limit_speed_mmps = 400.0f;                    // VD_task_main.cpp:24,26
+  p->default_rot_radps = (float)(2.0f * M_PI / 1.0f), p->limit_rot_radps = (float)(6.0f * M_PI / 1.0f); // :25,27 (double expressions)
+  p->task_freq_hz = 100; // :22
 }
 
 size_t rk_vdt_state_words(void) { return RK_VS_WORDS; }
@@ -437,6 +422,10 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
   }
   if(args->sensor_mode == RK_SENSOR_STREAM && (!args->d_frames || ((uintptr_t)args->d_frames & 7u) != 0)) {
     set_error("rk_vdt_rollout: RK_SENSOR_STREAM needs 8-byte aligned d_frames");
+    return RK_ERR_ARG;
+  }
+  if(args->task_period < 0 || (args->task_period > 0 && args->d_cmd && args->seg_len % args->task_period != 0)) {
+    set_error("rk_vdt_rollout: task_period must be >= 0 and divide seg_len (messages are taken at task-period boundaries)");
     return RK_ERR_ARG;
   }
   if(int rc = require_device()) return rc;

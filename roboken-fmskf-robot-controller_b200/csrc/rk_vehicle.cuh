@@ -9,6 +9,8 @@
 // operation.
 #pragma once
 #include "rk_common.cuh"
+#include <limits.h>
+
 #include "rk_math.cuh"
 
 namespace rk {
@@ -34,6 +36,7 @@ struct Motor { // MOTOR_IF_M2006 head Status + sums + synthetic plant
 struct Veh {
   float    pos[3], vel[3], tgt[3];
   uint32_t flags;
+  uint32_t move_cnt, rsv1; // VDT::U32_MOVE_TIME_CNT_ORDER (VD_task_main.cpp:115); reserved word, carried through
   Interp   it[3];
   Ctrl     c[4];
   Motor    m[4];
@@ -107,7 +110,7 @@ RK_DEV void load_veh(const uint4 *blk, int64_t n, int64_t i, Veh &v) {
   uint4 q0 = ld_plane(blk, n, 0, i), q1 = ld_plane(blk, n, 1, i), q2 = ld_plane(blk, n, 2, i);
   v.pos[0] = u2f(q0.x), v.pos[1] = u2f(q0.y), v.pos[2] = u2f(q0.z), v.flags = q0.w;
   v.vel[0] = u2f(q1.x), v.vel[1] = u2f(q1.y), v.vel[2] = u2f(q1.z), v.tgt[0] = u2f(q1.w);
-  v.tgt[1] = u2f(q2.x), v.tgt[2] = u2f(q2.y);
+  v.tgt[1] = u2f(q2.x), v.tgt[2] = u2f(q2.y), v.move_cnt = q2.z, v.rsv1 = q2.w;
 #pragma unroll
   for(int a = 0; a < 3; a++) load_interp(blk, n, i, a, v.it[a]);
 #pragma unroll
@@ -118,7 +121,7 @@ RK_DEV void load_veh(const uint4 *blk, int64_t n, int64_t i, Veh &v) {
 RK_DEV void store_veh(uint4 *blk, int64_t n, int64_t i, const Veh &v) {
   st_plane(blk, n, 0, i, make_uint4(f2u(v.pos[0]), f2u(v.pos[1]), f2u(v.pos[2]), v.flags));
   st_plane(blk, n, 1, i, make_uint4(f2u(v.vel[0]), f2u(v.vel[1]), f2u(v.vel[2]), f2u(v.tgt[0])));
-  st_plane(blk, n, 2, i, make_uint4(f2u(v.tgt[1]), f2u(v.tgt[2]), 0u, 0u));
+  st_plane(blk, n, 2, i, make_uint4(f2u(v.tgt[1]), f2u(v.tgt[2]), v.move_cnt, v.rsv1));
 #pragma unroll
   for(int a = 0; a < 3; a++) store_interp(blk, n, i, a, v.it[a]);
 #pragma unroll
@@ -316,6 +319,121 @@ RK_DEV void veh_update(Veh &v, const rk_vdt_params_t &p, const Derived &d, float
 RK_DEV void veh_set_target(Veh &v, const float vv[3], const float a[3], const float j[3]) {
 #pragma unroll
   for(int k = 0; k < 3; k++) interp_set(v.it[k], vv[k], a[k], j[k]);
+}
+
+// ---- VDT::main, the 100 Hz command layer (VD_task_main.cpp:119-151,165-322) ---------------------
+// speed_limit :119-125 / rot_speed_limit :144-151
+RK_DEV float vdt_speed_limit(const rk_vdt_params_t &p, uint32_t spd) {
+  if(spd == 0u) return p.default_speed_mmps;
+  const float f = __uint2float_rn(spd);
+  return (f > p.limit_speed_mmps) ? p.limit_speed_mmps : f;
+}
+RK_DEV float vdt_rot_speed_limit(const rk_vdt_params_t &p, uint32_t spd) {
+  if(spd == 0u) return p.default_rot_radps;
+  const float f = __double2float_rn(__dmul_rn((double)__uint2float_rn(spd), 0.1)); // `(float)u32_spd * 0.1`: a double product
+  return (f > p.limit_rot_radps) ? p.limit_rot_radps : f;
+}
+// one received MSG_REQ (the switch at :178-296); cq = {vx | u32_cmd, vy | u32_speed, vth, kind | time_ms << 8}
+RK_DEV void vdt_task_message(Veh &v, const rk_vdt_params_t &p, uint4 cq) {
+  const uint32_t kind = cq.w & 0xFFu, time_ms = cq.w >> 8;
+  float          mv[3] = {0.0f, 0.0f, 0.0f};
+  if(kind == RK_CMD_MSG_MOVE_DIR) {
+    v.move_cnt = time_ms * p.task_freq_hz / 1000u + 1u;
+    bool stop  = false;
+    switch(cq.x) {
+    case RK_DIR_GO_FORWARD: mv[0] = vdt_speed_limit(p, cq.y); break;
+    case RK_DIR_GO_BACK: mv[0] = -vdt_speed_limit(p, cq.y); break;
+    case RK_DIR_GO_RIGHT: mv[1] = -vdt_speed_limit(p, cq.y); break;
+    case RK_DIR_GO_LEFT: mv[1] = vdt_speed_limit(p, cq.y); break;
+    case RK_DIR_GO_RIGHT_FORWARD:
+    case RK_DIR_GO_LEFT_FORWARD:
+    case RK_DIR_GO_RIGHT_BACK:
+    case RK_DIR_GO_LEFT_BACK: {
+      // (+-(float)speed * sqrtf(2)) * 0.5f: the sign commutes with both products
+      const float diag = fmul(fmul(vdt_speed_limit(p, cq.y), 1.41421354f /* sqrtf(2) */), 0.5f);
+      mv[0] = (cq.x == RK_DIR_GO_RIGHT_FORWARD || cq.x == RK_DIR_GO_LEFT_FORWARD) ? diag : -diag;
+      mv[1] = (cq.x == RK_DIR_GO_LEFT_FORWARD || cq.x == RK_DIR_GO_LEFT_BACK) ? diag : -diag;
+    } break;
+    case RK_DIR_ROT_RIGHT: mv[2] = -vdt_rot_speed_limit(p, cq.y); break;
+    case RK_DIR_ROT_LEFT: mv[2] = vdt_rot_speed_limit(p, cq.y); break;
+    default: stop = true; break; // MOVE_STOP and any other code
+    }
+    v.flags |= RK_VS_FLAG_POWER_ON;
+    if(stop) veh_set_target(v, mv, p.accel_stop, p.jerk_stop);
+    else veh_set_target(v, mv, p.accel_move, p.jerk_move);
+  } else if(kind == RK_CMD_MSG_MOVE_CONT_DIR) {
+    v.move_cnt     = time_ms * p.task_freq_hz / 1000u + 1u;
+    const float vx = u2f(cq.x), vy = u2f(cq.y), vth = u2f(cq.z);
+    const float len = arm_sqrt(fadd(fmul(vx, vx), fmul(vy, vy))); // speed_limit_xy :127-137
+    const float lim = (len > p.limit_speed_mmps) ? p.limit_speed_mmps : len;
+    if(len != 0.0f) mv[0] = fdiv(fmul(vx, lim), len), mv[1] = fdiv(fmul(vy, lim), len);
+    mv[2] = (vth > p.limit_rot_radps) ? p.limit_rot_radps : ((vth < -p.limit_rot_radps) ? -p.limit_rot_radps : vth);
+    v.flags |= RK_VS_FLAG_POWER_ON;
+    veh_set_target(v, mv, p.accel_move, p.jerk_move);
+  }
+}
+// the move-time countdown that ends every VDT::main iteration  :298-316
+RK_DEV void vdt_task_countdown(Veh &v, const rk_vdt_params_t &p) {
+  if(v.move_cnt > 1u) {
+    v.move_cnt--;
+  } else if(v.move_cnt == 1u) {
+    const float z[3] = {0.0f, 0.0f, 0.0f};
+    v.flags |= RK_VS_FLAG_POWER_ON;
+    veh_set_target(v, z, p.accel_stop, p.jerk_stop);
+    v.move_cnt = 0u;
+  }
+}
+
+// Command / task events scheduled at tick t (commands BEFORE the tick, as rk_vdt_rollout_t documents).
+struct Sched {
+  int next_cmd, seg, next_task;
+};
+RK_DEV void sched_init(Sched &s, const rk_vdt_rollout_t &a) {
+  const bool has_cmd = a.d_cmd != nullptr && a.seg_len > 0 && a.n_seg > 0;
+  s.next_cmd = has_cmd ? 0 : INT_MAX, s.seg = 0;
+  s.next_task = (a.task_period > 0) ? 0 : INT_MAX;
+}
+RK_DEV void sched_events(Veh &v, const rk_vdt_params_t &p, const rk_vdt_rollout_t &a, int64_t n, int64_t i, int t, Sched &s) {
+  uint4 cq   = make_uint4(0u, 0u, 0u, 0u);
+  bool  have = false;
+  if(t == s.next_cmd) {
+    cq   = __ldcs(reinterpret_cast<const uint4 *>(a.d_cmd) + (int64_t)s.seg * n + i);
+    have = true;
+    const uint32_t kind = cq.w & 0xFFu;
+    if(kind == RK_CMD_MOVE || kind == RK_CMD_STOP) { // VDT::main -> start(); set_target_vel()   VD_task_main.cpp:280-281,294-295
+      const float vv[3] = {u2f(cq.x), u2f(cq.y), u2f(cq.z)};
+      v.flags |= RK_VS_FLAG_POWER_ON;
+      if(kind == RK_CMD_STOP) veh_set_target(v, vv, p.accel_stop, p.jerk_stop);
+      else veh_set_target(v, vv, p.accel_move, p.jerk_move);
+    }
+    s.seg++;
+    s.next_cmd = (s.seg < a.n_seg) ? s.next_cmd + a.seg_len : INT_MAX;
+  }
+  if(t == s.next_task) { // one VDT::main iteration: message (if any), then the countdown
+    if(have) vdt_task_message(v, p, cq);
+    vdt_task_countdown(v, p);
+    s.next_task += a.task_period;
+  }
+}
+// tick at which the countdown will issue its stop, given the state after the events of the current tick
+RK_DEV int sched_fire_tick(const Veh &v, const rk_vdt_rollout_t &a, const Sched &s) {
+  if(s.next_task == INT_MAX || v.move_cnt == 0u) return INT_MAX;
+  const long long f = (long long)s.next_task + (long long)(v.move_cnt - 1u) * (long long)a.task_period;
+  return f > (long long)INT_MAX ? INT_MAX : (int)f;
+}
+// after jumping from a tick < t_now to t_now without visiting the task boundaries in between: each of them
+// only decremented the countdown (the jump never crosses sched_fire_tick)
+RK_DEV void sched_skip_to(Veh &v, const rk_vdt_rollout_t &a, Sched &s, int t_now) {
+  if(s.next_task == INT_MAX || t_now <= s.next_task) return;
+  const int passed = (t_now - 1 - s.next_task) / a.task_period + 1;
+  if(v.move_cnt > 0u) v.move_cnt -= (uint32_t)passed;
+  s.next_task += passed * a.task_period;
+}
+// the countdown as it stands after tick t's events, for the trace (word 13)
+RK_DEV uint32_t sched_cnt_at(uint32_t move_cnt, const rk_vdt_rollout_t &a, const Sched &s, int t) {
+  if(a.task_period <= 0) return 0u;
+  if(move_cnt == 0u || t < s.next_task) return move_cnt;
+  return move_cnt - (uint32_t)((t - s.next_task) / a.task_period + 1);
 }
 
 } // namespace rk

@@ -8,7 +8,7 @@ import numpy as np
 # ---- vehicle (RK_VS_*) ----------------------------------------------------------------
 VS_POS_X, VS_POS_Y, VS_POS_TH, VS_FLAGS = 0, 1, 2, 3
 VS_VEL_X, VS_VEL_Y, VS_VEL_TH, VS_TGT_X = 4, 5, 6, 7
-VS_TGT_Y, VS_TGT_TH = 8, 9
+VS_TGT_Y, VS_TGT_TH, VS_MOVE_CNT = 8, 9, 10
 VS_INTERP0 = 12
 VS_CTRL0 = VS_INTERP0 + 3 * 12
 VS_MOTOR0 = VS_CTRL0 + 4 * 8

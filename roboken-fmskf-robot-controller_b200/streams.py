@@ -67,7 +67,7 @@ def vehicle_commands(n, n_seg, seed=0x5EED, first=0, stop_every=8):
 DEG2RAD = np.float32(np.float32(3.14159265358979) / np.float32(180.0))  # util_mymath.hpp:13
 
 
-def vehicle_yaw(n, n_yaw, seed=0x5EED, first=0):
+def vehicle_yaw(n, n_yaw, seed=0x5EED, first=0, degrees=False):
     """Yaw stream at the IMU rate: integer-stepped triangle wave in whole degrees in
     [-180, 180), converted with mymath::deg2rad (util_mymath.hpp:16).  [n_yaw, n] float32."""
     inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[None, :]
@@ -76,6 +76,8 @@ def vehicle_yaw(n, n_yaw, seed=0x5EED, first=0):
     rate = (_hash(seed, 6, inst, 0) % np.uint64(5)).astype(np.int64) + 1  # deg per IMU sample
     u = (phase + rate * k) % 720
     deg = np.where(u < 360, u - 180, 539 - u)  # -180..179 then 179..-180
+    if degrees:  # what IMT::get_status_now_yaw() reports; the ISR applies mymath::deg2rad itself (VD_task_main.cpp:368)
+        return deg.astype(np.float32)
     return (deg.astype(np.float32) * DEG2RAD).astype(np.float32)
 
 
@@ -153,3 +155,33 @@ def arm_seq_image(seq_id, waypoints):
         img[4 + 8 * k] = dt
         img[5 + 8 * k : 10 + 8 * k] = np.asarray(deg, dtype=np.float32).view(np.uint32)
     return img
+
+
+def vehicle_messages(n, n_seg, seed=0x5EED, first=0):
+    """VDT::main message schedule (VD_task_main.hpp:8-60): [n_seg, n] rk_vdt_cmd_t records of kind
+    RK_CMD_MSG_*: 5/8 REQ_MOVE_DIR (direction 0..12 incl. two undefined codes, speed 0 = default / up to 700
+    = over the limit, time 0..1500 ms), 2/8 REQ_MOVE_CONT_DIR (vx, vy ~ U[-600, 600] mm/s, vth ~ U[-25, 25]
+    rad/s: both limiters act; 1 in 16 is exactly zero), 1/8 nothing / an ignored MsgId."""
+    inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[None, :]
+    seg = np.arange(n_seg, dtype=np.uint64)[:, None]
+    f32 = np.float32
+    sel = (_hash(seed, 40, inst, seg) % np.uint64(8)).astype(np.int64)
+    time_ms = (_hash(seed, 41, inst, seg) % np.uint64(1501)).astype(np.uint32)
+    time_ms[(_hash(seed, 42, inst, seg) % np.uint64(6)) == 0] = 0
+    d = (_hash(seed, 43, inst, seg) % np.uint64(13)).astype(np.uint32)
+    spd = (_hash(seed, 44, inst, seg) % np.uint64(701)).astype(np.uint32)
+    spd[(_hash(seed, 45, inst, seg) % np.uint64(5)) == 0] = 0
+    vx = _u01(_hash(seed, 46, inst, seg)) * f32(1200.0) - f32(600.0)
+    vy = _u01(_hash(seed, 47, inst, seg)) * f32(1200.0) - f32(600.0)
+    vth = _u01(_hash(seed, 48, inst, seg)) * f32(50.0) - f32(25.0)
+    zero = (_hash(seed, 49, inst, seg) % np.uint64(16)) == 0
+    vx, vy = np.where(zero, f32(0), vx), np.where(zero, f32(0), vy)
+    cmd = np.zeros((n_seg, n), dtype=np.dtype([("vx", "<f4"), ("vy", "<f4"), ("vth", "<f4"), ("kind", "<i4")]))
+    is_dir, is_cont, is_unk = sel < 5, (sel == 5) | (sel == 6), (sel == 7) & (time_ms % 2 == 1)
+    cmd["vx"] = np.where(is_dir, d.view(np.float32), np.where(is_cont, vx, f32(0)))
+    cmd["vy"] = np.where(is_dir, spd.view(np.float32), np.where(is_cont, vy, f32(0)))
+    cmd["vth"] = np.where(is_cont, vth, f32(0))
+    kind = np.where(is_dir, _cabi.RK_CMD_MSG_MOVE_DIR, np.where(is_cont, _cabi.RK_CMD_MSG_MOVE_CONT_DIR,
+                                                               np.where(is_unk, _cabi.RK_CMD_MSG_UNKNOWN, 0))).astype(np.uint32)
+    cmd["kind"] = (kind | np.where(kind != 0, time_ms << np.uint32(8), np.uint32(0))).view(np.int32)
+    return cmd

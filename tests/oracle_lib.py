@@ -63,7 +63,7 @@ def ref(name="libref_vdt.so"):
             _build("ref")
         lib = C.CDLL(path)
         vp = C.c_void_p
-        if name.startswith("libref_vdt"):
+        if name.startswith("libref_vdt") and not name.startswith("libref_vdt_task"):
             lib.ref_vdt_create.restype = vp
             lib.ref_vdt_destroy.argtypes = [vp]
             lib.ref_vdt_start.argtypes = [vp]
@@ -84,6 +84,9 @@ def ref(name="libref_vdt.so"):
                 getattr(lib, nm).restype = C.c_float
             lib.ref_atan2f.argtypes = [C.c_float, C.c_float]
             lib.ref_atan2f.restype = C.c_float
+        if name.startswith("libref_vdt_task"):
+            lib.ref_vdt_task_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_cabi.VdtRollout), vp]
+            lib.ref_vdt_task_rollout.restype = None
         if name.startswith("libref_imu"):
             lib.ref_imt_create.restype = vp
             lib.ref_imt_destroy.argtypes = [vp]
@@ -126,7 +129,7 @@ class HostRollout:
     """Builds an rk_vdt_rollout_t over HOST numpy arrays and keeps them alive."""
 
     def __init__(self, n, steps, sensor_mode, cmd=None, seg_len=0, yaw=None, yaw_period=0, frames=None,
-                 trace=False, goal=None):
+                 trace=False, goal=None, task_period=0):
         self.n = n
         self.keep = [cmd, yaw, frames, goal]
         self.trace = np.zeros((steps, _cabi.RK_VDT_TRACE_WORDS, n), dtype=np.uint32) if trace else None
@@ -138,6 +141,7 @@ class HostRollout:
         a.d_frames = _ptr(frames)
         a.d_trace = _ptr(self.trace)
         a.d_goal, a.d_cost = _ptr(goal), _ptr(self.cost)
+        a.task_period = task_period
         self.args = a
 
 
@@ -148,6 +152,11 @@ def run_port(state_soa, n, ro, params=None, nthreads=1):
 
 def run_ref(state_soa, n, ro, nthreads=1, name="libref_vdt.so"):
     ref(name).ref_vdt_rollout(_ptr(state_soa), n, 0, n, C.byref(ro.args), nthreads)
+
+
+def run_task_ref(state_soa, n, ro, yaw_deg):
+    """The reference's whole vehicle task (VD_task_main.cpp compiled unmodified) from the power-on state."""
+    ref("libref_vdt_task.so").ref_vdt_task_rollout(_ptr(state_soa), n, 0, n, C.byref(ro.args), _ptr(yaw_deg))
 
 
 def imu_port(state_soa, n, regs, have=None, want_out=False, do_init=False):

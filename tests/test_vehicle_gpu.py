@@ -42,7 +42,7 @@ def gpu_run(inp, sensor=_cabi.RK_SENSOR_PLANT, frames=None, state=None, trace=Tr
     tr = torch.zeros((steps, 16, n), dtype=torch.int32, device=DEV) if trace else None
     if chunks is None:
         vb.rollout(steps, sensor_mode=sensor, cmd=cmd, seg_len=inp.get("seg_len", 0), yaw=yaw,
-                   yaw_period=inp.get("yaw_period", 0), frames=fr, trace=tr)
+                   yaw_period=inp.get("yaw_period", 0), frames=fr, trace=tr, task_period=inp.get("task_period", 0))
     else:
         # resume: K ticks as several launches, each taking its slice of the input tables
         seg_len, yp = inp.get("seg_len", 0), inp.get("yaw_period", 0)
@@ -55,7 +55,7 @@ def gpu_run(inp, sensor=_cabi.RK_SENSOR_PLANT, frames=None, state=None, trace=Tr
                        seg_len=seg_len,
                        yaw=None if yaw is None else yaw[c * k // yp:(c + 1) * k // yp].contiguous(), yaw_period=yp,
                        frames=None if fr is None else fr[c * k:(c + 1) * k].contiguous(),
-                       trace=None if tr is None else tr[c * k:(c + 1) * k])
+                       trace=None if tr is None else tr[c * k:(c + 1) * k], task_period=inp.get("task_period", 0))
     torch.cuda.synchronize()
     st = vb.state.cpu().numpy().view(np.uint32)
     return st, (tr.cpu().numpy().view(np.uint32) if trace else None)
