@@ -434,7 +434,8 @@ def run_ours(a):
     # ---- e2e: host tables in, costs out, through the same C-ABI call ------------------------
     e2e = None
     if not a.no_e2e:
-        copy_s = torch.cuda.Stream(dev)
+        copy_s = torch.cuda.Stream(dev)  # H2D
+        back_s = torch.cuda.Stream(dev)  # D2H: its wait for the rollout must not hold up the next step's H2D
         comp_s = torch.cuda.Stream(dev)
         bufs = []
         for b in range(2):
@@ -461,10 +462,10 @@ def run_ours(a):
                 vb.state.zero_()  # every rollout starts from the power-on state
                 vb.rollout_args(b["args"], stream=comp_s)
                 b["done"].record(comp_s)
-            with torch.cuda.stream(copy_s):
-                copy_s.wait_event(b["done"])
+            with torch.cuda.stream(back_s):
+                back_s.wait_event(b["done"])
                 b["cost_h"].copy_(b["cost"], non_blocking=True)
-                b["down"].record(copy_s)
+                b["down"].record(back_s)
 
         for s in range(max(W, 2)):
             e2e_pass(s)
@@ -474,10 +475,12 @@ def run_ours(a):
         clocks.start()
         t0e.record(stream)
         copy_s.wait_stream(stream)
+        back_s.wait_stream(stream)
         comp_s.wait_stream(stream)
         for s in range(K):
             e2e_pass(s)
         stream.wait_stream(copy_s)
+        stream.wait_stream(back_s)
         stream.wait_stream(comp_s)
         t1e.record(stream)
         torch.cuda.synchronize()
@@ -487,7 +490,7 @@ def run_ours(a):
         e2e = {"value": world * n * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / K,
                "path": "rk_vdt_rollout() via ctypes; pinned host cmd+yaw tables H2D, state reset to power-on, "
-                       "cost vector D2H, double-buffered on a copy stream"}
+                       "cost vector D2H, double-buffered: H2D, rollout and D2H on three streams"}
         launches += 0  # e2e launches are outside the `value` region; gpu_launches counts that region
 
     # ---- optional NCCL gather of the summary costs (outside the timed regions) --------------
@@ -693,7 +696,7 @@ def run_ours_full(a):
     # ---- e2e: host tables in, costs out, through rk_tick_rollout ----------------------------------
     e2e = None
     if not a.no_e2e:
-        copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        copy_s, comp_s, back_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         bufs = []
         for b in range(2):
             d = dict(cmd=torch.empty_like(cmd_d), regs=torch.empty_like(regs_d), have=torch.empty_like(have_d),
@@ -727,10 +730,10 @@ def run_ours_full(a):
                                                      yaw=yaw_d, goal=goal_d, cost=b["cost"])
                     rb.rollout_args(argcache[key], stream=comp_s)
                     b["done"].record(comp_s)
-                with torch.cuda.stream(copy_s):
-                    copy_s.wait_event(b["done"])
+                with torch.cuda.stream(back_s):
+                    back_s.wait_event(b["done"])
                     b["cost_h"].copy_(b["cost"], non_blocking=True)
-                    b["down"].record(copy_s)
+                    b["down"].record(back_s)
 
         for s in range(2):
             e2e_pass(s)
@@ -740,10 +743,12 @@ def run_ours_full(a):
         clocks.start()
         t0e.record(stream)
         copy_s.wait_stream(stream)
+        back_s.wait_stream(stream)
         comp_s.wait_stream(stream)
         for s in range(K):
             e2e_pass(s)
         stream.wait_stream(copy_s)
+        stream.wait_stream(back_s)
         stream.wait_stream(comp_s)
         t1e.record(stream)
         torch.cuda.synchronize()
@@ -753,7 +758,7 @@ def run_ours_full(a):
         e2e = {"value": a.total * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / K,
                "path": "rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout via ctypes per chunk; pinned host command, IMU-register "
-                       "and arm-sequence tables H2D, vehicle reset to power-on, cost vector D2H, double-buffered on a copy stream"}
+                       "and arm-sequence tables H2D, vehicle reset to power-on, cost vector D2H, double-buffered: H2D, compute and D2H on three streams"}
 
     clk = clocks.result()
     cpu = None
