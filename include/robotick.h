@@ -273,6 +273,26 @@ int rk_imt_update(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, co
 int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat,
                       float *d_out, float *d_yaw_rad, int do_init, void *stream);
 
+/* ---- WIT serial wire codec: the byte stream of the WT901C through the vendor parser's state
+ * machine -- WitSerialDataIn (lib/wt901c/wit_c_sdk.c:132-164: 11-byte window, 0x55 header resync, byte-sum
+ * check), CopeWitData (:77-130: which registers a frame type writes), the update flags of SensorDataUpdata
+ * (imu_if_wt901c.cpp:24-46) -- followed by IMU_IF_WT901C::update() (isComComp :132-143 drains every byte on the
+ * wire, then asks for a quaternion frame).  Parser block per IMU (3 planes): */
+enum {
+  RK_IP_WINDOW = 0, /* s_ucWitDataBuff[0..10] packed little-endian in words 0-2; byte 11 = s_uiWitDataCnt */
+  RK_IP_FLAGS  = 3, /* bit 0: QUAT_UPDATE pending; bits 8-15: s_uiReadRegIndex (0, or q0 = 0x51 after init()) */
+  RK_IP_SREG   = 4, /* sReg[AX..Yaw], sReg[q0..q3]: 16 x int16 in RK_IMT_REG_* order, two per word */
+  RK_IP_WORDS  = 12
+};
+size_t rk_imt_parser_words(void);
+size_t rk_imt_parser_bytes(int64_t n);
+/* K updates, each preceded by nwords*4 serial bytes per IMU: d_bytes word w of update u, IMU i at
+ * (u*nwords + w)*n + i, bytes in wire order from the low byte up.  do_init: the first update is
+ * IMU_IF_WT901C::init() (:63-77; WitInit empties the window, WitReadReg(q0, 4) arms the read index; its bytes must
+ * contain a quaternion frame -- the firmware spins until one arrives).  d_out / d_yaw_rad as rk_imt_update_yaw. */
+int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32_t nwords, const uint32_t *d_bytes,
+                      float *d_out, float *d_yaw_rad, int do_init, void *stream);
+
 /* single-instance handle (drop-in for `static IMU_IF_WT901C imu_if`, imu_task_main.cpp:25) */
 typedef struct rk_imt rk_imt_t;
 int   rk_imt_create(rk_imt_t **out);

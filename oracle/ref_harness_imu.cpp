@@ -163,4 +163,42 @@ void ref_imt_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, 
     free(m);
   }
 }
+
+/* Byte-stream path (rk_imt_feed_bytes): the serial bytes go to the UART stub unframed and the vendor parser
+ * (wit_c_sdk.c, compiled as it is) does the rest.  The parser's window and flags are file-static in the
+ * reference, so every instance is replayed from power-on: update 0 is init(), the following K-1 are update().
+ * bytes: word w of update u, instance i at (u*nwords + w)*n + i.  Outputs as ref_imt_rollout; final sReg
+ * (16 tracked registers) into sreg_out[16*i ..]. */
+void ref_imt_bytes_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, int nwords, const uint32_t *bytes,
+                           uint32_t *out, int16_t *sreg_out) {
+  for(int64_t i = i0; i < i1; i++) {
+    memset(sReg, 0, sizeof(int16_t) * REGSIZE);
+    IMU_IF_WT901C *m = make();
+    for(int u = 0; u < K; u++) {
+      for(int w = 0; w < nwords; w++) {
+        uint32_t word = bytes[((int64_t)u * nwords + w) * n + i];
+        Serial6.feed((const uint8_t *)&word, 4);
+      }
+      if(u == 0) m->init();
+      else m->update();
+      if(out) {
+        IMT::IMU_IF::Data d;
+        m->getDataLatest(d);
+        const uint32_t *dw = (const uint32_t *)&d;
+        for(int k = 0; k < 16; k++) out[(((int64_t)u * 4 + k / 4) * n + i) * 4 + (k % 4)] = dw[k];
+      }
+    }
+    if(state) {
+      uint32_t w[RK_IS_WORDS];
+      export_state(m, w);
+      for(int k = 0; k < RK_IS_WORDS; k++) soa(state, n, i, k) = w[k];
+    }
+    if(sreg_out) {
+      for(int k = 0; k < 12; k++) sreg_out[16 * i + k] = sReg[AX + k];
+      for(int k = 0; k < 4; k++) sreg_out[16 * i + 12 + k] = sReg[q0 + k];
+    }
+    m->~IMU_IF_WT901C();
+    free(m);
+  }
+}
 }

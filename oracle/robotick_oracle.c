@@ -1033,3 +1033,125 @@ void orc_adp_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *
     }
   }
 }
+
+
+/* ------------------------------------------------------------------------------------ */
+/* WIT serial codec: WitSerialDataIn / CopeWitData (lib/wt901c/wit_c_sdk.c:77-164) + the update flags   */
+/* of SensorDataUpdata (imu_if_wt901c.cpp:24-46) + IMU_IF_WT901C::update / init on the parsed registers */
+typedef struct {
+  uint8_t  buf[11], cnt;
+  uint32_t flags; /* bit 0 QUAT_UPDATE; bits 8-15 s_uiReadRegIndex */
+  int16_t  reg[16];
+} wit_t;
+static int wit_reg_slot(uint32_t r) { /* tracked registers -> RK_IMT_REG_* slot, else -1 */
+  if(r >= 0x34 && r <= 0x3f) return (int)(r - 0x34);
+  if(r >= 0x51 && r <= 0x54) return (int)(r - 0x51) + 12;
+  return -1;
+}
+static void wit_write_regs(wit_t *w, uint32_t reg, uint32_t len, const uint16_t *val) {
+  uint32_t k;
+  for(k = 0; k < len; k++) {
+    int slot = wit_reg_slot(reg + k);
+    if(slot >= 0) w->reg[slot] = (int16_t)val[k];
+    if(reg + k == 0x54) w->flags |= 1u; /* q3 -> QUAT_UPDATE */
+  }
+}
+static void wit_byte(wit_t *w, uint8_t b) {
+  uint16_t d[4];
+  uint8_t  sum = 0, type;
+  uint32_t reg1 = 0, reg2 = 0, len1 = 4, len2 = 0;
+  int      k;
+  w->buf[w->cnt++] = b;
+  if(w->buf[0] != 0x55) {
+    w->cnt--;
+    memmove(w->buf, w->buf + 1, w->cnt);
+    return;
+  }
+  if(w->cnt < 11) return;
+  for(k = 0; k < 10; k++) sum += w->buf[k];
+  if(sum != w->buf[10]) {
+    w->cnt--;
+    memmove(w->buf, w->buf + 1, w->cnt);
+    return;
+  }
+  for(k = 0; k < 4; k++) d[k] = (uint16_t)(((uint16_t)w->buf[3 + 2 * k] << 8) | w->buf[2 + 2 * k]);
+  type   = w->buf[1];
+  w->cnt = 0;
+  switch(type) { /* CopeWitData :85-113 */
+  case 0x51: reg1 = 0x34, len1 = 3, reg2 = 0x40, len2 = 1; break; /* WIT_ACC: AX.., TEMP */
+  case 0x53: reg1 = 0x3d, len1 = 3, reg2 = 0x2e, len2 = 1; break; /* WIT_ANGLE: Roll.., VERSION */
+  case 0x50: reg1 = 0x30; break;                                  /* WIT_TIME */
+  case 0x52: reg1 = 0x37, len1 = 3; break;                        /* WIT_GYRO */
+  case 0x54: reg1 = 0x3a, len1 = 3; break;                        /* WIT_MAGNETIC */
+  case 0x55: reg1 = 0x41; break;                                  /* WIT_DPORT */
+  case 0x56: reg1 = 0x45; break;                                  /* WIT_PRESS */
+  case 0x57: reg1 = 0x49; break;                                  /* WIT_GPS */
+  case 0x58: reg1 = 0x4d; break;                                  /* WIT_VELOCITY */
+  case 0x59: reg1 = 0x51; break;                                  /* WIT_QUATER */
+  case 0x5A: reg1 = 0x55; break;                                  /* WIT_GSA */
+  case 0x5F: reg1 = (w->flags >> 8) & 0xFFu; break;               /* WIT_REGVALUE: s_uiReadRegIndex */
+  default: return;
+  }
+  wit_write_regs(w, reg1, len1, d);
+  if(len2) wit_write_regs(w, reg2, len2, d + 3);
+}
+
+void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0, int64_t i1, int K, int nwords,
+                        const uint32_t *bytes, uint32_t *out, float *yaw_rad, int do_init) {
+  int64_t i;
+  int     u, k, b;
+  for(i = i0; i < i1; i++) {
+    float    qi[4], d[16];
+    uint32_t flags = *soa(state, n, i, RK_IS_FLAGS);
+    wit_t    w;
+    for(k = 0; k < 4; k++) qi[k] = u2f(*soa(state, n, i, RK_IS_QINIT + k));
+    for(k = 0; k < 16; k++) d[k] = u2f(*soa(state, n, i, RK_IS_DATA + k));
+    for(k = 0; k < 12; k++) {
+      uint32_t word = *soa(parser, n, i, RK_IP_WINDOW + k / 4);
+      uint8_t  by   = (uint8_t)(word >> (8 * (k % 4)));
+      if(k < 11) w.buf[k] = by;
+      else w.cnt = by > 11 ? 11 : by;
+    }
+    w.flags = *soa(parser, n, i, RK_IP_FLAGS);
+    for(k = 0; k < 16; k++) w.reg[k] = (int16_t)(*soa(parser, n, i, RK_IP_SREG + k / 2) >> (16 * (k % 2)));
+    for(u = 0; u < K; u++) {
+      int init = do_init && u == 0;
+      if(init) { /* WitInit: s_uiWitDataCnt = 0 ; WitReadReg(q0, 4): s_uiReadRegIndex = q0 */
+        w.cnt   = 0;
+        w.flags = (w.flags & ~0xFF00u) | (0x51u << 8);
+      }
+      for(b = 0; b < nwords * 4; b++) {
+        uint32_t word = bytes[((int64_t)u * nwords + b / 4) * n + i];
+        wit_byte(&w, (uint8_t)(word >> (8 * (b % 4))));
+      }
+      {
+        int hq = (w.flags & 1u) != 0;
+        if(hq) w.flags &= ~0xFFu; /* s_cDataUpdate = 0 */
+        if(init) {              /* getDataImmediately: (spins until a quaternion frame) updateData; latch q_init */
+          imu_update_data(qi, w.reg, d);
+          for(k = 0; k < 4; k++) qi[k] = w.reg[RK_IMT_REG_Q0 + k] / 32768.0f;
+        } else if(hq) {
+          flags &= ~RK_IS_FLAG_ERROR;
+          imu_update_data(qi, w.reg, d);
+        } else {
+          flags |= RK_IS_FLAG_ERROR;
+        }
+      }
+      if(out)
+        for(k = 0; k < 16; k++) out[(((int64_t)u * 4 + k / 4) * n + i) * 4 + (k % 4)] = f2u(d[k]);
+      if(yaw_rad) yaw_rad[(int64_t)u * n + i] = d[RK_IS_D_ANGLE + 2] * (ORC_PI / 180.0f);
+    }
+    for(k = 0; k < 4; k++) *soa(state, n, i, RK_IS_QINIT + k) = f2u(qi[k]);
+    for(k = 0; k < 16; k++) *soa(state, n, i, RK_IS_DATA + k) = f2u(d[k]);
+    *soa(state, n, i, RK_IS_FLAGS) = flags;
+    {
+      uint32_t pw[RK_IP_WORDS];
+      memset(pw, 0, sizeof(pw));
+      for(k = 0; k < (int)w.cnt; k++) pw[k / 4] |= (uint32_t)w.buf[k] << (8 * (k % 4)); /* bytes past the count are kept zero */
+      pw[2] |= (uint32_t)w.cnt << 24;
+      pw[RK_IP_FLAGS] = w.flags;
+      for(k = 0; k < 16; k++) pw[RK_IP_SREG + k / 2] |= ((uint32_t)(uint16_t)w.reg[k]) << (16 * (k % 2));
+      for(k = 0; k < RK_IP_WORDS; k++) *soa(parser, n, i, k) = pw[k];
+    }
+  }
+}

@@ -90,6 +90,138 @@ imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__
   st_plane(state, n, 5, i, make_uint4(flags, 0u, 0u, 0u));
 }
 
+// ---------------------------------------------------------------------------------------------
+// WIT serial codec (lib/wt901c/wit_c_sdk.c:77-164): the vendor parser's byte-wise state machine, one
+// thread per IMU.  The 11-byte window lives in three registers (bytes past the fill count are kept
+// zero, so inserting is an OR and dropping the first byte a funnel shift); the checksum is two SIMD
+// byte sums.  Bytes arrive as 32-bit words, 128 B per warp per load.
+// ---------------------------------------------------------------------------------------------
+struct Wit {
+  uint32_t w0, w1, w2, cnt, flags;
+  int      reg[16];
+};
+RK_DEV void wit_drop_first(Wit &p) {
+  p.w0 = __funnelshift_r(p.w0, p.w1, 8);
+  p.w1 = __funnelshift_r(p.w1, p.w2, 8);
+  p.w2 >>= 8;
+  p.cnt--;
+}
+RK_DEV void wit_store_reg(Wit &p, uint32_t reg, uint32_t val) { // CopeWitData's memcpy into sReg, tracked registers only
+  const int v = sext16((int)val);
+#pragma unroll
+  for(int k = 0; k < 12; k++)
+    if(reg == 0x34u + k) p.reg[k] = v;
+#pragma unroll
+  for(int k = 0; k < 4; k++)
+    if(reg == 0x51u + k) p.reg[12 + k] = v;
+  if(reg == 0x54u) p.flags |= 1u; // q3 -> QUAT_UPDATE (SensorDataUpdata)
+}
+RK_DEV void wit_byte(Wit &p, uint32_t b) { // WitSerialDataIn, WIT_PROTOCOL_NORMAL  :132-164
+  const uint32_t sh = 8u * (p.cnt & 3u), ins = b << sh;
+  if(p.cnt < 4u) p.w0 |= ins;
+  else if(p.cnt < 8u) p.w1 |= ins;
+  else p.w2 |= ins;
+  p.cnt++;
+  if((p.w0 & 0xFFu) != 0x55u) {
+    wit_drop_first(p);
+    return;
+  }
+  if(p.cnt < 11u) return;
+  const uint32_t sum = (__vsadu4(p.w0, 0u) + __vsadu4(p.w1, 0u) + __vsadu4(p.w2 & 0xFFFFu, 0u)) & 0xFFu;
+  if(sum != ((p.w2 >> 16) & 0xFFu)) {
+    wit_drop_first(p);
+    return;
+  }
+  const uint32_t type = (p.w0 >> 8) & 0xFFu;
+  const uint32_t d0 = p.w0 >> 16, d1 = p.w1 & 0xFFFFu, d2 = p.w1 >> 16, d3 = p.w2 & 0xFFFFu;
+  p.w0 = 0u, p.w1 = 0u, p.w2 = 0u, p.cnt = 0u;
+  switch(type) { // CopeWitData :85-113
+  case 0x51u: p.reg[0] = sext16((int)d0), p.reg[1] = sext16((int)d1), p.reg[2] = sext16((int)d2); break;    // WIT_ACC (+ TEMP)
+  case 0x52u: p.reg[3] = sext16((int)d0), p.reg[4] = sext16((int)d1), p.reg[5] = sext16((int)d2); break;    // WIT_GYRO
+  case 0x54u: p.reg[6] = sext16((int)d0), p.reg[7] = sext16((int)d1), p.reg[8] = sext16((int)d2); break;    // WIT_MAGNETIC
+  case 0x53u: p.reg[9] = sext16((int)d0), p.reg[10] = sext16((int)d1), p.reg[11] = sext16((int)d2); break;  // WIT_ANGLE (+ VERSION)
+  case 0x59u:                                                                                                // WIT_QUATER
+    p.reg[12] = sext16((int)d0), p.reg[13] = sext16((int)d1), p.reg[14] = sext16((int)d2), p.reg[15] = sext16((int)d3);
+    p.flags |= 1u;
+    break;
+  case 0x5Fu: { // WIT_REGVALUE: four registers from s_uiReadRegIndex
+    const uint32_t r = (p.flags >> 8) & 0xFFu;
+    wit_store_reg(p, r, d0), wit_store_reg(p, r + 1, d1), wit_store_reg(p, r + 2, d2), wit_store_reg(p, r + 3, d3);
+  } break;
+  default: break; // TIME / DPORT / PRESS / GPS / VELOCITY / GSA write registers the IMU interface never reads; others are ignored
+  }
+}
+
+__global__ void __launch_bounds__(128)
+imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int64_t n, int K, int nwords,
+                      const uint32_t *__restrict__ bytes, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  float   qi[4];
+  ImuData cur;
+  {
+    const uint4 q = ld_plane(state, n, 0, i);
+    qi[0] = u2f(q.x), qi[1] = u2f(q.y), qi[2] = u2f(q.z), qi[3] = u2f(q.w);
+#pragma unroll
+    for(int pl = 0; pl < 4; pl++) {
+      const uint4 v = ld_plane(state, n, 1 + pl, i);
+      cur.d[4 * pl] = u2f(v.x), cur.d[4 * pl + 1] = u2f(v.y), cur.d[4 * pl + 2] = u2f(v.z), cur.d[4 * pl + 3] = u2f(v.w);
+    }
+  }
+  uint32_t flags = ld_plane(state, n, 5, i).x;
+  Wit      p;
+  {
+    const uint4 a = ld_plane(parser, n, 0, i), b = ld_plane(parser, n, 1, i), c = ld_plane(parser, n, 2, i);
+    p.cnt = min(a.z >> 24, 11u);
+    p.w0 = a.x, p.w1 = a.y, p.w2 = a.z & 0x00FFFFFFu, p.flags = a.w;
+    const uint32_t r[8] = {b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for(int k = 0; k < 8; k++) p.reg[2 * k] = lo16(r[k]), p.reg[2 * k + 1] = hi16(r[k]);
+  }
+  for(int u = 0; u < K; u++) {
+    const bool init = do_init && u == 0;
+    if(init) { // WitInit: s_uiWitDataCnt = 0 ; WitReadReg(q0, 4): s_uiReadRegIndex = q0
+      p.w0 = 0u, p.w1 = 0u, p.w2 = 0u, p.cnt = 0u;
+      p.flags = (p.flags & ~0xFF00u) | (0x51u << 8);
+    }
+    for(int w = 0; w < nwords; w++) {
+      const uint32_t word = __ldcs(bytes + ((int64_t)u * nwords + w) * n + i);
+#pragma unroll
+      for(int b = 0; b < 4; b++) wit_byte(p, (word >> (8 * b)) & 0xFFu);
+    }
+    const bool hq = (p.flags & 1u) != 0u; // isComComp :132-143
+    if(hq) p.flags &= ~0xFFu;
+    if(init) {
+      imu_update_data(qi, p.reg, cur);
+      const float S = 1.0f / 32768.0f;
+#pragma unroll
+      for(int k = 0; k < 4; k++) qi[k] = fmul((float)p.reg[RK_IMT_REG_Q0 + k], S);
+    } else if(hq) {
+      flags &= ~RK_IS_FLAG_ERROR;
+      imu_update_data(qi, p.reg, cur);
+    } else {
+      flags |= RK_IS_FLAG_ERROR;
+    }
+    if(yaw_rad) __stcs(yaw_rad + (int64_t)u * n + i, fmul(cur.d[RK_IS_D_ANGLE + 2], RK_DEG2RAD));
+    if(out) {
+#pragma unroll
+      for(int pl = 0; pl < 4; pl++)
+        __stcs(out + ((int64_t)u * 4 + pl) * n + i, make_float4(cur.d[4 * pl], cur.d[4 * pl + 1], cur.d[4 * pl + 2], cur.d[4 * pl + 3]));
+    }
+  }
+  st_plane(state, n, 0, i, make_uint4(f2u(qi[0]), f2u(qi[1]), f2u(qi[2]), f2u(qi[3])));
+#pragma unroll
+  for(int pl = 0; pl < 4; pl++)
+    st_plane(state, n, 1 + pl, i, make_uint4(f2u(cur.d[4 * pl]), f2u(cur.d[4 * pl + 1]), f2u(cur.d[4 * pl + 2]), f2u(cur.d[4 * pl + 3])));
+  st_plane(state, n, 5, i, make_uint4(flags, 0u, 0u, 0u));
+  uint32_t r[8];
+#pragma unroll
+  for(int k = 0; k < 8; k++) r[k] = pack16(p.reg[2 * k], p.reg[2 * k + 1]);
+  st_plane(parser, n, 0, i, make_uint4(p.w0, p.w1, p.w2 | (p.cnt << 24), p.flags));
+  st_plane(parser, n, 1, i, make_uint4(r[0], r[1], r[2], r[3]));
+  st_plane(parser, n, 2, i, make_uint4(r[4], r[5], r[6], r[7]));
+}
+
 } // namespace rk
 
 using namespace rk;
@@ -118,6 +250,27 @@ int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs
   if(int rc = require_device()) return rc;
   imt_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint4 *)d_state, n, K, d_regs, d_have_quat,
                                                                                   (float4 *)d_out, d_yaw_rad, do_init);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+size_t rk_imt_parser_words(void) { return RK_IP_WORDS; }
+size_t rk_imt_parser_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_IP_WORDS * 4u; }
+
+int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32_t nwords, const uint32_t *d_bytes, float *d_out,
+                      float *d_yaw_rad, int do_init, void *stream) {
+  if(n == 0 || K == 0) return RK_OK;
+  if(n < 0 || K < 0 || nwords < 0 || (nwords > 0 && !d_bytes)) {
+    set_error("rk_imt_feed_bytes: bad n / K / nwords / bytes");
+    return RK_ERR_ARG;
+  }
+  if(!d_state || !d_parser || ((uintptr_t)d_state & 15u) || ((uintptr_t)d_parser & 15u) || ((uintptr_t)d_out & 15u)) {
+    set_error("rk_imt_feed_bytes: d_state / d_parser / d_out must be 16-byte aligned (state and parser non-NULL)");
+    return RK_ERR_ARG;
+  }
+  if(int rc = require_device()) return rc;
+  imt_feed_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_state, (uint4 *)d_parser, n, K, nwords,
+                                                                                       d_bytes, (float4 *)d_out, d_yaw_rad, do_init);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }

@@ -18,6 +18,7 @@ class ImuBatch:
         assert self.lib.rk_imt_state_words() == layout.IS_WORDS
         with torch.cuda.device(self.dev_index):
             self.state = torch.zeros(layout.IS_WORDS * self.n, dtype=torch.int32, device=self.device)
+        self.parser = None  # WIT serial parser block (RK_IP_*), allocated by the first feed_bytes()
 
     def update(self, regs, have_quat=None, out=None, do_init=False, stream=None):
         """regs: int16 [K, 16, n]; have_quat: uint8 [K, n] or None; out: float32 [K, 4, n, 4] or
@@ -34,6 +35,28 @@ class ImuBatch:
                                            None if have_quat is None else have_quat.data_ptr(),
                                            None if out is None else out.data_ptr(), int(bool(do_init)),
                                            C.c_void_p(st.cuda_stream)))
+
+    def feed_bytes(self, wire, out=None, yaw_rad=None, do_init=False, stream=None):
+        """wire: uint32/int32 [K, nwords, n] serial bytes (first byte in the low byte of each word) through the
+        vendor parser's state machine (lib/wt901c/wit_c_sdk.c:132-164), then IMU_IF_WT901C::update per update
+        (::init for the first when do_init).  out: float32 [K, 4, n, 4] or None; yaw_rad: float32 [K, n] or None."""
+        assert wire.is_cuda and wire.dtype in (torch.int32, torch.uint32) and wire.is_contiguous() and wire.dim() == 3
+        assert wire.shape[2] == self.n
+        K, nwords = int(wire.shape[0]), int(wire.shape[1])
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (K, 4, self.n, 4)
+        if yaw_rad is not None:
+            assert yaw_rad.is_cuda and yaw_rad.dtype == torch.float32 and tuple(yaw_rad.shape) == (K, self.n)
+        if self.parser is None:
+            assert self.lib.rk_imt_parser_words() == layout.IP_WORDS
+            with torch.cuda.device(self.dev_index):
+                self.parser = torch.zeros(layout.IP_WORDS * self.n, dtype=torch.int32, device=self.device)
+        st = stream if stream is not None else torch.cuda.current_stream(self.dev_index)
+        _cabi.check(self.lib.rk_set_device(self.dev_index))
+        _cabi.check(self.lib.rk_imt_feed_bytes(self.state.data_ptr(), self.parser.data_ptr(), self.n, K, nwords, wire.data_ptr(),
+                                               None if out is None else out.data_ptr(),
+                                               None if yaw_rad is None else yaw_rad.data_ptr(), int(bool(do_init)),
+                                               C.c_void_p(st.cuda_stream)))
 
     def state_aos(self):
         return layout.soa_to_aos(self.state.cpu().numpy().view(np.uint32), self.n, layout.IS_WORDS)

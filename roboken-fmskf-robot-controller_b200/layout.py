@@ -34,6 +34,8 @@ IS_FLAG_ERROR = 1
 IMT_REGS = 16
 (REG_AX, REG_AY, REG_AZ, REG_GX, REG_GY, REG_GZ, REG_HX, REG_HY, REG_HZ, REG_ROLL, REG_PITCH, REG_YAW,
  REG_Q0, REG_Q1, REG_Q2, REG_Q3) = range(16)
+# WIT serial parser block (RK_IP_*): 11-byte window + fill count, flags, the 16 tracked sReg words
+IP_WINDOW, IP_FLAGS, IP_SREG, IP_WORDS = 0, 3, 4, 12
 
 # ---- arm (RK_AS_* / RK_ACMD_*) ------------------------------------------------------------
 AJ_Y0, AJ_P1, AJ_DFL, AJ_DFR, AJ_P2, AJ_R0, AJ_P3, AJ_NUM = range(8)

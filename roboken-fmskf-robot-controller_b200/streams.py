@@ -185,3 +185,91 @@ def vehicle_messages(n, n_seg, seed=0x5EED, first=0):
                                                                np.where(is_unk, _cabi.RK_CMD_MSG_UNKNOWN, 0))).astype(np.uint32)
     cmd["kind"] = (kind | np.where(kind != 0, time_ms << np.uint32(8), np.uint32(0))).view(np.int32)
     return cmd
+
+
+# ---- WIT serial wire (lib/wt901c/wit_c_sdk.c:132-164: 0x55, type, 4 x LE int16, byte-sum) ----------
+WIT_ACC, WIT_GYRO, WIT_ANGLE, WIT_MAGNETIC, WIT_QUATER, WIT_REGVALUE = 0x51, 0x52, 0x53, 0x54, 0x59, 0x5F
+
+
+def wit_frame(ftype, d):
+    """One 11-byte WIT frame: header 0x55, type, four little-endian int16, checksum = byte sum of the first ten."""
+    b = [0x55, int(ftype) & 0xFF]
+    for v in d:
+        v = int(v) & 0xFFFF
+        b += [v & 0xFF, v >> 8]
+    return bytes(b + [sum(b) & 0xFF])
+
+
+def imu_wire_clean(regs, nwords=14, pad=0x00):
+    """The byte stream a healthy WT901C would send for the register snapshots `regs` (int16 [K, 16, n], as
+    imu_samples): per update the five frames ACC, GYRO, ANGLE, MAGNETIC, QUATER (4th words: TEMP / VERSION = 0)
+    and padding up to nwords*4 bytes.  Returns uint32 [K, nwords, n] in rk_imt_feed_bytes layout."""
+    K, _, n = regs.shape
+    assert nwords * 4 >= 55
+    b = np.full((K, nwords * 4, n), pad, dtype=np.uint8)
+    r = regs.astype(np.int16).view(np.uint16)
+    plan = ((WIT_ACC, (0, 1, 2, None)), (WIT_GYRO, (3, 4, 5, None)), (WIT_ANGLE, (9, 10, 11, None)),
+            (WIT_MAGNETIC, (6, 7, 8, None)), (WIT_QUATER, (12, 13, 14, 15)))
+    for f, (t, slots) in enumerate(plan):
+        o = 11 * f
+        b[:, o, :], b[:, o + 1, :] = 0x55, t
+        for k, s in enumerate(slots):
+            if s is not None:
+                b[:, o + 2 + 2 * k, :] = r[:, s, :] & 0xFF
+                b[:, o + 3 + 2 * k, :] = r[:, s, :] >> 8
+            else:
+                b[:, o + 2 + 2 * k, :] = b[:, o + 3 + 2 * k, :] = 0
+        b[:, o + 10, :] = b[:, o : o + 10, :].astype(np.uint32).sum(axis=1).astype(np.uint8)
+    return _pack_wire(b)
+
+
+def _pack_wire(b):
+    """uint8 [K, nbytes, n] (wire order) -> uint32 [K, nwords, n], first byte in the low byte."""
+    K, nb, n = b.shape
+    q = b.reshape(K, nb // 4, 4, n).astype(np.uint32)
+    return np.ascontiguousarray(q[:, :, 0] | (q[:, :, 1] << 8) | (q[:, :, 2] << 16) | (q[:, :, 3] << 24))
+
+
+def imu_wire_fuzz(n, K, nwords=14, seed=0x5EED, first=0):
+    """Adversarial serial traffic: per IMU one continuous byte stream cut into K updates of nwords*4 bytes, so
+    frames straddle update boundaries.  Items: valid frames of every type CopeWitData knows (0x50..0x5A, 0x5F)
+    and of unknown types, frames with a broken checksum, truncated frames, 0x55 runs and random garbage; data
+    words are biased towards 0x55 bytes so that false headers occur inside payloads.  The stream always opens
+    with a valid quaternion frame (IMU_IF_WT901C::init() spins until one arrives).  uint32 [K, nwords, n]."""
+    total = K * nwords * 4
+    assert total >= 11
+    out = np.zeros((n, total), dtype=np.uint8)
+    for i in range(n):
+        rng = np.random.default_rng([int(seed) & 0xFFFFFFFF, int(first) + i, 0x317])
+        buf = bytearray()
+
+        def words():
+            w = rng.integers(-32768, 32768, size=4)
+            m = rng.integers(0, 8, size=4)
+            w = np.where(m == 0, 0x5555, np.where(m == 1, (w & 0xFF00) | 0x55, w))
+            return [int(x) for x in w]
+
+        buf += wit_frame(WIT_QUATER if rng.integers(0, 2) else WIT_REGVALUE, words())
+        while len(buf) < total:
+            kind = int(rng.integers(0, 16))
+            if kind < 8:
+                t = (WIT_ACC, WIT_GYRO, WIT_ANGLE, WIT_MAGNETIC, WIT_QUATER, WIT_QUATER, WIT_QUATER, WIT_REGVALUE)[kind]
+                buf += wit_frame(t, words())
+            elif kind == 8:
+                buf += wit_frame(int(rng.integers(0x50, 0x5B)), words())
+            elif kind == 9:
+                buf += wit_frame(int(rng.integers(0, 256)), words())
+            elif kind == 10:  # broken checksum
+                f = bytearray(wit_frame(WIT_QUATER, words()))
+                f[int(rng.integers(2, 11))] ^= 1 << int(rng.integers(0, 8))
+                buf += f
+            elif kind == 11:  # truncated frame
+                buf += wit_frame(WIT_QUATER, words())[: int(rng.integers(1, 11))]
+            elif kind == 12:
+                buf += bytes([0x55] * int(rng.integers(1, 14)))
+            elif kind == 13:
+                buf += bytes(int(x) for x in rng.integers(0, 256, size=int(rng.integers(1, 24))))
+            else:  # a quiet line: an update without any byte is not expressible (fixed nwords), idle = zeros
+                buf += bytes(int(rng.integers(1, nwords * 4 + 12)))
+        out[i] = np.frombuffer(bytes(buf[:total]), dtype=np.uint8)
+    return _pack_wire(np.ascontiguousarray(out.reshape(n, K, nwords * 4).transpose(1, 2, 0)))

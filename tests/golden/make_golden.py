@@ -63,13 +63,15 @@ def arm_golden():
 
 
 def main():
-    which = set(sys.argv[1:]) or {"vdt", "imu", "arm"}
+    which = set(sys.argv[1:]) or {"vdt", "imu", "arm", "wire"}
     if "arm" in which:
         arm_golden()
     if "vdt" in which:
         vdt_golden()
     if "imu" in which:
         imu_golden()
+    if "wire" in which:
+        imu_wire_golden()
 
 
 def vdt_golden():
@@ -106,6 +108,17 @@ def imu_golden():
     o = ol.imu_ref(st, n, regs, have, want_out=True, do_init=True)
     path = os.path.join(HERE, "imu_golden.npz")
     np.savez_compressed(path, out=o, state=st)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def imu_wire_golden():
+    # WIT serial codec: adversarial byte streams through the unmodified vendor parser + IMU_IF_WT901C
+    n, K, nwords = 48, 20, 6
+    wire = streams.imu_wire_fuzz(n, K, nwords=nwords, seed=0x5EED)
+    st = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
+    o, sreg = ol.imu_bytes_ref(st, n, wire, want_out=True)
+    path = os.path.join(HERE, "imu_wire_golden.npz")
+    np.savez_compressed(path, wire=wire, out=o, state=st, sreg=sreg)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

@@ -2,7 +2,7 @@
 """Kernel-level measurements of the two slow-rate modules (BASELINE configs[2] and [3]) -- one JSON
 line each, CUDA-event timed with inputs resident in HBM, roofline against MEASURED_PEAKS.json.
 
-    python tools/bench_modules.py [--n 1048576] [--imu-updates 64] [--arm-ticks 1000] [--reps 10] [--only imu|arm]
+    python tools/bench_modules.py [--n 1048576] [--imu-updates 64] [--arm-ticks 1000] [--reps 10] [--only imu|wire|arm]
 """
 import argparse
 import json
@@ -61,6 +61,28 @@ def bench_imu(a, dev):
                                        "algorithmic_bytes_per_update": per, "algorithmic_bytes_per_launch": nbytes}}), flush=True)
 
 
+def bench_wire(a, dev):
+    """rk_imt_feed_bytes: 56 serial bytes (five WIT frames + 1 idle byte) per update through the parser state machine."""
+    n, K, nwords = a.n, a.imu_updates, 14
+    uniq = min(n, 1 << 14)
+    regs, _ = streams.imu_samples(uniq, K, seed=3)
+    wire = streams.imu_wire_clean(regs, nwords=nwords)
+    wire_d = torch.from_numpy(np.tile(wire, (1, 1, n // uniq)).view(np.int32)).to(dev)
+    ib = ImuBatch(n, dev)
+    ib.feed_bytes(wire_d[:1].contiguous(), None, None, do_init=True)
+    out = torch.empty((K, 4, n, 4), dtype=torch.float32, device=dev)
+    peak, src = hbm_peak()
+    for mode in ("full_output", "state_only"):
+        ms = timed(lambda: ib.feed_bytes(wire_d, out if mode == "full_output" else None, None), a.reps)
+        per = nwords * 4 + (64 if mode == "full_output" else 0)
+        nbytes = n * (K * per + 2 * (96 + 48))
+        print(json.dumps({"kernel": "rk::imt_feed_bytes_kernel", "workload": f"8f-3: {n} IMUs x {K} updates x {nwords * 4} wire bytes, {mode}",
+                          "updates_per_s": n * K / (ms * 1e-3), "wire_bytes_per_s": n * K * nwords * 4 / (ms * 1e-3), "ms_per_launch": ms,
+                          "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "peak_source": src,
+                                       "algorithmic_bytes_per_update": per, "algorithmic_bytes_per_launch": nbytes}}), flush=True)
+
+
 def bench_arm(a, dev):
     n, K = a.n, a.arm_ticks
     seq = torch.from_numpy(layout.aos_to_soa(streams.arm_sequences(n, seed=0xC4, seq_id=9, max_len=32)).view(np.int32)).to(dev)
@@ -91,6 +113,8 @@ def main():
     dev = torch.device("cuda", 0)
     if a.only in ("", "imu"):
         bench_imu(a, dev)
+    if a.only in ("", "wire"):
+        bench_wire(a, dev)
     if a.only in ("", "arm"):
         bench_arm(a, dev)
 
