@@ -286,12 +286,15 @@ enum {
 };
 size_t rk_imt_parser_words(void);
 size_t rk_imt_parser_bytes(int64_t n);
-/* K updates, each preceded by nwords*4 serial bytes per IMU: d_bytes word w of update u, IMU i at
- * (u*nwords + w)*n + i, bytes in wire order from the low byte up.  do_init: the first update is
- * IMU_IF_WT901C::init() (:63-77; WitInit empties the window, WitReadReg(q0, 4) arms the read index; its bytes must
- * contain a quaternion frame -- the firmware spins until one arrives).  d_out / d_yaw_rad as rk_imt_update_yaw. */
-int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32_t nwords, const uint32_t *d_bytes,
-                      float *d_out, float *d_yaw_rad, int do_init, void *stream);
+/* K updates, each preceded by the serial bytes that arrived since the last one.  The wire is laid out like every
+ * other block, in 128-bit cells: cell c (bytes 16c .. 16c+15 of the update, wire order from the low byte of the
+ * first word up) of update u, IMU i at cell index (u*ncells + c)*n + i.  d_nbytes (NULL: every slot is full) gives
+ * the number of bytes really on the wire in update u of IMU i, at [u*n + i], clamped to 16*ncells -- an idle line
+ * is 0 bytes, not zeros.  do_init: the first update is IMU_IF_WT901C::init() (:63-77; WitInit empties the window,
+ * WitReadReg(q0, 4) arms the read index; its bytes must contain a quaternion frame -- the firmware spins until one
+ * arrives).  d_out / d_yaw_rad as rk_imt_update_yaw. */
+int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32_t ncells, const void *d_cells,
+                      const uint16_t *d_nbytes, float *d_out, float *d_yaw_rad, int do_init, void *stream);
 
 /* single-instance handle (drop-in for `static IMU_IF_WT901C imu_if`, imu_task_main.cpp:25) */
 typedef struct rk_imt rk_imt_t;

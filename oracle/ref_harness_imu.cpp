@@ -167,17 +167,19 @@ void ref_imt_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, 
 /* Byte-stream path (rk_imt_feed_bytes): the serial bytes go to the UART stub unframed and the vendor parser
  * (wit_c_sdk.c, compiled as it is) does the rest.  The parser's window and flags are file-static in the
  * reference, so every instance is replayed from power-on: update 0 is init(), the following K-1 are update().
- * bytes: word w of update u, instance i at (u*nwords + w)*n + i.  Outputs as ref_imt_rollout; final sReg
- * (16 tracked registers) into sreg_out[16*i ..]. */
-void ref_imt_bytes_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, int nwords, const uint32_t *bytes,
-                           uint32_t *out, int16_t *sreg_out) {
+ * cells / nbytes: the rk_imt_feed_bytes wire layout (128-bit cells; nbytes NULL = full slots).  Outputs as
+ * ref_imt_rollout; final sReg (16 tracked registers) into sreg_out[16*i ..]. */
+void ref_imt_bytes_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, int ncells, const uint32_t *cells,
+                           const uint16_t *nbytes, uint32_t *out, int16_t *sreg_out) {
   for(int64_t i = i0; i < i1; i++) {
     memset(sReg, 0, sizeof(int16_t) * REGSIZE);
     IMU_IF_WT901C *m = make();
     for(int u = 0; u < K; u++) {
-      for(int w = 0; w < nwords; w++) {
-        uint32_t word = bytes[((int64_t)u * nwords + w) * n + i];
-        Serial6.feed((const uint8_t *)&word, 4);
+      int nb = 16 * ncells;
+      if(nbytes && nbytes[(int64_t)u * n + i] < nb) nb = nbytes[(int64_t)u * n + i];
+      for(int c = 0; 16 * c < nb; c++) {
+        const uint32_t *cell = cells + (((int64_t)u * ncells + c) * n + i) * 4;
+        Serial6.feed((const uint8_t *)cell, nb - 16 * c < 16 ? nb - 16 * c : 16);
       }
       if(u == 0) m->init();
       else m->update();

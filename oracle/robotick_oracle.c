@@ -1096,8 +1096,8 @@ static void wit_byte(wit_t *w, uint8_t b) {
   if(len2) wit_write_regs(w, reg2, len2, d + 3);
 }
 
-void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0, int64_t i1, int K, int nwords,
-                        const uint32_t *bytes, uint32_t *out, float *yaw_rad, int do_init) {
+void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0, int64_t i1, int K, int ncells,
+                        const uint32_t *cells, const uint16_t *nbytes, uint32_t *out, float *yaw_rad, int do_init) {
   int64_t i;
   int     u, k, b;
   for(i = i0; i < i1; i++) {
@@ -1110,7 +1110,7 @@ void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0
       uint32_t word = *soa(parser, n, i, RK_IP_WINDOW + k / 4);
       uint8_t  by   = (uint8_t)(word >> (8 * (k % 4)));
       if(k < 11) w.buf[k] = by;
-      else w.cnt = by > 11 ? 11 : by;
+      else w.cnt = by > 10 ? 10 : by;
     }
     w.flags = *soa(parser, n, i, RK_IP_FLAGS);
     for(k = 0; k < 16; k++) w.reg[k] = (int16_t)(*soa(parser, n, i, RK_IP_SREG + k / 2) >> (16 * (k % 2)));
@@ -1120,9 +1120,13 @@ void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0
         w.cnt   = 0;
         w.flags = (w.flags & ~0xFF00u) | (0x51u << 8);
       }
-      for(b = 0; b < nwords * 4; b++) {
-        uint32_t word = bytes[((int64_t)u * nwords + b / 4) * n + i];
-        wit_byte(&w, (uint8_t)(word >> (8 * (b % 4))));
+      {
+        int nb = 16 * ncells;
+        if(nbytes && nbytes[(int64_t)u * n + i] < nb) nb = nbytes[(int64_t)u * n + i];
+        for(b = 0; b < nb; b++) { /* byte b of the update: cell b/16, word (b%16)/4, from the low byte up */
+          uint32_t word = cells[(((int64_t)u * ncells + b / 16) * n + i) * 4 + (b % 16) / 4];
+          wit_byte(&w, (uint8_t)(word >> (8 * (b % 4))));
+        }
       }
       {
         int hq = (w.flags & 1u) != 0;

@@ -154,7 +154,7 @@ def _proto(lib):
     lib.rk_imt_parser_words.restype = C.c_size_t
     lib.rk_imt_parser_bytes.argtypes = [C.c_int64]
     lib.rk_imt_parser_bytes.restype = C.c_size_t
-    lib.rk_imt_feed_bytes.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, C.c_int, vp]
+    lib.rk_imt_feed_bytes.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int, vp]
     lib.rk_tick_rollout.argtypes = [C.POINTER(VdtParams), C.POINTER(AdtParams), vp, vp, vp, vp, C.c_int64,
                                     C.POINTER(TickRollout), vp]
     lib.rk_imt_create.argtypes = [C.POINTER(vp)]

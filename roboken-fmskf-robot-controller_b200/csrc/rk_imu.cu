@@ -92,19 +92,29 @@ imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__
 
 // ---------------------------------------------------------------------------------------------
 // WIT serial codec (lib/wt901c/wit_c_sdk.c:77-164): the vendor parser's byte-wise state machine, one
-// thread per IMU.  The 11-byte window lives in three registers (bytes past the fill count are kept
-// zero, so inserting is an OR and dropping the first byte a funnel shift); the checksum is two SIMD
-// byte sums.  Bytes arrive as 32-bit words, 128 B per warp per load.
+// thread per IMU.  WitSerialDataIn does one of two things with a byte: while the window head is 0x55
+// it appends (and tests the checksum when the window reaches 11 bytes), otherwise it appends and
+// drops the head -- the window slides by one.  So whole runs of bytes are appended at once while the
+// head is 0x55 and no frame can complete inside the run; single bytes are handled only while sliding.
+// The window is a 96-bit shift register (w2:w1:w0) whose TOP cnt bytes are the parser's buffer, oldest
+// byte lowest: appending k bytes is three funnel shifts by 8k, dropping the head is cnt-- and a full
+// frame always sits at fixed positions (bytes 1..11).  Bytes arrive as 128-bit cells, 512 B per warp
+// per load, the next cell in flight while this one is parsed.
 // ---------------------------------------------------------------------------------------------
 struct Wit {
   uint32_t w0, w1, w2, cnt, flags;
+  bool     head_ok; // cnt != 0 and the oldest byte of the window is 0x55
   int      reg[16];
 };
-RK_DEV void wit_drop_first(Wit &p) {
-  p.w0 = __funnelshift_r(p.w0, p.w1, 8);
-  p.w1 = __funnelshift_r(p.w1, p.w2, 8);
-  p.w2 >>= 8;
-  p.cnt--;
+RK_DEV void wit_push(Wit &p, uint32_t R, uint32_t k) { // shift the low k (1..4) bytes of R in at the top
+  const uint32_t s = 8u * k;
+  p.w0 = __funnelshift_rc(p.w0, p.w1, s);
+  p.w1 = __funnelshift_rc(p.w1, p.w2, s);
+  p.w2 = __funnelshift_rc(p.w2, R, s);
+}
+RK_DEV bool wit_head_is_55(const Wit &p) { // byte at offset 12 - cnt of the register, cnt in 1..11
+  const uint32_t off = 12u - p.cnt, w = off < 4u ? p.w0 : (off < 8u ? p.w1 : p.w2);
+  return ((w >> (8u * (off & 3u))) & 0xFFu) == 0x55u;
 }
 RK_DEV void wit_store_reg(Wit &p, uint32_t reg, uint32_t val) { // CopeWitData's memcpy into sReg, tracked registers only
   const int v = sext16((int)val);
@@ -116,45 +126,80 @@ RK_DEV void wit_store_reg(Wit &p, uint32_t reg, uint32_t val) { // CopeWitData's
     if(reg == 0x51u + k) p.reg[12 + k] = v;
   if(reg == 0x54u) p.flags |= 1u; // q3 -> QUAT_UPDATE (SensorDataUpdata)
 }
-RK_DEV void wit_byte(Wit &p, uint32_t b) { // WitSerialDataIn, WIT_PROTOCOL_NORMAL  :132-164
-  const uint32_t sh = 8u * (p.cnt & 3u), ins = b << sh;
-  if(p.cnt < 4u) p.w0 |= ins;
-  else if(p.cnt < 8u) p.w1 |= ins;
-  else p.w2 |= ins;
-  p.cnt++;
-  if((p.w0 & 0xFFu) != 0x55u) {
-    wit_drop_first(p);
-    return;
-  }
-  if(p.cnt < 11u) return;
-  const uint32_t sum = (__vsadu4(p.w0, 0u) + __vsadu4(p.w1, 0u) + __vsadu4(p.w2 & 0xFFFFu, 0u)) & 0xFFu;
-  if(sum != ((p.w2 >> 16) & 0xFFu)) {
-    wit_drop_first(p);
-    return;
-  }
-  const uint32_t type = (p.w0 >> 8) & 0xFFu;
-  const uint32_t d0 = p.w0 >> 16, d1 = p.w1 & 0xFFFFu, d2 = p.w1 >> 16, d3 = p.w2 & 0xFFFFu;
-  p.w0 = 0u, p.w1 = 0u, p.w2 = 0u, p.cnt = 0u;
-  switch(type) { // CopeWitData :85-113
-  case 0x51u: p.reg[0] = sext16((int)d0), p.reg[1] = sext16((int)d1), p.reg[2] = sext16((int)d2); break;    // WIT_ACC (+ TEMP)
-  case 0x52u: p.reg[3] = sext16((int)d0), p.reg[4] = sext16((int)d1), p.reg[5] = sext16((int)d2); break;    // WIT_GYRO
-  case 0x54u: p.reg[6] = sext16((int)d0), p.reg[7] = sext16((int)d1), p.reg[8] = sext16((int)d2); break;    // WIT_MAGNETIC
-  case 0x53u: p.reg[9] = sext16((int)d0), p.reg[10] = sext16((int)d1), p.reg[11] = sext16((int)d2); break;  // WIT_ANGLE (+ VERSION)
-  case 0x59u:                                                                                                // WIT_QUATER
-    p.reg[12] = sext16((int)d0), p.reg[13] = sext16((int)d1), p.reg[14] = sext16((int)d2), p.reg[15] = sext16((int)d3);
+RK_DEV void wit_frame(Wit &p) { // a full window (bytes 1..11 of the register) with a good checksum: CopeWitData :77-130
+  const uint32_t type = (p.w0 >> 16) & 0xFFu;
+  const int d0 = sext16((int)__byte_perm(p.w0, p.w1, 0x0043)), d1 = sext16((int)(p.w1 >> 8));
+  const int d2 = sext16((int)__byte_perm(p.w1, p.w2, 0x0043)), d3 = sext16((int)(p.w2 >> 8));
+  switch(type) {
+  case 0x51u: p.reg[0] = d0, p.reg[1] = d1, p.reg[2] = d2; break;   // WIT_ACC (+ TEMP)
+  case 0x52u: p.reg[3] = d0, p.reg[4] = d1, p.reg[5] = d2; break;   // WIT_GYRO
+  case 0x54u: p.reg[6] = d0, p.reg[7] = d1, p.reg[8] = d2; break;   // WIT_MAGNETIC
+  case 0x53u: p.reg[9] = d0, p.reg[10] = d1, p.reg[11] = d2; break; // WIT_ANGLE (+ VERSION)
+  case 0x59u:                                                        // WIT_QUATER
+    p.reg[12] = d0, p.reg[13] = d1, p.reg[14] = d2, p.reg[15] = d3;
     p.flags |= 1u;
     break;
   case 0x5Fu: { // WIT_REGVALUE: four registers from s_uiReadRegIndex
     const uint32_t r = (p.flags >> 8) & 0xFFu;
-    wit_store_reg(p, r, d0), wit_store_reg(p, r + 1, d1), wit_store_reg(p, r + 2, d2), wit_store_reg(p, r + 3, d3);
+    wit_store_reg(p, r, (uint32_t)d0), wit_store_reg(p, r + 1, (uint32_t)d1), wit_store_reg(p, r + 2, (uint32_t)d2),
+        wit_store_reg(p, r + 3, (uint32_t)d3);
   } break;
   default: break; // TIME / DPORT / PRESS / GPS / VELOCITY / GSA write registers the IMU interface never reads; others are ignored
   }
 }
+// `rem` (<= 4) bytes, first byte in the low byte of R: WitSerialDataIn for each  :132-164
+RK_DEV void wit_bytes(Wit &p, uint32_t R, uint32_t rem) {
+  while(rem) {
+    if(p.cnt == 0u) p.head_ok = (R & 0xFFu) == 0x55u;
+    if(p.head_ok) { // appending: nothing happens before the window is full
+      const uint32_t take = min(rem, 11u - p.cnt);
+      wit_push(p, R, take);
+      p.cnt += take;
+      R = __funnelshift_rc(R, 0u, 8u * take);
+      rem -= take;
+      if(p.cnt == 11u) {
+        const uint32_t sum = __vsadu4(p.w0 & 0xFFFFFF00u, 0u) + __vsadu4(p.w1, 0u) + __vsadu4(p.w2 & 0x00FFFFFFu, 0u);
+        if((sum & 0xFFu) == (p.w2 >> 24)) {
+          wit_frame(p);
+          p.cnt = 0u; // s_uiWitDataCnt = 0
+        } else { // drop the head: the type byte is the new one
+          p.cnt     = 10u;
+          p.head_ok = ((p.w0 >> 16) & 0xFFu) == 0x55u;
+        }
+      }
+    } else { // sliding: append one byte, drop the head (a no-op on an empty window)
+      if(p.cnt) {
+        wit_push(p, R, 1u);
+        p.head_ok = wit_head_is_55(p);
+      }
+      R >>= 8;
+      rem--;
+    }
+  }
+}
+RK_DEV void wit_load(Wit &p, const uint4 a) { // parser block plane 0: window left-aligned, zeros past the count
+  p.cnt = min(a.z >> 24, 10u);                 // the window never rests full
+  p.w0 = a.x, p.w1 = a.y, p.w2 = a.z & 0x00FFFFFFu, p.flags = a.w;
+  p.head_ok = p.cnt && (p.w0 & 0xFFu) == 0x55u;
+  for(uint32_t k = p.cnt; k < 12u; k++) { // move the cnt bytes to the top
+    p.w2 = __funnelshift_l(p.w1, p.w2, 8);
+    p.w1 = __funnelshift_l(p.w0, p.w1, 8);
+    p.w0 <<= 8;
+  }
+}
+RK_DEV uint4 wit_save(const Wit &p) {
+  uint32_t w0 = p.w0, w1 = p.w1, w2 = p.w2;
+  for(uint32_t k = p.cnt; k < 12u; k++) {
+    w0 = __funnelshift_r(w0, w1, 8);
+    w1 = __funnelshift_r(w1, w2, 8);
+    w2 >>= 8;
+  }
+  return make_uint4(w0, w1, w2 | (p.cnt << 24), p.flags);
+}
 
 __global__ void __launch_bounds__(128)
-imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int64_t n, int K, int nwords,
-                      const uint32_t *__restrict__ bytes, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
+imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int64_t n, int K, int ncells, const uint4 *__restrict__ cells,
+                      const uint16_t *__restrict__ nbytes, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
   float   qi[4];
@@ -172,22 +217,33 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
   Wit      p;
   {
     const uint4 a = ld_plane(parser, n, 0, i), b = ld_plane(parser, n, 1, i), c = ld_plane(parser, n, 2, i);
-    p.cnt = min(a.z >> 24, 11u);
-    p.w0 = a.x, p.w1 = a.y, p.w2 = a.z & 0x00FFFFFFu, p.flags = a.w;
+    wit_load(p, a);
     const uint32_t r[8] = {b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
 #pragma unroll
     for(int k = 0; k < 8; k++) p.reg[2 * k] = lo16(r[k]), p.reg[2 * k + 1] = hi16(r[k]);
   }
+  const uint4 *src  = cells + i; // cell t = u * ncells + c of this IMU at src[t * n]
+  const int64_t total = (int64_t)K * ncells;
+  uint4 nxt = total > 0 ? __ldcs(src) : make_uint4(0u, 0u, 0u, 0u);
+  int64_t t = 0;
   for(int u = 0; u < K; u++) {
     const bool init = do_init && u == 0;
     if(init) { // WitInit: s_uiWitDataCnt = 0 ; WitReadReg(q0, 4): s_uiReadRegIndex = q0
-      p.w0 = 0u, p.w1 = 0u, p.w2 = 0u, p.cnt = 0u;
+      p.cnt   = 0u;
       p.flags = (p.flags & ~0xFF00u) | (0x51u << 8);
     }
-    for(int w = 0; w < nwords; w++) {
-      const uint32_t word = __ldcs(bytes + ((int64_t)u * nwords + w) * n + i);
+    uint32_t left = nbytes ? min((uint32_t)nbytes[(int64_t)u * n + i], 16u * (uint32_t)ncells) : 16u * (uint32_t)ncells;
+    for(int c = 0; c < ncells; c++) {
+      const uint4 cell = nxt;
+      t++;
+      if(t < total) nxt = __ldcs(src + t * n);
+      const uint32_t w[4] = {cell.x, cell.y, cell.z, cell.w};
 #pragma unroll
-      for(int b = 0; b < 4; b++) wit_byte(p, (word >> (8 * b)) & 0xFFu);
+      for(int j = 0; j < 4; j++) {
+        const uint32_t v = min(left, 4u);
+        left -= v;
+        wit_bytes(p, w[j], v);
+      }
     }
     const bool hq = (p.flags & 1u) != 0u; // isComComp :132-143
     if(hq) p.flags &= ~0xFFu;
@@ -217,7 +273,7 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
   uint32_t r[8];
 #pragma unroll
   for(int k = 0; k < 8; k++) r[k] = pack16(p.reg[2 * k], p.reg[2 * k + 1]);
-  st_plane(parser, n, 0, i, make_uint4(p.w0, p.w1, p.w2 | (p.cnt << 24), p.flags));
+  st_plane(parser, n, 0, i, wit_save(p));
   st_plane(parser, n, 1, i, make_uint4(r[0], r[1], r[2], r[3]));
   st_plane(parser, n, 2, i, make_uint4(r[4], r[5], r[6], r[7]));
 }
@@ -257,20 +313,22 @@ int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs
 size_t rk_imt_parser_words(void) { return RK_IP_WORDS; }
 size_t rk_imt_parser_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_IP_WORDS * 4u; }
 
-int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32_t nwords, const uint32_t *d_bytes, float *d_out,
-                      float *d_yaw_rad, int do_init, void *stream) {
+int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32_t ncells, const void *d_cells, const uint16_t *d_nbytes,
+                      float *d_out, float *d_yaw_rad, int do_init, void *stream) {
   if(n == 0 || K == 0) return RK_OK;
-  if(n < 0 || K < 0 || nwords < 0 || (nwords > 0 && !d_bytes)) {
-    set_error("rk_imt_feed_bytes: bad n / K / nwords / bytes");
+  if(n < 0 || K < 0 || ncells < 0 || ncells > 4095 || (ncells > 0 && !d_cells)) {
+    set_error("rk_imt_feed_bytes: bad n / K / ncells / cells");
     return RK_ERR_ARG;
   }
-  if(!d_state || !d_parser || ((uintptr_t)d_state & 15u) || ((uintptr_t)d_parser & 15u) || ((uintptr_t)d_out & 15u)) {
-    set_error("rk_imt_feed_bytes: d_state / d_parser / d_out must be 16-byte aligned (state and parser non-NULL)");
+  if(!d_state || !d_parser || ((uintptr_t)d_state & 15u) || ((uintptr_t)d_parser & 15u) || ((uintptr_t)d_out & 15u) ||
+     ((uintptr_t)d_cells & 15u) || ((uintptr_t)d_nbytes & 1u)) {
+    set_error("rk_imt_feed_bytes: d_state / d_parser / d_cells / d_out must be 16-byte aligned (state and parser non-NULL)");
     return RK_ERR_ARG;
   }
   if(int rc = require_device()) return rc;
-  imt_feed_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_state, (uint4 *)d_parser, n, K, nwords,
-                                                                                       d_bytes, (float4 *)d_out, d_yaw_rad, do_init);
+  imt_feed_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_state, (uint4 *)d_parser, n, K, ncells,
+                                                                                       (const uint4 *)d_cells, d_nbytes, (float4 *)d_out,
+                                                                                       d_yaw_rad, do_init);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }

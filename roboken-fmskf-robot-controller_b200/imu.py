@@ -36,13 +36,17 @@ class ImuBatch:
                                            None if out is None else out.data_ptr(), int(bool(do_init)),
                                            C.c_void_p(st.cuda_stream)))
 
-    def feed_bytes(self, wire, out=None, yaw_rad=None, do_init=False, stream=None):
-        """wire: uint32/int32 [K, nwords, n] serial bytes (first byte in the low byte of each word) through the
-        vendor parser's state machine (lib/wt901c/wit_c_sdk.c:132-164), then IMU_IF_WT901C::update per update
-        (::init for the first when do_init).  out: float32 [K, 4, n, 4] or None; yaw_rad: float32 [K, n] or None."""
-        assert wire.is_cuda and wire.dtype in (torch.int32, torch.uint32) and wire.is_contiguous() and wire.dim() == 3
-        assert wire.shape[2] == self.n
-        K, nwords = int(wire.shape[0]), int(wire.shape[1])
+    def feed_bytes(self, cells, nbytes=None, out=None, yaw_rad=None, do_init=False, stream=None):
+        """cells: int32 [K, ncells, n, 4] serial bytes in 128-bit cells (wire order from the low byte up); nbytes:
+        int16/uint16 [K, n] bytes really on the wire per update, or None (full slots).  Runs the vendor parser's
+        state machine (lib/wt901c/wit_c_sdk.c:132-164), then IMU_IF_WT901C::update per update (::init for the
+        first when do_init).  out: float32 [K, 4, n, 4] or None; yaw_rad: float32 [K, n] or None."""
+        assert cells.is_cuda and cells.dtype in (torch.int32, torch.uint32) and cells.is_contiguous() and cells.dim() == 4
+        assert cells.shape[2] == self.n and cells.shape[3] == 4
+        K, ncells = int(cells.shape[0]), int(cells.shape[1])
+        if nbytes is not None:
+            assert nbytes.is_cuda and nbytes.dtype in (torch.int16, torch.uint16) and nbytes.is_contiguous()
+            assert tuple(nbytes.shape) == (K, self.n)
         if out is not None:
             assert out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (K, 4, self.n, 4)
         if yaw_rad is not None:
@@ -53,7 +57,8 @@ class ImuBatch:
                 self.parser = torch.zeros(layout.IP_WORDS * self.n, dtype=torch.int32, device=self.device)
         st = stream if stream is not None else torch.cuda.current_stream(self.dev_index)
         _cabi.check(self.lib.rk_set_device(self.dev_index))
-        _cabi.check(self.lib.rk_imt_feed_bytes(self.state.data_ptr(), self.parser.data_ptr(), self.n, K, nwords, wire.data_ptr(),
+        _cabi.check(self.lib.rk_imt_feed_bytes(self.state.data_ptr(), self.parser.data_ptr(), self.n, K, ncells, cells.data_ptr(),
+                                               None if nbytes is None else nbytes.data_ptr(),
                                                None if out is None else out.data_ptr(),
                                                None if yaw_rad is None else yaw_rad.data_ptr(), int(bool(do_init)),
                                                C.c_void_p(st.cuda_stream)))

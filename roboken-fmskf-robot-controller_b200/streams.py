@@ -200,13 +200,13 @@ def wit_frame(ftype, d):
     return bytes(b + [sum(b) & 0xFF])
 
 
-def imu_wire_clean(regs, nwords=14, pad=0x00):
+def imu_wire_clean(regs, ncells=4):
     """The byte stream a healthy WT901C would send for the register snapshots `regs` (int16 [K, 16, n], as
-    imu_samples): per update the five frames ACC, GYRO, ANGLE, MAGNETIC, QUATER (4th words: TEMP / VERSION = 0)
-    and padding up to nwords*4 bytes.  Returns uint32 [K, nwords, n] in rk_imt_feed_bytes layout."""
+    imu_samples): per update the five frames ACC, GYRO, ANGLE, MAGNETIC, QUATER (4th words: TEMP / VERSION = 0),
+    55 bytes.  Returns (cells uint32 [K, ncells, n, 4], nbytes uint16 [K, n]) in rk_imt_feed_bytes layout."""
     K, _, n = regs.shape
-    assert nwords * 4 >= 55
-    b = np.full((K, nwords * 4, n), pad, dtype=np.uint8)
+    assert ncells * 16 >= 55
+    b = np.zeros((K, ncells * 16, n), dtype=np.uint8)
     r = regs.astype(np.int16).view(np.uint16)
     plan = ((WIT_ACC, (0, 1, 2, None)), (WIT_GYRO, (3, 4, 5, None)), (WIT_ANGLE, (9, 10, 11, None)),
             (WIT_MAGNETIC, (6, 7, 8, None)), (WIT_QUATER, (12, 13, 14, 15)))
@@ -217,30 +217,38 @@ def imu_wire_clean(regs, nwords=14, pad=0x00):
             if s is not None:
                 b[:, o + 2 + 2 * k, :] = r[:, s, :] & 0xFF
                 b[:, o + 3 + 2 * k, :] = r[:, s, :] >> 8
-            else:
-                b[:, o + 2 + 2 * k, :] = b[:, o + 3 + 2 * k, :] = 0
         b[:, o + 10, :] = b[:, o : o + 10, :].astype(np.uint32).sum(axis=1).astype(np.uint8)
-    return _pack_wire(b)
+    return _pack_wire(b), np.full((K, n), 55, dtype=np.uint16)
 
 
 def _pack_wire(b):
-    """uint8 [K, nbytes, n] (wire order) -> uint32 [K, nwords, n], first byte in the low byte."""
+    """uint8 [K, 16*ncells, n] (wire order) -> uint32 [K, ncells, n, 4]: 128-bit cells, first byte in the low byte."""
     K, nb, n = b.shape
-    q = b.reshape(K, nb // 4, 4, n).astype(np.uint32)
-    return np.ascontiguousarray(q[:, :, 0] | (q[:, :, 1] << 8) | (q[:, :, 2] << 16) | (q[:, :, 3] << 24))
+    q = b.reshape(K, nb // 16, 4, 4, n).astype(np.uint32)  # [K, cell, word, byte, n]
+    w = q[:, :, :, 0] | (q[:, :, :, 1] << 8) | (q[:, :, :, 2] << 16) | (q[:, :, :, 3] << 24)  # [K, cell, word, n]
+    return np.ascontiguousarray(w.transpose(0, 1, 3, 2))
 
 
-def imu_wire_fuzz(n, K, nwords=14, seed=0x5EED, first=0):
-    """Adversarial serial traffic: per IMU one continuous byte stream cut into K updates of nwords*4 bytes, so
-    frames straddle update boundaries.  Items: valid frames of every type CopeWitData knows (0x50..0x5A, 0x5F)
-    and of unknown types, frames with a broken checksum, truncated frames, 0x55 runs and random garbage; data
-    words are biased towards 0x55 bytes so that false headers occur inside payloads.  The stream always opens
-    with a valid quaternion frame (IMU_IF_WT901C::init() spins until one arrives).  uint32 [K, nwords, n]."""
-    total = K * nwords * 4
-    assert total >= 11
-    out = np.zeros((n, total), dtype=np.uint8)
+def imu_wire_fuzz(n, K, ncells=4, seed=0x5EED, first=0, full_slots=False):
+    """Adversarial serial traffic: per IMU one continuous byte stream cut into K updates of 0 .. 16*ncells bytes
+    (1 update in 8 sees an idle line; full_slots: every update carries exactly 16*ncells bytes), so frames straddle
+    update boundaries.  Items: valid frames of every type CopeWitData knows (0x50..0x5A, 0x5F) and of unknown
+    types, frames with a broken checksum, truncated frames, 0x55 runs, zeros and random garbage; data words are
+    biased towards 0x55 bytes so that false headers occur inside payloads.  The stream always opens with a valid
+    quaternion frame inside update 0 (IMU_IF_WT901C::init() spins until one arrives).
+    Returns (cells uint32 [K, ncells, n, 4], nbytes uint16 [K, n])."""
+    cap = 16 * ncells
+    out = np.zeros((n, K, cap), dtype=np.uint8)
+    nbytes = np.zeros((K, n), dtype=np.uint16)
     for i in range(n):
         rng = np.random.default_rng([int(seed) & 0xFFFFFFFF, int(first) + i, 0x317])
+        if full_slots:
+            lens = np.full(K, cap, dtype=np.int64)
+        else:
+            lens = rng.integers(0, cap + 1, size=K)
+            lens[rng.integers(0, 8, size=K) == 0] = 0
+            lens[0] = rng.integers(11, cap + 1)
+        total = int(lens.sum())
         buf = bytearray()
 
         def words():
@@ -269,7 +277,13 @@ def imu_wire_fuzz(n, K, nwords=14, seed=0x5EED, first=0):
                 buf += bytes([0x55] * int(rng.integers(1, 14)))
             elif kind == 13:
                 buf += bytes(int(x) for x in rng.integers(0, 256, size=int(rng.integers(1, 24))))
-            else:  # a quiet line: an update without any byte is not expressible (fixed nwords), idle = zeros
-                buf += bytes(int(rng.integers(1, nwords * 4 + 12)))
-        out[i] = np.frombuffer(bytes(buf[:total]), dtype=np.uint8)
-    return _pack_wire(np.ascontiguousarray(out.reshape(n, K, nwords * 4).transpose(1, 2, 0)))
+            else:
+                buf += bytes(int(rng.integers(1, 20)))
+        o = 0
+        for u in range(K):
+            out[i, u, : lens[u]] = np.frombuffer(bytes(buf[o : o + lens[u]]), dtype=np.uint8)
+            # bytes past the count are junk the engine must not look at
+            out[i, u, lens[u] :] = rng.integers(0, 256, size=cap - lens[u])
+            o += int(lens[u])
+        nbytes[:, i] = lens
+    return _pack_wire(np.ascontiguousarray(out.transpose(1, 2, 0))), nbytes

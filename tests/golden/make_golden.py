@@ -113,12 +113,12 @@ def imu_golden():
 
 def imu_wire_golden():
     # WIT serial codec: adversarial byte streams through the unmodified vendor parser + IMU_IF_WT901C
-    n, K, nwords = 48, 20, 6
-    wire = streams.imu_wire_fuzz(n, K, nwords=nwords, seed=0x5EED)
+    n, K, ncells = 48, 20, 2
+    cells, nbytes = streams.imu_wire_fuzz(n, K, ncells=ncells, seed=0x5EED)
     st = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
-    o, sreg = ol.imu_bytes_ref(st, n, wire, want_out=True)
+    o, sreg = ol.imu_bytes_ref(st, n, cells, nbytes, want_out=True)
     path = os.path.join(HERE, "imu_wire_golden.npz")
-    np.savez_compressed(path, wire=wire, out=o, state=st, sreg=sreg)
+    np.savez_compressed(path, cells=cells, nbytes=nbytes, out=o, state=st, sreg=sreg)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

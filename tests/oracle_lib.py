@@ -40,7 +40,7 @@ def port():
         lib.orc_vdt_update.argtypes = [C.POINTER(_cabi.VdtParams), vp]
         lib.orc_imt_update.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int]
         lib.orc_imt_update.restype = None
-        lib.orc_imt_feed_bytes.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp, vp, C.c_int]
+        lib.orc_imt_feed_bytes.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]
         lib.orc_imt_feed_bytes.restype = None
         lib.orc_adt_batch.argtypes = [C.c_int, C.POINTER(_cabi.AdtParams), vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                       vp, vp, vp, vp, vp]
@@ -103,7 +103,7 @@ def ref(name="libref_vdt.so"):
             lib.ref_imt_import.argtypes = [vp, vp]
             lib.ref_imt_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int]
             lib.ref_imt_rollout.restype = None
-            lib.ref_imt_bytes_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
+            lib.ref_imt_bytes_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp]
             lib.ref_imt_bytes_rollout.restype = None
         if name.startswith("libref_arm"):
             lib.ref_adt_create.restype = vp
@@ -177,23 +177,28 @@ def imu_ref(state_soa, n, regs, have=None, want_out=False, do_init=False):
     return out
 
 
-def imu_bytes_port(state_soa, parser_soa, n, wire, want_out=False, want_yaw=False, do_init=False):
-    """rk_imt_feed_bytes on host arrays (the port).  wire: uint32 [K, nwords, n]."""
-    K, nwords = wire.shape[0], wire.shape[1]
+def imu_bytes_port(state_soa, parser_soa, n, cells, nbytes=None, want_out=False, want_yaw=False, do_init=False):
+    """rk_imt_feed_bytes on host arrays (the port).  cells: uint32 [K, ncells, n, 4]; nbytes: uint16 [K, n] or None."""
+    K, ncells = cells.shape[0], cells.shape[1]
+    assert cells.dtype == np.uint32 and cells.shape[2:] == (n, 4) and cells.flags.c_contiguous
+    assert nbytes is None or (nbytes.dtype == np.uint16 and nbytes.shape == (K, n) and nbytes.flags.c_contiguous)
     out = np.zeros((K, 4, n, 4), dtype=np.uint32) if want_out else None
     yaw = np.zeros((K, n), dtype=np.float32) if want_yaw else None
-    port().orc_imt_feed_bytes(_ptr(state_soa), _ptr(parser_soa), n, 0, n, K, nwords, _ptr(wire), _ptr(out), _ptr(yaw), int(do_init))
+    port().orc_imt_feed_bytes(_ptr(state_soa), _ptr(parser_soa), n, 0, n, K, ncells, _ptr(cells), _ptr(nbytes), _ptr(out), _ptr(yaw),
+                              int(do_init))
     return (out, yaw) if want_yaw else out
 
 
-def imu_bytes_ref(state_soa, n, wire, want_out=False):
+def imu_bytes_ref(state_soa, n, cells, nbytes=None, want_out=False):
     """The compiled reference (vendor parser + IMU_IF_WT901C) replayed from power-on: update 0 is init().
     Returns (out, sreg int16 [n, 16])."""
-    K, nwords = wire.shape[0], wire.shape[1]
-    assert nwords * 4 <= 512  # the fake Serial6 FIFO
+    K, ncells = cells.shape[0], cells.shape[1]
+    assert ncells * 16 <= 512  # the fake Serial6 FIFO
+    assert cells.dtype == np.uint32 and cells.shape[2:] == (n, 4) and cells.flags.c_contiguous
+    assert nbytes is None or (nbytes.dtype == np.uint16 and nbytes.shape == (K, n) and nbytes.flags.c_contiguous)
     out = np.zeros((K, 4, n, 4), dtype=np.uint32) if want_out else None
     sreg = np.zeros((n, 16), dtype=np.int16)
-    ref("libref_imu.so").ref_imt_bytes_rollout(_ptr(state_soa), n, 0, n, K, nwords, _ptr(wire), _ptr(out), _ptr(sreg))
+    ref("libref_imu.so").ref_imt_bytes_rollout(_ptr(state_soa), n, 0, n, K, ncells, _ptr(cells), _ptr(nbytes), _ptr(out), _ptr(sreg))
     return out, sreg
 
 

@@ -29,11 +29,11 @@ def test_clean_wire_equals_register_path():
     """The five frames of a healthy sensor give exactly what the register-level entry gives."""
     n, K = 50, 12
     regs, _ = streams.imu_samples(n, K, seed=11)
-    wire = streams.imu_wire_clean(regs, nwords=14)
+    cells, nbytes = streams.imu_wire_clean(regs)
     a = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
     oa = ol.imu_port(a, n, regs, None, want_out=True, do_init=True)
     b, pb = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
-    ob, yaw = ol.imu_bytes_port(b, pb, n, wire, want_out=True, want_yaw=True, do_init=True)
+    ob, yaw = ol.imu_bytes_port(b, pb, n, cells, nbytes, want_out=True, want_yaw=True, do_init=True)
     np.testing.assert_array_equal(oa, ob)
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(parser_sreg(pb, n), regs[-1].T)
@@ -42,14 +42,16 @@ def test_clean_wire_equals_register_path():
 
 
 @needs_ref
-@pytest.mark.parametrize("n,K,nwords,seed", [(64, 24, 14, 1), (48, 40, 3, 2), (32, 10, 64, 3), (40, 64, 4, 4)])
-def test_port_equals_ref_fuzzed_wire(n, K, nwords, seed):
-    # nwords >= 3: the opening quaternion frame must fit update 0 (init() spins until it sees one)
-    wire = streams.imu_wire_fuzz(n, K, nwords=nwords, seed=seed)
+@pytest.mark.parametrize("n,K,ncells,seed,full", [(64, 24, 4, 1, False), (48, 40, 1, 2, False), (32, 10, 16, 3, False),
+                                                   (40, 64, 1, 4, True), (24, 12, 3, 5, True)])
+def test_port_equals_ref_fuzzed_wire(n, K, ncells, seed, full):
+    cells, nbytes = streams.imu_wire_fuzz(n, K, ncells=ncells, seed=seed, full_slots=full)
+    if full:
+        nbytes = None
     a, pa = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
-    oa = ol.imu_bytes_port(a, pa, n, wire, want_out=True, do_init=True)
+    oa = ol.imu_bytes_port(a, pa, n, cells, nbytes, want_out=True, do_init=True)
     b = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
-    ob, sreg = ol.imu_bytes_ref(b, n, wire, want_out=True)
+    ob, sreg = ol.imu_bytes_ref(b, n, cells, nbytes, want_out=True)
     np.testing.assert_array_equal(oa, ob)
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(parser_sreg(pa, n), sreg)
@@ -61,15 +63,16 @@ def test_port_equals_ref_fuzzed_wire(n, K, nwords, seed):
 @needs_ref
 def test_port_chunked_equals_ref_one_pass():
     """Parser state carried across calls (window, fill count, read index, sReg) == one uninterrupted replay."""
-    n, K, nwords = 40, 30, 5
-    wire = streams.imu_wire_fuzz(n, K, nwords=nwords, seed=9)
+    n, K, ncells = 40, 30, 2
+    cells, nbytes = streams.imu_wire_fuzz(n, K, ncells=ncells, seed=9)
     a, pa = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
     outs, k0 = [], 0
     for k1 in (1, 2, 9, 10, 23, 30):
-        outs.append(ol.imu_bytes_port(a, pa, n, np.ascontiguousarray(wire[k0:k1]), want_out=True, do_init=(k0 == 0)))
+        outs.append(ol.imu_bytes_port(a, pa, n, np.ascontiguousarray(cells[k0:k1]), np.ascontiguousarray(nbytes[k0:k1]),
+                                      want_out=True, do_init=(k0 == 0)))
         k0 = k1
     b = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
-    ob, sreg = ol.imu_bytes_ref(b, n, wire, want_out=True)
+    ob, sreg = ol.imu_bytes_ref(b, n, cells, nbytes, want_out=True)
     np.testing.assert_array_equal(np.concatenate(outs), ob)
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(parser_sreg(pa, n), sreg)
@@ -81,11 +84,11 @@ def test_false_header_resync_known_answer():
     q = streams.wit_frame(streams.WIT_QUATER, [16384, 0, 0, 0])
     acc = streams.wit_frame(streams.WIT_ACC, [2048, -1024, 512, 77])
     raw = q + bytes([0x55, 0x51, 1, 2, 3]) + acc + bytes(3)
-    raw += bytes(-len(raw) % 4)
-    nb = len(raw)
-    wire = np.frombuffer(raw, dtype="<u4").reshape(1, nb // 4, 1).copy()
+    nb = np.array([[len(raw)]], dtype=np.uint16)
+    raw += bytes([0xEE] * (-len(raw) % 16))  # junk past the count
+    cells = np.frombuffer(raw, dtype="<u4").reshape(1, len(raw) // 16, 1, 4).copy()
     st, ps = np.zeros(layout.IS_WORDS, dtype=np.uint32), np.zeros(layout.IP_WORDS, dtype=np.uint32)
-    out = ol.imu_bytes_port(st, ps, 1, wire, want_out=True, do_init=True)
+    out = ol.imu_bytes_port(st, ps, 1, cells, nb, want_out=True, do_init=True)
     d = out.view(np.float32).reshape(16)
     # the false header swallowed the real header: 0x55 0x51 01 02 03 55 51 00 08 00 fc | sum mismatch -> slide
     sreg = parser_sreg(ps, 1)[0]
@@ -96,11 +99,12 @@ def test_false_header_resync_known_answer():
 
 def test_golden_imu_wire():
     g = np.load(GOLD)
-    n, K, nwords = 48, 20, 6
-    wire = streams.imu_wire_fuzz(n, K, nwords=nwords, seed=0x5EED)
-    np.testing.assert_array_equal(wire, g["wire"])
+    n, K, ncells = 48, 20, 2
+    cells, nbytes = streams.imu_wire_fuzz(n, K, ncells=ncells, seed=0x5EED)
+    np.testing.assert_array_equal(cells, g["cells"])
+    np.testing.assert_array_equal(nbytes, g["nbytes"])
     st, ps = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
-    out = ol.imu_bytes_port(st, ps, n, wire, want_out=True, do_init=True)
+    out = ol.imu_bytes_port(st, ps, n, cells, nbytes, want_out=True, do_init=True)
     np.testing.assert_array_equal(out, g["out"])
     np.testing.assert_array_equal(st, g["state"])
     np.testing.assert_array_equal(parser_sreg(ps, n), g["sreg"])

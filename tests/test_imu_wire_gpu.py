@@ -15,11 +15,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def gpu_feed(ib, wire, do_init, want_yaw=False):
-    K, _, n = wire.shape
+def gpu_feed(ib, cells, nbytes, do_init, want_yaw=False):
+    K, _, n, _ = cells.shape
     out = torch.zeros((K, 4, n, 4), dtype=torch.float32, device=DEV)
     yaw = torch.zeros((K, n), dtype=torch.float32, device=DEV) if want_yaw else None
-    ib.feed_bytes(torch.from_numpy(wire.view(np.int32)).to(DEV), out, yaw, do_init)
+    ib.feed_bytes(torch.from_numpy(cells.view(np.int32)).to(DEV),
+                  None if nbytes is None else torch.from_numpy(nbytes.view(np.int16)).to(DEV), out, yaw, do_init)
     torch.cuda.synchronize()
     o = out.cpu().numpy().view(np.uint32)
     return (o, yaw.cpu().numpy()) if want_yaw else o
@@ -33,29 +34,34 @@ def test_wire_golden():
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "imu_wire_golden.npz"))
     n = 48
     ib = ImuBatch(n, DEV)
-    out = gpu_feed(ib, g["wire"], True)
+    out = gpu_feed(ib, g["cells"], g["nbytes"], True)
     st, ps = blocks(ib)
     np.testing.assert_array_equal(out, g["out"])
     np.testing.assert_array_equal(st, g["state"])
     np.testing.assert_array_equal(parser_sreg(ps, n), g["sreg"])
 
 
-@pytest.mark.parametrize("n,K,nwords,seed", [(1, 6, 3, 1), (300, 40, 14, 2), (1031, 12, 5, 3), (129, 7, 40, 4)])
-def test_wire_fuzz_vs_port(n, K, nwords, seed):
-    wire = streams.imu_wire_fuzz(n, K, nwords=nwords, seed=seed)
+@pytest.mark.parametrize("n,K,ncells,seed,full", [(1, 6, 1, 1, False), (300, 40, 4, 2, False), (1031, 12, 2, 3, False),
+                                                   (129, 7, 10, 4, False), (513, 20, 3, 5, True)])
+def test_wire_fuzz_vs_port(n, K, ncells, seed, full):
+    wire, nb = streams.imu_wire_fuzz(n, K, ncells=ncells, seed=seed, full_slots=full)
+    if full:
+        nb = None
     a, pa = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
-    oa, ya = ol.imu_bytes_port(a, pa, n, wire, want_out=True, want_yaw=True, do_init=True)
+    oa, ya = ol.imu_bytes_port(a, pa, n, wire, nb, want_out=True, want_yaw=True, do_init=True)
     ib = ImuBatch(n, DEV)
-    out, yaw = gpu_feed(ib, wire, True, want_yaw=True)
+    out, yaw = gpu_feed(ib, wire, nb, True, want_yaw=True)
     st, ps = blocks(ib)
     np.testing.assert_array_equal(out, oa)
     np.testing.assert_array_equal(yaw.view(np.uint32), ya.view(np.uint32))
     np.testing.assert_array_equal(st, a)
     np.testing.assert_array_equal(ps, pa)  # window bytes, fill count, read index, pending flag, sReg: all of it
     # carry on from that parser state, no init, different traffic
-    wire2 = streams.imu_wire_fuzz(n, K, nwords=nwords, seed=seed + 50)
-    ob = ol.imu_bytes_port(a, pa, n, wire2, want_out=True)
-    out2 = gpu_feed(ib, wire2, False)
+    wire2, nb2 = streams.imu_wire_fuzz(n, K, ncells=ncells, seed=seed + 50, full_slots=full)
+    if full:
+        nb2 = None
+    ob = ol.imu_bytes_port(a, pa, n, wire2, nb2, want_out=True)
+    out2 = gpu_feed(ib, wire2, nb2, False)
     st, ps = blocks(ib)
     np.testing.assert_array_equal(out2, ob)
     np.testing.assert_array_equal(st, a)
@@ -63,13 +69,13 @@ def test_wire_fuzz_vs_port(n, K, nwords, seed):
 
 
 def test_wire_one_launch_equals_many():
-    n, K, nwords = 257, 24, 4
-    wire = streams.imu_wire_fuzz(n, K, nwords=nwords, seed=77)
+    n, K, ncells = 257, 24, 2
+    wire, nb = streams.imu_wire_fuzz(n, K, ncells=ncells, seed=77)
     one = ImuBatch(n, DEV)
-    o1 = gpu_feed(one, wire, True)
+    o1 = gpu_feed(one, wire, nb, True)
     many, outs, k0 = ImuBatch(n, DEV), [], 0
     for k1 in (1, 5, 6, 17, 24):
-        outs.append(gpu_feed(many, np.ascontiguousarray(wire[k0:k1]), k0 == 0))
+        outs.append(gpu_feed(many, np.ascontiguousarray(wire[k0:k1]), np.ascontiguousarray(nb[k0:k1]), k0 == 0))
         k0 = k1
     np.testing.assert_array_equal(np.concatenate(outs), o1)
     for x, y in zip(blocks(one), blocks(many)):
@@ -80,12 +86,12 @@ def test_clean_wire_equals_register_kernel():
     """A healthy sensor's five frames through the byte codec == the same registers through rk_imt_update."""
     n, K = 5000, 16
     regs, _ = streams.imu_samples(n, K, seed=31)
-    wire = streams.imu_wire_clean(regs, nwords=14)
+    wire, nb = streams.imu_wire_clean(regs)
     a = ImuBatch(n, DEV)
     oa = torch.zeros((K, 4, n, 4), dtype=torch.float32, device=DEV)
     a.update(torch.from_numpy(regs).to(DEV), None, oa, True)
     b = ImuBatch(n, DEV)
-    ob = gpu_feed(b, wire, True)
+    ob = gpu_feed(b, wire, nb, True)
     np.testing.assert_array_equal(oa.cpu().numpy().view(np.uint32), ob)
     np.testing.assert_array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
     np.testing.assert_array_equal(parser_sreg(blocks(b)[1], n), regs[-1].T)
@@ -96,6 +102,6 @@ def test_feed_bytes_argument_errors():
     from roboken_fmskf_robot_controller_b200 import _cabi
     lib = _cabi.load()
     ib.parser = torch.zeros(layout.IP_WORDS * 4, dtype=torch.int32, device=DEV)
-    assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), ib.parser.data_ptr(), 4, 1, 2, None, None, None, 0, None) == 1
-    assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), None, 4, 1, 0, None, None, None, 0, None) == 1
-    assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), ib.parser.data_ptr(), 0, 1, 2, None, None, None, 0, None) == 0
+    assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), ib.parser.data_ptr(), 4, 1, 2, None, None, None, None, 0, None) == 1
+    assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), None, 4, 1, 0, None, None, None, None, 0, None) == 1
+    assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), ib.parser.data_ptr(), 0, 1, 2, None, None, None, None, 0, None) == 0

@@ -62,22 +62,23 @@ def bench_imu(a, dev):
 
 
 def bench_wire(a, dev):
-    """rk_imt_feed_bytes: 56 serial bytes (five WIT frames + 1 idle byte) per update through the parser state machine."""
-    n, K, nwords = a.n, a.imu_updates, 14
+    """rk_imt_feed_bytes: 55 serial bytes (five WIT frames) per update in four 128-bit cells through the parser."""
+    n, K, ncells = a.n, a.imu_updates, 4
     uniq = min(n, 1 << 14)
     regs, _ = streams.imu_samples(uniq, K, seed=3)
-    wire = streams.imu_wire_clean(regs, nwords=nwords)
-    wire_d = torch.from_numpy(np.tile(wire, (1, 1, n // uniq)).view(np.int32)).to(dev)
+    cells, nb = streams.imu_wire_clean(regs, ncells=ncells)
+    cells_d = torch.from_numpy(np.tile(cells, (1, 1, n // uniq, 1)).view(np.int32)).to(dev)
+    nb_d = torch.from_numpy(np.tile(nb, (1, n // uniq)).view(np.int16)).to(dev)
     ib = ImuBatch(n, dev)
-    ib.feed_bytes(wire_d[:1].contiguous(), None, None, do_init=True)
+    ib.feed_bytes(cells_d[:1].contiguous(), nb_d[:1].contiguous(), None, None, do_init=True)
     out = torch.empty((K, 4, n, 4), dtype=torch.float32, device=dev)
     peak, src = hbm_peak()
     for mode in ("full_output", "state_only"):
-        ms = timed(lambda: ib.feed_bytes(wire_d, out if mode == "full_output" else None, None), a.reps)
-        per = nwords * 4 + (64 if mode == "full_output" else 0)
+        ms = timed(lambda: ib.feed_bytes(cells_d, nb_d, out if mode == "full_output" else None, None), a.reps)
+        per = ncells * 16 + 2 + (64 if mode == "full_output" else 0)
         nbytes = n * (K * per + 2 * (96 + 48))
-        print(json.dumps({"kernel": "rk::imt_feed_bytes_kernel", "workload": f"8f-3: {n} IMUs x {K} updates x {nwords * 4} wire bytes, {mode}",
-                          "updates_per_s": n * K / (ms * 1e-3), "wire_bytes_per_s": n * K * nwords * 4 / (ms * 1e-3), "ms_per_launch": ms,
+        print(json.dumps({"kernel": "rk::imt_feed_bytes_kernel", "workload": f"8f-3: {n} IMUs x {K} updates x 55 wire bytes in {ncells} cells, {mode}",
+                          "updates_per_s": n * K / (ms * 1e-3), "wire_bytes_per_s": n * K * 55 / (ms * 1e-3), "ms_per_launch": ms,
                           "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                        "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "peak_source": src,
                                        "algorithmic_bytes_per_update": per, "algorithmic_bytes_per_launch": nbytes}}), flush=True)
