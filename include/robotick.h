@@ -469,6 +469,60 @@ typedef struct rk_tick_rollout {
 int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t *ap, void *d_vdt_state, void *d_imt_state,
                     void *d_adt_state, const void *d_adt_cmdtab, int64_t n, const rk_tick_rollout_t *args, void *stream);
 
+/* =====================================================================================
+ * RobotManager guard: the vehicle-management block of RMT's routine_ros()
+ * (src/RobotManager/RM_task_main.cpp:484-767), one call = K manager cycles of n robots.  Per
+ * cycle: at most one ROS message is delivered through the callback the firmware runs for it
+ * (sb_mecanumCmd_callback :206-218, sb_mecanumContOdr_callback :220-233, sb_mecanumCmdVel_callback
+ * :235-248, sb_cmd_callback :159-204), the floor / wall sensors are read (FDT::get_now_FDinfo), and
+ * the block decides what VDT receives: the command as it is, a wall-leave move (:546-577), a floor
+ * veto -- MOVE_STOP for direction commands (:581-673), zeroed translation for continuous commands
+ * by the sector the table arctangent UTIL::mymath::atan2f (src/Utility/util_mymath.cpp:98-126) puts
+ * the heading in (:674-749) -- or the 200-cycle no-command watchdog stop (:752-767).  The output
+ * record is the RK_CMD_MSG_* vocabulary rk_vdt_rollout's command layer takes (kind 0: nothing sent),
+ * so guarded rollouts chain the two calls.  u32_time_ms travels in kind >> 8 (24 bits).
+ * ===================================================================================== */
+typedef struct rk_rmt_params {
+  uint32_t no_cmd_stop_thre;      /* U32_MCN_NO_CMD_STOP_THRE       :62 */
+  uint32_t wall_leave_time_ms;    /* U32_MCN_WALL_LEAVE_TIME_MS     :63 */
+  uint32_t wall_leave_speed_mmps; /* U32_MCN_WALL_LEAVE_SPEED_MMPS  :64 */
+} rk_rmt_params_t;
+void rk_rmt_default_params(rk_rmt_params_t *p);
+
+/* manager state per robot: one plane */
+enum {
+  RK_RS_CMD_STATUS   = 0, /* NOW_CMD_STATUS (CmdStatus :45-59; RELAX = 0 at power-on) */
+  RK_RS_IGNORE_FLOOR = 1, /* IS_IGNORE_FLOOR_DETECTION */
+  RK_RS_NO_CMD_CNT   = 2, /* U32_MCN_NO_CMD_CNT */
+  RK_RS_ABORT        = 3, /* vdt_abort.val (VDT_REQ_ABORT :70-92): wall_abort x+/x-/y+/y- bits 0-3, fllr_abort
+                             x+/x-/y+/y- bits 8-11, fllr_abort_vdt_cont_trans_dir bit 16 */
+  RK_RS_WORDS        = 4
+};
+/* input record per robot per cycle: three 128-bit cells, cell c of cycle u, robot i at (u*3 + c)*n + i */
+enum {
+  RK_ROS_NONE = 0,
+  RK_ROS_MECANUM_CMD  = 1, /* interfaces/MecanumCommand {cmd, time, speed}: words A, B, C */
+  RK_ROS_MECANUM_CONT = 2, /* interfaces/MecanumContOrder {Twist speed, time_ms}: doubles X, Y, Z (linear.x, linear.y
+                              in mm/s, angular.z), time_ms in word A */
+  RK_ROS_CMD_VEL      = 3, /* geometry_msgs/Twist on cmd_vel: doubles X, Y (m/s, scaled x1000.0 in double), Z; 500 ms */
+  RK_ROS_COMMAND      = 4  /* interfaces/Command {command}: word A */
+};
+enum {
+  RK_RI_KIND = 0, RK_RI_A = 1, RK_RI_B = 2, RK_RI_C = 3,
+  RK_RI_X = 4, RK_RI_Y = 6, RK_RI_Z = 8, /* IEEE doubles, low word first */
+  RK_RI_FLOOR = 10, /* FDT::Info_FloorDetect (FD_task_main.hpp:24-33) as bytes from the low byte of word 10 up:
+                       rForward, lForward, rBack, lBack, right, left, forward, back; 0 none, 1 floor, 2 wall */
+  RK_RI_WORDS = 12
+};
+size_t rk_rmt_state_words(void);
+size_t rk_rmt_state_bytes(int64_t n);
+/* d_cmd_out: [K][n] rk_vdt_cmd_t (the message VDT::send_req_msg got this cycle, kind 0 if none);
+ * d_abort_out: [K][n] vdt_abort.val after the cycle (VehicleInfo.fault, :828) or NULL */
+int rk_rmt_guard(const rk_rmt_params_t *p, void *d_state, int64_t n, int32_t K, const void *d_in, rk_vdt_cmd_t *d_cmd_out,
+                 uint32_t *d_abort_out, void *stream);
+/* UTIL::mymath::atan2f on device arrays (the guard's sector test uses it; exposed for parity tests) */
+int rk_mymath_atan2f(const float *d_y, const float *d_x, float *d_out, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1159,3 +1159,168 @@ void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0
     }
   }
 }
+
+
+/* ------------------------------------------------------------------------------------ */
+/* RobotManager guard: the vehicle-management block of routine_ros()                      */
+/* (src/RobotManager/RM_task_main.cpp:484-767) + UTIL::mymath::atanf / atan2f                */
+/* (src/Utility/util_mymath.cpp:98-126; tables restated by tools/gen_atan_table.py)          */
+#include "atan_table.inc"
+static const float orc_atan_table[]   = {RK_ATAN_TABLE_VALUES};
+static const float orc_atan_delimit[] = {RK_ATAN_DELIMIT_VALUES};
+static const float orc_atan_width[]   = {RK_ATAN_WIDTH_VALUES};
+
+float orc_atanf(float x) { /* util_mymath.cpp:98-115 */
+  int   i, index_int;
+  float index, index_dec;
+  if(x < 0) return -orc_atanf(-x);
+  if(x == 0.0) return 0.0f;
+  for(i = 1; i <= 26; i++) {
+    if(x <= orc_atan_delimit[i]) {
+      index     = 24 * (i - 1) + ((x - orc_atan_delimit[i - 1]) / orc_atan_width[i - 1]);
+      index_int = (int)index;
+      index_dec = index - (float)index_int;
+      return orc_atan_table[index_int] + index_dec * ((orc_atan_table[index_int + 1] - orc_atan_table[index_int]));
+    }
+  }
+  return orc_atan_table[577 - 1]; /* TABLE_SIXE_ATAN is 577 although the table has 625 entries: :6,114 */
+}
+float orc_atan2f(float y, float x) { /* :117-126 */
+  if(x > 0.0) return orc_atanf(y / x);
+  if(y >= 0.0 && x < 0.0) return orc_atanf(y / x) + ORC_PI;
+  if(y < 0.0 && x < 0.0) return orc_atanf(y / x) - ORC_PI;
+  if(y > 0.0 && x == 0.0) return (float)(ORC_PI / 2.0);
+  if(y < 0.0 && x == 0.0) return (float)(-ORC_PI / 2.0);
+  return 0.0f;
+}
+
+enum { RM_REQ_MOVE_DIR = 1, RM_REQ_MOVE_CONT_DIR = 2 }; /* VDT::MSG_ID  VD_task_main.hpp:8-12 */
+enum { RM_FLOOR = 1, RM_WALL = 2 };                     /* FD_task_main.hpp:20-22 */
+typedef struct {
+  uint32_t id, cmd, time_ms, speed; /* MSG_ReqMoveDir */
+  float    vx, vy, vth;             /* MSG_ReqMoveContDir (time_ms shared) */
+} rm_msg_t;
+static double rm_double(const uint32_t *w) {
+  uint64_t u = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+  double   d;
+  memcpy(&d, &u, 8);
+  return d;
+}
+static void rm_stop(rm_msg_t *m) { /* the MOVE_STOP every veto writes  :584-589 */
+  m->id = RM_REQ_MOVE_DIR, m->cmd = RK_DIR_MOVE_STOP, m->time_ms = 1, m->speed = 0;
+}
+static rk_vdt_cmd_t rm_record(const rm_msg_t *m) {
+  rk_vdt_cmd_t c;
+  memset(&c, 0, sizeof(c));
+  if(m->id == RM_REQ_MOVE_DIR) {
+    memcpy(&c.vx, &m->cmd, 4), memcpy(&c.vy, &m->speed, 4);
+    c.kind = (int32_t)(RK_CMD_MSG_MOVE_DIR | (m->time_ms << 8));
+  } else {
+    c.vx = m->vx, c.vy = m->vy, c.vth = m->vth;
+    c.kind = (int32_t)(RK_CMD_MSG_MOVE_CONT_DIR | (m->time_ms << 8));
+  }
+  return c;
+}
+
+void orc_rmt_guard(const rk_rmt_params_t *p, uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, const uint32_t *in,
+                   rk_vdt_cmd_t *cmd_out, uint32_t *abort_out) {
+  int64_t i;
+  int     u, k;
+  for(i = i0; i < i1; i++) {
+    uint32_t cmd_status = *soa(state, n, i, RK_RS_CMD_STATUS), ignore = *soa(state, n, i, RK_RS_IGNORE_FLOOR);
+    uint32_t no_cmd = *soa(state, n, i, RK_RS_NO_CMD_CNT), abort_v = *soa(state, n, i, RK_RS_ABORT);
+    for(u = 0; u < K; u++) {
+      uint32_t w[RK_RI_WORDS];
+      rm_msg_t buf, msg;
+      int      updated = 0, exist = 0, sent = 0, nf = 0, nw = 0;
+      uint8_t  rF, lF, rB, lB, right, left, fwd, back, fl[8];
+      rk_vdt_cmd_t rec;
+      for(k = 0; k < RK_RI_WORDS; k++) w[k] = in[(((int64_t)u * 3 + k / 4) * n + i) * 4 + (k % 4)];
+      memset(&buf, 0, sizeof(buf));
+      /* rclc_executor_spin_some(): the subscription callbacks  :159-248 */
+      switch(w[RK_RI_KIND]) {
+      case RK_ROS_MECANUM_CMD: buf.id = RM_REQ_MOVE_DIR, buf.cmd = w[RK_RI_A], buf.time_ms = w[RK_RI_B], buf.speed = w[RK_RI_C], updated = 1; break;
+      case RK_ROS_MECANUM_CONT:
+        buf.id = RM_REQ_MOVE_CONT_DIR, buf.vx = (float)rm_double(w + RK_RI_X), buf.vy = (float)rm_double(w + RK_RI_Y);
+        buf.vth = (float)rm_double(w + RK_RI_Z), buf.time_ms = w[RK_RI_A], updated = 1;
+        break;
+      case RK_ROS_CMD_VEL:
+        buf.id = RM_REQ_MOVE_CONT_DIR, buf.vx = (float)(rm_double(w + RK_RI_X) * 1000.0), buf.vy = (float)(rm_double(w + RK_RI_Y) * 1000.0);
+        buf.vth = (float)rm_double(w + RK_RI_Z), buf.time_ms = 500, updated = 1;
+        break;
+      case RK_ROS_COMMAND: /* a Command always stops the vehicle, then switches the manager's mode  :162-201 */
+        rm_stop(&buf), updated = 1;
+        cmd_status = w[RK_RI_A];
+        switch(w[RK_RI_A]) {
+        case 0: case 1: case 2: case 4: break;         /* RELAX, MOVE_READY, MOVE_START, INIT (arm / gimbal requests: out of scope) */
+        case 10: ignore = !ignore; break;              /* SWITCH_FLOOR_SENSOR */
+        default: cmd_status = 0xFF; break;             /* QUIT_PG and the rest: UNKNOWN_CMD */
+        }
+        break;
+      default: break;
+      }
+      /* :484-505 */
+      if(updated) exist = 1, abort_v = 0, msg = buf;
+      else memset(&msg, 0, sizeof(msg)), msg.id = RM_REQ_MOVE_DIR;
+      for(k = 0; k < 8; k++) fl[k] = (uint8_t)(w[RK_RI_FLOOR + k / 4] >> (8 * (k % 4)));
+      for(k = 0; k < 8; k++) { /* :507-530 */
+        if(fl[k] == 0) nf++;
+        else if(fl[k] == RM_WALL) nw++;
+      }
+      if(nf >= 5 || nw >= 5 || ignore)
+        for(k = 0; k < 8; k++) fl[k] = RM_FLOOR; /* :532-542 */
+      rF = fl[0], lF = fl[1], rB = fl[2], lB = fl[3], right = fl[4], left = fl[5], fwd = fl[6], back = fl[7];
+      if(cmd_status == 2) { /* MOVE_START: leave a wall (an opponent)  :546-577 */
+        uint32_t dir = 0;
+        if(fwd == RM_WALL) dir = RK_DIR_GO_BACK, abort_v |= 1u << 0;
+        else if(back == RM_WALL) dir = RK_DIR_GO_FORWARD, abort_v |= 1u << 1;
+        else if(left == RM_WALL) dir = RK_DIR_GO_RIGHT, abort_v |= 1u << 2;
+        else if(right == RM_WALL) dir = RK_DIR_GO_LEFT, abort_v |= 1u << 3;
+        if(dir) msg.id = RM_REQ_MOVE_DIR, msg.cmd = dir, msg.time_ms = p->wall_leave_time_ms, msg.speed = p->wall_leave_speed_mmps, exist = 1;
+      }
+      if(msg.id == RM_REQ_MOVE_DIR) { /* :581-673 */
+        uint8_t  need = RM_FLOOR;
+        uint32_t bits = 0;
+        switch(msg.cmd) {
+        case RK_DIR_GO_FORWARD: need = fwd, bits = 1u << 8; break;
+        case RK_DIR_GO_BACK: need = back, bits = 1u << 9; break;
+        case RK_DIR_GO_RIGHT: need = right, bits = 1u << 11; break;
+        case RK_DIR_GO_LEFT: need = left, bits = 1u << 10; break;
+        case RK_DIR_GO_RIGHT_FORWARD: need = rF, bits = (1u << 8) | (1u << 11); break;
+        case RK_DIR_GO_LEFT_FORWARD: need = lF, bits = (1u << 8) | (1u << 10); break;
+        case RK_DIR_GO_RIGHT_BACK: need = rB, bits = (1u << 9) | (1u << 11); break;
+        case RK_DIR_GO_LEFT_BACK: need = lB, bits = (1u << 9) | (1u << 10); break;
+        default: break;
+        }
+        if(need != RM_FLOOR) rm_stop(&msg), exist = 1, abort_v |= bits;
+      } else if(msg.id == RM_REQ_MOVE_CONT_DIR) { /* :674-749 */
+        const float ax = msg.vx < 0 ? -msg.vx : msg.vx, ay = msg.vy < 0 ? -msg.vy : msg.vy;
+        if(!(ax < 0.01f && ay < 0.01f)) {
+          const float vph = orc_atan2f(msg.vy, msg.vx);
+          int         veto = 0;
+          if(fwd != RM_FLOOR && (-3.1415f * 0.33f < vph && vph <= +3.1415f * 0.33f)) veto = 1;
+          if(back != RM_FLOOR && (+3.1415f * 0.66f < vph || vph <= -3.1415f * 0.66f)) veto = 1;
+          if(left != RM_FLOOR && (+3.1415f * 0.16f < vph && vph <= +3.1415f * 0.84f)) veto = 1;
+          if(right != RM_FLOOR && (-3.1415f * 0.84f < vph && vph <= -3.1415f * 0.16f)) veto = 1;
+          if(rB != RM_FLOOR && (+3.1415f * 0.92f < vph || vph <= -3.1415f * 0.42f)) veto = 1;
+          if(rF != RM_FLOOR && (-3.1415f * 0.58f < vph && vph <= +3.1415f * 0.08f)) veto = 1;
+          if(lF != RM_FLOOR && (-3.1415f * 0.08f < vph && vph <= +3.1415f * 0.58f)) veto = 1;
+          if(lB != RM_FLOOR && (+3.1415f * 0.42f < vph || vph <= -3.1415f * 0.92f)) veto = 1;
+          if(veto) msg.vx = 0, msg.vy = 0, abort_v |= 1u << 16;
+        }
+      }
+      memset(&rec, 0, sizeof(rec));
+      if(exist) no_cmd = 0, rec = rm_record(&msg), sent = 1; /* :752-757 */
+      else no_cmd++;
+      if(no_cmd > p->no_cmd_stop_thre) { /* :760-767 */
+        rm_stop(&msg), rec = rm_record(&msg), sent = 1;
+        no_cmd = 0;
+      }
+      (void)sent;
+      cmd_out[(int64_t)u * n + i] = rec;
+      if(abort_out) abort_out[(int64_t)u * n + i] = abort_v;
+    }
+    *soa(state, n, i, RK_RS_CMD_STATUS) = cmd_status, *soa(state, n, i, RK_RS_IGNORE_FLOOR) = ignore;
+    *soa(state, n, i, RK_RS_NO_CMD_CNT) = no_cmd, *soa(state, n, i, RK_RS_ABORT) = abort_v;
+  }
+}

@@ -44,6 +44,12 @@ void orc_adp_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *
 void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0, int64_t i1, int K, int ncells,
                         const uint32_t *cells, const uint16_t *nbytes, uint32_t *out, float *yaw_rad, int do_init);
 
+/* rk_rmt_guard() on HOST arrays; UTIL::mymath::atanf / atan2f */
+void orc_rmt_guard(const rk_rmt_params_t *p, uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, const uint32_t *in,
+                   rk_vdt_cmd_t *cmd_out, uint32_t *abort_out);
+float orc_atanf(float x);
+float orc_atan2f(float y, float x);
+
 float orc_sin(float x);
 float orc_cos(float x);
 float orc_normalize_rad_0to2pi(float x);

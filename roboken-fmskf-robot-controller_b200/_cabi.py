@@ -53,6 +53,15 @@ class VdtParams(C.Structure):
     ]
 
 
+class RmtParams(C.Structure):
+    """rk_rmt_params_t"""
+
+    _fields_ = [("no_cmd_stop_thre", C.c_uint32), ("wall_leave_time_ms", C.c_uint32), ("wall_leave_speed_mmps", C.c_uint32)]
+
+
+RK_ROS_NONE, RK_ROS_MECANUM_CMD, RK_ROS_MECANUM_CONT, RK_ROS_CMD_VEL, RK_ROS_COMMAND = range(5)
+
+
 class VdtCmd(C.Structure):
     """rk_vdt_cmd_t"""
 
@@ -157,6 +166,13 @@ def _proto(lib):
     lib.rk_imt_feed_bytes.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int, vp]
     lib.rk_tick_rollout.argtypes = [C.POINTER(VdtParams), C.POINTER(AdtParams), vp, vp, vp, vp, C.c_int64,
                                     C.POINTER(TickRollout), vp]
+    lib.rk_rmt_default_params.argtypes = [C.POINTER(RmtParams)]
+    lib.rk_rmt_default_params.restype = None
+    lib.rk_rmt_state_words.restype = C.c_size_t
+    lib.rk_rmt_state_bytes.argtypes = [C.c_int64]
+    lib.rk_rmt_state_bytes.restype = C.c_size_t
+    lib.rk_rmt_guard.argtypes = [C.POINTER(RmtParams), vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
+    lib.rk_mymath_atan2f.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.rk_imt_create.argtypes = [C.POINTER(vp)]
     lib.rk_imt_destroy.argtypes = [vp]
     lib.rk_imt_destroy.restype = None

@@ -37,6 +37,13 @@ IMT_REGS = 16
 # WIT serial parser block (RK_IP_*): 11-byte window + fill count, flags, the 16 tracked sReg words
 IP_WINDOW, IP_FLAGS, IP_SREG, IP_WORDS = 0, 3, 4, 12
 
+# ---- RobotManager guard (RK_RS_* / RK_RI_*) -------------------------------------------------
+RS_CMD_STATUS, RS_IGNORE_FLOOR, RS_NO_CMD_CNT, RS_ABORT, RS_WORDS = 0, 1, 2, 3, 4
+RI_KIND, RI_A, RI_B, RI_C, RI_X, RI_Y, RI_Z, RI_FLOOR, RI_WORDS = 0, 1, 2, 3, 4, 6, 8, 10, 12
+RM_ABORT_WALL_XP, RM_ABORT_WALL_XM, RM_ABORT_WALL_YP, RM_ABORT_WALL_YM = 1 << 0, 1 << 1, 1 << 2, 1 << 3
+RM_ABORT_FLOOR_XP, RM_ABORT_FLOOR_XM, RM_ABORT_FLOOR_YP, RM_ABORT_FLOOR_YM = 1 << 8, 1 << 9, 1 << 10, 1 << 11
+RM_ABORT_CONT_TRANS = 1 << 16
+
 # ---- arm (RK_AS_* / RK_ACMD_*) ------------------------------------------------------------
 AJ_Y0, AJ_P1, AJ_DFL, AJ_DFR, AJ_P2, AJ_R0, AJ_P3, AJ_NUM = range(8)
 AS_FSM, AS_SEQ_IDX, AS_CMD_IDX, AS_MOVE_CNT, AS_CYCLE, AS_TOTAL_MS, AS_NOW_DT = range(7)

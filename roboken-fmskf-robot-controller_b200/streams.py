@@ -287,3 +287,60 @@ def imu_wire_fuzz(n, K, ncells=4, seed=0x5EED, first=0, full_slots=False):
             o += int(lens[u])
         nbytes[:, i] = lens
     return _pack_wire(np.ascontiguousarray(out.transpose(1, 2, 0))), nbytes
+
+
+# ---- RobotManager cycles (src/RobotManager/RM_task_main.cpp:484-767) ----------------------------------
+def rm_inputs(n, K, seed=0x5EED, first=0, idle_every=4):
+    """Manager cycles: uint32 [K, 3, n, 4] rk_rmt_guard input records (RK_RI_* words in three 128-bit cells).
+
+    Per cycle one of: nothing (45 %; robots with index % idle_every == 0 stay silent for 3/4 of their cycles
+    so the 200-cycle watchdog fires), MecanumCommand (direction 0..12 incl. undefined codes, time 0..1500,
+    speed 0..700), MecanumContOrder (mm/s doubles: U[-600, 600], 1 in 8 below the 0.01 dead band on both axes, 1 in
+    8 exactly on a heading k * pi/50 so sector edges are probed, doubles that do not fit a float exactly), cmd_vel
+    Twist (m/s), Command (RELAX, MOVE_READY, MOVE_START x3, QUIT_PG, INIT, HW_DEBUG, SWITCH_FLOOR_SENSOR, 77).
+    Floor sensors: 70 % floor, 15 % nothing, 15 % wall per sensor; 1 cycle in 16 is mostly-nothing / mostly-wall."""
+    inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[None, :]
+    u = np.arange(K, dtype=np.uint64)[:, None]
+    sel = (_hash(seed, 60, inst, u) % np.uint64(100)).astype(np.int64)
+    silent = ((inst % np.uint64(idle_every)) == 0) & ((_hash(seed, 61, inst, u // np.uint64(300)) % np.uint64(4)) != 0)
+    kind = np.where(sel < 45, 0, np.where(sel < 65, 1, np.where(sel < 80, 2, np.where(sel < 88, 3, 4))))
+    kind = np.where(silent, 0, kind).astype(np.uint32)
+    w = np.zeros((K, n, 12), dtype=np.uint32)
+    w[..., 0] = kind
+    d = (_hash(seed, 62, inst, u) % np.uint64(13)).astype(np.uint32)
+    tm = (_hash(seed, 63, inst, u) % np.uint64(1501)).astype(np.uint32)
+    sp = (_hash(seed, 64, inst, u) % np.uint64(701)).astype(np.uint32)
+    cmds = np.array([0, 1, 2, 2, 2, 3, 4, 5, 10, 77], dtype=np.uint32)
+    command = cmds[(_hash(seed, 65, inst, u) % np.uint64(len(cmds))).astype(np.int64)]
+    w[..., 1] = np.where(kind == 1, d, np.where(kind == 2, tm, np.where(kind == 4, command, 0)))
+    w[..., 2] = np.where(kind == 1, tm, 0)
+    w[..., 3] = np.where(kind == 1, sp, 0)
+    def u53(stream):  # full-mantissa uniform doubles in [0, 1)
+        return (_hash(seed, stream, inst, u) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    vx, vy, vz = u53(66) * 1200.0 - 600.0, u53(67) * 1200.0 - 600.0, u53(68) * 50.0 - 25.0
+    mode = (_hash(seed, 69, inst, u) % np.uint64(8)).astype(np.int64)
+    tiny = mode == 0
+    vx, vy = np.where(tiny, vx * 1e-5, vx), np.where(tiny, vy * 1e-5, vy)
+    edge = mode == 1
+    k50 = (_hash(seed, 70, inst, u) % np.uint64(101)).astype(np.float64) - 50.0
+    r = 50.0 + u53(71) * 400.0
+    vx, vy = np.where(edge, r * np.cos(k50 * np.pi / 50.0), vx), np.where(edge, r * np.sin(k50 * np.pi / 50.0), vy)
+    axis = mode == 2  # on an axis: one component exactly zero
+    vx = np.where(axis & (sel % 2 == 0), 0.0, vx)
+    vy = np.where(axis & (sel % 2 == 1), 0.0, vy)
+    scale = np.where(kind == 3, 1e-3, 1.0)
+    for k, v in ((4, vx * scale), (6, vy * scale), (8, vz)):
+        bits = np.ascontiguousarray(v).view(np.uint64)
+        w[..., k] = np.where(kind >= 2, bits & np.uint64(0xFFFFFFFF), 0).astype(np.uint32)
+        w[..., k + 1] = np.where((kind == 2) | (kind == 3), bits >> np.uint64(32), 0).astype(np.uint32)
+    w[..., 4:10] = np.where(((kind == 2) | (kind == 3))[..., None], w[..., 4:10], 0)
+    s = np.arange(8, dtype=np.uint64)[None, None, :]
+    fsel = (_hash(seed, 72, inst[..., None] * np.uint64(8) + s, u[..., None]) % np.uint64(100)).astype(np.int64)
+    fl = np.where(fsel < 70, 1, np.where(fsel < 85, 0, 2)).astype(np.uint32)
+    bulk = (_hash(seed, 73, inst, u) % np.uint64(16)).astype(np.int64)
+    bsel = (_hash(seed, 74, inst[..., None] * np.uint64(8) + s, u[..., None]) % np.uint64(8)).astype(np.int64)
+    fl = np.where((bulk == 0)[..., None] & (bsel < 6), 0, fl)
+    fl = np.where((bulk == 1)[..., None] & (bsel < 6), 2, fl).astype(np.uint32)
+    w[..., 10] = fl[..., 0] | (fl[..., 1] << 8) | (fl[..., 2] << 16) | (fl[..., 3] << 24)
+    w[..., 11] = fl[..., 4] | (fl[..., 5] << 8) | (fl[..., 6] << 16) | (fl[..., 7] << 24)
+    return np.ascontiguousarray(w.reshape(K, n, 3, 4).transpose(0, 2, 1, 3))

@@ -63,7 +63,7 @@ def arm_golden():
 
 
 def main():
-    which = set(sys.argv[1:]) or {"vdt", "imu", "arm", "wire"}
+    which = set(sys.argv[1:]) or {"vdt", "imu", "arm", "wire", "rmt"}
     if "arm" in which:
         arm_golden()
     if "vdt" in which:
@@ -72,6 +72,8 @@ def main():
         imu_golden()
     if "wire" in which:
         imu_wire_golden()
+    if "rmt" in which:
+        rmt_golden()
 
 
 def vdt_golden():
@@ -119,6 +121,22 @@ def imu_wire_golden():
     o, sreg = ol.imu_bytes_ref(st, n, cells, nbytes, want_out=True)
     path = os.path.join(HERE, "imu_wire_golden.npz")
     np.savez_compressed(path, cells=cells, nbytes=nbytes, out=o, state=st, sreg=sreg)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def rmt_golden():
+    # RobotManager guard: the unmodified RM_task_main.cpp routine_ros() + util_mymath.cpp arctangent
+    n, K = 40, 460
+    inp = streams.rm_inputs(n, K, seed=0x5EED)
+    st = np.zeros(layout.RS_WORDS * n, dtype=np.uint32)
+    cmd, ab = ol.rm_guard("ref", st, n, inp)
+    rng = np.random.default_rng(7)
+    y = np.concatenate([rng.standard_normal(300) * 300, [0, 0, 1, -1, 0.0, 5e5, -3, np.inf]]).astype(np.float32)
+    x = np.concatenate([rng.standard_normal(300) * 300, [0, 1, 0, 0, -2.0, 1e-3, 1e7, 1.0]]).astype(np.float32)
+    r = ol.ref("libref_rm.so")
+    out = np.array([r.ref_rm_atan2f(float(a), float(b)) for a, b in zip(y, x)], dtype=np.float32)
+    path = os.path.join(HERE, "rmt_golden.npz")
+    np.savez_compressed(path, cmd=cmd, abort=ab, state=st, atan_y=y, atan_x=x, atan_out=out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

@@ -42,6 +42,12 @@ def port():
         lib.orc_imt_update.restype = None
         lib.orc_imt_feed_bytes.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int]
         lib.orc_imt_feed_bytes.restype = None
+        lib.orc_rmt_guard.argtypes = [C.POINTER(_cabi.RmtParams), vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp]
+        lib.orc_rmt_guard.restype = None
+        lib.orc_atanf.argtypes = [C.c_float]
+        lib.orc_atanf.restype = C.c_float
+        lib.orc_atan2f.argtypes = [C.c_float, C.c_float]
+        lib.orc_atan2f.restype = C.c_float
         lib.orc_adt_batch.argtypes = [C.c_int, C.POINTER(_cabi.AdtParams), vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                       vp, vp, vp, vp, vp]
         lib.orc_adt_batch.restype = None
@@ -89,6 +95,14 @@ def ref(name="libref_vdt.so"):
         if name.startswith("libref_vdt_task"):
             lib.ref_vdt_task_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_cabi.VdtRollout), vp]
             lib.ref_vdt_task_rollout.restype = None
+        if name.startswith("libref_rm"):
+            lib.ref_rmt_guard.argtypes = [C.POINTER(_cabi.RmtParams), vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp]
+            lib.ref_rmt_guard.restype = None
+            lib.ref_rm_atanf.argtypes = [C.c_float]
+            lib.ref_rm_atanf.restype = C.c_float
+            lib.ref_rm_atan2f.argtypes = [C.c_float, C.c_float]
+            lib.ref_rm_atan2f.restype = C.c_float
+            lib.ref_rm_atan_tables.argtypes = [vp, vp, vp]
         if name.startswith("libref_imu"):
             lib.ref_imt_create.restype = vp
             lib.ref_imt_destroy.argtypes = [vp]
@@ -200,6 +214,23 @@ def imu_bytes_ref(state_soa, n, cells, nbytes=None, want_out=False):
     sreg = np.zeros((n, 16), dtype=np.int16)
     ref("libref_imu.so").ref_imt_bytes_rollout(_ptr(state_soa), n, 0, n, K, ncells, _ptr(cells), _ptr(nbytes), _ptr(out), _ptr(sreg))
     return out, sreg
+
+
+def rm_default_params():
+    return _cabi.RmtParams(200, 200, 100)
+
+
+def rm_guard(kind, state_soa, n, inp, params=None, want_abort=True):
+    """rk_rmt_guard on host arrays through the port ("port") or the compiled RobotManager task ("ref").
+    inp: uint32 [K, 3, n, 4].  Returns (cmd uint32 [K, n, 4], abort uint32 [K, n])."""
+    K = inp.shape[0]
+    assert inp.dtype == np.uint32 and inp.shape[1:] == (3, n, 4) and inp.flags.c_contiguous
+    p = params or rm_default_params()
+    cmd = np.zeros((K, n, 4), dtype=np.uint32)
+    ab = np.zeros((K, n), dtype=np.uint32) if want_abort else None
+    fn = port().orc_rmt_guard if kind == "port" else ref("libref_rm.so").ref_rmt_guard
+    fn(C.byref(p), _ptr(state_soa), n, 0, n, K, _ptr(inp), _ptr(cmd), _ptr(ab))
+    return cmd, ab
 
 
 # ---- arm ---------------------------------------------------------------------------------

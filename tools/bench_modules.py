@@ -2,7 +2,7 @@
 """Kernel-level measurements of the two slow-rate modules (BASELINE configs[2] and [3]) -- one JSON
 line each, CUDA-event timed with inputs resident in HBM, roofline against MEASURED_PEAKS.json.
 
-    python tools/bench_modules.py [--n 1048576] [--imu-updates 64] [--arm-ticks 1000] [--reps 10] [--only imu|wire|arm]
+    python tools/bench_modules.py [--n 1048576] [--imu-updates 64] [--arm-ticks 1000] [--reps 10] [--only imu|wire|guard|arm]
 """
 import argparse
 import json
@@ -84,6 +84,28 @@ def bench_wire(a, dev):
                                        "algorithmic_bytes_per_update": per, "algorithmic_bytes_per_launch": nbytes}}), flush=True)
 
 
+def bench_guard(a, dev):
+    """rk_rmt_guard: 48 B command + floor record in, 16 B vehicle message + 4 B abort word out per manager cycle."""
+    from roboken_fmskf_robot_controller_b200.rmt import ManagerBatch
+
+    n, K = a.n, a.imu_updates
+    uniq = min(n, 1 << 14)
+    inp = streams.rm_inputs(uniq, K, seed=3)
+    inp_d = torch.from_numpy(np.tile(inp, (1, 1, n // uniq, 1)).view(np.int32)).to(dev)
+    mb = ManagerBatch(n, dev)
+    cmd = torch.empty((K, n, 4), dtype=torch.int32, device=dev)
+    ab = torch.empty((K, n), dtype=torch.int32, device=dev)
+    peak, src = hbm_peak()
+    ms = timed(lambda: mb.guard(inp_d, cmd, ab), a.reps)
+    per = 48 + 16 + 4
+    nbytes = n * (K * per + 2 * 16)
+    print(json.dumps({"kernel": "rk::rmt_guard_kernel", "workload": f"8f-2: {n} managers x {K} cycles (command + 8 floor sensors -> guarded vehicle message)",
+                      "cycles_per_s": n * K / (ms * 1e-3), "ms_per_launch": ms,
+                      "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "peak_source": src,
+                                   "algorithmic_bytes_per_cycle": per, "algorithmic_bytes_per_launch": nbytes}}), flush=True)
+
+
 def bench_arm(a, dev):
     n, K = a.n, a.arm_ticks
     seq = torch.from_numpy(layout.aos_to_soa(streams.arm_sequences(n, seed=0xC4, seq_id=9, max_len=32)).view(np.int32)).to(dev)
@@ -116,6 +138,8 @@ def main():
         bench_imu(a, dev)
     if a.only in ("", "wire"):
         bench_wire(a, dev)
+    if a.only in ("", "guard"):
+        bench_guard(a, dev)
     if a.only in ("", "arm"):
         bench_arm(a, dev)
 
