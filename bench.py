@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--ticks", type=int, default=1000, help="fused control ticks per launch")
     ap.add_argument("--seg-len", type=int, default=125)
     ap.add_argument("--yaw-period", type=int, default=10)
+    ap.add_argument("--yaw-format", choices=("reg", "rad"), default="reg",
+                    help="vehicle workload: yaw input as the WT901C Yaw register (int16, what the sensor sends; default) "
+                         "or as float32 radians")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall budget of the cpu_baseline leg")
     ap.add_argument("--occupancy", type=int, default=0, help="RK_OPT_FAST_OCCUPANCY override (tuning)")
     ap.add_argument("--packed", type=int, default=-1, help="RK_OPT_FAST_PACKED override (tuning; -1 = library default)")
@@ -75,7 +78,8 @@ def workload_name(a):
                 f"chunks of {a.chunk} robots")
     return (f"configs[1]: {a.instances} mecanum vehicles/GPU x {a.ticks} fused 1 kHz ticks "
             f"(rx_callback + FK/odometry + 3x const-jerk target + IK + 4x FF_PI_D + current saturation), "
-            f"closed loop through the integer motor plant, command every {a.seg_len} ticks, yaw every {a.yaw_period}")
+            f"closed loop through the integer motor plant, command every {a.seg_len} ticks, yaw every {a.yaw_period}"
+            + (" as the WT901C Yaw register (int16)" if a.yaw_format == "reg" else " as float32 radians"))
 
 
 # ------------------------------------------------------------------------------------------
@@ -104,6 +108,10 @@ class CpuArm:
         a = self.a
         if n not in self._inp:
             inp = self.wl.plant_inputs(n, a.ticks, seed=0x5EED, seg_len=a.seg_len, yaw_period=a.yaw_period)
+            if getattr(a, "yaw_format", "rad") == "reg" and a.workload != "full":
+                from roboken_fmskf_robot_controller_b200 import streams
+
+                inp["yaw"] = streams.vehicle_yaw_reg(n, inp["yaw"].shape[0], 0x5EED, 0)
             ro = self.ol.HostRollout(n, a.ticks, self._cabi.RK_SENSOR_PLANT, inp["cmd"], inp["seg_len"], inp["yaw"],
                                      inp["yaw_period"])
             self._inp[n] = (inp, ro)
@@ -354,7 +362,10 @@ def run_ours(a):
 
     # ---- synthetic inputs, generated on the host (pinned) ---------------------------------
     cmd_h = torch.from_numpy(streams.vehicle_commands(n, n_seg, 0x5EED, first).view(np.int32).reshape(n_seg, n, 4)).pin_memory()
-    yaw_h = torch.from_numpy(streams.vehicle_yaw(n, n_yaw, 0x5EED, first)).pin_memory()
+    if a.yaw_format == "reg":
+        yaw_h = torch.from_numpy(streams.vehicle_yaw_reg(n, n_yaw, 0x5EED, first)).pin_memory()
+    else:
+        yaw_h = torch.from_numpy(streams.vehicle_yaw(n, n_yaw, 0x5EED, first)).pin_memory()
     goal_h = torch.zeros((n, 2), dtype=torch.float32).pin_memory()
     cmd_d, yaw_d, goal_d = cmd_h.to(dev), yaw_h.to(dev), goal_h.to(dev)
     cost_d = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -408,7 +419,7 @@ def run_ours(a):
 
     launch_s = ms_local * 1e-3 / K
     achieved_tflops = FLOP_PER_TICK * n * T / launch_s / 1e12
-    alg_bytes = n * (2 * STATE_BYTES + n_seg * 16 + n_yaw * 4 + 8 + 4)  # state ld+st, cmd, yaw, goal, cost
+    alg_bytes = n * (2 * STATE_BYTES + n_seg * 16 + n_yaw * yaw_h.element_size() + 8 + 4)  # state ld+st, cmd, yaw, goal, cost
     roofline = {
         "bound": "fp32",
         "achieved": achieved_tflops, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / ffma_tflops,
@@ -446,7 +457,7 @@ def run_ours(a):
                                                yaw_period=a.yaw_period, goal=goal_d, cost=co),
                              up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event()))
             keep += [c, y, co]
-        h2d = cmd_h.numel() * 4 + yaw_h.numel() * 4
+        h2d = cmd_h.numel() * 4 + yaw_h.numel() * yaw_h.element_size()
         d2h = n * 4
 
         def e2e_pass(s):
@@ -523,7 +534,7 @@ def run_ours(a):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "instances_per_gpu": n, "ticks_per_launch": T,
                        "l2": f"inputs larger than L2: {n * STATE_BYTES >> 20} MiB state + "
-                             f"{(cmd_h.numel() + yaw_h.numel()) * 4 >> 20} MiB tables per pass vs 126 MB L2",
+                             f"{(cmd_h.numel() * 4 + yaw_h.numel() * yaw_h.element_size()) >> 20} MiB tables per pass vs 126 MB L2",
                        "parity_spot_check": spot},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -197,6 +197,11 @@ typedef struct rk_vdt_rollout {
    * RK_CMD_MSG_* records are decoded and the move-time countdown (U32_MOVE_TIME_CNT_ORDER, :298-316) issues
    * the automatic stop.  0: no task loop (RK_CMD_MOVE / RK_CMD_STOP records only). */
   int32_t task_period;
+  /* the same yaw stream as the sensor reports it (used when d_yaw is NULL): the WT901C's Yaw register, int16,
+   * 180/32768 degrees per count, same indexing as d_yaw.  The engine forms the float the ISR would see:
+   * angle[2] = reg / 32768.0f * 180.0f (IMU_IF_WT901C::updateData, imu_if_wt901c.cpp:100) -> getYawDate() ->
+   * mymath::deg2rad (VD_task_main.cpp:368).  Half the bytes of d_yaw -- the rollout's largest input. */
+  const int16_t *d_yaw_reg;
 } rk_vdt_rollout_t;
 
 /* VEHICLE_CTRL::update() x steps   (VD_vehicle_controller.cpp:6-99), fused with the callers

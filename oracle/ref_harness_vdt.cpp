@@ -252,8 +252,12 @@ void rollout_one(VehicleSet *s, int64_t n, int64_t i, const rk_vdt_rollout_t *a)
   for(int t = 0; t < a->steps; t++) {
     if(a->d_cmd && a->seg_len > 0 && (t % a->seg_len) == 0 && (t / a->seg_len) < a->n_seg)
       apply_cmd(s, a->d_cmd[(int64_t)(t / a->seg_len) * n + i]);
-    if(a->d_yaw && a->yaw_period > 0 && (t % a->yaw_period) == 0 && (t / a->yaw_period) < a->n_yaw)
-      s->vhcl.set_now_yaw_world(a->d_yaw[(int64_t)(t / a->yaw_period) * n + i]);
+    if((a->d_yaw || a->d_yaw_reg) && a->yaw_period > 0 && (t % a->yaw_period) == 0 && (t / a->yaw_period) < a->n_yaw) {
+      const int64_t yi = (int64_t)(t / a->yaw_period) * n + i;
+      /* from the Yaw register: what IMU_IF_WT901C::updateData (imu_if_wt901c.cpp:100) stores, then the ISR's deg2rad */
+      s->vhcl.set_now_yaw_world(a->d_yaw ? a->d_yaw[yi]
+                                         : UTIL::mymath::deg2rad(static_cast<float>(a->d_yaw_reg[yi]) / 32768.0f * 180.0f));
+    }
     int16_t us = (int16_t)(((t + 1) * 1000) & 0x7FFF);
     if(a->sensor_mode == RK_SENSOR_PLANT) {
       for(int k = 0; k < 4; k++) {

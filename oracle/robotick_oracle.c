@@ -444,8 +444,11 @@ static void rollout_one(veh_t *v, const rk_vdt_params_t *p, int64_t n, int64_t i
       if(c) vdt_task_message(v, p, c);
       vdt_task_countdown(v, p);
     }
-    if(a->d_yaw && a->yaw_period > 0 && (t % a->yaw_period) == 0 && (t / a->yaw_period) < a->n_yaw)
-      v->pos[2] = a->d_yaw[(int64_t)(t / a->yaw_period) * n + i]; /* set_now_yaw_world :57 */
+    if((a->d_yaw || a->d_yaw_reg) && a->yaw_period > 0 && (t % a->yaw_period) == 0 && (t / a->yaw_period) < a->n_yaw) {
+      const int64_t yi = (int64_t)(t / a->yaw_period) * n + i;
+      /* set_now_yaw_world :57; from the Yaw register: imu_if_wt901c.cpp:100, getYawDate :160, deg2rad VD_task_main.cpp:368 */
+      v->pos[2] = a->d_yaw ? a->d_yaw[yi] : ((float)a->d_yaw_reg[yi] / 32768.0f * 180.0f) * (ORC_PI / 180.0f);
+    }
     us = (int16_t)(((t + 1) * 1000) & 0x7FFF);
     if(a->sensor_mode == RK_SENSOR_PLANT) {
       for(k = 0; k < 4; k++) {

@@ -83,7 +83,9 @@ class VdtRollout(C.Structure):
         ("d_frames", C.c_void_p),
         ("d_trace", C.c_void_p),
         ("d_goal", C.c_void_p),
-        ("d_cost", C.c_void_p),        ("task_period", C.c_int32),
+        ("d_cost", C.c_void_p),
+        ("task_period", C.c_int32),
+        ("d_yaw_reg", C.c_void_p),
     ]
 
 

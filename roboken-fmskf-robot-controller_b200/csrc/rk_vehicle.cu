@@ -16,6 +16,15 @@ namespace rk {
 // -----------------------------------------------------------------------------------------
 constexpr int kRolloutThreads = 128;
 
+// the yaw the ISR hands to set_now_yaw_world(): the float stream, or formed from the WT901C Yaw register exactly as
+// IMU_IF_WT901C::updateData (imu_if_wt901c.cpp:100: reg / 32768.0f * 180.0f; the division by 2^15 is exact) ->
+// getYawDate() -> mymath::deg2rad (VD_task_main.cpp:368) would
+RK_DEV float load_yaw(const rk_vdt_rollout_t &a, int64_t idx) {
+  if(a.d_yaw) return __ldcs(a.d_yaw + idx);
+  const float reg = (float)(int)__ldcs(a.d_yaw_reg + idx);
+  return fmul(fmul(fmul(reg, 1.0f / 32768.0f), 180.0f), RK_DEG2RAD);
+}
+
 template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(kRolloutThreads)
 vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
@@ -30,7 +39,7 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
   float         cth, sth;
   yaw_trig(s_tab, v.pos[2], cth, sth);
 
-  const bool has_yaw  = a.d_yaw != nullptr && a.yaw_period > 0 && a.n_yaw > 0;
+  const bool has_yaw  = (a.d_yaw != nullptr || a.d_yaw_reg != nullptr) && a.yaw_period > 0 && a.n_yaw > 0;
   int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
   Sched      sc;
   sched_init(sc, a);
@@ -38,7 +47,7 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
   for(int t = 0; t < a.steps; t++) {
     sched_events(v, p, a, n, i, t, sc);
     if(t == next_yaw) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
-      v.pos[2] = __ldcs(a.d_yaw + (int64_t)yk * n + i);
+      v.pos[2] = load_yaw(a, (int64_t)yk * n + i);
       yaw_trig(s_tab, v.pos[2], cth, sth);
       yk++;
       next_yaw = (yk < a.n_yaw) ? next_yaw + a.yaw_period : INT_MAX;
@@ -129,21 +138,21 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
   float cth, sth;
   yaw_trig(s_tab, v.pos[2], cth, sth);
 
-  const bool has_yaw  = a.d_yaw != nullptr && a.yaw_period > 0 && a.n_yaw > 0;
+  const bool has_yaw  = (a.d_yaw != nullptr || a.d_yaw_reg != nullptr) && a.yaw_period > 0 && a.n_yaw > 0;
   int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
   const int  K        = a.steps;
   Sched      sch;
   sched_init(sch, a);
   // The yaw sample for the next boundary is fetched one period ahead, so its HBM latency
   // hides behind yaw_period ticks of arithmetic instead of stalling every warp at once.
-  float yaw_pf = has_yaw ? __ldcs(a.d_yaw + i) : 0.0f;
+  float yaw_pf = has_yaw ? load_yaw(a, i) : 0.0f;
   auto  take_yaw = [&](float &pth) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
     pth = yaw_pf;
     yaw_trig(s_tab, pth, cth, sth);
     yk++;
     if(yk < a.n_yaw) {
       next_yaw += a.yaw_period;
-      yaw_pf = __ldcs(a.d_yaw + (int64_t)yk * n + i);
+      yaw_pf = load_yaw(a, (int64_t)yk * n + i);
     } else {
       next_yaw = INT_MAX;
     }

@@ -81,6 +81,25 @@ def vehicle_yaw(n, n_yaw, seed=0x5EED, first=0, degrees=False):
     return (deg.astype(np.float32) * DEG2RAD).astype(np.float32)
 
 
+def vehicle_yaw_reg(n, n_yaw, seed=0x5EED, first=0):
+    """The same kind of yaw stream as the sensor delivers it: the WT901C Yaw register, int16 [n_yaw, n], 180/32768
+    degrees per count.  Per instance a constant turn rate of 1..5 steps of 182 counts (about one degree) per IMU sample
+    from a random phase, wrapping at +-180 degrees like the real heading (int16 overflow)."""
+    inst = (np.arange(n, dtype=np.uint64) + np.uint64(first))[None, :]
+    k = np.arange(n_yaw, dtype=np.int64)[:, None]
+    phase = (_hash(seed, 5, inst, 0) % np.uint64(65536)).astype(np.int64)
+    rate = ((_hash(seed, 6, inst, 0) % np.uint64(5)).astype(np.int64) + 1) * 182
+    sign = np.where((_hash(seed, 9, inst, 0) % np.uint64(2)) == 0, 1, -1)
+    return ((phase + sign * rate * k) & 0xFFFF).astype(np.uint16).view(np.int16)
+
+
+def yaw_reg_to_rad(reg):
+    """What the vehicle ISR sees for a Yaw register value: reg / 32768.0f * 180.0f (imu_if_wt901c.cpp:100), then
+    mymath::deg2rad (VD_task_main.cpp:368); float32, one rounding per operation."""
+    deg = (reg.astype(np.float32) / np.float32(32768.0)) * np.float32(180.0)
+    return (deg * DEG2RAD).astype(np.float32)
+
+
 def vehicle_frames(n, steps, seed=0x5EED, first=0):
     """RK_SENSOR_STREAM input: [steps, 4, n] uint64 M2006 feedback frames
     (VD_motor_if_m2006.hpp:13-21, big-endian angle/speed/current) from a per-wheel random

@@ -53,7 +53,7 @@ class VehicleBatch:
     def make_args(self, steps, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=None, seg_len=0, yaw=None, yaw_period=0,
                   frames=None, trace=None, goal=None, cost=None, task_period=0):
         """Device tensors -> rk_vdt_rollout_t.  cmd: int32/float32 [n_seg, n, 4] (rk_vdt_cmd_t
-        records), yaw: float32 [n_yaw, n], frames: int64 [steps, 4, n], trace: int32
+        records), yaw: float32 [n_yaw, n] radians or int16 [n_yaw, n] WT901C Yaw register counts, frames: int64 [steps, 4, n], trace: int32
         [steps, 16, n], goal: float32 [n, 2], cost: float32 [n]."""
         a = _cabi.VdtRollout()
         a.steps, a.sensor_mode = int(steps), int(sensor_mode)
@@ -62,8 +62,12 @@ class VehicleBatch:
             assert cmd.is_cuda and cmd.is_contiguous() and cmd.shape[1] == self.n and cmd.element_size() * cmd.shape[-1] == 16
             a.d_cmd, a.n_seg, a.seg_len = cmd.data_ptr(), cmd.shape[0], int(seg_len)
         if yaw is not None:
-            assert yaw.is_cuda and yaw.is_contiguous() and yaw.dtype == torch.float32 and yaw.shape[1] == self.n
-            a.d_yaw, a.n_yaw, a.yaw_period = yaw.data_ptr(), yaw.shape[0], int(yaw_period)
+            assert yaw.is_cuda and yaw.is_contiguous() and yaw.dtype in (torch.float32, torch.int16) and yaw.shape[1] == self.n
+            a.n_yaw, a.yaw_period = yaw.shape[0], int(yaw_period)
+            if yaw.dtype == torch.float32:
+                a.d_yaw = yaw.data_ptr()  # radians
+            else:
+                a.d_yaw_reg = yaw.data_ptr()  # the WT901C Yaw register (180/32768 deg per count)
         if frames is not None:
             assert frames.is_cuda and frames.is_contiguous() and frames.dtype == torch.int64
             assert tuple(frames.shape) == (steps, 4, self.n)

@@ -155,7 +155,11 @@ class HostRollout:
         a = _cabi.VdtRollout()
         a.steps, a.sensor_mode = steps, sensor_mode
         a.d_cmd, a.n_seg, a.seg_len = _ptr(cmd), (0 if cmd is None else cmd.shape[0]), seg_len
-        a.d_yaw, a.n_yaw, a.yaw_period = _ptr(yaw), (0 if yaw is None else yaw.shape[0]), yaw_period
+        a.n_yaw, a.yaw_period = (0 if yaw is None else yaw.shape[0]), yaw_period
+        if yaw is not None and yaw.dtype == np.int16:
+            a.d_yaw_reg = _ptr(yaw)  # the WT901C Yaw register stream
+        else:
+            a.d_yaw = _ptr(yaw)
         a.d_frames = _ptr(frames)
         a.d_trace = _ptr(self.trace)
         a.d_goal, a.d_cost = _ptr(goal), _ptr(self.cost)

@@ -440,3 +440,25 @@ def test_other_wirings_use_transcription_and_match():
         ol.run_port(st, n, ro, params=p, nthreads=8)
         assert_same(tr.cpu().numpy().view(np.uint32), ro.trace, f"variant {variant} trace")
         assert_same(vb.state.cpu().numpy().view(np.uint32), st, f"variant {variant} state")
+
+
+def test_yaw_register_input_equals_float_yaw_and_port():
+    """rk_vdt_rollout_t::d_yaw_reg (the WT901C Yaw register, int16) on both kernels == the float stream the IMU would
+    have produced == the port."""
+    lib = rk.load()
+    n, steps = 1500, 1000
+    inp = wl.plant_inputs(n, steps, seed=41)
+    reg = streams.vehicle_yaw_reg(n, steps // 10, seed=41)
+    st_r, tr_r = gpu_run(dict(inp, yaw=reg))
+    st_f, tr_f = gpu_run(dict(inp, yaw=streams.yaw_reg_to_rad(reg)))
+    assert_same(tr_r, tr_f, "register yaw vs float yaw trace")
+    assert_same(st_r, st_f, "register yaw vs float yaw state")
+    lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, 1)
+    try:
+        st_t, tr_t = gpu_run(dict(inp, yaw=reg))
+    finally:
+        lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, 0)
+    assert_same(tr_r, tr_t, "register yaw: fast vs transcription")
+    pst, ptr = port_run(dict(inp, yaw=reg))
+    assert_same(tr_r, ptr, "register yaw vs port trace")
+    assert_same(st_r, pst, "register yaw vs port state")
