@@ -329,6 +329,11 @@ typedef struct rk_adt_params {
   float motor_dir[RK_AJ_NUM];    /* fl_motor_dir    -1,1,1,1,1,1,-1              */
   float curlim_default_A[RK_AJ_NUM];
   float cycle_time_s;            /* ADTModeBase::FL_CYCLE_TIME_S 0.01f  AD_task_main.cpp:149 */
+  /* homing (ADTModeInitialize / ADTModeInitPosMove) */
+  float mechend_pos_deg[RK_AJ_NUM]; /* fl_mechend_pos_deg  -45,150,0,0,0,0,-90       */
+  float vel_init_degps[RK_AJ_NUM];  /* fl_vel_init_degps   15,30,10,10,30,30,-60     */
+  float curlim_init_A[RK_AJ_NUM];   /* fl_curlim_init_A    1,0.15,0.5,0.5,1,1,0.5    */
+  float initpos_deg[RK_AJ_NUM];     /* fl_initpos_deg      0,145,0,0,-90,0,0         */
 } rk_adt_params_t;
 void rk_adt_default_params(rk_adt_params_t *p);
 
@@ -434,6 +439,31 @@ int rk_adp_push_cmd(void *d_pstate, int64_t n, const void *d_cmd, const uint8_t 
 int rk_adp_update(const rk_adt_params_t *p, void *d_state, void *d_pstate, int64_t n, int32_t K, uint32_t *d_trace, void *stream);
 /* ::get_q_cmd_status (:134-148): 0 PROCESSING (queued), 1 DONE (one of the last two finished), 99 NO_DATA */
 int rk_adp_cmd_status(const void *d_pstate, int64_t n, const uint32_t *d_id, int32_t *d_status, void *stream);
+
+/* ---- Homing modes: ADTModeInitialize (src/ArmDrive/AD_mode_initialize.{hpp,cpp}: INIT -> TORQUE_ON
+ * (100 cycles) -> MOVE_MECH_END (500 cycles, J1 and J4 pushed towards their mechanical end at the init speed and
+ * current limit, the target frozen while it leads the measured angle by more than 45 deg) -> RESET_ANGLE
+ * (JointBase::mech_reset_pos and the DfGear overrides re-reference the offsets) -> MOVE_INIT_POS (every axis ramps
+ * to its init pose) -> COMPLETED) and ADTModeInitPosMove (AD_mode_initpos_move.{hpp,cpp}: the same without touching
+ * the offsets).  Same joints (the RK_AS_* block: the modes switch torque / initialised flags, current limits and
+ * offsets, so the MG joint passes through its torque-control branches), their own mode block: */
+enum {
+  RK_HS_STATE = 0,    /* nowState | is_comp << 9 | mode << 16 */
+  RK_HS_WAIT_CNT,     /* u16_wait_cnt_ */
+  RK_HS_VEL_DIR = 4,  /* ADTModeInitPosMove::fl_move_vel_dir_[5] */
+  RK_HS_WORDS = 12    /* 3 planes */
+};
+enum { RK_ADH_MODE_INIT = 1, RK_ADH_MODE_INIT_POS_MOVE = 2 };
+size_t rk_adh_state_words(void);
+size_t rk_adh_state_bytes(int64_t n);
+/* ADTModeBase::init() -> doInit() of the chosen mode for every arm */
+int rk_adh_mode_init(void *d_hstate, int64_t n, int mode, void *stream);
+/* K fused ticks of ADT::main's loop body with the homing mode active.  d_now (optional): the angles the servos
+ * reported since the last tick, float [K][4][n] = fl_raw_now_deg of P1 (MG), DF_Left, DF_Right, P3 (MyBldc) as their
+ * CAN rx callbacks store them, applied before the mode runs; NULL keeps the angles of the state block (Y0 always
+ * follows the ideal ICS servo).  Trace as rk_adt_update with word 11 = nowState, word 12 = u16_wait_cnt_. */
+int rk_adh_update(const rk_adt_params_t *p, void *d_state, void *d_hstate, int64_t n, int32_t K, const float *d_now,
+                  uint32_t *d_trace, void *stream);
 
 /* single-instance handle (drop-in for the statics of AD_task_main.cpp:108-156) */
 typedef struct rk_adt rk_adt_t;

@@ -19,6 +19,8 @@
 #include "ArmDrive/AD_joint_ics_servo.hpp"
 #include "ArmDrive/AD_joint_mg_servo.hpp"
 #include "ArmDrive/AD_joint_mybldc_servo.hpp"
+#include "ArmDrive/AD_mode_initialize.hpp"
+#include "ArmDrive/AD_mode_initpos_move.hpp"
 #include "ArmDrive/AD_mode_positioning.hpp"
 #include "ArmDrive/AD_mode_positioning_seq.hpp"
 /* the three in-tree command sequences (POS_CMD_SEQ_DEBUG_0/1/2 have internal linkage, so the
@@ -76,6 +78,8 @@ struct ArmSet {
   JointMyBldcServo       j_P3;
   ADTModePositioningSeq  posseq;
   ADTModePositioning     pos; /* the single-command mode (REQ_MOVE_POS) on the same joints */
+  ADTModeInitialize      m_init;    /* homing: INIT           (AD_task_main.cpp:152) */
+  ADTModeInitPosMove     m_initpos; /* homing: INIT_POS_MOVE  (:153) */
   /* what the CAN tx routines / the UART took this tick */
   uint8_t  mg_tx[8];
   int      mg_valid;
@@ -128,7 +132,9 @@ void bringup(ArmSet *s) {
 /* ADT::main loop body  AD_task_main.cpp:208-229 ; which = the active mode object */
 void tick(ArmSet *s, int which = 0) {
   if(which == 0) s->posseq.update();
-  else s->pos.update();
+  else if(which == 1) s->pos.update();
+  else if(which == 2) s->m_init.update();
+  else s->m_initpos.update();
   s->j_P1.update();
   s->j_DFL.update();
   s->j_DFR.update();
@@ -298,6 +304,34 @@ void import_pstate(ArmSet *s, const uint32_t *w) {
   }
 }
 
+void export_hstate(ArmSet *s, int mode, uint32_t *w) {
+  memset(w, 0, 4 * RK_HS_WORDS);
+  if(mode == RK_ADH_MODE_INIT) {
+    auto &m = s->m_init;
+    w[RK_HS_STATE] = (uint32_t)m.nowState | (m.is_comp ? RK_AS_FSM_IS_COMP : 0u) | ((uint32_t)mode << 16);
+    w[RK_HS_WAIT_CNT] = m.u16_wait_cnt_;
+  } else {
+    auto &m = s->m_initpos;
+    w[RK_HS_STATE] = (uint32_t)m.nowState | (m.is_comp ? RK_AS_FSM_IS_COMP : 0u) | ((uint32_t)mode << 16);
+    w[RK_HS_WAIT_CNT] = m.u16_wait_cnt_;
+    for(int j = 0; j < 5; j++) w[RK_HS_VEL_DIR + j] = f2u(m.fl_move_vel_dir_[j]);
+  }
+}
+int import_hstate(ArmSet *s, const uint32_t *w) {
+  const int mode = (int)(w[RK_HS_STATE] >> 16);
+  if(mode == RK_ADH_MODE_INIT) {
+    auto &m = s->m_init;
+    m.nowState = (ADTModeInitialize::State)(w[RK_HS_STATE] & 0xFF), m.is_comp = (w[RK_HS_STATE] & RK_AS_FSM_IS_COMP) != 0;
+    m.u16_wait_cnt_ = (uint16_t)w[RK_HS_WAIT_CNT];
+  } else {
+    auto &m = s->m_initpos;
+    m.nowState = (ADTModeInitPosMove::State)(w[RK_HS_STATE] & 0xFF), m.is_comp = (w[RK_HS_STATE] & RK_AS_FSM_IS_COMP) != 0;
+    m.u16_wait_cnt_ = (uint16_t)w[RK_HS_WAIT_CNT];
+    for(int j = 0; j < 5; j++) m.fl_move_vel_dir_[j] = u2f(w[RK_HS_VEL_DIR + j]);
+  }
+  return mode;
+}
+
 inline uint32_t &soa(uint32_t *blk, int64_t n, int64_t i, int w) { return blk[((int64_t)(w / 4) * n + i) * 4 + (w % 4)]; }
 
 void load_cmdtab(ArmSet *s, const uint32_t *tab, int64_t n, int64_t i) {
@@ -335,8 +369,10 @@ void trace_row(ArmSet *s, uint32_t *tr, int64_t n, int which = 0) {
   tr[5 * n] = vl, tr[6 * n] = (uint32_t)ang;
   for(int k = 0; k < 3; k++) tr[(int64_t)(7 + k) * n] = ld32(s->bldc_tx[k]);
   tr[10 * n] = (uint32_t)ics_pos_word(s);
-  tr[11 * n] = which == 0 ? (uint32_t)s->posseq.nowState : (uint32_t)s->pos.nowState;
-  tr[12 * n] = which == 0 ? (uint32_t)s->posseq.u8_nowcmd_idx_ : (uint32_t)s->pos.cmd_q_.size();
+  tr[11 * n] = which == 0 ? (uint32_t)s->posseq.nowState : which == 1 ? (uint32_t)s->pos.nowState
+               : which == 2 ? (uint32_t)s->m_init.nowState : (uint32_t)s->m_initpos.nowState;
+  tr[12 * n] = which == 0 ? (uint32_t)s->posseq.u8_nowcmd_idx_ : which == 1 ? (uint32_t)s->pos.cmd_q_.size()
+               : which == 2 ? (uint32_t)s->m_init.u16_wait_cnt_ : (uint32_t)s->m_initpos.u16_wait_cnt_;
   tr[13 * n] = bldc_id_byte(s->bl(0)->u32_txcmdid) | (bldc_id_byte(s->bl(1)->u32_txcmdid) << 8) | (bldc_id_byte(s->bl(2)->u32_txcmdid) << 16);
   tr[14 * n] = 0, tr[15 * n] = 0;
 }
@@ -469,6 +505,39 @@ void ref_adp_batch(int op, uint32_t *state, uint32_t *pstate, int64_t n, int64_t
         for(int k = 0; k < RK_AS_WORDS; k++) soa(state, n, i, k) = w[k];
       for(int k = 0; k < RK_PS_WORDS; k++) soa(pstate, n, i, k) = pw[k];
     }
+    s->~ArmSet();
+    free(s);
+  }
+}
+
+/* Homing modes on HOST arrays, same contracts as rk_adh_mode_init (op 0, mode in K) / rk_adh_update (op 2):
+ * the servo feedback stream `now` ([K][4][n]: P1, DF_Left, DF_Right, P3) lands where the CAN rx callbacks store it */
+void ref_adh_batch(int op, uint32_t *state, uint32_t *hstate, int64_t n, int64_t i0, int64_t i1, int K, const float *now,
+                   uint32_t *trace) {
+  for(int64_t i = i0; i < i1; i++) {
+    ArmSet  *s = make();
+    uint32_t w[RK_AS_WORDS], hw[RK_HS_WORDS];
+    for(int k = 0; k < RK_AS_WORDS; k++) w[k] = soa(state, n, i, k);
+    for(int k = 0; k < RK_HS_WORDS; k++) hw[k] = soa(hstate, n, i, k);
+    import_state(s, w);
+    int mode = import_hstate(s, hw);
+    if(op == 0) {
+      mode = K;
+      if(mode == RK_ADH_MODE_INIT) s->m_init.init();
+      else s->m_initpos.init();
+    } else {
+      JointBase *fb[4] = {&s->j_P1, &s->j_DFL, &s->j_DFR, &s->j_P3};
+      for(int t = 0; t < K; t++) {
+        if(now)
+          for(int k = 0; k < 4; k++) fb[k]->fl_raw_now_deg = now[((int64_t)t * 4 + k) * n + i];
+        tick(s, mode == RK_ADH_MODE_INIT ? 2 : 3);
+        if(trace) trace_row(s, trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, mode == RK_ADH_MODE_INIT ? 2 : 3);
+      }
+      export_state(s, w);
+      for(int k = 0; k < RK_AS_WORDS; k++) soa(state, n, i, k) = w[k];
+    }
+    export_hstate(s, mode, hw);
+    for(int k = 0; k < RK_HS_WORDS; k++) soa(hstate, n, i, k) = hw[k];
     s->~ArmSet();
     free(s);
   }

@@ -1039,6 +1039,186 @@ void orc_adp_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *
 
 
 /* ------------------------------------------------------------------------------------ */
+/* Homing modes: ADTModeInitialize (src/ArmDrive/AD_mode_initialize.cpp) and              */
+/* ADTModeInitPosMove (src/ArmDrive/AD_mode_initpos_move.cpp) on the same joints           */
+static float adt_absf(float x) { return (x < 0) ? -x : x; } /* mymath::absf  util_mymath.hpp:40 */
+/* set_torque_on: JointBase :39; DfGearPitch/Roll forward to both motors (AD_joint_dfgear.hpp:50-53) */
+static void adh_set_torque_on(uint32_t *w, int axis, int on) {
+  int k = ADT_AXIS[axis];
+  if(k == RK_AJ_P2 || k == RK_AJ_R0) {
+    set_jflag(w, RK_AJ_DFL, (jflag(w, RK_AJ_DFL) & ~RK_AJF_TORQUE_ON) | (on ? RK_AJF_TORQUE_ON : 0u));
+    set_jflag(w, RK_AJ_DFR, (jflag(w, RK_AJ_DFR) & ~RK_AJF_TORQUE_ON) | (on ? RK_AJF_TORQUE_ON : 0u));
+  } else {
+    set_jflag(w, k, (jflag(w, k) & ~RK_AJF_TORQUE_ON) | (on ? RK_AJF_TORQUE_ON : 0u));
+  }
+}
+static void adh_set_initialized(uint32_t *w, int axis, int on) { /* JointBase :40 (not overridden) */
+  int k = ADT_AXIS[axis];
+  set_jflag(w, k, (jflag(w, k) & ~RK_AJF_INITIALIZED) | (on ? RK_AJF_INITIALIZED : 0u));
+}
+static void adh_set_curlim(uint32_t *w, int axis, float lim) { /* JointBase :43; DfGear forwards (:55-58) */
+  int k = ADT_AXIS[axis];
+  if(k == RK_AJ_P2 || k == RK_AJ_R0) AJ(w, RK_AJ_DFL, RK_AJ_CURLIM) = f2u(lim), AJ(w, RK_AJ_DFR, RK_AJ_CURLIM) = f2u(lim);
+  else AJ(w, k, RK_AJ_CURLIM) = f2u(lim);
+}
+static void adh_mech_reset_pos(const rk_adt_params_t *p, uint32_t *w, int axis) { /* JointBase :36-38; DfGear :65-71,100-106 */
+  int k = ADT_AXIS[axis];
+  if(k == RK_AJ_P2) { /* the pitch joint resets both motors, the roll joint does not */
+    AJ(w, RK_AJ_DFL, RK_AJ_OFS) = f2u(u2f(AJ(w, RK_AJ_DFL, RK_AJ_RAW_NOW)) - p->mechend_pos_deg[RK_AJ_DFL]);
+    AJ(w, RK_AJ_DFR, RK_AJ_OFS) = f2u(u2f(AJ(w, RK_AJ_DFR, RK_AJ_RAW_NOW)) - p->mechend_pos_deg[RK_AJ_DFR]);
+  }
+  AJ(w, k, RK_AJ_OFS) = f2u(u2f(AJ(w, k, RK_AJ_RAW_NOW)) - p->mechend_pos_deg[k]);
+}
+static void adh_joint_init(const rk_adt_params_t *p, uint32_t *w, int axis) { /* JointBase::init() and its overrides */
+  int k = ADT_AXIS[axis];
+  if(k == RK_AJ_Y0) { /* JointIcsServo::init  AD_joint_ics_servo.cpp:35-55 over the ideal servo (setFree answers the last position) */
+    float now = (float)ics_posDeg100((int)(int32_t)w[RK_AS_ICS_SERVO] + 7500) * 0.01f * p->motor_dir[RK_AJ_Y0];
+    AJ(w, k, RK_AJ_RAW_NOW) = f2u(now), AJ(w, k, RK_AJ_RAW_TGT) = f2u(now);
+    w[RK_AS_ICS_POS] = (uint32_t)-1;
+    set_jflag(w, k, jflag(w, k) | RK_AJF_CONNECTED);
+  } else if(k == RK_AJ_P1) { /* JointMgServo::init  AD_joint_mg_servo.cpp:38-48 */
+    set_jflag(w, k, (jflag(w, k) & ~(RK_AJF_TORQUE_PREV | RK_AJF_TORQUE_ON)) | RK_AJF_CONNECTED);
+    w[RK_AS_MG_CTRL + MGC_GAINSET] = 1; /* set_myctrl_gain_params(InitGain): gains, and set_VelLpf_CutOff resets the IIR */
+    w[RK_AS_MG_CTRL + MGC_LPF_Y] = 0, w[RK_AS_MG_CTRL + MGC_LPF_X] = 0;
+  }
+}
+/* exec_move_initpos of either mode (AD_mode_initialize.cpp:113-143 / AD_mode_initpos_move.cpp:70-95) for one axis;
+ * returns whether the axis has arrived */
+static int adh_ramp_axis(const rk_adt_params_t *p, uint32_t *w, int axis, float dir_vel) {
+  int   k = ADT_AXIS[axis], arrived;
+  float initpos = p->initpos_deg[k], nowpos = adt_get_tgt_deg(w, k);
+  float vel = dir_vel * adt_absf(p->vel_init_degps[k]);
+  float tgtpos = nowpos + vel * p->cycle_time_s;
+  arrived = ((vel > 0) && (tgtpos > initpos)) || ((vel < 0) && (tgtpos < initpos));
+  if(arrived) tgtpos = initpos;
+  adt_set_tgt(p, w, axis, tgtpos);
+  adh_set_curlim(w, axis, p->curlim_default_A[k]);
+  return arrived;
+}
+static void adh_move_mechend(const rk_adt_params_t *p, uint32_t *w, int axis) { /* ax_move_mechend :150-167 */
+  int   k = ADT_AXIS[axis];
+  float vel = p->vel_init_degps[k], nowpos = adt_get_now_deg(p, w, axis), tgtpos = adt_get_tgt_deg(w, k);
+  if(adt_absf(nowpos - tgtpos) > 45.0f) adt_set_tgt(p, w, axis, tgtpos); /* gone too far: hold */
+  else adt_set_tgt(p, w, axis, tgtpos + vel * p->cycle_time_s);
+  adh_set_curlim(w, axis, p->curlim_init_A[k]);
+}
+static void adh_mode_update(const rk_adt_params_t *p, uint32_t *w, uint32_t *hw) {
+  uint32_t state = hw[RK_HS_STATE] & 0xFFu, comp = hw[RK_HS_STATE] & RK_AS_FSM_IS_COMP, mode = hw[RK_HS_STATE] >> 16;
+  uint32_t cnt = hw[RK_HS_WAIT_CNT] & 0xFFFFu;
+  int      ax, all;
+  if(mode == RK_ADH_MODE_INIT) {
+    switch(state) {
+    case 0: /* exec_init :43-50 */
+      for(ax = 0; ax < 5; ax++) adh_joint_init(p, w, ax), adh_set_initialized(w, ax, 0);
+      state = 1;
+      break;
+    case 1: /* exec_torqueon :56-72 */
+      if(cnt == 0) {
+        for(ax = 0; ax < 5; ax++) adh_set_torque_on(w, ax, 1);
+        cnt++;
+      } else if(cnt == 100) state = 2, cnt = 0;
+      else cnt++;
+      break;
+    case 2: /* exec_move_mechend :79-94 */
+      if(cnt < 500) {
+        adh_move_mechend(p, w, 1);
+        adh_move_mechend(p, w, 4);
+        cnt++;
+      } else if(cnt == 500) state = 3, cnt = 0;
+      break;
+    case 3: /* exec_resetangle :100-109 + ax_reset_angle :174-179 */
+      for(ax = 1; ax < 5; ax++) {
+        adh_mech_reset_pos(p, w, ax);
+        adt_set_tgt(p, w, ax, adt_get_now_deg(p, w, ax));
+      }
+      state = 4;
+      break;
+    case 4: /* exec_move_initpos :115-143 */
+      all = 1;
+      for(ax = 0; ax < 5; ax++) {
+        int   k = ADT_AXIS[ax];
+        float d = p->initpos_deg[k] - adt_get_tgt_deg(w, k);
+        adh_set_initialized(w, ax, 1); /* before set_tgt_ang_deg in the reference too; neither reads the other */
+        all &= adh_ramp_axis(p, w, ax, (d >= 0.0f) ? 1.0f : -1.0f);
+      }
+      if(all) state = 5;
+      break;
+    case 5: comp = RK_AS_FSM_IS_COMP; break;
+    default: break;
+    }
+  } else if(mode == RK_ADH_MODE_INIT_POS_MOVE) {
+    switch(state) {
+    case 0: /* exec_init :37-45 */
+      for(ax = 0; ax < 5; ax++) {
+        int k = ADT_AXIS[ax];
+        adt_set_tgt(p, w, ax, adt_get_now_deg(p, w, ax));
+        hw[RK_HS_VEL_DIR + ax] = f2u((p->initpos_deg[k] >= adt_get_now_deg(p, w, ax)) ? 1.0f : -1.0f);
+      }
+      state = 1;
+      break;
+    case 1: /* exec_torqueon :51-67 */
+      if(cnt == 0) {
+        for(ax = 0; ax < 5; ax++) adh_set_torque_on(w, ax, 1);
+        cnt++;
+      } else if(cnt == 100) state = 2, cnt = 0;
+      else cnt++;
+      break;
+    case 2: /* exec_move_initpos :73-95 */
+      all = 1;
+      for(ax = 0; ax < 5; ax++) all &= adh_ramp_axis(p, w, ax, u2f(hw[RK_HS_VEL_DIR + ax]));
+      if(all) state = 3;
+      break;
+    case 3: comp = RK_AS_FSM_IS_COMP; break;
+    default: break;
+    }
+  }
+  hw[RK_HS_STATE]    = state | comp | (mode << 16);
+  hw[RK_HS_WAIT_CNT] = cnt;
+}
+
+/* op 0 = rk_adh_mode_init(mode = K), op 2 = K ticks (+ feedback stream, + trace) */
+void orc_adh_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *hstate, int64_t n, int64_t i0, int64_t i1, int K,
+                   const float *now, uint32_t *trace) {
+  int64_t i;
+  int     k, t;
+  for(i = i0; i < i1; i++) {
+    uint32_t w[RK_AS_WORDS], hw[RK_HS_WORDS];
+    for(k = 0; k < RK_AS_WORDS; k++) w[k] = *soa(state, n, i, k);
+    for(k = 0; k < RK_HS_WORDS; k++) hw[k] = *soa(hstate, n, i, k);
+    if(op == 0) { /* ADTModeBase::init(): is_comp = false; doInit(): nowState = INIT, u16_wait_cnt_ = 0, flags / directions zeroed */
+      memset(hw, 0, sizeof(hw));
+      hw[RK_HS_STATE] = (uint32_t)K << 16;
+    } else {
+      for(t = 0; t < K; t++) {
+        if(now) {
+          static const int JK[4] = {RK_AJ_P1, RK_AJ_DFL, RK_AJ_DFR, RK_AJ_P3};
+          for(k = 0; k < 4; k++) AJ(w, JK[k], RK_AJ_RAW_NOW) = f2u(now[((int64_t)t * 4 + k) * n + i]);
+        }
+        adh_mode_update(p, w, hw);
+        adt_mg_update(p, w);
+        adt_bldc_update(p, w, 0);
+        adt_bldc_update(p, w, 1);
+        adt_bldc_update(p, w, 2);
+        adt_ics_update(p, w);
+        if(trace) {
+          uint32_t *tr = trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i;
+          for(k = 0; k < 5; k++) tr[(int64_t)k * n] = f2u(adt_get_tgt_deg(w, ADT_AXIS[k]));
+          tr[5 * n] = w[RK_AS_MG_TX] >> 16, tr[6 * n] = w[RK_AS_MG_TX + 1];
+          for(k = 0; k < 3; k++) tr[(int64_t)(7 + k) * n] = w[RK_AS_BLDC_TX0 + 4 * k];
+          tr[10 * n] = w[RK_AS_ICS_POS];
+          tr[11 * n] = hw[RK_HS_STATE] & 0xFFu, tr[12 * n] = hw[RK_HS_WAIT_CNT];
+          tr[13 * n] = bldc_id_byte(w[RK_AS_BLDC_TX0 + 2]) | (bldc_id_byte(w[RK_AS_BLDC_TX0 + 6]) << 8) | (bldc_id_byte(w[RK_AS_BLDC_TX0 + 10]) << 16);
+          tr[14 * n] = 0, tr[15 * n] = 0;
+        }
+      }
+      for(k = 0; k < RK_AS_WORDS; k++) *soa(state, n, i, k) = w[k];
+    }
+    for(k = 0; k < RK_HS_WORDS; k++) *soa(hstate, n, i, k) = hw[k];
+  }
+}
+
+
+/* ------------------------------------------------------------------------------------ */
 /* WIT serial codec: WitSerialDataIn / CopeWitData (lib/wt901c/wit_c_sdk.c:77-164) + the update flags   */
 /* of SensorDataUpdata (imu_if_wt901c.cpp:24-46) + IMU_IF_WT901C::update / init on the parsed registers */
 typedef struct {

@@ -40,6 +40,10 @@ void orc_adt_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *
 void orc_adp_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *pstate, int64_t n, int64_t i0, int64_t i1, int K,
                    const uint32_t *cmd, const uint8_t *valid, uint32_t *trace, const uint32_t *ids, int32_t *status);
 
+/* rk_adh_* on HOST arrays: op 0 = mode init (mode in K), 2 = K ticks */
+void orc_adh_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *hstate, int64_t n, int64_t i0, int64_t i1, int K,
+                   const float *now, uint32_t *trace);
+
 /* rk_imt_feed_bytes() on HOST arrays */
 void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0, int64_t i1, int K, int ncells,
                         const uint32_t *cells, const uint16_t *nbytes, uint32_t *out, float *yaw_rad, int do_init);

@@ -59,6 +59,7 @@ class RmtParams(C.Structure):
     _fields_ = [("no_cmd_stop_thre", C.c_uint32), ("wall_leave_time_ms", C.c_uint32), ("wall_leave_speed_mmps", C.c_uint32)]
 
 
+RK_ADH_MODE_INIT, RK_ADH_MODE_INIT_POS_MOVE = 1, 2
 RK_ROS_NONE, RK_ROS_MECANUM_CMD, RK_ROS_MECANUM_CONT, RK_ROS_CMD_VEL, RK_ROS_COMMAND = range(5)
 
 
@@ -98,6 +99,10 @@ class AdtParams(C.Structure):
         ("motor_dir", C.c_float * 7),
         ("curlim_default_A", C.c_float * 7),
         ("cycle_time_s", C.c_float),
+        ("mechend_pos_deg", C.c_float * 7),
+        ("vel_init_degps", C.c_float * 7),
+        ("curlim_init_A", C.c_float * 7),
+        ("initpos_deg", C.c_float * 7),
     ]
 
 
@@ -286,4 +291,8 @@ def default_arm_params():
     p.motor_dir[:] = [-1.0, 1.0, 1.0, 1.0, 1.0, 1.0, -1.0]
     p.curlim_default_A[:] = [3.0, 0.7, 0.5, 0.5, 1.0, 1.0, 0.8]
     p.cycle_time_s = 0.01
+    p.mechend_pos_deg[:] = [-45.0, 150.0, 0.0, 0.0, 0.0, 0.0, -90.0]
+    p.vel_init_degps[:] = [15.0, 30.0, 10.0, 10.0, 30.0, 30.0, -60.0]
+    p.curlim_init_A[:] = [1.0, 0.15, 0.5, 0.5, 1.0, 1.0, 0.5]
+    p.initpos_deg[:] = [0.0, 145.0, 0.0, 0.0, -90.0, 0.0, 0.0]
     return p

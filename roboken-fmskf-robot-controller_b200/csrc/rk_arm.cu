@@ -764,6 +764,11 @@ void rk_adt_default_params(rk_adt_params_t *p) {
   const float cl[RK_AJ_NUM]   = {3.0f, 0.7f, 0.5f, 0.5f, 1.0f, 1.0f, 0.8f};
   for(int k = 0; k < RK_AJ_NUM; k++) p->ctrl_time_s[k] = 0.01f, p->gear_ratio[k] = gear[k], p->motor_dir[k] = dir[k], p->curlim_default_A[k] = cl[k];
   p->cycle_time_s = 0.01f; // AD_task_main.cpp:149
+  const float mech[RK_AJ_NUM] = {-45.0f, 150.0f, 0.0f, 0.0f, 0.0f, 0.0f, -90.0f};
+  const float vin[RK_AJ_NUM]  = {15.0f, 30.0f, 10.0f, 10.0f, 30.0f, 30.0f, -60.0f};
+  const float cin[RK_AJ_NUM]  = {1.0f, 0.15f, 0.5f, 0.5f, 1.0f, 1.0f, 0.5f};
+  const float ipos[RK_AJ_NUM] = {0.0f, 145.0f, 0.0f, 0.0f, -90.0f, 0.0f, 0.0f};
+  for(int k = 0; k < RK_AJ_NUM; k++) p->mechend_pos_deg[k] = mech[k], p->vel_init_degps[k] = vin[k], p->curlim_init_A[k] = cin[k], p->initpos_deg[k] = ipos[k];
 }
 
 size_t rk_adt_state_words(void) { return RK_AS_WORDS; }

@@ -60,6 +60,8 @@ ADT_TRACE_WORDS = 16
 # ADTModePositioning mode block (RK_PS_*)
 PS_STATE, PS_MOVE_CNT, PS_CYCLE, PS_QSIZE, PS_PREV_ID0, PS_PREV_ID1 = 0, 1, 2, 3, 4, 5
 PS_NOW_CMD, PS_MOVE_DEG, PS_QUEUE, PS_WORDS = 8, 16, 24, 56
+# homing mode block (RK_HS_*)
+HS_STATE, HS_WAIT_CNT, HS_VEL_DIR, HS_WORDS = 0, 1, 4, 12
 ADT_AXIS = (AJ_Y0, AJ_P1, AJ_P2, AJ_R0, AJ_P3)  # mode axes J0..J4 (AD_task_main.cpp:148)
 
 

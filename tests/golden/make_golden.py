@@ -63,7 +63,7 @@ def arm_golden():
 
 
 def main():
-    which = set(sys.argv[1:]) or {"vdt", "imu", "arm", "wire", "rmt"}
+    which = set(sys.argv[1:]) or {"vdt", "imu", "arm", "wire", "rmt", "armhome"}
     if "arm" in which:
         arm_golden()
     if "vdt" in which:
@@ -74,6 +74,8 @@ def main():
         imu_wire_golden()
     if "rmt" in which:
         rmt_golden()
+    if "armhome" in which:
+        armhome_golden()
 
 
 def vdt_golden():
@@ -137,6 +139,20 @@ def rmt_golden():
     out = np.array([r.ref_rm_atan2f(float(a), float(b)) for a, b in zip(y, x)], dtype=np.float32)
     path = os.path.join(HERE, "rmt_golden.npz")
     np.savez_compressed(path, cmd=cmd, abort=ab, state=st, atan_y=y, atan_x=x, atan_out=out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def armhome_golden():
+    # arm homing modes: the unmodified ADTModeInitialize / ADTModeInitPosMove on the unmodified joints
+    import test_armhome_cpu as th
+
+    n, K = 24, 1300
+    out = {}
+    for mode, tag in ((_cabi.RK_ADH_MODE_INIT, "init"), (_cabi.RK_ADH_MODE_INIT_POS_MOVE, "ipm")):
+        st, hs, tr = th.run("ref", mode, th.start_states(n, seed=0x5EED + mode), n, K, th.feedback(n, K, seed=0x5EED))
+        out[tag + "_state"], out[tag + "_hstate"], out[tag + "_trace"] = st, hs, tr[::13]
+    path = os.path.join(HERE, "armhome_golden.npz")
+    np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 

@@ -53,6 +53,8 @@ def port():
         lib.orc_adt_batch.restype = None
         lib.orc_adp_batch.argtypes = lib.orc_adt_batch.argtypes
         lib.orc_adp_batch.restype = None
+        lib.orc_adh_batch.argtypes = [C.c_int, C.POINTER(_cabi.AdtParams), vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp]
+        lib.orc_adh_batch.restype = None
         for nm in ("orc_sin", "orc_cos", "orc_normalize_rad_0to2pi", "orc_normalize_deg_0to360"):
             getattr(lib, nm).argtypes = [C.c_float]
             getattr(lib, nm).restype = C.c_float
@@ -120,6 +122,8 @@ def ref(name="libref_vdt.so"):
             lib.ref_imt_bytes_rollout.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp]
             lib.ref_imt_bytes_rollout.restype = None
         if name.startswith("libref_arm"):
+            lib.ref_adh_batch.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp]
+            lib.ref_adh_batch.restype = None
             lib.ref_adt_create.restype = vp
             for nm in ("ref_adt_destroy", "ref_adt_bringup", "ref_adt_tick"):
                 getattr(lib, nm).argtypes = [vp]
@@ -218,6 +222,21 @@ def imu_bytes_ref(state_soa, n, cells, nbytes=None, want_out=False):
     sreg = np.zeros((n, 16), dtype=np.int16)
     ref("libref_imu.so").ref_imt_bytes_rollout(_ptr(state_soa), n, 0, n, K, ncells, _ptr(cells), _ptr(nbytes), _ptr(out), _ptr(sreg))
     return out, sreg
+
+
+def arm_homing(kind, op, state, hstate, n, K=0, mode=0, now=None, trace=False, params=None):
+    """rk_adh_mode_init ("init", mode) / rk_adh_update ("update", K ticks) on host arrays via the port or the compiled
+    reference modes.  now: float32 [K, 4, n] servo feedback or None.  Returns the trace (uint32 [K, 16, n]) or None."""
+    p = params or _cabi.default_arm_params()
+    tr = np.zeros((K, layout.ADT_TRACE_WORDS, n), dtype=np.uint32) if (trace and op == "update") else None
+    if now is not None:
+        assert now.dtype == np.float32 and now.shape == (K, 4, n) and now.flags.c_contiguous
+    o, k = (0, mode) if op == "init" else (2, K)
+    if kind == "port":
+        port().orc_adh_batch(o, C.byref(p), _ptr(state), _ptr(hstate), n, 0, n, k, _ptr(now), _ptr(tr))
+    else:
+        ref("libref_arm.so").ref_adh_batch(o, _ptr(state), _ptr(hstate), n, 0, n, k, _ptr(now), _ptr(tr))
+    return tr
 
 
 def rm_default_params():
