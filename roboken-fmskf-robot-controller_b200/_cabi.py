@@ -202,6 +202,11 @@ def _proto(lib):
     lib.rk_adp_state_words.restype = C.c_size_t
     lib.rk_adp_state_bytes.argtypes = [C.c_int64]
     lib.rk_adp_state_bytes.restype = C.c_size_t
+    lib.rk_adh_state_words.restype = C.c_size_t
+    lib.rk_adh_state_bytes.argtypes = [C.c_int64]
+    lib.rk_adh_state_bytes.restype = C.c_size_t
+    lib.rk_adh_mode_init.argtypes = [vp, C.c_int64, C.c_int, vp]
+    lib.rk_adh_update.argtypes = [C.POINTER(AdtParams), vp, vp, C.c_int64, C.c_int32, vp, vp, vp]
     lib.rk_adp_mode_init.argtypes = [vp, C.c_int64, vp]
     lib.rk_adp_push_cmd.argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.rk_adp_update.argtypes = [C.POINTER(AdtParams), vp, vp, C.c_int64, C.c_int32, vp, vp]

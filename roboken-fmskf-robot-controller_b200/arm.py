@@ -103,6 +103,29 @@ class ArmPositioningBatch:
         return out
 
 
+class ArmHomingBatch:
+    """The homing modes ADTModeInitialize (mode RK_ADH_MODE_INIT) and ADTModeInitPosMove (RK_ADH_MODE_INIT_POS_MOVE) for
+    the arms of an ArmBatch: the joints are the ArmBatch's, the mode block (state, wait counter, ramp directions) lives
+    here.  isCompleted() of the firmware = (hstate word 0 >> 9) & 1."""
+
+    def __init__(self, arms):
+        self.arms, self.lib, self.n = arms, arms.lib, arms.n
+        assert self.lib.rk_adh_state_words() == layout.HS_WORDS
+        with torch.cuda.device(arms.dev_index):
+            self.hstate = torch.zeros(layout.HS_WORDS * self.n, dtype=torch.int32, device=arms.device)
+
+    def mode_init(self, mode, stream=None):
+        _cabi.check(self.lib.rk_adh_mode_init(self.hstate.data_ptr(), self.n, int(mode), self.arms._st(stream)))
+
+    def update(self, K=1, now=None, trace=None, stream=None):
+        """now: float32 [K, 4, n] servo angles (P1, DF_Left, DF_Right, P3) reported before each tick, or None."""
+        if now is not None:
+            assert now.is_cuda and now.dtype == torch.float32 and now.is_contiguous() and tuple(now.shape) == (int(K), 4, self.n)
+        _cabi.check(self.lib.rk_adh_update(C.byref(self.arms.params), self.arms.state.data_ptr(), self.hstate.data_ptr(), self.n, int(K),
+                                           None if now is None else now.data_ptr(), None if trace is None else trace.data_ptr(),
+                                           self.arms._st(stream)))
+
+
 class Arm:
     """Single arm (rk_adt_t): the statics of AD_task_main.cpp:108-156 behind one handle."""
 

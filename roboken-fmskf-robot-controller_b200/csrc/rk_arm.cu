@@ -617,6 +617,297 @@ adp_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, uint4 *__r
   st_plane(ps, n, 5, i, make_uint4(f2u(move[4]), m1.y, m1.z, m1.w));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Homing modes: ADTModeInitialize (AD_mode_initialize.cpp) and ADTModeInitPosMove (AD_mode_initpos_move.cpp).
+// They rewrite what the positioning tick treats as launch constants (torque / initialised flags, current limits,
+// offsets), and run once per power-up, so this is a plain transcription: the whole arm block lives in registers
+// as words (every index below is a compile-time constant) and each joint class is restated on it.
+// ---------------------------------------------------------------------------------------------
+#define AJW(w, k, f) ((w)[RK_AS_JOINT0 + 4 * (k) + (f)])
+RK_DEV uint32_t hj_flag(const uint32_t *w, int k) { return (w[RK_AS_JFLAGS] >> (4 * k)) & 0xFu; }
+RK_DEV void     hj_set_flag(uint32_t *w, int k, uint32_t b) { w[RK_AS_JFLAGS] = (w[RK_AS_JFLAGS] & ~(0xFu << (4 * k))) | (b << (4 * k)); }
+RK_DEV void     hj_set_bit(uint32_t *w, int k, uint32_t bit, bool on) { hj_set_flag(w, k, (hj_flag(w, k) & ~bit) | (on ? bit : 0u)); }
+RK_DEV float    hj_absf(float x) { return (x < 0.0f) ? -x : x; } // mymath::absf  util_mymath.hpp:40
+
+template <int AX> RK_DEV float hj_get_tgt(const uint32_t *w) { // JointBase::get_tgt_deg :47
+  return fsub(u2f(AJW(w, axis_joint(AX), RK_AJ_RAW_TGT)), u2f(AJW(w, axis_joint(AX), RK_AJ_OFS)));
+}
+template <int AX> RK_DEV float hj_get_now(const rk_adt_params_t &p, const uint32_t *w) { // ::get_now_deg :48; DfGear :76-77,98
+  constexpr int k = axis_joint(AX);
+  if(k == RK_AJ_P2 || k == RK_AJ_R0) {
+    const float ln = fsub(u2f(AJW(w, RK_AJ_DFL, RK_AJ_RAW_NOW)), u2f(AJW(w, RK_AJ_DFL, RK_AJ_OFS)));
+    const float rn = fsub(u2f(AJW(w, RK_AJ_DFR, RK_AJ_RAW_NOW)), u2f(AJW(w, RK_AJ_DFR, RK_AJ_OFS)));
+    const float m  = (k == RK_AJ_P2) ? fsub(ln, rn) : -fadd(ln, rn);
+    return fsub(fdiv(fmul(m, 0.5f), p.gear_ratio[k]), u2f(AJW(w, k, RK_AJ_OFS)));
+  }
+  return fsub(u2f(AJW(w, k, RK_AJ_RAW_NOW)), u2f(AJW(w, k, RK_AJ_OFS)));
+}
+template <int AX> RK_DEV void hj_set_tgt(const rk_adt_params_t &p, uint32_t *w, float tgt) { // ::set_tgt_ang_deg :42; DfGear :14-37,60-63,93-96
+  constexpr int k = axis_joint(AX);
+  const float   raw = fadd(tgt, u2f(AJW(w, k, RK_AJ_OFS)));
+  AJW(w, k, RK_AJ_RAW_TGT) = f2u(raw);
+  if(k == RK_AJ_P2 || k == RK_AJ_R0) {
+    if(k == RK_AJ_P2) w[RK_AS_DFV_P] = f2u(fmul(raw, p.gear_ratio[k]));
+    else w[RK_AS_DFV_R] = f2u(fmul(raw, p.gear_ratio[k]));
+    const float P = u2f(w[RK_AS_DFV_P]), R = u2f(w[RK_AS_DFV_R]);
+    AJW(w, RK_AJ_DFL, RK_AJ_RAW_TGT) = f2u(fadd(fsub(P, R), u2f(AJW(w, RK_AJ_DFL, RK_AJ_OFS))));
+    AJW(w, RK_AJ_DFR, RK_AJ_RAW_TGT) = f2u(fadd(-fadd(P, R), u2f(AJW(w, RK_AJ_DFR, RK_AJ_OFS))));
+  }
+}
+template <int AX> RK_DEV void hj_set_torque_on(uint32_t *w, bool on) { // :39; DfGear forwards to both motors :50-53
+  constexpr int k = axis_joint(AX);
+  if(k == RK_AJ_P2 || k == RK_AJ_R0) hj_set_bit(w, RK_AJ_DFL, RK_AJF_TORQUE_ON, on), hj_set_bit(w, RK_AJ_DFR, RK_AJF_TORQUE_ON, on);
+  else hj_set_bit(w, k, RK_AJF_TORQUE_ON, on);
+}
+template <int AX> RK_DEV void hj_set_curlim(uint32_t *w, float lim) { // :43; DfGear forwards :55-58
+  constexpr int k = axis_joint(AX);
+  if(k == RK_AJ_P2 || k == RK_AJ_R0) AJW(w, RK_AJ_DFL, RK_AJ_CURLIM) = f2u(lim), AJW(w, RK_AJ_DFR, RK_AJ_CURLIM) = f2u(lim);
+  else AJW(w, k, RK_AJ_CURLIM) = f2u(lim);
+}
+template <int AX> RK_DEV void hj_mech_reset(const rk_adt_params_t &p, uint32_t *w) { // :36-38; DfGear :65-71,100-106
+  constexpr int k = axis_joint(AX);
+  if(k == RK_AJ_P2) { // the pitch joint resets both motors, the roll joint does not
+    AJW(w, RK_AJ_DFL, RK_AJ_OFS) = f2u(fsub(u2f(AJW(w, RK_AJ_DFL, RK_AJ_RAW_NOW)), p.mechend_pos_deg[RK_AJ_DFL]));
+    AJW(w, RK_AJ_DFR, RK_AJ_OFS) = f2u(fsub(u2f(AJW(w, RK_AJ_DFR, RK_AJ_RAW_NOW)), p.mechend_pos_deg[RK_AJ_DFR]));
+  }
+  AJW(w, k, RK_AJ_OFS) = f2u(fsub(u2f(AJW(w, k, RK_AJ_RAW_NOW)), p.mechend_pos_deg[k]));
+}
+template <int AX> RK_DEV void hj_joint_init(const rk_adt_params_t &p, uint32_t *w) { // JointBase::init() and its overrides
+  constexpr int k = axis_joint(AX);
+  if(k == RK_AJ_Y0) { // JointIcsServo::init  AD_joint_ics_servo.cpp:35-55 over the ideal servo (setFree answers the last position)
+    const float now = fmul(fmul((float)ics_posDeg100((int)(int32_t)w[RK_AS_ICS_SERVO] + 7500), 0.01f), p.motor_dir[RK_AJ_Y0]);
+    AJW(w, k, RK_AJ_RAW_NOW) = f2u(now), AJW(w, k, RK_AJ_RAW_TGT) = f2u(now);
+    w[RK_AS_ICS_POS] = 0xFFFFFFFFu;
+    hj_set_bit(w, k, RK_AJF_CONNECTED, true);
+  } else if(k == RK_AJ_P1) { // JointMgServo::init  AD_joint_mg_servo.cpp:38-48
+    hj_set_flag(w, k, (hj_flag(w, k) & ~(RK_AJF_TORQUE_PREV | RK_AJF_TORQUE_ON)) | RK_AJF_CONNECTED);
+    w[RK_AS_MG_CTRL + 7] = 1u; // set_myctrl_gain_params(InitGain): gains, and set_VelLpf_CutOff resets the IIR
+    w[RK_AS_MG_CTRL + 2] = 0u, w[RK_AS_MG_CTRL + 3] = 0u;
+  }
+}
+// exec_move_initpos of either mode (AD_mode_initialize.cpp:113-143 / AD_mode_initpos_move.cpp:70-95), one axis
+template <int AX> RK_DEV bool hj_ramp_axis(const rk_adt_params_t &p, uint32_t *w, float dir_vel) {
+  constexpr int k = axis_joint(AX);
+  const float initpos = p.initpos_deg[k], nowpos = hj_get_tgt<AX>(w);
+  const float vel     = fmul(dir_vel, hj_absf(p.vel_init_degps[k]));
+  float       tgtpos  = fadd(nowpos, fmul(vel, p.cycle_time_s));
+  const bool  arrived = ((vel > 0.0f) && (tgtpos > initpos)) || ((vel < 0.0f) && (tgtpos < initpos));
+  if(arrived) tgtpos = initpos;
+  hj_set_tgt<AX>(p, w, tgtpos);
+  hj_set_curlim<AX>(w, p.curlim_default_A[k]);
+  return arrived;
+}
+template <int AX> RK_DEV void hj_move_mechend(const rk_adt_params_t &p, uint32_t *w) { // ax_move_mechend :150-167
+  constexpr int k = axis_joint(AX);
+  const float vel = p.vel_init_degps[k], nowpos = hj_get_now<AX>(p, w), tgtpos = hj_get_tgt<AX>(w);
+  if(hj_absf(fsub(nowpos, tgtpos)) > 45.0f) hj_set_tgt<AX>(p, w, tgtpos); // gone too far: hold
+  else hj_set_tgt<AX>(p, w, fadd(tgtpos, fmul(vel, p.cycle_time_s)));
+  hj_set_curlim<AX>(w, p.curlim_init_A[k]);
+}
+template <int AX> RK_DEV void hj_reset_angle(const rk_adt_params_t &p, uint32_t *w) { // ax_reset_angle :174-179
+  hj_mech_reset<AX>(p, w);
+  hj_set_tgt<AX>(p, w, hj_get_now<AX>(p, w));
+}
+template <int AX> RK_DEV bool hj_init_ramp(const rk_adt_params_t &p, uint32_t *w) {
+  const float d = fsub(p.initpos_deg[axis_joint(AX)], hj_get_tgt<AX>(w));
+  hj_set_bit(w, axis_joint(AX), RK_AJF_INITIALIZED, true);
+  return hj_ramp_axis<AX>(p, w, (d >= 0.0f) ? 1.0f : -1.0f);
+}
+template <int AX> RK_DEV void hj_ipm_init(const rk_adt_params_t &p, uint32_t *w, uint32_t *hw) { // ADTModeInitPosMove::exec_init :37-45
+  hj_set_tgt<AX>(p, w, hj_get_now<AX>(p, w));
+  hw[RK_HS_VEL_DIR + AX] = f2u((p.initpos_deg[axis_joint(AX)] >= hj_get_now<AX>(p, w)) ? 1.0f : -1.0f);
+}
+
+RK_DEV void hj_mode_update(const rk_adt_params_t &p, uint32_t *w, uint32_t *hw) {
+  uint32_t       state = hw[RK_HS_STATE] & 0xFFu, comp = hw[RK_HS_STATE] & RK_AS_FSM_IS_COMP;
+  const uint32_t mode  = hw[RK_HS_STATE] >> 16;
+  uint32_t       cnt   = hw[RK_HS_WAIT_CNT] & 0xFFFFu;
+  const bool     torque_state = state == 1u && (mode == RK_ADH_MODE_INIT || mode == RK_ADH_MODE_INIT_POS_MOVE);
+  if(torque_state) { // exec_torqueon of both modes
+    if(cnt == 0u) {
+      hj_set_torque_on<0>(w, true), hj_set_torque_on<1>(w, true), hj_set_torque_on<2>(w, true), hj_set_torque_on<3>(w, true), hj_set_torque_on<4>(w, true);
+      cnt++;
+    } else if(cnt == 100u) state = 2u, cnt = 0u;
+    else cnt++;
+  } else if(mode == RK_ADH_MODE_INIT) {
+    if(state == 0u) { // exec_init :43-50
+      hj_joint_init<0>(p, w), hj_joint_init<1>(p, w);
+      hj_set_bit(w, RK_AJ_Y0, RK_AJF_INITIALIZED, false), hj_set_bit(w, RK_AJ_P1, RK_AJF_INITIALIZED, false);
+      hj_set_bit(w, RK_AJ_P2, RK_AJF_INITIALIZED, false), hj_set_bit(w, RK_AJ_R0, RK_AJF_INITIALIZED, false);
+      hj_set_bit(w, RK_AJ_P3, RK_AJF_INITIALIZED, false);
+      state = 1u;
+    } else if(state == 2u) { // exec_move_mechend :79-94
+      if(cnt < 500u) {
+        hj_move_mechend<1>(p, w);
+        hj_move_mechend<4>(p, w);
+        cnt++;
+      } else if(cnt == 500u) state = 3u, cnt = 0u;
+    } else if(state == 3u) { // exec_resetangle :100-109
+      hj_reset_angle<1>(p, w), hj_reset_angle<2>(p, w), hj_reset_angle<3>(p, w), hj_reset_angle<4>(p, w);
+      state = 4u;
+    } else if(state == 4u) { // exec_move_initpos :115-143
+      bool all = hj_init_ramp<0>(p, w);
+      all &= hj_init_ramp<1>(p, w);
+      all &= hj_init_ramp<2>(p, w);
+      all &= hj_init_ramp<3>(p, w);
+      all &= hj_init_ramp<4>(p, w);
+      if(all) state = 5u;
+    } else if(state == 5u) comp = RK_AS_FSM_IS_COMP;
+  } else if(mode == RK_ADH_MODE_INIT_POS_MOVE) {
+    if(state == 0u) {
+      hj_ipm_init<0>(p, w, hw), hj_ipm_init<1>(p, w, hw), hj_ipm_init<2>(p, w, hw), hj_ipm_init<3>(p, w, hw), hj_ipm_init<4>(p, w, hw);
+      state = 1u;
+    } else if(state == 2u) { // exec_move_initpos :73-95
+      bool all = hj_ramp_axis<0>(p, w, u2f(hw[RK_HS_VEL_DIR + 0]));
+      all &= hj_ramp_axis<1>(p, w, u2f(hw[RK_HS_VEL_DIR + 1]));
+      all &= hj_ramp_axis<2>(p, w, u2f(hw[RK_HS_VEL_DIR + 2]));
+      all &= hj_ramp_axis<3>(p, w, u2f(hw[RK_HS_VEL_DIR + 3]));
+      all &= hj_ramp_axis<4>(p, w, u2f(hw[RK_HS_VEL_DIR + 4]));
+      if(all) state = 3u;
+    } else if(state == 3u) comp = RK_AS_FSM_IS_COMP;
+  }
+  hw[RK_HS_STATE]    = state | comp | (mode << 16);
+  hw[RK_HS_WAIT_CNT] = cnt;
+}
+
+// JointMgServo::update on the word block: all four branches  AD_joint_mg_servo.cpp:50-73
+RK_DEV void hj_mg_update(const rk_adt_params_t &p, uint32_t *w, const float *s_sin) {
+  const uint32_t b = hj_flag(w, RK_AJ_P1);
+  const bool     on = (b & RK_AJF_TORQUE_ON) != 0, prev = (b & RK_AJF_TORQUE_PREV) != 0, ini = (b & RK_AJF_INITIALIZED) != 0;
+  const float    tgt = u2f(AJW(w, RK_AJ_P1, RK_AJ_RAW_TGT));
+  uint32_t      *c = w + RK_AS_MG_CTRL;
+  w[RK_AS_MG_TX + 2] = 0u;
+  if(prev && !on) { // pos_ctrl_.reset(): everything but the gains
+    c[0] = 0u, c[1] = 0u, c[2] = 0u, c[3] = 0u, c[4] = 0u, c[5] = 0u, c[6] = 0u;
+  } else if(on && ini) { // subproc_posctrl :136-149
+    const float    v  = fabsf(fmul(fdiv(fsub(tgt, u2f(w[RK_AS_MG_PRE_TGT])), p.ctrl_time_s[RK_AJ_P1]), -10.0f));
+    const uint32_t vl = (uint32_t)f2i_x86((v > 1800.0f) ? 1800.0f : v) & 0xFFFFu;
+    w[RK_AS_MG_TX]     = 0xA4u | (vl << 16);
+    w[RK_AS_MG_TX + 1] = (uint32_t)f2i_x86(fmul(tgt, -100.0f * 10.0f));
+    w[RK_AS_MG_TX + 2] = 1u;
+  } else { // subproc_torquectrl :104-134 (torque off: InitGain first -- set_VelLpf_CutOff resets the IIR)
+    if(!on) c[7] = 1u, c[2] = 0u, c[3] = 0u;
+    const float freq = fdiv(1.0f, p.ctrl_time_s[RK_AJ_P1]), dt = fdiv(1.0f, freq), lpf = 10.0f;
+    const float den  = fadd(fmul(2.0f, freq), lpf);
+    const float A1 = fdiv(fsub(fmul(2.0f, freq), lpf), den), B0 = fdiv(lpf, den);
+    const float pg = c[7] ? 0.01f : 0.0f, ig = 0.0f, dg = 0.0f, ilim = 0.0f;
+    const float now = u2f(AJW(w, RK_AJ_P1, RK_AJ_RAW_NOW)), curlim = u2f(AJW(w, RK_AJ_P1, RK_AJ_CURLIM));
+    const float err = fsub(tgt, now);
+    const float x   = fmul(fsub(now, u2f(c[0])), freq);
+    const float y   = fadd(fadd(fmul(A1, u2f(c[2])), fmul(B0, x)), fmul(B0, u2f(c[3])));
+    float integ     = fadd(u2f(c[1]), fmul(fmul(ig, dt), err));
+    integ           = (integ >= ilim) ? ilim : ((integ <= -ilim) ? -ilim : integ);
+    float iq        = fsub(fadd(fmul(pg, err), integ), fmul(dg, y));
+    c[0] = f2u(now), c[1] = f2u(integ), c[2] = f2u(y), c[3] = f2u(x), c[4] = f2u(tgt), c[5] = f2u(err), c[6] = f2u(iq);
+    if(ini) iq = fsub(iq, fmul(0.05f, arm_sin(s_sin, fmul(fsub(now, u2f(AJW(w, RK_AJ_P1, RK_AJ_OFS))), RK_DEG2RAD))));
+    iq = (iq > curlim) ? curlim : ((iq < -curlim) ? -curlim : iq);
+    const double C_A = 0.0000057204, C_B = -0.0000485371, d = (double)iq;
+    double       raw;
+    if(d >= 0) raw = __ddiv_rn(__dadd_rn(-C_B, (double)arm_sqrt(__double2float_rn(__dadd_rn(C_B * C_B, __dmul_rn(4.0 * C_A, d))))), 2.0 * C_A);
+    else raw = __ddiv_rn(__dsub_rn(C_B, (double)arm_sqrt(__double2float_rn(__dsub_rn(C_B * C_B, __dmul_rn(4.0 * C_A, d))))), 2.0 * C_A);
+    int32_t s = sext16(d2i_x86(__dmul_rn(-1.0, raw)));
+    s         = (s > 450) ? 450 : ((s < -450) ? -450 : s);
+    w[RK_AS_MG_TX] = 0xA1u, w[RK_AS_MG_TX + 1] = (uint32_t)s & 0xFFFFu, w[RK_AS_MG_TX + 2] = 1u;
+  }
+  hj_set_bit(w, RK_AJ_P1, RK_AJF_TORQUE_PREV, on);
+  w[RK_AS_MG_PRE_TGT] = f2u(tgt);
+}
+// JointMyBldcServo::update  AD_joint_mybldc_servo.cpp:7-36
+template <int SLOT> RK_DEV void hj_bldc_update(const rk_adt_params_t &p, uint32_t *w) {
+  constexpr int  k  = SLOT == 0 ? RK_AJ_DFL : SLOT == 1 ? RK_AJ_DFR : RK_AJ_P3;
+  const uint32_t b  = hj_flag(w, k);
+  const bool     on = (b & RK_AJF_TORQUE_ON) != 0, prev = (b & RK_AJF_TORQUE_PREV) != 0;
+  uint32_t      *q  = w + RK_AS_BLDC_TX0 + 4 * SLOT;
+  if(!on) {
+    q[0] = 0u, q[1] = 0u, q[2] = 0x8002u;
+  } else if(!prev) {
+    q[0] = 0u, q[1] = 0u, q[2] = 0x8001u;
+  } else {
+    const int32_t  a  = f2i_x86(fmul(fmul(fmul(u2f(AJW(w, k, RK_AJ_RAW_TGT)), p.gear_ratio[k]), p.motor_dir[k]), 65536.0f));
+    const uint32_t ms = (uint32_t)f2i_x86(fmul(p.ctrl_time_s[k], 1000.0f)) & 0xFFFFu;
+    const uint32_t cl = (uint32_t)f2i_x86(fmul(u2f(AJW(w, k, RK_AJ_CURLIM)), 256.0f)) & 0xFFFFu;
+    q[0] = (uint32_t)a, q[1] = ms | (cl << 16), q[2] = 0x8010u;
+  }
+  q[3] = 1u;
+  hj_set_bit(w, k, RK_AJF_TORQUE_PREV, on);
+}
+// JointIcsServo::update  AD_joint_ics_servo.cpp:5-29 over the ideal servo
+RK_DEV void hj_ics_update(const rk_adt_params_t &p, uint32_t *w) {
+  const uint32_t b = hj_flag(w, RK_AJ_Y0);
+  if(!(b & RK_AJF_CONNECTED)) return;
+  const int tgt_pos = ics_degPos100(f2i_x86(fmul(fmul(u2f(AJW(w, RK_AJ_Y0, RK_AJ_RAW_TGT)), p.motor_dir[RK_AJ_Y0]), 100.0f)));
+  if(tgt_pos == -1) return;
+  int now_pos;
+  if(b & RK_AJF_TORQUE_ON) {
+    if(tgt_pos > 11500 || tgt_pos < 3500) {
+      now_pos = -1;
+    } else {
+      w[RK_AS_ICS_POS] = (uint32_t)tgt_pos, w[RK_AS_ICS_SERVO] = (uint32_t)(tgt_pos - 7500);
+      now_pos          = tgt_pos;
+    }
+  } else {
+    w[RK_AS_ICS_POS] = 0xFFFFFFFFu;
+    now_pos          = (int)(int32_t)w[RK_AS_ICS_SERVO] + 7500;
+  }
+  AJW(w, RK_AJ_Y0, RK_AJ_RAW_NOW) = f2u(fmul(fmul((float)ics_posDeg100(now_pos), 0.01f), p.motor_dir[RK_AJ_Y0]));
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(128)
+adh_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, uint4 *__restrict__ hs, int64_t n, int K,
+                  const float *__restrict__ now, uint32_t *__restrict__ trace) {
+  __shared__ float s_sin[513];
+  stage_sin_table(s_sin);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  uint32_t w[RK_AS_WORDS], hw[RK_HS_WORDS];
+#pragma unroll
+  for(int pl = 0; pl < RK_AS_WORDS / 4; pl++) {
+    const uint4 v = ld_plane(state, n, pl, i);
+    w[4 * pl] = v.x, w[4 * pl + 1] = v.y, w[4 * pl + 2] = v.z, w[4 * pl + 3] = v.w;
+  }
+#pragma unroll
+  for(int pl = 0; pl < RK_HS_WORDS / 4; pl++) {
+    const uint4 v = ld_plane(hs, n, pl, i);
+    hw[4 * pl] = v.x, hw[4 * pl + 1] = v.y, hw[4 * pl + 2] = v.z, hw[4 * pl + 3] = v.w;
+  }
+#pragma unroll 1
+  for(int t = 0; t < K; t++) {
+    if(now) { // what the CAN rx callbacks stored since the last tick
+      const float *f = now + (int64_t)t * 4 * n + i;
+      AJW(w, RK_AJ_P1, RK_AJ_RAW_NOW) = f2u(__ldcs(f)), AJW(w, RK_AJ_DFL, RK_AJ_RAW_NOW) = f2u(__ldcs(f + n));
+      AJW(w, RK_AJ_DFR, RK_AJ_RAW_NOW) = f2u(__ldcs(f + 2 * n)), AJW(w, RK_AJ_P3, RK_AJ_RAW_NOW) = f2u(__ldcs(f + 3 * n));
+    }
+    hj_mode_update(p, w, hw);
+    hj_mg_update(p, w, s_sin);
+    hj_bldc_update<0>(p, w), hj_bldc_update<1>(p, w), hj_bldc_update<2>(p, w);
+    hj_ics_update(p, w);
+    if(TRACE) {
+      uint32_t *tr = trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i;
+      tr[0] = f2u(hj_get_tgt<0>(w)), tr[n] = f2u(hj_get_tgt<1>(w)), tr[2 * n] = f2u(hj_get_tgt<2>(w));
+      tr[3 * n] = f2u(hj_get_tgt<3>(w)), tr[4 * n] = f2u(hj_get_tgt<4>(w));
+      tr[5 * n] = w[RK_AS_MG_TX] >> 16, tr[6 * n] = w[RK_AS_MG_TX + 1];
+      tr[7 * n] = w[RK_AS_BLDC_TX0], tr[8 * n] = w[RK_AS_BLDC_TX0 + 4], tr[9 * n] = w[RK_AS_BLDC_TX0 + 8];
+      tr[10 * n] = w[RK_AS_ICS_POS];
+      tr[11 * n] = hw[RK_HS_STATE] & 0xFFu, tr[12 * n] = hw[RK_HS_WAIT_CNT];
+      tr[13 * n] = bldc_id_byte(w[RK_AS_BLDC_TX0 + 2]) | (bldc_id_byte(w[RK_AS_BLDC_TX0 + 6]) << 8) | (bldc_id_byte(w[RK_AS_BLDC_TX0 + 10]) << 16);
+      tr[14 * n] = 0u, tr[15 * n] = 0u;
+    }
+  }
+#pragma unroll
+  for(int pl = 0; pl < RK_AS_WORDS / 4; pl++) st_plane(state, n, pl, i, make_uint4(w[4 * pl], w[4 * pl + 1], w[4 * pl + 2], w[4 * pl + 3]));
+#pragma unroll
+  for(int pl = 0; pl < RK_HS_WORDS / 4; pl++) st_plane(hs, n, pl, i, make_uint4(hw[4 * pl], hw[4 * pl + 1], hw[4 * pl + 2], hw[4 * pl + 3]));
+}
+__global__ void __launch_bounds__(128) adh_mode_init_kernel(uint4 *__restrict__ hs, int64_t n, uint32_t mode) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  // ADTModeBase::init(): is_comp = false; doInit(): nowState = INIT, u16_wait_cnt_ = 0, flags / directions zeroed
+  st_plane(hs, n, 0, i, make_uint4(mode << 16, 0u, 0u, 0u));
+  st_plane(hs, n, 1, i, make_uint4(0u, 0u, 0u, 0u));
+  st_plane(hs, n, 2, i, make_uint4(0u, 0u, 0u, 0u));
+}
+
 __global__ void __launch_bounds__(128) adp_mode_init_kernel(uint4 *__restrict__ ps, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
@@ -917,6 +1208,43 @@ int rk_adp_cmd_status(const void *d_pstate, int64_t n, const uint32_t *d_id, int
 }
 
 // ---- single-instance handle: a batch of one over the same kernels ---------------------------
+size_t rk_adh_state_words(void) { return RK_HS_WORDS; }
+size_t rk_adh_state_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_HS_WORDS * 4u; }
+
+int rk_adh_mode_init(void *d_hstate, int64_t n, int mode, void *stream) {
+  if(n == 0) return RK_OK;
+  if(n < 0 || !d_hstate || ((uintptr_t)d_hstate & 15u) || (mode != RK_ADH_MODE_INIT && mode != RK_ADH_MODE_INIT_POS_MOVE)) {
+    set_error("rk_adh_mode_init: bad n / mode, or d_hstate NULL / not 16-byte aligned");
+    return RK_ERR_ARG;
+  }
+  if(int rc = require_device()) return rc;
+  adh_mode_init_kernel<<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_hstate, n, (uint32_t)mode);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_adh_update(const rk_adt_params_t *p, void *d_state, void *d_hstate, int64_t n, int32_t K, const float *d_now, uint32_t *d_trace,
+                  void *stream) {
+  if(n == 0 || K == 0) return RK_OK;
+  if(K < 0) {
+    set_error("rk_adh_update: K < 0");
+    return RK_ERR_ARG;
+  }
+  if(!d_hstate || ((uintptr_t)d_now & 3u) || ((uintptr_t)d_trace & 3u)) {
+    set_error("rk_adh_update: d_hstate NULL or misaligned d_now / d_trace");
+    return RK_ERR_ARG;
+  }
+  if(int rc = adt_check("rk_adh_update", d_state, d_hstate, n)) return rc;
+  rk_adt_params_t q;
+  if(p) q = *p;
+  else rk_adt_default_params(&q);
+  if(int rc = require_device()) return rc;
+  if(d_trace) adh_update_kernel<true><<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>(q, (uint4 *)d_state, (uint4 *)d_hstate, n, K, d_now, d_trace);
+  else adh_update_kernel<false><<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>(q, (uint4 *)d_state, (uint4 *)d_hstate, n, K, d_now, d_trace);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
 struct rk_adt {
   rk_adt_params_t p;
   uint32_t       *d_state, *d_tab, *d_seq, *d_misc; // d_misc: [0] id, [1] status, [2..6] targets
