@@ -593,7 +593,7 @@ def run_ours_full(a):
     regs_np, have_np = np.tile(regs_np, (1, 1, n // uniq)), np.tile(have_np, (1, n // uniq))
     seq_np = streams.arm_sequences(n, seed=seed, first=lo, seq_id=1, max_len=32)
     cmd_h = torch.from_numpy(cmd_np.view(np.int32).reshape(n_seg, n, 4)).pin_memory()
-    regs_h = torch.from_numpy(np.ascontiguousarray(regs_np[1:])).pin_memory()
+    regs_h = torch.from_numpy(streams.imu_cells(regs_np[1:])).pin_memory()  # two 128-bit cells per sample
     have_h = torch.from_numpy(np.ascontiguousarray(have_np[1:])).pin_memory()
     seq_h = torch.from_numpy(layout.aos_to_soa(seq_np).view(np.int32)).pin_memory()
     goal_d = torch.zeros((n, 2), dtype=torch.float32, device=dev)
@@ -605,7 +605,7 @@ def run_ours_full(a):
     yaws = [torch.zeros((n_slow, n), dtype=torch.float32, device=dev) for _ in range(lanes)]
     rings = [torch.zeros(layout.ACMD_WORDS * n, dtype=torch.int32, device=dev) for _ in range(lanes)]
     yaw_d = yaws[0]
-    boot = torch.from_numpy(np.ascontiguousarray(regs_np[:1])).to(dev)
+    boot = torch.from_numpy(streams.imu_cells(regs_np[:1])).to(dev)
     chunks = []
     for c in range(n_chunks):
         rb = RobotBatch(n, dev, arm_cmdtab=rings[c % lanes])

@@ -261,8 +261,9 @@ size_t rk_imt_state_words(void);
 size_t rk_imt_state_bytes(int64_t n);
 
 /* K fused IMU_IF_WT901C::update() calls (imu_if_wt901c.cpp:83-89) for n instances.
- *  d_regs      int16, sample u / register r / instance i at ((u*16)+r)*n + i  (16 SoA planes
- *              per sample: the sReg[] snapshot at the time update() runs)
+ *  d_regs      int16, the sReg[] snapshot at the time update() runs, in two 128-bit cells per sample like every
+ *              other block: register r (RK_IMT_REG_*) of sample u, instance i at ((u*2 + r/8)*n + i)*8 + r%8
+ *              (16-byte aligned; for n = 1 simply 16 consecutive registers per sample)
  *  d_have_quat uint8 [K][n] or NULL (= all 1): whether a quaternion frame arrived since the
  *              last call (isComComp(), :132-143); 0 -> is_error = true, data retained
  *  d_out       optional getDataLatest() after each update, as 128-bit planes like the state:
@@ -492,7 +493,7 @@ typedef struct rk_tick_rollout {
   int32_t slow_period;       /* vehicle ticks per IMU / arm tick (firmware: 10) */
   const rk_vdt_cmd_t *d_cmd; /* vehicle commands, as rk_vdt_rollout_t */
   int32_t n_seg, seg_len;
-  const int16_t *d_regs;     /* IMU samples [n_slow][16][n], n_slow = ceil(K / slow_period) */
+  const int16_t *d_regs;     /* IMU samples as rk_imt_update takes them (two 128-bit cells each), n_slow = ceil(K / slow_period) */
   const uint8_t *d_have_quat;/* [n_slow][n] or NULL */
   float *d_yaw;              /* scratch, n_slow * n floats: the yaw stream (radians) */
   const float *d_goal;       /* optional cost epilogue, as rk_vdt_rollout_t */

@@ -124,7 +124,7 @@ void ref_imt_export(void *h, uint32_t *words) { export_state((IMU_IF_WT901C *)h,
 void ref_imt_import(void *h, const uint32_t *words) { import_state((IMU_IF_WT901C *)h, words); }
 
 /* Same contract as rk_imt_update() on HOST arrays: K updates of instances [i0,i1).
- * regs: int16 [K][16][n] (sample u, register r, instance i at ((u*16)+r)*n+i);
+ * regs: int16 in two 128-bit cells per sample (register r of sample u, instance i at ((u*2 + r/8)*n + i)*8 + r%8);
  * have_quat: uint8 [K][n] or NULL; out: Data planes [K][4][n] float4 or NULL; do_init: run init() with the
  * first sample instead of update(). */
 void ref_imt_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, const int16_t *regs,
@@ -139,7 +139,7 @@ void ref_imt_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, 
     }
     for(int u = 0; u < K; u++) {
       int16_t r[16];
-      for(int k = 0; k < 16; k++) r[k] = regs[((int64_t)u * 16 + k) * n + i];
+      for(int k = 0; k < 16; k++) r[k] = regs[(((int64_t)u * 2 + k / 8) * n + i) * 8 + k % 8];
       int hq = have_quat ? have_quat[(int64_t)u * n + i] : 1;
       if(do_init && u == 0) {
         push_sample(r, 1);

@@ -593,7 +593,7 @@ void orc_imt_update(uint32_t *state, int64_t n, int64_t i0, int64_t i1, int K, c
     for(u = 0; u < K; u++) {
       int16_t r[16];
       int     hq = have_quat ? have_quat[(int64_t)u * n + i] : 1;
-      for(k = 0; k < 16; k++) r[k] = regs[((int64_t)u * 16 + k) * n + i];
+      for(k = 0; k < 16; k++) r[k] = regs[(((int64_t)u * 2 + k / 8) * n + i) * 8 + k % 8]; /* two 128-bit cells per sample */
       if(do_init && u == 0) { /* IMU_IF_WT901C::init  :63-77 (getDataImmediately -> updateData, then latch) */
         imu_update_data(qi, r, d);
         for(k = 0; k < 4; k++) qi[k] = r[RK_IMT_REG_Q0 + k] / 32768.0f;

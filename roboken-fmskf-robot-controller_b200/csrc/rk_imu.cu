@@ -1,8 +1,8 @@
 // rk_imu.cu -- IMU_IF_WT901C::update()/updateData()/init() batched (src/Imu/imu_if_wt901c.cpp).
 //
 // Streaming, HBM-bound form: one thread per IMU, q_init and the readable Data page held in
-// registers across the K fused updates; per update 32 B of registers in (16 coalesced int16
-// planes) and, when the caller wants every sample's output, 64 B out (four 128-bit stores).
+// registers across the K fused updates; per update 32 B of registers in (two 128-bit cells, the next
+// update in flight) and, when the caller wants every sample's output, 64 B out (four 128-bit stores).
 #include <string.h>
 
 #include "rk_common.cuh"
@@ -58,11 +58,26 @@ imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__
     }
   }
   uint32_t flags = ld_plane(state, n, 5, i).x;
+  // the register snapshot is two 128-bit cells; the loads of update u + 1 are in flight while update u is
+  // computed and stored
+  const uint4 *src = (const uint4 *)regs + i;
+  uint4        c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
+  bool         nhq = true;
+  if(K > 0) {
+    c0 = __ldcs(src), c1 = __ldcs(src + n);
+    nhq = have_quat ? (__ldcs(have_quat + i) != 0) : true;
+  }
   for(int u = 0; u < K; u++) {
-    int r[16];
+    const uint32_t rw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    int            r[16];
 #pragma unroll
-    for(int k = 0; k < 16; k++) r[k] = (int)__ldcs(regs + ((int64_t)u * 16 + k) * n + i);
-    const bool hq = have_quat ? (__ldcs(have_quat + (int64_t)u * n + i) != 0) : true;
+    for(int k = 0; k < 8; k++) r[2 * k] = lo16(rw[k]), r[2 * k + 1] = hi16(rw[k]);
+    const bool hq = nhq;
+    if(u + 1 < K) {
+      const uint4 *nx = src + (int64_t)(u + 1) * 2 * n;
+      c0 = __ldcs(nx), c1 = __ldcs(nx + n);
+      nhq = have_quat ? (__ldcs(have_quat + (int64_t)(u + 1) * n + i) != 0) : true;
+    }
     if(do_init && u == 0) { // IMU_IF_WT901C::init  :63-77
       imu_update_data(qi, r, cur);
       const float S = 1.0f / 32768.0f;
@@ -295,8 +310,8 @@ int rk_imt_update(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, co
 int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
                       float *d_yaw_rad, int do_init, void *stream) {
   if(n == 0 || K == 0) return RK_OK;
-  if(n < 0 || K < 0 || !d_regs) {
-    set_error("rk_imt_update: bad n/K/regs");
+  if(n < 0 || K < 0 || !d_regs || ((uintptr_t)d_regs & 15u)) {
+    set_error("rk_imt_update: bad n / K, or d_regs NULL / not 16-byte aligned");
     return RK_ERR_ARG;
   }
   if(!d_state || ((uintptr_t)d_state & 15u) || ((uintptr_t)d_out & 15u)) {

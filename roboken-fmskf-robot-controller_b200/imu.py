@@ -21,9 +21,9 @@ class ImuBatch:
         self.parser = None  # WIT serial parser block (RK_IP_*), allocated by the first feed_bytes()
 
     def update(self, regs, have_quat=None, out=None, do_init=False, stream=None):
-        """regs: int16 [K, 16, n]; have_quat: uint8 [K, n] or None; out: float32 [K, 4, n, 4] or
+        """regs: int16 [K, 2, n, 8] (two 128-bit cells per sample, streams.imu_cells); have_quat: uint8 [K, n] or None; out: float32 [K, 4, n, 4] or
         None (IMU_IF_WT901C::update / ::init when do_init)."""
-        assert regs.is_cuda and regs.dtype == torch.int16 and regs.is_contiguous() and regs.shape[1:] == (16, self.n)
+        assert regs.is_cuda and regs.dtype == torch.int16 and regs.is_contiguous() and tuple(regs.shape[1:]) == (2, self.n, 8)
         K = regs.shape[0]
         if have_quat is not None:
             assert have_quat.is_cuda and have_quat.dtype == torch.uint8 and tuple(have_quat.shape) == (K, self.n)

@@ -139,6 +139,13 @@ def imu_samples(n, n_upd, seed=0x5EED, first=0, drop_every=64):
     return np.ascontiguousarray(regs), np.ascontiguousarray(have)
 
 
+def imu_cells(regs):
+    """Register snapshots int16 [K, 16, n] -> the two-128-bit-cells-per-sample layout rk_imt_update takes:
+    int16 [K, 2, n, 8] (register r of sample u, IMU i at ((u*2 + r//8)*n + i)*8 + r%8)."""
+    K, _, n = regs.shape
+    return np.ascontiguousarray(regs.reshape(K, 2, 8, n).transpose(0, 1, 3, 2))
+
+
 def arm_sequences(n, seed=0x5EED, first=0, max_len=32, min_len=2, seq_id=1, dt_zero_every=4):
     """C4 command sequences: one PosCmdSeq per arm as an AoS slot image, uint32 [n, 260]
     (word 0 u32_id, 1 u8_cmd_seq_len, 2-3 zero, then 32 x {u32_dt_ms, fl_tgt_pos_deg[5], 0, 0};

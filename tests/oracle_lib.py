@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 import roboken_fmskf_robot_controller_b200 as rk
-from roboken_fmskf_robot_controller_b200 import _cabi, layout
+from roboken_fmskf_robot_controller_b200 import _cabi, layout, streams
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE = os.path.join(ROOT, "oracle")
@@ -188,14 +188,16 @@ def run_task_ref(state_soa, n, ro, yaw_deg):
 def imu_port(state_soa, n, regs, have=None, want_out=False, do_init=False):
     K = regs.shape[0]
     out = np.zeros((K, 4, n, 4), dtype=np.uint32) if want_out else None
-    port().orc_imt_update(_ptr(state_soa), n, 0, n, K, _ptr(regs), _ptr(have), _ptr(out), int(do_init))
+    cells = streams.imu_cells(regs)  # regs: logical int16 [K, 16, n]
+    port().orc_imt_update(_ptr(state_soa), n, 0, n, K, _ptr(cells), _ptr(have), _ptr(out), int(do_init))
     return out
 
 
 def imu_ref(state_soa, n, regs, have=None, want_out=False, do_init=False):
     K = regs.shape[0]
     out = np.zeros((K, 4, n, 4), dtype=np.uint32) if want_out else None
-    ref("libref_imu.so").ref_imt_rollout(_ptr(state_soa), n, 0, n, K, _ptr(regs), _ptr(have), _ptr(out), int(do_init))
+    cells = streams.imu_cells(regs)
+    ref("libref_imu.so").ref_imt_rollout(_ptr(state_soa), n, 0, n, K, _ptr(cells), _ptr(have), _ptr(out), int(do_init))
     return out
 
 

@@ -19,7 +19,7 @@ def gpu_imu(n, regs, have, state=None, do_init=False, want_out=True):
         ib.load_state_soa(state)
     K = regs.shape[0]
     out = torch.zeros((K, 4, n, 4), dtype=torch.float32, device=DEV) if want_out else None
-    ib.update(torch.from_numpy(regs).to(DEV), None if have is None else torch.from_numpy(have).to(DEV), out, do_init)
+    ib.update(torch.from_numpy(streams.imu_cells(regs)).to(DEV), None if have is None else torch.from_numpy(have).to(DEV), out, do_init)
     torch.cuda.synchronize()
     return ib.state.cpu().numpy().view(np.uint32), (out.cpu().numpy().view(np.uint32) if want_out else None)
 

@@ -89,7 +89,7 @@ def test_clean_wire_equals_register_kernel():
     wire, nb = streams.imu_wire_clean(regs)
     a = ImuBatch(n, DEV)
     oa = torch.zeros((K, 4, n, 4), dtype=torch.float32, device=DEV)
-    a.update(torch.from_numpy(regs).to(DEV), None, oa, True)
+    a.update(torch.from_numpy(streams.imu_cells(regs)).to(DEV), None, oa, True)
     b = ImuBatch(n, DEV)
     ob = gpu_feed(b, wire, nb, True)
     np.testing.assert_array_equal(oa.cpu().numpy().view(np.uint32), ob)

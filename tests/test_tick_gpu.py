@@ -25,11 +25,11 @@ def gpu_full(n, steps, slow, cmd, regs, have, seq, trace=True, goal=None):
     rb = RobotBatch(n, DEV)
     rb.reset()
     # IMU boot: IMU_IF_WT901C::init() consumes the first sample; arm: one sequence pushed
-    rb.imu.update(torch.from_numpy(regs[:1]).to(DEV), None, None, do_init=True)
+    rb.imu.update(torch.from_numpy(streams.imu_cells(regs[:1])).to(DEV), None, None, do_init=True)
     rb.arm.push_cmdseq(torch.from_numpy(layout.aos_to_soa(seq).view(np.int32)).to(DEV))
     n_slow = (steps + slow - 1) // slow
     cmd_d = torch.from_numpy(cmd.view(np.int32).reshape(cmd.shape[0], n, 4)).to(DEV)
-    regs_d = torch.from_numpy(np.ascontiguousarray(regs[1 : 1 + n_slow])).to(DEV)
+    regs_d = torch.from_numpy(streams.imu_cells(regs[1 : 1 + n_slow])).to(DEV)
     have_d = torch.from_numpy(np.ascontiguousarray(have[1 : 1 + n_slow])).to(DEV)
     yaw_d = torch.zeros((n_slow, n), dtype=torch.float32, device=DEV)
     vtr = torch.zeros((steps, 16, n), dtype=torch.int32, device=DEV) if trace else None

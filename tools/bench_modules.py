@@ -44,7 +44,7 @@ def bench_imu(a, dev):
     n, K = a.n, a.imu_updates
     uniq = min(n, 1 << 16)
     regs, have = streams.imu_samples(uniq, K, seed=3, drop_every=64)
-    regs_d = torch.from_numpy(np.tile(regs, (1, 1, n // uniq))).to(dev)
+    regs_d = torch.from_numpy(np.tile(streams.imu_cells(regs), (1, 1, n // uniq, 1))).to(dev)
     have_d = torch.from_numpy(np.tile(have, (1, n // uniq))).to(dev)
     ib = ImuBatch(n, dev)
     ib.update(regs_d[:1].contiguous(), None, None, do_init=True)
