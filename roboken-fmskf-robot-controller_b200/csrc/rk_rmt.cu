@@ -32,9 +32,13 @@ RK_DEV float my_atanf(const AtanTab &s, float x) {
   if(x == 0.0f) {
     r = 0.0f;
   } else if(x <= s.delimit[26]) { // first i in 1..26 with x <= delimit[i]
-    int i = 1;
+    int i = 1, hi = 26; // the delimiters ascend, so the firmware's linear scan is a lower bound: 5 halvings of 26
 #pragma unroll
-    for(int j = 1; j < 26; j++) i += (x > s.delimit[j]) ? 1 : 0;
+    for(int st = 0; st < 5; st++) {
+      const int  mid = (i + hi) >> 1;
+      const bool le  = x <= s.delimit[mid];
+      hi = le ? mid : hi, i = le ? i : mid + 1;
+    }
     const float index = fadd((float)(24 * (i - 1)), fdiv(fsub(x, s.delimit[i - 1]), s.width[i - 1]));
     const int   ii    = __float2int_rz(index);
     const float dec   = fsub(index, (float)ii);
