@@ -19,11 +19,14 @@ constexpr int kRolloutThreads = 128;
 // the yaw the ISR hands to set_now_yaw_world(): the float stream, or formed from the WT901C Yaw register exactly as
 // IMU_IF_WT901C::updateData (imu_if_wt901c.cpp:100: reg / 32768.0f * 180.0f; the division by 2^15 is exact) ->
 // getYawDate() -> mymath::deg2rad (VD_task_main.cpp:368) would
-RK_DEV float load_yaw(const rk_vdt_rollout_t &a, int64_t idx) {
-  if(a.d_yaw) return __ldcs(a.d_yaw + idx);
-  const float reg = (float)(int)__ldcs(a.d_yaw_reg + idx);
-  return fmul(fmul(fmul(reg, 1.0f / 32768.0f), 180.0f), RK_DEG2RAD);
+RK_DEV uint32_t load_yaw_raw(const rk_vdt_rollout_t &a, int64_t idx) { // the load only: nothing here waits for it
+  return a.d_yaw ? __float_as_uint(__ldcs(a.d_yaw + idx)) : (uint32_t)(int)__ldcs(a.d_yaw_reg + idx);
 }
+RK_DEV float yaw_of_raw(const rk_vdt_rollout_t &a, uint32_t raw) {
+  if(a.d_yaw) return __uint_as_float(raw);
+  return fmul(fmul(fmul((float)(int)raw, 1.0f / 32768.0f), 180.0f), RK_DEG2RAD);
+}
+RK_DEV float load_yaw(const rk_vdt_rollout_t &a, int64_t idx) { return yaw_of_raw(a, load_yaw_raw(a, idx)); }
 
 template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(kRolloutThreads)
@@ -145,14 +148,14 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
   sched_init(sch, a);
   // The yaw sample for the next boundary is fetched one period ahead, so its HBM latency
   // hides behind yaw_period ticks of arithmetic instead of stalling every warp at once.
-  float yaw_pf = has_yaw ? load_yaw(a, i) : 0.0f;
-  auto  take_yaw = [&](float &pth) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
-    pth = yaw_pf;
+  uint32_t yaw_pf = has_yaw ? load_yaw_raw(a, i) : 0u; // raw word: converted when taken, so the load stays in flight
+  auto     take_yaw = [&](float &pth) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
+    pth = yaw_of_raw(a, yaw_pf);
     yaw_trig(s_tab, pth, cth, sth);
     yk++;
     if(yk < a.n_yaw) {
       next_yaw += a.yaw_period;
-      yaw_pf = load_yaw(a, (int64_t)yk * n + i);
+      yaw_pf = load_yaw_raw(a, (int64_t)yk * n + i);
     } else {
       next_yaw = INT_MAX;
     }
