@@ -87,64 +87,58 @@ rmt_guard_kernel(const rk_rmt_params_t p, uint4 *__restrict__ state, int64_t n, 
       const uint4 *nx = src + (int64_t)(u + 1) * 3 * n;
       c0 = __ldcs(nx), c1 = __ldcs(nx + n), c2 = __ldcs(nx + 2 * n);
     }
-    // rclc_executor_spin_some(): the subscription callbacks  :159-248
-    uint32_t id = MSG_NONE, m_cmd = 0u, m_time = 0u, m_speed = 0u;
-    float    vx = 0.0f, vy = 0.0f, vth = 0.0f;
-    bool     updated = true;
-    switch(a.x) {
-    case RK_ROS_MECANUM_CMD: id = MSG_DIR, m_cmd = a.y, m_time = a.z, m_speed = a.w; break;
-    case RK_ROS_MECANUM_CONT:
-      id = MSG_CONT, m_time = a.y;
-      vx = __double2float_rn(u2d(b.x, b.y)), vy = __double2float_rn(u2d(b.z, b.w)), vth = __double2float_rn(u2d(c.x, c.y));
-      break;
-    case RK_ROS_CMD_VEL:
-      id = MSG_CONT, m_time = 500u;
-      vx = __double2float_rn(__dmul_rn(u2d(b.x, b.y), 1000.0)), vy = __double2float_rn(__dmul_rn(u2d(b.z, b.w), 1000.0));
-      vth = __double2float_rn(u2d(c.x, c.y));
-      break;
-    case RK_ROS_COMMAND: // a Command always stops the vehicle, then switches the manager's mode  :162-201
-      id = MSG_DIR, m_cmd = RK_DIR_MOVE_STOP, m_time = 1u, m_speed = 0u;
-      cmd_status = a.y;
-      if(a.y == 10u) ignore = ignore ? 0u : 1u;                               // SWITCH_FLOOR_SENSOR
-      else if(!(a.y == 0u || a.y == 1u || a.y == 2u || a.y == 4u)) cmd_status = 0xFFu; // QUIT_PG and the rest: UNKNOWN_CMD
-      break;
-    default: updated = false; break;
+    // rclc_executor_spin_some(): the subscription callbacks  :159-248.  The record kind differs from lane to lane,
+    // so everything but the double-precision conversions and the arctangent is selects, not branches.
+    const uint32_t kind = a.x;
+    const bool k_cmd = kind == RK_ROS_MECANUM_CMD, k_cont = kind == RK_ROS_MECANUM_CONT, k_vel = kind == RK_ROS_CMD_VEL;
+    const bool k_command = kind == RK_ROS_COMMAND; // a Command always stops the vehicle, then switches the manager's mode :162-201
+    const bool updated = k_cmd || k_cont || k_vel || k_command;
+    uint32_t   id = (k_cont || k_vel) ? MSG_CONT : MSG_DIR; // not updated: the idle message MOVE_DIR / MOVE_STOP / 0 / 0
+    uint32_t   m_cmd = k_cmd ? a.y : (uint32_t)RK_DIR_MOVE_STOP, m_speed = k_cmd ? a.w : 0u;
+    uint32_t   m_time = k_cmd ? a.z : (k_cont ? a.y : (k_vel ? 500u : (k_command ? 1u : 0u)));
+    float      vx = 0.0f, vy = 0.0f, vth = 0.0f;
+    if(k_cont || k_vel) {
+      double dx = u2d(b.x, b.y), dy = u2d(b.z, b.w);
+      if(k_vel) dx = __dmul_rn(dx, 1000.0), dy = __dmul_rn(dy, 1000.0);
+      vx = __double2float_rn(dx), vy = __double2float_rn(dy), vth = __double2float_rn(u2d(c.x, c.y));
+    }
+    {
+      const bool known = a.y == 0u || a.y == 1u || a.y == 2u || a.y == 4u || a.y == 10u; // the rest: UNKNOWN_CMD
+      cmd_status = k_command ? (known ? a.y : 0xFFu) : cmd_status;
+      ignore     = (k_command && a.y == 10u) ? (ignore ? 0u : 1u) : ignore; // SWITCH_FLOOR_SENSOR
     }
     bool exist = updated; // :484-505
-    if(updated) abort_v = 0u;
-    else id = MSG_DIR;    // the idle message: MOVE_DIR / MOVE_STOP / 0 / 0
+    abort_v    = updated ? 0u : abort_v;
     // floor sensors :507-542 -- bytes rForward, lForward, rBack, lBack | right, left, forward, back
     uint32_t f0 = c.z, f1 = c.w;
     {
       const uint32_t nf = __popc(__vcmpeq4(f0, 0u) & 0x01010101u) + __popc(__vcmpeq4(f1, 0u) & 0x01010101u);
       const uint32_t nw = __popc(__vcmpeq4(f0, 0x02020202u) & 0x01010101u) + __popc(__vcmpeq4(f1, 0x02020202u) & 0x01010101u);
-      if(nf >= 5u || nw >= 5u || ignore) f0 = 0x01010101u, f1 = 0x01010101u;
+      const bool     all_floor = nf >= 5u || nw >= 5u || ignore != 0u;
+      f0 = all_floor ? 0x01010101u : f0, f1 = all_floor ? 0x01010101u : f1;
     }
     const uint32_t rF = f0 & 0xFFu, lF = (f0 >> 8) & 0xFFu, rB = (f0 >> 16) & 0xFFu, lB = f0 >> 24;
     const uint32_t right = f1 & 0xFFu, left = (f1 >> 8) & 0xFFu, fwd = (f1 >> 16) & 0xFFu, back = f1 >> 24;
-    if(cmd_status == 2u) { // MOVE_START: leave a wall (an opponent)  :546-577
-      uint32_t dir = 0u;
-      if(fwd == WALL) dir = RK_DIR_GO_BACK, abort_v |= 1u << 0;
-      else if(back == WALL) dir = RK_DIR_GO_FORWARD, abort_v |= 1u << 1;
-      else if(left == WALL) dir = RK_DIR_GO_RIGHT, abort_v |= 1u << 2;
-      else if(right == WALL) dir = RK_DIR_GO_LEFT, abort_v |= 1u << 3;
-      if(dir) id = MSG_DIR, m_cmd = dir, m_time = p.wall_leave_time_ms, m_speed = p.wall_leave_speed_mmps, exist = true;
+    { // MOVE_START: leave a wall (an opponent)  :546-577 -- the first of forward, back, left, right that sees one
+      const bool     w_f = fwd == WALL, w_b = back == WALL, w_l = left == WALL, w_r = right == WALL;
+      const uint32_t dir = w_f ? RK_DIR_GO_BACK : (w_b ? RK_DIR_GO_FORWARD : (w_l ? RK_DIR_GO_RIGHT : (w_r ? RK_DIR_GO_LEFT : 0u)));
+      const uint32_t bit = w_f ? 1u : (w_b ? 2u : (w_l ? 4u : (w_r ? 8u : 0u)));
+      const bool     leave = cmd_status == 2u && dir != 0u;
+      abort_v |= leave ? bit : 0u;
+      id = leave ? (uint32_t)MSG_DIR : id, m_cmd = leave ? dir : m_cmd, m_time = leave ? p.wall_leave_time_ms : m_time;
+      m_speed = leave ? p.wall_leave_speed_mmps : m_speed, exist = exist || leave;
     }
-    if(id == MSG_DIR) { // :581-673
-      uint32_t need = FLOOR, bits = 0u;
-      switch(m_cmd) {
-      case RK_DIR_GO_FORWARD: need = fwd, bits = 1u << 8; break;
-      case RK_DIR_GO_BACK: need = back, bits = 1u << 9; break;
-      case RK_DIR_GO_RIGHT: need = right, bits = 1u << 11; break;
-      case RK_DIR_GO_LEFT: need = left, bits = 1u << 10; break;
-      case RK_DIR_GO_RIGHT_FORWARD: need = rF, bits = (1u << 8) | (1u << 11); break;
-      case RK_DIR_GO_LEFT_FORWARD: need = lF, bits = (1u << 8) | (1u << 10); break;
-      case RK_DIR_GO_RIGHT_BACK: need = rB, bits = (1u << 9) | (1u << 11); break;
-      case RK_DIR_GO_LEFT_BACK: need = lB, bits = (1u << 9) | (1u << 10); break;
-      default: break;
-      }
-      if(need != FLOOR) m_cmd = RK_DIR_MOVE_STOP, m_time = 1u, m_speed = 0u, exist = true, abort_v |= bits;
-    } else { // REQ_MOVE_CONT_DIR :674-749
+    { // direction commands: the sensor a direction needs and the abort bits it raises  :581-673
+      // GO_FORWARD..GO_LEFT_BACK (1..8) -> sensor byte index 6,7,4,5,0,1,2,3 ; fllr_abort bits 8..11 as a nibble
+      const uint32_t k    = (m_cmd - 1u) & 7u;
+      const uint32_t sidx = (0x32105476u >> (4u * k)) & 7u;
+      const uint32_t need = (((sidx & 4u) ? f1 : f0) >> (8u * (sidx & 3u))) & 0xFFu;
+      const uint32_t bits = ((0x6A594821u >> (4u * k)) & 0xFu) << 8;
+      const bool     veto = id == MSG_DIR && m_cmd >= 1u && m_cmd <= 8u && need != FLOOR;
+      m_cmd = veto ? (uint32_t)RK_DIR_MOVE_STOP : m_cmd, m_time = veto ? 1u : m_time, m_speed = veto ? 0u : m_speed;
+      exist = exist || veto, abort_v |= veto ? bits : 0u;
+    }
+    if(id == MSG_CONT) { // REQ_MOVE_CONT_DIR :674-749
       const float ax = vx < 0.0f ? -vx : vx, ay = vy < 0.0f ? -vy : vy;
       if(!(ax < 0.01f && ay < 0.01f)) {
         const float vph = my_atan2f(s, vy, vx);
