@@ -350,6 +350,7 @@ def run_ours(a):
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = sharding.bind_to_gpu_numa(local_rank) if world > 1 else None  # pinned host tables local to the GPU's PCIe root
     _cabi.check(lib.rk_set_device(local_rank))
     if a.occupancy:
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_OCCUPANCY, a.occupancy))
@@ -501,7 +502,8 @@ def run_ours(a):
         e2e = {"value": world * n * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / K,
                "path": "rk_vdt_rollout() via ctypes; pinned host cmd+yaw tables H2D, state reset to power-on, "
-                       "cost vector D2H, double-buffered: H2D, rollout and D2H on three streams"}
+                       "cost vector D2H, double-buffered: H2D, rollout and D2H on three streams",
+               "host_numa_node": numa}
         launches += 0  # e2e launches are outside the `value` region; gpu_launches counts that region
 
     # ---- optional NCCL gather of the summary costs (outside the timed regions) --------------
@@ -569,6 +571,7 @@ def run_ours_full(a):
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = sharding.bind_to_gpu_numa(local_rank) if world > 1 else None  # pinned host tables local to the GPU's PCIe root
     _cabi.check(lib.rk_set_device(local_rank))
     if a.occupancy:
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_OCCUPANCY, a.occupancy))

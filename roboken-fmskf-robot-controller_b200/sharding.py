@@ -37,6 +37,29 @@ def init(backend=None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers it allocates
+    next (first touch) and the threads that drive the copies are local to the GPU's PCIe root.  Returns the node, or
+    None when the topology is not exposed (single socket, containers without sysfs): nothing is changed then."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def barrier():
     if dist.is_initialized():
         dist.barrier()
