@@ -47,6 +47,14 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
   Sched      sc;
   sched_init(sc, a);
 
+  // RK_SENSOR_STREAM: the four frames of tick t + 1 are in flight while tick t is computed
+  const unsigned long long *fsrc = reinterpret_cast<const unsigned long long *>(a.d_frames) + i;
+  uint64_t                  fpf[4] = {0, 0, 0, 0};
+  if(MODE == RK_SENSOR_STREAM && a.steps > 0) {
+#pragma unroll
+    for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + (int64_t)k * n);
+  }
+
   for(int t = 0; t < a.steps; t++) {
     sched_events(v, p, a, n, i, t, sc);
     if(t == next_yaw) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
@@ -57,15 +65,15 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
     }
     if(MODE != RK_SENSOR_HOLD) {
       const int32_t us = ((t + 1) * 1000) & 0x7FFF;
+      uint64_t      fr[4];
 #pragma unroll
-      for(int k = 0; k < 4; k++) {
-        uint64_t f;
-        if(MODE == RK_SENSOR_PLANT)
-          f = plant_frame(v.m[k]);
-        else
-          f = __ldcs(reinterpret_cast<const unsigned long long *>(a.d_frames) + ((int64_t)t * 4 + k) * n + i);
-        motor_rx(v.m[k], p.motor_dir[k], f, us);
+      for(int k = 0; k < 4; k++) fr[k] = (MODE == RK_SENSOR_PLANT) ? plant_frame(v.m[k]) : fpf[k];
+      if(MODE == RK_SENSOR_STREAM && t + 1 < a.steps) {
+#pragma unroll
+        for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + ((int64_t)(t + 1) * 4 + k) * n);
       }
+#pragma unroll
+      for(int k = 0; k < 4; k++) motor_rx(v.m[k], p.motor_dir[k], fr[k], us);
     }
     veh_update(v, p, d, cth, sth);
     if(TRACE) {

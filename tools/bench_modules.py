@@ -2,7 +2,7 @@
 """Kernel-level measurements of the two slow-rate modules (BASELINE configs[2] and [3]) -- one JSON
 line each, CUDA-event timed with inputs resident in HBM, roofline against MEASURED_PEAKS.json.
 
-    python tools/bench_modules.py [--n 1048576] [--imu-updates 64] [--arm-ticks 1000] [--reps 10] [--only imu|wire|guard|arm]
+    python tools/bench_modules.py [--n 1048576] [--imu-updates 64] [--arm-ticks 1000] [--reps 10] [--only imu|wire|guard|stream|arm]
 """
 import argparse
 import json
@@ -106,6 +106,31 @@ def bench_guard(a, dev):
                                    "algorithmic_bytes_per_cycle": per, "algorithmic_bytes_per_launch": nbytes}}), flush=True)
 
 
+def bench_stream(a, dev):
+    """rk_vdt_rollout in RK_SENSOR_STREAM mode: 32 B of M2006 feedback frames per vehicle tick from HBM."""
+    from roboken_fmskf_robot_controller_b200 import _cabi
+    from roboken_fmskf_robot_controller_b200.vehicle import VehicleBatch
+
+    n, T = min(a.n, 1 << 18), 200
+    uniq = min(n, 1 << 12)
+    fr = streams.vehicle_frames(uniq, T, seed=3)
+    fr_d = torch.from_numpy(np.tile(fr, (1, 1, n // uniq)).view(np.int64)).to(dev)
+    cmd = streams.vehicle_commands(n, 2, seed=3)
+    cmd_d = torch.from_numpy(cmd.view(np.int32).reshape(2, n, 4)).to(dev)
+    yaw_d = torch.from_numpy(streams.vehicle_yaw(n, T // 10, seed=3)).to(dev)
+    vb = VehicleBatch(n, dev)
+    args = vb.make_args(T, sensor_mode=_cabi.RK_SENSOR_STREAM, cmd=cmd_d, seg_len=100, yaw=yaw_d, yaw_period=10, frames=fr_d)
+    peak, src = hbm_peak()
+    ms = timed(lambda: vb.rollout_args(args), a.reps)
+    nbytes = n * (T * 32 + 2 * 448)
+    print(json.dumps({"kernel": "rk::vdt_rollout_kernel<RK_SENSOR_STREAM>", "workload": f"configs[1] streamed sensors: {n} vehicles x {T} ticks, 32 B of CAN frames per tick",
+                      "steps_per_s": n * T / (ms * 1e-3), "ms_per_launch": ms,
+                      "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "peak_source": src,
+                                   "algorithmic_bytes_per_tick": 32, "algorithmic_bytes_per_launch": nbytes,
+                                   "fp32_tflops": 183 * n * T / (ms * 1e-3) / 1e12}}), flush=True)
+
+
 def bench_arm(a, dev):
     n, K = a.n, a.arm_ticks
     seq = torch.from_numpy(layout.aos_to_soa(streams.arm_sequences(n, seed=0xC4, seq_id=9, max_len=32)).view(np.int32)).to(dev)
@@ -140,6 +165,8 @@ def main():
         bench_wire(a, dev)
     if a.only in ("", "guard"):
         bench_guard(a, dev)
+    if a.only in ("", "stream"):
+        bench_stream(a, dev)
     if a.only in ("", "arm"):
         bench_arm(a, dev)
 
