@@ -104,8 +104,9 @@ class CpuArm:
         self.kind = "reference" if os.path.exists(os.path.join(ol.ORACLE, "_ref", "libref_vdt.so")) else "port"
         self._inp = {}
 
-    def _run(self, n):
+    def _run(self, n, threads=None):
         a = self.a
+        threads = threads or self.threads
         if n not in self._inp:
             inp = self.wl.plant_inputs(n, a.ticks, seed=0x5EED, seg_len=a.seg_len, yaw_period=a.yaw_period)
             if getattr(a, "yaw_format", "rad") == "reg" and a.workload != "full":
@@ -118,9 +119,9 @@ class CpuArm:
         _, ro = self._inp[n]
         t0 = time.perf_counter()
         if self.kind == "reference":
-            self.ol.run_ref(None, n, ro, nthreads=self.threads)
+            self.ol.run_ref(None, n, ro, nthreads=threads)
         else:
-            self.ol.run_port(None, n, ro, nthreads=self.threads)
+            self.ol.run_port(None, n, ro, nthreads=threads)
         return time.perf_counter() - t0
 
     def calibrate(self, step_budget_s):
@@ -528,6 +529,9 @@ def run_ours(a):
         nc = arm.calibrate(a.cpu_seconds / 3.0)
         t = min(arm._run(nc) for _ in range(2))
         cpu = {"value": nc * T / t, "unit": UNIT, "cores": arm.threads, "kind": arm.kind, "sample": arm.sample_desc(nc)}
+        n1 = max(64, nc // (4 * arm.threads))  # the single-core figure SURVEY 8d asks for, on a quarter of one thread's share
+        arm._run(n1, threads=1)
+        cpu["single_core_value"] = n1 * T / arm._run(n1, threads=1)
 
     if rank == 0:
         line = {
