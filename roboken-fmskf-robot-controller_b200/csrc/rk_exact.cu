@@ -8,7 +8,7 @@
 //      x == 0 and |x| >= 2^-40 (their operand is a sum of wheel speeds derived from int16 rpm,
 //      which is 0 or >= 2^-34 in magnitude).
 //   2. fma(d, K_hi, d*K_lo) == (float)((double)d * OUT_RAD_PER_RAW_ANGLE * GEAR_RATIO_INV)
-//      for every integer |d| <= 8192.
+//      for every integer |d| <= 2^17 (the closed-loop plant needs |d| < 4096, recorded frames |d| <= 40960).
 //   3. plant_dang(r) == r * 8192 / 60000 (C truncation) for every int16 r.
 #include <mutex>
 #include <string.h>
@@ -45,8 +45,8 @@ __global__ void proof_small_kernel(ProofOut *out) {
   const double K    = (double)RK_OUT_RAD_PER_RAW_ANGLE * (double)RK_GEAR_RATIO_INV;
   const float  k_hi = __double2float_rn(K);
   const float  k_lo = __double2float_rn(K - (double)k_hi);
-  if(i <= 2 * 8192) {
-    const int   d   = i - 8192;
+  if(i <= 2 * 131072) { // |d| <= 2^17: every step rx_callback's int16 unwrap can produce, plant or recorded frames
+    const int   d   = i - 131072;
     const float ref = __double2float_rn(__dmul_rn(__dmul_rn((double)d, (double)RK_OUT_RAD_PER_RAW_ANGLE), (double)RK_GEAR_RATIO_INV));
     const float df  = (float)d;
     if(f2u(ref) != f2u(__fmaf_rn(df, k_hi, fmul(df, k_lo)))) atomicAdd(&out->mrad_fail, 1u);
@@ -85,7 +85,7 @@ bool fast_path_proven(const rk_vdt_params_t &p) {
   cudaMemcpy(d_out, h, sizeof(h), cudaMemcpyHostToDevice);
   const float cs[3] = {p.wheel_radius_mm, p.sqrtf2, p.wheel_l_mm};
   for(int k = 0; k < 3; k++) proof_div_kernel<<<148 * 16, 256>>>(cs[k], d_out + k);
-  proof_small_kernel<<<256, 256>>>(d_out + 3);
+  proof_small_kernel<<<1025, 256>>>(d_out + 3);
   cudaError_t e = cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost); // synchronises
   cudaFree(d_out);
   if(e != cudaSuccess) {

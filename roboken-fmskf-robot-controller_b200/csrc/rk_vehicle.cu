@@ -235,6 +235,117 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
   }
 }
 
+// -----------------------------------------------------------------------------------------
+// RK_SENSOR_STREAM on the packed fast tick: the same chunk structure as vdt_rollout_fast_kernel, the wheel
+// feedback decoded from the recorded frames (fast_tick2_stream); the four frames of tick t + 1 are in flight
+// while tick t is computed.  Command ticks, the last tick and threads outside the fast domain run the
+// transcription on the same frames.
+// -----------------------------------------------------------------------------------------
+template <bool TRACE, bool FFSAT>
+__global__ void __launch_bounds__(kFastThreads, 3)
+vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
+  constexpr int D0 = 1, D1 = 1, D2 = -1, D3 = -1;
+  __shared__ float s_tab[513];
+  stage_sin_table(s_tab);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+
+  Veh v;
+  load_veh(state, n, i, v);
+  const Derived d = derive(p);
+  FastConsts    fc;
+  {
+    fc.rcp_r = fdiv(1.0f, p.wheel_radius_mm), fc.rcp_s2 = fdiv(1.0f, p.sqrtf2), fc.rcp_l = fdiv(1.0f, p.wheel_l_mm);
+    const double K = (double)RK_OUT_RAD_PER_RAW_ANGLE * (double)RK_GEAR_RATIO_INV;
+    fc.k_hi        = __double2float_rn(K);
+    fc.k_lo        = __double2float_rn(K - (double)fc.k_hi);
+    fc.A1 = d.A1, fc.B0 = d.B0, fc.ki_dt = d.ki_dt, fc.s2l = d.s2l;
+    fc.neg_i_limit = -p.i_limit, fc.neg_ff_limit = -p.ff_limit;
+  }
+  float cth, sth;
+  yaw_trig(s_tab, v.pos[2], cth, sth);
+
+  const bool has_yaw  = (a.d_yaw != nullptr || a.d_yaw_reg != nullptr) && a.yaw_period > 0 && a.n_yaw > 0;
+  int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
+  const int  K        = a.steps;
+  Sched      sch;
+  sched_init(sch, a);
+  uint32_t yaw_pf = has_yaw ? load_yaw_raw(a, i) : 0u;
+  auto     take_yaw = [&](float &pth) {
+    pth = yaw_of_raw(a, yaw_pf);
+    yaw_trig(s_tab, pth, cth, sth);
+    yk++;
+    if(yk < a.n_yaw) {
+      next_yaw += a.yaw_period;
+      yaw_pf = load_yaw_raw(a, (int64_t)yk * n + i);
+    } else {
+      next_yaw = INT_MAX;
+    }
+  };
+  const unsigned long long *fsrc = reinterpret_cast<const unsigned long long *>(a.d_frames) + i;
+  uint64_t                  fpf[4]; // the frames of tick t
+#pragma unroll
+  for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + (int64_t)k * n);
+
+  int t = 0;
+  while(t < K) {
+    sched_events(v, p, a, n, i, t, sch);
+    // chunks are capped so the 32-bit per-chunk angle sum cannot overflow (|step| <= 40960)
+    const int t_end = min(min(min(sch.next_cmd, sched_fire_tick(v, a, sch)), K - 1), t + 32768);
+    if(t < t_end && fast_ok<D0, D1, D2, D3, true>(v, p)) {
+      const int   t0  = t;
+      float       pth = v.pos[2];
+      FastVeh2    f;
+      StreamSense ss;
+      to_fast2(v, f, p.ts, fc.B0);
+      stream_sense_load(ss, v);
+      const float nz = fmul(-0.0f, p.ts);
+      while(t < t_end) {
+        if(t == next_yaw) take_yaw(pth);
+        const int    t_stop = min(t_end, next_yaw);
+        const float2 cs = make_float2(cth, sth), sc = make_float2(sth, cth);
+#pragma unroll 2
+        for(; t < t_stop; t++) {
+          uint64_t fr[4];
+#pragma unroll
+          for(int k = 0; k < 4; k++) fr[k] = fpf[k];
+#pragma unroll
+          for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + ((int64_t)(t + 1) * 4 + k) * n); // t + 1 <= K - 1 inside a chunk
+          float vel[3], tgt[3];
+          fast_tick2_stream<FFSAT>(f, ss, fr, p, fc, cs, sc, nz, vel, tgt);
+          trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1],
+                           TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
+        }
+      }
+      v.pos[2] = pth;
+      from_fast2_stream(v, f, ss, t - t0);
+      sched_skip_to(v, a, sch, t);
+    } else {
+      if(t == next_yaw) take_yaw(v.pos[2]);
+      const int32_t us = ((t + 1) * 1000) & 0x7FFF;
+      uint64_t      fr[4];
+#pragma unroll
+      for(int k = 0; k < 4; k++) fr[k] = fpf[k];
+      if(t + 1 < K) {
+#pragma unroll
+        for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + ((int64_t)(t + 1) * 4 + k) * n);
+      }
+#pragma unroll
+      for(int k = 0; k < 4; k++) motor_rx(v.m[k], p.motor_dir[k], fr[k], us);
+      veh_update(v, p, d, cth, sth);
+      trace_row<TRACE>(a.d_trace, n, i, t, v.pos[0], v.pos[1], v.pos[2], v.vel, v.tgt, v.m[0].cur_tgt, v.m[1].cur_tgt,
+                       v.m[2].cur_tgt, v.m[3].cur_tgt, (a.task_period > 0) ? v.move_cnt : 0u);
+      t++;
+    }
+  }
+  store_veh(state, n, i, v);
+  if(a.d_cost != nullptr && a.d_goal != nullptr) {
+    const float2 g  = reinterpret_cast<const float2 *>(a.d_goal)[i];
+    const float  dx = fsub(v.pos[0], g.x), dy = fsub(v.pos[1], g.y);
+    a.d_cost[i]     = fadd(fmul(dx, dx), fmul(dy, dy));
+  }
+}
+
 // ---- small batched setters ------------------------------------------------------------
 __global__ void vdt_set_power_kernel(uint4 *state, int64_t n, const uint8_t *on) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -487,7 +598,22 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
       e = launch_rollout<RK_SENSOR_PLANT>(*p, d_state, n, *args, st);
     }
     break;
-  case RK_SENSOR_STREAM: e = launch_rollout<RK_SENSOR_STREAM>(*p, d_state, n, *args, st); break;
+  case RK_SENSOR_STREAM:
+    if(fast_path_usable(*p)) {
+      const unsigned grid  = (unsigned)((n + kFastThreads - 1) / kFastThreads);
+      const bool     ffsat = (p->ff_limit == 1.0f);
+      if(args->d_trace) {
+        if(ffsat) vdt_rollout_stream_fast_kernel<true, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+        else vdt_rollout_stream_fast_kernel<true, false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+      } else {
+        if(ffsat) vdt_rollout_stream_fast_kernel<false, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+        else vdt_rollout_stream_fast_kernel<false, false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+      }
+      e = cudaGetLastError();
+    } else {
+      e = launch_rollout<RK_SENSOR_STREAM>(*p, d_state, n, *args, st);
+    }
+    break;
   default: set_error("rk_vdt_rollout: bad sensor_mode %d", args->sensor_mode); return RK_ERR_ARG;
   }
   if(e != cudaSuccess) return cuda_fail(e, "vdt_rollout_kernel launch");

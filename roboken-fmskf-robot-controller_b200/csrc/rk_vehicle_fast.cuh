@@ -109,11 +109,19 @@ template <int DIR> RK_DEV bool fast_motor_ok(const Motor &m, int lim) {
 }
 RK_DEV bool finite_bounded(float x) { return fabsf(x) <= 1.0e9f; } // false for NaN / Inf
 
-template <int D0, int D1, int D2, int D3>
+// RK_SENSOR_STREAM: the plant fields are not used; the status words are whatever the last frame said
+RK_DEV bool fast_motor_ok_stream(const Motor &m, int lim) { return (m.sum == m.prev) && (m.cur_tgt >= -lim) && (m.cur_tgt <= lim); }
+
+template <int D0, int D1, int D2, int D3, bool STREAM = false>
 RK_DEV bool fast_ok(const Veh &v, const rk_vdt_params_t &p) {
   bool ok = (v.flags & RK_VS_FLAG_POWER_ON) != 0;
-  ok &= fast_motor_ok<D0>(v.m[0], p.raw_curr_lim) && fast_motor_ok<D1>(v.m[1], p.raw_curr_lim);
-  ok &= fast_motor_ok<D2>(v.m[2], p.raw_curr_lim) && fast_motor_ok<D3>(v.m[3], p.raw_curr_lim);
+  if(STREAM) {
+#pragma unroll
+    for(int k = 0; k < 4; k++) ok &= fast_motor_ok_stream(v.m[k], p.raw_curr_lim);
+  } else {
+    ok &= fast_motor_ok<D0>(v.m[0], p.raw_curr_lim) && fast_motor_ok<D1>(v.m[1], p.raw_curr_lim);
+    ok &= fast_motor_ok<D2>(v.m[2], p.raw_curr_lim) && fast_motor_ok<D3>(v.m[3], p.raw_curr_lim);
+  }
   ok &= finite_bounded(v.pos[0]) && finite_bounded(v.pos[1]);
 #pragma unroll
   for(int a = 0; a < 3; a++) {

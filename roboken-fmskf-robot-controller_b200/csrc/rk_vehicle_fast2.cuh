@@ -115,20 +115,63 @@ RK_DEV FastWheel lane_wheel(const FastWheel2 &w, int l) {
   s.lpf_y = l ? w.lpf_y.y : w.lpf_y.x, s.lpf_x = l ? w.lpf_x.y : w.lpf_x.x, s.b0x = l ? w.b0x.y : w.b0x.x;
   return s;
 }
-template <int D0, int D1, int D2, int D3>
-RK_DEV void from_fast2(Veh &v, const FastVeh2 &f, int nticks) {
-  if(nticks <= 0) return;
+RK_DEV void from_fast2_common(Veh &v, const FastVeh2 &f, FastWheel w[4]) {
   v.pos[0] = f.p.x, v.pos[1] = f.p.y;
   fast_interp2_store(f.xy, v.it[0], v.it[1]);
   fast_interp_store(f.th, v.it[2]);
-  const FastWheel w0 = lane_wheel(f.w01, 0), w1 = lane_wheel(f.w01, 1), w2 = lane_wheel(f.w23, 0), w3 = lane_wheel(f.w23, 1);
-  const FastWheel *w[4] = {&w0, &w1, &w2, &w3};
+  w[0] = lane_wheel(f.w01, 0), w[1] = lane_wheel(f.w01, 1), w[2] = lane_wheel(f.w23, 0), w[3] = lane_wheel(f.w23, 1);
 #pragma unroll
-  for(int k = 0; k < 4; k++) v.c[k].prev_val = w[k]->prev_val, v.c[k].integ = w[k]->integ, v.c[k].lpf_y = w[k]->lpf_y, v.c[k].lpf_x = w[k]->lpf_x;
-  from_fast_motor<D0>(v.m[0], w0, nticks);
-  from_fast_motor<D1>(v.m[1], w1, nticks);
-  from_fast_motor<D2>(v.m[2], w2, nticks);
-  from_fast_motor<D3>(v.m[3], w3, nticks);
+  for(int k = 0; k < 4; k++) v.c[k].prev_val = w[k].prev_val, v.c[k].integ = w[k].integ, v.c[k].lpf_y = w[k].lpf_y, v.c[k].lpf_x = w[k].lpf_x;
+}
+template <int D0, int D1, int D2, int D3>
+RK_DEV void from_fast2(Veh &v, const FastVeh2 &f, int nticks) {
+  if(nticks <= 0) return;
+  FastWheel w[4];
+  from_fast2_common(v, f, w);
+  from_fast_motor<D0>(v.m[0], w[0], nticks);
+  from_fast_motor<D1>(v.m[1], w[1], nticks);
+  from_fast_motor<D2>(v.m[2], w[2], nticks);
+  from_fast_motor<D3>(v.m[3], w[3], nticks);
+}
+
+// ---- RK_SENSOR_STREAM on the fast tick: the wheel feedback comes from recorded C610 frames, so rx_callback
+// (VD_motor_if_m2006.cpp:32-72) runs in full -- big-endian fields, direction, the +-4096 unwrap -- instead of the
+// collapsed plant.  The odometry product fma(d, K_hi, d*K_lo) is proven for every step the unwrap can produce
+// (|d| <= 2^17, rk_exact.cu), so no frame can leave the fast path's domain.
+struct StreamSense {
+  int32_t ang[4], rpm[4], cur[4]; // head Status: s16_rawAngle, s16_rawSpeedRpm, s16_rawCurr after the direction is applied
+};
+RK_DEV void stream_sense_load(StreamSense &ss, const Veh &v) {
+#pragma unroll
+  for(int k = 0; k < 4; k++) ss.ang[k] = v.m[k].ang, ss.rpm[k] = v.m[k].rpm, ss.cur[k] = v.m[k].cur;
+}
+template <int DIR>
+RK_DEV float2 fast_wheel_rx2(StreamSense &ss, int k, int32_t &dsum, uint64_t frame, const FastConsts &fc) {
+  const uint32_t lo = (uint32_t)frame, hi = (uint32_t)(frame >> 32);
+  const int32_t  a = sext16((int32_t)(__byte_perm(lo, 0, 0x4401))); // (b0<<8)|b1
+  const int32_t  r = sext16((int32_t)(__byte_perm(lo, 0, 0x4423))); // (b2<<8)|b3
+  const int32_t  c = sext16((int32_t)(__byte_perm(hi, 0, 0x4401))); // (b4<<8)|b5
+  const int32_t  raw_ang = (DIR == 1) ? a : sext16(8192 - a);
+  int32_t        d       = sext16(raw_ang - ss.ang[k]);
+  d                      = (d > 4096) ? sext16(d - 8192) : ((d < -4096) ? sext16(d + 8192) : d);
+  dsum += d;
+  ss.ang[k] = raw_ang, ss.rpm[k] = sext16(r * DIR), ss.cur[k] = sext16(c * DIR);
+  const float df = (float)d;
+  return make_float2(fmul(fmul((float)ss.rpm[k], RK_RPM_TO_RADPS), RK_GEAR_RATIO_INV), __fmaf_rn(df, fc.k_hi, fmul(df, fc.k_lo)));
+}
+RK_DEV void from_fast2_stream(Veh &v, const FastVeh2 &f, const StreamSense &ss, int nticks) {
+  if(nticks <= 0) return;
+  FastWheel w[4];
+  from_fast2_common(v, f, w);
+#pragma unroll
+  for(int k = 0; k < 4; k++) {
+    Motor &m = v.m[k];
+    m.sum += (int64_t)w[k].dsum;
+    m.prev = m.sum;
+    m.ang = ss.ang[k], m.rpm = ss.rpm[k], m.cur = ss.cur[k];
+    m.cur_tgt = w[k].cur;
+    m.head    = (m.head + nticks) % 3;
+  }
 }
 
 // plant step + collapsed rx_callback for one wheel; returns {Mvel, Mrad} as one lane pair
@@ -176,12 +219,30 @@ RK_DEV void fast_wheel_ctrl2(FastWheel2 &w, const rk_vdt_params_t &p, const Fast
 
 // One packed fast tick.  cs = {cos, sin}(yaw), sc = {sin, cos}(yaw).
 template <bool FFSAT>
+RK_DEV void fast_tick2_core(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &fc, float2 cs, float2 sc, float nz,
+                            float vel[3], float tgt[3], float2 m0, float2 m1, float2 m2, float2 m3);
+template <bool FFSAT>
 RK_DEV void fast_tick2(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &fc, float2 cs, float2 sc, float nz,
                        float vel[3], float tgt[3]) {
   const float2 m0 = fast_wheel_sense2<1>(f.w01.rpm[0], f.w01.cur[0], f.w01.dsum[0], fc);
   const float2 m1 = fast_wheel_sense2<1>(f.w01.rpm[1], f.w01.cur[1], f.w01.dsum[1], fc);
   const float2 m2 = fast_wheel_sense2<-1>(f.w23.rpm[0], f.w23.cur[0], f.w23.dsum[0], fc);
   const float2 m3 = fast_wheel_sense2<-1>(f.w23.rpm[1], f.w23.cur[1], f.w23.dsum[1], fc);
+  fast_tick2_core<FFSAT>(f, p, fc, cs, sc, nz, vel, tgt, m0, m1, m2, m3);
+}
+// the same tick fed by four recorded frames (RK_SENSOR_STREAM)
+template <bool FFSAT>
+RK_DEV void fast_tick2_stream(FastVeh2 &f, StreamSense &ss, const uint64_t fr[4], const rk_vdt_params_t &p, const FastConsts &fc,
+                              float2 cs, float2 sc, float nz, float vel[3], float tgt[3]) {
+  const float2 m0 = fast_wheel_rx2<1>(ss, 0, f.w01.dsum[0], fr[0], fc);
+  const float2 m1 = fast_wheel_rx2<1>(ss, 1, f.w01.dsum[1], fr[1], fc);
+  const float2 m2 = fast_wheel_rx2<-1>(ss, 2, f.w23.dsum[0], fr[2], fc);
+  const float2 m3 = fast_wheel_rx2<-1>(ss, 3, f.w23.dsum[1], fr[3], fc);
+  fast_tick2_core<FFSAT>(f, p, fc, cs, sc, nz, vel, tgt, m0, m1, m2, m3);
+}
+template <bool FFSAT>
+RK_DEV void fast_tick2_core(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &fc, float2 cs, float2 sc, float nz,
+                            float vel[3], float tgt[3], float2 m0, float2 m1, float2 m2, float2 m3) {
   // conv_Mdir_to_Vdir on both paths at once  VD_vehicle_controller.cpp:126-130 (called at :26 and :42)
   // (sum * 0.25f) * R == sum * (0.25f * R) bit for bit: scaling by 2^-2 is exact in both places as long as
   // nothing underflows, and a sum of wheel speeds / angle steps is 0 or >= 2^-40 in magnitude (they derive

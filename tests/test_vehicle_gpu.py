@@ -462,3 +462,38 @@ def test_yaw_register_input_equals_float_yaw_and_port():
     pst, ptr = port_run(dict(inp, yaw=reg))
     assert_same(tr_r, ptr, "register yaw vs port trace")
     assert_same(st_r, pst, "register yaw vs port state")
+
+
+def test_stream_fast_tick_equals_transcription_and_port():
+    """RK_SENSOR_STREAM runs on the packed fast tick (vdt_rollout_stream_fast_kernel): same bits as the transcription
+    kernel and the port -- on realistic recorded traffic with the VDT task layer active, on adversarial angle fields
+    with the vehicles powered (so the fast path is really taken), and resumed over several launches."""
+    lib = rk.load()
+    from test_vdt_task_cpu import task_inputs
+
+    n, steps = 1100, 1000
+    rng = np.random.default_rng(8)
+    fr_real = streams.vehicle_frames(n, steps, seed=31)
+    fr_adv = rng.integers(0, 1 << 63, size=(steps, 4, n), dtype=np.int64).view(np.uint64) & ~np.uint64(0x00000000FFFF0000)
+    cases = (("plain", wl.plant_inputs(n, steps, seed=31), fr_real), ("task", dict(task_inputs(n, steps, 32, seg_len=50), task_period=10), fr_real),
+             ("adversarial", wl.plant_inputs(n, steps, seed=33), fr_adv))
+    for name, inp, fr in cases:
+        st, tr = gpu_run(inp, sensor=_cabi.RK_SENSOR_STREAM, frames=fr)
+        lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, 1)
+        try:
+            st_t, tr_t = gpu_run(inp, sensor=_cabi.RK_SENSOR_STREAM, frames=fr)
+        finally:
+            lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, 0)
+        assert_same(tr, tr_t, name + ": stream fast vs transcription trace")
+        assert_same(st, st_t, name + ": stream fast vs transcription state")
+        if name != "task":
+            pst, ptr = port_run(inp, sensor=_cabi.RK_SENSOR_STREAM, frames=fr, nthreads=8)
+            assert_same(tr, ptr, name + ": stream fast vs port trace")
+            assert_same(st, pst, name + ": stream fast vs port state")
+        if name == "plain":
+            st5, _ = gpu_run(inp, sensor=_cabi.RK_SENSOR_STREAM, frames=fr, trace=False, chunks=4)
+            a1, a5 = layout.soa_to_aos(st, n, layout.VS_WORDS), layout.soa_to_aos(st5, n, layout.VS_WORDS)
+            for w in range(4):  # microsecond ids restart per launch (dead telemetry word)
+                a1[:, layout.VS_MOTOR0 + 8 * w + layout.VM_USEC] &= 0xFFFF0000
+                a5[:, layout.VS_MOTOR0 + 8 * w + layout.VM_USEC] &= 0xFFFF0000
+            assert_same(a1, a5, "stream: one launch vs four")
