@@ -241,8 +241,11 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
 // while tick t is computed.  Command ticks, the last tick and threads outside the fast domain run the
 // transcription on the same frames.
 // -----------------------------------------------------------------------------------------
+#ifndef RK_STREAM_OCC
+#define RK_STREAM_OCC 3
+#endif
 template <bool TRACE, bool FFSAT>
-__global__ void __launch_bounds__(kFastThreads, 3)
+__global__ void __launch_bounds__(kFastThreads, RK_STREAM_OCC)
 vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
   constexpr int D0 = 1, D1 = 1, D2 = -1, D3 = -1;
   __shared__ float s_tab[513];
