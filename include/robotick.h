@@ -473,6 +473,10 @@ void rk_adt_destroy(rk_adt_t *h);
 int  rk_adt_init(rk_adt_t *h);                                    /* mode init, see rk_adt_mode_init */
 int  rk_adt_push(rk_adt_t *h, const rk_adt_poscmdseq_t *seq);     /* push_cmdseq                     */
 int  rk_adt_tick(rk_adt_t *h);                                    /* one ADT::main loop body         */
+int  rk_adt_home_init(rk_adt_t *h, int mode);                     /* set_next_mode(INIT / INIT_POS_MOVE): RK_ADH_MODE_* */
+/* one loop body with the homing mode active; servo_now_deg (or NULL): fl_raw_now_deg of P1, DF_Left, DF_Right, P3
+ * as received since the last tick; *completed = ADTModeBase::isCompleted() */
+int  rk_adt_home_tick(rk_adt_t *h, const float servo_now_deg[4], int *completed);
 int  rk_adt_status(rk_adt_t *h, uint32_t id, int32_t *status);    /* get_q_cmdseq_status             */
 int  rk_adt_get_targets_deg(rk_adt_t *h, float out[5]);           /* JointBase::get_tgt_deg x5       */
 int  rk_adt_get_state(rk_adt_t *h, uint32_t words[RK_AS_WORDS]);
@@ -556,6 +560,14 @@ size_t rk_rmt_state_bytes(int64_t n);
  * d_abort_out: [K][n] vdt_abort.val after the cycle (VehicleInfo.fault, :828) or NULL */
 int rk_rmt_guard(const rk_rmt_params_t *p, void *d_state, int64_t n, int32_t K, const void *d_in, rk_vdt_cmd_t *d_cmd_out,
                  uint32_t *d_abort_out, void *stream);
+/* single-instance handle (drop-in for the manager's file-static state, RM_task_main.cpp:61-92): one routine_ros()
+ * vehicle-management block per call, record in / message out on the host */
+typedef struct rk_rmt rk_rmt_t;
+int  rk_rmt_create(rk_rmt_t **out, const rk_rmt_params_t *p /* NULL = defaults */);
+void rk_rmt_destroy(rk_rmt_t *h);
+int  rk_rmt_cycle(rk_rmt_t *h, const uint32_t in[RK_RI_WORDS], rk_vdt_cmd_t *out, uint32_t *abort_val);
+int  rk_rmt_get_state(rk_rmt_t *h, uint32_t words[RK_RS_WORDS]);
+
 /* UTIL::mymath::atan2f on device arrays (the guard's sector test uses it; exposed for parity tests) */
 int rk_mymath_atan2f(const float *d_y, const float *d_x, float *d_out, int64_t n, void *stream);
 

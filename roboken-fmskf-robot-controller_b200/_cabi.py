@@ -180,6 +180,13 @@ def _proto(lib):
     lib.rk_rmt_state_bytes.restype = C.c_size_t
     lib.rk_rmt_guard.argtypes = [C.POINTER(RmtParams), vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
     lib.rk_mymath_atan2f.argtypes = [vp, vp, vp, C.c_int64, vp]
+    lib.rk_rmt_create.argtypes = [C.POINTER(vp), C.POINTER(RmtParams)]
+    lib.rk_rmt_destroy.argtypes = [vp]
+    lib.rk_rmt_destroy.restype = None
+    lib.rk_rmt_cycle.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(VdtCmd), C.POINTER(C.c_uint32)]
+    lib.rk_rmt_get_state.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.rk_adt_home_init.argtypes = [vp, C.c_int]
+    lib.rk_adt_home_tick.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.rk_imt_create.argtypes = [C.POINTER(vp)]
     lib.rk_imt_destroy.argtypes = [vp]
     lib.rk_imt_destroy.restype = None

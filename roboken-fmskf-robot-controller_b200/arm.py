@@ -160,6 +160,17 @@ class Arm:
     def update(self):
         _cabi.check(self.lib.rk_adt_tick(self.h))
 
+    def home_init(self, mode):
+        """set_next_mode(INIT / INIT_POS_MOVE) -> init() of that mode (RK_ADH_MODE_*)."""
+        _cabi.check(self.lib.rk_adt_home_init(self.h, int(mode)))
+
+    def home_update(self, servo_now_deg=None):
+        """One loop body with the homing mode active; returns isCompleted()."""
+        done = C.c_int()
+        now = None if servo_now_deg is None else (C.c_float * 4)(*[float(x) for x in servo_now_deg])
+        _cabi.check(self.lib.rk_adt_home_tick(self.h, now, C.byref(done)))
+        return bool(done.value)
+
     def get_q_cmdseq_status(self, seq_id):
         s = C.c_int32()
         _cabi.check(self.lib.rk_adt_status(self.h, int(seq_id), C.byref(s)))

@@ -1248,6 +1248,7 @@ int rk_adh_update(const rk_adt_params_t *p, void *d_state, void *d_hstate, int64
 struct rk_adt {
   rk_adt_params_t p;
   uint32_t       *d_state, *d_tab, *d_seq, *d_misc; // d_misc: [0] id, [1] status, [2..6] targets
+  uint32_t       *d_hs;                             // homing mode block (RK_HS_WORDS) + 4 floats of servo feedback
   uint32_t       *h_stage;                         // pinned, RK_ACMD_SLOT_WORDS words
   cudaStream_t    st;
 };
@@ -1264,10 +1265,12 @@ int rk_adt_create(rk_adt_t **out, const rk_adt_params_t *p) {
   if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_tab, RK_ACMD_WORDS * 4);
   if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_seq, RK_ACMD_SLOT_WORDS * 4);
   if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_misc, 32);
+  if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_hs, (RK_HS_WORDS + 4) * 4);
   if(e == cudaSuccess) e = cudaMallocHost((void **)&h->h_stage, RK_ACMD_SLOT_WORDS * 4);
   if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
   if(e == cudaSuccess) e = cudaMemsetAsync(h->d_state, 0, RK_AS_WORDS * 4, h->st);
   if(e == cudaSuccess) e = cudaMemsetAsync(h->d_tab, 0, RK_ACMD_WORDS * 4, h->st);
+  if(e == cudaSuccess) e = cudaMemsetAsync(h->d_hs, 0, (RK_HS_WORDS + 4) * 4, h->st);
   if(e != cudaSuccess) {
     int rc = cuda_fail(e, "rk_adt_create");
     rk_adt_destroy(h);
@@ -1286,6 +1289,7 @@ void rk_adt_destroy(rk_adt_t *h) {
   if(h->d_tab) cudaFree(h->d_tab);
   if(h->d_seq) cudaFree(h->d_seq);
   if(h->d_misc) cudaFree(h->d_misc);
+  if(h->d_hs) cudaFree(h->d_hs);
   if(h->h_stage) cudaFreeHost(h->h_stage);
   delete h;
 }
@@ -1305,6 +1309,27 @@ int rk_adt_push(rk_adt_t *h, const rk_adt_poscmdseq_t *seq) {
   }
   RK_CUDA(cudaMemcpyAsync(h->d_seq, w, RK_ACMD_SLOT_WORDS * 4, cudaMemcpyHostToDevice, h->st));
   return rk_adt_push_cmdseq(h->d_state, h->d_tab, 1, h->d_seq, nullptr, h->st);
+}
+int rk_adt_home_init(rk_adt_t *h, int mode) { // set_next_mode(INIT / INIT_POS_MOVE) -> m_nowProcess->init()
+  if(!h) return RK_ERR_ARG;
+  return rk_adh_mode_init(h->d_hs, 1, mode, h->st);
+}
+int rk_adt_home_tick(rk_adt_t *h, const float servo_now_deg[4], int *completed) {
+  if(!h) return RK_ERR_ARG;
+  float *d_now = nullptr;
+  if(servo_now_deg) {
+    RK_CUDA(cudaStreamSynchronize(h->st));
+    memcpy(h->h_stage, servo_now_deg, 16);
+    d_now = (float *)(h->d_hs + RK_HS_WORDS);
+    RK_CUDA(cudaMemcpyAsync(d_now, h->h_stage, 16, cudaMemcpyHostToDevice, h->st));
+  }
+  if(int rc = rk_adh_update(&h->p, h->d_state, h->d_hs, 1, 1, d_now, nullptr, h->st)) return rc;
+  if(completed) { // ADTModeBase::isCompleted()
+    RK_CUDA(cudaMemcpyAsync(h->h_stage + 8, h->d_hs, 4, cudaMemcpyDeviceToHost, h->st));
+    RK_CUDA(cudaStreamSynchronize(h->st));
+    *completed = (h->h_stage[8] & RK_AS_FSM_IS_COMP) ? 1 : 0;
+  }
+  return RK_OK;
 }
 int rk_adt_tick(rk_adt_t *h) {
   if(!h) return RK_ERR_ARG;

@@ -5,6 +5,8 @@
 // cycles; per cycle three 128-bit loads (48 B record) and one 128-bit + one 32-bit store.  The table arctangent
 // UTIL::mymath::atanf (src/Utility/util_mymath.cpp:98-115) is staged in shared memory once per CTA (per-lane
 // indices differ, a __constant__ bank would serialise).
+#include <string.h>
+
 #include "rk_common.cuh"
 #include "rk_math.cuh"
 
@@ -204,6 +206,62 @@ int rk_rmt_guard(const rk_rmt_params_t *p, void *d_state, int64_t n, int32_t K, 
   rmt_guard_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(q, (uint4 *)d_state, n, K, (const uint4 *)d_in,
                                                                                   (uint4 *)d_cmd_out, d_abort_out);
   RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+struct rk_rmt {
+  rk_rmt_params_t p;
+  uint32_t       *d_buf; // [0..3] state plane, [4..15] input record, [16..19] output record, [20] abort
+  uint32_t       *h_stage;
+  cudaStream_t    st;
+};
+int rk_rmt_create(rk_rmt_t **out, const rk_rmt_params_t *p) {
+  if(!out) return RK_ERR_ARG;
+  *out = nullptr;
+  if(int rc = require_device()) return rc;
+  rk_rmt *h = new rk_rmt();
+  memset(h, 0, sizeof(*h));
+  if(p) h->p = *p;
+  else rk_rmt_default_params(&h->p);
+  cudaError_t e = cudaMalloc((void **)&h->d_buf, 24 * 4);
+  if(e == cudaSuccess) e = cudaMallocHost((void **)&h->h_stage, 24 * 4);
+  if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  if(e == cudaSuccess) e = cudaMemsetAsync(h->d_buf, 0, 24 * 4, h->st);
+  if(e != cudaSuccess) {
+    int rc = cuda_fail(e, "rk_rmt_create");
+    rk_rmt_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return RK_OK;
+}
+void rk_rmt_destroy(rk_rmt_t *h) {
+  if(!h) return;
+  if(h->st) {
+    cudaStreamSynchronize(h->st);
+    cudaStreamDestroy(h->st);
+  }
+  if(h->d_buf) cudaFree(h->d_buf);
+  if(h->h_stage) cudaFreeHost(h->h_stage);
+  delete h;
+}
+int rk_rmt_cycle(rk_rmt_t *h, const uint32_t in[RK_RI_WORDS], rk_vdt_cmd_t *out, uint32_t *abort_val) {
+  if(!h || !in) return RK_ERR_ARG;
+  RK_CUDA(cudaStreamSynchronize(h->st));
+  memcpy(h->h_stage + 4, in, RK_RI_WORDS * 4); // n = 1: the three cells of a record are consecutive
+  RK_CUDA(cudaMemcpyAsync(h->d_buf + 4, h->h_stage + 4, RK_RI_WORDS * 4, cudaMemcpyHostToDevice, h->st));
+  if(int rc = rk_rmt_guard(&h->p, h->d_buf, 1, 1, h->d_buf + 4, (rk_vdt_cmd_t *)(h->d_buf + 16), h->d_buf + 20, h->st)) return rc;
+  RK_CUDA(cudaMemcpyAsync(h->h_stage + 16, h->d_buf + 16, 5 * 4, cudaMemcpyDeviceToHost, h->st));
+  RK_CUDA(cudaStreamSynchronize(h->st));
+  if(out) memcpy(out, h->h_stage + 16, 16);
+  if(abort_val) *abort_val = h->h_stage[20];
+  return RK_OK;
+}
+int rk_rmt_get_state(rk_rmt_t *h, uint32_t words[RK_RS_WORDS]) {
+  if(!h || !words) return RK_ERR_ARG;
+  RK_CUDA(cudaMemcpyAsync(h->h_stage, h->d_buf, RK_RS_WORDS * 4, cudaMemcpyDeviceToHost, h->st));
+  RK_CUDA(cudaStreamSynchronize(h->st));
+  memcpy(words, h->h_stage, RK_RS_WORDS * 4);
   return RK_OK;
 }
 

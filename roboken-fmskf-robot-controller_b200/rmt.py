@@ -35,6 +35,39 @@ class ManagerBatch:
                                           None if abort_out is None else abort_out.data_ptr(), C.c_void_p(st.cuda_stream)))
 
 
+class Manager:
+    """Single RobotManager (rk_rmt_t): the file-static state of RM_task_main.cpp behind one handle; one
+    routine_ros() vehicle-management block per cycle()."""
+
+    def __init__(self, params=None):
+        self.lib = _cabi.load()
+        self.h = C.c_void_p()
+        _cabi.check(self.lib.rk_rmt_create(C.byref(self.h), None if params is None else C.byref(params)))
+
+    def close(self):
+        if self.h:
+            self.lib.rk_rmt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def cycle(self, record):
+        """record: 12 uint32 words (RK_RI_*).  Returns (rk_vdt_cmd_t as 4 uint32 words, vdt_abort.val)."""
+        rec = (C.c_uint32 * layout.RI_WORDS)(*[int(x) for x in record])
+        out, ab = _cabi.VdtCmd(), C.c_uint32()
+        _cabi.check(self.lib.rk_rmt_cycle(self.h, rec, C.byref(out), C.byref(ab)))
+        return list((C.c_uint32 * 4).from_buffer_copy(out)), ab.value
+
+    def state(self):
+        w = (C.c_uint32 * layout.RS_WORDS)()
+        _cabi.check(self.lib.rk_rmt_get_state(self.h, w))
+        return list(w)
+
+
 def atan2f(y, x, stream=None):
     """UTIL::mymath::atan2f (table arctangent, src/Utility/util_mymath.cpp:98-126) on float32 CUDA tensors."""
     lib = _cabi.load()

@@ -102,3 +102,27 @@ def test_homing_argument_errors():
     import ctypes as C
     assert lib.rk_adh_update(C.byref(ab.params), ab.state.data_ptr(), None, 4, 1, None, None, None) == 1
     assert lib.rk_adh_update(C.byref(ab.params), ab.state.data_ptr(), hb.hstate.data_ptr(), 4, -1, None, None, None) == 1
+
+
+def test_arm_handle_homing_equals_port():
+    """rk_adt_t: rk_adt_home_init / rk_adt_home_tick (host feedback, isCompleted) == the port, tick by tick."""
+    from roboken_fmskf_robot_controller_b200.arm import Arm
+
+    K = 1000
+    now = feedback(1, K, seed=2)
+    s0 = start_states(1, 0, zero=True)
+    st, hs = s0.copy(), np.zeros(layout.HS_WORDS, dtype=np.uint32)
+    ol.arm_homing("port", "init", st, hs, 1, mode=_cabi.RK_ADH_MODE_INIT)
+    arm = Arm()
+    arm.home_init(_cabi.RK_ADH_MODE_INIT)
+    done_at = None
+    for t in range(K):
+        ol.arm_homing("port", "update", st, hs, 1, K=1, now=np.ascontiguousarray(now[t : t + 1]))
+        done = arm.home_update(now[t, :, 0])
+        assert done == bool(hs[0] & layout.AS_FSM_IS_COMP), t
+        if done and done_at is None:
+            done_at = t
+        if t % 97 == 0 or t == K - 1:
+            np.testing.assert_array_equal(arm.get_state(), st)
+    assert done_at is not None and done_at > 600
+    arm.close()

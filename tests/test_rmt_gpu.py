@@ -121,3 +121,19 @@ def test_guard_argument_errors():
     assert lib.rk_rmt_guard(C.byref(p), mb.state.data_ptr(), 4, 1, None, None, None, None) == 1
     assert lib.rk_rmt_guard(C.byref(p), mb.state.data_ptr(), 0, 1, None, None, None, None) == 0
     assert lib.rk_rmt_guard(C.byref(p), mb.state.data_ptr() + 4, 4, 1, mb.state.data_ptr(), mb.state.data_ptr(), None, None) == 1
+
+
+def test_manager_handle_equals_port():
+    """rk_rmt_t: one routine_ros() block per call on host words == the port, cycle by cycle."""
+    from roboken_fmskf_robot_controller_b200.rmt import Manager
+
+    K = 260
+    inp = streams.rm_inputs(1, K, seed=4, idle_every=1)  # index 0 is a mostly-silent robot: the watchdog fires
+    st = np.zeros(layout.RS_WORDS, dtype=np.uint32)
+    ca, aa = ol.rm_guard("port", st, 1, inp)
+    m = Manager()
+    for u in range(K):
+        rec, ab = m.cycle(inp[u, :, 0, :].reshape(-1))
+        assert rec == list(ca[u, 0]) and ab == aa[u, 0], u
+    assert m.state() == list(st)
+    m.close()
