@@ -1349,9 +1349,12 @@ void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0
 /* (src/RobotManager/RM_task_main.cpp:484-767) + UTIL::mymath::atanf / atan2f                */
 /* (src/Utility/util_mymath.cpp:98-126; tables restated by tools/gen_atan_table.py)          */
 #include "atan_table.inc"
-static const float orc_atan_table[]   = {RK_ATAN_TABLE_VALUES};
-static const float orc_atan_delimit[] = {RK_ATAN_DELIMIT_VALUES};
-static const float orc_atan_width[]   = {RK_ATAN_WIDTH_VALUES};
+static const uint32_t orc_atan_table_bits[]   = {RK_ATAN_TABLE_BITS};
+static const uint32_t orc_atan_delimit_bits[] = {RK_ATAN_DELIMIT_BITS};
+static const uint32_t orc_atan_width_bits[]   = {RK_ATAN_WIDTH_BITS};
+#define orc_atan_table(i) u2f(orc_atan_table_bits[i])
+#define orc_atan_delimit(i) u2f(orc_atan_delimit_bits[i])
+#define orc_atan_width(i) u2f(orc_atan_width_bits[i])
 
 float orc_atanf(float x) { /* util_mymath.cpp:98-115 */
   int   i, index_int;
@@ -1359,14 +1362,14 @@ float orc_atanf(float x) { /* util_mymath.cpp:98-115 */
   if(x < 0) return -orc_atanf(-x);
   if(x == 0.0) return 0.0f;
   for(i = 1; i <= 26; i++) {
-    if(x <= orc_atan_delimit[i]) {
-      index     = 24 * (i - 1) + ((x - orc_atan_delimit[i - 1]) / orc_atan_width[i - 1]);
+    if(x <= orc_atan_delimit(i)) {
+      index     = 24 * (i - 1) + ((x - orc_atan_delimit(i - 1)) / orc_atan_width(i - 1));
       index_int = (int)index;
       index_dec = index - (float)index_int;
-      return orc_atan_table[index_int] + index_dec * ((orc_atan_table[index_int + 1] - orc_atan_table[index_int]));
+      return orc_atan_table(index_int) + index_dec * ((orc_atan_table(index_int + 1) - orc_atan_table(index_int)));
     }
   }
-  return orc_atan_table[577 - 1]; /* TABLE_SIXE_ATAN is 577 although the table has 625 entries: :6,114 */
+  return orc_atan_table(577 - 1); /* TABLE_SIXE_ATAN is 577 although the table has 625 entries: :6,114 */
 }
 float orc_atan2f(float y, float x) { /* :117-126 */
   if(x > 0.0) return orc_atanf(y / x);

@@ -13,17 +13,17 @@
 namespace rk {
 
 #include "atan_table.inc"
-__device__ const float g_atan_table[626]  = {RK_ATAN_TABLE_VALUES};
-__device__ const float g_atan_delimit[27] = {RK_ATAN_DELIMIT_VALUES};
-__device__ const float g_atan_width[26]   = {RK_ATAN_WIDTH_VALUES};
+__device__ const uint32_t g_atan_table[626]  = {RK_ATAN_TABLE_BITS};
+__device__ const uint32_t g_atan_delimit[27] = {RK_ATAN_DELIMIT_BITS};
+__device__ const uint32_t g_atan_width[26]   = {RK_ATAN_WIDTH_BITS};
 
 struct AtanTab {
   float table[626], delimit[27], width[26];
 };
 RK_DEV void stage_atan(AtanTab &s) {
-  for(int k = threadIdx.x; k < 626; k += blockDim.x) s.table[k] = g_atan_table[k];
-  for(int k = threadIdx.x; k < 27; k += blockDim.x) s.delimit[k] = g_atan_delimit[k];
-  for(int k = threadIdx.x; k < 26; k += blockDim.x) s.width[k] = g_atan_width[k];
+  for(int k = threadIdx.x; k < 626; k += blockDim.x) s.table[k] = u2f(g_atan_table[k]);
+  for(int k = threadIdx.x; k < 27; k += blockDim.x) s.delimit[k] = u2f(g_atan_delimit[k]);
+  for(int k = threadIdx.x; k < 26; k += blockDim.x) s.width[k] = u2f(g_atan_width[k]);
   __syncthreads();
 }
 // mymath::atanf :98-115 (the recursion on negative x unrolled: atanf(-x) = -atanf(x))

@@ -20,10 +20,11 @@ def generated_tables():
     text = open(os.path.join(ROOT, "oracle", "atan_table.inc")).read()
     assert text == open(os.path.join(ROOT, "roboken-fmskf-robot-controller_b200", "csrc", "atan_table.inc")).read()
     out = []
-    for name in ("RK_ATAN_TABLE_VALUES", "RK_ATAN_DELIMIT_VALUES", "RK_ATAN_WIDTH_VALUES"):
+    for name in ("RK_ATAN_TABLE_BITS", "RK_ATAN_DELIMIT_BITS", "RK_ATAN_WIDTH_BITS"):
         body = text.split("#define " + name)[1].split("#define")[0]
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-        out.append(np.array([np.float32(float(v)) for v in re.findall(r"\(float\)([0-9.]+)", body)], dtype=np.float32))
+        out.append(np.array([int(v, 16) for v in re.findall(r"0x([0-9A-Fa-f]{8})u", body)], dtype=np.uint32).view(np.float32))
+    out[0] = out[0][:625]  # the pad word after the table
     return out
 
 
