@@ -422,8 +422,9 @@ RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c
     float q;
     if(DIVC == 2) {
       q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
-    } else if(DIVC == 1) { // proven for zero and |d| >= 2^-40; anything tinier takes the IEEE division
-      if(d == 0.0f || fabsf(d) >= 9.094947017729282e-13f) q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
+    } else if(DIVC == 1) { // proven for zero and 2^-40 <= |d| <= 2^64; anything else takes the IEEE division
+      const float ad = fabsf(d);
+      if(d == 0.0f || (ad >= 9.094947017729282e-13f && ad <= 18446744073709551616.0f)) q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
       else q = fdiv(d, c.mg_ctrl_time);
     } else { // 0 / c = 0 with the numerator's sign for c > 0; keeps an idle joint off the division's slow path
       q = (d == 0.0f && c.mg_ctrl_time > 0.0f) ? d : fdiv(d, c.mg_ctrl_time);

@@ -21,11 +21,12 @@ struct ProofOut {
   unsigned int div_fail_any;     // failures anywhere (finite x)
   unsigned int div_fail_outside; // failures with x == +-0 or |x| >= 2^-40
   unsigned int mrad_fail, dang_fail;
+  unsigned int div_fail_mid;     // failures with x == +-0 or 2^-40 <= |x| <= 2^64 (small divisors overflow / underflow beyond)
 };
 
 __global__ void proof_div_kernel(float c, ProofOut *out) {
   const float    rcp = fdiv(1.0f, c);
-  unsigned int   any = 0, outside = 0;
+  unsigned int   any = 0, outside = 0, mid = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for(uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < 0x100000000ull; b += stride) {
     const unsigned int u = (unsigned int)b, au = u & 0x7fffffffu;
@@ -34,10 +35,12 @@ __global__ void proof_div_kernel(float c, ProofOut *out) {
     if(f2u(div_const(x, c, rcp)) != f2u(fdiv(x, c))) {
       any++;
       if(au == 0u || au >= 0x2b800000u /* 2^-40 */) outside++;
+      if(au == 0u || (au >= 0x2b800000u && au <= 0x5f800000u /* 2^64 */)) mid++;
     }
   }
   if(any) atomicAdd(&out->div_fail_any, any);
   if(outside) atomicAdd(&out->div_fail_outside, outside);
+  if(mid) atomicAdd(&out->div_fail_mid, mid);
 }
 
 __global__ void proof_small_kernel(ProofOut *out) {
@@ -81,7 +84,7 @@ bool fast_path_proven(const rk_vdt_params_t &p) {
     cudaGetLastError();
     return false;
   }
-  for(int k = 0; k < 4; k++) h[k] = ProofOut{0u, 0u, 0u, 0u};
+  for(int k = 0; k < 4; k++) h[k] = ProofOut{0u, 0u, 0u, 0u, 0u};
   cudaMemcpy(d_out, h, sizeof(h), cudaMemcpyHostToDevice);
   const float cs[3] = {p.wheel_radius_mm, p.sqrtf2, p.wheel_l_mm};
   for(int k = 0; k < 3; k++) proof_div_kernel<<<148 * 16, 256>>>(cs[k], d_out + k);
@@ -117,7 +120,7 @@ int div_const_exact(float c) {
   std::lock_guard<std::mutex> lk(mu);
   for(int k = 0; k < n_cache; k++)
     if(cache[k].dev == dev && cache[k].bits == bits) return cache[k].ok;
-  ProofOut *d_out = nullptr, h = ProofOut{0u, 0u, 0u, 0u};
+  ProofOut *d_out = nullptr, h = ProofOut{0u, 0u, 0u, 0u, 0u};
   if(cudaMalloc((void **)&d_out, sizeof(ProofOut)) != cudaSuccess) {
     cudaGetLastError();
     return 0;
@@ -130,7 +133,7 @@ int div_const_exact(float c) {
     cudaGetLastError();
     return 0;
   }
-  const int ok = (h.div_fail_any == 0u) ? 2 : (h.div_fail_outside == 0u) ? 1 : 0;
+  const int ok = (h.div_fail_any == 0u) ? 2 : (h.div_fail_mid == 0u) ? 1 : 0; // 1: exact for 0 and 2^-40 <= |x| <= 2^64
   if(n_cache < 16) cache[n_cache].dev = dev, cache[n_cache].bits = bits, cache[n_cache].ok = ok, n_cache++;
   return ok;
 }

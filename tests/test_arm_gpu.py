@@ -112,6 +112,21 @@ def test_arm_extreme_waypoints_vs_port():
     assert_same(gpu_script(3, script), run_script("port", 3, script))
 
 
+def test_arm_mg_velocity_division_domains_vs_port():
+    """The MG velocity limit divides the per-tick target step by the control period through the exact reciprocal form
+    only where rk_exact.cu proves it (0 and 2^-40 <= |step| <= 2^64 for 0.01 s); J1 targets that make the step tiny,
+    denormal, huge or overflowing (quotient = inf) must take the IEEE division and still match the port bit for bit.  (A step
+    that is itself inf - inf is left out: NaN payloads differ between x86 and the GPU.)"""
+    mags = [0.0, 1e-45, 1e-38, 1e-30, 3e-13, 9.2e-13, 1e-6, 1.0, 1e6, 1e18, 1.9e19, 3e19, 1e30, 1e37]
+    imgs = []
+    for k, m in enumerate(mags):
+        wp = [(10, (0, m, 0, 0, 0)), (20, (0, -m, 0, 0, 0)), (40, (0, m * 0.5, 0, 0, 0)), (50, (0, 0, 0, 0, 0))]
+        imgs.append(streams.arm_seq_image(7, wp))
+    img = np.stack(imgs)
+    script = [("init",), ("push", img, None), ("update", 12)]
+    assert_same(gpu_script(len(mags), script), run_script("port", len(mags), script))
+
+
 @pytest.mark.skipif(not ol.have_ref("libref_arm.so"), reason="oracle/_ref/libref_arm.so not present")
 def test_arm_vs_compiled_reference():
     n = 64
