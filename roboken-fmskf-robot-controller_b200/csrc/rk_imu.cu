@@ -240,14 +240,16 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
   const uint4 *src  = cells + i; // cell t = u * ncells + c of this IMU at src[t * n]
   const int64_t total = (int64_t)K * ncells;
   uint4 nxt = total > 0 ? __ldcs(src) : make_uint4(0u, 0u, 0u, 0u);
-  int64_t t = 0;
+  int64_t  t = 0;
+  uint32_t nb_next = (nbytes && K > 0) ? (uint32_t)__ldcs(nbytes + i) : 0xFFFFFFFFu;
   for(int u = 0; u < K; u++) {
     const bool init = do_init && u == 0;
     if(init) { // WitInit: s_uiWitDataCnt = 0 ; WitReadReg(q0, 4): s_uiReadRegIndex = q0
       p.cnt   = 0u;
       p.flags = (p.flags & ~0xFF00u) | (0x51u << 8);
     }
-    uint32_t left = nbytes ? min((uint32_t)nbytes[(int64_t)u * n + i], 16u * (uint32_t)ncells) : 16u * (uint32_t)ncells;
+    uint32_t left = min(nb_next, 16u * (uint32_t)ncells);
+    if(nbytes && u + 1 < K) nb_next = (uint32_t)__ldcs(nbytes + (int64_t)(u + 1) * n + i); // consumed an update later
     for(int c = 0; c < ncells; c++) {
       const uint4 cell = nxt;
       t++;
