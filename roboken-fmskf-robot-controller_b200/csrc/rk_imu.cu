@@ -141,10 +141,8 @@ RK_DEV void wit_store_reg(Wit &p, uint32_t reg, uint32_t val) { // CopeWitData's
     if(reg == 0x51u + k) p.reg[12 + k] = v;
   if(reg == 0x54u) p.flags |= 1u; // q3 -> QUAT_UPDATE (SensorDataUpdata)
 }
-RK_DEV void wit_frame(Wit &p) { // a full window (bytes 1..11 of the register) with a good checksum: CopeWitData :77-130
-  const uint32_t type = (p.w0 >> 16) & 0xFFu;
-  const int d0 = sext16((int)__byte_perm(p.w0, p.w1, 0x0043)), d1 = sext16((int)(p.w1 >> 8));
-  const int d2 = sext16((int)__byte_perm(p.w1, p.w2, 0x0043)), d3 = sext16((int)(p.w2 >> 8));
+// CopeWitData :77-130 for a frame with a good checksum: which registers the four data words land in
+RK_DEV void wit_dispatch(Wit &p, uint32_t type, int d0, int d1, int d2, int d3) {
   switch(type) {
   case 0x51u: p.reg[0] = d0, p.reg[1] = d1, p.reg[2] = d2; break;   // WIT_ACC (+ TEMP)
   case 0x52u: p.reg[3] = d0, p.reg[4] = d1, p.reg[5] = d2; break;   // WIT_GYRO
@@ -161,6 +159,21 @@ RK_DEV void wit_frame(Wit &p) { // a full window (bytes 1..11 of the register) w
   } break;
   default: break; // TIME / DPORT / PRESS / GPS / VELOCITY / GSA write registers the IMU interface never reads; others are ignored
   }
+}
+RK_DEV void wit_frame(Wit &p) { // a full window: bytes 1..11 of the shift register
+  wit_dispatch(p, (p.w0 >> 16) & 0xFFu, sext16((int)__byte_perm(p.w0, p.w1, 0x0043)), sext16((int)(p.w1 >> 8)),
+               sext16((int)__byte_perm(p.w1, p.w2, 0x0043)), sext16((int)(p.w2 >> 8)));
+}
+// Healthy traffic is frames back to back.  With the window empty and 11 bytes of this update at hand, a frame that
+// starts right here with a good checksum is what the byte machine would accept after appending those 11 bytes one by
+// one -- nothing else can happen on the way -- so it is taken in one step; anything else goes through wit_bytes().
+// f0, f1, f2: the 11 bytes, first byte in the low byte of f0.
+RK_DEV bool wit_try_frame(Wit &p, uint32_t f0, uint32_t f1, uint32_t f2) {
+  if((f0 & 0xFFu) != 0x55u) return false;
+  const uint32_t sum = __vsadu4(f0, 0u) + __vsadu4(f1, 0u) + __vsadu4(f2 & 0xFFFFu, 0u);
+  if((sum & 0xFFu) != ((f2 >> 16) & 0xFFu)) return false;
+  wit_dispatch(p, (f0 >> 8) & 0xFFu, sext16((int)(f0 >> 16)), sext16((int)f1), sext16((int)(f1 >> 16)), sext16((int)f2));
+  return true;
 }
 // `rem` (<= 4) bytes, first byte in the low byte of R: WitSerialDataIn for each  :132-164
 RK_DEV void wit_bytes(Wit &p, uint32_t R, uint32_t rem) {
@@ -212,54 +225,124 @@ RK_DEV uint4 wit_save(const Wit &p) {
   return make_uint4(w0, w1, w2 | (p.cnt << 24), p.flags);
 }
 
+// ---- mbarrier + bulk async copy (TMA 1-D) primitives, sm_90+/sm_100a PTX --------------------------------
+RK_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+RK_DEV void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+RK_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+RK_DEV void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+RK_DEV void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RK_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while(!ok);
+}
+// global -> shared bulk copy by the TMA unit, completion counted in bytes on `bar`
+RK_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// The wire arrives through a ring of kWireStages shared-memory stages per CTA, one stage = the 128 consecutive cells
+// of one cell plane (2 KB), filled by bulk async copies that thread 0 keeps kWireStages cells ahead: the byte
+// automaton's irregular pace never exposes HBM latency and no registers are spent on prefetch.  full[s] flips when
+// the bytes have landed, empty[s] when the four warps have taken their cells out of the stage.
+constexpr int kWireStages = 16;
+
 __global__ void __launch_bounds__(128)
 imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int64_t n, int K, int ncells, const uint4 *__restrict__ cells,
                       const uint16_t *__restrict__ nbytes, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
-  float   qi[4];
+  __shared__ __align__(128) uint4 ring[kWireStages][128];
+  __shared__ __align__(8) uint64_t full_bar[kWireStages], empty_bar[kWireStages];
+  const int      tid = threadIdx.x;
+  const int64_t  i0 = (int64_t)blockIdx.x * 128, i = i0 + tid;
+  const bool     live = i < n; // idle lanes of the last CTA still take part in the stage hand-over
+  const uint32_t row_bytes = (uint32_t)min((int64_t)128, n - i0) * 16u;
+  const int64_t  total = (int64_t)K * ncells;
+  if(tid == 0) {
+    for(int s = 0; s < kWireStages; s++) mbar_init(&full_bar[s], 1u), mbar_init(&empty_bar[s], 4u);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t T) { // thread 0: cell plane T -> its stage
+    const int s = (int)(T % kWireStages);
+    mbar_arrive_expect_tx(&full_bar[s], row_bytes);
+    bulk_g2s(&ring[s][0], cells + T * n + i0, row_bytes, &full_bar[s]);
+  };
+  if(tid == 0)
+    for(int64_t T = 0; T < total && T < kWireStages; T++) issue(T);
+  auto fetch = [&](int64_t T) -> uint4 { // this thread's cell of plane T; the stage is refilled once all four warps are through
+    const int      s   = (int)(T % kWireStages);
+    const uint32_t par = (uint32_t)((T / kWireStages) & 1);
+    mbar_wait(&full_bar[s], par);
+    const uint4 v = ring[s][tid];
+    __syncwarp();
+    if((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
+    if(tid == 0 && T + kWireStages < total) {
+      mbar_wait(&empty_bar[s], par);
+      issue(T + kWireStages);
+    }
+    return v;
+  };
+
+  float   qi[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   ImuData cur;
+  uint32_t flags = 0u;
+  Wit      p;
+  const int64_t il = live ? i : 0; // idle lanes read instance 0 and never write
   {
-    const uint4 q = ld_plane(state, n, 0, i);
+    const uint4 q = ld_plane(state, n, 0, il);
     qi[0] = u2f(q.x), qi[1] = u2f(q.y), qi[2] = u2f(q.z), qi[3] = u2f(q.w);
 #pragma unroll
     for(int pl = 0; pl < 4; pl++) {
-      const uint4 v = ld_plane(state, n, 1 + pl, i);
+      const uint4 v = ld_plane(state, n, 1 + pl, il);
       cur.d[4 * pl] = u2f(v.x), cur.d[4 * pl + 1] = u2f(v.y), cur.d[4 * pl + 2] = u2f(v.z), cur.d[4 * pl + 3] = u2f(v.w);
     }
-  }
-  uint32_t flags = ld_plane(state, n, 5, i).x;
-  Wit      p;
-  {
-    const uint4 a = ld_plane(parser, n, 0, i), b = ld_plane(parser, n, 1, i), c = ld_plane(parser, n, 2, i);
+    flags = ld_plane(state, n, 5, il).x;
+    const uint4 a = ld_plane(parser, n, 0, il), b = ld_plane(parser, n, 1, il), c = ld_plane(parser, n, 2, il);
     wit_load(p, a);
     const uint32_t r[8] = {b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
 #pragma unroll
     for(int k = 0; k < 8; k++) p.reg[2 * k] = lo16(r[k]), p.reg[2 * k + 1] = hi16(r[k]);
   }
-  const uint4 *src  = cells + i; // cell t = u * ncells + c of this IMU at src[t * n]
-  const int64_t total = (int64_t)K * ncells;
-  uint4 nxt = total > 0 ? __ldcs(src) : make_uint4(0u, 0u, 0u, 0u);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  // two cells in registers: A is being parsed, B follows it (a frame may straddle into it)
+  uint4    B = total > 0 ? fetch(0) : zero4;
   int64_t  t = 0;
-  uint32_t nb_next = (nbytes && K > 0) ? (uint32_t)__ldcs(nbytes + i) : 0xFFFFFFFFu;
+  uint32_t nb_next = (nbytes && K > 0 && live) ? (uint32_t)__ldcs(nbytes + i) : 0xFFFFFFFFu;
   for(int u = 0; u < K; u++) {
     const bool init = do_init && u == 0;
     if(init) { // WitInit: s_uiWitDataCnt = 0 ; WitReadReg(q0, 4): s_uiReadRegIndex = q0
       p.cnt   = 0u;
       p.flags = (p.flags & ~0xFF00u) | (0x51u << 8);
     }
-    uint32_t left = min(nb_next, 16u * (uint32_t)ncells);
-    if(nbytes && u + 1 < K) nb_next = (uint32_t)__ldcs(nbytes + (int64_t)(u + 1) * n + i); // consumed an update later
+    const uint32_t nb = live ? min(nb_next, 16u * (uint32_t)ncells) : 0u; // bytes on the wire in this update
+    if(nbytes && live && u + 1 < K) nb_next = (uint32_t)__ldcs(nbytes + (int64_t)(u + 1) * n + i); // consumed an update later
+    uint32_t done = 0u; // bytes of this update already parsed
     for(int c = 0; c < ncells; c++) {
-      const uint4 cell = nxt;
+      const uint4 A = B;
       t++;
-      if(t < total) nxt = __ldcs(src + t * n);
-      const uint32_t w[4] = {cell.x, cell.y, cell.z, cell.w};
-#pragma unroll
-      for(int j = 0; j < 4; j++) {
-        const uint32_t v = min(left, 4u);
-        left -= v;
-        wit_bytes(p, w[j], v);
+      B = (t < total) ? fetch(t) : zero4;
+      const uint32_t lo = 16u * (uint32_t)c, end = min(nb, lo + 16u);      // this cell holds bytes [lo, lo + 16) of the update
+      const uint32_t span = min(nb, (c + 1 < ncells) ? lo + 32u : lo + 16u); // ... and B the next 16 when it belongs to the update
+      while(done < end) {
+        const uint32_t off = done - lo, wi = off >> 2, sh = 8u * (off & 3u);
+        const uint32_t x0 = wi == 0u ? A.x : (wi == 1u ? A.y : (wi == 2u ? A.z : A.w));
+        if(p.cnt == 0u && span - done >= 11u) {
+          const uint32_t x1 = wi == 0u ? A.y : (wi == 1u ? A.z : (wi == 2u ? A.w : B.x));
+          const uint32_t x2 = wi == 0u ? A.z : (wi == 1u ? A.w : (wi == 2u ? B.x : B.y));
+          const uint32_t x3 = wi == 0u ? A.w : (wi == 1u ? B.x : (wi == 2u ? B.y : B.z));
+          if(wit_try_frame(p, __funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh))) {
+            done += 11u;
+            continue;
+          }
+        }
+        const uint32_t k = min(4u - (off & 3u), end - done); // the rest of this word, byte by byte semantics
+        wit_bytes(p, x0 >> sh, k);
+        done += k;
       }
     }
     const bool hq = (p.flags & 1u) != 0u; // isComComp :132-143
@@ -275,13 +358,16 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
     } else {
       flags |= RK_IS_FLAG_ERROR;
     }
-    if(yaw_rad) __stcs(yaw_rad + (int64_t)u * n + i, fmul(cur.d[RK_IS_D_ANGLE + 2], RK_DEG2RAD));
-    if(out) {
+    if(live) {
+      if(yaw_rad) __stcs(yaw_rad + (int64_t)u * n + i, fmul(cur.d[RK_IS_D_ANGLE + 2], RK_DEG2RAD));
+      if(out) {
 #pragma unroll
-      for(int pl = 0; pl < 4; pl++)
-        __stcs(out + ((int64_t)u * 4 + pl) * n + i, make_float4(cur.d[4 * pl], cur.d[4 * pl + 1], cur.d[4 * pl + 2], cur.d[4 * pl + 3]));
+        for(int pl = 0; pl < 4; pl++)
+          __stcs(out + ((int64_t)u * 4 + pl) * n + i, make_float4(cur.d[4 * pl], cur.d[4 * pl + 1], cur.d[4 * pl + 2], cur.d[4 * pl + 3]));
+      }
     }
   }
+  if(!live) return;
   st_plane(state, n, 0, i, make_uint4(f2u(qi[0]), f2u(qi[1]), f2u(qi[2]), f2u(qi[3])));
 #pragma unroll
   for(int pl = 0; pl < 4; pl++)
