@@ -76,6 +76,35 @@ def test_header_enums_match_python_layout():
     assert layout.VS_CTRL0 == 48 and layout.VS_MOTOR0 == 80
 
 
+def test_new_block_layouts_match_header(lib):
+    text = open(os.path.join(ROOT, "include", "robotick.h")).read()
+    for name, val in (("RK_IP_FLAGS", layout.IP_FLAGS), ("RK_IP_SREG", layout.IP_SREG), ("RK_IP_WORDS", layout.IP_WORDS),
+                      ("RK_HS_WAIT_CNT", None), ("RK_HS_VEL_DIR", layout.HS_VEL_DIR), ("RK_HS_WORDS", layout.HS_WORDS),
+                      ("RK_RS_NO_CMD_CNT", layout.RS_NO_CMD_CNT), ("RK_RS_ABORT", layout.RS_ABORT), ("RK_RS_WORDS", layout.RS_WORDS),
+                      ("RK_RI_FLOOR", layout.RI_FLOOR), ("RK_RI_WORDS", layout.RI_WORDS), ("RK_RI_X", layout.RI_X)):
+        if val is None:
+            assert name in text
+        else:
+            assert re.search(rf"{name}\s*=\s*{val}\b", text), name
+    assert lib.rk_imt_parser_words() == layout.IP_WORDS and lib.rk_imt_parser_bytes(5) == 5 * 48
+    assert lib.rk_adh_state_words() == layout.HS_WORDS and lib.rk_adh_state_bytes(3) == 3 * 48
+    assert lib.rk_rmt_state_words() == layout.RS_WORDS and lib.rk_rmt_state_bytes(7) == 7 * 16
+    p = _cabi.RmtParams()
+    lib.rk_rmt_default_params(C.byref(p))
+    assert (p.no_cmd_stop_thre, p.wall_leave_time_ms, p.wall_leave_speed_mmps) == (200, 200, 100)  # RM_task_main.cpp:62-64
+    import torch
+
+    if not torch.cuda.is_available():  # no CPU fallback on the new entry points either
+        buf = (C.c_uint32 * 256)()
+        addr = (C.addressof(buf) + 15) & ~15
+        a = C.c_void_p(addr)
+        assert lib.rk_rmt_guard(C.byref(p), a, 1, 1, a, a, None, None) == 2
+        assert lib.rk_imt_feed_bytes(a, a, 1, 1, 1, a, None, None, None, 0, None) == 2
+        assert lib.rk_adh_mode_init(a, 1, 1, None) == 2
+        h = C.c_void_p()
+        assert lib.rk_rmt_create(C.byref(h), None) == 2
+
+
 def test_no_cpu_fallback(lib):
     import torch
 
