@@ -119,7 +119,7 @@ imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__
 struct Wit {
   uint32_t w0, w1, w2, cnt, flags;
   bool     head_ok; // cnt != 0 and the oldest byte of the window is 0x55
-  int      reg[16];
+  uint32_t rw[8];   // the 16 tracked sReg words, two int16 per register (RK_IMT_REG_* order, even slot in the low half)
 };
 RK_DEV void wit_push(Wit &p, uint32_t R, uint32_t k) { // shift the low k (1..4) bytes of R in at the top
   const uint32_t s = 8u * k;
@@ -132,37 +132,38 @@ RK_DEV bool wit_head_is_55(const Wit &p) { // byte at offset 12 - cnt of the reg
   return ((w >> (8u * (off & 3u))) & 0xFFu) == 0x55u;
 }
 RK_DEV void wit_store_reg(Wit &p, uint32_t reg, uint32_t val) { // CopeWitData's memcpy into sReg, tracked registers only
-  const int v = sext16((int)val);
+  const uint32_t slot = (reg >= 0x34u && reg <= 0x3Fu) ? reg - 0x34u : ((reg >= 0x51u && reg <= 0x54u) ? reg - 0x51u + 12u : 0xFFu);
 #pragma unroll
-  for(int k = 0; k < 12; k++)
-    if(reg == 0x34u + k) p.reg[k] = v;
-#pragma unroll
-  for(int k = 0; k < 4; k++)
-    if(reg == 0x51u + k) p.reg[12 + k] = v;
+  for(int k = 0; k < 8; k++) {
+    if(slot == 2u * k) p.rw[k] = __byte_perm(p.rw[k], val, 0x3254);     // low half
+    if(slot == 2u * k + 1u) p.rw[k] = __byte_perm(p.rw[k], val, 0x5410); // high half
+  }
   if(reg == 0x54u) p.flags |= 1u; // q3 -> QUAT_UPDATE (SensorDataUpdata)
 }
-// CopeWitData :77-130 for a frame with a good checksum: which registers the four data words land in
-RK_DEV void wit_dispatch(Wit &p, uint32_t type, int d0, int d1, int d2, int d3) {
-  switch(type) {
-  case 0x51u: p.reg[0] = d0, p.reg[1] = d1, p.reg[2] = d2; break;   // WIT_ACC (+ TEMP)
-  case 0x52u: p.reg[3] = d0, p.reg[4] = d1, p.reg[5] = d2; break;   // WIT_GYRO
-  case 0x54u: p.reg[6] = d0, p.reg[7] = d1, p.reg[8] = d2; break;   // WIT_MAGNETIC
-  case 0x53u: p.reg[9] = d0, p.reg[10] = d1, p.reg[11] = d2; break; // WIT_ANGLE (+ VERSION)
-  case 0x59u:                                                        // WIT_QUATER
-    p.reg[12] = d0, p.reg[13] = d1, p.reg[14] = d2, p.reg[15] = d3;
-    p.flags |= 1u;
-    break;
-  case 0x5Fu: { // WIT_REGVALUE: four registers from s_uiReadRegIndex
+// CopeWitData :77-130 for a frame with a good checksum: which registers the four data words (d01 = d0 | d1 << 16,
+// d23 = d2 | d3 << 16) land in.  The frame type differs from lane to lane and the register file is live across it, so
+// the five fixed types are selects on the packed words; only WIT_REGVALUE (a dynamic register index) branches.
+RK_DEV void wit_dispatch(Wit &p, uint32_t type, uint32_t d01, uint32_t d23) {
+  const bool acc = type == 0x51u, gyr = type == 0x52u, ang = type == 0x53u, mag = type == 0x54u, qut = type == 0x59u;
+  const uint32_t d12 = __byte_perm(d01, d23, 0x5432); // d1 | d2 << 16
+  p.rw[0] = acc ? d01 : p.rw[0];                                                                   // AX AY      <- WIT_ACC (+ TEMP)
+  p.rw[1] = acc ? __byte_perm(p.rw[1], d23, 0x3254) : (gyr ? __byte_perm(p.rw[1], d01, 0x5410) : p.rw[1]); // AZ | GX
+  p.rw[2] = gyr ? d12 : p.rw[2];                                                                   // GY GZ      <- WIT_GYRO
+  p.rw[3] = mag ? d01 : p.rw[3];                                                                   // HX HY      <- WIT_MAGNETIC
+  p.rw[4] = mag ? __byte_perm(p.rw[4], d23, 0x3254) : (ang ? __byte_perm(p.rw[4], d01, 0x5410) : p.rw[4]); // HZ | Roll
+  p.rw[5] = ang ? d12 : p.rw[5];                                                                   // Pitch Yaw  <- WIT_ANGLE (+ VERSION)
+  p.rw[6] = qut ? d01 : p.rw[6];                                                                   // q0 q1      <- WIT_QUATER
+  p.rw[7] = qut ? d23 : p.rw[7];                                                                   // q2 q3
+  p.flags |= qut ? 1u : 0u;
+  if(type == 0x5Fu) { // WIT_REGVALUE: four registers from s_uiReadRegIndex
     const uint32_t r = (p.flags >> 8) & 0xFFu;
-    wit_store_reg(p, r, (uint32_t)d0), wit_store_reg(p, r + 1, (uint32_t)d1), wit_store_reg(p, r + 2, (uint32_t)d2),
-        wit_store_reg(p, r + 3, (uint32_t)d3);
-  } break;
-  default: break; // TIME / DPORT / PRESS / GPS / VELOCITY / GSA write registers the IMU interface never reads; others are ignored
+    wit_store_reg(p, r, d01 & 0xFFFFu), wit_store_reg(p, r + 1, d01 >> 16), wit_store_reg(p, r + 2, d23 & 0xFFFFu), wit_store_reg(p, r + 3, d23 >> 16);
   }
+  // TIME / DPORT / PRESS / GPS / VELOCITY / GSA write registers the IMU interface never reads; other types are ignored
 }
 RK_DEV void wit_frame(Wit &p) { // a full window: bytes 1..11 of the shift register
-  wit_dispatch(p, (p.w0 >> 16) & 0xFFu, sext16((int)__byte_perm(p.w0, p.w1, 0x0043)), sext16((int)(p.w1 >> 8)),
-               sext16((int)__byte_perm(p.w1, p.w2, 0x0043)), sext16((int)(p.w2 >> 8)));
+  const uint32_t f0 = __funnelshift_r(p.w0, p.w1, 8), f1 = __funnelshift_r(p.w1, p.w2, 8), f2 = p.w2 >> 8;
+  wit_dispatch(p, (f0 >> 8) & 0xFFu, __byte_perm(f0, f1, 0x5432), __byte_perm(f1, f2, 0x5432));
 }
 // Healthy traffic is frames back to back.  With the window empty and 11 bytes of this update at hand, a frame that
 // starts right here with a good checksum is what the byte machine would accept after appending those 11 bytes one by
@@ -172,8 +173,12 @@ RK_DEV bool wit_try_frame(Wit &p, uint32_t f0, uint32_t f1, uint32_t f2) {
   if((f0 & 0xFFu) != 0x55u) return false;
   const uint32_t sum = __vsadu4(f0, 0u) + __vsadu4(f1, 0u) + __vsadu4(f2 & 0xFFFFu, 0u);
   if((sum & 0xFFu) != ((f2 >> 16) & 0xFFu)) return false;
-  wit_dispatch(p, (f0 >> 8) & 0xFFu, sext16((int)(f0 >> 16)), sext16((int)f1), sext16((int)(f1 >> 16)), sext16((int)f2));
+  wit_dispatch(p, (f0 >> 8) & 0xFFu, __byte_perm(f0, f1, 0x5432), __byte_perm(f1, f2, 0x5432));
   return true;
+}
+RK_DEV void wit_regs(const Wit &p, int r[16]) { // the register file as updateData reads it
+#pragma unroll
+  for(int k = 0; k < 8; k++) r[2 * k] = lo16(p.rw[k]), r[2 * k + 1] = hi16(p.rw[k]);
 }
 // `rem` (<= 4) bytes, first byte in the low byte of R: WitSerialDataIn for each  :132-164
 RK_DEV void wit_bytes(Wit &p, uint32_t R, uint32_t rem) {
@@ -304,9 +309,7 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
     flags = ld_plane(state, n, 5, il).x;
     const uint4 a = ld_plane(parser, n, 0, il), b = ld_plane(parser, n, 1, il), c = ld_plane(parser, n, 2, il);
     wit_load(p, a);
-    const uint32_t r[8] = {b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-    for(int k = 0; k < 8; k++) p.reg[2 * k] = lo16(r[k]), p.reg[2 * k + 1] = hi16(r[k]);
+    p.rw[0] = b.x, p.rw[1] = b.y, p.rw[2] = b.z, p.rw[3] = b.w, p.rw[4] = c.x, p.rw[5] = c.y, p.rw[6] = c.z, p.rw[7] = c.w;
   }
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   // two cells in registers: A is being parsed, B follows it (a frame may straddle into it)
@@ -347,14 +350,16 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
     }
     const bool hq = (p.flags & 1u) != 0u; // isComComp :132-143
     if(hq) p.flags &= ~0xFFu;
-    if(init) {
-      imu_update_data(qi, p.reg, cur);
-      const float S = 1.0f / 32768.0f;
+    if(init || hq) {
+      int r[16];
+      wit_regs(p, r);
+      if(!init) flags &= ~RK_IS_FLAG_ERROR;
+      imu_update_data(qi, r, cur);
+      if(init) { // q_init latched from q0..q3  :72-75
+        const float S = 1.0f / 32768.0f;
 #pragma unroll
-      for(int k = 0; k < 4; k++) qi[k] = fmul((float)p.reg[RK_IMT_REG_Q0 + k], S);
-    } else if(hq) {
-      flags &= ~RK_IS_FLAG_ERROR;
-      imu_update_data(qi, p.reg, cur);
+        for(int k = 0; k < 4; k++) qi[k] = fmul((float)r[RK_IMT_REG_Q0 + k], S);
+      }
     } else {
       flags |= RK_IS_FLAG_ERROR;
     }
@@ -373,12 +378,9 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
   for(int pl = 0; pl < 4; pl++)
     st_plane(state, n, 1 + pl, i, make_uint4(f2u(cur.d[4 * pl]), f2u(cur.d[4 * pl + 1]), f2u(cur.d[4 * pl + 2]), f2u(cur.d[4 * pl + 3])));
   st_plane(state, n, 5, i, make_uint4(flags, 0u, 0u, 0u));
-  uint32_t r[8];
-#pragma unroll
-  for(int k = 0; k < 8; k++) r[k] = pack16(p.reg[2 * k], p.reg[2 * k + 1]);
   st_plane(parser, n, 0, i, wit_save(p));
-  st_plane(parser, n, 1, i, make_uint4(r[0], r[1], r[2], r[3]));
-  st_plane(parser, n, 2, i, make_uint4(r[4], r[5], r[6], r[7]));
+  st_plane(parser, n, 1, i, make_uint4(p.rw[0], p.rw[1], p.rw[2], p.rw[3]));
+  st_plane(parser, n, 2, i, make_uint4(p.rw[4], p.rw[5], p.rw[6], p.rw[7]));
 }
 
 } // namespace rk
