@@ -113,8 +113,8 @@ imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__
 // head is 0x55 and no frame can complete inside the run; single bytes are handled only while sliding.
 // The window is a 96-bit shift register (w2:w1:w0) whose TOP cnt bytes are the parser's buffer, oldest
 // byte lowest: appending k bytes is three funnel shifts by 8k, dropping the head is cnt-- and a full
-// frame always sits at fixed positions (bytes 1..11).  Bytes arrive as 128-bit cells, 512 B per warp
-// per load, the next cell in flight while this one is parsed.
+// frame always sits at fixed positions (bytes 1..11).  Bytes arrive as 128-bit cells through a
+// shared-memory ring the TMA unit keeps sixteen cell planes ahead (see imt_feed_bytes_kernel).
 // ---------------------------------------------------------------------------------------------
 struct Wit {
   uint32_t w0, w1, w2, cnt, flags;
