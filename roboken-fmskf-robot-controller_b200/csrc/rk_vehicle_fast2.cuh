@@ -139,25 +139,26 @@ RK_DEV void from_fast2(Veh &v, const FastVeh2 &f, int nticks) {
 // collapsed plant.  The odometry product fma(d, K_hi, d*K_lo) is proven for every step the unwrap can produce
 // (|d| <= 2^17, rk_exact.cu), so no frame can leave the fast path's domain.
 struct StreamSense {
-  int32_t ang[4], rpm[4], cur[4]; // head Status: s16_rawAngle, s16_rawSpeedRpm, s16_rawCurr after the direction is applied
+  int32_t ang[4]; // head Status s16_rawAngle (direction applied): the one status word the next frame's unwrap needs.
+                  // s16_rawSpeedRpm / s16_rawCurr are rewritten by the next rx_callback before anything reads them, and
+                  // every launch ends on a transcription tick, so they are not carried through the fast ticks.
 };
 RK_DEV void stream_sense_load(StreamSense &ss, const Veh &v) {
 #pragma unroll
-  for(int k = 0; k < 4; k++) ss.ang[k] = v.m[k].ang, ss.rpm[k] = v.m[k].rpm, ss.cur[k] = v.m[k].cur;
+  for(int k = 0; k < 4; k++) ss.ang[k] = v.m[k].ang;
 }
 template <int DIR>
 RK_DEV float2 fast_wheel_rx2(StreamSense &ss, int k, int32_t &dsum, uint64_t frame, const FastConsts &fc) {
-  const uint32_t lo = (uint32_t)frame, hi = (uint32_t)(frame >> 32);
+  const uint32_t lo = (uint32_t)frame;
   const int32_t  a = sext16((int32_t)(__byte_perm(lo, 0, 0x4401))); // (b0<<8)|b1
   const int32_t  r = sext16((int32_t)(__byte_perm(lo, 0, 0x4423))); // (b2<<8)|b3
-  const int32_t  c = sext16((int32_t)(__byte_perm(hi, 0, 0x4401))); // (b4<<8)|b5
   const int32_t  raw_ang = (DIR == 1) ? a : sext16(8192 - a);
   int32_t        d       = sext16(raw_ang - ss.ang[k]);
   d                      = (d > 4096) ? sext16(d - 8192) : ((d < -4096) ? sext16(d + 8192) : d);
   dsum += d;
-  ss.ang[k] = raw_ang, ss.rpm[k] = sext16(r * DIR), ss.cur[k] = sext16(c * DIR);
+  ss.ang[k] = raw_ang;
   const float df = (float)d;
-  return make_float2(fmul(fmul((float)ss.rpm[k], RK_RPM_TO_RADPS), RK_GEAR_RATIO_INV), __fmaf_rn(df, fc.k_hi, fmul(df, fc.k_lo)));
+  return make_float2(fmul(fmul((float)sext16(r * DIR), RK_RPM_TO_RADPS), RK_GEAR_RATIO_INV), __fmaf_rn(df, fc.k_hi, fmul(df, fc.k_lo)));
 }
 RK_DEV void from_fast2_stream(Veh &v, const FastVeh2 &f, const StreamSense &ss, int nticks) {
   if(nticks <= 0) return;
@@ -168,7 +169,7 @@ RK_DEV void from_fast2_stream(Veh &v, const FastVeh2 &f, const StreamSense &ss, 
     Motor &m = v.m[k];
     m.sum += (int64_t)w[k].dsum;
     m.prev = m.sum;
-    m.ang = ss.ang[k], m.rpm = ss.rpm[k], m.cur = ss.cur[k];
+    m.ang = ss.ang[k]; // rpm / cur: see StreamSense
     m.cur_tgt = w[k].cur;
     m.head    = (m.head + nticks) % 3;
   }
