@@ -1,27 +1,31 @@
 #!/usr/bin/env python3
-"""bench.py -- robot-instance control steps/s of the fused vehicle rollout on N B200s.
+"""bench.py -- robot-instance control steps/s of the full controller tick on N B200s (BASELINE.json configs[4]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload full|vehicle]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch.
-  --workload vehicle (default; BASELINE.json configs[1]): one launch of the fused rollout kernel over
+  --workload full (default; BASELINE.json configs[4]): the full controller tick -- vehicle at 1 kHz, IMU
+      update + arm tick at 100 Hz, coupled through the IMU yaw -- over `--total` robots (2^24)
+      batch-sharded across the GPUs (strong scaling), run in chunks of `--chunk` robots x `--ticks` fused ticks.
+      The configs[1] / [2] / [3] module numbers ride along under "modules".
+  --workload vehicle (BASELINE.json configs[1]): one launch of the fused rollout kernel over
       `--instances` vehicles per GPU x `--ticks` 1 kHz control ticks, closed loop through the
       integer motor plant.  Weak scaling (per-GPU batch fixed).
-  --workload full (BASELINE.json configs[4]): the full controller tick -- vehicle at 1 kHz, IMU
-      update + arm tick at 100 Hz, coupled through the IMU yaw -- over `--total` robots (2^24)
-      batch-sharded across the GPUs (strong scaling), run in chunks of `--chunk` robots.
 Rank 0 prints ONE JSON line (see DESIGN.md "Measurement").
 
   value        whole-job instance-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e          the same metric through the C-ABI with HOST (pinned) command/yaw tables copied
-               H2D and the per-instance cost vector copied D2H inside the timed region
-  roofline     algorithmic FP32 flops (183 per tick) / launch duration against
-               the FP32 FFMA peak measured live by rk_probe_fp32 (MEASURED_PEAKS.json carries no
-               FP32 entry); the HBM side of the same launch is reported under roofline["hbm"]
+  e2e          the same metric through the C-ABI starting from HOST memory: per chunk a 48-byte stream
+               descriptor (seed, first robot, distribution parameters) is copied H2D, the rk_stream_* kernels
+               expand it into the command / sensor tables on the device, the rollout runs, the per-robot cost
+               vector is copied D2H -- all inside the timed region
+  roofline     algorithmic FP32 flops of the dominant kernel (183 per vehicle tick) / its
+               slot of the timed region, against the FP32 FFMA peak measured live by rk_probe_fp32
+               (MEASURED_PEAKS.json carries no FP32 entry); HBM figures of the step under roofline["step"]
   cpu_baseline the reference's own sources compiled for x86 (oracle/_ref) -- or the plain-C port
                if the prebuilt .so is absent -- on the box's host cores, bounded sample
   --impl reference   times only that CPU implementation and prints the same JSON shape
+The parity spot check (sampled robots of the exact bench launch against the oracle) runs on EVERY rank.
 """
 import argparse
 import ctypes as C
@@ -50,7 +54,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vehicle", choices=["vehicle", "full"])
+    ap.add_argument("--workload", default="full", choices=["vehicle", "full"])
     ap.add_argument("--instances", type=int, default=1 << 20, help="vehicles per GPU (workload vehicle)")
     ap.add_argument("--total", type=int, default=1 << 24, help="robots over all GPUs (workload full)")
     ap.add_argument("--chunk", type=int, default=1 << 20, help="robots per rk_tick_rollout call (workload full)")
@@ -59,12 +63,11 @@ def parse():
     ap.add_argument("--ticks", type=int, default=1000, help="fused control ticks per launch")
     ap.add_argument("--seg-len", type=int, default=125)
     ap.add_argument("--yaw-period", type=int, default=10)
-    ap.add_argument("--yaw-format", choices=("reg", "rad"), default="reg",
-                    help="vehicle workload: yaw input as the WT901C Yaw register (int16, what the sensor sends; default) "
-                         "or as float32 radians")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall budget of the cpu_baseline leg")
     ap.add_argument("--occupancy", type=int, default=0, help="RK_OPT_FAST_OCCUPANCY override (tuning)")
     ap.add_argument("--packed", type=int, default=-1, help="RK_OPT_FAST_PACKED override (tuning; -1 = library default)")
+    ap.add_argument("--side-ctas", type=int, default=-1, help="RK_OPT_TICK_SIDE_CTAS override (tuning; -1 = library default)")
+    ap.add_argument("--no-modules", action="store_true", help="workload full: skip the configs[1..3] module measurements")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -79,7 +82,7 @@ def workload_name(a):
     return (f"configs[1]: {a.instances} mecanum vehicles/GPU x {a.ticks} fused 1 kHz ticks "
             f"(rx_callback + FK/odometry + 3x const-jerk target + IK + 4x FF_PI_D + current saturation), "
             f"closed loop through the integer motor plant, command every {a.seg_len} ticks, yaw every {a.yaw_period}"
-            + (" as the WT901C Yaw register (int16)" if a.yaw_format == "reg" else " as float32 radians"))
+            " as the WT901C Yaw register (int16)")
 
 
 # ------------------------------------------------------------------------------------------
@@ -108,13 +111,11 @@ class CpuArm:
         a = self.a
         threads = threads or self.threads
         if n not in self._inp:
-            inp = self.wl.plant_inputs(n, a.ticks, seed=0x5EED, seg_len=a.seg_len, yaw_period=a.yaw_period)
-            if getattr(a, "yaw_format", "rad") == "reg" and a.workload != "full":
-                from roboken_fmskf_robot_controller_b200 import streams
+            from roboken_fmskf_robot_controller_b200 import streams
 
-                inp["yaw"] = streams.vehicle_yaw_reg(n, inp["yaw"].shape[0], 0x5EED, 0)
-            ro = self.ol.HostRollout(n, a.ticks, self._cabi.RK_SENSOR_PLANT, inp["cmd"], inp["seg_len"], inp["yaw"],
-                                     inp["yaw_period"])
+            n_seg, n_yaw = (a.ticks + a.seg_len - 1) // a.seg_len, (a.ticks + a.yaw_period - 1) // a.yaw_period
+            inp = dict(cmd=streams.vehicle_commands_v2(n, n_seg, 0x5EED, 0), yaw=streams.vehicle_yaw_reg_v2(n, n_yaw, 0x5EED, 0))
+            ro = self.ol.HostRollout(n, a.ticks, self._cabi.RK_SENSOR_PLANT, inp["cmd"], a.seg_len, inp["yaw"], a.yaw_period)
             self._inp[n] = (inp, ro)
         _, ro = self._inp[n]
         t0 = time.perf_counter()
@@ -153,9 +154,9 @@ def _full_cpu_worker(job):
     key = (n, first, ticks, slow, seg_len, seed)
     if key not in _FULL_CACHE:
         n_seg, n_slow = (ticks + seg_len - 1) // seg_len, (ticks + slow - 1) // slow
-        cmd = streams.vehicle_commands(n, n_seg, seed, first)
-        regs, have = streams.imu_samples(n, n_slow + 1, seed=seed, first=first, drop_every=64)
-        seq = layout.aos_to_soa(streams.arm_sequences(n, seed=seed, first=first, seq_id=1, max_len=32))
+        cmd = streams.vehicle_commands_v2(n, n_seg, seed, first)
+        regs, have = streams.imu_samples_v2(n, n_slow + 1, seed=seed, first=first, drop_every=64)
+        seq = layout.aos_to_soa(streams.arm_sequences_v2(n, seed=seed, first=first, seq_id=1, max_len=32))
         _FULL_CACHE.clear()
         _FULL_CACHE[key] = (cmd, regs, have, seq)
     cmd, regs, have, seq = _FULL_CACHE[key]
@@ -335,13 +336,125 @@ def hbm_peak_measured():
 
 
 # ------------------------------------------------------------------------------------------
-# GPU arm
+# helpers shared by the GPU arms
+# ------------------------------------------------------------------------------------------
+def timed_launches(fn, stream, reps, warm=2):
+    """Average duration (ms) of fn() over `reps` back-to-back calls on `stream`, CUDA events on that stream."""
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def all_ranks_ok(ok, dev):
+    """True iff `ok` on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        return bool(ok)
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item() > 0.5)
+
+
+def oracle_kind():
+    import oracle_lib as ol
+
+    have = all(os.path.exists(os.path.join(ol.ORACLE, "_ref", f)) for f in ("libref_vdt.so", "libref_imu.so", "libref_arm.so"))
+    return ("ref", "the reference's own sources compiled for x86 (oracle/_ref)") if have else ("port", "the plain-C port (oracle/)")
+
+
+def vehicle_module(a, lib, dev, stream, peaks):
+    """BASELINE configs[1] on this GPU: 2^20 vehicles x 1000 fused ticks, device-resident inputs; the dominant kernel alone."""
+    import torch
+
+    from roboken_fmskf_robot_controller_b200 import _cabi
+    from roboken_fmskf_robot_controller_b200.devstreams import DeviceStreams
+    from roboken_fmskf_robot_controller_b200.vehicle import VehicleBatch
+
+    n, T = a.instances, a.ticks
+    n_seg, n_yaw = (T + a.seg_len - 1) // a.seg_len, (T + a.yaw_period - 1) // a.yaw_period
+    ds = DeviceStreams(dev, seed=0x5EED, first=0)
+    cmd = ds.vehicle_commands(torch.empty((n_seg, n, 4), dtype=torch.int32, device=dev))
+    yaw = ds.vehicle_yaw_reg(torch.empty((n_yaw, n), dtype=torch.int16, device=dev))
+    vb = VehicleBatch(n, dev)
+    args = vb.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=cmd, seg_len=a.seg_len, yaw=yaw, yaw_period=a.yaw_period)
+    ms = timed_launches(lambda: vb.rollout_args(args, stream=stream), stream, 5)
+    ffma, issue = peaks
+    tf = FLOP_PER_TICK * n * T / (ms * 1e-3) / 1e12
+    return {"workload": f"configs[1]: {n} vehicles x {T} fused 1 kHz ticks, closed loop through the integer plant, Yaw-register input",
+            "kernel": "rk::vdt_rollout_fast_kernel", "value": n * T / (ms * 1e-3), "unit": UNIT, "ms_per_launch": ms,
+            "roofline": {"bound": "fp32", "achieved": tf, "peak": ffma, "unit": "TFLOP/s", "frac": tf / ffma,
+                         "frac_of_nonfused_issue_peak": tf / issue, "algorithmic_flop_per_tick": FLOP_PER_TICK}}
+
+
+def imu_module(a, dev, stream, hbm):
+    """BASELINE configs[2]: 2^20 IMUs x 64 fused updates with the full Data page written back per update."""
+    import torch
+
+    from roboken_fmskf_robot_controller_b200.devstreams import DeviceStreams
+    from roboken_fmskf_robot_controller_b200.imu import ImuBatch
+
+    n, K = a.instances, 64
+    ds = DeviceStreams(dev, seed=3, first=0)
+    regs, have = ds.imu_samples(torch.empty((K, 2, n, 8), dtype=torch.int16, device=dev), torch.empty((K, n), dtype=torch.uint8, device=dev))
+    ib = ImuBatch(n, dev)
+    ib.update(regs[:1].contiguous(), None, None, do_init=True)
+    out = torch.empty((K, 4, n, 4), dtype=torch.float32, device=dev)
+    ms = timed_launches(lambda: ib.update(regs, have, out), stream, 5)
+    nbytes = n * (K * (32 + 1 + 64) + 2 * 96)
+    peak, src = hbm
+    return {"workload": f"configs[2]: {n} WT901 IMUs x {K} fused updates, Data page written per update", "kernel": "rk::imt_update_kernel",
+            "value": n * K / (ms * 1e-3), "unit": "IMU updates/s", "ms_per_launch": ms,
+            "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "peak_source": src, "algorithmic_bytes_per_update": 97}}
+
+
+def arm_module(a, dev, stream):
+    """BASELINE configs[3]: 2^20 arms x 1000 fused 100 Hz ticks, one PosCmdSeq each."""
+    import torch
+
+    from roboken_fmskf_robot_controller_b200 import layout
+    from roboken_fmskf_robot_controller_b200.arm import ArmBatch
+    from roboken_fmskf_robot_controller_b200.devstreams import DeviceStreams
+
+    n, K = a.instances, 1000
+    ds = DeviceStreams(dev, seed=0xC4, first=0, arm_seq_id=9)
+    seq = ds.arm_sequences(torch.empty(layout.ACMD_SLOT_WORDS * n, dtype=torch.int32, device=dev))
+    ab = ArmBatch(n, dev)
+
+    def setup():
+        ab.mode_init(stream=stream)
+        ab.push_cmdseq(seq, stream=stream)
+
+    def full():
+        setup()
+        ab.update(K, stream=stream)
+
+    ms = timed_launches(full, stream, 5) - timed_launches(setup, stream, 5)
+    return {"workload": f"configs[3]: {n} 5-axis arms x {K} fused 100 Hz ticks, one PosCmdSeq each", "kernel": "rk::adt_update_kernel",
+            "value": n * K / (ms * 1e-3), "unit": "arm ticks/s", "ms_per_launch": ms,
+            "roofline": {"bound": "issue", "achieved": 46 * n * K / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "algorithmic_flop_per_tick": 46}}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm, workload "vehicle" (BASELINE configs[1], weak scaling)
 # ------------------------------------------------------------------------------------------
 def run_ours(a):
     import torch
 
     import roboken_fmskf_robot_controller_b200 as rk
     from roboken_fmskf_robot_controller_b200 import _cabi, layout, sharding, streams
+    from roboken_fmskf_robot_controller_b200.devstreams import DeviceStreams
     from roboken_fmskf_robot_controller_b200.vehicle import VehicleBatch
 
     lib = rk.load()  # raises if the CUDA library is not built: no fallback
@@ -351,7 +464,6 @@ def run_ours(a):
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = sharding.bind_to_gpu_numa(local_rank) if world > 1 else None  # pinned host tables local to the GPU's PCIe root
     _cabi.check(lib.rk_set_device(local_rank))
     if a.occupancy:
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_OCCUPANCY, a.occupancy))
@@ -361,41 +473,37 @@ def run_ours(a):
     first = rank * n  # contiguous slice of the global instance index space
     n_seg = (T + a.seg_len - 1) // a.seg_len
     n_yaw = (T + a.yaw_period - 1) // a.yaw_period
+    stream = torch.cuda.current_stream(dev)
+    clocks = ClockSampler(local_rank)
 
-    # ---- synthetic inputs, generated on the host (pinned) ---------------------------------
-    cmd_h = torch.from_numpy(streams.vehicle_commands(n, n_seg, 0x5EED, first).view(np.int32).reshape(n_seg, n, 4)).pin_memory()
-    if a.yaw_format == "reg":
-        yaw_h = torch.from_numpy(streams.vehicle_yaw_reg(n, n_yaw, 0x5EED, first)).pin_memory()
-    else:
-        yaw_h = torch.from_numpy(streams.vehicle_yaw(n, n_yaw, 0x5EED, first)).pin_memory()
-    goal_h = torch.zeros((n, 2), dtype=torch.float32).pin_memory()
-    cmd_d, yaw_d, goal_d = cmd_h.to(dev), yaw_h.to(dev), goal_h.to(dev)
+    # ---- synthetic inputs, generated on the device from a 48-byte descriptor ----------------
+    seed = 0x5EED
+    ds = DeviceStreams(dev, seed=seed, first=first)
+    cmd_d = ds.vehicle_commands(torch.empty((n_seg, n, 4), dtype=torch.int32, device=dev))
+    yaw_d = ds.vehicle_yaw_reg(torch.empty((n_yaw, n), dtype=torch.int16, device=dev))
+    goal_d = torch.zeros((n, 2), dtype=torch.float32, device=dev)
     cost_d = torch.zeros(n, dtype=torch.float32, device=dev)
     vb = VehicleBatch(n, dev)
     args = vb.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=cmd_d, seg_len=a.seg_len, yaw=yaw_d,
                         yaw_period=a.yaw_period, goal=goal_d, cost=cost_d)
-    keep = [cmd_d, yaw_d, goal_d, cost_d]
-    stream = torch.cuda.current_stream(dev)
-    clocks = ClockSampler(local_rank)
 
-    # ---- parity spot check of the exact bench launch (first pass, power-on state) ----------
+    # ---- parity spot check of the exact bench launch (first pass, power-on state), every rank -----
     vb.rollout_args(args)
     torch.cuda.synchronize()
-    spot = None
-    if rank == 0:
-        import oracle_lib as ol
+    import oracle_lib as ol
 
-        idx = np.unique(np.concatenate([[0, n - 1], np.random.default_rng(0).integers(0, n, 62)]))
-        cmd_np = cmd_h.numpy().view(streams.vehicle_commands(1, 1).dtype).reshape(n_seg, n)
-        ro = ol.HostRollout(len(idx), T, _cabi.RK_SENSOR_PLANT, np.ascontiguousarray(cmd_np[:, idx]), a.seg_len,
-                            np.ascontiguousarray(yaw_h.numpy()[:, idx]), a.yaw_period)
-        exp = np.zeros(layout.VS_WORDS * len(idx), dtype=np.uint32)
-        ol.run_port(exp, len(idx), ro, nthreads=min(8, host_threads()))
-        got = layout.soa_to_aos(vb.state.cpu().numpy().view(np.uint32), n, layout.VS_WORDS)[idx]
-        same = np.array_equal(got, layout.soa_to_aos(exp, len(idx), layout.VS_WORDS))
-        spot = f"{len(idx)} sampled instances x {T} ticks {'bit-exact' if same else 'MISMATCH'} vs oracle"
-        if not same:
-            raise SystemExit("bench parity spot check failed: " + spot)
+    idx = np.unique(np.concatenate([[0, n - 1], np.random.default_rng(rank).integers(0, n, 62)]))
+    gidx = idx.astype(np.uint64) + np.uint64(first)
+    ro = ol.HostRollout(len(idx), T, _cabi.RK_SENSOR_PLANT, streams.vehicle_commands_v2(0, n_seg, seed, inst=gidx), a.seg_len,
+                        streams.vehicle_yaw_reg_v2(0, n_yaw, seed, inst=gidx), a.yaw_period)
+    exp = np.zeros(layout.VS_WORDS * len(idx), dtype=np.uint32)
+    kind, kind_desc = oracle_kind()
+    (ol.run_ref if kind == "ref" else ol.run_port)(exp, len(idx), ro, nthreads=min(8, host_threads()))
+    got = layout.soa_to_aos(vb.state.cpu().numpy().view(np.uint32), n, layout.VS_WORDS)[idx]
+    same = all_ranks_ok(np.array_equal(got, layout.soa_to_aos(exp, len(idx), layout.VS_WORDS)), dev)
+    spot = f"{len(idx)} sampled instances x {T} ticks on each of {world} rank(s) {'bit-exact' if same else 'MISMATCH'} vs {kind_desc}"
+    if not same:
+        raise SystemExit("bench parity spot check failed: " + spot)
 
     # ---- value: inputs resident in HBM -----------------------------------------------------
     for _ in range(max(W - 1, 0)):
@@ -418,10 +526,9 @@ def run_ours(a):
 
     ffma_tflops, issue_tflops, sm_count = fp32_probes(lib, local_rank, dev, stream)
     hbm_peak, hbm_src = hbm_peak_measured()
-
     launch_s = ms_local * 1e-3 / K
     achieved_tflops = FLOP_PER_TICK * n * T / launch_s / 1e12
-    alg_bytes = n * (2 * STATE_BYTES + n_seg * 16 + n_yaw * yaw_h.element_size() + 8 + 4)  # state ld+st, cmd, yaw, goal, cost
+    alg_bytes = n * (2 * STATE_BYTES + n_seg * 16 + n_yaw * 2 + 8 + 4)  # state ld+st, cmd, yaw, goal, cost
     roofline = {
         "bound": "fp32",
         "achieved": achieved_tflops, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / ffma_tflops,
@@ -429,46 +536,38 @@ def run_ours(a):
         "nonfused_issue_peak": issue_tflops,
         "frac_of_nonfused_issue_peak": achieved_tflops / issue_tflops,
         "algorithmic_flop_per_tick": FLOP_PER_TICK,
-        "kernel": "rk::vdt_rollout_fast_kernel<false,OCC>",
+        "kernel": "rk::vdt_rollout_fast_kernel",
         "launch_ms": launch_s * 1e3,
-        "traffic": None,
+        "traffic": traffic_note("vdt_rollout_plant_bytes_per_launch"),
         "hbm": {"achieved": alg_bytes / launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / launch_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": alg_bytes},
         "sm_count": sm_count,
     }
-    traffic_note = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_note):
-        try:
-            roofline["traffic"] = json.load(open(traffic_note)).get("vdt_rollout_plant_bytes_per_launch")
-        except Exception:
-            pass
 
-    # ---- e2e: host tables in, costs out, through the same C-ABI call ------------------------
+    # ---- e2e: descriptor in (pinned host -> device), tables expanded on the device, costs out ----
     e2e = None
     if not a.no_e2e:
-        copy_s = torch.cuda.Stream(dev)  # H2D
-        back_s = torch.cuda.Stream(dev)  # D2H: its wait for the rollout must not hold up the next step's H2D
-        comp_s = torch.cuda.Stream(dev)
+        gen_s, comp_s, back_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         bufs = []
         for b in range(2):
             c, y = torch.empty_like(cmd_d), torch.empty_like(yaw_d)
             co = torch.zeros(n, dtype=torch.float32, device=dev)
             bufs.append(dict(cmd=c, yaw=y, cost=co, cost_h=torch.empty(n, dtype=torch.float32).pin_memory(),
+                             ds=DeviceStreams(dev, seed=seed, first=first),
                              args=vb.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=c, seg_len=a.seg_len, yaw=y,
                                                yaw_period=a.yaw_period, goal=goal_d, cost=co),
                              up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event()))
-            keep += [c, y, co]
-        h2d = cmd_h.numel() * 4 + yaw_h.numel() * yaw_h.element_size()
-        d2h = n * 4
+        h2d, d2h = DeviceStreams.NBYTES, n * 4
 
         def e2e_pass(s):
             b = bufs[s % 2]
-            with torch.cuda.stream(copy_s):
-                copy_s.wait_event(b["done"])  # buffer free again (previous use computed)
-                b["cmd"].copy_(cmd_h, non_blocking=True)
-                b["yaw"].copy_(yaw_h, non_blocking=True)
-                b["up"].record(copy_s)
+            with torch.cuda.stream(gen_s):
+                gen_s.wait_event(b["done"])  # buffer free again (previous use computed)
+                b["ds"].upload(gen_s)
+                b["ds"].vehicle_commands(b["cmd"], gen_s)
+                b["ds"].vehicle_yaw_reg(b["yaw"], gen_s)
+                b["up"].record(gen_s)
             with torch.cuda.stream(comp_s):
                 comp_s.wait_event(b["up"])
                 comp_s.wait_event(b["down"])  # cost buffer drained
@@ -487,14 +586,12 @@ def run_ours(a):
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clocks.start()
         t0e.record(stream)
-        copy_s.wait_stream(stream)
-        back_s.wait_stream(stream)
-        comp_s.wait_stream(stream)
+        for st_ in (gen_s, back_s, comp_s):
+            st_.wait_stream(stream)
         for s in range(K):
             e2e_pass(s)
-        stream.wait_stream(copy_s)
-        stream.wait_stream(back_s)
-        stream.wait_stream(comp_s)
+        for st_ in (gen_s, back_s, comp_s):
+            stream.wait_stream(st_)
         t1e.record(stream)
         torch.cuda.synchronize()
         clocks.pause()
@@ -502,10 +599,9 @@ def run_ours(a):
         ms_e = sharding.max_over_ranks(t0e.elapsed_time(t1e), dev)
         e2e = {"value": world * n * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / K,
-               "path": "rk_vdt_rollout() via ctypes; pinned host cmd+yaw tables H2D, state reset to power-on, "
-                       "cost vector D2H, double-buffered: H2D, rollout and D2H on three streams",
-               "host_numa_node": numa}
-        launches += 0  # e2e launches are outside the `value` region; gpu_launches counts that region
+               "path": "per step: 48-byte stream descriptor pinned host -> device, rk_stream_vehicle_commands + "
+                       "rk_stream_vehicle_yaw_reg expand it on the device, state reset to power-on, rk_vdt_rollout() via "
+                       "ctypes, cost vector D2H; double-buffered on three streams"}
 
     # ---- optional NCCL gather of the summary costs (outside the timed regions) --------------
     gather_ms = None
@@ -540,7 +636,7 @@ def run_ours(a):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "instances_per_gpu": n, "ticks_per_launch": T,
                        "l2": f"inputs larger than L2: {n * STATE_BYTES >> 20} MiB state + "
-                             f"{(cmd_h.numel() * 4 + yaw_h.numel() * yaw_h.element_size()) >> 20} MiB tables per pass vs 126 MB L2",
+                             f"{(cmd_d.numel() * 4 + yaw_d.numel() * 2) >> 20} MiB tables per pass vs 126 MB L2",
                        "parity_spot_check": spot},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
@@ -554,11 +650,19 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def traffic_note(key):
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(key)
+    except Exception:
+        return None
+
 
 # ------------------------------------------------------------------------------------------
-# GPU arm, workload "full" (BASELINE configs[4])
+# GPU arm, workload "full" (BASELINE configs[4], the default)
 # ------------------------------------------------------------------------------------------
 FLOP_PER_FULL_STEP = 183 + 1 + (55 + 46) / 10.0  # vehicle + deg2rad + (IMU + arm) at 1/10 rate
+FULL_BYTES_PER_ROBOT = 4  # filled in run_ours_full
 
 
 def run_ours_full(a):
@@ -566,6 +670,7 @@ def run_ours_full(a):
 
     import roboken_fmskf_robot_controller_b200 as rk
     from roboken_fmskf_robot_controller_b200 import _cabi, layout, sharding, streams
+    from roboken_fmskf_robot_controller_b200.devstreams import DeviceStreams
     from roboken_fmskf_robot_controller_b200.robot import RobotBatch
 
     lib = rk.load()
@@ -575,52 +680,63 @@ def run_ours_full(a):
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = sharding.bind_to_gpu_numa(local_rank) if world > 1 else None  # pinned host tables local to the GPU's PCIe root
     _cabi.check(lib.rk_set_device(local_rank))
     if a.occupancy:
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_OCCUPANCY, a.occupancy))
+    if a.side_ctas >= 0:
+        _cabi.check(lib.rk_set_option(_cabi.RK_OPT_TICK_SIDE_CTAS, a.side_ctas))
     K, W, T, slow = a.steps, a.warmup, a.ticks, a.slow_period
     lo, hi = sharding.shard_range(a.total, rank, world)
     n_rank = hi - lo
     n = min(a.chunk, n_rank)
-    assert n_rank % n == 0, "--total / --gpus must be a multiple of --chunk"
+    assert n_rank % n == 0 and a.total % world == 0, "--total / --gpus must be a multiple of --chunk"
     n_chunks = n_rank // n
     n_seg, n_slow = (T + a.seg_len - 1) // a.seg_len, (T + slow - 1) // slow
     stream = torch.cuda.current_stream(dev)
     clocks = ClockSampler(local_rank)
-
-    # ---- synthetic inputs of ONE chunk (every chunk replays them; states are per chunk) ----------
     seed = 0x5EED
-    cmd_np = streams.vehicle_commands(n, n_seg, seed, lo)
-    # the IMU register stream is generated for 2^16 distinct robots and tiled over the chunk (hashing 1.7e9
-    # register words on the host would take minutes); commands and arm sequences are distinct per robot
-    uniq = min(n, 1 << 16)
-    assert n % uniq == 0
-    regs_np, have_np = streams.imu_samples(uniq, n_slow + 1, seed=seed, first=lo, drop_every=64)
-    regs_np, have_np = np.tile(regs_np, (1, 1, n // uniq)), np.tile(have_np, (1, n // uniq))
-    seq_np = streams.arm_sequences(n, seed=seed, first=lo, seq_id=1, max_len=32)
-    cmd_h = torch.from_numpy(cmd_np.view(np.int32).reshape(n_seg, n, 4)).pin_memory()
-    regs_h = torch.from_numpy(streams.imu_cells(regs_np[1:])).pin_memory()  # two 128-bit cells per sample
-    have_h = torch.from_numpy(np.ascontiguousarray(have_np[1:])).pin_memory()
-    seq_h = torch.from_numpy(layout.aos_to_soa(seq_np).view(np.int32)).pin_memory()
+
+    # ---- synthetic inputs: every chunk's tables expanded on the device from its 48-byte descriptor; resident in HBM
+    # for the `value` region (distinct per chunk when they fit, else one set replayed by every chunk) ----------------
+    per_robot_in = n_seg * 16 + n_slow * 33 + layout.ACMD_SLOT_WORDS * 4
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    distinct = n_chunks * n * (per_robot_in + 4 * (layout.VS_WORDS + layout.IS_WORDS + layout.AS_WORDS)) + 4 * n * (per_robot_in + 4 * layout.ACMD_WORDS) < 0.85 * free_b
+
+    def alloc_tables():
+        return dict(cmd=torch.empty((n_seg, n, 4), dtype=torch.int32, device=dev),
+                    regs=torch.empty((n_slow, 2, n, 8), dtype=torch.int16, device=dev),
+                    have=torch.empty((n_slow, n), dtype=torch.uint8, device=dev),
+                    seq=torch.empty(layout.ACMD_SLOT_WORDS * n, dtype=torch.int32, device=dev))
+
+    def generate(ds, tb, st=None):
+        ds.vehicle_commands(tb["cmd"], st)
+        ds.imu_samples(tb["regs"], tb["have"], st)
+        ds.arm_sequences(tb["seq"], st)
+
+    def chunk_desc(c):
+        return DeviceStreams(dev, seed=seed, first=lo + c * n, first_update=1, arm_seq_id=1)
+
     goal_d = torch.zeros((n, 2), dtype=torch.float32, device=dev)
-    cmd_d, regs_d, have_d, seq_d = cmd_h.to(dev), regs_h.to(dev), have_h.to(dev), seq_h.to(dev)
-    # chunks alternate over `lanes` streams so that the bandwidth-bound kernels of one chunk (ring push, IMU) overlap
-    # the issue-bound vehicle rollout of another; each lane owns its yaw scratch and command ring
     lanes = max(1, min(a.lanes, 4))
     lane_s = [torch.cuda.Stream(dev) for _ in range(lanes)]
-    yaws = [torch.zeros((n_slow, n), dtype=torch.float32, device=dev) for _ in range(lanes)]
+    yaws = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(lanes)]
     rings = [torch.zeros(layout.ACMD_WORDS * n, dtype=torch.int32, device=dev) for _ in range(lanes)]
-    yaw_d = yaws[0]
-    boot = torch.from_numpy(streams.imu_cells(regs_np[:1])).to(dev)
-    chunks = []
+    tables, chunks = [], []
+    boot = torch.empty((1, 2, n, 8), dtype=torch.int16, device=dev)
     for c in range(n_chunks):
+        ds = chunk_desc(c)
+        if distinct or c == 0:
+            tb = alloc_tables()
+            generate(ds, tb)
+            tables.append(tb)
+        tb = tables[c if distinct else 0]
         rb = RobotBatch(n, dev, arm_cmdtab=rings[c % lanes])
-        rb.imu.update(boot, None, None, do_init=True)  # IMU_IF_WT901C::init() at boot
+        DeviceStreams(dev, seed=seed, first=lo + c * n, first_update=0).imu_samples(boot, None)
+        rb.imu.update(boot, None, None, do_init=True)  # IMU_IF_WT901C::init() at boot consumes sample 0
         cost = torch.zeros(n, dtype=torch.float32, device=dev)
-        args = rb.make_args(T, slow, cmd=cmd_d, seg_len=a.seg_len, regs=regs_d, have_quat=have_d, yaw=yaws[c % lanes], goal=goal_d,
-                            cost=cost)
-        chunks.append((rb, cost, args))
+        args = rb.make_args(T, slow, cmd=tb["cmd"], seg_len=a.seg_len, regs=tb["regs"], have_quat=tb["have"], yaw=yaws[c % lanes],
+                            goal=goal_d, cost=cost)
+        chunks.append(dict(rb=rb, cost=cost, args=args, tb=tb, ds=ds))
     torch.cuda.synchronize()
 
     def one_pass():
@@ -628,37 +744,48 @@ def run_ours_full(a):
         from and join the current stream, so events recorded on it bracket the whole pass."""
         for ls in lane_s:
             ls.wait_stream(stream)
-        for c, (rb, _, args) in enumerate(chunks):
+        for c, ch in enumerate(chunks):
             ls = lane_s[c % lanes]
-            rb.arm.mode_init(stream=ls)
-            rb.arm.push_cmdseq(seq_d, stream=ls)
-            rb.rollout_args(args, stream=ls)
+            ch["rb"].arm.mode_init(stream=ls)
+            ch["rb"].arm.push_cmdseq(ch["tb"]["seq"], stream=ls)
+            ch["rb"].rollout_args(ch["args"], stream=ls)
         for ls in lane_s:
             stream.wait_stream(ls)
 
-    # ---- parity spot check of the exact bench launch (first pass of chunk 0) ---------------------
+    # ---- parity spot check of the exact bench launch (first pass), on EVERY rank: robots sampled from the first,
+    # a middle and the last chunk of the rank against the oracle on host-generated copies of their streams ----------
     one_pass()
     torch.cuda.synchronize()
-    spot = None
-    if rank == 0:
-        import oracle_lib as ol
+    import oracle_lib as ol
 
-        rb0 = chunks[0][0]
-        idx = np.unique(np.concatenate([[0, n - 1], np.random.default_rng(0).integers(0, n, 46)]))
+    kind, kind_desc = oracle_kind()
+    same, m_total = True, 0
+    for c in sorted({0, n_chunks // 2, n_chunks - 1}):
+        rbc = chunks[c]["rb"]
+        idx = np.unique(np.concatenate([[0, n - 1], np.random.default_rng(1000 * rank + c).integers(0, n, 30)]))
+        gidx = idx.astype(np.uint64) + np.uint64(lo + (c if distinct else 0) * n)
         m = len(idx)
-        v, i_, ar, tb = (np.zeros(w * m, dtype=np.uint32) for w in (layout.VS_WORDS, layout.IS_WORDS, layout.AS_WORDS, layout.ACMD_WORDS))
-        sub = lambda x: np.ascontiguousarray(x[..., idx])
-        ol.imu_port(i_, m, sub(regs_np[:1]), None, do_init=True)
-        ol.arm_batch("port", "init", ar, tb, m)
-        ol.arm_batch("port", "push", ar, tb, m, seq=layout.aos_to_soa(seq_np[idx]))
-        ol.full_tick("port", m, T, slow, sub(cmd_np), a.seg_len, sub(regs_np[1:]), sub(have_np[1:]), v, i_, ar, tb, nthreads=min(8, host_threads()))
-        same = True
-        for got, exp, words in ((rb0.vehicle.state, v, layout.VS_WORDS), (rb0.imu.state, i_, layout.IS_WORDS), (rb0.arm.state, ar, layout.AS_WORDS)):
+        m_total += m
+        cmd_np = streams.vehicle_commands_v2(0, n_seg, seed, inst=gidx)
+        regs_np, have_np = streams.imu_samples_v2(0, n_slow + 1, seed, inst=gidx)
+        if not distinct:  # boot samples are per chunk even when the tables are shared
+            regs_np[:1] = streams.imu_samples_v2(0, 1, seed, inst=idx.astype(np.uint64) + np.uint64(lo + c * n))[0]
+        seq_np = streams.arm_sequences_v2(0, seed, inst=gidx, seq_id=1)
+        v, i_, ar, tb_ = (np.zeros(w * m, dtype=np.uint32) for w in (layout.VS_WORDS, layout.IS_WORDS, layout.AS_WORDS, layout.ACMD_WORDS))
+        (ol.imu_ref if kind == "ref" else ol.imu_port)(i_, m, regs_np[:1], None, do_init=True)
+        ol.arm_batch(kind, "init", ar, tb_, m)
+        ol.arm_batch(kind, "push", ar, tb_, m, seq=layout.aos_to_soa(seq_np))
+        _, _, _, cost_np = ol.full_tick(kind, m, T, slow, cmd_np, a.seg_len, np.ascontiguousarray(regs_np[1:]), np.ascontiguousarray(have_np[1:]),
+                                        v, i_, ar, tb_, goal=np.zeros((m, 2), dtype=np.float32), nthreads=min(8, host_threads()))
+        for got, exp, words in ((rbc.vehicle.state, v, layout.VS_WORDS), (rbc.imu.state, i_, layout.IS_WORDS), (rbc.arm.state, ar, layout.AS_WORDS)):
             g = layout.soa_to_aos(got.cpu().numpy().view(np.uint32), n, words)[idx]
             same &= np.array_equal(g, layout.soa_to_aos(exp, m, words))
-        spot = f"{m} sampled robots x {T} ticks (vehicle + IMU + arm state) {'bit-exact' if same else 'MISMATCH'} vs oracle"
-        if not same:
-            raise SystemExit("bench parity spot check failed: " + spot)
+        same &= np.array_equal(chunks[c]["cost"].cpu().numpy()[idx].view(np.uint32), np.asarray(cost_np, dtype=np.float32).view(np.uint32))
+    same = all_ranks_ok(same, dev)
+    spot = (f"{m_total} sampled robots x {T} ticks (vehicle + IMU + arm state, rollout cost) on each of {world} rank(s) "
+            f"{'bit-exact' if same else 'MISMATCH'} vs {kind_desc}")
+    if not same:
+        raise SystemExit("bench parity spot check failed: " + spot)
 
     # ---- value: inputs resident in HBM -----------------------------------------------------------
     for _ in range(max(W - 1, 0)):
@@ -677,65 +804,63 @@ def run_ours_full(a):
     ms_local = ev0.elapsed_time(ev1)
     ms = sharding.max_over_ranks(ms_local, dev)
     value = a.total * T * K / (ms * 1e-3)
-    launches = K * n_chunks * 5  # mode_init, push, arm update, IMU update, vehicle rollout
+    launches = K * n_chunks * 6  # mode_init, push, yaw snapshot, IMU update, arm update, vehicle rollout
 
-    # ---- dominant kernel alone (the vehicle rollout fed by the yaw stream), for the roofline -----
-    rb0 = chunks[0][0]
-    vargs = rb0.vehicle.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=cmd_d, seg_len=a.seg_len, yaw=yaw_d, yaw_period=slow,
-                                  goal=goal_d, cost=chunks[0][1])
-    rb0.vehicle.rollout_args(vargs)
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record(stream)
-    for _ in range(5):
-        rb0.vehicle.rollout_args(vargs)
-    k1.record(stream)
-    torch.cuda.synchronize()
-    launch_s = k0.elapsed_time(k1) * 1e-3 / 5
+    # ---- roofline of the dominant kernel: its share of the timed region, and timed alone -----------------------------
     ffma_tflops, issue_tflops, sm_count = fp32_probes(lib, local_rank, dev, stream)
-    hbm_peak, hbm_src = hbm_peak_measured()
-    achieved = FLOP_PER_TICK * n * T / launch_s / 1e12
-    step_bytes = n_rank * (2 * (448 + 96 + 304) + n_seg * 16 + n_slow * (32 + 1 + 8) + 1040 * 2 + 8 + 4)
+    hbm = hbm_peak_measured()
     step_s = ms_local * 1e-3 / K
+    chunk_s = step_s / n_chunks  # one chunk's slot of the timed region: its vehicle rollout with the IMU / arm kernels in its shadow
+    rb0 = chunks[0]["rb"]
+    vargs = rb0.vehicle.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=chunks[0]["tb"]["cmd"], seg_len=a.seg_len, goal=goal_d,
+                                  cost=chunks[0]["cost"])
+    vargs.d_imu_regs, vargs.d_imu_have_quat = chunks[0]["tb"]["regs"].data_ptr(), chunks[0]["tb"]["have"].data_ptr()
+    vargs.d_imu_yaw0_deg, vargs.n_yaw, vargs.yaw_period = yaws[0].data_ptr(), n_slow, slow
+    alone_ms = timed_launches(lambda: rb0.vehicle.rollout_args(vargs, stream=stream), stream, 5)
+    achieved = FLOP_PER_TICK * n * T / chunk_s / 1e12
+    step_bytes = n_rank * (2 * 4 * (layout.VS_WORDS + layout.IS_WORDS + layout.AS_WORDS) + n_seg * 16 + n_slow * (33 + 16 + 1) +
+                           2 * 4 * layout.ACMD_SLOT_WORDS + 8 + 4 + 8)
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": achieved / ffma_tflops,
         "peak_source": "rk_probe_fp32 FFMA chains, measured live in this run (no FP32 entry in MEASURED_PEAKS.json)",
         "nonfused_issue_peak": issue_tflops, "frac_of_nonfused_issue_peak": achieved / issue_tflops,
-        "algorithmic_flop_per_tick": FLOP_PER_TICK, "kernel": "rk::vdt_rollout_fast_kernel (dominant kernel, timed alone on one chunk)",
-        "launch_ms": launch_s * 1e3, "traffic": None,
+        "algorithmic_flop_per_tick": FLOP_PER_TICK,
+        "kernel": "rk::vdt_rollout_fast_kernel (dominant kernel)",
+        "launch_ms": chunk_s * 1e3,
+        "launch_ms_note": "timed region / vehicle launches in it: the kernel's slot including the IMU, arm and ring-push kernels that "
+                          "run in its shadow (CUDA events on the launching streams' parent)",
+        "launch_ms_alone": alone_ms, "frac_alone": FLOP_PER_TICK * n * T / (alone_ms * 1e-3) / 1e12 / ffma_tflops,
+        "traffic": traffic_note("vdt_rollout_imu_regs_bytes_per_launch"),
         "step": {"algorithmic_flop_per_robot_step": FLOP_PER_FULL_STEP,
                  "achieved_tflops": FLOP_PER_FULL_STEP * n_rank * T / step_s / 1e12,
                  "frac_of_ffma_peak": FLOP_PER_FULL_STEP * n_rank * T / step_s / 1e12 / ffma_tflops,
                  "algorithmic_bytes": step_bytes, "hbm_gbs": step_bytes / step_s / 1e9,
-                 "hbm_frac": step_bytes / step_s / 1e9 / hbm_peak, "hbm_peak_source": hbm_src},
+                 "hbm_frac": step_bytes / step_s / 1e9 / hbm[0], "hbm_peak_source": hbm[1]},
         "sm_count": sm_count,
     }
 
-    # ---- e2e: host tables in, costs out, through rk_tick_rollout ----------------------------------
+    # ---- e2e: per chunk a 48-byte descriptor in, tables expanded on the device, costs out, through rk_tick_rollout ----
     e2e = None
     if not a.no_e2e:
-        copy_s, comp_s, back_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        gen_s, comp_s, back_s = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         bufs = []
         for b in range(2):
-            d = dict(cmd=torch.empty_like(cmd_d), regs=torch.empty_like(regs_d), have=torch.empty_like(have_d),
-                     seq=torch.empty_like(seq_d), cost=torch.zeros(n, dtype=torch.float32, device=dev),
-                     cost_h=torch.empty(n, dtype=torch.float32).pin_memory(), up=torch.cuda.Event(), done=torch.cuda.Event(),
-                     down=torch.cuda.Event())
+            d = alloc_tables()
+            d.update(cost=torch.zeros(n, dtype=torch.float32, device=dev), cost_h=torch.empty(n, dtype=torch.float32).pin_memory(),
+                     up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event())
             bufs.append(d)
-        h2d = n_chunks * 4 * (cmd_h.numel() + seq_h.numel()) + n_chunks * (2 * regs_h.numel() + have_h.numel())
-        d2h = n_chunks * n * 4
+        h2d, d2h = n_chunks * DeviceStreams.NBYTES, n_chunks * n * 4
         argcache = {}
 
         def e2e_pass(s):
-            for c, (rb, _, _) in enumerate(chunks):
+            for c, ch in enumerate(chunks):
                 b = bufs[(s * n_chunks + c) % 2]
-                with torch.cuda.stream(copy_s):
-                    copy_s.wait_event(b["done"])
-                    b["cmd"].copy_(cmd_h, non_blocking=True)
-                    b["regs"].copy_(regs_h, non_blocking=True)
-                    b["have"].copy_(have_h, non_blocking=True)
-                    b["seq"].copy_(seq_h, non_blocking=True)
-                    b["up"].record(copy_s)
+                rb = ch["rb"]
+                with torch.cuda.stream(gen_s):
+                    gen_s.wait_event(b["done"])
+                    ch["ds"].upload(gen_s)
+                    generate(ch["ds"], b, gen_s)
+                    b["up"].record(gen_s)
                 with torch.cuda.stream(comp_s):
                     comp_s.wait_event(b["up"])
                     comp_s.wait_event(b["down"])
@@ -745,7 +870,7 @@ def run_ours_full(a):
                     key = (c, (s * n_chunks + c) % 2)
                     if key not in argcache:
                         argcache[key] = rb.make_args(T, slow, cmd=b["cmd"], seg_len=a.seg_len, regs=b["regs"], have_quat=b["have"],
-                                                     yaw=yaw_d, goal=goal_d, cost=b["cost"])
+                                                     yaw=yaws[0], goal=goal_d, cost=b["cost"])
                     rb.rollout_args(argcache[key], stream=comp_s)
                     b["done"].record(comp_s)
                 with torch.cuda.stream(back_s):
@@ -760,14 +885,12 @@ def run_ours_full(a):
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clocks.start()
         t0e.record(stream)
-        copy_s.wait_stream(stream)
-        back_s.wait_stream(stream)
-        comp_s.wait_stream(stream)
+        for st_ in (gen_s, back_s, comp_s):
+            st_.wait_stream(stream)
         for s in range(K):
             e2e_pass(s)
-        stream.wait_stream(copy_s)
-        stream.wait_stream(back_s)
-        stream.wait_stream(comp_s)
+        for st_ in (gen_s, back_s, comp_s):
+            stream.wait_stream(st_)
         t1e.record(stream)
         torch.cuda.synchronize()
         clocks.pause()
@@ -775,8 +898,20 @@ def run_ours_full(a):
         ms_e = sharding.max_over_ranks(t0e.elapsed_time(t1e), dev)
         e2e = {"value": a.total * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / K,
-               "path": "rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout via ctypes per chunk; pinned host command, IMU-register "
-                       "and arm-sequence tables H2D, vehicle reset to power-on, cost vector D2H, double-buffered: H2D, compute and D2H on three streams"}
+               "path": "per chunk: 48-byte stream descriptor pinned host -> device; rk_stream_vehicle_commands / rk_stream_imu_samples / "
+                       "rk_stream_arm_sequences expand it into the command, IMU-register and arm-sequence tables on the device (4.5 KB per "
+                       "robot that never cross PCIe); vehicle reset to power-on; rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout via "
+                       "ctypes; cost vector D2H; generation, compute and D2H double-buffered on three streams"}
+
+    # ---- the module configurations (BASELINE configs[1..3]) on this GPU, outside the timed regions ----------------------
+    modules = None
+    if rank == 0 and not a.no_modules:
+        for ch in chunks[1:]:
+            ch.clear()  # release the chunk tables before the modules allocate theirs
+        del chunks[1:], tables[1:]
+        torch.cuda.empty_cache()
+        modules = {"vehicle": vehicle_module(a, lib, dev, stream, (ffma_tflops, issue_tflops)), "imu": imu_module(a, dev, stream, hbm),
+                   "arm": arm_module(a, dev, stream)}
 
     clk = clocks.result()
     cpu = None
@@ -791,10 +926,10 @@ def run_ours_full(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "robots_total": a.total, "robots_per_gpu": n_rank, "chunk": n, "lanes": lanes, "ticks_per_launch": T,
-                       "l2": f"inputs larger than L2: {(cmd_h.numel() * 4 + regs_h.numel() * 2 + seq_h.numel() * 4) >> 20} MiB tables + "
-                             f"{n * 848 >> 20} MiB state per chunk vs 126 MB L2",
+                       "tables": "distinct per chunk" if distinct else "one chunk's tables replayed by every chunk (HBM budget)",
+                       "l2": f"inputs larger than L2: {n * per_robot_in >> 20} MiB tables + {n * 848 >> 20} MiB state per chunk vs 126 MB L2",
                        "parity_spot_check": spot},
-            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "modules": modules,
         }
         emit(line)
     if world > 1:

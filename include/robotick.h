@@ -57,8 +57,10 @@ int rk_set_device(int device);
  * are bit-identical; the tests compare them). */
 enum {
   RK_OPT_FORCE_TRANSCRIPTION = 1,
-  RK_OPT_FAST_OCCUPANCY = 2, /* 3, 4 (default) or 5 resident CTAs/SM: register budget of the rollout kernel */
-  RK_OPT_FAST_PACKED = 3     /* 1 (default): packed FADD2/FFMA2 tick; 0: scalar tick.  Bit-identical; tests compare. */
+  RK_OPT_FAST_OCCUPANCY = 2, /* 3 or 4 (default) resident CTAs/SM: register budget of the rollout kernel */
+  RK_OPT_FAST_PACKED = 3,    /* 1 (default): packed FADD2/FFMA2 tick; 0: scalar tick.  Bit-identical; tests compare. */
+  RK_OPT_TICK_SIDE_CTAS = 4  /* rk_tick_rollout: CTAs per SM its IMU / arm kernels may occupy beside the vehicle
+                              * rollout (default 1; 0 = full grids).  Scheduling only, results do not depend on it. */
 };
 int rk_set_option(int option, int value);
 /* 1 if the exhaustive on-device proofs that gate the issue-optimised kernel hold for these
@@ -202,6 +204,16 @@ typedef struct rk_vdt_rollout {
    * angle[2] = reg / 32768.0f * 180.0f (IMU_IF_WT901C::updateData, imu_if_wt901c.cpp:100) -> getYawDate() ->
    * mymath::deg2rad (VD_task_main.cpp:368).  Half the bytes of d_yaw -- the rollout's largest input. */
   const int16_t *d_yaw_reg;
+  /* the yaw straight from the IMU's register snapshots (used when d_yaw and d_yaw_reg are NULL): d_imu_regs is
+   * the block rk_imt_update() consumes (two 128-bit cells per sample; sample y is taken before tick
+   * y*yaw_period), d_imu_have_quat its have_quat flags ([n_yaw][n], NULL = all 1).  The vehicle forms what
+   * IMT::get_status_now_yaw() returns after IMU update y -- the Yaw register scaled as updateData() does, held
+   * over updates without a quaternion frame (imu_if_wt901c.cpp:83-89,100,160) -- so the rollout does not wait for
+   * the IMU kernel.  d_imu_yaw0_deg (float[n], may be NULL = keep the vehicle's yaw word): Data.angle[2] of the
+   * IMU block at launch, the value held when update 0 carries no quaternion frame. */
+  const int16_t *d_imu_regs;
+  const uint8_t *d_imu_have_quat;
+  const float *d_imu_yaw0_deg;
 } rk_vdt_rollout_t;
 
 /* VEHICLE_CTRL::update() x steps   (VD_vehicle_controller.cpp:6-99), fused with the callers
@@ -487,10 +499,12 @@ int  rk_adt_set_state(rk_adt_t *h, const uint32_t words[RK_AS_WORDS]);
  * `slow_period` vehicle ticks (10: the tasks run at 100 Hz, imu_task_main.cpp:17,
  * AD_task_main.cpp loop), coupled exactly as the firmware couples them: the vehicle ISR reads
  * deg2rad(IMU yaw) before every update (VD_task_main.cpp:368).  Slow tick k runs before
- * vehicle tick k * slow_period.  The three sub-systems are independent apart from that yaw
- * stream, so the call runs the IMU kernel, then the vehicle rollout fed by the yaw stream it
- * emitted, with the arm kernel concurrent on an internal side stream; it is asynchronous on
- * `stream` like every other batch call.
+ * vehicle tick k * slow_period.  The three sub-systems are independent apart from that yaw:
+ * the vehicle rollout forms it from the IMU's register snapshots itself (rk_vdt_rollout_t::
+ * d_imu_regs), so no kernel waits for another -- the IMU update and the arm tick run on an
+ * internal high-priority side stream inside the vehicle rollout's shadow (csrc/rk_tick.cu).
+ * The call is asynchronous on `stream` like every other batch call; concurrent callers on one
+ * device are serialised while they enqueue.
  * ===================================================================================== */
 typedef struct rk_tick_rollout {
   int32_t steps;             /* K vehicle ticks */
@@ -499,7 +513,7 @@ typedef struct rk_tick_rollout {
   int32_t n_seg, seg_len;
   const int16_t *d_regs;     /* IMU samples as rk_imt_update takes them (two 128-bit cells each), n_slow = ceil(K / slow_period) */
   const uint8_t *d_have_quat;/* [n_slow][n] or NULL */
-  float *d_yaw;              /* scratch, n_slow * n floats: the yaw stream (radians) */
+  float *d_yaw;              /* scratch, >= n floats (receives Data.angle[2] of every IMU block as it was at launch) */
   const float *d_goal;       /* optional cost epilogue, as rk_vdt_rollout_t */
   float *d_cost;
   uint32_t *d_vdt_trace;     /* optional traces (tests) */
@@ -508,6 +522,34 @@ typedef struct rk_tick_rollout {
 
 int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t *ap, void *d_vdt_state, void *d_imt_state,
                     void *d_adt_state, const void *d_adt_cmdtab, int64_t n, const rk_tick_rollout_t *args, void *stream);
+
+/* =====================================================================================
+ * Synthetic command / sensor streams, generated on the device.  A rollout engine fed over PCIe
+ * is bound by the host link (the full tick consumes 4.5 KB of tables per robot and launch); a planner ships the
+ * distribution, not the samples.  Each call expands a descriptor held in DEVICE memory into the block the
+ * corresponding engine entry consumes, for the n robots first .. first + n - 1 of the global index space.  The
+ * streams are defined by streams.py (`*_v2`, a 32-bit counter hash of (seed, stream, robot, index)); the kernels
+ * reproduce them bit for bit (tests/test_streams_gpu.py).
+ * ===================================================================================== */
+typedef struct rk_stream_desc {
+  int64_t  first;             /* global index of the batch's robot 0 (robots are hashed modulo 2^32) */
+  uint32_t seed;
+  uint32_t first_update;      /* IMU: update index of sample 0 */
+  uint32_t stop_every;        /* vehicle commands: one segment in stop_every is a STOP (0: never) */
+  uint32_t drop_every;        /* IMU: one update in drop_every carries no quaternion frame (0: never) */
+  uint32_t arm_min_len, arm_max_len, arm_seq_id, arm_dt_zero_every;
+  uint32_t rsv[2];
+} rk_stream_desc_t; /* 48 bytes */
+void rk_stream_default_desc(rk_stream_desc_t *d); /* seed 0x5EED, first 0, 8, 64, 2..32 waypoints, id 1, 4 */
+/* [n_seg][n] rk_vdt_cmd_t (RK_CMD_MOVE / RK_CMD_STOP): vx, vy ~ U[-400, 400] mm/s through speed_limit_xy
+ * (VD_task_main.cpp:127-137), vth ~ U[-2 pi, 2 pi] through speed_limit_rot (:139-142) */
+int rk_stream_vehicle_commands(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_seg, rk_vdt_cmd_t *d_cmd, void *stream);
+/* int16 [n_yaw][n]: the WT901C Yaw register of a vehicle turning at a constant 1..5 x 182 counts per sample */
+int rk_stream_vehicle_yaw_reg(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_yaw, int16_t *d_yaw_reg, void *stream);
+/* WT901 register snapshots in the two-cells-per-sample layout of rk_imt_update (+ have_quat [n_upd][n], may be NULL) */
+int rk_stream_imu_samples(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat, void *stream);
+/* one PosCmdSeq per arm as the 65-plane slot image rk_adt_push_cmdseq takes */
+int rk_stream_arm_sequences(const rk_stream_desc_t *d_desc, int64_t n, void *d_seq, void *stream);
 
 /* =====================================================================================
  * RobotManager guard: the vehicle-management block of RMT's routine_ros()

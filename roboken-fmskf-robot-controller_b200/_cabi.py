@@ -21,6 +21,7 @@ RK_VDT_TRACE_WORDS = 16
 RK_OPT_FORCE_TRANSCRIPTION = 1
 RK_OPT_FAST_OCCUPANCY = 2
 RK_OPT_FAST_PACKED = 3
+RK_OPT_TICK_SIDE_CTAS = 4
 
 
 class VdtParams(C.Structure):
@@ -87,6 +88,9 @@ class VdtRollout(C.Structure):
         ("d_cost", C.c_void_p),
         ("task_period", C.c_int32),
         ("d_yaw_reg", C.c_void_p),
+        ("d_imu_regs", C.c_void_p),
+        ("d_imu_have_quat", C.c_void_p),
+        ("d_imu_yaw0_deg", C.c_void_p),
     ]
 
 
@@ -116,6 +120,23 @@ class AdtPosCmdSeq(C.Structure):
     """rk_adt_poscmdseq_t == ADTModePositioningSeq::PosCmdSeq (:20-24), 776 bytes"""
 
     _fields_ = [("id", C.c_uint32), ("len", C.c_uint8), ("cmd", AdtPosCmd * 32)]
+
+
+class StreamDesc(C.Structure):
+    """rk_stream_desc_t"""
+
+    _fields_ = [
+        ("first", C.c_int64),
+        ("seed", C.c_uint32),
+        ("first_update", C.c_uint32),
+        ("stop_every", C.c_uint32),
+        ("drop_every", C.c_uint32),
+        ("arm_min_len", C.c_uint32),
+        ("arm_max_len", C.c_uint32),
+        ("arm_seq_id", C.c_uint32),
+        ("arm_dt_zero_every", C.c_uint32),
+        ("rsv", C.c_uint32 * 2),
+    ]
 
 
 class TickRollout(C.Structure):
@@ -173,6 +194,12 @@ def _proto(lib):
     lib.rk_imt_feed_bytes.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int, vp]
     lib.rk_tick_rollout.argtypes = [C.POINTER(VdtParams), C.POINTER(AdtParams), vp, vp, vp, vp, C.c_int64,
                                     C.POINTER(TickRollout), vp]
+    lib.rk_stream_default_desc.argtypes = [C.POINTER(StreamDesc)]
+    lib.rk_stream_default_desc.restype = None
+    lib.rk_stream_vehicle_commands.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
+    lib.rk_stream_vehicle_yaw_reg.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
+    lib.rk_stream_imu_samples.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp]
+    lib.rk_stream_arm_sequences.argtypes = [vp, C.c_int64, vp, vp]
     lib.rk_rmt_default_params.argtypes = [C.POINTER(RmtParams)]
     lib.rk_rmt_default_params.restype = None
     lib.rk_rmt_state_words.restype = C.c_size_t

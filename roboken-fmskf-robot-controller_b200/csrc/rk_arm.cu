@@ -13,13 +13,6 @@
 namespace rk {
 int div_const_exact(float c); // rk_exact.cu: 2 = exact for all x, 1 = for x == 0 or |x| >= 2^-40, 0 = no
 
-// (int32_t)(float) as the x86 build of the firmware source performs it: cvttss2si, which
-// returns INT_MIN for NaN / out of range (F2I.TRUNC saturates instead).
-RK_DEV int32_t f2i_x86(float f) {
-  const int32_t r = __float2int_rz(f);
-  return (fabsf(f) < 2147483648.0f) ? r : (int32_t)0x80000000u;
-}
-
 // IcsBaseClass::degPos100 / posDeg100   lib/IcsClass_V210/src/IcsBaseClass.cpp:105-137
 // (|deg| <= 18000 so the products fit 32 bits; C division truncates toward zero)
 RK_DEV int ics_degPos100(int deg) {
@@ -499,11 +492,8 @@ RK_DEV void arm_trace_row(uint32_t *tr, int64_t n, const ArmLoop &a, uint32_t w1
 }
 
 template <bool TRACE, int DIVC>
-__global__ void __launch_bounds__(128, 4)
-adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
-                  uint32_t *__restrict__ trace, float mg_rcp) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
+RK_DEV void adt_update_body(int64_t i, const rk_adt_params_t &p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
+                            uint32_t *__restrict__ trace, float mg_rcp) {
   ArmLoop  a;
   uint32_t jflags;
   loop_load(state, n, i, a, jflags);
@@ -533,6 +523,14 @@ adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint
     }
   }
   loop_store(state, n, i, a, jflags, K > 0);
+}
+// One thread per arm; CTAs stride over the batch when the grid is capped (see imt_update_kernel).
+template <bool TRACE, int DIVC>
+__global__ void __launch_bounds__(128, 4)
+adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
+                  uint32_t *__restrict__ trace, float mg_rcp) {
+  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    adt_update_body<TRACE, DIVC>(i, p, state, tab, n, K, trace, mg_rcp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1105,6 +1103,13 @@ int rk_adt_push_cmdseq(void *d_state, void *d_cmdtab, int64_t n, const void *d_s
 }
 
 int rk_adt_update(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab, int64_t n, int32_t K, uint32_t *d_trace, void *stream) {
+  return rk::adt_update_launch(p, d_state, d_cmdtab, n, K, d_trace, 0, stream);
+}
+} // extern "C"
+
+// max_ctas > 0: at most that many CTAs (each strides over the batch)
+int rk::adt_update_launch(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab, int64_t n, int32_t K, uint32_t *d_trace,
+                          int max_ctas, void *stream) {
   if(n == 0 || K == 0) return RK_OK;
   if(!p || K < 0 || !d_cmdtab) {
     set_error("rk_adt_update: params / cmdtab NULL or K < 0");
@@ -1115,8 +1120,10 @@ int rk_adt_update(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab,
   const int   divc = div_const_exact(ct); // exhaustive on-device proof, cached per constant
   const float rcp  = divc ? 1.0f / ct : 0.0f; // one correctly rounded host division: RN(1/c)
   cudaStream_t st  = (cudaStream_t)stream;
+  unsigned grid = adt_grid(n);
+  if(max_ctas > 0 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;
 #define RK_LAUNCH_ADT(TR, DV) \
-  adt_update_kernel<TR, DV><<<adt_grid(n), 128, 0, st>>>(*p, (uint4 *)d_state, (const uint4 *)d_cmdtab, n, K, d_trace, rcp)
+  adt_update_kernel<TR, DV><<<grid, 128, 0, st>>>(*p, (uint4 *)d_state, (const uint4 *)d_cmdtab, n, K, d_trace, rcp)
   if(d_trace) {
     if(divc == 2) RK_LAUNCH_ADT(true, 2);
     else if(divc == 1) RK_LAUNCH_ADT(true, 1);
@@ -1130,6 +1137,8 @@ int rk_adt_update(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab,
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
+
+extern "C" {
 
 int rk_adt_cmdseq_status(const void *d_state, const void *d_cmdtab, int64_t n, const uint32_t *d_id, int32_t *d_status, void *stream) {
   if(n == 0) return RK_OK;

@@ -27,9 +27,15 @@ RK_DEV uint32_t pack16(int32_t lo, int32_t hi) { return ((uint32_t)lo & 0xFFFFu)
 RK_DEV int32_t lo16(uint32_t w) { return (int32_t)(int16_t)(w & 0xFFFFu); }
 RK_DEV int32_t hi16(uint32_t w) { return ((int32_t)w) >> 16; }
 
-// (int16_t)(float) as the x86 build of the firmware source performs it: cvttss2si to 32 bits,
-// keep the low 16 (C++ leaves out-of-range undefined).
-RK_DEV int32_t f2s16(float f) { return sext16(__float2int_rz(f)); }
+// (int32_t)(float) as the x86 build of the firmware source performs it: cvttss2si, which
+// returns INT_MIN for NaN / out of range (F2I.TRUNC saturates instead).
+RK_DEV int32_t f2i_x86(float f) {
+  const int32_t r = __float2int_rz(f);
+  return (fabsf(f) < 2147483648.0f) ? r : (int32_t)0x80000000u;
+}
+// (int16_t)(float), likewise: cvttss2si to 32 bits, keep the low 16 (C++ leaves out-of-range
+// undefined) -- so a value beyond +-2^31 becomes 0, not -1.
+RK_DEV int32_t f2s16(float f) { return sext16(f2i_x86(f)); }
 
 // ---- 128-bit plane access ------------------------------------------------------------
 // plane pl of an n-instance block, instance i.  Streaming: each cell is touched once per
@@ -49,6 +55,11 @@ namespace rk {
 void        set_error(const char *fmt, ...);
 int         cuda_fail(cudaError_t e, const char *what);
 int         require_device();
+// rk_imt_update_yaw / rk_adt_update with a cap on the grid (rk_tick.cu runs them beside the vehicle rollout)
+int imt_update_launch(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
+                      float *d_yaw_rad, int do_init, int max_ctas, void *stream);
+int adt_update_launch(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab, int64_t n, int32_t K, uint32_t *d_trace,
+                      int max_ctas, void *stream);
 } // namespace rk
 
 #define RK_CUDA(call)                                        \

@@ -41,11 +41,8 @@ RK_DEV void imu_update_data(const float qi[4], const int r[16], ImuData &o) {
   o.d[15] = fadd(fadd(fadd(fmul(qi[0], q[0]), fmul(qi[1], q[1])), fmul(qi[2], q[2])), fmul(qi[3], q[3]));
 }
 
-__global__ void __launch_bounds__(256)
-imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__restrict__ regs,
-                  const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
+RK_DEV void imt_update_body(int64_t i, uint4 *__restrict__ state, int64_t n, int K, const int16_t *__restrict__ regs,
+                            const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
   float   qi[4];
   ImuData cur;
   {
@@ -103,6 +100,14 @@ imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__
   for(int pl = 0; pl < 4; pl++)
     st_plane(state, n, 1 + pl, i, make_uint4(f2u(cur.d[4 * pl]), f2u(cur.d[4 * pl + 1]), f2u(cur.d[4 * pl + 2]), f2u(cur.d[4 * pl + 3])));
   st_plane(state, n, 5, i, make_uint4(flags, 0u, 0u, 0u));
+}
+// One thread per IMU; the grid may be smaller than the batch (rk_tick_rollout runs this kernel beside the
+// issue-bound vehicle rollout on a capped number of CTAs), so CTAs stride over the blocks of 256 IMUs.
+__global__ void __launch_bounds__(256)
+imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__restrict__ regs,
+                  const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
+  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    imt_update_body(i, state, n, K, regs, have_quat, out, yaw_rad, do_init);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -399,6 +404,13 @@ int rk_imt_update(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, co
 
 int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
                       float *d_yaw_rad, int do_init, void *stream) {
+  return rk::imt_update_launch(d_state, n, K, d_regs, d_have_quat, d_out, d_yaw_rad, do_init, 0, stream);
+}
+} // extern "C"
+
+// max_ctas > 0: at most that many CTAs (each strides over the batch)
+int rk::imt_update_launch(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
+                          float *d_yaw_rad, int do_init, int max_ctas, void *stream) {
   if(n == 0 || K == 0) return RK_OK;
   if(n < 0 || K < 0 || !d_regs || ((uintptr_t)d_regs & 15u)) {
     set_error("rk_imt_update: bad n / K, or d_regs NULL / not 16-byte aligned");
@@ -409,11 +421,15 @@ int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs
     return RK_ERR_ARG;
   }
   if(int rc = require_device()) return rc;
-  imt_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint4 *)d_state, n, K, d_regs, d_have_quat,
-                                                                                  (float4 *)d_out, d_yaw_rad, do_init);
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if(max_ctas > 0 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;
+  imt_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint4 *)d_state, n, K, d_regs, d_have_quat, (float4 *)d_out, d_yaw_rad,
+                                                            do_init);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
+
+extern "C" {
 
 size_t rk_imt_parser_words(void) { return RK_IP_WORDS; }
 size_t rk_imt_parser_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_IP_WORDS * 4u; }

@@ -1,0 +1,197 @@
+// rk_stream.cu -- the seeded synthetic command / sensor streams of SURVEY.md section 8d, generated on the device.
+//
+// A rollout engine fed over PCIe is bound by the host link: the full tick consumes 4.5 KB of tables per robot and
+// launch (3.2 KB of WT901 register snapshots, 1 KB of arm waypoints, commands), 75 GB per 2^24-robot pass.  A
+// sampling planner does not ship its samples from the host -- it ships the distribution.  These kernels expand a
+// 48-byte descriptor (seed, global index of the batch's first robot, distribution parameters) into exactly the
+// blocks rk_vdt_rollout / rk_imt_update / rk_adt_push_cmdseq consume, one thread per robot, every store a full
+// 128-bit cell.  The definition is the numpy code in streams.py (`*_v2`, 32-bit counter hash); every value here is
+// the same integer arithmetic or the same single IEEE operation in the same order, and tests/test_streams_gpu.py
+// compares the blocks bit for bit.
+#include <math.h>
+
+#include "rk_common.cuh"
+
+namespace rk {
+
+RK_DEV uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+RK_DEV uint32_t h32_prefix(uint32_t seed, uint32_t stream, uint64_t inst) { // the part that does not depend on the index
+  return mix32(mix32(seed ^ (stream * 0x9E3779B9u)) ^ (uint32_t)inst);
+}
+RK_DEV uint32_t h32_idx(uint32_t prefix, uint32_t idx) { return mix32(prefix ^ (idx * 0x85EBCA6Bu)); }
+RK_DEV uint32_t sub32(uint32_t h, uint32_t k) { return mix32(h + (k + 1u) * 0x9E3779B9u); }
+RK_DEV float    u01_32(uint32_t h) { return fmul((float)(h >> 8), 1.0f / 16777216.0f); }
+
+// streams.vehicle_commands_v2: [n_seg][n] rk_vdt_cmd_t
+__global__ void __launch_bounds__(256)
+stream_vehicle_commands_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, int n_seg, uint4 *__restrict__ cmd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const rk_stream_desc_t d = *dd;
+  const uint32_t         px = h32_prefix(d.seed, 1u, (uint64_t)(d.first + i));
+  const float four_pi = (float)(4.0 * M_PI), two_pi = (float)(2.0 * M_PI), rl = (float)(6.0 * M_PI);
+  for(int s = 0; s < n_seg; s++) {
+    const uint32_t b = h32_idx(px, (uint32_t)s);
+    float vx  = fsub(fmul(u01_32(sub32(b, 0u)), 800.0f), 400.0f);
+    float vy  = fsub(fmul(u01_32(sub32(b, 1u)), 800.0f), 400.0f);
+    float vth = fsub(fmul(u01_32(sub32(b, 2u)), four_pi), two_pi);
+    // speed_limit_xy (VD_task_main.cpp:127-137): sqrt, clamp, x * lim / len
+    const float ln  = fsqrt(fadd(fmul(vx, vx), fmul(vy, vy)));
+    const float lim = fminf(ln, 400.0f);
+    if(ln != 0.0f) vx = fdiv(fmul(vx, lim), ln), vy = fdiv(fmul(vy, lim), ln);
+    else vx = 0.0f, vy = 0.0f;
+    vth             = fminf(fmaxf(vth, -rl), rl);
+    const bool stop = d.stop_every != 0u && (sub32(b, 3u) % d.stop_every) == 0u;
+    uint4      q;
+    q.x = stop ? 0u : f2u(vx), q.y = stop ? 0u : f2u(vy), q.z = stop ? 0u : f2u(vth);
+    q.w = stop ? (uint32_t)RK_CMD_STOP : (uint32_t)RK_CMD_MOVE;
+    __stcs(cmd + (int64_t)s * n + i, q);
+  }
+}
+
+// streams.vehicle_yaw_reg_v2: int16 [n_yaw][n]; a thread serves two neighbouring vehicles so that stores are 32-bit
+__global__ void __launch_bounds__(256)
+stream_vehicle_yaw_reg_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, int n_yaw, int16_t *__restrict__ out) {
+  const int64_t i2 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if(i2 >= n) return;
+  const rk_stream_desc_t d = *dd;
+  uint32_t phase[2], step[2];
+#pragma unroll
+  for(int k = 0; k < 2; k++) {
+    const uint32_t b    = h32_idx(h32_prefix(d.seed, 5u, (uint64_t)(d.first + i2 + k)), 0u);
+    phase[k]            = sub32(b, 0u) & 0xFFFFu;
+    const uint32_t rate = ((sub32(b, 1u) % 5u) + 1u) * 182u;
+    step[k]             = (sub32(b, 2u) & 1u) ? (0u - rate) : rate; // modulo 2^16 in the end
+  }
+  const bool pair = (i2 + 1 < n) && ((n & 1) == 0);
+  for(int y = 0; y < n_yaw; y++) {
+    const uint32_t r0 = (phase[0] + step[0] * (uint32_t)y) & 0xFFFFu, r1 = (phase[1] + step[1] * (uint32_t)y) & 0xFFFFu;
+    int16_t       *row = out + (int64_t)y * n + i2;
+    if(pair) {
+      *reinterpret_cast<uint32_t *>(row) = r0 | (r1 << 16);
+    } else {
+      row[0] = (int16_t)r0;
+      if(i2 + 1 < n) row[1] = (int16_t)r1;
+    }
+  }
+}
+
+// streams.imu_samples_v2 in the cell layout rk_imt_update takes: int16 [n_upd][2][n][8] + have_quat uint8 [n_upd][n]
+__global__ void __launch_bounds__(256)
+stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, int n_upd, uint4 *__restrict__ cells,
+                          uint8_t *__restrict__ have) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const rk_stream_desc_t d  = *dd;
+  const uint32_t         px = h32_prefix(d.seed, 20u, (uint64_t)(d.first + i));
+  for(int u = 0; u < n_upd; u++) {
+    const uint32_t b = h32_idx(px, d.first_update + (uint32_t)u);
+    uint32_t       w[8];
+#pragma unroll
+    for(int k = 0; k < 6; k++) w[k] = sub32(b, (uint32_t)k); // AX..Yaw, two registers a word
+    const uint32_t w6 = sub32(b, 6u), w7 = sub32(b, 7u);
+    const uint32_t gu[4] = {w6 & 0xFFFFu, w6 >> 16, w7 & 0xFFFFu, w7 >> 16};
+    double         g[4];
+#pragma unroll
+    for(int k = 0; k < 4; k++) g[k] = __dadd_rn(__dmul_rn(__dadd_rn((double)gu[k], 0.5), 1.0 / 32768.0), -1.0);
+    const double ss  = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g[0], g[0]), __dmul_rn(g[1], g[1])), __dmul_rn(g[2], g[2])), __dmul_rn(g[3], g[3]));
+    const double nrm = __dsqrt_rn(ss);
+    uint32_t     q[4];
+#pragma unroll
+    for(int k = 0; k < 4; k++) q[k] = (uint32_t)__double2int_rn(__dmul_rn(__ddiv_rn(g[k], nrm), 32767.0)) & 0xFFFFu;
+    w[6] = q[0] | (q[1] << 16), w[7] = q[2] | (q[3] << 16);
+    __stcs(cells + ((int64_t)u * 2 + 0) * n + i, make_uint4(w[0], w[1], w[2], w[3]));
+    __stcs(cells + ((int64_t)u * 2 + 1) * n + i, make_uint4(w[4], w[5], w[6], w[7]));
+    if(have) have[(int64_t)u * n + i] = (d.drop_every == 0u || (sub32(b, 8u) % d.drop_every) != 0u) ? 1u : 0u;
+  }
+}
+
+// streams.arm_sequences_v2 as the SoA slot image rk_adt_push_cmdseq takes: 65 planes of uint4 [n]
+__global__ void __launch_bounds__(256)
+stream_arm_sequences_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, uint4 *__restrict__ img) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const rk_stream_desc_t d    = *dd;
+  const uint64_t         inst = (uint64_t)(d.first + i);
+  const uint32_t         b0   = h32_idx(h32_prefix(d.seed, 30u, inst), 0u);
+  const uint32_t         ln   = (sub32(b0, 0u) % (d.arm_max_len - d.arm_min_len + 1u)) + d.arm_min_len;
+  const bool             z    = d.arm_dt_zero_every != 0u && (sub32(b0, 1u) % d.arm_dt_zero_every) == 0u;
+  __stcs(img + i, make_uint4(d.arm_seq_id, ln, 0u, 0u));
+  const uint32_t px = h32_prefix(d.seed, 31u, inst);
+  uint32_t       dt = 0u;
+  for(int k = 0; k < RK_ACMD_MAX_LEN; k++) {
+    const uint32_t b   = h32_idx(px, (uint32_t)k);
+    uint32_t       inc = (sub32(b, 0u) % 991u) + 10u;
+    if((sub32(b, 1u) % 8u) == 0u) inc = 0u;
+    if(z && k == 0) inc = 0u;
+    dt += inc;
+    uint32_t a[5];
+#pragma unroll
+    for(int j = 0; j < 5; j++) a[j] = f2u(fmul((float)((int32_t)(sub32(b, 2u + (uint32_t)j) % (300u * 64u + 1u)) - 150 * 64), 1.0f / 64.0f));
+    __stcs(img + (int64_t)(1 + 2 * k) * n + i, make_uint4(dt, a[0], a[1], a[2]));
+    __stcs(img + (int64_t)(2 + 2 * k) * n + i, make_uint4(a[3], a[4], 0u, 0u));
+  }
+}
+
+static int stream_check(const char *who, const void *d_desc, const void *out, int64_t n) {
+  if(n < 0 || !d_desc || ((uintptr_t)d_desc & 7u) || !out || ((uintptr_t)out & 15u)) {
+    set_error("%s: n < 0, or descriptor / output NULL or misaligned (descriptor 8, blocks 16 bytes)", who);
+    return RK_ERR_ARG;
+  }
+  return require_device();
+}
+
+} // namespace rk
+
+using namespace rk;
+
+extern "C" {
+
+void rk_stream_default_desc(rk_stream_desc_t *d) {
+  if(!d) return;
+  d->seed = 0x5EEDu, d->first_update = 0u, d->first = 0;
+  d->stop_every = 8u, d->drop_every = 64u;
+  d->arm_min_len = 2u, d->arm_max_len = 32u, d->arm_seq_id = 1u, d->arm_dt_zero_every = 4u;
+}
+
+int rk_stream_vehicle_commands(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_seg, rk_vdt_cmd_t *d_cmd, void *stream) {
+  if(n == 0 || n_seg <= 0) return RK_OK;
+  if(int rc = stream_check("rk_stream_vehicle_commands", d_desc, d_cmd, n)) return rc;
+  stream_vehicle_commands_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_seg, (uint4 *)d_cmd);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_stream_vehicle_yaw_reg(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_yaw, int16_t *d_yaw_reg, void *stream) {
+  if(n == 0 || n_yaw <= 0) return RK_OK;
+  if(int rc = stream_check("rk_stream_vehicle_yaw_reg", d_desc, d_yaw_reg, n)) return rc;
+  const int64_t pairs = (n + 1) / 2;
+  stream_vehicle_yaw_reg_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_yaw, d_yaw_reg);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_stream_imu_samples(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat, void *stream) {
+  if(n == 0 || n_upd <= 0) return RK_OK;
+  if(int rc = stream_check("rk_stream_imu_samples", d_desc, d_regs, n)) return rc;
+  stream_imu_samples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_upd, (uint4 *)d_regs, d_have_quat);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_stream_arm_sequences(const rk_stream_desc_t *d_desc, int64_t n, void *d_seq, void *stream) {
+  if(n == 0) return RK_OK;
+  if(int rc = stream_check("rk_stream_arm_sequences", d_desc, d_seq, n)) return rc;
+  stream_arm_sequences_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_desc, n, (uint4 *)d_seq);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+} // extern "C"

@@ -16,17 +16,53 @@ namespace rk {
 // -----------------------------------------------------------------------------------------
 constexpr int kRolloutThreads = 128;
 
-// the yaw the ISR hands to set_now_yaw_world(): the float stream, or formed from the WT901C Yaw register exactly as
-// IMU_IF_WT901C::updateData (imu_if_wt901c.cpp:100: reg / 32768.0f * 180.0f; the division by 2^15 is exact) ->
-// getYawDate() -> mymath::deg2rad (VD_task_main.cpp:368) would
-RK_DEV uint32_t load_yaw_raw(const rk_vdt_rollout_t &a, int64_t idx) { // the load only: nothing here waits for it
-  return a.d_yaw ? __float_as_uint(__ldcs(a.d_yaw + idx)) : (uint32_t)(int)__ldcs(a.d_yaw_reg + idx);
+// The yaw the ISR hands to set_now_yaw_world() (VD_task_main.cpp:368) before tick y * yaw_period, from one of three
+// sources: the float stream d_yaw; the WT901C Yaw register stream d_yaw_reg; or the IMU's own register snapshots
+// d_imu_regs (the cells rk_imt_update consumes) -- then the vehicle forms what IMT::get_status_now_yaw() would
+// return after IMU update y without waiting for the IMU kernel:
+//   angle[2] = reg / 32768.0f * 180.0f (IMU_IF_WT901C::updateData, imu_if_wt901c.cpp:100; /2^15 is exact) ->
+//   getYawDate() (:160) -> mymath::deg2rad (util_mymath.hpp:16);
+//   an update without a quaternion frame (d_imu_have_quat == 0) leaves the IMU's Data page as it was
+//   (imu_if_wt901c.cpp:83-89), i.e. the yaw of the last good update -- before the first one of this launch that is
+//   the Data page the IMU block held at launch (d_imu_yaw0_deg).
+struct YawPf {
+  uint32_t raw;  // float bits, or the sign-extended register
+  uint32_t have; // 0: hold
+};
+RK_DEV YawPf load_yaw_pf(const rk_vdt_rollout_t &a, int64_t n, int64_t i, int yk) { // the loads only: nothing here waits for them
+  YawPf         pf;
+  const int64_t idx = (int64_t)yk * n + i;
+  pf.have           = 1u;
+  if(a.d_yaw) {
+    pf.raw = __float_as_uint(__ldcs(a.d_yaw + idx));
+  } else if(a.d_yaw_reg) {
+    pf.raw = (uint32_t)(int)__ldcs(a.d_yaw_reg + idx);
+  } else {
+    pf.raw = (uint32_t)(int)__ldcs(a.d_imu_regs + (((int64_t)yk * 2 + 1) * n + i) * 8 + (RK_IMT_REG_YAW - 8));
+    if(a.d_imu_have_quat) pf.have = (uint32_t)__ldcs(a.d_imu_have_quat + idx);
+  }
+  return pf;
 }
-RK_DEV float yaw_of_raw(const rk_vdt_rollout_t &a, uint32_t raw) {
-  if(a.d_yaw) return __uint_as_float(raw);
-  return fmul(fmul(fmul((float)(int)raw, 1.0f / 32768.0f), 180.0f), RK_DEG2RAD);
+RK_DEV float yaw_of_reg(int32_t reg) { return fmul(fmul(fmul((float)reg, 1.0f / 32768.0f), 180.0f), RK_DEG2RAD); }
+// false: the yaw word stays as it is
+RK_DEV bool yaw_of_pf(const rk_vdt_rollout_t &a, const YawPf &pf, int yk, int64_t i, float &pth) {
+  if(a.d_yaw) {
+    pth = __uint_as_float(pf.raw);
+    return true;
+  }
+  if(pf.have) {
+    pth = yaw_of_reg((int32_t)pf.raw);
+    return true;
+  }
+  if(yk == 0 && a.d_imu_yaw0_deg) {
+    pth = fmul(__ldcs(a.d_imu_yaw0_deg + i), RK_DEG2RAD);
+    return true;
+  }
+  return false;
 }
-RK_DEV float load_yaw(const rk_vdt_rollout_t &a, int64_t idx) { return yaw_of_raw(a, load_yaw_raw(a, idx)); }
+RK_DEV bool yaw_enabled(const rk_vdt_rollout_t &a) {
+  return (a.d_yaw != nullptr || a.d_yaw_reg != nullptr || a.d_imu_regs != nullptr) && a.yaw_period > 0 && a.n_yaw > 0;
+}
 
 template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(kRolloutThreads)
@@ -42,9 +78,8 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
   float         cth, sth;
   yaw_trig(s_tab, v.pos[2], cth, sth);
 
-  const bool has_yaw  = (a.d_yaw != nullptr || a.d_yaw_reg != nullptr) && a.yaw_period > 0 && a.n_yaw > 0;
-  int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
-  Sched      sc;
+  int   next_yaw = yaw_enabled(a) ? 0 : INT_MAX, yk = 0;
+  Sched sc;
   sched_init(sc, a);
 
   // RK_SENSOR_STREAM: the four frames of tick t + 1 are in flight while tick t is computed
@@ -58,8 +93,7 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
   for(int t = 0; t < a.steps; t++) {
     sched_events(v, p, a, n, i, t, sc);
     if(t == next_yaw) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
-      v.pos[2] = load_yaw(a, (int64_t)yk * n + i);
-      yaw_trig(s_tab, v.pos[2], cth, sth);
+      if(yaw_of_pf(a, load_yaw_pf(a, n, i, yk), yk, i, v.pos[2])) yaw_trig(s_tab, v.pos[2], cth, sth);
       yk++;
       next_yaw = (yk < a.n_yaw) ? next_yaw + a.yaw_period : INT_MAX;
     }
@@ -99,10 +133,11 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
 }
 
 // -----------------------------------------------------------------------------------------
-// Closed-loop rollout, issue-optimised (rk_vehicle_fast.cuh).  Ticks between two command
-// boundaries ("chunks") run on the fast tick when the thread's state satisfies fast_ok();
-// command application, the last tick of the launch and any thread outside the fast path's
-// domain run the transcription (veh_update), so the stored state is complete and identical.
+// Closed-loop rollout, issue-optimised (rk_vehicle_fast.cuh / rk_vehicle_fast2.cuh).  Ticks between two
+// command boundaries ("chunks") run on the fast tick when the thread's state satisfies fast_ok() and the
+// chunk's constants bound the controller output (fast_u_bounded); command application, the last tick of
+// the launch and any thread outside the fast path's domain run the transcription (veh_update), so the
+// stored state is complete and identical.
 // -----------------------------------------------------------------------------------------
 #ifndef RK_FAST_THREADS
 #define RK_FAST_THREADS 128
@@ -112,6 +147,7 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
 #endif
 constexpr int kFastThreads = RK_FAST_THREADS;
 constexpr int kFastUnroll  = RK_FAST_UNROLL;
+constexpr int kMaxChunk    = 262144; // ticks per chunk: keeps the 32-bit per-chunk angle sum far from overflow
 
 template <bool TRACE>
 RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, float py, float pth, const float vel[3],
@@ -123,6 +159,41 @@ RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, 
   for(int j = 0; j < 3; j++) tr[(int64_t)(3 + j) * n] = f2u(vel[j]), tr[(int64_t)(6 + j) * n] = f2u(tgt[j]);
   tr[9 * n] = (uint32_t)c0, tr[10 * n] = (uint32_t)c1, tr[11 * n] = (uint32_t)c2, tr[12 * n] = (uint32_t)c3;
   tr[13 * n] = cnt, tr[14 * n] = 0u, tr[15 * n] = 0u;
+}
+
+RK_DEV void fast_consts(FastConsts &fc, const rk_vdt_params_t &p, const Derived &d) {
+  fc.rcp_r = fdiv(1.0f, p.wheel_radius_mm), fc.rcp_s2 = fdiv(1.0f, p.sqrtf2), fc.rcp_l = fdiv(1.0f, p.wheel_l_mm);
+  const double K = (double)RK_OUT_RAD_PER_RAW_ANGLE * (double)RK_GEAR_RATIO_INV;
+  fc.k_hi        = __double2float_rn(K);
+  fc.k_lo        = __double2float_rn(K - (double)fc.k_hi);
+  fc.A1 = d.A1, fc.B0 = d.B0, fc.ki_dt = d.ki_dt, fc.s2l = d.s2l;
+  fc.neg_i_limit = -p.i_limit, fc.neg_ff_limit = -p.ff_limit;
+  fc.khi_pm = make_float2(fc.k_hi, -fc.k_hi), fc.klo_pm = make_float2(fc.k_lo, -fc.k_lo);
+  asm volatile("" : "+f"(fc.khi_pm.x), "+f"(fc.khi_pm.y), "+f"(fc.klo_pm.x), "+f"(fc.klo_pm.y)); // not rematerialised per tick
+}
+
+// The yaw sample for the next boundary is fetched one period ahead, so its HBM latency hides behind
+// yaw_period ticks of arithmetic instead of stalling every warp at once.
+struct YawFeed {
+  int   next, yk;
+  YawPf pf;
+};
+RK_DEV void yaw_feed_init(YawFeed &y, const rk_vdt_rollout_t &a, int64_t n, int64_t i) {
+  y.next = yaw_enabled(a) ? 0 : INT_MAX, y.yk = 0;
+  y.pf.raw = 0u, y.pf.have = 0u;
+  if(y.next == 0) y.pf = load_yaw_pf(a, n, i, 0);
+}
+// can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
+RK_DEV void yaw_feed_take(YawFeed &y, const rk_vdt_rollout_t &a, int64_t n, int64_t i, const float *s_tab, float &pth, float &cth,
+                          float &sth) {
+  if(yaw_of_pf(a, y.pf, y.yk, i, pth)) yaw_trig(s_tab, pth, cth, sth);
+  y.yk++;
+  if(y.yk < a.n_yaw) {
+    y.next += a.yaw_period;
+    y.pf = load_yaw_pf(a, n, i, y.yk);
+  } else {
+    y.next = INT_MAX;
+  }
 }
 
 template <bool TRACE, int OCC, bool FFSAT, bool PACKED>
@@ -138,36 +209,15 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
   load_veh(state, n, i, v);
   const Derived d = derive(p);
   FastConsts    fc;
-  {
-    fc.rcp_r = fdiv(1.0f, p.wheel_radius_mm), fc.rcp_s2 = fdiv(1.0f, p.sqrtf2), fc.rcp_l = fdiv(1.0f, p.wheel_l_mm);
-    const double K = (double)RK_OUT_RAD_PER_RAW_ANGLE * (double)RK_GEAR_RATIO_INV;
-    fc.k_hi        = __double2float_rn(K);
-    fc.k_lo        = __double2float_rn(K - (double)fc.k_hi);
-    fc.A1 = d.A1, fc.B0 = d.B0, fc.ki_dt = d.ki_dt, fc.s2l = d.s2l;
-    fc.neg_i_limit = -p.i_limit, fc.neg_ff_limit = -p.ff_limit;
-  }
+  fast_consts(fc, p, d);
   float cth, sth;
   yaw_trig(s_tab, v.pos[2], cth, sth);
 
-  const bool has_yaw  = (a.d_yaw != nullptr || a.d_yaw_reg != nullptr) && a.yaw_period > 0 && a.n_yaw > 0;
-  int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
-  const int  K        = a.steps;
-  Sched      sch;
+  const int K = a.steps;
+  Sched     sch;
   sched_init(sch, a);
-  // The yaw sample for the next boundary is fetched one period ahead, so its HBM latency
-  // hides behind yaw_period ticks of arithmetic instead of stalling every warp at once.
-  uint32_t yaw_pf = has_yaw ? load_yaw_raw(a, i) : 0u; // raw word: converted when taken, so the load stays in flight
-  auto     take_yaw = [&](float &pth) { // can_tx_routine_intr -> set_now_yaw_world()   VD_task_main.cpp:368
-    pth = yaw_of_raw(a, yaw_pf);
-    yaw_trig(s_tab, pth, cth, sth);
-    yk++;
-    if(yk < a.n_yaw) {
-      next_yaw += a.yaw_period;
-      yaw_pf = load_yaw_raw(a, (int64_t)yk * n + i);
-    } else {
-      next_yaw = INT_MAX;
-    }
-  };
+  YawFeed yf;
+  yaw_feed_init(yf, a, n, i);
 
   int t = 0;
   while(t < K) {
@@ -175,8 +225,8 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
     // run to the next event: a command, the countdown's automatic stop, or the last tick of the launch
     // (always a transcription tick).  Lanes of a warp whose countdowns fire at different ticks leave
     // the fast loop at different times; results do not depend on it.
-    const int t_end = min(min(sch.next_cmd, sched_fire_tick(v, a, sch)), K - 1);
-    if(t < t_end && fast_ok<D0, D1, D2, D3>(v, p)) {
+    const int t_end = min(min(min(sch.next_cmd, sched_fire_tick(v, a, sch)), K - 1), t + kMaxChunk);
+    if(t < t_end && fast_ok<D0, D1, D2, D3>(v, p) && fast_u_bounded<false>(v, p, fc)) {
       const int t0  = t;
       float     pth = v.pos[2];
       if(PACKED) { // FADD2 / FFMA2 form of the same tick (rk_vehicle_fast2.cuh)
@@ -184,13 +234,13 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
         to_fast2(v, f, p.ts, fc.B0);
         const float nz = fmul(-0.0f, p.ts); // opaque -0.0f (p.ts > 0 is a fast-path precondition)
         while(t < t_end) {
-          if(t == next_yaw) take_yaw(pth);
-          const int    t_stop = min(t_end, next_yaw);
+          if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
+          const int    t_stop = min(t_end, yf.next);
           const float2 cs = make_float2(cth, sth), sc = make_float2(sth, cth);
 #pragma unroll kFastUnroll
           for(; t < t_stop; t++) {
             float vel[3], tgt[3];
-            fast_tick2<FFSAT>(f, p, fc, cs, sc, nz, vel, tgt);
+            fast_tick2<FFSAT, TRACE>(f, p, fc, cs, sc, nz, vel, tgt);
             trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1],
                              TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
           }
@@ -202,8 +252,8 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
         FastVeh f;
         to_fast<D0, D1, D2, D3>(v, f, p.ts, fc.B0);
         while(t < t_end) {
-          if(t == next_yaw) take_yaw(pth);
-          const int t_stop = min(t_end, next_yaw);
+          if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
+          const int t_stop = min(t_end, yf.next);
 #pragma unroll kFastUnroll
           for(; t < t_stop; t++) {
             float vel[3], tgt[3];
@@ -217,7 +267,7 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
         sched_skip_to(v, a, sch, t);
       }
     } else {
-      if(t == next_yaw) take_yaw(v.pos[2]);
+      if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, v.pos[2], cth, sth);
       const int32_t us = ((t + 1) * 1000) & 0x7FFF;
 #pragma unroll
       for(int k = 0; k < 4; k++) motor_rx(v.m[k], p.motor_dir[k], plant_frame(v.m[k]), us);
@@ -257,34 +307,15 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
   load_veh(state, n, i, v);
   const Derived d = derive(p);
   FastConsts    fc;
-  {
-    fc.rcp_r = fdiv(1.0f, p.wheel_radius_mm), fc.rcp_s2 = fdiv(1.0f, p.sqrtf2), fc.rcp_l = fdiv(1.0f, p.wheel_l_mm);
-    const double K = (double)RK_OUT_RAD_PER_RAW_ANGLE * (double)RK_GEAR_RATIO_INV;
-    fc.k_hi        = __double2float_rn(K);
-    fc.k_lo        = __double2float_rn(K - (double)fc.k_hi);
-    fc.A1 = d.A1, fc.B0 = d.B0, fc.ki_dt = d.ki_dt, fc.s2l = d.s2l;
-    fc.neg_i_limit = -p.i_limit, fc.neg_ff_limit = -p.ff_limit;
-  }
+  fast_consts(fc, p, d);
   float cth, sth;
   yaw_trig(s_tab, v.pos[2], cth, sth);
 
-  const bool has_yaw  = (a.d_yaw != nullptr || a.d_yaw_reg != nullptr) && a.yaw_period > 0 && a.n_yaw > 0;
-  int        next_yaw = has_yaw ? 0 : INT_MAX, yk = 0;
-  const int  K        = a.steps;
-  Sched      sch;
+  const int K = a.steps;
+  Sched     sch;
   sched_init(sch, a);
-  uint32_t yaw_pf = has_yaw ? load_yaw_raw(a, i) : 0u;
-  auto     take_yaw = [&](float &pth) {
-    pth = yaw_of_raw(a, yaw_pf);
-    yaw_trig(s_tab, pth, cth, sth);
-    yk++;
-    if(yk < a.n_yaw) {
-      next_yaw += a.yaw_period;
-      yaw_pf = load_yaw_raw(a, (int64_t)yk * n + i);
-    } else {
-      next_yaw = INT_MAX;
-    }
-  };
+  YawFeed yf;
+  yaw_feed_init(yf, a, n, i);
   const unsigned long long *fsrc = reinterpret_cast<const unsigned long long *>(a.d_frames) + i;
   uint64_t                  fpf[4]; // the frames of tick t
 #pragma unroll
@@ -295,7 +326,7 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
     sched_events(v, p, a, n, i, t, sch);
     // chunks are capped so the 32-bit per-chunk angle sum cannot overflow (|step| <= 40960)
     const int t_end = min(min(min(sch.next_cmd, sched_fire_tick(v, a, sch)), K - 1), t + 32768);
-    if(t < t_end && fast_ok<D0, D1, D2, D3, true>(v, p)) {
+    if(t < t_end && fast_ok<D0, D1, D2, D3, true>(v, p) && fast_u_bounded<true>(v, p, fc)) {
       const int   t0  = t;
       float       pth = v.pos[2];
       FastVeh2    f;
@@ -304,8 +335,8 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
       stream_sense_load(ss, v);
       const float nz = fmul(-0.0f, p.ts);
       while(t < t_end) {
-        if(t == next_yaw) take_yaw(pth);
-        const int    t_stop = min(t_end, next_yaw);
+        if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
+        const int    t_stop = min(t_end, yf.next);
         const float2 cs = make_float2(cth, sth), sc = make_float2(sth, cth);
 #pragma unroll 2
         for(; t < t_stop; t++) {
@@ -315,7 +346,7 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
 #pragma unroll
           for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + ((int64_t)(t + 1) * 4 + k) * n); // t + 1 <= K - 1 inside a chunk
           float vel[3], tgt[3];
-          fast_tick2_stream<FFSAT>(f, ss, fr, p, fc, cs, sc, nz, vel, tgt);
+          fast_tick2_stream<FFSAT, TRACE>(f, ss, fr, p, fc, cs, sc, nz, vel, tgt);
           trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1],
                            TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
         }
@@ -324,7 +355,7 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
       from_fast2_stream(v, f, ss, t - t0);
       sched_skip_to(v, a, sch, t);
     } else {
-      if(t == next_yaw) take_yaw(v.pos[2]);
+      if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, v.pos[2], cth, sth);
       const int32_t us = ((t + 1) * 1000) & 0x7FFF;
       uint64_t      fr[4];
 #pragma unroll
@@ -447,6 +478,7 @@ static cudaError_t launch_rollout(const rk_vdt_params_t &p, void *d_state, int64
 }
 
 bool fast_path_proven(const rk_vdt_params_t &p); // rk_exact.cu
+int  tick_set_side_ctas(int v);                     // rk_tick.cu
 
 static int g_fast_occupancy = 4;       // rk_set_option(RK_OPT_FAST_OCCUPANCY, 3|4|5): tuning
 static int g_fast_packed = 1;          // rk_set_option(RK_OPT_FAST_PACKED, 0|1): packed FP32 tick (default) or scalar
@@ -500,10 +532,11 @@ int rk_set_option(int option, int value) {
     rk::g_fast_packed = value != 0;
     return RK_OK;
   }
-  if(option == RK_OPT_FAST_OCCUPANCY && (value >= 3 && value <= 5)) {
+  if(option == RK_OPT_FAST_OCCUPANCY && (value >= 3 && value <= 4)) {
     rk::g_fast_occupancy = value;
     return RK_OK;
   }
+  if(option == RK_OPT_TICK_SIDE_CTAS && rk::tick_set_side_ctas(value) == RK_OK) return RK_OK;
   set_error("rk_set_option: unknown option %d / bad value %d", option, value);
   return RK_ERR_ARG;
 }
@@ -590,7 +623,6 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
       } else {
         switch(g_fast_occupancy) { // resident CTAs per SM the kernel is compiled for (register budget)
         case 3: RK_LAUNCH_FAST(false, 3); break;
-        case 5: RK_LAUNCH_FAST(false, 5); break;
         default: RK_LAUNCH_FAST(false, 4); break;
         }
       }

@@ -28,6 +28,7 @@ struct FastConsts {
   float k_hi, k_lo;           // split of (double)OUT_RAD_PER_RAW_ANGLE * (double)GEAR_RATIO_INV
   float A1, B0, ki_dt, s2l;   // = Derived (computed on device by derive(), copied here)
   float neg_i_limit, neg_ff_limit;
+  float2 khi_pm, klo_pm;      // {k_hi, -k_hi}, {k_lo, -k_lo}: lane constants of the packed tick, pinned in registers
 };
 
 // exact x / c for launch-constant c > 0 (see header comment); rcp = RN(1/c).

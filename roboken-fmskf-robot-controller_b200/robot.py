@@ -32,10 +32,10 @@ class RobotBatch:
     def make_args(self, steps, slow_period, cmd, seg_len, regs, have_quat, yaw, goal=None, cost=None, vdt_trace=None,
                   adt_trace=None):
         """cmd: [n_seg, n, 4] rk_vdt_cmd_t records; regs: int16 [n_slow, 2, n, 8] (streams.imu_cells); have_quat: uint8
-        [n_slow, n] or None; yaw: float32 scratch [n_slow, n]."""
+        [n_slow, n] or None; yaw: float32 scratch, >= n words (receives the IMU yaw as it was at launch)."""
         n_slow = (steps + slow_period - 1) // slow_period
         assert regs.is_cuda and regs.dtype == torch.int16 and tuple(regs.shape) == (n_slow, 2, self.n, 8) and regs.is_contiguous()
-        assert yaw.is_cuda and yaw.dtype == torch.float32 and yaw.numel() >= n_slow * self.n
+        assert yaw.is_cuda and yaw.dtype == torch.float32 and yaw.numel() >= self.n
         a = _cabi.TickRollout()
         a.steps, a.slow_period = int(steps), int(slow_period)
         if cmd is not None:

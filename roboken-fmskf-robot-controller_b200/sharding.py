@@ -83,10 +83,23 @@ def sum_over_ranks(value, device="cpu"):
 
 
 def gather_costs(cost):
-    """All ranks' per-instance cost vectors concatenated in rank order (equal-size slices)."""
+    """All ranks' per-instance cost vectors concatenated in rank order.  Slices may differ in size by one
+    (shard_range gives the first n_total % world ranks one more instance): every rank pads to the largest
+    slice for the collective and the padding is trimmed afterwards."""
     if not dist.is_initialized():
         return cost
     world = dist.get_world_size()
-    out = torch.empty(world * cost.numel(), dtype=cost.dtype, device=cost.device)
-    dist.all_gather_into_tensor(out, cost.contiguous())
-    return out
+    sizes = torch.zeros(world, dtype=torch.int64, device=cost.device)
+    sizes[dist.get_rank()] = cost.numel()
+    dist.all_reduce(sizes, op=dist.ReduceOp.SUM)
+    sizes = [int(x) for x in sizes.tolist()]
+    m = max(sizes)
+    if all(x == m for x in sizes):
+        out = torch.empty(world * m, dtype=cost.dtype, device=cost.device)
+        dist.all_gather_into_tensor(out, cost.contiguous())
+        return out
+    padded = torch.zeros(m, dtype=cost.dtype, device=cost.device)
+    padded[: cost.numel()] = cost
+    out = torch.empty(world * m, dtype=cost.dtype, device=cost.device)
+    dist.all_gather_into_tensor(out, padded)
+    return torch.cat([out[r * m : r * m + sizes[r]] for r in range(world)])

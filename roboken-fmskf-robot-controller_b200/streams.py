@@ -370,3 +370,135 @@ def rm_inputs(n, K, seed=0x5EED, first=0, idle_every=4):
     w[..., 10] = fl[..., 0] | (fl[..., 1] << 8) | (fl[..., 2] << 16) | (fl[..., 3] << 24)
     w[..., 11] = fl[..., 4] | (fl[..., 5] << 8) | (fl[..., 6] << 16) | (fl[..., 7] << 24)
     return np.ascontiguousarray(w.reshape(K, n, 3, 4).transpose(0, 2, 1, 3))
+
+
+# ---- v2 streams: the same distributions on a 32-bit counter hash -------------------------------------------------
+# The generators above hash with splitmix64 three times per value: fine on the host, but a rollout engine that is fed
+# over PCIe is bound by the host link (4.5 KB of tables per robot for the full tick), so the bench's workload is
+# generated ON THE DEVICE from a 48-byte descriptor (csrc/rk_stream.cu, rk_stream_* in include/robotick.h).  These
+# numpy restatements are the definition; the device kernels must reproduce them bit for bit
+# (tests/test_streams_gpu.py).  All float32 results come from exactly representable integers or single IEEE float32 /
+# float64 operations in a fixed order.
+_U32 = np.uint32
+
+
+def mix32(x):
+    """32-bit finaliser (two odd multiplies, three xor-shifts)."""
+    x = np.asarray(x, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        x = x ^ (x >> _U32(16))
+        x = x * _U32(0x7FEB352D)
+        x = x ^ (x >> _U32(15))
+        x = x * _U32(0x846CA68B)
+        x = x ^ (x >> _U32(16))
+    return x
+
+
+def h32(seed, stream, inst, idx):
+    """Counter hash of (seed, stream, instance, index); instance and index are taken modulo 2^32."""
+    with np.errstate(over="ignore"):
+        h = mix32(_U32(int(seed) & 0xFFFFFFFF) ^ (_U32(stream) * _U32(0x9E3779B9)))
+        h = mix32(h ^ (np.asarray(inst, dtype=np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+        h = mix32(h ^ ((np.asarray(idx, dtype=np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32) * _U32(0x85EBCA6B)))
+    return h
+
+
+def sub32(h, k):
+    """k-th draw under one hash."""
+    with np.errstate(over="ignore"):
+        return mix32(np.asarray(h, dtype=np.uint32) + _U32(((k + 1) * 0x9E3779B9) & 0xFFFFFFFF))
+
+
+def _u01_32(h):
+    """24-bit uniform in [0,1) as exact float32."""
+    return (np.asarray(h, dtype=np.uint32) >> _U32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def _inst(n, first, inst):
+    return (np.arange(n, dtype=np.uint64) + np.uint64(first)) if inst is None else np.asarray(inst, dtype=np.uint64)
+
+
+def vehicle_commands_v2(n, n_seg, seed=0x5EED, first=0, stop_every=8, inst=None):
+    """vehicle_commands() on the 32-bit hash.  `inst` (optional): explicit global instance indices instead of
+    first .. first + n - 1 (spot checks generate just the sampled robots)."""
+    inst = _inst(n, first, inst)[None, :]
+    seg = np.arange(n_seg, dtype=np.uint64)[:, None]
+    f32 = np.float32
+    b = h32(seed, 1, inst, seg)
+    vx = _u01_32(sub32(b, 0)) * f32(800.0) - f32(400.0)
+    vy = _u01_32(sub32(b, 1)) * f32(800.0) - f32(400.0)
+    vth = _u01_32(sub32(b, 2)) * f32(4.0 * np.pi) - f32(2.0 * np.pi)
+    ln = np.sqrt(vx * vx + vy * vy, dtype=np.float32)
+    lim = np.minimum(ln, f32(400.0))
+    nz = ln != 0
+    safe = np.where(nz, ln, f32(1.0))
+    vx = np.where(nz, (vx * lim) / safe, f32(0.0)).astype(np.float32)
+    vy = np.where(nz, (vy * lim) / safe, f32(0.0)).astype(np.float32)
+    rl = f32(6.0 * np.pi)
+    vth = np.clip(vth, -rl, rl).astype(np.float32)
+    stop = (sub32(b, 3) % _U32(stop_every)) == 0
+    cmd = np.zeros(b.shape, dtype=np.dtype([("vx", "<f4"), ("vy", "<f4"), ("vth", "<f4"), ("kind", "<i4")]))
+    cmd["vx"] = np.where(stop, f32(0), vx)
+    cmd["vy"] = np.where(stop, f32(0), vy)
+    cmd["vth"] = np.where(stop, f32(0), vth)
+    cmd["kind"] = np.where(stop, _cabi.RK_CMD_STOP, _cabi.RK_CMD_MOVE)
+    return cmd
+
+
+def vehicle_yaw_reg_v2(n, n_yaw, seed=0x5EED, first=0, inst=None):
+    """vehicle_yaw_reg() on the 32-bit hash: int16 [n_yaw, n]."""
+    inst = _inst(n, first, inst)[None, :]
+    k = np.arange(n_yaw, dtype=np.int64)[:, None]
+    b = h32(seed, 5, inst, 0)
+    phase = (sub32(b, 0) & _U32(0xFFFF)).astype(np.int64)
+    rate = ((sub32(b, 1) % _U32(5)).astype(np.int64) + 1) * 182
+    sign = np.where((sub32(b, 2) & _U32(1)) == 0, 1, -1)
+    return ((phase + sign * rate * k) & 0xFFFF).astype(np.uint16).view(np.int16)
+
+
+def imu_samples_v2(n, n_upd, seed=0x5EED, first=0, drop_every=64, inst=None, first_update=0):
+    """imu_samples() on the 32-bit hash: int16 [n_upd, 16, n] (+ have_quat uint8 [n_upd, n]).  One hash per
+    (IMU, update); its draws 0-5 are AX..Yaw two registers a word, 6-7 four 16-bit uniforms in (-1, 1) normalised in
+    float64 to a unit quaternion x 32767 (rounded half to even), 8 the missing-quaternion-frame flag."""
+    inst = _inst(n, first, inst)[None, :]
+    u = (np.arange(n_upd, dtype=np.uint64) + np.uint64(first_update))[:, None]
+    b = h32(seed, 20, inst, u)  # [n_upd, n]
+    regs = np.zeros((n_upd, 16, b.shape[1]), dtype=np.int16)
+    for k in range(6):
+        w = sub32(b, k)
+        regs[:, 2 * k, :] = (w & _U32(0xFFFF)).astype(np.uint16).view(np.int16)
+        regs[:, 2 * k + 1, :] = (w >> _U32(16)).astype(np.uint16).view(np.int16)
+    w6, w7 = sub32(b, 6), sub32(b, 7)
+    g = [((x.astype(np.float64) + 0.5) * (1.0 / 32768.0)) - 1.0 for x in (w6 & _U32(0xFFFF), w6 >> _U32(16), w7 & _U32(0xFFFF), w7 >> _U32(16))]
+    nrm = np.sqrt(((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]) + g[3] * g[3])
+    for k in range(4):
+        regs[:, 12 + k, :] = np.rint((g[k] / nrm) * 32767.0).astype(np.int16)
+    if drop_every:
+        have = ((sub32(b, 8) % _U32(drop_every)) != 0).astype(np.uint8)
+    else:
+        have = np.ones(b.shape, dtype=np.uint8)
+    return regs, np.ascontiguousarray(have)
+
+
+def arm_sequences_v2(n, seed=0x5EED, first=0, max_len=32, min_len=2, seq_id=1, dt_zero_every=4, inst=None):
+    """arm_sequences() on the 32-bit hash: uint32 [n, 260] slot images."""
+    inst = _inst(n, first, inst)
+    m = len(inst)
+    k = np.arange(32, dtype=np.uint64)[None, :]
+    b0 = h32(seed, 30, inst, 0)
+    ln = (sub32(b0, 0) % _U32(max_len - min_len + 1)).astype(np.int64) + min_len
+    z = (sub32(b0, 1) % _U32(dt_zero_every)) == 0
+    b = h32(seed, 31, inst[:, None], k)  # [m, 32]
+    inc = (sub32(b, 0) % _U32(991)).astype(np.int64) + 10
+    inc[(sub32(b, 1) % _U32(8)) == 0] = 0
+    inc[z, 0] = 0
+    dt = np.cumsum(inc, axis=1)
+    img = np.zeros((m, 260), dtype=np.uint32)
+    img[:, 0] = seq_id
+    img[:, 1] = ln
+    wp = img[:, 4:].reshape(m, 32, 8)
+    wp[:, :, 0] = dt.astype(np.uint32)
+    for j in range(5):
+        q = (sub32(b, 2 + j) % _U32(300 * 64 + 1)).astype(np.int64) - 150 * 64
+        wp[:, :, 1 + j] = (q.astype(np.float32) * np.float32(1.0 / 64.0)).view(np.uint32)
+    return img

@@ -34,12 +34,12 @@ def _rollout_cost(lo, hi, steps, seed):
     return ro.cost.copy(), st
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, total=64):
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     r, lr, w = sharding.init("gloo")
     assert (r, w) == (rank, world)
-    lo, hi = sharding.shard_range(64, r, w)
+    lo, hi = sharding.shard_range(total, r, w)
     cost, _ = _rollout_cost(lo, hi, 300, seed=31)
     sharding.barrier()
     t = sharding.max_over_ranks(1.0 + rank)
@@ -50,17 +50,18 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_slices_equal_single_run():
+@pytest.mark.parametrize("total", [64, 65])  # 65: unequal slices (33 + 32) through the padded gather
+def test_two_rank_slices_equal_single_run(total):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 300)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 300) + (1 if total == 65 else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, total)) for r in range(2)]
     for p in procs:
         p.start()
     t, tot, allc = q.get(timeout=120)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    assert t == 2.0 and tot == 64
-    ref, _ = _rollout_cost(0, 64, 300, seed=31)
+    assert t == 2.0 and tot == total
+    ref, _ = _rollout_cost(0, total, 300, seed=31)
     np.testing.assert_array_equal(allc, ref)  # slice results == single-process results, bit for bit

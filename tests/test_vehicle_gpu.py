@@ -497,3 +497,68 @@ def test_stream_fast_tick_equals_transcription_and_port():
                 a1[:, layout.VS_MOTOR0 + 8 * w + layout.VM_USEC] &= 0xFFFF0000
                 a5[:, layout.VS_MOTOR0 + 8 * w + layout.VM_USEC] &= 0xFFFF0000
             assert_same(a1, a5, "stream: one launch vs four")
+
+
+def test_current_conversion_overflow_matches_x86():
+    """(int16_t)(A * 1000.0f) beyond +-2^31: cvttss2si gives 0x80000000 (low 16 bits 0), a saturating F2I would give
+    -1 for the positive side.  Gains that wrap the int16 (kp = 50: stays on the fast tick) and gains large enough to
+    leave the int32 (kp = 4e3, 2e5; kff large with a wide FF limit) must
+    still match the x86 port bit for bit -- the fast path's chunk bound (fast_u_bounded) sends such chunks to the
+    transcription tick, whose conversion is f2i_x86."""
+    for variant, (kp, kff, fflim) in enumerate([(50.0, 0.0075, 1.0), (4.0e3, 0.0075, 1.0), (2.0e5, 0.0075, 1.0), (0.02, 5.0e4, 1.0e9)]):
+        p = rk.default_params()
+        p.kp, p.kff, p.ff_limit = kp, kff, fflim
+        n, steps = 256, 300
+        inp = wl.plant_inputs(n, steps, seed=60 + variant, seg_len=50)
+        vb = VehicleBatch(n, DEV, params=p)
+        cmd = _dev(inp["cmd"], np.int32).reshape(-1, n, 4)
+        tr = torch.zeros((steps, 16, n), dtype=torch.int32, device=DEV)
+        vb.rollout(steps, cmd=cmd, seg_len=inp["seg_len"], yaw=_dev(inp["yaw"]), yaw_period=inp["yaw_period"], trace=tr)
+        torch.cuda.synchronize()
+        st = np.zeros(layout.VS_WORDS * n, dtype=np.uint32)
+        ro = ol.HostRollout(n, steps, _cabi.RK_SENSOR_PLANT, inp["cmd"], inp["seg_len"], inp["yaw"], inp["yaw_period"], trace=True)
+        ol.run_port(st, n, ro, params=p, nthreads=8)
+        gtr = tr.cpu().numpy().view(np.uint32)
+        assert_same(gtr, ro.trace, f"overflow variant {variant} trace")
+        assert_same(vb.state.cpu().numpy().view(np.uint32), st, f"overflow variant {variant} state")
+
+
+def test_yaw_from_imu_register_snapshots():
+    """rk_vdt_rollout_t::d_imu_regs: the vehicle forms the yaw from the IMU's own register snapshots (Yaw register
+    scaled as updateData() does, held over updates without a quaternion frame, Data.angle[2] at launch if update 0
+    has none) == the float stream the IMU port emits for the same samples; fast and transcription kernels."""
+    lib = rk.load()
+    n, steps, slow = 777, 500, 10
+    n_slow = steps // slow
+    inp = wl.plant_inputs(n, steps, seed=71)
+    regs, have = streams.imu_samples(n, n_slow + 1, seed=71, drop_every=5)
+    have[1, : n // 2] = 0  # update 0 without a quaternion frame: the launch-time Data page is held
+    ist = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
+    ol.imu_port(ist, n, regs[:1], None, do_init=True)
+    yaw0 = layout.soa_to_aos(ist, n, layout.IS_WORDS)[:, layout.IS_DATA + 11].copy().view(np.float32)
+    out = ol.imu_port(ist, n, np.ascontiguousarray(regs[1:]), np.ascontiguousarray(have[1:]), want_out=True)
+    yaw = (np.ascontiguousarray(out[:, 2, :, 3]).view(np.float32) * streams.DEG2RAD).astype(np.float32)
+    pst, ptr = port_run(dict(inp, yaw=yaw, yaw_period=slow), nthreads=8)
+
+    def run():
+        vb = VehicleBatch(n, DEV)
+        cmd = _dev(inp["cmd"], np.int32).reshape(-1, n, 4)
+        tr = torch.zeros((steps, 16, n), dtype=torch.int32, device=DEV)
+        a = vb.make_args(steps, cmd=cmd, seg_len=inp["seg_len"], trace=tr)
+        regs_d, have_d, yaw0_d = _dev(streams.imu_cells(regs[1:])), _dev(have[1:]), _dev(yaw0)
+        a.d_imu_regs, a.d_imu_have_quat, a.d_imu_yaw0_deg = regs_d.data_ptr(), have_d.data_ptr(), yaw0_d.data_ptr()
+        a.n_yaw, a.yaw_period = n_slow, slow
+        vb.rollout_args(a)
+        torch.cuda.synchronize()
+        return vb.state.cpu().numpy().view(np.uint32), tr.cpu().numpy().view(np.uint32)
+
+    st, tr = run()
+    assert_same(tr, ptr, "IMU-register yaw vs port trace")
+    assert_same(st, pst, "IMU-register yaw vs port state")
+    lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, 1)
+    try:
+        st_t, tr_t = run()
+    finally:
+        lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, 0)
+    assert_same(tr_t, ptr, "IMU-register yaw, transcription kernel vs port trace")
+    assert_same(st_t, pst, "IMU-register yaw, transcription kernel vs port state")
