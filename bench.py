@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall budget of the cpu_baseline leg")
     ap.add_argument("--occupancy", type=int, default=0, help="RK_OPT_FAST_OCCUPANCY override (tuning)")
     ap.add_argument("--packed", type=int, default=-1, help="RK_OPT_FAST_PACKED override (tuning; -1 = library default)")
+    ap.add_argument("--ffsat", type=int, default=-1, help="RK_OPT_FAST_FFSAT override (tuning; -1 = library default)")
     ap.add_argument("--side-ctas", type=int, default=-1, help="RK_OPT_TICK_SIDE_CTAS override (tuning; -1 = library default)")
     ap.add_argument("--no-modules", action="store_true", help="workload full: skip the configs[1..3] module measurements")
     ap.add_argument("--no-e2e", action="store_true")
@@ -469,6 +470,8 @@ def run_ours(a):
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_OCCUPANCY, a.occupancy))
     if a.packed >= 0:
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_PACKED, a.packed))
+    if a.ffsat >= 0:
+        _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_FFSAT, a.ffsat))
     n, K, W, T = a.instances, a.steps, a.warmup, a.ticks
     first = rank * n  # contiguous slice of the global instance index space
     n_seg = (T + a.seg_len - 1) // a.seg_len
@@ -685,6 +688,8 @@ def run_ours_full(a):
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_OCCUPANCY, a.occupancy))
     if a.side_ctas >= 0:
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_TICK_SIDE_CTAS, a.side_ctas))
+    if a.ffsat >= 0:
+        _cabi.check(lib.rk_set_option(_cabi.RK_OPT_FAST_FFSAT, a.ffsat))
     K, W, T, slow = a.steps, a.warmup, a.ticks, a.slow_period
     lo, hi = sharding.shard_range(a.total, rank, world)
     n_rank = hi - lo

@@ -59,6 +59,7 @@ enum {
   RK_OPT_FORCE_TRANSCRIPTION = 1,
   RK_OPT_FAST_OCCUPANCY = 2, /* 3 or 4 (default) resident CTAs/SM: register budget of the rollout kernel */
   RK_OPT_FAST_PACKED = 3,    /* 1 (default): packed FADD2/FFMA2 tick; 0: scalar tick.  Bit-identical; tests compare. */
+  RK_OPT_FAST_FFSAT = 5,     /* 1: the feed-forward clamp to +-1 as two FMUL.SAT (FMA pipe); 0 (default): as FMNMX (ALU pipe).  Bit-identical. */
   RK_OPT_TICK_SIDE_CTAS = 4  /* rk_tick_rollout: CTAs per SM its IMU / arm kernels may occupy beside the vehicle
                               * rollout (default 1; 0 = full grids).  Scheduling only, results do not depend on it. */
 };
@@ -479,6 +480,11 @@ int rk_adh_update(const rk_adt_params_t *p, void *d_state, void *d_hstate, int64
                   uint32_t *d_trace, void *stream);
 
 /* single-instance handle (drop-in for the statics of AD_task_main.cpp:108-156) */
+/* Self-test (tests): the arm tick divides its five per-segment steps by one count through a shared double-precision
+ * reciprocal (csrc/rk_arm.cu div_by_rcp64, proven equal to the IEEE division); this compares the two on `pairs`
+ * pseudo-random (x, c) pairs on the device and returns the number of mismatches.  Synchronous. */
+int rk_selftest_div_rcp64(uint64_t pairs, uint64_t seed, uint32_t *mismatches);
+
 typedef struct rk_adt rk_adt_t;
 int  rk_adt_create(rk_adt_t **out, const rk_adt_params_t *p /* NULL = defaults */);
 void rk_adt_destroy(rk_adt_t *h);
@@ -522,6 +528,10 @@ typedef struct rk_tick_rollout {
 
 int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t *ap, void *d_vdt_state, void *d_imt_state,
                     void *d_adt_state, const void *d_adt_cmdtab, int64_t n, const rk_tick_rollout_t *args, void *stream);
+/* Diagnostics (tools/tick_timeline.py): enable != 0 makes later rk_tick_rollout calls record timestamps; with out !=
+ * NULL the call synchronises the device and returns, for the last rk_tick_rollout on the current device, milliseconds
+ * since its entry: side stream starts, IMU kernel done, arm kernel done, vehicle rollout starts, vehicle rollout done. */
+int rk_tick_debug_timeline(int enable, float out[5]);
 
 /* =====================================================================================
  * Synthetic command / sensor streams, generated on the device.  A rollout engine fed over PCIe

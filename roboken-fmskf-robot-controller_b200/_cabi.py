@@ -22,6 +22,7 @@ RK_OPT_FORCE_TRANSCRIPTION = 1
 RK_OPT_FAST_OCCUPANCY = 2
 RK_OPT_FAST_PACKED = 3
 RK_OPT_TICK_SIDE_CTAS = 4
+RK_OPT_FAST_FFSAT = 5
 
 
 class VdtParams(C.Structure):
@@ -200,6 +201,8 @@ def _proto(lib):
     lib.rk_stream_vehicle_yaw_reg.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
     lib.rk_stream_imu_samples.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp]
     lib.rk_stream_arm_sequences.argtypes = [vp, C.c_int64, vp, vp]
+    lib.rk_selftest_div_rcp64.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.rk_tick_debug_timeline.argtypes = [C.c_int, C.POINTER(C.c_float)]
     lib.rk_rmt_default_params.argtypes = [C.POINTER(RmtParams)]
     lib.rk_rmt_default_params.restype = None
     lib.rk_rmt_state_words.restype = C.c_size_t

@@ -185,6 +185,22 @@ RK_DEV void ring_next(const ArmLoop &a, uint32_t slot, uint32_t idx, uint32_t &n
   nslot = next ? nx : slot, nidx = more ? idx + 1 : (next ? 0u : idx);
 }
 
+// IEEE single-precision x / c through one double-precision reciprocal shared by several numerators:
+//   RN32(x / c) == RN32(RN64((double)x * RN64(1 / (double)c)))   whenever the quotient is a NORMAL float (or 0, inf, NaN).
+// Why: a normal-range quotient of two floats is never a midpoint of two adjacent floats, and is at least 2^-49
+// (relative) away from every such midpoint (|A * 2^ea - B * M * 2^e| >= 2^e for the 24-bit significands A, B and a 25-bit
+// odd M, over B * M * 2^e < 2^49 * 2^e), while the double product carries at most 2^-52 of relative error (2^-53 from the
+// rounded reciprocal, 2^-53 from the product) -- so it lies on the same side of every float rounding boundary as the
+// exact quotient.  Zeros keep the numerator's sign, x / inf = 0, x / 0 = inf, 0 / 0 = NaN as in the IEEE division.
+// SUBNORMAL quotients can be exact ties (3 * 2^-149 / 6 = 2^-150), where the inexact reciprocal decides the rounding
+// instead of ties-to-even: those (|q| < 2^-125, x != 0) take the IEEE division.  rk_selftest_div_rcp64
+// (tests/test_arm_gpu.py) compares the function with div.rn.f32 on 2^32 (x, c) pairs, integer counts included.
+RK_DEV float div_by_rcp64(float x, float c, double rc) {
+  const float q = __double2float_rn(__dmul_rn((double)x, rc));
+  if(fabsf(q) < 2.3509887e-38f /* 2^-125 */ && x != 0.0f) return fdiv(x, c);
+  return q;
+}
+
 RK_DEV uint4 ldp(const uint4 *st, int64_t n, int64_t i, int word) { return ld_plane(st, n, word / 4, i); }
 
 RK_DEV void loop_load(const uint4 *st, int64_t n, int64_t i, ArmLoop &a, uint32_t &jflags) {
@@ -301,11 +317,10 @@ RK_DEV void loop_fsm_transitions(ArmLoop &a, const rk_adt_params_t &p, const uin
       int32_t     cnt  = f2i_x86((span == 0.0f && p.cycle_time_s > 0.0f) ? span : fdiv(span, p.cycle_time_s));
       cnt              = (cnt <= 0) ? 1 : cnt;
       const float fc   = (float)cnt; // >= 1
+      // the five divisions by the same count: x / c == (float)((double)x * RN64(1 / c)) for every float x and c (div_by_rcp64)
+      const double rc = __drcp_rn((double)fc);
 #pragma unroll
-      for(int k = 0; k < 5; k++) {
-        const float d = fsub(a.now_tgt[k], fsub(a.tgt[k], a.ofs[k]));
-        a.move[k]     = (d == 0.0f) ? d : fdiv(d, fc);
-      }
+      for(int k = 0; k < 5; k++) a.move[k] = div_by_rcp64(fsub(a.now_tgt[k], fsub(a.tgt[k], a.ofs[k])), fc, rc);
       a.cnt      = cnt;
       a.total_ms = a.now_dt;
       a.cyc      = 0;
@@ -1078,6 +1093,25 @@ static int adt_check(const char *who, const void *a, const void *b, int64_t n) {
 }
 static unsigned adt_grid(int64_t n) { return (unsigned)((n + 127) / 128); }
 
+// div_by_rcp64 against div.rn.f32 on `total` pseudo-random (x, c) pairs: all bit patterns of x, c alternately any
+// float and an integer count in 1 .. 2^24; counts the mismatches (NaNs compare as NaNs).
+__global__ void selftest_div_rcp64_kernel(unsigned long long total, unsigned long long seed, unsigned int *bad) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned int             mine   = 0;
+  for(unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+    unsigned long long z = (k + seed) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull, z = (z ^ (z >> 27)) * 0x94D049BB133111EBull, z ^= z >> 31;
+    const uint32_t hi = (uint32_t)(z >> 32);
+    // every fourth pair: a subnormal / tiny numerator over a small count -- the domain of exact ties
+    const float x = ((k & 3) == 2) ? u2f(((uint32_t)z & 0x81FFFFFFu)) : u2f((uint32_t)z);
+    const float c = (k & 1) ? u2f(hi) : (float)((hi & (((k & 3) == 2) ? 0xFFFu : 0xFFFFFFu)) + 1u);
+    const float want = fdiv(x, c), got = div_by_rcp64(x, c, __drcp_rn((double)c));
+    const bool  same = (f2u(want) == f2u(got)) || (want != want && got != got);
+    mine += same ? 0u : 1u;
+  }
+  if(mine) atomicAdd(bad, mine);
+}
+
 int rk_adt_mode_init(const rk_adt_params_t *p, void *d_state, int64_t n, void *stream) {
   if(n == 0) return RK_OK;
   if(!p) {
@@ -1380,4 +1414,19 @@ int rk_adt_get_targets_deg(rk_adt_t *h, float out[5]) {
   memcpy(out, h->h_stage, 20);
   return RK_OK;
 }
+}
+
+/* Self-test of the shared-reciprocal division the arm tick uses (div_by_rcp64): `pairs` pseudo-random (x, c) pairs
+ * against div.rn.f32; *mismatches receives the number that differ.  Synchronous. */
+extern "C" int rk_selftest_div_rcp64(uint64_t pairs, uint64_t seed, uint32_t *mismatches) {
+  if(!mismatches) return RK_ERR_ARG;
+  if(int rc = require_device()) return rc;
+  unsigned int *d = nullptr;
+  RK_CUDA(cudaMalloc((void **)&d, 4));
+  cudaMemset(d, 0, 4);
+  selftest_div_rcp64_kernel<<<148 * 8, 256>>>(pairs, seed, d);
+  const cudaError_t e = cudaMemcpy(mismatches, d, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if(e != cudaSuccess) return cuda_fail(e, "rk_selftest_div_rcp64");
+  return RK_OK;
 }

@@ -98,14 +98,13 @@ stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, in
     for(int k = 0; k < 6; k++) w[k] = sub32(b, (uint32_t)k); // AX..Yaw, two registers a word
     const uint32_t w6 = sub32(b, 6u), w7 = sub32(b, 7u);
     const uint32_t gu[4] = {w6 & 0xFFFFu, w6 >> 16, w7 & 0xFFFFu, w7 >> 16};
-    double         g[4];
+    float          g[4];
 #pragma unroll
-    for(int k = 0; k < 4; k++) g[k] = __dadd_rn(__dmul_rn(__dadd_rn((double)gu[k], 0.5), 1.0 / 32768.0), -1.0);
-    const double ss  = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g[0], g[0]), __dmul_rn(g[1], g[1])), __dmul_rn(g[2], g[2])), __dmul_rn(g[3], g[3]));
-    const double nrm = __dsqrt_rn(ss);
-    uint32_t     q[4];
+    for(int k = 0; k < 4; k++) g[k] = fsub(fmul(fadd((float)gu[k], 0.5f), 1.0f / 32768.0f), 1.0f);
+    const float nrm = fsqrt(fadd(fadd(fadd(fmul(g[0], g[0]), fmul(g[1], g[1])), fmul(g[2], g[2])), fmul(g[3], g[3])));
+    uint32_t    q[4];
 #pragma unroll
-    for(int k = 0; k < 4; k++) q[k] = (uint32_t)__double2int_rn(__dmul_rn(__ddiv_rn(g[k], nrm), 32767.0)) & 0xFFFFu;
+    for(int k = 0; k < 4; k++) q[k] = (uint32_t)__float2int_rn(fmul(fdiv(g[k], nrm), 32767.0f)) & 0xFFFFu;
     w[6] = q[0] | (q[1] << 16), w[7] = q[2] | (q[3] << 16);
     __stcs(cells + ((int64_t)u * 2 + 0) * n + i, make_uint4(w[0], w[1], w[2], w[3]));
     __stcs(cells + ((int64_t)u * 2 + 1) * n + i, make_uint4(w[4], w[5], w[6], w[7]));

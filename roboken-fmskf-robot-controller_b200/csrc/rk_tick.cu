@@ -24,7 +24,10 @@ struct TickStreams {
   cudaStream_t side = nullptr;
   cudaEvent_t  fork = nullptr, join = nullptr;
   int          sm_count = 0;
+  // diagnostics (rk_tick_debug_timeline): timestamps of the last call's kernels, recorded only while enabled
+  cudaEvent_t tl[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+static bool g_tick_timeline = false;
 static std::mutex  g_tick_mu; // held across the whole fork / launch / join sequence: the event pair is per device
 static TickStreams g_tick[64];
 static int         g_tick_side_ctas_per_sm = 1; // rk_set_option(RK_OPT_TICK_SIDE_CTAS, 0..8): 0 = uncapped grids
@@ -86,6 +89,12 @@ extern "C" int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t 
   const int32_t n_slow = (a->steps + a->slow_period - 1) / a->slow_period;
   const int     cap    = g_tick_side_ctas_per_sm * ts->sm_count;
 
+  auto mark = [&](int k, cudaStream_t s) { // diagnostics only
+    if(!g_tick_timeline) return;
+    if(!ts->tl[k]) cudaEventCreate(&ts->tl[k]);
+    cudaEventRecord(ts->tl[k], s);
+  };
+  mark(0, st);
   // what the vehicle holds if IMU update 0 carries no quaternion frame; taken before the IMU kernel can store
   tick_yaw0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4 *)d_imt_state, n, a->d_yaw);
   RK_CUDA(cudaGetLastError());
@@ -93,8 +102,11 @@ extern "C" int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t 
   // IMU: n_slow updates, arm: n_slow ticks -- on the side stream, forked from / joined to the caller's stream
   RK_CUDA(cudaEventRecord(ts->fork, st));
   RK_CUDA(cudaStreamWaitEvent(ts->side, ts->fork, 0));
+  mark(1, ts->side);
   int rc = imt_update_launch(d_imt_state, n, n_slow, a->d_regs, a->d_have_quat, nullptr, nullptr, 0, cap, ts->side);
+  mark(2, ts->side);
   if(rc == RK_OK) rc = adt_update_launch(ap, d_adt_state, d_adt_cmdtab, n, n_slow, a->d_adt_trace, cap, ts->side);
+  mark(3, ts->side);
   const cudaError_t ej = cudaEventRecord(ts->join, ts->side); // whatever was enqueued on the side stream is joined below
   if(rc == RK_OK && ej == cudaSuccess) {
     rk_vdt_rollout_t v = {};
@@ -103,7 +115,9 @@ extern "C" int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t 
     v.d_imu_regs = a->d_regs, v.d_imu_have_quat = a->d_have_quat, v.d_imu_yaw0_deg = a->d_yaw;
     v.n_yaw = n_slow, v.yaw_period = a->slow_period;
     v.d_trace = a->d_vdt_trace, v.d_goal = a->d_goal, v.d_cost = a->d_cost;
+    mark(4, st);
     rc = rk_vdt_rollout(vp, d_vdt_state, n, &v, st);
+    mark(5, st);
   }
   if(ej == cudaSuccess) {
     const cudaError_t ew = cudaStreamWaitEvent(st, ts->join, 0);
@@ -112,4 +126,24 @@ extern "C" int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t 
     rc = cuda_fail(ej, "cudaEventRecord(join)");
   }
   return rc;
+}
+
+/* Diagnostics: enable = 1 makes the following rk_tick_rollout calls record timestamps; with out != NULL the call
+ * synchronises the device and returns, for the LAST rk_tick_rollout on the current device, milliseconds relative to
+ * its entry: [0] side stream starts, [1] IMU kernel done, [2] arm kernel done, [3] vehicle rollout starts,
+ * [4] vehicle rollout done. */
+extern "C" int rk_tick_debug_timeline(int enable, float out[5]) {
+  if(int rc = require_device()) return rc;
+  std::lock_guard<std::mutex> lk(g_tick_mu);
+  g_tick_timeline = enable != 0;
+  if(!out) return RK_OK;
+  TickStreams *ts = nullptr;
+  if(int rc = tick_streams(&ts)) return rc;
+  RK_CUDA(cudaDeviceSynchronize());
+  for(int k = 0; k < 5; k++) {
+    out[k] = -1.0f;
+    if(ts->tl[0] && ts->tl[k + 1]) cudaEventElapsedTime(&out[k], ts->tl[0], ts->tl[k + 1]);
+  }
+  cudaGetLastError();
+  return RK_OK;
 }

@@ -196,10 +196,12 @@ RK_DEV void yaw_feed_take(YawFeed &y, const rk_vdt_rollout_t &a, int64_t n, int6
   }
 }
 
-template <bool TRACE, int OCC, bool FFSAT, bool PACKED>
+// FLAGS: bit 0 FFSAT (ff_limit == 1: FMUL.SAT form of the feed-forward clamp), bit 1 KD0 (kd == 0, packed tick only)
+template <bool TRACE, int OCC, int FLAGS, bool PACKED>
 __global__ void __launch_bounds__(kFastThreads, OCC * 128 / kFastThreads)
 vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
-  constexpr int D0 = 1, D1 = 1, D2 = -1, D3 = -1; // VD_task_main.cpp:75-78 (host checks params match)
+  constexpr int  D0 = 1, D1 = 1, D2 = -1, D3 = -1; // VD_task_main.cpp:75-78 (host checks params match)
+  constexpr bool FFSAT = (FLAGS & 1) != 0, KD0 = (FLAGS & 2) != 0;
   __shared__ float s_tab[513];
   stage_sin_table(s_tab);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,17 +235,19 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
         FastVeh2 f;
         to_fast2(v, f, p.ts, fc.B0);
         const float nz = fmul(-0.0f, p.ts); // opaque -0.0f (p.ts > 0 is a fast-path precondition)
-        while(t < t_end) {
-          if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
-          const int    t_stop = min(t_end, yf.next);
-          const float2 cs = make_float2(cth, sth), sc = make_float2(sth, cth);
+        // ONE loop over the chunk; the yaw boundary (every yaw_period ticks, the same tick in every lane) is a cold
+        // branch inside it, so the tick's loop-carried registers stay where they are across boundaries
+        float2 cs = make_float2(cth, sth), sc = make_float2(sth, cth);
 #pragma unroll kFastUnroll
-          for(; t < t_stop; t++) {
-            float vel[3], tgt[3];
-            fast_tick2<FFSAT, TRACE>(f, p, fc, cs, sc, nz, vel, tgt);
-            trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1],
-                             TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
+        for(; t < t_end; t++) {
+          if(t == yf.next) {
+            yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
+            cs = make_float2(cth, sth), sc = make_float2(sth, cth);
           }
+          float vel[3], tgt[3];
+          fast_tick2<FFSAT, TRACE, KD0>(f, p, fc, cs, sc, nz, vel, tgt);
+          trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1],
+                           TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
         }
         v.pos[2] = pth;
         from_fast2<D0, D1, D2, D3>(v, f, t - t0);
@@ -251,16 +255,13 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
       } else {
         FastVeh f;
         to_fast<D0, D1, D2, D3>(v, f, p.ts, fc.B0);
-        while(t < t_end) {
-          if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
-          const int t_stop = min(t_end, yf.next);
 #pragma unroll kFastUnroll
-          for(; t < t_stop; t++) {
-            float vel[3], tgt[3];
-            fast_tick<D0, D1, D2, D3, FFSAT>(f, p, fc, cth, sth, vel, tgt);
-            trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur,
-                             TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
-          }
+        for(; t < t_end; t++) {
+          if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
+          float vel[3], tgt[3];
+          fast_tick<D0, D1, D2, D3, FFSAT>(f, p, fc, cth, sth, vel, tgt);
+          trace_row<TRACE>(a.d_trace, n, i, t, f.px, f.py, pth, vel, tgt, f.w[0].cur, f.w[1].cur, f.w[2].cur, f.w[3].cur,
+                           TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
         }
         v.pos[2] = pth;
         from_fast<D0, D1, D2, D3>(v, f, t - t0);
@@ -294,10 +295,11 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
 #ifndef RK_STREAM_OCC
 #define RK_STREAM_OCC 3
 #endif
-template <bool TRACE, bool FFSAT>
+template <bool TRACE, int FLAGS>
 __global__ void __launch_bounds__(kFastThreads, RK_STREAM_OCC)
 vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
-  constexpr int D0 = 1, D1 = 1, D2 = -1, D3 = -1;
+  constexpr int  D0 = 1, D1 = 1, D2 = -1, D3 = -1;
+  constexpr bool FFSAT = (FLAGS & 1) != 0, KD0 = (FLAGS & 2) != 0;
   __shared__ float s_tab[513];
   stage_sin_table(s_tab);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,19 +336,21 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
       to_fast2(v, f, p.ts, fc.B0);
       stream_sense_load(ss, v);
       const float nz = fmul(-0.0f, p.ts);
-      while(t < t_end) {
-        if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
-        const int    t_stop = min(t_end, yf.next);
-        const float2 cs = make_float2(cth, sth), sc = make_float2(sth, cth);
+      float2 cs = make_float2(cth, sth), sc = make_float2(sth, cth);
+      {
 #pragma unroll 2
-        for(; t < t_stop; t++) {
+        for(; t < t_end; t++) {
+          if(t == yf.next) {
+            yaw_feed_take(yf, a, n, i, s_tab, pth, cth, sth);
+            cs = make_float2(cth, sth), sc = make_float2(sth, cth);
+          }
           uint64_t fr[4];
 #pragma unroll
           for(int k = 0; k < 4; k++) fr[k] = fpf[k];
 #pragma unroll
           for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + ((int64_t)(t + 1) * 4 + k) * n); // t + 1 <= K - 1 inside a chunk
           float vel[3], tgt[3];
-          fast_tick2_stream<FFSAT, TRACE>(f, ss, fr, p, fc, cs, sc, nz, vel, tgt);
+          fast_tick2_stream<FFSAT, TRACE, KD0>(f, ss, fr, p, fc, cs, sc, nz, vel, tgt);
           trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1],
                            TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
         }
@@ -482,6 +486,8 @@ int  tick_set_side_ctas(int v);                     // rk_tick.cu
 
 static int g_fast_occupancy = 4;       // rk_set_option(RK_OPT_FAST_OCCUPANCY, 3|4|5): tuning
 static int g_fast_packed = 1;          // rk_set_option(RK_OPT_FAST_PACKED, 0|1): packed FP32 tick (default) or scalar
+static int g_fast_ffsat = 0;           // rk_set_option(RK_OPT_FAST_FFSAT, 0|1): FMUL.SAT form of the feed-forward clamp.  Off since
+                                       // round 2: the packed tick is bound by FP32 lanes, the FMNMX form runs on the ALU pipe (8.83 vs 8.94 ms)
 static int g_force_transcription = 0; // rk_vdt_set_option(RK_OPT_FORCE_TRANSCRIPTION, 1): tests
 
 // The fast kernel is compiled for the firmware's wiring (directions +,+,-,-) and needs
@@ -534,6 +540,10 @@ int rk_set_option(int option, int value) {
   }
   if(option == RK_OPT_FAST_OCCUPANCY && (value >= 3 && value <= 4)) {
     rk::g_fast_occupancy = value;
+    return RK_OK;
+  }
+  if(option == RK_OPT_FAST_FFSAT) {
+    rk::g_fast_ffsat = value != 0;
     return RK_OK;
   }
   if(option == RK_OPT_TICK_SIDE_CTAS && rk::tick_set_side_ctas(value) == RK_OK) return RK_OK;
@@ -602,21 +612,22 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
   case RK_SENSOR_HOLD: e = launch_rollout<RK_SENSOR_HOLD>(*p, d_state, n, *args, st); break;
   case RK_SENSOR_PLANT:
     if(fast_path_usable(*p)) {
-      const unsigned grid = (unsigned)((n + kFastThreads - 1) / kFastThreads);
-      const bool ffsat = (p->ff_limit == 1.0f);
-#define RK_LAUNCH_FAST2(TR, OCC, SAT)                                                                              \
-  do {                                                                                                             \
-    if(g_fast_packed)                                                                                              \
-      vdt_rollout_fast_kernel<TR, OCC, SAT, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); \
-    else                                                                                                           \
-      vdt_rollout_fast_kernel<TR, OCC, SAT, false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);\
-  } while(0)
-#define RK_LAUNCH_FAST(TR, OCC)                                                                                    \
-  do {                                                                                                             \
-    if(ffsat)                                                                                                      \
-      RK_LAUNCH_FAST2(TR, OCC, true);                                                                              \
-    else                                                                                                           \
-      RK_LAUNCH_FAST2(TR, OCC, false);                                                                             \
+      const unsigned grid  = (unsigned)((n + kFastThreads - 1) / kFastThreads);
+      const int      flags = ((p->ff_limit == 1.0f && g_fast_ffsat) ? 1 : 0) | ((p->kd == 0.0f && g_fast_packed) ? 2 : 0);
+#define RK_LAUNCH_FAST3(TR, OCC, FL, PK) vdt_rollout_fast_kernel<TR, OCC, FL, PK><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args)
+#define RK_LAUNCH_FAST(TR, OCC)                                    \
+  do {                                                             \
+    if(!g_fast_packed) {                                           \
+      if(flags & 1) RK_LAUNCH_FAST3(TR, OCC, 1, false);            \
+      else RK_LAUNCH_FAST3(TR, OCC, 0, false);                     \
+    } else {                                                       \
+      switch(flags) {                                              \
+      case 3: RK_LAUNCH_FAST3(TR, OCC, 3, true); break;            \
+      case 2: RK_LAUNCH_FAST3(TR, OCC, 2, true); break;            \
+      case 1: RK_LAUNCH_FAST3(TR, OCC, 1, true); break;            \
+      default: RK_LAUNCH_FAST3(TR, OCC, 0, true); break;           \
+      }                                                            \
+    }                                                              \
   } while(0)
       if(args->d_trace) {
         RK_LAUNCH_FAST(true, 4);
@@ -627,7 +638,7 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
         }
       }
 #undef RK_LAUNCH_FAST
-#undef RK_LAUNCH_FAST2
+#undef RK_LAUNCH_FAST3
       e = cudaGetLastError();
     } else {
       e = launch_rollout<RK_SENSOR_PLANT>(*p, d_state, n, *args, st);
@@ -636,14 +647,19 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
   case RK_SENSOR_STREAM:
     if(fast_path_usable(*p)) {
       const unsigned grid  = (unsigned)((n + kFastThreads - 1) / kFastThreads);
-      const bool     ffsat = (p->ff_limit == 1.0f);
-      if(args->d_trace) {
-        if(ffsat) vdt_rollout_stream_fast_kernel<true, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
-        else vdt_rollout_stream_fast_kernel<true, false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
-      } else {
-        if(ffsat) vdt_rollout_stream_fast_kernel<false, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
-        else vdt_rollout_stream_fast_kernel<false, false><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
-      }
+      const int      flags = ((p->ff_limit == 1.0f && g_fast_ffsat) ? 1 : 0) | ((p->kd == 0.0f) ? 2 : 0);
+#define RK_LAUNCH_STREAM(TR)                                                                                                  \
+  do {                                                                                                                        \
+    switch(flags) {                                                                                                           \
+    case 3: vdt_rollout_stream_fast_kernel<TR, 3><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); break;      \
+    case 2: vdt_rollout_stream_fast_kernel<TR, 2><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); break;      \
+    case 1: vdt_rollout_stream_fast_kernel<TR, 1><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); break;      \
+    default: vdt_rollout_stream_fast_kernel<TR, 0><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); break;     \
+    }                                                                                                                         \
+  } while(0)
+      if(args->d_trace) RK_LAUNCH_STREAM(true);
+      else RK_LAUNCH_STREAM(false);
+#undef RK_LAUNCH_STREAM
       e = cudaGetLastError();
     } else {
       e = launch_rollout<RK_SENSOR_STREAM>(*p, d_state, n, *args, st);

@@ -246,7 +246,11 @@ RK_DEV void from_fast2_stream(Veh &v, const FastVeh2 &f, const StreamSense &ss, 
 // (int16_t)(u * 1000.0f) * dir: trunc(-x) == -trunc(x) and sext16(-sext16(t)) == sext16(-t), so the direction
 // folds into the multiplier.  The chunk only runs here when |u * 1000| < 2^31 is guaranteed (fast_u_bounded),
 // so the conversion never saturates and equals x86's cvttss2si.
-template <int DIR, bool FFSAT>
+// KD0: Dgain_ == 0 (the firmware's setting, VD_task_main.cpp:86-89).  Kd * y is then +-0 for every finite y (the chunk
+// bound keeps y finite), and (Kp*e + I) - (+-0) is (Kp*e + I) -- except that a zero result may come out as +0 where the
+// subtraction gives -0; the sum only feeds the integer conversion of u * 1000, which maps both zeros to 0.  So the product
+// and the subtraction are dropped; the filter itself still runs (its state is stored).
+template <int DIR, bool FFSAT, bool KD0>
 RK_DEV void fast_wheel_ctrl2(FastWheel2 &w, const rk_vdt_params_t &p, const FastConsts &fc, float2 tgt, float2 now, float nz) {
   const float2 err = sub2(tgt, now);
   const float2 x   = mul2(sub2(now, w.prev_val), bc2(p.ctrl_freq), nz);
@@ -255,7 +259,8 @@ RK_DEV void fast_wheel_ctrl2(FastWheel2 &w, const rk_vdt_params_t &p, const Fast
   w.lpf_y = y, w.x_l = x, w.b0x = b0x;
   const float2 ig = add2(w.integ, mul2(err, bc2(fc.ki_dt), nz));
   w.integ         = make_float2(clamp_sym(ig.x, p.i_limit, fc.neg_i_limit), clamp_sym(ig.y, p.i_limit, fc.neg_i_limit));
-  float2 u        = sub2(add2(mul2(err, bc2(p.kp), nz), w.integ), mul2(y, bc2(p.kd), nz));
+  float2 u        = add2(mul2(err, bc2(p.kp), nz), w.integ);
+  if(!KD0) u = sub2(u, mul2(y, bc2(p.kd), nz));
   w.prev_val      = now;
   float2 ff;
   if(FFSAT) {
@@ -275,7 +280,7 @@ RK_DEV void fast_wheel_ctrl2(FastWheel2 &w, const rk_vdt_params_t &p, const Fast
 
 // One packed fast tick on the feedback s.  cs = {cos, sin}(yaw), sc = {sin, cos}(yaw).
 // TRACE: also forms now_vhcl_vel_mmps (vel) -- see the header comment.
-template <bool FFSAT, bool TRACE>
+template <bool FFSAT, bool TRACE, bool KD0>
 RK_DEV void fast_tick2_core(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &fc, float2 cs, float2 sc, float nz,
                             float vel[3], float tgt[3], const Sense &s) {
   // Mvel = (rpm * RPM_TO_RADPS) * GEAR_RATIO_INV ; controller input = Mvel * GEAR_RATIO   :21-24,70-73
@@ -315,11 +320,11 @@ RK_DEV void fast_tick2_core(FastVeh2 &f, const rk_vdt_params_t &p, const FastCon
   const float2 xy = make_float2(fsub(tgt[0], tgt[1]), fadd(tgt[0], tgt[1]));
   const float2 t01 = mul2(div_const2(sub2(xy, bc2(T)), R, fc.rcp_r, nz), bc2(RK_GEAR_RATIO), nz);
   const float2 t23 = mul2(div_const2(add2(xy, bc2(T)), R, fc.rcp_r, nz), bc2(RK_GEAR_RATIO), nz);
-  fast_wheel_ctrl2<1, FFSAT>(f.w01, p, fc, t01, now01, nz);
-  fast_wheel_ctrl2<-1, FFSAT>(f.w23, p, fc, t23, now23, nz);
+  fast_wheel_ctrl2<1, FFSAT, KD0>(f.w01, p, fc, t01, now01, nz);
+  fast_wheel_ctrl2<-1, FFSAT, KD0>(f.w23, p, fc, t23, now23, nz);
 }
 
-template <bool FFSAT, bool TRACE>
+template <bool FFSAT, bool TRACE, bool KD0>
 RK_DEV void fast_tick2(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &fc, float2 cs, float2 sc, float nz,
                        float vel[3], float tgt[3]) {
   Sense s;
@@ -327,10 +332,10 @@ RK_DEV void fast_tick2(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &
   fast_wheel_sense2<1>(f.w01.rpm[1], f.w01.cur[1], f.w01.dsum[1], s.rw01.y, s.d1);
   fast_wheel_sense2<-1>(f.w23.rpm[0], f.w23.cur[0], f.w23.dsum[0], s.rw23.x, s.d2);
   fast_wheel_sense2<-1>(f.w23.rpm[1], f.w23.cur[1], f.w23.dsum[1], s.rw23.y, s.d3);
-  fast_tick2_core<FFSAT, TRACE>(f, p, fc, cs, sc, nz, vel, tgt, s);
+  fast_tick2_core<FFSAT, TRACE, KD0>(f, p, fc, cs, sc, nz, vel, tgt, s);
 }
 // the same tick fed by four recorded frames (RK_SENSOR_STREAM)
-template <bool FFSAT, bool TRACE>
+template <bool FFSAT, bool TRACE, bool KD0>
 RK_DEV void fast_tick2_stream(FastVeh2 &f, StreamSense &ss, const uint64_t fr[4], const rk_vdt_params_t &p, const FastConsts &fc,
                               float2 cs, float2 sc, float nz, float vel[3], float tgt[3]) {
   Sense s;
@@ -338,7 +343,7 @@ RK_DEV void fast_tick2_stream(FastVeh2 &f, StreamSense &ss, const uint64_t fr[4]
   fast_wheel_rx2<1>(ss, 1, f.w01.dsum[1], fr[1], s.rw01.y, s.d1);
   fast_wheel_rx2<-1>(ss, 2, f.w23.dsum[0], fr[2], s.rw23.x, s.d2);
   fast_wheel_rx2<-1>(ss, 3, f.w23.dsum[1], fr[3], s.rw23.y, s.d3);
-  fast_tick2_core<FFSAT, TRACE>(f, p, fc, cs, sc, nz, vel, tgt, s);
+  fast_tick2_core<FFSAT, TRACE, KD0>(f, p, fc, cs, sc, nz, vel, tgt, s);
 }
 
 // ---- |u * 1000| < 2^31 for every tick of a chunk that starts in state v -------------------------------

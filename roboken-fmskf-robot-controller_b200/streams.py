@@ -459,7 +459,8 @@ def vehicle_yaw_reg_v2(n, n_yaw, seed=0x5EED, first=0, inst=None):
 def imu_samples_v2(n, n_upd, seed=0x5EED, first=0, drop_every=64, inst=None, first_update=0):
     """imu_samples() on the 32-bit hash: int16 [n_upd, 16, n] (+ have_quat uint8 [n_upd, n]).  One hash per
     (IMU, update); its draws 0-5 are AX..Yaw two registers a word, 6-7 four 16-bit uniforms in (-1, 1) normalised in
-    float64 to a unit quaternion x 32767 (rounded half to even), 8 the missing-quaternion-frame flag."""
+    float32 (IEEE sqrt / division, fixed order) to a unit quaternion x 32767 (rounded half to even), 8 the
+    missing-quaternion-frame flag."""
     inst = _inst(n, first, inst)[None, :]
     u = (np.arange(n_upd, dtype=np.uint64) + np.uint64(first_update))[:, None]
     b = h32(seed, 20, inst, u)  # [n_upd, n]
@@ -469,10 +470,11 @@ def imu_samples_v2(n, n_upd, seed=0x5EED, first=0, drop_every=64, inst=None, fir
         regs[:, 2 * k, :] = (w & _U32(0xFFFF)).astype(np.uint16).view(np.int16)
         regs[:, 2 * k + 1, :] = (w >> _U32(16)).astype(np.uint16).view(np.int16)
     w6, w7 = sub32(b, 6), sub32(b, 7)
-    g = [((x.astype(np.float64) + 0.5) * (1.0 / 32768.0)) - 1.0 for x in (w6 & _U32(0xFFFF), w6 >> _U32(16), w7 & _U32(0xFFFF), w7 >> _U32(16))]
-    nrm = np.sqrt(((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]) + g[3] * g[3])
+    f32 = np.float32
+    g = [((x.astype(np.float32) + f32(0.5)) * f32(1.0 / 32768.0)) - f32(1.0) for x in (w6 & _U32(0xFFFF), w6 >> _U32(16), w7 & _U32(0xFFFF), w7 >> _U32(16))]
+    nrm = np.sqrt(((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]) + g[3] * g[3], dtype=np.float32)
     for k in range(4):
-        regs[:, 12 + k, :] = np.rint((g[k] / nrm) * 32767.0).astype(np.int16)
+        regs[:, 12 + k, :] = np.rint((g[k] / nrm) * f32(32767.0)).astype(np.int16)
     if drop_every:
         have = ((sub32(b, 8) % _U32(drop_every)) != 0).astype(np.uint8)
     else:

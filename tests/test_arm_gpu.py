@@ -191,3 +191,15 @@ def test_arm_single_instance_handle_debug_2():
     ol.arm_batch("port", "update", st, tb, 1, K=2 + 3 * 101 + 1)
     np.testing.assert_array_equal(arm.get_state(), st)
     arm.close()
+
+
+def test_shared_reciprocal_division_is_ieee():
+    """div_by_rcp64 (the arm tick's five per-segment divisions by one count) == div.rn.f32: 2^32 pseudo-random (x, c)
+    pairs on the device -- every bit pattern class of x; c alternately an arbitrary float and an integer 1 .. 2^24."""
+    import ctypes as C
+
+    from roboken_fmskf_robot_controller_b200 import _cabi
+
+    bad = C.c_uint32(123)
+    _cabi.check(_cabi.load().rk_selftest_div_rcp64(1 << 32, 2024, C.byref(bad)))
+    assert bad.value == 0
