@@ -176,7 +176,8 @@ typedef struct rk_vdt_cmd { float vx, vy, vth; int32_t kind; } rk_vdt_cmd_t; /* 
 
 /* Trace record written per tick when d_trace != NULL (tests / small N only):
  * word 0-2 pos, 3-5 vel, 6-8 vel_tgt, 9-12 s16_rawCurr_tgt (sign-extended), 13 the move-time countdown
- * (task_period > 0, else zero), 14-15 zero. */
+ * (task_period > 0, else zero), 14-15 the C610 current frame CAN_CTRL::tx_routine() puts on the bus after the tick
+ * (VD_can_controller.hpp:43-55: id 0x200, the four currents as big-endian s16; buf[0] in the low byte of word 14). */
 #define RK_VDT_TRACE_WORDS 16
 
 typedef struct rk_vdt_rollout {
@@ -233,6 +234,10 @@ int rk_vdt_set_target_vel(const rk_vdt_params_t *p, void *d_state, int64_t n, co
 int rk_vdt_motor_rx(const rk_vdt_params_t *p, void *d_state, int64_t n, int wheel,
                     const uint64_t *d_frames, const int16_t *d_usec, void *stream);
 
+/* CAN_CTRL::tx_routine  VD_can_controller.hpp:43-55 for every vehicle: d_frames[i] = the 8-byte C610 frame (id 0x200)
+ * holding the four s16_rawCurr_tgt big-endian, FL, BL, BR, FR; buf[0] in the low byte. */
+int rk_vdt_tx_frames(const void *d_state, int64_t n, uint64_t *d_frames, void *stream);
+
 /* ---- single-instance handle (drop-in for the static objects of VD_task_main.cpp:75-108) */
 typedef struct rk_vdt rk_vdt_t;
 int  rk_vdt_create(rk_vdt_t **out, const rk_vdt_params_t *p /* NULL = defaults */);
@@ -248,6 +253,7 @@ int  rk_vdt_get_vel(rk_vdt_t *h, float out[3]);     /* get_vehicle_vel_mmps_late
 int  rk_vdt_get_vel_tgt(rk_vdt_t *h, float out[3]); /* get_vehicle_vel_tgt_mmps_latest :61 */
 int  rk_vdt_get_raw_current(rk_vdt_t *h, int16_t out[4]); /* MOTOR_IF_M2006::get_rawCurr_tgt :52 */
 int  rk_vdt_get_angle_sum(rk_vdt_t *h, int64_t out[4]);   /* MOTOR_IF_M2006::get_rawAngleSum :42 */
+int  rk_vdt_get_tx_frame(rk_vdt_t *h, uint8_t frame[8]);  /* CAN_CTRL::tx_routine's msg.buf  VD_can_controller.hpp:43-55 */
 int  rk_vdt_get_state(rk_vdt_t *h, uint32_t words[RK_VS_WORDS]);
 int  rk_vdt_set_state(rk_vdt_t *h, const uint32_t words[RK_VS_WORDS]);
 
@@ -424,6 +430,22 @@ int rk_adt_update(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab,
  * d_status[i] in {0 PROCESSING, 1 DONE, 99 NO_DATA} for command id d_id[i]. */
 int rk_adt_cmdseq_status(const void *d_state, const void *d_cmdtab, int64_t n, const uint32_t *d_id,
                          int32_t *d_status, void *stream);
+
+/* ---- servo feedback (arm side): the CAN rx callbacks of the arm's servos, one 8-byte frame per arm.
+ * JointMyBldcServo::rx_callback -> rx_summary_status (AD_joint_mybldc_servo.cpp:45-70) for servo `slot` (0 DF_Left,
+ * 1 DF_Right, 2 P3): fl_raw_now_deg = s16_out_ang_deg_Q4 / 16 / gear * dir, fl_out_now_cur = s8_motor_curr_A_Q4 / 16
+ * * dir, and fl_raw_tgt_deg follows the measured angle while torque is off.  d_cmdid (uint32[n], the id without the
+ * device id; NULL = CMD_ID_RES_STATUS_SUMMARY 0x1000 for all): other ids are ignored as in the firmware.
+ * d_cur_A (float[n], optional) receives fl_out_now_cur -- nothing on the tick reads it, so it is not a state word. */
+int rk_adt_bldc_rx(const rk_adt_params_t *p, void *d_state, int64_t n, int slot, const uint64_t *d_frames, const uint32_t *d_cmdid,
+                   float *d_cur_A, void *stream);
+/* JointMgServo::rx_callback (AD_joint_mg_servo.cpp:75-92): command byte 0x9C / 0xA1 -> fl_out_now_cur through the
+ * double-precision quadratic conv_raw_to_current (AD_joint_mg_servo.hpp:120-128) into d_cur_A (optional; untouched by
+ * other frames); 0x92 -> fl_raw_now_deg from the multi-turn angle (and fl_raw_tgt_deg while torque is off).  The
+ * firmware's byte assembly shifts a promoted int by up to 48 bits (undefined in C++): the Cortex-M7 result -- the
+ * sign-extended low 32 bits -- is what is computed; the x86 build of the reference agrees for frames whose bytes 5..7
+ * are zero.  Other command bytes are ignored. */
+int rk_adt_mg_rx(const rk_adt_params_t *p, void *d_state, int64_t n, const uint64_t *d_frames, float *d_cur_A, void *stream);
 
 /* ---- ADTModePositioning (src/ArmDrive/AD_mode_positioning.{hpp,cpp}): the single-command mode behind
  * REQ_MOVE_POS (AD_task_main.cpp:260-272).  Same joints (the RK_AS_* block), its own mode block:

@@ -470,6 +470,33 @@ void ref_adt_batch(int op, uint32_t *state, uint32_t *cmdtab, int64_t n, int64_t
   }
 }
 
+/* Servo feedback frames through the reference's own CAN rx callbacks (arm side), same contract as
+ * rk_adt_bldc_rx / rk_adt_mg_rx: kind 0..2 = JointMyBldcServo::rx_callback of DF_Left / DF_Right / P3
+ * (AD_joint_mybldc_servo.cpp:45-70; cmdid NULL = CMD_ID_RES_STATUS_SUMMARY), kind 3 = JointMgServo::rx_callback
+ * (AD_joint_mg_servo.cpp:75-92).  cur[i] receives fl_out_now_cur when the frame carries a current, else stays. */
+void ref_adt_rx_batch(int kind, uint32_t *state, int64_t n, int64_t i0, int64_t i1, const uint64_t *frames, const uint32_t *cmdid,
+                      float *cur) {
+  for(int64_t i = i0; i < i1; i++) {
+    ArmSet  *s = make();
+    uint32_t w[RK_AS_WORDS];
+    for(int k = 0; k < RK_AS_WORDS; k++) w[k] = soa(state, n, i, k);
+    import_state(s, w);
+    const uint32_t SENT = 0x7FC12345u; /* a NaN no arithmetic produces: "not written" */
+    JointBase     *j    = (kind == 3) ? (JointBase *)&s->j_P1 : (JointBase *)s->bl(kind);
+    memcpy(&j->fl_out_now_cur, &SENT, 4);
+    uint64_t f = frames[i];
+    if(kind == 3) s->j_P1.rx_callback((JointMgServo::MgMsgRx *)&f, 0);
+    else s->bl(kind)->rx_callback(cmdid ? cmdid[i] : (uint32_t)CMD_ID_RES_STATUS_SUMMARY, (RES_MESSAGE *)&f, 0);
+    uint32_t cb;
+    memcpy(&cb, &j->fl_out_now_cur, 4);
+    if(cur && cb != SENT) memcpy(&cur[i], &cb, 4);
+    export_state(s, w);
+    for(int k = 0; k < RK_AS_WORDS; k++) soa(state, n, i, k) = w[k];
+    s->~ArmSet();
+    free(s);
+  }
+}
+
 /* ADTModePositioning batch driver on HOST arrays, same contracts as the rk_adp_* calls:
  * op 0 = rk_adp_mode_init, 1 = rk_adp_push_cmd (cmd: two planes per arm), 2 = K ticks (+trace), 3 = status */
 void ref_adp_batch(int op, uint32_t *state, uint32_t *pstate, int64_t n, int64_t i0, int64_t i1, int K, const uint32_t *cmd,

@@ -280,7 +280,18 @@ void rollout_one(VehicleSet *s, int64_t n, int64_t i, const rk_vdt_rollout_t *a)
       float f[9] = {p.x, p.y, p.th, v.x, v.y, v.th, g.x, g.y, g.th};
       for(int j = 0; j < 9; j++) tr[(int64_t)j * n] = f2u(f[j]);
       for(int k = 0; k < 4; k++) tr[(int64_t)(9 + k) * n] = (uint32_t)(int32_t)s->motor[k].get_rawCurr_tgt();
-      for(int j = 13; j < 16; j++) tr[(int64_t)j * n] = 0;
+      tr[(int64_t)13 * n] = 0;
+      { /* the C610 frame: VD_can_controller.hpp:43-55 needs FlexCAN and a static motor table, so the reference's own
+         * tx_routine() runs in the whole-task harness (libref_vdt_task.so, where tests/test_vdt_task_cpu.py pins these
+         * words); here the same bytes are laid out from get_rawCurr_tgt() */
+        uint8_t b[8];
+        for(int k = 0; k < 4; k++) {
+          b[2 * k]     = (uint8_t)(s->motor[k].get_rawCurr_tgt() >> 8);
+          b[2 * k + 1] = (uint8_t)(s->motor[k].get_rawCurr_tgt() & 0x00FF);
+        }
+        for(int j = 0; j < 2; j++)
+          tr[(int64_t)(14 + j) * n] = (uint32_t)b[4 * j] | ((uint32_t)b[4 * j + 1] << 8) | ((uint32_t)b[4 * j + 2] << 16) | ((uint32_t)b[4 * j + 3] << 24);
+      }
     }
   }
   if(a->d_cost && a->d_goal) {

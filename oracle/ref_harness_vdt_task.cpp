@@ -138,7 +138,11 @@ void run_isr_tick() {
     for(int k = 0; k < 4; k++)
       tr[(int64_t)(9 + k) * g_run.n] = (uint32_t)(int32_t)(int16_t)((M_CAN.last_tx.buf[2 * k] << 8) | M_CAN.last_tx.buf[2 * k + 1]);
     tr[(int64_t)13 * g_run.n] = U32_MOVE_TIME_CNT_ORDER;
-    for(int j = 14; j < 16; j++) tr[(int64_t)j * g_run.n] = 0;
+    /* ... and the frame itself, as CAN_CTRL<CAN1>::tx_routine() handed it to write() (words 14-15, wire order from the low byte) */
+    for(int j = 0; j < 2; j++) {
+      const uint8_t *b = M_CAN.last_tx.buf + 4 * j;
+      tr[(int64_t)(14 + j) * g_run.n] = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+    }
   }
   g_run.tick++;
 }

@@ -473,7 +473,12 @@ static void rollout_one(veh_t *v, const rk_vdt_params_t *p, int64_t n, int64_t i
       }
       for(k = 0; k < 4; k++) tr[(int64_t)(9 + k) * n] = (uint32_t)(int32_t)v->m[k].cur_tgt;
       tr[(int64_t)13 * n] = (a->task_period > 0) ? v->move_cnt : 0u;
-      for(j = 14; j < 16; j++) tr[(int64_t)j * n] = 0;
+      { /* CAN_CTRL::tx_routine  VD_can_controller.hpp:43-55: the C610 frame (id 0x200), four currents big-endian */
+        uint8_t b[8];
+        for(k = 0; k < 4; k++) b[2 * k] = (uint8_t)(v->m[k].cur_tgt >> 8), b[2 * k + 1] = (uint8_t)(v->m[k].cur_tgt & 0x00FF);
+        tr[(int64_t)14 * n] = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+        tr[(int64_t)15 * n] = (uint32_t)b[4] | ((uint32_t)b[5] << 8) | ((uint32_t)b[6] << 16) | ((uint32_t)b[7] << 24);
+      }
     }
   }
   if(a->d_cost && a->d_goal) {
@@ -926,6 +931,58 @@ void orc_adt_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *
     }
     if(op != 3)
       for(k = 0; k < RK_AS_WORDS; k++) *soa(state, n, i, k) = w[k];
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Servo feedback (arm side): the CAN rx callbacks of the arm's servos       */
+static int16_t le16(const uint8_t *b) { return (int16_t)((uint16_t)b[0] | ((uint16_t)b[1] << 8)); }
+/* JointMyBldcServo::rx_callback -> rx_summary_status  AD_joint_mybldc_servo.cpp:45-70, frame layout
+ * RES_STATUS_SUMMAY AD_joint_mybldc_servo.hpp:49-60: [0] flags, [1] mode, [2..3] s16_out_ang_deg_Q4, [4] s8_motor_curr_A_Q4 */
+static void adt_bldc_rx(const rk_adt_params_t *p, uint32_t *w, int slot, uint32_t cmdid, const uint8_t f[8], float *cur) {
+  static const int JK[3] = {RK_AJ_DFL, RK_AJ_DFR, RK_AJ_P3};
+  const int        k    = JK[slot];
+  float            now;
+  if(cmdid != 0x1000u) return; /* CMD_ID_RES_STATUS_SUMMARY; every other id is ignored (:49-57) */
+  now = (float)le16(f + 2) / 16.0f / p->gear_ratio[k] * p->motor_dir[k];
+  AJ(w, k, RK_AJ_RAW_NOW) = f2u(now);
+  if(cur) *cur = (float)(int8_t)f[4] / 16.0f * p->motor_dir[k];
+  if(!((w[RK_AS_JFLAGS] >> (4 * k)) & RK_AJF_TORQUE_ON)) AJ(w, k, RK_AJ_RAW_TGT) = f2u(now); /* :69 */
+}
+/* JointMgServo::rx_callback  AD_joint_mg_servo.cpp:75-92; conv_raw_to_current AD_joint_mg_servo.hpp:120-128.
+ * 0x92 (multi-turn angle): the firmware ORs `u8_ang[i] << (i * 8)` for i = 0..6 with the byte promoted to a 32-bit int,
+ * so shifts of 32 and more are undefined in C++.  On the Cortex-M7 a register shift by >= 32 yields 0 and the i = 3
+ * term sign-extends into the 64-bit accumulator: the angle is the sign-extended low 32 bits.  That is what is
+ * restated here; the x86 build of the reference agrees whenever bytes 5..7 of the frame are zero (x86 masks the
+ * shift count to 5 bits instead), which is where tests pin it. */
+static void adt_mg_rx(uint32_t *w, const uint8_t f[8], float *cur) {
+  if(f[0] == 0x92) {
+    const int32_t lo   = (int32_t)((uint32_t)f[1] | ((uint32_t)f[2] << 8) | ((uint32_t)f[3] << 16) | ((uint32_t)f[4] << 24));
+    const int64_t ang  = (int64_t)((uint64_t)(int64_t)lo << 8);
+    const double  DB   = -1.0f / 100.0f / 10.0f / 256.0f; /* DB_ANG_RAW_TO_DEG :17: float arithmetic, then widened */
+    const float   now  = (float)((double)ang * DB);
+    AJ(w, RK_AJ_P1, RK_AJ_RAW_NOW) = f2u(now);
+    if(!((w[RK_AS_JFLAGS] >> (4 * RK_AJ_P1)) & RK_AJF_TORQUE_ON)) AJ(w, RK_AJ_P1, RK_AJ_RAW_TGT) = f2u(now);
+  } else if(f[0] == 0x9C || f[0] == 0xA1) {
+    const double C_A = 0.0000057204, C_B = -0.0000485371, raw = (double)le16(f + 2);
+    double       c;
+    if(raw >= 0) c = C_A * raw * raw + C_B * raw;
+    else c = -(C_A * raw * raw - C_B * raw);
+    if(cur) *cur = -1.0f * (float)c; /* FL_CURR_DIR */
+  }
+}
+void orc_adt_rx_batch(int kind, const rk_adt_params_t *p, uint32_t *state, int64_t n, int64_t i0, int64_t i1, const uint64_t *frames,
+                      const uint32_t *cmdid, float *cur) {
+  int64_t i;
+  int     k;
+  for(i = i0; i < i1; i++) {
+    uint32_t w[RK_AS_WORDS];
+    uint8_t  f[8];
+    for(k = 0; k < RK_AS_WORDS; k++) w[k] = *soa(state, n, i, k);
+    memcpy(f, &frames[i], 8);
+    if(kind == 3) adt_mg_rx(w, f, cur ? &cur[i] : NULL);
+    else adt_bldc_rx(p, w, kind, cmdid ? cmdid[i] : 0x1000u, f, cur ? &cur[i] : NULL);
+    for(k = 0; k < RK_AS_WORDS; k++) *soa(state, n, i, k) = w[k];
   }
 }
 

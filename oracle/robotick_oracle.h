@@ -44,6 +44,10 @@ void orc_adp_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *
 void orc_adh_batch(int op, const rk_adt_params_t *p, uint32_t *state, uint32_t *hstate, int64_t n, int64_t i0, int64_t i1, int K,
                    const float *now, uint32_t *trace);
 
+/* rk_adt_bldc_rx() (kind 0..2) / rk_adt_mg_rx() (kind 3) on HOST arrays */
+void orc_adt_rx_batch(int kind, const rk_adt_params_t *p, uint32_t *state, int64_t n, int64_t i0, int64_t i1, const uint64_t *frames,
+                      const uint32_t *cmdid, float *cur);
+
 /* rk_imt_feed_bytes() on HOST arrays */
 void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0, int64_t i1, int K, int ncells,
                         const uint32_t *cells, const uint16_t *nbytes, uint32_t *out, float *yaw_rad, int do_init);

@@ -183,6 +183,7 @@ def _proto(lib):
     lib.rk_vdt_rollout.argtypes = [C.POINTER(VdtParams), vp, C.c_int64, C.POINTER(VdtRollout), vp]
     lib.rk_vdt_set_power.argtypes = [vp, C.c_int64, vp, vp]
     lib.rk_vdt_set_target_vel.argtypes = [C.POINTER(VdtParams), vp, C.c_int64, vp, vp, vp, vp]
+    lib.rk_vdt_tx_frames.argtypes = [vp, C.c_int64, vp, vp]
     lib.rk_vdt_motor_rx.argtypes = [C.POINTER(VdtParams), vp, C.c_int64, C.c_int, vp, vp, vp]
     lib.rk_imt_state_words.restype = C.c_size_t
     lib.rk_imt_state_bytes.argtypes = [C.c_int64]
@@ -201,6 +202,8 @@ def _proto(lib):
     lib.rk_stream_vehicle_yaw_reg.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
     lib.rk_stream_imu_samples.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp]
     lib.rk_stream_arm_sequences.argtypes = [vp, C.c_int64, vp, vp]
+    lib.rk_adt_bldc_rx.argtypes = [C.POINTER(AdtParams), vp, C.c_int64, C.c_int, vp, vp, vp, vp]
+    lib.rk_adt_mg_rx.argtypes = [C.POINTER(AdtParams), vp, C.c_int64, vp, vp, vp]
     lib.rk_selftest_div_rcp64.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
     lib.rk_tick_debug_timeline.argtypes = [C.c_int, C.POINTER(C.c_float)]
     lib.rk_rmt_default_params.argtypes = [C.POINTER(RmtParams)]
@@ -271,6 +274,7 @@ def _proto(lib):
         getattr(lib, name).argtypes = [vp, f3]
     lib.rk_vdt_get_raw_current.argtypes = [vp, C.POINTER(C.c_int16)]
     lib.rk_vdt_get_angle_sum.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.rk_vdt_get_tx_frame.argtypes = [vp, C.POINTER(C.c_uint8)]
     lib.rk_vdt_get_state.argtypes = [vp, C.POINTER(C.c_uint32)]
     lib.rk_vdt_set_state.argtypes = [vp, C.POINTER(C.c_uint32)]
     return lib

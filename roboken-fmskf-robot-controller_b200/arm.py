@@ -55,6 +55,20 @@ class ArmBatch:
         _cabi.check(self.lib.rk_adt_update(C.byref(self.params), self.state.data_ptr(), self.cmdtab.data_ptr(), self.n, int(K),
                                            None if trace is None else trace.data_ptr(), self._st(stream)))
 
+    def bldc_rx(self, slot, frames, cmdid=None, cur=None, stream=None):
+        """JointMyBldcServo::rx_callback for servo slot 0 DF_Left / 1 DF_Right / 2 P3; frames: int64 [n] device tensor,
+        cmdid: int32 [n] or None (= status summary), cur: float32 [n] or None (receives fl_out_now_cur)."""
+        assert frames.is_cuda and frames.dtype == torch.int64 and frames.numel() == self.n
+        _cabi.check(self.lib.rk_adt_bldc_rx(C.byref(self.params), self.state.data_ptr(), self.n, int(slot), frames.data_ptr(),
+                                            None if cmdid is None else cmdid.data_ptr(), None if cur is None else cur.data_ptr(),
+                                            self._st(stream)))
+
+    def mg_rx(self, frames, cur=None, stream=None):
+        """JointMgServo::rx_callback; frames: int64 [n] device tensor, cur: float32 [n] or None."""
+        assert frames.is_cuda and frames.dtype == torch.int64 and frames.numel() == self.n
+        _cabi.check(self.lib.rk_adt_mg_rx(C.byref(self.params), self.state.data_ptr(), self.n, frames.data_ptr(),
+                                          None if cur is None else cur.data_ptr(), self._st(stream)))
+
     def cmdseq_status(self, ids, stream=None):
         assert ids.is_cuda and ids.element_size() == 4 and ids.numel() == self.n
         out = torch.empty(self.n, dtype=torch.int32, device=self.device)

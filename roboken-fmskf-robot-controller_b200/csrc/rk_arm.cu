@@ -1091,6 +1091,62 @@ static int adt_check(const char *who, const void *a, const void *b, int64_t n) {
   }
   return require_device();
 }
+// ---------------------------------------------------------------------------------------------
+// Servo feedback (arm side): the CAN rx callbacks of the arm's servos, one frame per arm.
+// KIND 0..2: JointMyBldcServo::rx_callback -> rx_summary_status of DF_Left / DF_Right / P3
+//   (AD_joint_mybldc_servo.cpp:45-70; RES_STATUS_SUMMAY AD_joint_mybldc_servo.hpp:49-60: byte 0 flags, 1 mode,
+//   2..3 s16_out_ang_deg_Q4, 4 s8_motor_curr_A_Q4); ids other than CMD_ID_RES_STATUS_SUMMARY are ignored.
+// KIND 3: JointMgServo::rx_callback (AD_joint_mg_servo.cpp:75-92): 0x9C / 0xA1 -> the current through the
+//   double-precision quadratic conv_raw_to_current (AD_joint_mg_servo.hpp:120-128); 0x92 -> the multi-turn angle.
+//   The firmware assembles it as `u64 |= u8_ang[i] << (i * 8)`, i = 0..6, the byte promoted to a 32-bit int: shifts of
+//   32 and more are undefined in C++.  A Cortex-M7 register shift by >= 32 gives 0 and the i = 3 term sign-extends,
+//   so the value is the sign-extended low 32 bits -- restated here.  (The x86 build masks the count to 5 bits; the
+//   two agree whenever bytes 5..7 of the frame are zero, which is where the compiled reference pins this.)
+// The joint's fl_raw_now_deg is stored; fl_raw_tgt_deg follows it while torque is off; fl_out_now_cur, which
+// nothing on the tick reads, goes to the optional cur[] (left untouched by frames that carry no current).
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(128)
+adt_rx_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, int64_t n, const unsigned long long *__restrict__ frames,
+              const uint32_t *__restrict__ cmdid, float *__restrict__ cur) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  constexpr int  k  = KIND == 0 ? RK_AJ_DFL : KIND == 1 ? RK_AJ_DFR : KIND == 2 ? RK_AJ_P3 : RK_AJ_P1;
+  const uint64_t f  = frames[i];
+  const uint32_t lo = (uint32_t)f, hi = (uint32_t)(f >> 32);
+  const int      pl = (RK_AS_JOINT0 + 4 * k) / 4;
+  const bool     on = ((ld_plane(state, n, RK_AS_JFLAGS / 4, i).x >> (4 * k)) & RK_AJF_TORQUE_ON) != 0;
+  bool           have_now = false;
+  float          now      = 0.0f;
+  if(KIND < 3) {
+    if((cmdid ? cmdid[i] : 0x1000u) != 0x1000u) return;
+    now      = fmul(fdiv(fdiv((float)hi16(lo), 16.0f), p.gear_ratio[k]), p.motor_dir[k]);
+    have_now = true;
+    if(cur) cur[i] = fmul(fdiv((float)(int32_t)(int8_t)(hi & 0xFFu), 16.0f), p.motor_dir[k]);
+  } else {
+    const uint32_t cmd = lo & 0xFFu;
+    if(cmd == 0x92u) {
+      const int32_t a32 = (int32_t)((lo >> 8) | (hi << 24)); // bytes 1..4, little-endian
+      const int64_t ang = (int64_t)((uint64_t)(int64_t)a32 << 8);
+      const float   dbf = -1.0f / 100.0f / 10.0f / 256.0f;   // DB_ANG_RAW_TO_DEG: float arithmetic, then widened
+      now      = __double2float_rn(__dmul_rn((double)ang, (double)dbf));
+      have_now = true;
+    } else if(cmd == 0x9Cu || cmd == 0xA1u) {
+      const double C_A = 0.0000057204, C_B = -0.0000485371, raw = (double)hi16(lo); // s16_iq = bytes 2..3
+      double       c;
+      if(raw >= 0) c = __dadd_rn(__dmul_rn(__dmul_rn(C_A, raw), raw), __dmul_rn(C_B, raw));
+      else c = -__dsub_rn(__dmul_rn(__dmul_rn(C_A, raw), raw), __dmul_rn(C_B, raw));
+      if(cur) cur[i] = fmul(-1.0f, __double2float_rn(c));
+    }
+  }
+  if(have_now) {
+    uint4 j = ld_plane(state, n, pl, i);
+    j.w     = f2u(now);
+    if(!on) j.y = f2u(now);
+    st_plane(state, n, pl, i, j);
+  }
+}
+
 static unsigned adt_grid(int64_t n) { return (unsigned)((n + 127) / 128); }
 
 // div_by_rcp64 against div.rn.f32 on `total` pseudo-random (x, c) pairs: all bit patterns of x, c alternately any
@@ -1173,6 +1229,35 @@ int rk::adt_update_launch(const rk_adt_params_t *p, void *d_state, const void *d
 }
 
 extern "C" {
+
+int rk_adt_bldc_rx(const rk_adt_params_t *p, void *d_state, int64_t n, int slot, const uint64_t *d_frames, const uint32_t *d_cmdid,
+                   float *d_cur_A, void *stream) {
+  if(n == 0) return RK_OK;
+  if(!p || !d_frames || slot < 0 || slot > 2 || ((uintptr_t)d_frames & 7u)) {
+    set_error("rk_adt_bldc_rx: params / frames NULL or misaligned, or slot outside 0..2");
+    return RK_ERR_ARG;
+  }
+  if(int rc = adt_check("rk_adt_bldc_rx", d_state, nullptr, n)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const auto  *fr = (const unsigned long long *)d_frames;
+  if(slot == 0) adt_rx_kernel<0><<<adt_grid(n), 128, 0, st>>>(*p, (uint4 *)d_state, n, fr, d_cmdid, d_cur_A);
+  else if(slot == 1) adt_rx_kernel<1><<<adt_grid(n), 128, 0, st>>>(*p, (uint4 *)d_state, n, fr, d_cmdid, d_cur_A);
+  else adt_rx_kernel<2><<<adt_grid(n), 128, 0, st>>>(*p, (uint4 *)d_state, n, fr, d_cmdid, d_cur_A);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
+int rk_adt_mg_rx(const rk_adt_params_t *p, void *d_state, int64_t n, const uint64_t *d_frames, float *d_cur_A, void *stream) {
+  if(n == 0) return RK_OK;
+  if(!p || !d_frames || ((uintptr_t)d_frames & 7u)) {
+    set_error("rk_adt_mg_rx: params / frames NULL or misaligned");
+    return RK_ERR_ARG;
+  }
+  if(int rc = adt_check("rk_adt_mg_rx", d_state, nullptr, n)) return rc;
+  adt_rx_kernel<3><<<adt_grid(n), 128, 0, (cudaStream_t)stream>>>(*p, (uint4 *)d_state, n, (const unsigned long long *)d_frames, nullptr, d_cur_A);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
 
 int rk_adt_cmdseq_status(const void *d_state, const void *d_cmdtab, int64_t n, const uint32_t *d_id, int32_t *d_status, void *stream) {
   if(n == 0) return RK_OK;

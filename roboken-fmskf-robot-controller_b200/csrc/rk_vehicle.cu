@@ -64,6 +64,10 @@ RK_DEV bool yaw_enabled(const rk_vdt_rollout_t &a) {
   return (a.d_yaw != nullptr || a.d_yaw_reg != nullptr || a.d_imu_regs != nullptr) && a.yaw_period > 0 && a.n_yaw > 0;
 }
 
+// CAN_CTRL::tx_routine (VD_can_controller.hpp:43-55): half of the C610 current frame (id 0x200) -- two s16 currents,
+// big-endian, wire order from the low byte of the word
+RK_DEV uint32_t c610_tx_word(int32_t cur_a, int32_t cur_b) { return __byte_perm((uint32_t)cur_a, (uint32_t)cur_b, 0x4501); }
+
 template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(kRolloutThreads)
 vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
@@ -121,7 +125,7 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
 #pragma unroll
       for(int k = 0; k < 4; k++) tr[(int64_t)(9 + k) * n] = (uint32_t)v.m[k].cur_tgt;
       tr[(int64_t)13 * n] = (a.task_period > 0) ? v.move_cnt : 0u;
-      tr[(int64_t)14 * n] = 0u, tr[(int64_t)15 * n] = 0u;
+      tr[(int64_t)14 * n] = c610_tx_word(v.m[0].cur_tgt, v.m[1].cur_tgt), tr[(int64_t)15 * n] = c610_tx_word(v.m[2].cur_tgt, v.m[3].cur_tgt);
     }
   }
   store_veh(state, n, i, v);
@@ -158,7 +162,7 @@ RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, 
 #pragma unroll
   for(int j = 0; j < 3; j++) tr[(int64_t)(3 + j) * n] = f2u(vel[j]), tr[(int64_t)(6 + j) * n] = f2u(tgt[j]);
   tr[9 * n] = (uint32_t)c0, tr[10 * n] = (uint32_t)c1, tr[11 * n] = (uint32_t)c2, tr[12 * n] = (uint32_t)c3;
-  tr[13 * n] = cnt, tr[14 * n] = 0u, tr[15 * n] = 0u;
+  tr[13 * n] = cnt, tr[14 * n] = c610_tx_word(c0, c1), tr[15 * n] = c610_tx_word(c2, c3);
 }
 
 RK_DEV void fast_consts(FastConsts &fc, const rk_vdt_params_t &p, const Derived &d) {
@@ -414,6 +418,16 @@ __global__ void vdt_motor_rx_kernel(const rk_vdt_params_t p, uint4 *state, int64
   load_motor(state, n, i, wheel, m);
   motor_rx(m, p.motor_dir[wheel], frames[i], usec ? (int32_t)usec[i] : 0);
   store_motor(state, n, i, wheel, m);
+}
+
+// CAN_CTRL::tx_routine for every vehicle: the 8-byte C610 frame from the four s16_rawCurr_tgt of the state block
+__global__ void vdt_tx_frames_kernel(const uint4 *state, int64_t n, unsigned long long *frames) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  int32_t c[4];
+#pragma unroll
+  for(int k = 0; k < 4; k++) c[k] = hi16(ld_plane(state, n, RK_VS_MOTOR0 / 4 + 2 * k + 1, i).y); // RK_VM_CUR_TGT: s16_rawCurr_tgt in the high half
+  frames[i] = (unsigned long long)c610_tx_word(c[0], c[1]) | ((unsigned long long)c610_tx_word(c[2], c[3]) << 32);
 }
 
 // single-instance pokes used by the handle API (arguments by value, one thread)
@@ -710,6 +724,19 @@ int rk_vdt_motor_rx(const rk_vdt_params_t *p, void *d_state, int64_t n, int whee
   return RK_OK;
 }
 
+int rk_vdt_tx_frames(const void *d_state, int64_t n, uint64_t *d_frames, void *stream) {
+  if(n <= 0) return RK_OK;
+  if(!d_frames || ((uintptr_t)d_frames & 7u)) {
+    set_error("rk_vdt_tx_frames: d_frames must be a non-NULL 8-byte aligned device pointer");
+    return RK_ERR_ARG;
+  }
+  if(int rc = check_block(d_state, "d_state")) return rc;
+  if(int rc = require_device()) return rc;
+  vdt_tx_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)d_state, n, (unsigned long long *)d_frames);
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+
 // ---- single-instance handle: a batch of one on the same kernels -------------------------
 struct rk_vdt {
   rk_vdt_params_t p;
@@ -828,6 +855,13 @@ int rk_vdt_get_raw_current(rk_vdt_t *h, int16_t out[4]) {
   uint32_t w[RK_VS_WORDS];
   if(int rc = rk_vdt_get_state(h, w)) return rc;
   for(int k = 0; k < 4; k++) out[k] = (int16_t)(w[RK_VS_MOTOR0 + 8 * k + RK_VM_CUR_TGT] >> 16);
+  return RK_OK;
+}
+int rk_vdt_get_tx_frame(rk_vdt_t *h, uint8_t frame[8]) {
+  if(!h || !frame) return RK_ERR_ARG;
+  int16_t c[4];
+  if(int rc = rk_vdt_get_raw_current(h, c)) return rc;
+  for(int k = 0; k < 4; k++) frame[2 * k] = (uint8_t)(c[k] >> 8), frame[2 * k + 1] = (uint8_t)(c[k] & 0x00FF);
   return RK_OK;
 }
 int rk_vdt_get_angle_sum(rk_vdt_t *h, int64_t out[4]) {

@@ -106,6 +106,16 @@ class VehicleBatch:
         _cabi.check(self.lib.rk_vdt_set_target_vel(C.byref(self.params), self.state.data_ptr(), self.n, v.data_ptr(),
                                                    a.data_ptr(), j.data_ptr(), C.c_void_p(st.cuda_stream)))
 
+    def tx_frames(self, out=None):
+        """CAN_CTRL::tx_routine for every vehicle: int64 [n] device tensor of C610 frames (four big-endian s16 currents)."""
+        st = torch.cuda.current_stream(self.dev_index)
+        if out is None:
+            with torch.cuda.device(self.dev_index):
+                out = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        _cabi.check(self.lib.rk_set_device(self.dev_index))
+        _cabi.check(self.lib.rk_vdt_tx_frames(self.state.data_ptr(), self.n, out.data_ptr(), C.c_void_p(st.cuda_stream)))
+        return out
+
     def motor_rx(self, wheel, frames, usec=None):
         """frames: int64 [n] device tensor of 8-byte M2006 frames (MOTOR_IF_M2006::rx_callback)"""
         st = torch.cuda.current_stream(self.dev_index)
@@ -172,6 +182,12 @@ class Vehicle:
         out = (C.c_int16 * 4)()
         _cabi.check(self.lib.rk_vdt_get_raw_current(self.h, out))
         return list(out)
+
+    def tx_routine(self):
+        """CAN_CTRL::tx_routine (VD_can_controller.hpp:43-55): the 8 bytes of the C610 current frame (id 0x200)."""
+        out = (C.c_uint8 * 8)()
+        _cabi.check(self.lib.rk_vdt_get_tx_frame(self.h, out))
+        return bytes(out)
 
     def get_rawAngleSum(self):
         out = (C.c_int64 * 4)()

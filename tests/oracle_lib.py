@@ -51,6 +51,8 @@ def port():
         lib.orc_adt_batch.argtypes = [C.c_int, C.POINTER(_cabi.AdtParams), vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                       vp, vp, vp, vp, vp]
         lib.orc_adt_batch.restype = None
+        lib.orc_adt_rx_batch.argtypes = [C.c_int, C.POINTER(_cabi.AdtParams), vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]
+        lib.orc_adt_rx_batch.restype = None
         lib.orc_adp_batch.argtypes = lib.orc_adt_batch.argtypes
         lib.orc_adp_batch.restype = None
         lib.orc_adh_batch.argtypes = [C.c_int, C.POINTER(_cabi.AdtParams), vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp]
@@ -137,6 +139,8 @@ def ref(name="libref_vdt.so"):
             lib.ref_adt_debug_seq.argtypes = [C.c_int, C.POINTER(_cabi.AdtPosCmdSeq)]
             lib.ref_adt_batch.argtypes = [C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, vp, vp]
             lib.ref_adt_batch.restype = None
+            lib.ref_adt_rx_batch.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]
+            lib.ref_adt_rx_batch.restype = None
             lib.ref_adp_batch.argtypes = lib.ref_adt_batch.argtypes
             lib.ref_adp_batch.restype = None
         _cache[name] = lib
@@ -276,6 +280,18 @@ def arm_batch(kind, op, state, cmdtab, n, K=0, seq=None, valid=None, trace=False
         ref("libref_arm.so").ref_adt_batch(ARM_OPS[op], _ptr(state), _ptr(cmdtab), n, 0, n, K, _ptr(seq), _ptr(valid),
                                            _ptr(tr), _ptr(ids), _ptr(status))
     return tr, status
+
+
+def arm_rx(kind, which, state, n, frames, cmdid=None, cur=None, params=None):
+    """Servo feedback frames through the rx callbacks (rk_adt_bldc_rx: which = 0..2, rk_adt_mg_rx: which = 3) on HOST
+    SoA arrays, port or compiled reference.  frames: uint64 [n]; cmdid: uint32 [n] or None; cur: float32 [n] (in/out) or None."""
+    assert frames.dtype == np.uint64 and frames.shape == (n,)
+    if kind == "port":
+        p = params or _cabi.default_arm_params()
+        port().orc_adt_rx_batch(which, C.byref(p), _ptr(state), n, 0, n, _ptr(frames), _ptr(cmdid), _ptr(cur))
+    else:
+        assert params is None, "the compiled reference has the firmware constants wired in"
+        ref("libref_arm.so").ref_adt_rx_batch(which, _ptr(state), n, 0, n, _ptr(frames), _ptr(cmdid), _ptr(cur))
 
 
 def armpos_batch(kind, op, state, pstate, n, K=0, cmd=None, valid=None, trace=False, ids=None, params=None):

@@ -562,3 +562,30 @@ def test_yaw_from_imu_register_snapshots():
         lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, 0)
     assert_same(tr_t, ptr, "IMU-register yaw, transcription kernel vs port trace")
     assert_same(st_t, pst, "IMU-register yaw, transcription kernel vs port state")
+
+
+def test_c610_tx_frame_words_and_batch_entry():
+    """SURVEY 8f-3, vehicle tx side: the C610 current frame CAN_CTRL::tx_routine() builds (VD_can_controller.hpp:43-55) --
+    trace words 14-15 equal the port's (pinned against the reference's own routine in tests/test_vdt_task_cpu.py), they
+    are the four currents big-endian, and rk_vdt_tx_frames / the handle's tx_routine() give the same bytes from the state."""
+    n, steps = 500, 300
+    inp = wl.plant_inputs(n, steps, seed=88)
+    st, tr = gpu_run(inp)
+    pst, ptr = port_run(inp, nthreads=8)
+    assert_same(tr[:, 14:16, :], ptr[:, 14:16, :], "C610 tx frame words")
+    cur = tr[:, 9:13, :].view(np.int32)
+    by = np.ascontiguousarray(tr[:, 14:16, :].transpose(0, 2, 1)).view(np.uint8).reshape(steps, n, 8)
+    for k in range(4):
+        wire = (by[:, :, 2 * k].astype(np.int32) << 8 | by[:, :, 2 * k + 1]).astype(np.uint16).view(np.int16)
+        np.testing.assert_array_equal(wire, cur[:, k, :].astype(np.int16))
+    assert np.abs(cur).max() > 256  # both bytes are exercised
+    vb = VehicleBatch(n, DEV)
+    vb.load_state_soa(st)
+    fr = vb.tx_frames()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(fr.cpu().numpy().view(np.uint8).reshape(n, 8), by[-1])
+    from roboken_fmskf_robot_controller_b200.vehicle import Vehicle
+
+    v = Vehicle()
+    v.set_state(layout.soa_to_aos(st, n, layout.VS_WORDS)[7])
+    assert v.tx_routine() == bytes(by[-1, 7])
