@@ -1057,40 +1057,7 @@ __global__ void adt_targets_kernel(const uint4 *__restrict__ state, int64_t n, i
 
 } // namespace rk
 
-using namespace rk;
-
-extern "C" {
-
-void rk_adt_default_params(rk_adt_params_t *p) {
-  if(!p) return;
-  // AD_task_main.cpp:38-107 in RK_AJ_* order (Y0, P1, DF_Left, DF_Right, P2, R0, P3)
-  const float gear[RK_AJ_NUM] = {1.0f, 1.0f, 1.0f, 1.0f, 24.0f / 7.0f, 48.0f / 7.0f, 48.0f / 19.0f};
-  const float dir[RK_AJ_NUM]  = {-1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, -1.0f};
-  const float cl[RK_AJ_NUM]   = {3.0f, 0.7f, 0.5f, 0.5f, 1.0f, 1.0f, 0.8f};
-  for(int k = 0; k < RK_AJ_NUM; k++) p->ctrl_time_s[k] = 0.01f, p->gear_ratio[k] = gear[k], p->motor_dir[k] = dir[k], p->curlim_default_A[k] = cl[k];
-  p->cycle_time_s = 0.01f; // AD_task_main.cpp:149
-  const float mech[RK_AJ_NUM] = {-45.0f, 150.0f, 0.0f, 0.0f, 0.0f, 0.0f, -90.0f};
-  const float vin[RK_AJ_NUM]  = {15.0f, 30.0f, 10.0f, 10.0f, 30.0f, 30.0f, -60.0f};
-  const float cin[RK_AJ_NUM]  = {1.0f, 0.15f, 0.5f, 0.5f, 1.0f, 1.0f, 0.5f};
-  const float ipos[RK_AJ_NUM] = {0.0f, 145.0f, 0.0f, 0.0f, -90.0f, 0.0f, 0.0f};
-  for(int k = 0; k < RK_AJ_NUM; k++) p->mechend_pos_deg[k] = mech[k], p->vel_init_degps[k] = vin[k], p->curlim_init_A[k] = cin[k], p->initpos_deg[k] = ipos[k];
-}
-
-size_t rk_adt_state_words(void) { return RK_AS_WORDS; }
-size_t rk_adt_state_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_AS_WORDS * 4u; }
-size_t rk_adt_cmdtab_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_ACMD_WORDS * 4u; }
-
-static int adt_check(const char *who, const void *a, const void *b, int64_t n) {
-  if(n < 0) {
-    set_error("%s: n < 0", who);
-    return RK_ERR_ARG;
-  }
-  if(!a || ((uintptr_t)a & 15u) || ((uintptr_t)b & 15u)) {
-    set_error("%s: blocks must be non-NULL and 16-byte aligned", who);
-    return RK_ERR_ARG;
-  }
-  return require_device();
-}
+namespace rk {
 // ---------------------------------------------------------------------------------------------
 // Servo feedback (arm side): the CAN rx callbacks of the arm's servos, one frame per arm.
 // KIND 0..2: JointMyBldcServo::rx_callback -> rx_summary_status of DF_Left / DF_Right / P3
@@ -1147,6 +1114,42 @@ adt_rx_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, int64_t n, con
   }
 }
 
+} // namespace rk
+
+using namespace rk;
+
+extern "C" {
+
+void rk_adt_default_params(rk_adt_params_t *p) {
+  if(!p) return;
+  // AD_task_main.cpp:38-107 in RK_AJ_* order (Y0, P1, DF_Left, DF_Right, P2, R0, P3)
+  const float gear[RK_AJ_NUM] = {1.0f, 1.0f, 1.0f, 1.0f, 24.0f / 7.0f, 48.0f / 7.0f, 48.0f / 19.0f};
+  const float dir[RK_AJ_NUM]  = {-1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, -1.0f};
+  const float cl[RK_AJ_NUM]   = {3.0f, 0.7f, 0.5f, 0.5f, 1.0f, 1.0f, 0.8f};
+  for(int k = 0; k < RK_AJ_NUM; k++) p->ctrl_time_s[k] = 0.01f, p->gear_ratio[k] = gear[k], p->motor_dir[k] = dir[k], p->curlim_default_A[k] = cl[k];
+  p->cycle_time_s = 0.01f; // AD_task_main.cpp:149
+  const float mech[RK_AJ_NUM] = {-45.0f, 150.0f, 0.0f, 0.0f, 0.0f, 0.0f, -90.0f};
+  const float vin[RK_AJ_NUM]  = {15.0f, 30.0f, 10.0f, 10.0f, 30.0f, 30.0f, -60.0f};
+  const float cin[RK_AJ_NUM]  = {1.0f, 0.15f, 0.5f, 0.5f, 1.0f, 1.0f, 0.5f};
+  const float ipos[RK_AJ_NUM] = {0.0f, 145.0f, 0.0f, 0.0f, -90.0f, 0.0f, 0.0f};
+  for(int k = 0; k < RK_AJ_NUM; k++) p->mechend_pos_deg[k] = mech[k], p->vel_init_degps[k] = vin[k], p->curlim_init_A[k] = cin[k], p->initpos_deg[k] = ipos[k];
+}
+
+size_t rk_adt_state_words(void) { return RK_AS_WORDS; }
+size_t rk_adt_state_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_AS_WORDS * 4u; }
+size_t rk_adt_cmdtab_bytes(int64_t n) { return n < 0 ? 0 : (size_t)n * RK_ACMD_WORDS * 4u; }
+
+static int adt_check(const char *who, const void *a, const void *b, int64_t n) {
+  if(n < 0) {
+    set_error("%s: n < 0", who);
+    return RK_ERR_ARG;
+  }
+  if(!a || ((uintptr_t)a & 15u) || ((uintptr_t)b & 15u)) {
+    set_error("%s: blocks must be non-NULL and 16-byte aligned", who);
+    return RK_ERR_ARG;
+  }
+  return require_device();
+}
 static unsigned adt_grid(int64_t n) { return (unsigned)((n + 127) / 128); }
 
 // div_by_rcp64 against div.rn.f32 on `total` pseudo-random (x, c) pairs: all bit patterns of x, c alternately any
