@@ -518,6 +518,9 @@ int  rk_adt_home_init(rk_adt_t *h, int mode);                     /* set_next_mo
  * as received since the last tick; *completed = ADTModeBase::isCompleted() */
 int  rk_adt_home_tick(rk_adt_t *h, const float servo_now_deg[4], int *completed);
 int  rk_adt_status(rk_adt_t *h, uint32_t id, int32_t *status);    /* get_q_cmdseq_status             */
+/* JointMyBldcServo::rx_callback(cmdid, frame) for slot 0 DF_Left / 1 DF_Right / 2 P3, JointMgServo::rx_callback(frame) for
+ * slot 3 (cmdid unused); *cur_A (optional) receives fl_out_now_cur when the frame carries a current */
+int  rk_adt_rx(rk_adt_t *h, int slot, uint32_t cmdid, const uint8_t frame[8], float *cur_A);
 int  rk_adt_get_targets_deg(rk_adt_t *h, float out[5]);           /* JointBase::get_tgt_deg x5       */
 int  rk_adt_get_state(rk_adt_t *h, uint32_t words[RK_AS_WORDS]);
 int  rk_adt_set_state(rk_adt_t *h, const uint32_t words[RK_AS_WORDS]);

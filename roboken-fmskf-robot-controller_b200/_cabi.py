@@ -218,6 +218,7 @@ def _proto(lib):
     lib.rk_rmt_destroy.restype = None
     lib.rk_rmt_cycle.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(VdtCmd), C.POINTER(C.c_uint32)]
     lib.rk_rmt_get_state.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.rk_adt_rx.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_uint8), C.POINTER(C.c_float)]
     lib.rk_adt_home_init.argtypes = [vp, C.c_int]
     lib.rk_adt_home_tick.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.rk_imt_create.argtypes = [C.POINTER(vp)]

@@ -1377,32 +1377,40 @@ int rk_adh_update(const rk_adt_params_t *p, void *d_state, void *d_hstate, int64
   return RK_OK;
 }
 
+// All blocks of the handle live in ONE mapped pinned allocation (zero-copy): the kernels read / write them over the
+// bus, the host writes inputs and reads results directly -- no cudaMemcpy anywhere; a reader synchronises the stream
+// only if a launch is still in flight.
 struct rk_adt {
   rk_adt_params_t p;
-  uint32_t       *d_state, *d_tab, *d_seq, *d_misc; // d_misc: [0] id, [1] status, [2..6] targets
-  uint32_t       *d_hs;                             // homing mode block (RK_HS_WORDS) + 4 floats of servo feedback
-  uint32_t       *h_stage;                         // pinned, RK_ACMD_SLOT_WORDS words
-  cudaStream_t    st;
+  uint32_t       *h_mem = nullptr;
+  cudaStream_t    st    = nullptr;
+  bool            in_flight = false;
+  uint32_t *state() { return h_mem; }
+  uint32_t *tab() { return h_mem + 80; }                                     // RK_ACMD_WORDS
+  uint32_t *seq() { return h_mem + 80 + RK_ACMD_WORDS; }                     // RK_ACMD_SLOT_WORDS
+  uint32_t *misc() { return h_mem + 80 + RK_ACMD_WORDS + RK_ACMD_SLOT_WORDS; } // [0] id, [1] status, [2..6] targets
+  uint32_t *hs() { return misc() + 8; }                                      // homing block (RK_HS_WORDS) + 4 floats of feedback
+  static size_t words() { return 80 + RK_ACMD_WORDS + RK_ACMD_SLOT_WORDS + 8 + RK_HS_WORDS + 4; }
 };
+static_assert(RK_AS_WORDS <= 80 && (80 + RK_ACMD_WORDS + RK_ACMD_SLOT_WORDS + 8) % 4 == 0, "16-byte aligned sub-blocks");
+static int adt_settle(rk_adt *h) {
+  if(h->in_flight) {
+    RK_CUDA(cudaStreamSynchronize(h->st));
+    h->in_flight = false;
+  }
+  return RK_OK;
+}
 
 int rk_adt_create(rk_adt_t **out, const rk_adt_params_t *p) {
   if(!out) return RK_ERR_ARG;
   *out = nullptr;
   if(int rc = require_device()) return rc;
   rk_adt *h = new rk_adt();
-  memset(h, 0, sizeof(*h));
   if(p) h->p = *p;
   else rk_adt_default_params(&h->p);
-  cudaError_t e = cudaMalloc((void **)&h->d_state, RK_AS_WORDS * 4);
-  if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_tab, RK_ACMD_WORDS * 4);
-  if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_seq, RK_ACMD_SLOT_WORDS * 4);
-  if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_misc, 32);
-  if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_hs, (RK_HS_WORDS + 4) * 4);
-  if(e == cudaSuccess) e = cudaMallocHost((void **)&h->h_stage, RK_ACMD_SLOT_WORDS * 4);
+  cudaError_t e = cudaHostAlloc((void **)&h->h_mem, rk_adt::words() * 4, cudaHostAllocMapped);
+  if(e == cudaSuccess) memset(h->h_mem, 0, rk_adt::words() * 4);
   if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
-  if(e == cudaSuccess) e = cudaMemsetAsync(h->d_state, 0, RK_AS_WORDS * 4, h->st);
-  if(e == cudaSuccess) e = cudaMemsetAsync(h->d_tab, 0, RK_ACMD_WORDS * 4, h->st);
-  if(e == cudaSuccess) e = cudaMemsetAsync(h->d_hs, 0, (RK_HS_WORDS + 4) * 4, h->st);
   if(e != cudaSuccess) {
     int rc = cuda_fail(e, "rk_adt_create");
     rk_adt_destroy(h);
@@ -1417,89 +1425,100 @@ void rk_adt_destroy(rk_adt_t *h) {
     cudaStreamSynchronize(h->st);
     cudaStreamDestroy(h->st);
   }
-  if(h->d_state) cudaFree(h->d_state);
-  if(h->d_tab) cudaFree(h->d_tab);
-  if(h->d_seq) cudaFree(h->d_seq);
-  if(h->d_misc) cudaFree(h->d_misc);
-  if(h->d_hs) cudaFree(h->d_hs);
-  if(h->h_stage) cudaFreeHost(h->h_stage);
+  if(h->h_mem) cudaFreeHost(h->h_mem);
   delete h;
 }
 int rk_adt_init(rk_adt_t *h) {
   if(!h) return RK_ERR_ARG;
-  return rk_adt_mode_init(&h->p, h->d_state, 1, h->st);
+  h->in_flight = true;
+  return rk_adt_mode_init(&h->p, h->state(), 1, h->st);
 }
 int rk_adt_push(rk_adt_t *h, const rk_adt_poscmdseq_t *seq) {
   if(!h || !seq) return RK_ERR_ARG;
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  uint32_t *w = h->h_stage;
+  if(int rc = adt_settle(h)) return rc; // the previous push may still read the image
+  uint32_t *w = h->seq();
   memset(w, 0, RK_ACMD_SLOT_WORDS * 4);
   w[0] = seq->id, w[1] = seq->len;
   for(int k = 0; k < RK_ACMD_MAX_LEN; k++) {
     w[4 + 8 * k] = seq->cmd[k].dt_ms;
     memcpy(&w[4 + 8 * k + 1], seq->cmd[k].tgt_deg, 20);
   }
-  RK_CUDA(cudaMemcpyAsync(h->d_seq, w, RK_ACMD_SLOT_WORDS * 4, cudaMemcpyHostToDevice, h->st));
-  return rk_adt_push_cmdseq(h->d_state, h->d_tab, 1, h->d_seq, nullptr, h->st);
+  h->in_flight = true;
+  return rk_adt_push_cmdseq(h->state(), h->tab(), 1, h->seq(), nullptr, h->st);
 }
 int rk_adt_home_init(rk_adt_t *h, int mode) { // set_next_mode(INIT / INIT_POS_MOVE) -> m_nowProcess->init()
   if(!h) return RK_ERR_ARG;
-  return rk_adh_mode_init(h->d_hs, 1, mode, h->st);
+  h->in_flight = true;
+  return rk_adh_mode_init(h->hs(), 1, mode, h->st);
 }
 int rk_adt_home_tick(rk_adt_t *h, const float servo_now_deg[4], int *completed) {
   if(!h) return RK_ERR_ARG;
-  float *d_now = nullptr;
+  float *now = nullptr;
   if(servo_now_deg) {
-    RK_CUDA(cudaStreamSynchronize(h->st));
-    memcpy(h->h_stage, servo_now_deg, 16);
-    d_now = (float *)(h->d_hs + RK_HS_WORDS);
-    RK_CUDA(cudaMemcpyAsync(d_now, h->h_stage, 16, cudaMemcpyHostToDevice, h->st));
+    if(int rc = adt_settle(h)) return rc;
+    now = (float *)(h->hs() + RK_HS_WORDS);
+    memcpy(now, servo_now_deg, 16);
   }
-  if(int rc = rk_adh_update(&h->p, h->d_state, h->d_hs, 1, 1, d_now, nullptr, h->st)) return rc;
+  h->in_flight = true;
+  if(int rc = rk_adh_update(&h->p, h->state(), h->hs(), 1, 1, now, nullptr, h->st)) return rc;
   if(completed) { // ADTModeBase::isCompleted()
-    RK_CUDA(cudaMemcpyAsync(h->h_stage + 8, h->d_hs, 4, cudaMemcpyDeviceToHost, h->st));
-    RK_CUDA(cudaStreamSynchronize(h->st));
-    *completed = (h->h_stage[8] & RK_AS_FSM_IS_COMP) ? 1 : 0;
+    if(int rc = adt_settle(h)) return rc;
+    *completed = (h->hs()[0] & RK_AS_FSM_IS_COMP) ? 1 : 0;
   }
   return RK_OK;
 }
 int rk_adt_tick(rk_adt_t *h) {
   if(!h) return RK_ERR_ARG;
-  return rk_adt_update(&h->p, h->d_state, h->d_tab, 1, 1, nullptr, h->st);
+  h->in_flight = true;
+  return rk_adt_update(&h->p, h->state(), h->tab(), 1, 1, nullptr, h->st);
 }
 int rk_adt_status(rk_adt_t *h, uint32_t id, int32_t *status) {
   if(!h || !status) return RK_ERR_ARG;
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  h->h_stage[0] = id;
-  RK_CUDA(cudaMemcpyAsync(h->d_misc, h->h_stage, 4, cudaMemcpyHostToDevice, h->st));
-  if(int rc = rk_adt_cmdseq_status(h->d_state, h->d_tab, 1, h->d_misc, (int32_t *)(h->d_misc + 1), h->st)) return rc;
-  RK_CUDA(cudaMemcpyAsync(h->h_stage + 1, h->d_misc + 1, 4, cudaMemcpyDeviceToHost, h->st));
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  *status = (int32_t)h->h_stage[1];
+  if(int rc = adt_settle(h)) return rc;
+  h->misc()[0] = id;
+  h->in_flight = true;
+  if(int rc = rk_adt_cmdseq_status(h->state(), h->tab(), 1, h->misc(), (int32_t *)(h->misc() + 1), h->st)) return rc;
+  if(int rc = adt_settle(h)) return rc;
+  *status = (int32_t)h->misc()[1];
   return RK_OK;
 }
 int rk_adt_get_state(rk_adt_t *h, uint32_t words[RK_AS_WORDS]) {
   if(!h || !words) return RK_ERR_ARG;
-  RK_CUDA(cudaMemcpyAsync(h->h_stage, h->d_state, RK_AS_WORDS * 4, cudaMemcpyDeviceToHost, h->st));
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  memcpy(words, h->h_stage, RK_AS_WORDS * 4);
+  if(int rc = adt_settle(h)) return rc;
+  memcpy(words, h->state(), RK_AS_WORDS * 4);
   return RK_OK;
 }
 int rk_adt_set_state(rk_adt_t *h, const uint32_t words[RK_AS_WORDS]) {
   if(!h || !words) return RK_ERR_ARG;
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  memcpy(h->h_stage, words, RK_AS_WORDS * 4);
-  RK_CUDA(cudaMemcpyAsync(h->d_state, h->h_stage, RK_AS_WORDS * 4, cudaMemcpyHostToDevice, h->st));
-  RK_CUDA(cudaStreamSynchronize(h->st));
+  if(int rc = adt_settle(h)) return rc;
+  memcpy(h->state(), words, RK_AS_WORDS * 4);
   return RK_OK;
 }
 int rk_adt_get_targets_deg(rk_adt_t *h, float out[5]) {
   if(!h || !out) return RK_ERR_ARG;
-  adt_targets_kernel<<<1, 32, 0, h->st>>>((const uint4 *)h->d_state, 1, 0, (float *)(h->d_misc + 2));
+  adt_targets_kernel<<<1, 32, 0, h->st>>>((const uint4 *)h->state(), 1, 0, (float *)(h->misc() + 2));
+  h->in_flight = true;
   RK_CUDA(cudaGetLastError());
-  RK_CUDA(cudaMemcpyAsync(h->h_stage, h->d_misc + 2, 20, cudaMemcpyDeviceToHost, h->st));
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  memcpy(out, h->h_stage, 20);
+  if(int rc = adt_settle(h)) return rc;
+  memcpy(out, h->misc() + 2, 20);
+  return RK_OK;
+}
+/* JointMyBldcServo / JointMgServo::rx_callback on the single instance (see rk_adt_bldc_rx / rk_adt_mg_rx); slot 0..2 =
+ * DF_Left, DF_Right, P3, slot 3 = the MG servo.  *cur_A (optional) receives fl_out_now_cur when the frame carries one. */
+int rk_adt_rx(rk_adt_t *h, int slot, uint32_t cmdid, const uint8_t frame[8], float *cur_A) {
+  if(!h || !frame || slot < 0 || slot > 3) return RK_ERR_ARG;
+  if(int rc = adt_settle(h)) return rc;
+  uint32_t *m = h->misc();
+  memcpy(m + 4, frame, 8); // misc words 4-5: the frame, 6: command id, 7: current (a NaN tag = "not written")
+  m[6] = cmdid, m[7] = 0x7FC12345u;
+  h->in_flight = true;
+  int rc = (slot == 3) ? rk_adt_mg_rx(&h->p, h->state(), 1, (const uint64_t *)(m + 4), (float *)(m + 7), h->st)
+                       : rk_adt_bldc_rx(&h->p, h->state(), 1, slot, (const uint64_t *)(m + 4), m + 6, (float *)(m + 7), h->st);
+  if(rc) return rc;
+  if(cur_A) {
+    if(int rc2 = adt_settle(h)) return rc2;
+    if(m[7] != 0x7FC12345u) memcpy(cur_A, m + 7, 4);
+  }
   return RK_OK;
 }
 }

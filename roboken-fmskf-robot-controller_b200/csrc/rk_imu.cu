@@ -454,26 +454,33 @@ int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32
   return RK_OK;
 }
 
+// The handle's blocks live in ONE mapped pinned allocation (zero-copy): the kernel reads the register snapshot and
+// reads / writes the state over the bus, the host writes inputs and reads the state directly -- no cudaMemcpy anywhere;
+// a getter synchronises the stream only if a launch is still in flight.
 struct rk_imt {
-  uint32_t    *d_state;
-  int16_t     *d_regs;
-  uint8_t     *d_zero; // one zero byte (have_quat = 0)
-  uint32_t    *h_stage; // pinned: RK_IS_WORDS words state + 16 int16
-  cudaStream_t st;
+  uint32_t    *h_mem = nullptr;  // mapped pinned: [0, RK_IS_WORDS) state, then 16 int16 registers, then the have_quat byte
+  cudaStream_t st    = nullptr;
+  bool         in_flight = false;
+  uint32_t *state() { return h_mem; }
+  int16_t  *regs() { return (int16_t *)(h_mem + RK_IS_WORDS); }
+  uint8_t  *flag() { return (uint8_t *)(h_mem + RK_IS_WORDS + 8); }
 };
+static int imt_settle(rk_imt *h) {
+  if(h->in_flight) {
+    RK_CUDA(cudaStreamSynchronize(h->st));
+    h->in_flight = false;
+  }
+  return RK_OK;
+}
 
 int rk_imt_create(rk_imt_t **out) {
   if(!out) return RK_ERR_ARG;
   *out = nullptr;
   if(int rc = require_device()) return rc;
   rk_imt     *h = new rk_imt();
-  cudaError_t e = cudaMalloc((void **)&h->d_state, RK_IS_WORDS * 4);
-  if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_regs, 16 * sizeof(int16_t));
-  if(e == cudaSuccess) e = cudaMalloc((void **)&h->d_zero, 16);
-  if(e == cudaSuccess) e = cudaMemset(h->d_zero, 0, 16);
-  if(e == cudaSuccess) e = cudaMallocHost((void **)&h->h_stage, RK_IS_WORDS * 4 + 64);
+  cudaError_t e = cudaHostAlloc((void **)&h->h_mem, (RK_IS_WORDS + 8 + 4) * 4, cudaHostAllocMapped);
+  if(e == cudaSuccess) memset(h->h_mem, 0, (RK_IS_WORDS + 8 + 4) * 4);
   if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
-  if(e == cudaSuccess) e = cudaMemsetAsync(h->d_state, 0, RK_IS_WORDS * 4, h->st);
   if(e != cudaSuccess) {
     int rc = cuda_fail(e, "rk_imt_create");
     rk_imt_destroy(h);
@@ -488,37 +495,29 @@ void rk_imt_destroy(rk_imt_t *h) {
     cudaStreamSynchronize(h->st);
     cudaStreamDestroy(h->st);
   }
-  if(h->d_state) cudaFree(h->d_state);
-  if(h->d_regs) cudaFree(h->d_regs);
-  if(h->d_zero) cudaFree(h->d_zero);
-  if(h->h_stage) cudaFreeHost(h->h_stage);
+  if(h->h_mem) cudaFreeHost(h->h_mem);
   delete h;
 }
 static int imt_step(rk_imt_t *h, const int16_t regs[16], int have_quat, int do_init) {
   if(!h || !regs) return RK_ERR_ARG;
-  RK_CUDA(cudaStreamSynchronize(h->st)); // staging buffer reuse
-  int16_t *stage = (int16_t *)(h->h_stage + RK_IS_WORDS);
-  memcpy(stage, regs, 32);
-  RK_CUDA(cudaMemcpyAsync(h->d_regs, stage, 32, cudaMemcpyHostToDevice, h->st));
-  // no quaternion frame since the last call: pass a zero have_quat byte (is_error = true)
-  const uint8_t *d_flag = (!have_quat && !do_init) ? h->d_zero : nullptr;
-  return rk_imt_update(h->d_state, 1, 1, h->d_regs, d_flag, nullptr, do_init, h->st);
+  if(int rc = imt_settle(h)) return rc; // the previous launch may still read the snapshot
+  memcpy(h->regs(), regs, 32);
+  *h->flag() = (uint8_t)((have_quat || do_init) ? 1 : 0); // no quaternion frame since the last call: is_error = true
+  h->in_flight = true;
+  return rk_imt_update(h->state(), 1, 1, h->regs(), h->flag(), nullptr, do_init, h->st);
 }
 int rk_imt_init(rk_imt_t *h, const int16_t regs[RK_IMT_REGS]) { return imt_step(h, regs, 1, 1); }
 int rk_imt_update1(rk_imt_t *h, const int16_t regs[RK_IMT_REGS], int have_quat) { return imt_step(h, regs, have_quat, 0); }
 int rk_imt_get_state(rk_imt_t *h, uint32_t words[RK_IS_WORDS]) {
   if(!h || !words) return RK_ERR_ARG;
-  RK_CUDA(cudaMemcpyAsync(h->h_stage, h->d_state, RK_IS_WORDS * 4, cudaMemcpyDeviceToHost, h->st));
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  memcpy(words, h->h_stage, RK_IS_WORDS * 4);
+  if(int rc = imt_settle(h)) return rc;
+  memcpy(words, h->state(), RK_IS_WORDS * 4);
   return RK_OK;
 }
 int rk_imt_set_state(rk_imt_t *h, const uint32_t words[RK_IS_WORDS]) {
   if(!h || !words) return RK_ERR_ARG;
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  memcpy(h->h_stage, words, RK_IS_WORDS * 4);
-  RK_CUDA(cudaMemcpyAsync(h->d_state, h->h_stage, RK_IS_WORDS * 4, cudaMemcpyHostToDevice, h->st));
-  RK_CUDA(cudaStreamSynchronize(h->st));
+  if(int rc = imt_settle(h)) return rc;
+  memcpy(h->state(), words, RK_IS_WORDS * 4);
   return RK_OK;
 }
 int rk_imt_get(rk_imt_t *h, float data[16], int *is_error) {

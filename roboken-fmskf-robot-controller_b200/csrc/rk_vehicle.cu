@@ -443,13 +443,6 @@ __global__ void vdt_set_target1_kernel(uint4 *state, float v0, float v1, float v
     store_interp(state, 1, 0, k, t);
   }
 }
-__global__ void vdt_rx1_kernel(const rk_vdt_params_t p, uint4 *state, int wheel, unsigned long long frame, int usec) {
-  Motor m;
-  load_motor(state, 1, 0, wheel, m);
-  motor_rx(m, p.motor_dir[wheel], frame, usec);
-  store_motor(state, 1, 0, wheel, m);
-}
-
 // -----------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------
@@ -737,13 +730,74 @@ int rk_vdt_tx_frames(const void *d_state, int64_t n, uint64_t *d_frames, void *s
   return RK_OK;
 }
 
-// ---- single-instance handle: a batch of one on the same kernels -------------------------
+// ---- single-instance handle: the drop-in for the static objects of VD_task_main.cpp:75-108 -------------
+// The state block lives in MAPPED PINNED host memory (zero-copy): the one-thread kernels read and write it over the
+// bus, the getters read it from the host side -- no device-to-host copy anywhere.  A 1 kHz firmware tick is
+//   rx_callback x4, set_now_yaw_world   -> kept on the host side of the handle (no launch),
+//   update()                            -> ONE launch that applies them in arrival order and runs the tick,
+//   get_rawCurr_tgt x4 / tx_routine     -> ONE stream synchronisation, then plain loads from the mirror.
 struct rk_vdt {
   rk_vdt_params_t p;
-  uint32_t       *d_state; // RK_VS_WORDS words, n = 1
-  uint32_t       *h_stage; // pinned
-  cudaStream_t    st;
+  uint32_t       *h_state = nullptr; // mapped pinned; the kernels use the same address (UVA)
+  cudaStream_t    st      = nullptr;
+  bool            in_flight = false; // a launch since the last synchronisation
+  // calls not yet handed to the device
+  uint32_t rx_mask = 0;
+  uint64_t rx_frame[4] = {0, 0, 0, 0};
+  int32_t  rx_usec[4]  = {0, 0, 0, 0};
+  bool     has_yaw = false;
+  float    yaw     = 0.0f;
 };
+
+} // extern "C"
+namespace rk {
+struct Tick1Args {
+  uint32_t           rx_mask;
+  unsigned long long frame[4];
+  int32_t            usec[4];
+  int32_t            has_yaw;
+  float              yaw;
+  int32_t            do_update;
+};
+// pending rx_callback()s (VD_motor_if_m2006.cpp:32-72), set_now_yaw_world() (VD_vehicle_controller.hpp:57) and, if asked,
+// VEHICLE_CTRL::update() (VD_vehicle_controller.cpp:6-99) on the single instance
+__global__ void vdt_tick1_kernel(const rk_vdt_params_t p, uint4 *state, const Tick1Args a) {
+  Veh v;
+  load_veh(state, 1, 0, v);
+#pragma unroll
+  for(int k = 0; k < 4; k++)
+    if(a.rx_mask & (1u << k)) motor_rx(v.m[k], p.motor_dir[k], a.frame[k], a.usec[k]);
+  if(a.has_yaw) v.pos[2] = a.yaw;
+  if(a.do_update) {
+    const Derived d = derive(p);
+    float         c, s;
+    yaw_trig(g_sin_table, v.pos[2], c, s);
+    veh_update(v, p, d, c, s);
+  }
+  store_veh(state, 1, 0, v);
+}
+static int vdt_flush(rk_vdt *h, bool do_update) {
+  if(!do_update && !h->rx_mask && !h->has_yaw) return RK_OK;
+  Tick1Args a;
+  a.rx_mask = h->rx_mask;
+  for(int k = 0; k < 4; k++) a.frame[k] = h->rx_frame[k], a.usec[k] = h->rx_usec[k];
+  a.has_yaw = h->has_yaw ? 1 : 0, a.yaw = h->yaw, a.do_update = do_update ? 1 : 0;
+  vdt_tick1_kernel<<<1, 1, 0, h->st>>>(h->p, (uint4 *)h->h_state, a);
+  h->rx_mask = 0, h->has_yaw = false, h->in_flight = true;
+  RK_CUDA(cudaGetLastError());
+  return RK_OK;
+}
+// everything handed to the device has finished: the mirror is current
+static int vdt_settle(rk_vdt *h) {
+  if(int rc = vdt_flush(h, false)) return rc;
+  if(h->in_flight) {
+    RK_CUDA(cudaStreamSynchronize(h->st));
+    h->in_flight = false;
+  }
+  return RK_OK;
+}
+} // namespace rk
+extern "C" {
 
 int rk_vdt_create(rk_vdt_t **out, const rk_vdt_params_t *p) {
   if(!out) {
@@ -757,10 +811,9 @@ int rk_vdt_create(rk_vdt_t **out, const rk_vdt_params_t *p) {
     h->p = *p;
   else
     rk_vdt_default_params(&h->p);
-  cudaError_t e = cudaMalloc((void **)&h->d_state, RK_VS_WORDS * 4);
-  if(e == cudaSuccess) e = cudaMallocHost((void **)&h->h_stage, RK_VS_WORDS * 4);
+  cudaError_t e = cudaHostAlloc((void **)&h->h_state, RK_VS_WORDS * 4, cudaHostAllocMapped);
+  if(e == cudaSuccess) memset(h->h_state, 0, RK_VS_WORDS * 4); // power-on = zero-initialised statics
   if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
-  if(e == cudaSuccess) e = cudaMemsetAsync(h->d_state, 0, RK_VS_WORDS * 4, h->st); // power-on = zero-initialised statics
   if(e != cudaSuccess) {
     int rc = cuda_fail(e, "rk_vdt_create");
     rk_vdt_destroy(h);
@@ -776,29 +829,28 @@ void rk_vdt_destroy(rk_vdt_t *h) {
     cudaStreamSynchronize(h->st);
     cudaStreamDestroy(h->st);
   }
-  if(h->d_state) cudaFree(h->d_state);
-  if(h->h_stage) cudaFreeHost(h->h_stage);
+  if(h->h_state) cudaFreeHost(h->h_state);
   delete h;
 }
 
 int rk_vdt_update(rk_vdt_t *h) {
   if(!h) return RK_ERR_ARG;
-  rk_vdt_rollout_t a;
-  memset(&a, 0, sizeof(a));
-  a.steps       = 1;
-  a.sensor_mode = RK_SENSOR_HOLD;
-  return rk_vdt_rollout(&h->p, h->d_state, 1, &a, h->st);
+  return vdt_flush(h, true);
 }
 
 static int poke(rk_vdt_t *h, int word, uint32_t val) {
-  vdt_poke_word_kernel<<<1, 1, 0, h->st>>>(h->d_state, (int64_t)word, val); // n = 1: SoA index == word
+  if(int rc = vdt_flush(h, false)) return rc;
+  vdt_poke_word_kernel<<<1, 1, 0, h->st>>>(h->h_state, (int64_t)word, val); // n = 1: SoA index == word
+  h->in_flight = true;
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
 
 int rk_vdt_start(rk_vdt_t *h) {
   if(!h) return RK_ERR_ARG;
-  return rk_vdt_set_power(h->d_state, 1, nullptr, h->st);
+  if(int rc = vdt_flush(h, false)) return rc;
+  h->in_flight = true;
+  return rk_vdt_set_power(h->h_state, 1, nullptr, h->st);
 }
 int rk_vdt_stop(rk_vdt_t *h) {
   if(!h) return RK_ERR_ARG;
@@ -807,44 +859,42 @@ int rk_vdt_stop(rk_vdt_t *h) {
 }
 int rk_vdt_set_target(rk_vdt_t *h, const float v[3], const float a[3], const float j[3]) {
   if(!h || !v || !a || !j) return RK_ERR_ARG;
-  vdt_set_target1_kernel<<<1, 1, 0, h->st>>>((uint4 *)h->d_state, v[0], v[1], v[2], a[0], a[1], a[2], j[0], j[1], j[2]);
+  if(int rc = vdt_flush(h, false)) return rc;
+  vdt_set_target1_kernel<<<1, 1, 0, h->st>>>((uint4 *)h->h_state, v[0], v[1], v[2], a[0], a[1], a[2], j[0], j[1], j[2]);
+  h->in_flight = true;
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
 int rk_vdt_set_yaw(rk_vdt_t *h, float yaw_rad) {
   if(!h) return RK_ERR_ARG;
-  uint32_t u;
-  memcpy(&u, &yaw_rad, 4);
-  return poke(h, RK_VS_POS_TH, u);
+  h->has_yaw = true, h->yaw = yaw_rad; // rides with the next launch
+  return RK_OK;
 }
 int rk_vdt_rx(rk_vdt_t *h, int wheel, const uint8_t frame[8], int16_t usec_id) {
   if(!h || !frame || wheel < 0 || wheel > 3) return RK_ERR_ARG;
-  unsigned long long f;
-  memcpy(&f, frame, 8);
-  vdt_rx1_kernel<<<1, 1, 0, h->st>>>(h->p, (uint4 *)h->d_state, wheel, f, (int)usec_id);
-  RK_CUDA(cudaGetLastError());
+  if(h->rx_mask & (1u << wheel)) // a second frame for the same wheel before the tick: keep the arrival order
+    if(int rc = vdt_flush(h, false)) return rc;
+  memcpy(&h->rx_frame[wheel], frame, 8);
+  h->rx_usec[wheel] = (int32_t)usec_id;
+  h->rx_mask |= 1u << wheel;
   return RK_OK;
 }
 
 int rk_vdt_get_state(rk_vdt_t *h, uint32_t words[RK_VS_WORDS]) {
   if(!h || !words) return RK_ERR_ARG;
-  RK_CUDA(cudaMemcpyAsync(h->h_stage, h->d_state, RK_VS_WORDS * 4, cudaMemcpyDeviceToHost, h->st));
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  memcpy(words, h->h_stage, RK_VS_WORDS * 4); // n = 1: SoA == AoS
+  if(int rc = vdt_settle(h)) return rc;
+  memcpy(words, h->h_state, RK_VS_WORDS * 4); // n = 1: SoA == AoS
   return RK_OK;
 }
 int rk_vdt_set_state(rk_vdt_t *h, const uint32_t words[RK_VS_WORDS]) {
   if(!h || !words) return RK_ERR_ARG;
-  RK_CUDA(cudaStreamSynchronize(h->st));
-  memcpy(h->h_stage, words, RK_VS_WORDS * 4);
-  RK_CUDA(cudaMemcpyAsync(h->d_state, h->h_stage, RK_VS_WORDS * 4, cudaMemcpyHostToDevice, h->st));
-  RK_CUDA(cudaStreamSynchronize(h->st));
+  if(int rc = vdt_settle(h)) return rc;
+  memcpy(h->h_state, words, RK_VS_WORDS * 4);
   return RK_OK;
 }
 static int get3(rk_vdt_t *h, int word0, float out[3]) {
-  uint32_t w[RK_VS_WORDS];
-  if(int rc = rk_vdt_get_state(h, w)) return rc;
-  memcpy(out, &w[word0], 12);
+  if(int rc = vdt_settle(h)) return rc;
+  memcpy(out, &h->h_state[word0], 12);
   return RK_OK;
 }
 int rk_vdt_get_pos(rk_vdt_t *h, float out[3]) { return (h && out) ? get3(h, RK_VS_POS_X, out) : RK_ERR_ARG; }
@@ -852,9 +902,8 @@ int rk_vdt_get_vel(rk_vdt_t *h, float out[3]) { return (h && out) ? get3(h, RK_V
 int rk_vdt_get_vel_tgt(rk_vdt_t *h, float out[3]) { return (h && out) ? get3(h, RK_VS_TGT_X, out) : RK_ERR_ARG; }
 int rk_vdt_get_raw_current(rk_vdt_t *h, int16_t out[4]) {
   if(!h || !out) return RK_ERR_ARG;
-  uint32_t w[RK_VS_WORDS];
-  if(int rc = rk_vdt_get_state(h, w)) return rc;
-  for(int k = 0; k < 4; k++) out[k] = (int16_t)(w[RK_VS_MOTOR0 + 8 * k + RK_VM_CUR_TGT] >> 16);
+  if(int rc = vdt_settle(h)) return rc;
+  for(int k = 0; k < 4; k++) out[k] = (int16_t)(h->h_state[RK_VS_MOTOR0 + 8 * k + RK_VM_CUR_TGT] >> 16);
   return RK_OK;
 }
 int rk_vdt_get_tx_frame(rk_vdt_t *h, uint8_t frame[8]) {
@@ -866,10 +915,9 @@ int rk_vdt_get_tx_frame(rk_vdt_t *h, uint8_t frame[8]) {
 }
 int rk_vdt_get_angle_sum(rk_vdt_t *h, int64_t out[4]) {
   if(!h || !out) return RK_ERR_ARG;
-  uint32_t w[RK_VS_WORDS];
-  if(int rc = rk_vdt_get_state(h, w)) return rc;
+  if(int rc = vdt_settle(h)) return rc;
   for(int k = 0; k < 4; k++) {
-    const uint32_t *q = &w[RK_VS_MOTOR0 + 8 * k];
+    const uint32_t *q = &h->h_state[RK_VS_MOTOR0 + 8 * k];
     out[k]            = (int64_t)(((uint64_t)q[RK_VM_SUM_HI] << 32) | q[RK_VM_SUM_LO]);
   }
   return RK_OK;
