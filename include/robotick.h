@@ -68,6 +68,10 @@ int rk_set_option(int option, int value);
  * parameters on the current device (csrc/rk_exact.cu), 0 if not, < 0 on error. */
 struct rk_vdt_params;
 int rk_vdt_fast_path_proven(const struct rk_vdt_params *p);
+/* Runs those proofs now (about 12 ms, once per parameter set and device; results are cached) instead of inside the
+ * first rk_vdt_rollout with these parameters.  The proofs allocate and synchronise on a private stream: call this
+ * before capturing rollouts into a CUDA graph or from latency-sensitive code. */
+int rk_vdt_prepare(const struct rk_vdt_params *p);
 /* Roofline probe (bench.py): launches a dense FP32 kernel on `stream` -- FFMA chains when
  * fused != 0, alternating FMUL/FADD otherwise -- and reports its flop count; the caller
  * times it with CUDA events.  d_out: >= 4 bytes of device memory. */
@@ -305,10 +309,12 @@ int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs
  * wire, then asks for a quaternion frame).  Parser block per IMU (3 planes): */
 enum {
   RK_IP_WINDOW = 0, /* s_ucWitDataBuff[0..10] packed little-endian in words 0-2; byte 11 = s_uiWitDataCnt */
-  RK_IP_FLAGS  = 3, /* bit 0: QUAT_UPDATE pending; bits 8-15: s_uiReadRegIndex (0, or q0 = 0x51 after init()) */
+  RK_IP_FLAGS  = 3, /* bit 0: QUAT_UPDATE pending; bits 8-15: s_uiReadRegIndex (0, or q0 = 0x51 after init());
+                     * bit 16 (RK_IP_FLAG_INIT_PENDING): init() is still waiting for its first quaternion frame */
   RK_IP_SREG   = 4, /* sReg[AX..Yaw], sReg[q0..q3]: 16 x int16 in RK_IMT_REG_* order, two per word */
   RK_IP_WORDS  = 12
 };
+#define RK_IP_FLAG_INIT_PENDING 0x10000u
 size_t rk_imt_parser_words(void);
 size_t rk_imt_parser_bytes(int64_t n);
 /* K updates, each preceded by the serial bytes that arrived since the last one.  The wire is laid out like every
@@ -316,7 +322,10 @@ size_t rk_imt_parser_bytes(int64_t n);
  * first word up) of update u, IMU i at cell index (u*ncells + c)*n + i.  d_nbytes (NULL: every slot is full) gives
  * the number of bytes really on the wire in update u of IMU i, at [u*n + i], clamped to 16*ncells -- an idle line
  * is 0 bytes, not zeros.  do_init: the first update is IMU_IF_WT901C::init() (:63-77; WitInit empties the window,
- * WitReadReg(q0, 4) arms the read index; its bytes must contain a quaternion frame -- the firmware spins until one
+ * WitReadReg(q0, 4) arms the read index; the firmware then spins in getDataImmediately() until a quaternion frame has
+ * arrived: update slots without one are part of that wait -- nothing is published, q_init is not latched, the pending
+ * state is carried in the parser block across slots and launches -- and the slot that brings one completes init().
+ * (the text below describes the common case of a frame inside update 0: its bytes contain a quaternion frame -- the firmware spins until one
  * arrives).  d_out / d_yaw_rad as rk_imt_update_yaw. */
 int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32_t ncells, const void *d_cells,
                       const uint16_t *d_nbytes, float *d_out, float *d_yaw_rad, int do_init, void *stream);

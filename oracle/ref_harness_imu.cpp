@@ -22,7 +22,34 @@ extern "C" {
 
 HardwareSerial Serial6;
 HardwareSerial Serial7;
-uint32_t       get_gptimer_cnt() { return 0; }
+/* isComComp() reads the timer on entry (imu_if_wt901c.cpp:133).  While init() spins in getDataImmediately() waiting for
+ * its first quaternion frame, that read is where the harness lets time pass: with the UART drained, the bytes of the next
+ * update slot "arrive" (see ref_imt_bytes_rollout).  A stream that ends before the frame would spin forever: thrown out. */
+namespace {
+struct InitFeed {
+  bool            active = false;
+  const uint32_t *cells  = nullptr;
+  const uint16_t *nbytes = nullptr;
+  int64_t         n = 0, i = 0;
+  int             K = 0, ncells = 0, next_u = 0;
+} g_feed;
+struct InitStarved {};
+void feed_slot(int u) {
+  int nb = 16 * g_feed.ncells;
+  if(g_feed.nbytes && g_feed.nbytes[(int64_t)u * g_feed.n + g_feed.i] < nb) nb = g_feed.nbytes[(int64_t)u * g_feed.n + g_feed.i];
+  for(int c = 0; 16 * c < nb; c++) {
+    const uint32_t *cell = g_feed.cells + (((int64_t)u * g_feed.ncells + c) * g_feed.n + g_feed.i) * 4;
+    Serial6.feed((const uint8_t *)cell, nb - 16 * c < 16 ? nb - 16 * c : 16);
+  }
+}
+} // namespace
+uint32_t get_gptimer_cnt() {
+  if(g_feed.active && Serial6.available() == 0) {
+    if(g_feed.next_u >= g_feed.K) throw InitStarved();
+    feed_slot(g_feed.next_u++);
+  }
+  return 0;
+}
 namespace DEBUG {
 char EXT_PRINT_BUF[1024];
 void print(char *, uint32_t) {}
@@ -174,21 +201,33 @@ void ref_imt_bytes_rollout(uint32_t *state, int64_t n, int64_t i0, int64_t i1, i
   for(int64_t i = i0; i < i1; i++) {
     memset(sReg, 0, sizeof(int16_t) * REGSIZE);
     IMU_IF_WT901C *m = make();
-    for(int u = 0; u < K; u++) {
-      int nb = 16 * ncells;
-      if(nbytes && nbytes[(int64_t)u * n + i] < nb) nb = nbytes[(int64_t)u * n + i];
-      for(int c = 0; 16 * c < nb; c++) {
-        const uint32_t *cell = cells + (((int64_t)u * ncells + c) * n + i) * 4;
-        Serial6.feed((const uint8_t *)cell, nb - 16 * c < 16 ? nb - 16 * c : 16);
+    g_feed.cells = cells, g_feed.nbytes = nbytes, g_feed.n = n, g_feed.i = i, g_feed.K = K, g_feed.ncells = ncells;
+    auto publish = [&](int u) {
+      if(!out) return;
+      IMT::IMU_IF::Data d;
+      m->getDataLatest(d);
+      const uint32_t *dw = (const uint32_t *)&d;
+      for(int k = 0; k < 16; k++) out[(((int64_t)u * 4 + k / 4) * n + i) * 4 + (k % 4)] = dw[k];
+    };
+    int u = 0;
+    if(K > 0) { /* update slot 0 is init(); it takes as many further slots as its wait for a quaternion frame needs */
+      for(int v = 0; v < K; v++) publish(v); /* slots swallowed by the wait publish nothing new: the power-on page */
+      feed_slot(0);
+      g_feed.next_u = 1, g_feed.active = true;
+      bool done = true;
+      try {
+        m->init();
+      } catch(const InitStarved &) {
+        done = false; /* the stream ended inside the wait */
       }
-      if(u == 0) m->init();
-      else m->update();
-      if(out) {
-        IMT::IMU_IF::Data d;
-        m->getDataLatest(d);
-        const uint32_t *dw = (const uint32_t *)&d;
-        for(int k = 0; k < 16; k++) out[(((int64_t)u * 4 + k / 4) * n + i) * 4 + (k % 4)] = dw[k];
-      }
+      g_feed.active = false;
+      u = g_feed.next_u;
+      if(done) publish(u - 1);
+    }
+    for(; u < K; u++) {
+      feed_slot(u);
+      m->update();
+      publish(u);
     }
     if(state) {
       uint32_t w[RK_IS_WORDS];

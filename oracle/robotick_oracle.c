@@ -1358,7 +1358,7 @@ void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0
       int init = do_init && u == 0;
       if(init) { /* WitInit: s_uiWitDataCnt = 0 ; WitReadReg(q0, 4): s_uiReadRegIndex = q0 */
         w.cnt   = 0;
-        w.flags = (w.flags & ~0xFF00u) | (0x51u << 8);
+        w.flags = (w.flags & ~0xFF00u) | (0x51u << 8) | RK_IP_FLAG_INIT_PENDING;
       }
       {
         int nb = 16 * ncells;
@@ -1371,9 +1371,15 @@ void orc_imt_feed_bytes(uint32_t *state, uint32_t *parser, int64_t n, int64_t i0
       {
         int hq = (w.flags & 1u) != 0;
         if(hq) w.flags &= ~0xFFu; /* s_cDataUpdate = 0 */
-        if(init) {              /* getDataImmediately: (spins until a quaternion frame) updateData; latch q_init */
-          imu_update_data(qi, w.reg, d);
-          for(k = 0; k < 4; k++) qi[k] = w.reg[RK_IMT_REG_Q0 + k] / 32768.0f;
+        if(w.flags & RK_IP_FLAG_INIT_PENDING) {
+          /* init() -> getDataImmediately (imu_if_wt901c.cpp:63-77,149-158) spins in isComComp() until a quaternion frame
+           * has arrived: an update slot without one is still part of that wait (nothing is published); the slot that
+           * brings it completes init: updateData, q_init latched */
+          if(hq) {
+            imu_update_data(qi, w.reg, d);
+            for(k = 0; k < 4; k++) qi[k] = w.reg[RK_IMT_REG_Q0 + k] / 32768.0f;
+            w.flags &= ~RK_IP_FLAG_INIT_PENDING;
+          }
         } else if(hq) {
           flags &= ~RK_IS_FLAG_ERROR;
           imu_update_data(qi, w.reg, d);

@@ -174,6 +174,7 @@ def _proto(lib):
     lib.rk_set_device.argtypes = [C.c_int]
     lib.rk_set_option.argtypes = [C.c_int, C.c_int]
     lib.rk_vdt_fast_path_proven.argtypes = [C.POINTER(VdtParams)]
+    lib.rk_vdt_prepare.argtypes = [C.POINTER(VdtParams)]
     lib.rk_probe_fp32.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_double), vp]
     lib.rk_vdt_default_params.argtypes = [C.POINTER(VdtParams)]
     lib.rk_vdt_default_params.restype = None

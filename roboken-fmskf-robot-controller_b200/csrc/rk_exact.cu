@@ -60,12 +60,17 @@ __global__ void proof_small_kernel(ProofOut *out) {
   }
 }
 
-struct ProofCache {
-  bool  valid = false, ok = false;
-  float r = 0, s2 = 0, l = 0;
-  int   device = -1;
+// Proof results are cached per (device, radius, sqrt2, L): alternating parameter sets or several GPUs in one process
+// prove each combination once.  The proofs run on a private non-blocking stream (never the legacy default stream), so
+// a first use inside rk_vdt_rollout synchronises with that stream only; rk_vdt_prepare() runs them ahead of time
+// (required before a rollout is captured into a CUDA graph: the proof allocates and synchronises).
+struct ProofEntry {
+  int   device;
+  float r, s2, l;
+  bool  ok;
 };
-static ProofCache g_proof;
+static ProofEntry g_proofs[32];
+static int        g_n_proofs = 0;
 static std::mutex g_proof_mu;
 
 // true iff the fast path may be used with these divisors on the current device
@@ -73,34 +78,47 @@ bool fast_path_proven(const rk_vdt_params_t &p) {
   std::lock_guard<std::mutex> lk(g_proof_mu);
   int dev = -1;
   if(cudaGetDevice(&dev) != cudaSuccess) return false;
-  if(g_proof.valid && g_proof.device == dev && g_proof.r == p.wheel_radius_mm && g_proof.s2 == p.sqrtf2 &&
-     g_proof.l == p.wheel_l_mm)
-    return g_proof.ok;
-  g_proof.valid = true, g_proof.ok = false, g_proof.device = dev;
-  g_proof.r = p.wheel_radius_mm, g_proof.s2 = p.sqrtf2, g_proof.l = p.wheel_l_mm;
-  if(!(p.wheel_radius_mm > 0.0f) || !(p.sqrtf2 > 0.0f) || !(p.wheel_l_mm > 0.0f)) return false;
-  ProofOut *d_out = nullptr, h[4];
-  if(cudaMalloc((void **)&d_out, 4 * sizeof(ProofOut)) != cudaSuccess) {
+  for(int k = 0; k < g_n_proofs; k++) {
+    const ProofEntry &e = g_proofs[k];
+    if(e.device == dev && e.r == p.wheel_radius_mm && e.s2 == p.sqrtf2 && e.l == p.wheel_l_mm) return e.ok;
+  }
+  ProofEntry ne = {dev, p.wheel_radius_mm, p.sqrtf2, p.wheel_l_mm, false};
+  auto       remember = [&](bool ok) {
+    ne.ok = ok;
+    if(g_n_proofs < 32) g_proofs[g_n_proofs++] = ne;
+    else g_proofs[31] = ne; // a 33rd combination: the last slot is recycled
+    return ok;
+  };
+  if(!(p.wheel_radius_mm > 0.0f) || !(p.sqrtf2 > 0.0f) || !(p.wheel_l_mm > 0.0f)) return remember(false);
+  cudaStream_t st = nullptr;
+  if(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
+  ProofOut *d_out = nullptr, h[4];
+  if(cudaMalloc((void **)&d_out, 4 * sizeof(ProofOut)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaStreamDestroy(st);
+    return false;
+  }
   for(int k = 0; k < 4; k++) h[k] = ProofOut{0u, 0u, 0u, 0u, 0u};
-  cudaMemcpy(d_out, h, sizeof(h), cudaMemcpyHostToDevice);
+  cudaMemcpyAsync(d_out, h, sizeof(h), cudaMemcpyHostToDevice, st);
   const float cs[3] = {p.wheel_radius_mm, p.sqrtf2, p.wheel_l_mm};
-  for(int k = 0; k < 3; k++) proof_div_kernel<<<148 * 16, 256>>>(cs[k], d_out + k);
-  proof_small_kernel<<<1025, 256>>>(d_out + 3);
-  cudaError_t e = cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost); // synchronises
+  for(int k = 0; k < 3; k++) proof_div_kernel<<<148 * 16, 256, 0, st>>>(cs[k], d_out + k);
+  proof_small_kernel<<<1025, 256, 0, st>>>(d_out + 3);
+  cudaError_t e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if(e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d_out);
+  cudaStreamDestroy(st);
   if(e != cudaSuccess) {
     cudaGetLastError();
-    return false;
+    return false; // not cached: a transient failure must not disable the fast path for good
   }
   bool ok = true;
   ok &= (h[0].div_fail_any == 0u);                                   // radius: every finite float
   for(int k = 1; k < 3; k++) ok &= (h[k].div_fail_outside == 0u);    // sqrt2, L: 0 and |x| >= 2^-40
   ok &= (h[3].mrad_fail == 0u) && (h[3].dang_fail == 0u);
-  g_proof.ok = ok;
-  return ok;
+  return remember(ok);
 }
 
 // Exhaustive check of div_const(x, c, RN(1/c)) == x / c (bit for bit) over every finite float x on
@@ -125,9 +143,17 @@ int div_const_exact(float c) {
     cudaGetLastError();
     return 0;
   }
-  cudaMemcpy(d_out, &h, sizeof(h), cudaMemcpyHostToDevice);
-  proof_div_kernel<<<148 * 16, 256>>>(c, d_out);
-  cudaError_t e = cudaMemcpy(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaStream_t st = nullptr;
+  if(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(d_out);
+    return 0;
+  }
+  cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, st);
+  proof_div_kernel<<<148 * 16, 256, 0, st>>>(c, d_out);
+  cudaError_t e = cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if(e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
   cudaFree(d_out);
   if(e != cudaSuccess) {
     cudaGetLastError();
@@ -144,6 +170,12 @@ extern "C" {
 /* Test / diagnostics hook: runs (or returns the cached result of) the fast-path proofs for
  * the given parameters on the current device.  1 = proven, 0 = not proven (transcription
  * kernel is used), <0 = error. */
+int rk_vdt_prepare(const rk_vdt_params_t *p) {
+  if(!p) return RK_ERR_ARG;
+  if(int rc = rk::require_device()) return rc;
+  (void)rk::fast_path_proven(*p);
+  return RK_OK;
+}
 int rk_vdt_fast_path_proven(const rk_vdt_params_t *p) {
   if(!p) return -RK_ERR_ARG;
   if(rk::require_device() != RK_OK) return -RK_ERR_CUDA;

@@ -325,7 +325,7 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
     const bool init = do_init && u == 0;
     if(init) { // WitInit: s_uiWitDataCnt = 0 ; WitReadReg(q0, 4): s_uiReadRegIndex = q0
       p.cnt   = 0u;
-      p.flags = (p.flags & ~0xFF00u) | (0x51u << 8);
+      p.flags = (p.flags & ~0xFF00u) | (0x51u << 8) | RK_IP_FLAG_INIT_PENDING;
     }
     const uint32_t nb = live ? min(nb_next, 16u * (uint32_t)ncells) : 0u; // bytes on the wire in this update
     if(nbytes && live && u + 1 < K) nb_next = (uint32_t)__ldcs(nbytes + (int64_t)(u + 1) * n + i); // consumed an update later
@@ -355,17 +355,22 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
     }
     const bool hq = (p.flags & 1u) != 0u; // isComComp :132-143
     if(hq) p.flags &= ~0xFFu;
-    if(init || hq) {
+    // init() -> getDataImmediately (:63-77,149-158) spins in isComComp() until a quaternion frame has arrived: an update
+    // slot without one is still part of that wait (nothing is published, q_init is not latched); the slot that brings it
+    // completes init.  The pending state lives in the parser block, so it survives slots and launches.
+    const bool pending = (p.flags & RK_IP_FLAG_INIT_PENDING) != 0u;
+    if(hq) {
       int r[16];
       wit_regs(p, r);
-      if(!init) flags &= ~RK_IS_FLAG_ERROR;
+      if(!pending) flags &= ~RK_IS_FLAG_ERROR;
       imu_update_data(qi, r, cur);
-      if(init) { // q_init latched from q0..q3  :72-75
+      if(pending) { // q_init latched from q0..q3  :72-75
         const float S = 1.0f / 32768.0f;
 #pragma unroll
         for(int k = 0; k < 4; k++) qi[k] = fmul((float)r[RK_IMT_REG_Q0 + k], S);
+        p.flags &= ~RK_IP_FLAG_INIT_PENDING;
       }
-    } else {
+    } else if(!pending) {
       flags |= RK_IS_FLAG_ERROR;
     }
     if(live) {

@@ -108,3 +108,54 @@ def test_golden_imu_wire():
     np.testing.assert_array_equal(out, g["out"])
     np.testing.assert_array_equal(st, g["state"])
     np.testing.assert_array_equal(parser_sreg(ps, n), g["sreg"])
+
+
+def late_quaternion_wire(n, K, seed):
+    """Healthy traffic (five frames per update) in which the FIRST quaternion frame is late for most IMUs: the
+    quaternion frame of updates 0 .. late-1 never makes it onto the wire (44 bytes instead of 55), so
+    IMU_IF_WT901C::init() -- update slot 0 -- keeps waiting in getDataImmediately() through those slots."""
+    regs, _ = streams.imu_samples(n, K, seed=seed)
+    cells, nb = streams.imu_wire_clean(regs, ncells=4)
+    late = np.arange(n) % 4  # 0: on time, 1..3: that many slots late
+    for i in range(n):
+        nb[: late[i], i] = 44
+    return cells, nb, late
+
+
+@pytest.mark.skipif(not ol.have_ref("libref_imu.so"), reason="oracle/_ref not built")
+def test_init_waits_for_a_late_first_quaternion_frame_like_the_reference():
+    """init() must not latch q_init (or publish) before its first quaternion frame.  Port == the compiled
+    reference, whose blocking init() is fed the following update slots while it spins."""
+    n, K = 64, 12
+    cells, nb, late = late_quaternion_wire(n, K, 77)
+    st_r = np.zeros(layout.IS_WORDS * n, dtype=np.uint32)
+    out_r, sreg_r = ol.imu_bytes_ref(st_r, n, cells, nb, want_out=True)
+    st_p, ps_p = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
+    out_p = ol.imu_bytes_port(st_p, ps_p, n, cells, nb, want_out=True, do_init=True)
+    np.testing.assert_array_equal(out_p, out_r)
+    np.testing.assert_array_equal(st_p, st_r)
+    np.testing.assert_array_equal(parser_sreg(ps_p, n), sreg_r)
+    # nothing is published while init() waits, and q_init is the quaternion of the frame that ended the wait
+    o = np.ascontiguousarray(out_p.transpose(0, 2, 1, 3)).reshape(K, n, 16)
+    for i in range(n):
+        assert not o[: late[i], i].any() and o[late[i], i].any()
+    regs, _ = streams.imu_samples(n, K, seed=77)
+    qi = layout.soa_to_aos(st_p, n, layout.IS_WORDS)[:, :4].view(np.float32)
+    for i in range(n):
+        np.testing.assert_array_equal(qi[i], regs[late[i], 12:16, i].astype(np.float32) / np.float32(32768.0))
+
+
+def test_pending_init_is_carried_across_launches_port():
+    """The wait survives a launch boundary: slots 0..1 in one call (no quaternion frame), the rest in the next."""
+    n, K = 32, 8
+    cells, nb, late = late_quaternion_wire(n, K, 78)
+    st_a, ps_a = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
+    out_a = ol.imu_bytes_port(st_a, ps_a, n, cells, nb, want_out=True, do_init=True)
+    st_b, ps_b = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
+    o1 = ol.imu_bytes_port(st_b, ps_b, n, np.ascontiguousarray(cells[:2]), np.ascontiguousarray(nb[:2]), want_out=True, do_init=True)
+    pend = layout.soa_to_aos(ps_b, n, layout.IP_WORDS)[:, 3] & 0x10000
+    assert ((pend != 0) == (late >= 2)).all()
+    o2 = ol.imu_bytes_port(st_b, ps_b, n, np.ascontiguousarray(cells[2:]), np.ascontiguousarray(nb[2:]), want_out=True, do_init=False)
+    np.testing.assert_array_equal(np.concatenate([o1, o2]), out_a)
+    np.testing.assert_array_equal(st_b, st_a)
+    np.testing.assert_array_equal(ps_b, ps_a)

@@ -105,3 +105,28 @@ def test_feed_bytes_argument_errors():
     assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), ib.parser.data_ptr(), 4, 1, 2, None, None, None, None, 0, None) == 1
     assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), None, 4, 1, 0, None, None, None, None, 0, None) == 1
     assert lib.rk_imt_feed_bytes(ib.state.data_ptr(), ib.parser.data_ptr(), 0, 1, 2, None, None, None, None, 0, None) == 0
+
+
+def test_init_waits_for_a_late_first_quaternion_frame():
+    """with the first quaternion frame up to three update slots late, the device neither latches q_init nor
+    publishes before it -- same bits as the port (pinned against the compiled reference's blocking init() on the CPU) --
+    in one launch and with the wait carried across a launch boundary in the parser block."""
+    from test_imu_wire_cpu import late_quaternion_wire
+
+    n, K = 300, 10
+    cells, nb, late = late_quaternion_wire(n, K, 91)
+    st, ps = np.zeros(layout.IS_WORDS * n, dtype=np.uint32), np.zeros(layout.IP_WORDS * n, dtype=np.uint32)
+    exp = ol.imu_bytes_port(st, ps, n, cells, nb, want_out=True, do_init=True)
+    ib = ImuBatch(n, DEV)
+    out = gpu_feed(ib, cells, nb, True)
+    gs, gp = blocks(ib)
+    np.testing.assert_array_equal(out, exp)
+    np.testing.assert_array_equal(gs, st)
+    np.testing.assert_array_equal(gp, ps)
+    ib2 = ImuBatch(n, DEV)
+    o1 = gpu_feed(ib2, np.ascontiguousarray(cells[:2]), np.ascontiguousarray(nb[:2]), True)
+    o2 = gpu_feed(ib2, np.ascontiguousarray(cells[2:]), np.ascontiguousarray(nb[2:]), False)
+    np.testing.assert_array_equal(np.concatenate([o1, o2]), exp)
+    gs2, gp2 = blocks(ib2)
+    np.testing.assert_array_equal(gs2, st)
+    np.testing.assert_array_equal(gp2, ps)
