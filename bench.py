@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--occupancy", type=int, default=0, help="RK_OPT_FAST_OCCUPANCY override (tuning)")
     ap.add_argument("--packed", type=int, default=-1, help="RK_OPT_FAST_PACKED override (tuning; -1 = library default)")
     ap.add_argument("--ffsat", type=int, default=-1, help="RK_OPT_FAST_FFSAT override (tuning; -1 = library default)")
+    ap.add_argument("--gen-ctas", type=int, default=2, help="e2e: RK_OPT_STREAM_CTAS while the stream generators run beside the rollout")
     ap.add_argument("--side-ctas", type=int, default=-1, help="RK_OPT_TICK_SIDE_CTAS override (tuning; -1 = library default)")
     ap.add_argument("--no-modules", action="store_true", help="workload full: skip the configs[1..3] module measurements")
     ap.add_argument("--no-e2e", action="store_true")
@@ -848,6 +849,7 @@ def run_ours_full(a):
     e2e = None
     if not a.no_e2e:
         gen_s, comp_s, back_s = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        _cabi.check(lib.rk_set_option(_cabi.RK_OPT_STREAM_CTAS, a.gen_ctas))  # the generators trickle beside the rollout
         bufs = []
         for b in range(2):
             d = alloc_tables()
@@ -901,6 +903,7 @@ def run_ours_full(a):
         clocks.pause()
         sharding.barrier()
         ms_e = sharding.max_over_ranks(t0e.elapsed_time(t1e), dev)
+        _cabi.check(lib.rk_set_option(_cabi.RK_OPT_STREAM_CTAS, 0))
         e2e = {"value": a.total * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / K,
                "path": "per chunk: 48-byte stream descriptor pinned host -> device; rk_stream_vehicle_commands / rk_stream_imu_samples / "

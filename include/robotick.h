@@ -60,6 +60,8 @@ enum {
   RK_OPT_FAST_OCCUPANCY = 2, /* 3 or 4 (default) resident CTAs/SM: register budget of the rollout kernel */
   RK_OPT_FAST_PACKED = 3,    /* 1 (default): packed FADD2/FFMA2 tick; 0: scalar tick.  Bit-identical; tests compare. */
   RK_OPT_FAST_FFSAT = 5,     /* 1: the feed-forward clamp to +-1 as two FMUL.SAT (FMA pipe); 0 (default): as FMNMX (ALU pipe).  Bit-identical. */
+  RK_OPT_STREAM_CTAS = 6,    /* rk_stream_*: at most this many CTAs per SM (0, the default: full grids).  A planner that expands
+                              * the next batch's streams beside a running rollout keeps them out of its way.  Scheduling only. */
   RK_OPT_TICK_SIDE_CTAS = 4  /* rk_tick_rollout: CTAs per SM its IMU / arm kernels may occupy beside the vehicle
                               * rollout (default 1; 0 = full grids).  Scheduling only, results do not depend on it. */
 };

@@ -23,6 +23,7 @@ RK_OPT_FAST_OCCUPANCY = 2
 RK_OPT_FAST_PACKED = 3
 RK_OPT_TICK_SIDE_CTAS = 4
 RK_OPT_FAST_FFSAT = 5
+RK_OPT_STREAM_CTAS = 6
 
 
 class VdtParams(C.Structure):

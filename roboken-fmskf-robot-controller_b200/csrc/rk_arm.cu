@@ -195,10 +195,11 @@ RK_DEV void ring_next(const ArmLoop &a, uint32_t slot, uint32_t idx, uint32_t &n
 // SUBNORMAL quotients can be exact ties (3 * 2^-149 / 6 = 2^-150), where the inexact reciprocal decides the rounding
 // instead of ties-to-even: those (|q| < 2^-125, x != 0) take the IEEE division.  rk_selftest_div_rcp64
 // (tests/test_arm_gpu.py) compares the function with div.rn.f32 on 2^32 (x, c) pairs, integer counts included.
+RK_DEV float div_by_rcp64_raw(float x, double rc) { return __double2float_rn(__dmul_rn((double)x, rc)); }
+RK_DEV bool  div_by_rcp64_unsafe(float x, float q) { return fabsf(q) < 2.3509887e-38f /* 2^-125 */ && x != 0.0f; }
 RK_DEV float div_by_rcp64(float x, float c, double rc) {
-  const float q = __double2float_rn(__dmul_rn((double)x, rc));
-  if(fabsf(q) < 2.3509887e-38f /* 2^-125 */ && x != 0.0f) return fdiv(x, c);
-  return q;
+  const float q = div_by_rcp64_raw(x, rc);
+  return div_by_rcp64_unsafe(x, q) ? fdiv(x, c) : q;
 }
 
 RK_DEV uint4 ldp(const uint4 *st, int64_t n, int64_t i, int word) { return ld_plane(st, n, word / 4, i); }
@@ -320,7 +321,18 @@ RK_DEV void loop_fsm_transitions(ArmLoop &a, const rk_adt_params_t &p, const uin
       // the five divisions by the same count: x / c == (float)((double)x * RN64(1 / c)) for every float x and c (div_by_rcp64)
       const double rc = __drcp_rn((double)fc);
 #pragma unroll
-      for(int k = 0; k < 5; k++) a.move[k] = div_by_rcp64(fsub(a.now_tgt[k], fsub(a.tgt[k], a.ofs[k])), fc, rc);
+      float d[5];
+      bool  slow = false; // one test for the five quotients: the IEEE division is out of the way of the common case
+#pragma unroll
+      for(int k = 0; k < 5; k++) {
+        d[k]      = fsub(a.now_tgt[k], fsub(a.tgt[k], a.ofs[k]));
+        a.move[k] = div_by_rcp64_raw(d[k], rc);
+        slow |= div_by_rcp64_unsafe(d[k], a.move[k]);
+      }
+      if(slow) {
+#pragma unroll 1
+        for(int k = 0; k < 5; k++) a.move[k] = fdiv(d[k], fc);
+      }
       a.cnt      = cnt;
       a.total_ms = a.now_dt;
       a.cyc      = 0;

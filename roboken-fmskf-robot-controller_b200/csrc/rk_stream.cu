@@ -32,11 +32,10 @@ RK_DEV float    u01_32(uint32_t h) { return fmul((float)(h >> 8), 1.0f / 1677721
 // streams.vehicle_commands_v2: [n_seg][n] rk_vdt_cmd_t
 __global__ void __launch_bounds__(256)
 stream_vehicle_commands_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, int n_seg, uint4 *__restrict__ cmd) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
   const rk_stream_desc_t d = *dd;
-  const uint32_t         px = h32_prefix(d.seed, 1u, (uint64_t)(d.first + i));
   const float four_pi = (float)(4.0 * M_PI), two_pi = (float)(2.0 * M_PI), rl = (float)(6.0 * M_PI);
+  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const uint32_t px = h32_prefix(d.seed, 1u, (uint64_t)(d.first + i));
   for(int s = 0; s < n_seg; s++) {
     const uint32_t b = h32_idx(px, (uint32_t)s);
     float vx  = fsub(fmul(u01_32(sub32(b, 0u)), 800.0f), 400.0f);
@@ -53,6 +52,7 @@ stream_vehicle_commands_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t 
     q.x = stop ? 0u : f2u(vx), q.y = stop ? 0u : f2u(vy), q.z = stop ? 0u : f2u(vth);
     q.w = stop ? (uint32_t)RK_CMD_STOP : (uint32_t)RK_CMD_MOVE;
     __stcs(cmd + (int64_t)s * n + i, q);
+  }
   }
 }
 
@@ -87,10 +87,9 @@ stream_vehicle_yaw_reg_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n
 __global__ void __launch_bounds__(256)
 stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, int n_upd, uint4 *__restrict__ cells,
                           uint8_t *__restrict__ have) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
-  const rk_stream_desc_t d  = *dd;
-  const uint32_t         px = h32_prefix(d.seed, 20u, (uint64_t)(d.first + i));
+  const rk_stream_desc_t d = *dd;
+  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const uint32_t px = h32_prefix(d.seed, 20u, (uint64_t)(d.first + i));
   for(int u = 0; u < n_upd; u++) {
     const uint32_t b = h32_idx(px, d.first_update + (uint32_t)u);
     uint32_t       w[8];
@@ -110,15 +109,15 @@ stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, in
     __stcs(cells + ((int64_t)u * 2 + 1) * n + i, make_uint4(w[4], w[5], w[6], w[7]));
     if(have) have[(int64_t)u * n + i] = (d.drop_every == 0u || (sub32(b, 8u) % d.drop_every) != 0u) ? 1u : 0u;
   }
+  }
 }
 
 // streams.arm_sequences_v2 as the SoA slot image rk_adt_push_cmdseq takes: 65 planes of uint4 [n]
 __global__ void __launch_bounds__(256)
 stream_arm_sequences_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, uint4 *__restrict__ img) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
-  const rk_stream_desc_t d    = *dd;
-  const uint64_t         inst = (uint64_t)(d.first + i);
+  const rk_stream_desc_t d = *dd;
+  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const uint64_t inst = (uint64_t)(d.first + i);
   const uint32_t         b0   = h32_idx(h32_prefix(d.seed, 30u, inst), 0u);
   const uint32_t         ln   = (sub32(b0, 0u) % (d.arm_max_len - d.arm_min_len + 1u)) + d.arm_min_len;
   const bool             z    = d.arm_dt_zero_every != 0u && (sub32(b0, 1u) % d.arm_dt_zero_every) == 0u;
@@ -137,6 +136,26 @@ stream_arm_sequences_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, 
     __stcs(img + (int64_t)(1 + 2 * k) * n + i, make_uint4(dt, a[0], a[1], a[2]));
     __stcs(img + (int64_t)(2 + 2 * k) * n + i, make_uint4(a[3], a[4], 0u, 0u));
   }
+  }
+}
+
+// rk_set_option(RK_OPT_STREAM_CTAS, k): the generators run on at most k CTAs per SM (0 = one thread per robot, full grid);
+// a planner that expands the next batch's streams while the current rollout runs keeps them out of the rollout's way
+static int g_stream_ctas_per_sm = 0;
+int        stream_set_ctas(int v) {
+  if(v < 0 || v > 32) return RK_ERR_ARG;
+  g_stream_ctas_per_sm = v;
+  return RK_OK;
+}
+static unsigned stream_grid(int64_t n) {
+  unsigned g = (unsigned)((n + 255) / 256);
+  if(g_stream_ctas_per_sm > 0) {
+    int dev = 0, sms = 148;
+    if(cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned cap = (unsigned)(g_stream_ctas_per_sm * sms);
+    if(g > cap) g = cap;
+  }
+  return g;
 }
 
 static int stream_check(const char *who, const void *d_desc, const void *out, int64_t n) {
@@ -163,7 +182,7 @@ void rk_stream_default_desc(rk_stream_desc_t *d) {
 int rk_stream_vehicle_commands(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_seg, rk_vdt_cmd_t *d_cmd, void *stream) {
   if(n == 0 || n_seg <= 0) return RK_OK;
   if(int rc = stream_check("rk_stream_vehicle_commands", d_desc, d_cmd, n)) return rc;
-  stream_vehicle_commands_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_seg, (uint4 *)d_cmd);
+  stream_vehicle_commands_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_seg, (uint4 *)d_cmd);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
@@ -180,7 +199,7 @@ int rk_stream_vehicle_yaw_reg(const rk_stream_desc_t *d_desc, int64_t n, int32_t
 int rk_stream_imu_samples(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat, void *stream) {
   if(n == 0 || n_upd <= 0) return RK_OK;
   if(int rc = stream_check("rk_stream_imu_samples", d_desc, d_regs, n)) return rc;
-  stream_imu_samples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_upd, (uint4 *)d_regs, d_have_quat);
+  stream_imu_samples_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_upd, (uint4 *)d_regs, d_have_quat);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
@@ -188,7 +207,7 @@ int rk_stream_imu_samples(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_u
 int rk_stream_arm_sequences(const rk_stream_desc_t *d_desc, int64_t n, void *d_seq, void *stream) {
   if(n == 0) return RK_OK;
   if(int rc = stream_check("rk_stream_arm_sequences", d_desc, d_seq, n)) return rc;
-  stream_arm_sequences_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_desc, n, (uint4 *)d_seq);
+  stream_arm_sequences_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(d_desc, n, (uint4 *)d_seq);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }

@@ -490,6 +490,7 @@ static cudaError_t launch_rollout(const rk_vdt_params_t &p, void *d_state, int64
 
 bool fast_path_proven(const rk_vdt_params_t &p); // rk_exact.cu
 int  tick_set_side_ctas(int v);                     // rk_tick.cu
+int  stream_set_ctas(int v);                        // rk_stream.cu
 
 static int g_fast_occupancy = 4;       // rk_set_option(RK_OPT_FAST_OCCUPANCY, 3|4|5): tuning
 static int g_fast_packed = 1;          // rk_set_option(RK_OPT_FAST_PACKED, 0|1): packed FP32 tick (default) or scalar
@@ -553,6 +554,7 @@ int rk_set_option(int option, int value) {
     rk::g_fast_ffsat = value != 0;
     return RK_OK;
   }
+  if(option == RK_OPT_STREAM_CTAS && rk::stream_set_ctas(value) == RK_OK) return RK_OK;
   if(option == RK_OPT_TICK_SIDE_CTAS && rk::tick_set_side_ctas(value) == RK_OK) return RK_OK;
   set_error("rk_set_option: unknown option %d / bad value %d", option, value);
   return RK_ERR_ARG;

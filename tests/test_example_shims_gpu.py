@@ -85,7 +85,8 @@ def test_arm_shim_replays_debug_sequences(exe, tmp_path):
             np.testing.assert_array_equal(f[1], np.array([0, 120, -90, 0, 45], dtype=np.float32))
             np.testing.assert_array_equal(f[100], np.array([19.6000004, 61.2000008, -31.2000008, 44.0999985, -57.9000015], dtype=np.float32))
             np.testing.assert_array_equal(f[304], np.array([0, 120, -60, 0, 45], dtype=np.float32))
-            assert int(rows[1 + 304].split()[6]) == 1  # DONE
+            done = [int(r.split()[6]) for r in rows[1:]]
+            assert done[0] == 0 and 304 <= done.index(1) <= 306  # PROCESSING from the first tick, DONE when the last segment ends
 
 
 def test_manager_shim_replays_golden(exe, tmp_path):

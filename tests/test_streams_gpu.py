@@ -41,3 +41,26 @@ def test_device_streams_defaults_and_no_have_block():
     np.testing.assert_array_equal(regs.cpu().numpy(), streams.imu_cells(eregs))
     q = eregs[:, 12:16, :].astype(np.float64)
     assert np.abs(np.sqrt((q * q).sum(axis=1)) - 32767.0).max() < 1.5  # unit quaternions x 32767
+
+
+def test_capped_generators_give_the_same_blocks():
+    """RK_OPT_STREAM_CTAS only changes how the robots are spread over CTAs."""
+    from roboken_fmskf_robot_controller_b200 import _cabi
+
+    n, lib = 70001, _cabi.load()
+    ref = None
+    try:
+        for cap in (0, 1, 3):
+            lib.rk_set_option(_cabi.RK_OPT_STREAM_CTAS, cap)
+            ds = DeviceStreams(DEV, seed=5, first=99)
+            got = [ds.vehicle_commands(torch.zeros((3, n, 4), dtype=torch.int32, device=DEV)),
+                   ds.imu_samples(torch.zeros((4, 2, n, 8), dtype=torch.int16, device=DEV), torch.zeros((4, n), dtype=torch.uint8, device=DEV))[0],
+                   ds.arm_sequences(torch.zeros(layout.ACMD_SLOT_WORDS * n, dtype=torch.int32, device=DEV))]
+            torch.cuda.synchronize()
+            got = [g.cpu().numpy().copy() for g in got]
+            if ref is None:
+                ref = got
+            for a, b in zip(got, ref):
+                np.testing.assert_array_equal(a, b)
+    finally:
+        lib.rk_set_option(_cabi.RK_OPT_STREAM_CTAS, 0)
