@@ -848,10 +848,12 @@ def run_ours_full(a):
     # ---- e2e: per chunk a 48-byte descriptor in, tables expanded on the device, costs out, through rk_tick_rollout ----
     e2e = None
     if not a.no_e2e:
-        gen_s, comp_s, back_s = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        gen_s, back_s = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev)
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_STREAM_CTAS, a.gen_ctas))  # the generators trickle beside the rollout
+        # table sets: one being generated, one per compute lane in flight
+        NB = lanes + 1
         bufs = []
-        for b in range(2):
+        for b in range(NB):
             d = alloc_tables()
             d.update(cost=torch.zeros(n, dtype=torch.float32, device=dev), cost_h=torch.empty(n, dtype=torch.float32).pin_memory(),
                      up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event())
@@ -860,26 +862,29 @@ def run_ours_full(a):
         argcache = {}
 
         def e2e_pass(s):
+            """Like one_pass, with every chunk's tables expanded on the device first (generation stream, beside the rollouts)
+            and its cost vector read back (copy stream)."""
             for c, ch in enumerate(chunks):
-                b = bufs[(s * n_chunks + c) % 2]
-                rb = ch["rb"]
+                g = s * n_chunks + c
+                b = bufs[g % NB]
+                rb, ls = ch["rb"], lane_s[c % lanes]
                 with torch.cuda.stream(gen_s):
-                    gen_s.wait_event(b["done"])
+                    gen_s.wait_event(b["done"])  # the rollout that last used this table set has finished
                     ch["ds"].upload(gen_s)
                     generate(ch["ds"], b, gen_s)
                     b["up"].record(gen_s)
-                with torch.cuda.stream(comp_s):
-                    comp_s.wait_event(b["up"])
-                    comp_s.wait_event(b["down"])
+                with torch.cuda.stream(ls):
+                    ls.wait_event(b["up"])
+                    ls.wait_event(b["down"])  # the cost buffer has been drained
                     rb.vehicle.state.zero_()  # every rollout starts from the power-on vehicle
-                    rb.arm.mode_init(stream=comp_s)
-                    rb.arm.push_cmdseq(b["seq"], stream=comp_s)
-                    key = (c, (s * n_chunks + c) % 2)
+                    rb.arm.mode_init(stream=ls)
+                    rb.arm.push_cmdseq(b["seq"], stream=ls)
+                    key = (c, g % NB)
                     if key not in argcache:
                         argcache[key] = rb.make_args(T, slow, cmd=b["cmd"], seg_len=a.seg_len, regs=b["regs"], have_quat=b["have"],
-                                                     yaw=yaws[0], goal=goal_d, cost=b["cost"])
-                    rb.rollout_args(argcache[key], stream=comp_s)
-                    b["done"].record(comp_s)
+                                                     yaw=yaws[c % lanes], goal=goal_d, cost=b["cost"])
+                    rb.rollout_args(argcache[key], stream=ls)
+                    b["done"].record(ls)
                 with torch.cuda.stream(back_s):
                     back_s.wait_event(b["done"])
                     b["cost_h"].copy_(b["cost"], non_blocking=True)
@@ -892,11 +897,11 @@ def run_ours_full(a):
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         clocks.start()
         t0e.record(stream)
-        for st_ in (gen_s, back_s, comp_s):
+        for st_ in [gen_s, back_s] + lane_s:
             st_.wait_stream(stream)
         for s in range(K):
             e2e_pass(s)
-        for st_ in (gen_s, back_s, comp_s):
+        for st_ in [gen_s, back_s] + lane_s:
             stream.wait_stream(st_)
         t1e.record(stream)
         torch.cuda.synchronize()
@@ -909,7 +914,7 @@ def run_ours_full(a):
                "path": "per chunk: 48-byte stream descriptor pinned host -> device; rk_stream_vehicle_commands / rk_stream_imu_samples / "
                        "rk_stream_arm_sequences expand it into the command, IMU-register and arm-sequence tables on the device (4.5 KB per "
                        "robot that never cross PCIe); vehicle reset to power-on; rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout via "
-                       "ctypes; cost vector D2H; generation, compute and D2H double-buffered on three streams"}
+                       "ctypes; cost vector D2H; generation (high-priority stream, capped grid), compute (the lanes of the value path) and D2H overlap"}
 
     # ---- the module configurations (BASELINE configs[1..3]) on this GPU, outside the timed regions ----------------------
     modules = None

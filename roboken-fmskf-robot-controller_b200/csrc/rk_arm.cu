@@ -329,8 +329,8 @@ RK_DEV void loop_fsm_transitions(ArmLoop &a, const rk_adt_params_t &p, const uin
         a.move[k] = div_by_rcp64_raw(d[k], rc);
         slow |= div_by_rcp64_unsafe(d[k], a.move[k]);
       }
-      if(slow) {
-#pragma unroll 1
+      if(slow) { // (static indices: a rolled loop would put d[] and move[] into local memory)
+#pragma unroll
         for(int k = 0; k < 5; k++) a.move[k] = fdiv(d[k], fc);
       }
       a.cnt      = cnt;

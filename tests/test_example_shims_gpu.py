@@ -85,8 +85,11 @@ def test_arm_shim_replays_debug_sequences(exe, tmp_path):
             np.testing.assert_array_equal(f[1], np.array([0, 120, -90, 0, 45], dtype=np.float32))
             np.testing.assert_array_equal(f[100], np.array([19.6000004, 61.2000008, -31.2000008, 44.0999985, -57.9000015], dtype=np.float32))
             np.testing.assert_array_equal(f[304], np.array([0, 120, -60, 0, 45], dtype=np.float32))
-            done = [int(r.split()[6]) for r in rows[1:]]
-            assert done[0] == 0 and 304 <= done.index(1) <= 306  # PROCESSING from the first tick, DONE when the last segment ends
+            # alone in the ring (Appendix D's run): PROCESSING from the first tick, DONE once the last segment has ended
+            solo = run(exe, "arm", struct.pack("<ii", K, 1) + seq_blob(g["seq_a"][i]), tmp_path)
+            done = [int(r.split()[6]) for r in solo[1:]]
+            assert done[0] == 0 and 304 <= done.index(1) <= 306 and all(x == 1 for x in done[done.index(1):])
+            np.testing.assert_array_equal(np.array([[int(x, 16) for x in r.split()[1:6]] for r in solo[1:306]], dtype=np.uint32), tg[:305])
 
 
 def test_manager_shim_replays_golden(exe, tmp_path):
