@@ -745,18 +745,27 @@ def run_ours_full(a):
         chunks.append(dict(rb=rb, cost=cost, args=args, tb=tb, ds=ds))
     torch.cuda.synchronize()
 
-    def one_pass():
-        """All chunks of this rank: arm bring-up + one command sequence pushed, then the fused tick; the lanes fork
-        from and join the current stream, so events recorded on it bracket the whole pass."""
+    def fork():
         for ls in lane_s:
             ls.wait_stream(stream)
+
+    def join():
+        for ls in lane_s:
+            stream.wait_stream(ls)
+
+    def one_pass(fork_join=True):
+        """All chunks of this rank: arm bring-up + one command sequence pushed, then the fused tick.  The lanes fork from
+        and join the current stream, so events recorded on it bracket the work; inside a timed region of several passes
+        only the first forks and the last joins (a chunk always runs on the same lane, which orders its passes)."""
+        if fork_join:
+            fork()
         for c, ch in enumerate(chunks):
             ls = lane_s[c % lanes]
             ch["rb"].arm.mode_init(stream=ls)
             ch["rb"].arm.push_cmdseq(ch["tb"]["seq"], stream=ls)
             ch["rb"].rollout_args(ch["args"], stream=ls)
-        for ls in lane_s:
-            stream.wait_stream(ls)
+        if fork_join:
+            join()
 
     # ---- parity spot check of the exact bench launch (first pass), on EVERY rank: robots sampled from the first,
     # a middle and the last chunk of the rank against the oracle on host-generated copies of their streams ----------
@@ -801,8 +810,10 @@ def run_ours_full(a):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks.start()
     ev0.record(stream)
+    fork()
     for _ in range(K):
-        one_pass()
+        one_pass(fork_join=False)
+    join()
     ev1.record(stream)
     torch.cuda.synchronize()
     clocks.pause()
