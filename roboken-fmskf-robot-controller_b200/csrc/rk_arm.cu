@@ -318,10 +318,9 @@ RK_DEV void loop_fsm_transitions(ArmLoop &a, const rk_adt_params_t &p, const uin
       int32_t     cnt  = f2i_x86((span == 0.0f && p.cycle_time_s > 0.0f) ? span : fdiv(span, p.cycle_time_s));
       cnt              = (cnt <= 0) ? 1 : cnt;
       const float fc   = (float)cnt; // >= 1
-      // the five divisions by the same count: x / c == (float)((double)x * RN64(1 / c)) for every float x and c (div_by_rcp64)
+      // the five divisions by the same count through one double-precision reciprocal (div_by_rcp64)
       const double rc = __drcp_rn((double)fc);
-#pragma unroll
-      float d[5];
+      float        d[5];
       bool  slow = false; // one test for the five quotients: the IEEE division is out of the way of the common case
 #pragma unroll
       for(int k = 0; k < 5; k++) {

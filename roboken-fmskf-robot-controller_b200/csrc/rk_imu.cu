@@ -14,35 +14,53 @@ struct ImuData {
   float d[16]; // IMU_IF::Data in struct order (imu_if_base.hpp:12-18)
 };
 
-// IMU_IF_WT901C::updateData  imu_if_wt901c.cpp:91-129.  x / 32768.0f is an exact scaling
-// (2^-15), written as a multiply.
-RK_DEV void imu_update_data(const float qi[4], const int r[16], ImuData &o) {
-  const float S = 1.0f / 32768.0f;
-  float       a[3], g[3], m[3], e[3], q[4];
+// IMU_IF_WT901C::updateData  imu_if_wt901c.cpp:91-129:
+//   acc = s / 32768 * 16, gyro = s / 32768 * 2000, mag = s, angle = s / 32768 * 180, q = s / 32768; Y and Z negated;
+//   roll = normalize_0to360(roll) - 180; q_out = the product with q_init in the rows of :123-126 (output order z, y, x, w),
+//   left to right, one rounding per operation.
+// On the packed snapshot (two int16 registers a word), arranged for the issue slots it takes:
+//  * cvt.rn.f32.s16 straight from the register halves (no unpacking);
+//  * (x / 32768) * k is ONE multiply by k * 2^-15: the division is an exact scaling, so the product is rounded once
+//    either way, and 16 * 2^-15, 2000 * 2^-15, 180 * 2^-15 are exact floats;
+//  * the four rows of the quaternion product run as two packed rows: a - p == a + (-p) and (-qi) * q == -(qi * q)
+//    exactly, so the inner signs move into eight constant lane pairs formed once per launch from q_init; the two
+//    outer negations of rows 14 and 12 stay where they are (they decide the sign of an exact zero).
+RK_DEV void cvt2_s16(uint32_t w, float &lo, float &hi) {
+  asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.rn.f32.s16 %0, l; cvt.rn.f32.s16 %1, h; }" : "=f"(lo), "=f"(hi) : "r"(w));
+}
+struct ImuQ { // lane pairs {row 14 | row 13} and {row 12 | row 15} of imu_if_wt901c.cpp:123-126, per factor q0..q3
+  float2 a[4], b[4];
+};
+RK_DEV void imu_q_pairs(ImuQ &k, const float qi[4]) {
+  k.a[0] = make_float2(qi[3], -qi[2]), k.a[1] = make_float2(qi[2], qi[3]), k.a[2] = make_float2(-qi[1], qi[0]), k.a[3] = make_float2(-qi[0], -qi[1]);
+  k.b[0] = make_float2(qi[1], qi[0]), k.b[1] = make_float2(-qi[0], qi[1]), k.b[2] = make_float2(qi[3], qi[2]), k.b[3] = make_float2(-qi[2], qi[3]);
+}
+RK_DEV float2 imu_mul2(float s, float2 k, float nz) { return __ffma2_rn(make_float2(s, s), k, make_float2(nz, nz)); } // RN(s * k) per lane
+RK_DEV void imu_update_data_w(const ImuQ &k, const uint32_t rw[8], float nz, ImuData &o) {
+  float f[16];
 #pragma unroll
-  for(int i = 0; i < 3; i++) {
-    a[i] = fmul(fmul((float)r[RK_IMT_REG_AX + i], S), 16.0f);
-    g[i] = fmul(fmul((float)r[RK_IMT_REG_GX + i], S), 2000.0f);
-    m[i] = (float)r[RK_IMT_REG_HX + i];
-    e[i] = fmul(fmul((float)r[RK_IMT_REG_ROLL + i], S), 180.0f);
-  }
+  for(int j = 0; j < 8; j++) cvt2_s16(rw[j], f[2 * j], f[2 * j + 1]);
+  const float KA = 16.0f / 32768.0f, KG = 2000.0f / 32768.0f, KE = 180.0f / 32768.0f, S = 1.0f / 32768.0f; // all exact
+  o.d[0] = fmul(f[0], KA), o.d[1] = fmul(f[1], -KA), o.d[2] = fmul(f[2], -KA);
+  o.d[3] = fmul(f[3], KG), o.d[4] = fmul(f[4], -KG), o.d[5] = fmul(f[5], -KG);
+  o.d[6] = f[6], o.d[7] = -f[7], o.d[8] = -f[8];
+  o.d[9]  = fsub(normalize_deg_0to360(fmul(f[9], KE)), 180.0f);
+  o.d[10] = fmul(f[10], KE);
+  o.d[11] = fmul(f[11], KE);
+  float q[4];
 #pragma unroll
-  for(int i = 0; i < 4; i++) q[i] = fmul((float)r[RK_IMT_REG_Q0 + i], S);
-  o.d[0] = a[0], o.d[1] = -a[1], o.d[2] = -a[2];
-  o.d[3] = g[0], o.d[4] = -g[1], o.d[5] = -g[2];
-  o.d[6] = m[0], o.d[7] = -m[1], o.d[8] = -m[2];
-  o.d[9]  = fsub(normalize_deg_0to360(e[0]), 180.0f);
-  o.d[10] = e[1];
-  o.d[11] = e[2];
-  // rows copied literally from :123-126 (left-to-right, one rounding per operation)
-  o.d[14] = -fsub(fsub(fadd(fmul(qi[3], q[0]), fmul(qi[2], q[1])), fmul(qi[1], q[2])), fmul(qi[0], q[3]));
-  o.d[13] = fsub(fadd(fadd(fmul(-qi[2], q[0]), fmul(qi[3], q[1])), fmul(qi[0], q[2])), fmul(qi[1], q[3]));
-  o.d[12] = -fsub(fadd(fsub(fmul(qi[1], q[0]), fmul(qi[0], q[1])), fmul(qi[3], q[2])), fmul(qi[2], q[3]));
-  o.d[15] = fadd(fadd(fadd(fmul(qi[0], q[0]), fmul(qi[1], q[1])), fmul(qi[2], q[2])), fmul(qi[3], q[3]));
+  for(int j = 0; j < 4; j++) q[j] = fmul(f[12 + j], S);
+  const float2 ra = __fadd2_rn(__fadd2_rn(__fadd2_rn(imu_mul2(q[0], k.a[0], nz), imu_mul2(q[1], k.a[1], nz)), imu_mul2(q[2], k.a[2], nz)),
+                               imu_mul2(q[3], k.a[3], nz));
+  const float2 rb = __fadd2_rn(__fadd2_rn(__fadd2_rn(imu_mul2(q[0], k.b[0], nz), imu_mul2(q[1], k.b[1], nz)), imu_mul2(q[2], k.b[2], nz)),
+                               imu_mul2(q[3], k.b[3], nz));
+  o.d[14] = -ra.x, o.d[13] = ra.y, o.d[12] = -rb.x, o.d[15] = rb.y;
 }
 
+template <bool OUT, bool YAW>
 RK_DEV void imt_update_body(int64_t i, uint4 *__restrict__ state, int64_t n, int K, const int16_t *__restrict__ regs,
-                            const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
+                            const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init,
+                            float nz) {
   float   qi[4];
   ImuData cur;
   {
@@ -56,44 +74,52 @@ RK_DEV void imt_update_body(int64_t i, uint4 *__restrict__ state, int64_t n, int
   }
   uint32_t flags = ld_plane(state, n, 5, i).x;
   // the register snapshot is two 128-bit cells; the loads of update u + 1 are in flight while update u is
-  // computed and stored
-  const uint4 *src = (const uint4 *)regs + i;
-  uint4        c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
-  bool         nhq = true;
-  if(K > 0) {
+  // computed and stored.  Pointers advance by one sample per update.
+  const uint4   *src = (const uint4 *)regs + i;
+  const uint8_t *hsrc = have_quat ? have_quat + i : nullptr;
+  uint4          c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
+  bool           nhq = true;
+  auto           fetch = [&]() {
     c0 = __ldcs(src), c1 = __ldcs(src + n);
-    nhq = have_quat ? (__ldcs(have_quat + i) != 0) : true;
-  }
-  for(int u = 0; u < K; u++) {
-    const uint32_t rw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    int            r[16];
-#pragma unroll
-    for(int k = 0; k < 8; k++) r[2 * k] = lo16(rw[k]), r[2 * k + 1] = hi16(rw[k]);
-    const bool hq = nhq;
-    if(u + 1 < K) {
-      const uint4 *nx = src + (int64_t)(u + 1) * 2 * n;
-      c0 = __ldcs(nx), c1 = __ldcs(nx + n);
-      nhq = have_quat ? (__ldcs(have_quat + (int64_t)(u + 1) * n + i) != 0) : true;
-    }
-    if(do_init && u == 0) { // IMU_IF_WT901C::init  :63-77
-      imu_update_data(qi, r, cur);
-      const float S = 1.0f / 32768.0f;
-#pragma unroll
-      for(int k = 0; k < 4; k++) qi[k] = fmul((float)r[RK_IMT_REG_Q0 + k], S);
-    } else if(hq) { // ::update  :83-89
-      flags &= ~RK_IS_FLAG_ERROR;
-      imu_update_data(qi, r, cur);
-    } else {
-      flags |= RK_IS_FLAG_ERROR; // previous page stays readable
-    }
+    src += 2 * n;
+    if(hsrc) nhq = __ldcs(hsrc) != 0, hsrc += n;
+  };
+  auto publish = [&](int u) {
     // what the vehicle ISR reads each tick: mymath::deg2rad(IMT::get_status_now_yaw())
     // (VD_task_main.cpp:368, imu_task_main.cpp:102-104, util_mymath.hpp:13,16)
-    if(yaw_rad) __stcs(yaw_rad + (int64_t)u * n + i, fmul(cur.d[RK_IS_D_ANGLE + 2], RK_DEG2RAD));
-    if(out) {
+    if(YAW) __stcs(yaw_rad + (int64_t)u * n + i, fmul(cur.d[RK_IS_D_ANGLE + 2], RK_DEG2RAD));
+    if(OUT) {
 #pragma unroll
       for(int pl = 0; pl < 4; pl++)
         __stcs(out + ((int64_t)u * 4 + pl) * n + i, make_float4(cur.d[4 * pl], cur.d[4 * pl + 1], cur.d[4 * pl + 2], cur.d[4 * pl + 3]));
     }
+  };
+  if(K > 0) fetch();
+  ImuQ kq;
+  imu_q_pairs(kq, qi);
+  int u = 0;
+  if(do_init && K > 0) { // IMU_IF_WT901C::init  :63-77: updateData against the current q_init, then latch q_init
+    const uint32_t rw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    if(K > 1) fetch();
+    imu_update_data_w(kq, rw, nz, cur);
+    cvt2_s16(rw[6], qi[0], qi[1]), cvt2_s16(rw[7], qi[2], qi[3]);
+#pragma unroll
+    for(int j = 0; j < 4; j++) qi[j] = fmul(qi[j], 1.0f / 32768.0f);
+    imu_q_pairs(kq, qi);
+    publish(0);
+    u = 1;
+  }
+  for(; u < K; u++) {
+    const uint32_t rw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const bool     hq    = nhq;
+    if(u + 1 < K) fetch();
+    if(hq) { // ::update  :83-89
+      flags &= ~RK_IS_FLAG_ERROR;
+      imu_update_data_w(kq, rw, nz, cur);
+    } else {
+      flags |= RK_IS_FLAG_ERROR; // previous page stays readable
+    }
+    publish(u);
   }
   st_plane(state, n, 0, i, make_uint4(f2u(qi[0]), f2u(qi[1]), f2u(qi[2]), f2u(qi[3])));
 #pragma unroll
@@ -103,11 +129,15 @@ RK_DEV void imt_update_body(int64_t i, uint4 *__restrict__ state, int64_t n, int
 }
 // One thread per IMU; the grid may be smaller than the batch (rk_tick_rollout runs this kernel beside the
 // issue-bound vehicle rollout on a capped number of CTAs), so CTAs stride over the blocks of 256 IMUs.
-__global__ void __launch_bounds__(256)
+// nz_src: any finite positive float; -0.0f is formed from it at run time so that ptxas cannot fold the packed
+// products' "+ (-0)" into the adds that follow (see rk_vehicle_fast2.cuh).
+template <bool OUT, bool YAW>
+__global__ void __launch_bounds__(256, 4) // 64 registers: one CTA fits the slot a retiring vehicle CTA frees (rk_tick.cu)
 imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__restrict__ regs,
-                  const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
+                  const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init, float nz_src) {
+  const float nz = fmul(-0.0f, nz_src);
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    imt_update_body(i, state, n, K, regs, have_quat, out, yaw_rad, do_init);
+    imt_update_body<OUT, YAW>(i, state, n, K, regs, have_quat, out, yaw_rad, do_init, nz);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -180,10 +210,6 @@ RK_DEV bool wit_try_frame(Wit &p, uint32_t f0, uint32_t f1, uint32_t f2) {
   if((sum & 0xFFu) != ((f2 >> 16) & 0xFFu)) return false;
   wit_dispatch(p, (f0 >> 8) & 0xFFu, __byte_perm(f0, f1, 0x5432), __byte_perm(f1, f2, 0x5432));
   return true;
-}
-RK_DEV void wit_regs(const Wit &p, int r[16]) { // the register file as updateData reads it
-#pragma unroll
-  for(int k = 0; k < 8; k++) r[2 * k] = lo16(p.rw[k]), r[2 * k + 1] = hi16(p.rw[k]);
 }
 // `rem` (<= 4) bytes, first byte in the low byte of R: WitSerialDataIn for each  :132-164
 RK_DEV void wit_bytes(Wit &p, uint32_t R, uint32_t rem) {
@@ -264,7 +290,7 @@ constexpr int kWireStages = 16;
 
 __global__ void __launch_bounds__(128)
 imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int64_t n, int K, int ncells, const uint4 *__restrict__ cells,
-                      const uint16_t *__restrict__ nbytes, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init) {
+                      const uint16_t *__restrict__ nbytes, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init, float nz_src) {
   __shared__ __align__(128) uint4 ring[kWireStages][128];
   __shared__ __align__(8) uint64_t full_bar[kWireStages], empty_bar[kWireStages];
   const int      tid = threadIdx.x;
@@ -316,6 +342,9 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
     wit_load(p, a);
     p.rw[0] = b.x, p.rw[1] = b.y, p.rw[2] = b.z, p.rw[3] = b.w, p.rw[4] = c.x, p.rw[5] = c.y, p.rw[6] = c.z, p.rw[7] = c.w;
   }
+  ImuQ kq;
+  imu_q_pairs(kq, qi);
+  const float nz    = fmul(-0.0f, nz_src);
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   // two cells in registers: A is being parsed, B follows it (a frame may straddle into it)
   uint4    B = total > 0 ? fetch(0) : zero4;
@@ -360,14 +389,13 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
     // completes init.  The pending state lives in the parser block, so it survives slots and launches.
     const bool pending = (p.flags & RK_IP_FLAG_INIT_PENDING) != 0u;
     if(hq) {
-      int r[16];
-      wit_regs(p, r);
       if(!pending) flags &= ~RK_IS_FLAG_ERROR;
-      imu_update_data(qi, r, cur);
+      imu_update_data_w(kq, p.rw, nz, cur);
       if(pending) { // q_init latched from q0..q3  :72-75
-        const float S = 1.0f / 32768.0f;
+        cvt2_s16(p.rw[6], qi[0], qi[1]), cvt2_s16(p.rw[7], qi[2], qi[3]);
 #pragma unroll
-        for(int k = 0; k < 4; k++) qi[k] = fmul((float)r[RK_IMT_REG_Q0 + k], S);
+        for(int k = 0; k < 4; k++) qi[k] = fmul(qi[k], 1.0f / 32768.0f);
+        imu_q_pairs(kq, qi);
         p.flags &= ~RK_IP_FLAG_INIT_PENDING;
       }
     } else if(!pending) {
@@ -428,8 +456,17 @@ int rk::imt_update_launch(void *d_state, int64_t n, int32_t K, const int16_t *d_
   if(int rc = require_device()) return rc;
   unsigned grid = (unsigned)((n + 255) / 256);
   if(max_ctas > 0 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;
-  imt_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint4 *)d_state, n, K, d_regs, d_have_quat, (float4 *)d_out, d_yaw_rad,
-                                                            do_init);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RK_LAUNCH_IMT(O, Y) \
+  imt_update_kernel<O, Y><<<grid, 256, 0, st>>>((uint4 *)d_state, n, K, d_regs, d_have_quat, (float4 *)d_out, d_yaw_rad, do_init, 1.0f)
+  if(d_out) {
+    if(d_yaw_rad) RK_LAUNCH_IMT(true, true);
+    else RK_LAUNCH_IMT(true, false);
+  } else {
+    if(d_yaw_rad) RK_LAUNCH_IMT(false, true);
+    else RK_LAUNCH_IMT(false, false);
+  }
+#undef RK_LAUNCH_IMT
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
@@ -454,7 +491,7 @@ int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32
   if(int rc = require_device()) return rc;
   imt_feed_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_state, (uint4 *)d_parser, n, K, ncells,
                                                                                        (const uint4 *)d_cells, d_nbytes, (float4 *)d_out,
-                                                                                       d_yaw_rad, do_init);
+                                                                                       d_yaw_rad, do_init, 1.0f);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
