@@ -133,6 +133,8 @@ struct ArmLoop {
   float    tgt[5], tgt_dfl, tgt_dfr; // fl_raw_tgt_deg of the same
   float    cl_dfl, cl_dfr, cl_p3;    // fl_curlim_A of the three MyBldc joints
   float    now_y0, mg_pre;
+  int32_t  y0_pos;  // LAZY_Y0: the position word of the ICS servo's last answer, converted after the last tick
+  bool     y0_seen;
   uint32_t ics_pos, ics_servo, mg_tx0, mg_tx1, mg_valid;
   uint32_t bl0[3], bl1[3], bl2[3];   // txmsg word 0, word 1, u32_txcmdid per MyBldc joint
   bool     mg_prev, bl_prev[3];
@@ -231,6 +233,7 @@ RK_DEV void loop_load(const uint4 *st, int64_t n, int64_t i, ArmLoop &a, uint32_
     a.bl0[s] = b.x, a.bl1[s] = b.y, a.bl2[s] = b.z;
   }
   a.lens = 0u, a.pf_key = 0xFFFFFFFFu, a.sel = false;
+  a.y0_pos = -1, a.y0_seen = false;
   a.pa0 = make_uint4(0u, 0u, 0u, 0u), a.pb0 = a.pa0, a.pa1 = make_uint2(0u, 0u), a.pb1 = a.pa1;
   a.mg_prev    = ((jflags >> (4 * RK_AJ_P1)) & RK_AJF_TORQUE_PREV) != 0;
   a.bl_prev[0] = ((jflags >> (4 * RK_AJ_DFL)) & RK_AJF_TORQUE_PREV) != 0;
@@ -407,7 +410,8 @@ __device__ __noinline__ MgFrame mg_update_slow(MgFrame f, float tgt, float ctrl_
   return f;
 }
 
-template <int DIVC, bool MGSLOW> RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i);
+template <int DIVC, bool MGSLOW, bool LAZY_Y0 = false>
+RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i);
 
 template <int DIVC, bool MGSLOW>
 RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
@@ -419,14 +423,18 @@ RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, 
   a.cmd_idx      = fin ? ((a.cmd_idx + 1) & 0xFFu) : a.cmd_idx;
   a.state        = fin ? (uint32_t)RK_ASTATE_MOVE_START : a.state;
   a.cyc          = (moving && !fin) ? a.cyc + 1 : a.cyc;
-  loop_joints<DIVC, MGSLOW>(a, p, c, st, n, i);
+  loop_joints<DIVC, MGSLOW, true>(a, p, c, st, n, i);
 }
 
 // ADT::main's joint updates (AD_task_main.cpp:213-228): j_P1, j_DF_Left, j_DF_Right, j_P3, [CAN tx], j_Y0
 // MGSLOW: the thread's MG joint is NOT in position control (c.mg_pos is invariant over the launch); the
 // kernel runs such threads through a separate instantiation of the tick loop so that the common loop
 // carries none of the torque-control code.
-template <int DIVC, bool MGSLOW>
+// LAZY_Y0: the ICS joint's fl_raw_now_deg (the position the servo answers with) is read by nobody inside
+// ADTModePositioningSeq's tick -- the mode measures from the targets -- so the sequence kernel only remembers the last
+// answer (y0_pos, y0_seen) and converts it once after its last tick (loop_finish_y0); ADTModePositioning measures
+// from get_now_deg() and keeps the eager form.
+template <int DIVC, bool MGSLOW, bool LAZY_Y0>
 RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i) {
   // ---- JointMgServo::update -> subproc_posctrl  AD_joint_mg_servo.cpp:50-73,136-149
   if(MGSLOW) {
@@ -481,9 +489,17 @@ RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c
     const int  now_pos = send ? tp : (fre ? (int)(int32_t)a.ics_servo + 7500 : -1);
     a.ics_pos   = send ? (uint32_t)tp : (fre ? 0xFFFFFFFFu : a.ics_pos);
     a.ics_servo = send ? (uint32_t)(tp - 7500) : a.ics_servo;
-    const float nn = fmul(fmul((float)ics_posDeg100(now_pos), 0.01f), c.dir_y0);
-    a.now_y0       = active ? nn : a.now_y0;
+    if(LAZY_Y0) {
+      a.y0_pos  = active ? now_pos : a.y0_pos;
+      a.y0_seen = a.y0_seen || active;
+    } else {
+      const float nn = fmul(fmul((float)ics_posDeg100(now_pos), 0.01f), c.dir_y0);
+      a.now_y0       = active ? nn : a.now_y0;
+    }
   }
+}
+RK_DEV void loop_finish_y0(ArmLoop &a, const ArmConsts &c) {
+  if(a.y0_seen) a.now_y0 = fmul(fmul((float)ics_posDeg100(a.y0_pos), 0.01f), c.dir_y0);
 }
 
 RK_DEV ArmConsts make_consts(const rk_adt_params_t &p, uint32_t jflags, float mg_rcp) {
@@ -548,11 +564,15 @@ RK_DEV void adt_update_body(int64_t i, const rk_adt_params_t &p, uint4 *__restri
       if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, a.state, a.cmd_idx);
     }
   }
+  loop_finish_y0(a, c);
   loop_store(state, n, i, a, jflags, K > 0);
 }
 // One thread per arm; CTAs stride over the batch when the grid is capped (see imt_update_kernel).
+#ifndef RK_ARM_OCC
+#define RK_ARM_OCC 5
+#endif
 template <bool TRACE, int DIVC>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, RK_ARM_OCC)
 adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
                   uint32_t *__restrict__ trace, float mg_rcp) {
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
