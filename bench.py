@@ -560,7 +560,7 @@ def run_ours(a):
             bufs.append(dict(cmd=c, yaw=y, cost=co, cost_h=torch.empty(n, dtype=torch.float32).pin_memory(),
                              ds=DeviceStreams(dev, seed=seed, first=first),
                              args=vb.make_args(T, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=c, seg_len=a.seg_len, yaw=y,
-                                               yaw_period=a.yaw_period, goal=goal_d, cost=co),
+                                               yaw_period=a.yaw_period, goal=goal_d, cost=co, reset_state=True),
                              up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event()))
         h2d, d2h = DeviceStreams.NBYTES, n * 4
 
@@ -575,8 +575,7 @@ def run_ours(a):
             with torch.cuda.stream(comp_s):
                 comp_s.wait_event(b["up"])
                 comp_s.wait_event(b["down"])  # cost buffer drained
-                vb.state.zero_()  # every rollout starts from the power-on state
-                vb.rollout_args(b["args"], stream=comp_s)
+                vb.rollout_args(b["args"], stream=comp_s)  # reset_state: every rollout starts from the power-on state
                 b["done"].record(comp_s)
             with torch.cuda.stream(back_s):
                 back_s.wait_event(b["done"])
@@ -795,7 +794,10 @@ def run_ours_full(a):
         for got, exp, words in ((rbc.vehicle.state, v, layout.VS_WORDS), (rbc.imu.state, i_, layout.IS_WORDS), (rbc.arm.state, ar, layout.AS_WORDS)):
             g = layout.soa_to_aos(got.cpu().numpy().view(np.uint32), n, words)[idx]
             same &= np.array_equal(g, layout.soa_to_aos(exp, m, words))
-        same &= np.array_equal(chunks[c]["cost"].cpu().numpy()[idx].view(np.uint32), np.asarray(cost_np, dtype=np.float32).view(np.uint32))
+        cost_np = np.asarray(cost_np, dtype=np.float32)
+        same &= np.array_equal(chunks[c]["cost"].cpu().numpy()[idx].view(np.uint32), cost_np.view(np.uint32))
+        if c == n_chunks - 1:
+            spot_last = (idx, cost_np)  # the e2e path must hand back the same costs (it starts every rollout from power-on)
     same = all_ranks_ok(same, dev)
     spot = (f"{m_total} sampled robots x {T} ticks (vehicle + IMU + arm state, rollout cost) on each of {world} rank(s) "
             f"{'bit-exact' if same else 'MISMATCH'} vs {kind_desc}")
@@ -887,13 +889,12 @@ def run_ours_full(a):
                 with torch.cuda.stream(ls):
                     ls.wait_event(b["up"])
                     ls.wait_event(b["down"])  # the cost buffer has been drained
-                    rb.vehicle.state.zero_()  # every rollout starts from the power-on vehicle
                     rb.arm.mode_init(stream=ls)
                     rb.arm.push_cmdseq(b["seq"], stream=ls)
                     key = (c, g % NB)
-                    if key not in argcache:
+                    if key not in argcache:  # reset_vehicle: every rollout starts from the power-on vehicle
                         argcache[key] = rb.make_args(T, slow, cmd=b["cmd"], seg_len=a.seg_len, regs=b["regs"], have_quat=b["have"],
-                                                     yaw=yaws[c % lanes], goal=goal_d, cost=b["cost"])
+                                                     yaw=yaws[c % lanes], goal=goal_d, cost=b["cost"], reset_vehicle=True)
                     rb.rollout_args(argcache[key], stream=ls)
                     b["done"].record(ls)
                 with torch.cuda.stream(back_s):
@@ -920,12 +921,18 @@ def run_ours_full(a):
         sharding.barrier()
         ms_e = sharding.max_over_ranks(t0e.elapsed_time(t1e), dev)
         _cabi.check(lib.rk_set_option(_cabi.RK_OPT_STREAM_CTAS, 0))
+        # the costs the last e2e rollout copied back == the oracle's for the sampled robots of that chunk
+        b_last = bufs[((K - 1) * n_chunks + n_chunks - 1) % NB]
+        e2e_same = all_ranks_ok(np.array_equal(b_last["cost_h"].numpy()[spot_last[0]].view(np.uint32), spot_last[1].view(np.uint32)), dev)
+        if not e2e_same:
+            raise SystemExit("bench e2e parity check failed: costs returned through the end-to-end path differ from the oracle")
         e2e = {"value": a.total * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / K,
                "path": "per chunk: 48-byte stream descriptor pinned host -> device; rk_stream_vehicle_commands / rk_stream_imu_samples / "
                        "rk_stream_arm_sequences expand it into the command, IMU-register and arm-sequence tables on the device (4.5 KB per "
-                       "robot that never cross PCIe); vehicle reset to power-on; rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout via "
-                       "ctypes; cost vector D2H; generation (high-priority stream, capped grid), compute (the lanes of the value path) and D2H overlap"}
+                       "robot that never cross PCIe); rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout (vehicles from power-on) via "
+                       "ctypes; cost vector D2H; generation (high-priority stream, capped grid), compute (the lanes of the value path) and D2H overlap",
+               "parity": "costs copied back by the last rollout bit-exact vs the oracle on the sampled robots of that chunk, every rank"}
 
     # ---- the module configurations (BASELINE configs[1..3]) on this GPU, outside the timed regions ----------------------
     modules = None

@@ -222,6 +222,10 @@ typedef struct rk_vdt_rollout {
   const int16_t *d_imu_regs;
   const uint8_t *d_imu_have_quat;
   const float *d_imu_yaw0_deg;
+  /* != 0: every vehicle starts this rollout from the power-on block (all zeros: the firmware's static initialisation)
+   * instead of the contents of d_state, which is then only written -- a planner's "reset and roll out" without a
+   * separate pass over the block. */
+  int32_t reset_state;
 } rk_vdt_rollout_t;
 
 /* VEHICLE_CTRL::update() x steps   (VD_vehicle_controller.cpp:6-99), fused with the callers
@@ -560,6 +564,7 @@ typedef struct rk_tick_rollout {
   float *d_cost;
   uint32_t *d_vdt_trace;     /* optional traces (tests) */
   uint32_t *d_adt_trace;
+  int32_t reset_vehicle;     /* != 0: the vehicles start from the power-on block (rk_vdt_rollout_t::reset_state) */
 } rk_tick_rollout_t;
 
 int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t *ap, void *d_vdt_state, void *d_imt_state,

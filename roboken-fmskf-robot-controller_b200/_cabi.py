@@ -157,6 +157,7 @@ class TickRollout(C.Structure):
         ("d_cost", C.c_void_p),
         ("d_vdt_trace", C.c_void_p),
         ("d_adt_trace", C.c_void_p),
+        ("reset_vehicle", C.c_int32),
     ]
 
 

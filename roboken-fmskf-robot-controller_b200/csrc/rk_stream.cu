@@ -101,9 +101,10 @@ stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, in
 #pragma unroll
     for(int k = 0; k < 4; k++) g[k] = fsub(fmul(fadd((float)gu[k], 0.5f), 1.0f / 32768.0f), 1.0f);
     const float nrm = fsqrt(fadd(fadd(fadd(fmul(g[0], g[0]), fmul(g[1], g[1])), fmul(g[2], g[2])), fmul(g[3], g[3])));
+    const float sc  = fdiv(32767.0f, nrm);
     uint32_t    q[4];
 #pragma unroll
-    for(int k = 0; k < 4; k++) q[k] = (uint32_t)__float2int_rn(fmul(fdiv(g[k], nrm), 32767.0f)) & 0xFFFFu;
+    for(int k = 0; k < 4; k++) q[k] = (uint32_t)__float2int_rn(fmul(g[k], sc)) & 0xFFFFu;
     w[6] = q[0] | (q[1] << 16), w[7] = q[2] | (q[3] << 16);
     __stcs(cells + ((int64_t)u * 2 + 0) * n + i, make_uint4(w[0], w[1], w[2], w[3]));
     __stcs(cells + ((int64_t)u * 2 + 1) * n + i, make_uint4(w[4], w[5], w[6], w[7]));

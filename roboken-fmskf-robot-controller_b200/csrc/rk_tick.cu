@@ -115,6 +115,7 @@ extern "C" int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t 
     v.d_imu_regs = a->d_regs, v.d_imu_have_quat = a->d_have_quat, v.d_imu_yaw0_deg = a->d_yaw;
     v.n_yaw = n_slow, v.yaw_period = a->slow_period;
     v.d_trace = a->d_vdt_trace, v.d_goal = a->d_goal, v.d_cost = a->d_cost;
+    v.reset_state = a->reset_vehicle;
     mark(4, st);
     rc = rk_vdt_rollout(vp, d_vdt_state, n, &v, st);
     mark(5, st);

@@ -77,7 +77,7 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
   if(i >= n) return;
 
   Veh v;
-  load_veh(state, n, i, v);
+  load_veh_or_reset(state, n, i, v, a.reset_state != 0);
   const Derived d = derive(p);
   float         cth, sth;
   yaw_trig(s_tab, v.pos[2], cth, sth);
@@ -212,7 +212,7 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
   if(i >= n) return;
 
   Veh v;
-  load_veh(state, n, i, v);
+  load_veh_or_reset(state, n, i, v, a.reset_state != 0);
   const Derived d = derive(p);
   FastConsts    fc;
   fast_consts(fc, p, d);
@@ -310,7 +310,7 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
   if(i >= n) return;
 
   Veh v;
-  load_veh(state, n, i, v);
+  load_veh_or_reset(state, n, i, v, a.reset_state != 0);
   const Derived d = derive(p);
   FastConsts    fc;
   fast_consts(fc, p, d);

@@ -30,7 +30,7 @@ class RobotBatch:
         self.arm.mode_init()
 
     def make_args(self, steps, slow_period, cmd, seg_len, regs, have_quat, yaw, goal=None, cost=None, vdt_trace=None,
-                  adt_trace=None):
+                  adt_trace=None, reset_vehicle=False):
         """cmd: [n_seg, n, 4] rk_vdt_cmd_t records; regs: int16 [n_slow, 2, n, 8] (streams.imu_cells); have_quat: uint8
         [n_slow, n] or None; yaw: float32 scratch, >= n words (receives the IMU yaw as it was at launch)."""
         n_slow = (steps + slow_period - 1) // slow_period
@@ -38,6 +38,7 @@ class RobotBatch:
         assert yaw.is_cuda and yaw.dtype == torch.float32 and yaw.numel() >= self.n
         a = _cabi.TickRollout()
         a.steps, a.slow_period = int(steps), int(slow_period)
+        a.reset_vehicle = 1 if reset_vehicle else 0  # the vehicles start from the power-on block
         if cmd is not None:
             assert cmd.is_cuda and cmd.is_contiguous() and cmd.shape[1] == self.n
             a.d_cmd, a.n_seg, a.seg_len = cmd.data_ptr(), cmd.shape[0], int(seg_len)

@@ -473,8 +473,9 @@ def imu_samples_v2(n, n_upd, seed=0x5EED, first=0, drop_every=64, inst=None, fir
     f32 = np.float32
     g = [((x.astype(np.float32) + f32(0.5)) * f32(1.0 / 32768.0)) - f32(1.0) for x in (w6 & _U32(0xFFFF), w6 >> _U32(16), w7 & _U32(0xFFFF), w7 >> _U32(16))]
     nrm = np.sqrt(((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]) + g[3] * g[3], dtype=np.float32)
+    sc = f32(32767.0) / nrm
     for k in range(4):
-        regs[:, 12 + k, :] = np.rint((g[k] / nrm) * f32(32767.0)).astype(np.int16)
+        regs[:, 12 + k, :] = np.rint(g[k] * sc).astype(np.int16)
     if drop_every:
         have = ((sub32(b, 8) % _U32(drop_every)) != 0).astype(np.uint8)
     else:

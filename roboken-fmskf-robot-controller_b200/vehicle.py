@@ -51,12 +51,13 @@ class VehicleBatch:
 
     # ---- the hot path -------------------------------------------------------------------
     def make_args(self, steps, sensor_mode=_cabi.RK_SENSOR_PLANT, cmd=None, seg_len=0, yaw=None, yaw_period=0,
-                  frames=None, trace=None, goal=None, cost=None, task_period=0):
+                  frames=None, trace=None, goal=None, cost=None, task_period=0, reset_state=False):
         """Device tensors -> rk_vdt_rollout_t.  cmd: int32/float32 [n_seg, n, 4] (rk_vdt_cmd_t
         records), yaw: float32 [n_yaw, n] radians or int16 [n_yaw, n] WT901C Yaw register counts, frames: int64 [steps, 4, n], trace: int32
         [steps, 16, n], goal: float32 [n, 2], cost: float32 [n]."""
         a = _cabi.VdtRollout()
         a.steps, a.sensor_mode = int(steps), int(sensor_mode)
+        a.reset_state = 1 if reset_state else 0  # start from the power-on block instead of the contents of self.state
         a.task_period = int(task_period)  # > 0: VDT::main runs every task_period ticks (RK_CMD_MSG_* records, move-time auto-stop)
         if cmd is not None:
             assert cmd.is_cuda and cmd.is_contiguous() and cmd.shape[1] == self.n and cmd.element_size() * cmd.shape[-1] == 16

@@ -589,3 +589,30 @@ def test_c610_tx_frame_words_and_batch_entry():
     v = Vehicle()
     v.set_state(layout.soa_to_aos(st, n, layout.VS_WORDS)[7])
     assert v.tx_routine() == bytes(by[-1, 7])
+
+
+def test_reset_state_flag_equals_a_zeroed_block():
+    """rk_vdt_rollout_t::reset_state: the rollout starts from the power-on block whatever d_state holds -- fast and
+    transcription kernels, plant and stream sensors."""
+    lib = rk.load()
+    n, steps = 700, 300
+    inp = wl.plant_inputs(n, steps, seed=55)
+    st0, tr0 = gpu_run(inp)
+    dirty = layout.aos_to_soa(wl.random_states(n, seed=4))
+    fr = streams.vehicle_frames(n, steps, seed=55)
+    for force in (0, 1):
+        lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, force)
+        try:
+            for sensor, frames in ((_cabi.RK_SENSOR_PLANT, None), (_cabi.RK_SENSOR_STREAM, fr)):
+                ref_st, ref_tr = gpu_run(inp, sensor=sensor, frames=frames)
+                vb = VehicleBatch(n, DEV)
+                vb.load_state_soa(dirty)
+                tr = torch.zeros((steps, 16, n), dtype=torch.int32, device=DEV)
+                vb.rollout(steps, sensor_mode=sensor, cmd=_dev(inp["cmd"], np.int32).reshape(-1, n, 4), seg_len=inp["seg_len"],
+                           yaw=_dev(inp["yaw"]), yaw_period=inp["yaw_period"], frames=_dev(frames, np.int64), trace=tr, reset_state=True)
+                torch.cuda.synchronize()
+                assert_same(tr.cpu().numpy().view(np.uint32), ref_tr, f"reset_state trace (force={force}, sensor={sensor})")
+                assert_same(vb.state.cpu().numpy().view(np.uint32), ref_st, f"reset_state state (force={force}, sensor={sensor})")
+        finally:
+            lib.rk_set_option(_cabi.RK_OPT_FORCE_TRANSCRIPTION, 0)
+    assert_same(st0, gpu_run(inp)[0], "sanity")
