@@ -93,6 +93,7 @@ class VdtRollout(C.Structure):
         ("d_imu_regs", C.c_void_p),
         ("d_imu_have_quat", C.c_void_p),
         ("d_imu_yaw0_deg", C.c_void_p),
+        ("reset_state", C.c_int32),
     ]
 
 

@@ -131,3 +131,35 @@ def test_argument_errors(lib):
     assert rc == 1
     # empty batch / zero steps are no-ops
     assert lib.rk_vdt_rollout(C.byref(rk.default_params()), None, 0, C.byref(a), None) == 0
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """Every structure that crosses the C-ABI has the same size and field offsets in _cabi.py as in include/robotick.h
+    (compiled with gcc): a field missing on the Python side would silently be read as garbage by the library."""
+    import ctypes as C
+    import subprocess
+
+    structs = {"rk_vdt_params_t": _cabi.VdtParams, "rk_vdt_rollout_t": _cabi.VdtRollout, "rk_adt_params_t": _cabi.AdtParams,
+               "rk_tick_rollout_t": _cabi.TickRollout, "rk_stream_desc_t": _cabi.StreamDesc, "rk_adt_poscmdseq_t": _cabi.AdtPosCmdSeq,
+               "rk_rmt_params_t": _cabi.RmtParams, "rk_vdt_cmd_t": _cabi.VdtCmd}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "robotick.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, fname, val = line.split()
+        cls = structs[cname]
+        if fname == "size":
+            assert C.sizeof(cls) == int(val), f"sizeof({cname}): header {val}, ctypes {C.sizeof(cls)}"
+        else:
+            assert getattr(cls, fname).offset == int(val), f"{cname}.{fname}: header {val}, ctypes {getattr(cls, fname).offset}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
