@@ -118,26 +118,11 @@ RK_DEV void load_veh(const uint4 *blk, int64_t n, int64_t i, Veh &v) {
 #pragma unroll
   for(int w = 0; w < 4; w++) load_motor(blk, n, i, w, v.m[w]);
 }
-// rk_vdt_rollout_t::reset_state: the power-on block (static zero-initialisation) without touching HBM
+// rk_vdt_rollout_t::reset_state: the power-on block (static zero-initialisation) without a pass over d_state -- the same
+// loads, all aimed at one zero cell (no second code path: a branch here costs the hot loop 2 % through ptxas' allocation)
+__device__ const uint4 g_zero_cell = {0u, 0u, 0u, 0u};
 RK_DEV void load_veh_or_reset(const uint4 *blk, int64_t n, int64_t i, Veh &v, bool reset) {
-  if(reset) {
-    v.pos[0] = v.pos[1] = v.pos[2] = 0.0f, v.vel[0] = v.vel[1] = v.vel[2] = 0.0f, v.tgt[0] = v.tgt[1] = v.tgt[2] = 0.0f;
-    v.flags = 0u, v.move_cnt = 0u, v.rsv1 = 0u;
-#pragma unroll
-    for(int a = 0; a < 3; a++) {
-      Interp &t = v.it[a];
-      t.vel = t.acl = t.vel_tgt = t.acl_max = t.jerk_p = t.jerk_m = t.dt1 = t.dt2 = t.dt3 = t.vel_ini = t.acl_ini = t.dt = 0.0f;
-    }
-#pragma unroll
-    for(int w = 0; w < 4; w++) {
-      Ctrl &c = v.c[w];
-      c.prev_val = c.integ = c.lpf_y = c.lpf_x = c.now_tgt = c.now_err = c.now_ctrl = 0.0f;
-      Motor &m = v.m[w];
-      m.sum = 0, m.prev = 0, m.ang = m.rpm = m.cur = m.cur_tgt = m.usec = m.head = m.p_ang = m.p_rpm = 0;
-    }
-  } else {
-    load_veh(blk, n, i, v);
-  }
+  load_veh(reset ? &g_zero_cell : blk, reset ? 0 : n, reset ? 0 : i, v);
 }
 RK_DEV void store_veh(uint4 *blk, int64_t n, int64_t i, const Veh &v) {
   st_plane(blk, n, 0, i, make_uint4(f2u(v.pos[0]), f2u(v.pos[1]), f2u(v.pos[2]), v.flags));
