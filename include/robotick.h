@@ -223,8 +223,8 @@ typedef struct rk_vdt_rollout {
   const uint8_t *d_imu_have_quat;
   const float *d_imu_yaw0_deg;
   /* != 0: every vehicle starts this rollout from the power-on block (all zeros: the firmware's static initialisation)
-   * instead of the contents of d_state, which is then only written -- a planner's "reset and roll out" without a
-   * separate pass over the block. */
+   * instead of the contents of d_state -- a planner's "reset and roll out" in one call (the block is cleared on the
+   * stream in front of the kernel). */
   int32_t reset_state;
 } rk_vdt_rollout_t;
 

@@ -118,12 +118,6 @@ RK_DEV void load_veh(const uint4 *blk, int64_t n, int64_t i, Veh &v) {
 #pragma unroll
   for(int w = 0; w < 4; w++) load_motor(blk, n, i, w, v.m[w]);
 }
-// rk_vdt_rollout_t::reset_state: the power-on block (static zero-initialisation) without a pass over d_state -- the same
-// loads, all aimed at one zero cell (no second code path: a branch here costs the hot loop 2 % through ptxas' allocation)
-__device__ const uint4 g_zero_cell = {0u, 0u, 0u, 0u};
-RK_DEV void load_veh_or_reset(const uint4 *blk, int64_t n, int64_t i, Veh &v, bool reset) {
-  load_veh(reset ? &g_zero_cell : blk, reset ? 0 : n, reset ? 0 : i, v);
-}
 RK_DEV void store_veh(uint4 *blk, int64_t n, int64_t i, const Veh &v) {
   st_plane(blk, n, 0, i, make_uint4(f2u(v.pos[0]), f2u(v.pos[1]), f2u(v.pos[2]), v.flags));
   st_plane(blk, n, 1, i, make_uint4(f2u(v.vel[0]), f2u(v.vel[1]), f2u(v.vel[2]), f2u(v.tgt[0])));
