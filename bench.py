@@ -797,7 +797,16 @@ def run_ours_full(a):
         cost_np = np.asarray(cost_np, dtype=np.float32)
         same &= np.array_equal(chunks[c]["cost"].cpu().numpy()[idx].view(np.uint32), cost_np.view(np.uint32))
         if c == n_chunks - 1:
-            spot_last = (idx, cost_np)  # the e2e path must hand back the same costs (it starts every rollout from power-on)
+            # What the e2e path must hand back for this chunk: every e2e rollout starts from the power-on vehicle and a freshly
+            # initialised arm, while the IMU carries on from the end of the previous rollout over the same samples (its last
+            # yaw is what the vehicle holds while the first samples of the table carry no quaternion frame).
+            v2, ar2, tb2 = (np.zeros(w * m, dtype=np.uint32) for w in (layout.VS_WORDS, layout.AS_WORDS, layout.ACMD_WORDS))
+            i2 = i_.copy()
+            ol.arm_batch(kind, "init", ar2, tb2, m)
+            ol.arm_batch(kind, "push", ar2, tb2, m, seq=layout.aos_to_soa(seq_np))
+            _, _, _, cost2 = ol.full_tick(kind, m, T, slow, cmd_np, a.seg_len, np.ascontiguousarray(regs_np[1:]), np.ascontiguousarray(have_np[1:]),
+                                          v2, i2, ar2, tb2, goal=np.zeros((m, 2), dtype=np.float32), nthreads=min(8, host_threads()))
+            spot_last = (idx, np.asarray(cost2, dtype=np.float32))
     same = all_ranks_ok(same, dev)
     spot = (f"{m_total} sampled robots x {T} ticks (vehicle + IMU + arm state, rollout cost) on each of {world} rank(s) "
             f"{'bit-exact' if same else 'MISMATCH'} vs {kind_desc}")
