@@ -297,8 +297,42 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
 // transcription on the same frames.
 // -----------------------------------------------------------------------------------------
 #ifndef RK_STREAM_OCC
-#define RK_STREAM_OCC 3
+#define RK_STREAM_OCC 4
 #endif
+#ifndef RK_STREAM_RING
+#define RK_STREAM_RING 4
+#endif
+// The recorded frames reach each thread through its own ring in shared memory, filled kStreamRing ticks ahead by
+// cp.async (LDGSTS): the HBM latency of a tick's four frames hides behind kStreamRing ticks of arithmetic and costs no
+// registers.  Every thread copies and reads only its own slots ([stage][wheel][thread], conflict-free LDS.64), so
+// threads of a warp that sit in different chunk paths need no barrier between them.
+constexpr int kStreamRing = RK_STREAM_RING;
+struct FrameRing {
+  uint32_t                  base; // shared-memory address of this thread's slot (stage 0, wheel 0)
+  const unsigned long long *src;  // the thread's column of d_frames
+  int64_t                   n;
+  int                       K;
+};
+RK_DEV void frame_ring_issue(const FrameRing &r, int t) { // the four frames of tick t (nothing past the launch); one group per tick
+  if(t < r.K) {
+#pragma unroll
+    for(int k = 0; k < 4; k++) {
+      const uint32_t dst = r.base + (uint32_t)(((t & (kStreamRing - 1)) * 4 + k) * (kFastThreads * 8));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(r.src + ((int64_t)t * 4 + k) * r.n) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+RK_DEV void frame_ring_take(const FrameRing &r, int t, uint64_t fr[4]) { // groups 0..t have landed once all but the last R-1 have
+  asm volatile("cp.async.wait_group %0;" ::"n"(kStreamRing - 1) : "memory");
+#pragma unroll
+  for(int k = 0; k < 4; k++) {
+    const uint32_t src = r.base + (uint32_t)(((t & (kStreamRing - 1)) * 4 + k) * (kFastThreads * 8));
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(src) : "memory");
+    fr[k] = v;
+  }
+}
 template <bool TRACE, int FLAGS>
 __global__ void __launch_bounds__(kFastThreads, RK_STREAM_OCC)
 vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
@@ -322,10 +356,12 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
   sched_init(sch, a);
   YawFeed yf;
   yaw_feed_init(yf, a, n, i);
-  const unsigned long long *fsrc = reinterpret_cast<const unsigned long long *>(a.d_frames) + i;
-  uint64_t                  fpf[4]; // the frames of tick t
+  __shared__ __align__(16) unsigned long long s_ring[kStreamRing * 4 * kFastThreads];
+  FrameRing ring;
+  ring.base = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x), ring.n = n, ring.K = a.steps;
+  ring.src  = reinterpret_cast<const unsigned long long *>(a.d_frames) + i;
 #pragma unroll
-  for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + (int64_t)k * n);
+  for(int s = 0; s < kStreamRing; s++) frame_ring_issue(ring, s);
 
   int t = 0;
   while(t < K) {
@@ -349,12 +385,10 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
             cs = make_float2(cth, sth), sc = make_float2(sth, cth);
           }
           uint64_t fr[4];
-#pragma unroll
-          for(int k = 0; k < 4; k++) fr[k] = fpf[k];
-#pragma unroll
-          for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + ((int64_t)(t + 1) * 4 + k) * n); // t + 1 <= K - 1 inside a chunk
+          frame_ring_take(ring, t, fr);
           float vel[3], tgt[3];
           fast_tick2_stream<FFSAT, TRACE, KD0>(f, ss, fr, p, fc, cs, sc, nz, vel, tgt);
+          frame_ring_issue(ring, t + kStreamRing); // into the stage just read
           trace_row<TRACE>(a.d_trace, n, i, t, f.p.x, f.p.y, pth, vel, tgt, f.w01.cur[0], f.w01.cur[1], f.w23.cur[0], f.w23.cur[1],
                            TRACE ? sched_cnt_at(v.move_cnt, a, sch, t) : 0u);
         }
@@ -366,15 +400,11 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
       if(t == yf.next) yaw_feed_take(yf, a, n, i, s_tab, v.pos[2], cth, sth);
       const int32_t us = ((t + 1) * 1000) & 0x7FFF;
       uint64_t      fr[4];
-#pragma unroll
-      for(int k = 0; k < 4; k++) fr[k] = fpf[k];
-      if(t + 1 < K) {
-#pragma unroll
-        for(int k = 0; k < 4; k++) fpf[k] = __ldcs(fsrc + ((int64_t)(t + 1) * 4 + k) * n);
-      }
+      frame_ring_take(ring, t, fr);
 #pragma unroll
       for(int k = 0; k < 4; k++) motor_rx(v.m[k], p.motor_dir[k], fr[k], us);
       veh_update(v, p, d, cth, sth);
+      frame_ring_issue(ring, t + kStreamRing);
       trace_row<TRACE>(a.d_trace, n, i, t, v.pos[0], v.pos[1], v.pos[2], v.vel, v.tgt, v.m[0].cur_tgt, v.m[1].cur_tgt,
                        v.m[2].cur_tgt, v.m[3].cur_tgt, (a.task_period > 0) ? v.move_cnt : 0u);
       t++;

@@ -214,17 +214,25 @@ RK_DEV void stream_sense_load(StreamSense &ss, const Veh &v) {
 #pragma unroll
   for(int k = 0; k < 4; k++) ss.ang[k] = v.m[k].ang;
 }
+// prmt.b32 with the selector's bit 3 (replicate the byte's sign) -- __byte_perm() only honours three bits per nibble
+RK_DEV int32_t prmt_sx(uint32_t x, uint32_t sel) {
+  int32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(sel));
+  return r;
+}
 template <int DIR>
 RK_DEV void fast_wheel_rx2(StreamSense &ss, int k, int32_t &dsum, uint64_t frame, float &rwf, float &df) {
   const uint32_t lo = (uint32_t)frame;
-  const int32_t  a = sext16((int32_t)(__byte_perm(lo, 0, 0x4401))); // (b0<<8)|b1
-  const int32_t  r = sext16((int32_t)(__byte_perm(lo, 0, 0x4423))); // (b2<<8)|b3
-  const int32_t  raw_ang = (DIR == 1) ? a : sext16(8192 - a);
-  int32_t        d       = sext16(raw_ang - ss.ang[k]);
-  d                      = (d > 4096) ? sext16(d - 8192) : ((d < -4096) ? sext16(d + 8192) : d);
+  // one PRMT each: the big-endian halfword with its sign replicated into the upper bytes (selector bit 3)
+  const int32_t a = prmt_sx(lo, 0x8801); // (int16_t)((b0 << 8) | b1)
+  const int32_t r = prmt_sx(lo, 0xAA23); // (int16_t)((b2 << 8) | b3)
+  const int32_t raw_ang = (DIR == 1) ? a : sext16(8192 - a);
+  int32_t       d       = sext16(raw_ang - ss.ang[k]);
+  // +-8192 once when the step leaves +-4096 (VD_motor_if_m2006.cpp:50-55); d is an int16, so neither sum can wrap
+  d += (d > 4096) ? -8192 : ((d < -4096) ? 8192 : 0);
   dsum += d;
   ss.ang[k] = raw_ang;
-  rwf = (float)sext16(r * DIR), df = (float)d;
+  rwf = (float)((DIR == 1) ? r : sext16(-r)), df = (float)d;
 }
 RK_DEV void from_fast2_stream(Veh &v, const FastVeh2 &f, const StreamSense &ss, int nticks) {
   if(nticks <= 0) return;
