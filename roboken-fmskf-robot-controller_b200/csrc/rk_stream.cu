@@ -12,6 +12,10 @@
 
 #include "rk_common.cuh"
 
+#ifndef RK_STREAM_BLOCK
+#define RK_STREAM_BLOCK 256
+#endif
+
 namespace rk {
 
 RK_DEV uint32_t mix32(uint32_t x) {
@@ -27,10 +31,15 @@ RK_DEV uint32_t h32_prefix(uint32_t seed, uint32_t stream, uint64_t inst) { // t
 }
 RK_DEV uint32_t h32_idx(uint32_t prefix, uint32_t idx) { return mix32(prefix ^ (idx * 0x85EBCA6Bu)); }
 RK_DEV uint32_t sub32(uint32_t h, uint32_t k) { return mix32(h + (k + 1u) * 0x9E3779B9u); }
+// k-th draw under an already mixed hash at a third of sub32's cost (streams.lite32): the per-sample streams use it
+RK_DEV uint32_t lite32(uint32_t h, uint32_t k) {
+  const uint32_t x = (h ^ ((k + 1u) * 0x9E3779B9u)) * 0x85EBCA6Bu;
+  return x ^ (x >> 13);
+}
 RK_DEV float    u01_32(uint32_t h) { return fmul((float)(h >> 8), 1.0f / 16777216.0f); }
 
 // streams.vehicle_commands_v2: [n_seg][n] rk_vdt_cmd_t
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RK_STREAM_BLOCK)
 stream_vehicle_commands_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, int n_seg, uint4 *__restrict__ cmd) {
   const rk_stream_desc_t d = *dd;
   const float four_pi = (float)(4.0 * M_PI), two_pi = (float)(2.0 * M_PI), rl = (float)(6.0 * M_PI);
@@ -84,7 +93,7 @@ stream_vehicle_yaw_reg_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n
 }
 
 // streams.imu_samples_v2 in the cell layout rk_imt_update takes: int16 [n_upd][2][n][8] + have_quat uint8 [n_upd][n]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RK_STREAM_BLOCK)
 stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, int n_upd, uint4 *__restrict__ cells,
                           uint8_t *__restrict__ have) {
   const rk_stream_desc_t d = *dd;
@@ -94,8 +103,8 @@ stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, in
     const uint32_t b = h32_idx(px, d.first_update + (uint32_t)u);
     uint32_t       w[8];
 #pragma unroll
-    for(int k = 0; k < 6; k++) w[k] = sub32(b, (uint32_t)k); // AX..Yaw, two registers a word
-    const uint32_t w6 = sub32(b, 6u), w7 = sub32(b, 7u);
+    for(int k = 0; k < 6; k++) w[k] = lite32(b, (uint32_t)k); // AX..Yaw, two registers a word
+    const uint32_t w6 = lite32(b, 6u), w7 = lite32(b, 7u);
     const uint32_t gu[4] = {w6 & 0xFFFFu, w6 >> 16, w7 & 0xFFFFu, w7 >> 16};
     float          g[4];
 #pragma unroll
@@ -108,13 +117,13 @@ stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, in
     w[6] = q[0] | (q[1] << 16), w[7] = q[2] | (q[3] << 16);
     __stcs(cells + ((int64_t)u * 2 + 0) * n + i, make_uint4(w[0], w[1], w[2], w[3]));
     __stcs(cells + ((int64_t)u * 2 + 1) * n + i, make_uint4(w[4], w[5], w[6], w[7]));
-    if(have) have[(int64_t)u * n + i] = (d.drop_every == 0u || (sub32(b, 8u) % d.drop_every) != 0u) ? 1u : 0u;
+    if(have) have[(int64_t)u * n + i] = (d.drop_every == 0u || (lite32(b, 8u) % d.drop_every) != 0u) ? 1u : 0u;
   }
   }
 }
 
 // streams.arm_sequences_v2 as the SoA slot image rk_adt_push_cmdseq takes: 65 planes of uint4 [n]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RK_STREAM_BLOCK)
 stream_arm_sequences_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, uint4 *__restrict__ img) {
   const rk_stream_desc_t d = *dd;
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -126,16 +135,20 @@ stream_arm_sequences_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, 
   const uint32_t px = h32_prefix(d.seed, 31u, inst);
   uint32_t       dt = 0u;
   for(int k = 0; k < RK_ACMD_MAX_LEN; k++) {
-    const uint32_t b   = h32_idx(px, (uint32_t)k);
-    uint32_t       inc = (sub32(b, 0u) % 991u) + 10u;
-    if((sub32(b, 1u) % 8u) == 0u) inc = 0u;
-    if(z && k == 0) inc = 0u;
-    dt += inc;
-    uint32_t a[5];
+    uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0; // waypoints past the sequence length are zero
+    if((uint32_t)k < ln) {
+      const uint32_t b   = h32_idx(px, (uint32_t)k);
+      uint32_t       inc = (lite32(b, 0u) % 991u) + 10u;
+      if((lite32(b, 1u) % 8u) == 0u) inc = 0u;
+      if(z && k == 0) inc = 0u;
+      dt += inc;
+      uint32_t a[5];
 #pragma unroll
-    for(int j = 0; j < 5; j++) a[j] = f2u(fmul((float)((int32_t)(sub32(b, 2u + (uint32_t)j) % (300u * 64u + 1u)) - 150 * 64), 1.0f / 64.0f));
-    __stcs(img + (int64_t)(1 + 2 * k) * n + i, make_uint4(dt, a[0], a[1], a[2]));
-    __stcs(img + (int64_t)(2 + 2 * k) * n + i, make_uint4(a[3], a[4], 0u, 0u));
+      for(int j = 0; j < 5; j++) a[j] = f2u(fmul((float)((int32_t)(lite32(b, 2u + (uint32_t)j) % (300u * 64u + 1u)) - 150 * 64), 1.0f / 64.0f));
+      w0 = make_uint4(dt, a[0], a[1], a[2]), w1 = make_uint4(a[3], a[4], 0u, 0u);
+    }
+    __stcs(img + (int64_t)(1 + 2 * k) * n + i, w0);
+    __stcs(img + (int64_t)(2 + 2 * k) * n + i, w1);
   }
   }
 }
@@ -149,7 +162,7 @@ int        stream_set_ctas(int v) {
   return RK_OK;
 }
 static unsigned stream_grid(int64_t n) {
-  unsigned g = (unsigned)((n + 255) / 256);
+  unsigned g = (unsigned)((n + RK_STREAM_BLOCK - 1) / RK_STREAM_BLOCK);
   if(g_stream_ctas_per_sm > 0) {
     int dev = 0, sms = 148;
     if(cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -183,7 +196,7 @@ void rk_stream_default_desc(rk_stream_desc_t *d) {
 int rk_stream_vehicle_commands(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_seg, rk_vdt_cmd_t *d_cmd, void *stream) {
   if(n == 0 || n_seg <= 0) return RK_OK;
   if(int rc = stream_check("rk_stream_vehicle_commands", d_desc, d_cmd, n)) return rc;
-  stream_vehicle_commands_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_seg, (uint4 *)d_cmd);
+  stream_vehicle_commands_kernel<<<stream_grid(n), RK_STREAM_BLOCK, 0, (cudaStream_t)stream>>>(d_desc, n, n_seg, (uint4 *)d_cmd);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
@@ -200,7 +213,7 @@ int rk_stream_vehicle_yaw_reg(const rk_stream_desc_t *d_desc, int64_t n, int32_t
 int rk_stream_imu_samples(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat, void *stream) {
   if(n == 0 || n_upd <= 0) return RK_OK;
   if(int rc = stream_check("rk_stream_imu_samples", d_desc, d_regs, n)) return rc;
-  stream_imu_samples_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(d_desc, n, n_upd, (uint4 *)d_regs, d_have_quat);
+  stream_imu_samples_kernel<<<stream_grid(n), RK_STREAM_BLOCK, 0, (cudaStream_t)stream>>>(d_desc, n, n_upd, (uint4 *)d_regs, d_have_quat);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }
@@ -208,7 +221,7 @@ int rk_stream_imu_samples(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_u
 int rk_stream_arm_sequences(const rk_stream_desc_t *d_desc, int64_t n, void *d_seq, void *stream) {
   if(n == 0) return RK_OK;
   if(int rc = stream_check("rk_stream_arm_sequences", d_desc, d_seq, n)) return rc;
-  stream_arm_sequences_kernel<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(d_desc, n, (uint4 *)d_seq);
+  stream_arm_sequences_kernel<<<stream_grid(n), RK_STREAM_BLOCK, 0, (cudaStream_t)stream>>>(d_desc, n, (uint4 *)d_seq);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }

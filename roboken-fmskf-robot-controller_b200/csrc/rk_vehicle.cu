@@ -202,7 +202,13 @@ RK_DEV void yaw_feed_take(YawFeed &y, const rk_vdt_rollout_t &a, int64_t n, int6
 
 // FLAGS: bit 0 FFSAT (ff_limit == 1: FMUL.SAT form of the feed-forward clamp), bit 1 KD0 (kd == 0, packed tick only)
 template <bool TRACE, int OCC, int FLAGS, bool PACKED>
+#if defined(RK_FAST_MAXNREG) // tuning builds: the register budget given directly (finer occupancy steps with small CTAs)
+__global__ void __maxnreg__(RK_FAST_MAXNREG)
+#elif defined(RK_FAST_MINBLOCKS)
+__global__ void __launch_bounds__(kFastThreads, RK_FAST_MINBLOCKS)
+#else
 __global__ void __launch_bounds__(kFastThreads, OCC * 128 / kFastThreads)
+#endif
 vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
   constexpr int  D0 = 1, D1 = 1, D2 = -1, D3 = -1; // VD_task_main.cpp:75-78 (host checks params match)
   constexpr bool FFSAT = (FLAGS & 1) != 0, KD0 = (FLAGS & 2) != 0;

@@ -409,6 +409,14 @@ def sub32(h, k):
         return mix32(np.asarray(h, dtype=np.uint32) + _U32(((k + 1) * 0x9E3779B9) & 0xFFFFFFFF))
 
 
+def lite32(h, k):
+    """k-th draw under one (already mixed) hash at a third of sub32's cost: one xor, one odd multiply, one xor-shift.
+    The per-sample streams (IMU registers, arm waypoints) use it; 16.8 M robots x 100 samples are expanded per pass."""
+    with np.errstate(over="ignore"):
+        x = (np.asarray(h, dtype=np.uint32) ^ _U32(((k + 1) * 0x9E3779B9) & 0xFFFFFFFF)) * _U32(0x85EBCA6B)
+    return x ^ (x >> _U32(13))
+
+
 def _u01_32(h):
     """24-bit uniform in [0,1) as exact float32."""
     return (np.asarray(h, dtype=np.uint32) >> _U32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
@@ -458,7 +466,7 @@ def vehicle_yaw_reg_v2(n, n_yaw, seed=0x5EED, first=0, inst=None):
 
 def imu_samples_v2(n, n_upd, seed=0x5EED, first=0, drop_every=64, inst=None, first_update=0):
     """imu_samples() on the 32-bit hash: int16 [n_upd, 16, n] (+ have_quat uint8 [n_upd, n]).  One hash per
-    (IMU, update); its draws 0-5 are AX..Yaw two registers a word, 6-7 four 16-bit uniforms in (-1, 1) normalised in
+    (IMU, update); its lite32 draws 0-5 are AX..Yaw two registers a word, 6-7 four 16-bit uniforms in (-1, 1) normalised in
     float32 (IEEE sqrt / division, fixed order) to a unit quaternion x 32767 (rounded half to even), 8 the
     missing-quaternion-frame flag."""
     inst = _inst(n, first, inst)[None, :]
@@ -466,10 +474,10 @@ def imu_samples_v2(n, n_upd, seed=0x5EED, first=0, drop_every=64, inst=None, fir
     b = h32(seed, 20, inst, u)  # [n_upd, n]
     regs = np.zeros((n_upd, 16, b.shape[1]), dtype=np.int16)
     for k in range(6):
-        w = sub32(b, k)
+        w = lite32(b, k)
         regs[:, 2 * k, :] = (w & _U32(0xFFFF)).astype(np.uint16).view(np.int16)
         regs[:, 2 * k + 1, :] = (w >> _U32(16)).astype(np.uint16).view(np.int16)
-    w6, w7 = sub32(b, 6), sub32(b, 7)
+    w6, w7 = lite32(b, 6), lite32(b, 7)
     f32 = np.float32
     g = [((x.astype(np.float32) + f32(0.5)) * f32(1.0 / 32768.0)) - f32(1.0) for x in (w6 & _U32(0xFFFF), w6 >> _U32(16), w7 & _U32(0xFFFF), w7 >> _U32(16))]
     nrm = np.sqrt(((g[0] * g[0] + g[1] * g[1]) + g[2] * g[2]) + g[3] * g[3], dtype=np.float32)
@@ -477,14 +485,14 @@ def imu_samples_v2(n, n_upd, seed=0x5EED, first=0, drop_every=64, inst=None, fir
     for k in range(4):
         regs[:, 12 + k, :] = np.rint(g[k] * sc).astype(np.int16)
     if drop_every:
-        have = ((sub32(b, 8) % _U32(drop_every)) != 0).astype(np.uint8)
+        have = ((lite32(b, 8) % _U32(drop_every)) != 0).astype(np.uint8)
     else:
         have = np.ones(b.shape, dtype=np.uint8)
     return regs, np.ascontiguousarray(have)
 
 
 def arm_sequences_v2(n, seed=0x5EED, first=0, max_len=32, min_len=2, seq_id=1, dt_zero_every=4, inst=None):
-    """arm_sequences() on the 32-bit hash: uint32 [n, 260] slot images."""
+    """arm_sequences() on the 32-bit hash: uint32 [n, 260] slot images; waypoints past the sequence length are zero."""
     inst = _inst(n, first, inst)
     m = len(inst)
     k = np.arange(32, dtype=np.uint64)[None, :]
@@ -492,8 +500,8 @@ def arm_sequences_v2(n, seed=0x5EED, first=0, max_len=32, min_len=2, seq_id=1, d
     ln = (sub32(b0, 0) % _U32(max_len - min_len + 1)).astype(np.int64) + min_len
     z = (sub32(b0, 1) % _U32(dt_zero_every)) == 0
     b = h32(seed, 31, inst[:, None], k)  # [m, 32]
-    inc = (sub32(b, 0) % _U32(991)).astype(np.int64) + 10
-    inc[(sub32(b, 1) % _U32(8)) == 0] = 0
+    inc = (lite32(b, 0) % _U32(991)).astype(np.int64) + 10
+    inc[(lite32(b, 1) % _U32(8)) == 0] = 0
     inc[z, 0] = 0
     dt = np.cumsum(inc, axis=1)
     img = np.zeros((m, 260), dtype=np.uint32)
@@ -502,6 +510,7 @@ def arm_sequences_v2(n, seed=0x5EED, first=0, max_len=32, min_len=2, seq_id=1, d
     wp = img[:, 4:].reshape(m, 32, 8)
     wp[:, :, 0] = dt.astype(np.uint32)
     for j in range(5):
-        q = (sub32(b, 2 + j) % _U32(300 * 64 + 1)).astype(np.int64) - 150 * 64
+        q = (lite32(b, 2 + j) % _U32(300 * 64 + 1)).astype(np.int64) - 150 * 64
         wp[:, :, 1 + j] = (q.astype(np.float32) * np.float32(1.0 / 64.0)).view(np.uint32)
+    wp[np.arange(32)[None, :] >= ln[:, None]] = 0
     return img
