@@ -279,6 +279,9 @@ RK_DEV void loop_store(uint4 *st, int64_t n, int64_t i, const ArmLoop &a, uint32
   for(int s = 0; s < 3; s++) st_plane(st, n, (RK_AS_BLDC_TX0 + 4 * s) / 4, i, make_uint4(a.bl0[s], a.bl1[s], a.bl2[s], 1u));
 }
 
+#ifndef RK_ARM_PEEL
+#define RK_ARM_PEEL 1
+#endif
 struct ArmConsts { // loop invariants derived from params + flags once per launch
   float    gear_p2, gear_r0, gear_dir[3], dir_y0, mg_ctrl_time, mg_rcp;
   uint32_t bl_ms[3];
@@ -410,10 +413,10 @@ __device__ __noinline__ MgFrame mg_update_slow(MgFrame f, float tgt, float ctrl_
   return f;
 }
 
-template <int DIVC, bool MGSLOW, bool LAZY_Y0 = false>
+template <int DIVC, bool MGSLOW, bool LAZY_Y0 = false, bool STEADY = false>
 RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i);
 
-template <int DIVC, bool MGSLOW>
+template <int DIVC, bool MGSLOW, bool STEADY = false>
 RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
   if(a.state != RK_ASTATE_MOVING) loop_fsm_transitions(a, p, tab, n, i);
   // ---- exec_moving :89-117
@@ -423,7 +426,7 @@ RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, 
   a.cmd_idx      = fin ? ((a.cmd_idx + 1) & 0xFFu) : a.cmd_idx;
   a.state        = fin ? (uint32_t)RK_ASTATE_MOVE_START : a.state;
   a.cyc          = (moving && !fin) ? a.cyc + 1 : a.cyc;
-  loop_joints<DIVC, MGSLOW, true>(a, p, c, st, n, i);
+  loop_joints<DIVC, MGSLOW, true, STEADY>(a, p, c, st, n, i);
 }
 
 // ADT::main's joint updates (AD_task_main.cpp:213-228): j_P1, j_DF_Left, j_DF_Right, j_P3, [CAN tx], j_Y0
@@ -434,12 +437,14 @@ RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, 
 // ADTModePositioningSeq's tick -- the mode measures from the targets -- so the sequence kernel only remembers the last
 // answer (y0_pos, y0_seen) and converts it once after its last tick (loop_finish_y0); ADTModePositioning measures
 // from get_now_deg() and keeps the eager form.
-template <int DIVC, bool MGSLOW, bool LAZY_Y0>
+// STEADY: not the first tick of the launch -- is_torque_on_prev already equals is_torque_on (a launch invariant), so the
+// torque-edge logic of the three MyBldc joints and of the MG joint folds into per-launch constants.
+template <int DIVC, bool MGSLOW, bool LAZY_Y0, bool STEADY>
 RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i) {
   // ---- JointMgServo::update -> subproc_posctrl  AD_joint_mg_servo.cpp:50-73,136-149
   if(MGSLOW) {
     MgFrame f = {a.mg_tx0, a.mg_tx1, a.mg_valid};
-    f         = mg_update_slow(f, a.tgt[1], c.mg_ctrl_time, a.mg_prev, c.mg_on, c.mg_ini, st, n, i);
+    f         = mg_update_slow(f, a.tgt[1], c.mg_ctrl_time, STEADY ? c.mg_on : a.mg_prev, c.mg_on, c.mg_ini, st, n, i);
     a.mg_tx0 = f.tx0, a.mg_tx1 = f.tx1, a.mg_valid = f.valid;
     a.mg_prev = c.mg_on;
     a.mg_pre  = a.tgt[1];
@@ -472,10 +477,11 @@ RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c
     const int32_t  ang   = f2i_x86(fmul(fmul(fmul(tg, p.gear_ratio[s == 0 ? RK_AJ_DFL : s == 1 ? RK_AJ_DFR : RK_AJ_P3]),
                                              p.motor_dir[s == 0 ? RK_AJ_DFL : s == 1 ? RK_AJ_DFR : RK_AJ_P3]), 65536.0f));
     const uint32_t clq   = (uint32_t)f2i_x86(fmul(cl, 256.0f)) & 0xFFFFu;
-    const bool     drive = c.bl_on[s] && a.bl_prev[s];
+    const bool     prev  = STEADY ? c.bl_on[s] : a.bl_prev[s];
+    const bool     drive = c.bl_on[s] && prev;
     a.bl0[s]     = drive ? (uint32_t)ang : 0u;
     a.bl1[s]     = drive ? (c.bl_ms[s] | (clq << 16)) : 0u;
-    a.bl2[s]     = !c.bl_on[s] ? 0x8002u : (a.bl_prev[s] ? 0x8010u : 0x8001u);
+    a.bl2[s]     = !c.bl_on[s] ? 0x8002u : (prev ? 0x8010u : 0x8001u);
     a.bl_prev[s] = c.bl_on[s];
   }
   // ---- JointIcsServo::update  AD_joint_ics_servo.cpp:5-29 over the ideal servo
@@ -553,8 +559,12 @@ RK_DEV void adt_update_body(int64_t i, const rk_adt_params_t &p, uint4 *__restri
     a.pf_key = ring_key(fs, fi);
   }
   if(c.mg_pos) {
-    for(int t = 0; t < K; t++) {
-      loop_tick<DIVC, false>(a, p, c, state, tab, n, i);
+    if(K > 0) { // the first tick sees the stored is_torque_on_prev flags, the others run on launch constants (STEADY)
+      loop_tick<DIVC, false, false>(a, p, c, state, tab, n, i);
+      if(TRACE) arm_trace_row(trace + i, n, a, a.state, a.cmd_idx);
+    }
+    for(int t = 1; t < K; t++) {
+      loop_tick<DIVC, false, RK_ARM_PEEL != 0>(a, p, c, state, tab, n, i);
       if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, a.state, a.cmd_idx);
     }
   } else {
