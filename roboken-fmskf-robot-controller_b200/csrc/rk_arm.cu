@@ -133,6 +133,7 @@ struct ArmLoop {
   float    tgt[5], tgt_dfl, tgt_dfr; // fl_raw_tgt_deg of the same
   float    cl_dfl, cl_dfr, cl_p3;    // fl_curlim_A of the three MyBldc joints
   float    now_y0, mg_pre;
+  float    mg_pp; // LAZY_MG: f_pre_tgt_deg as it stood before the last tick
   int32_t  y0_pos;  // LAZY_Y0: the position word of the ICS servo's last answer, converted after the last tick
   bool     y0_seen;
   uint32_t ics_pos, ics_servo, mg_tx0, mg_tx1, mg_valid;
@@ -279,6 +280,12 @@ RK_DEV void loop_store(uint4 *st, int64_t n, int64_t i, const ArmLoop &a, uint32
   for(int s = 0; s < 3; s++) st_plane(st, n, (RK_AS_BLDC_TX0 + 4 * s) / 4, i, make_uint4(a.bl0[s], a.bl1[s], a.bl2[s], 1u));
 }
 
+#ifndef RK_ARM_LAZY_TGT
+#define RK_ARM_LAZY_TGT 1
+#endif
+#ifndef RK_ARM_LAZY_MG
+#define RK_ARM_LAZY_MG 1
+#endif
 #ifndef RK_ARM_PEEL
 #define RK_ARM_PEEL 1
 #endif
@@ -413,20 +420,35 @@ __device__ __noinline__ MgFrame mg_update_slow(MgFrame f, float tgt, float ctrl_
   return f;
 }
 
-template <int DIVC, bool MGSLOW, bool LAZY_Y0 = false, bool STEADY = false>
+template <int DIVC, bool MGSLOW, bool LAZY_Y0 = false, bool STEADY = false, bool LAZY_MG = false>
 RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i);
 
-template <int DIVC, bool MGSLOW, bool STEADY = false>
-RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, const uint4 *__restrict__ tab, int64_t n, int64_t i) {
+// LAZY_TGT: inside a segment the five targets are a pure function of the segment's constants and the tick count
+// (now_cmd_ - move * rem + offset), and between two segment ends only the ICS joint (axis 0, which converts its target
+// every tick) looks at them: exec_move_start measures the next segment from the targets of the tick that ENDED the
+// previous one, the MyBldc / MG frames and the stored block need those of the launch's last ticks.  So axes 1..4 and the
+// differential are formed on the ticks that end a segment and on the last two ticks of the launch (`eager`), with the
+// same operations on the same operands.  Not with a trace attached, nor for an MG joint in torque control (its PI_D
+// consumes the target every tick).
+template <int DIVC, bool MGSLOW, bool STEADY = false, bool LAZY_MG = false, bool LAZY_TGT = false>
+RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, const uint4 *__restrict__ tab, int64_t n, int64_t i,
+                      bool eager = true) {
   if(a.state != RK_ASTATE_MOVING) loop_fsm_transitions(a, p, tab, n, i);
   // ---- exec_moving :89-117
-  const bool moving = a.state == RK_ASTATE_MOVING;
-  loop_set_targets(a, c, moving, (float)(a.cnt - a.cyc), a.now_tgt, a.move);
-  const bool fin = moving && (a.cnt <= a.cyc);
+  const bool  moving = a.state == RK_ASTATE_MOVING;
+  const bool  fin    = moving && (a.cnt <= a.cyc);
+  const float rem    = (float)(a.cnt - a.cyc);
+  if(LAZY_TGT) {
+    const float raw0 = fadd(fsub(a.now_tgt[0], fmul(a.move[0], rem)), a.ofs[0]);
+    a.tgt[0]         = moving ? raw0 : a.tgt[0];
+    if(fin || eager) loop_set_targets(a, c, moving, rem, a.now_tgt, a.move);
+  } else {
+    loop_set_targets(a, c, moving, rem, a.now_tgt, a.move);
+  }
   a.cmd_idx      = fin ? ((a.cmd_idx + 1) & 0xFFu) : a.cmd_idx;
   a.state        = fin ? (uint32_t)RK_ASTATE_MOVE_START : a.state;
   a.cyc          = (moving && !fin) ? a.cyc + 1 : a.cyc;
-  loop_joints<DIVC, MGSLOW, true, STEADY>(a, p, c, st, n, i);
+  loop_joints<DIVC, MGSLOW, true, STEADY, LAZY_MG>(a, p, c, st, n, i);
 }
 
 // ADT::main's joint updates (AD_task_main.cpp:213-228): j_P1, j_DF_Left, j_DF_Right, j_P3, [CAN tx], j_Y0
@@ -439,7 +461,33 @@ RK_DEV void loop_tick(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, 
 // from get_now_deg() and keeps the eager form.
 // STEADY: not the first tick of the launch -- is_torque_on_prev already equals is_torque_on (a launch invariant), so the
 // torque-edge logic of the three MyBldc joints and of the MG joint folds into per-launch constants.
-template <int DIVC, bool MGSLOW, bool LAZY_Y0, bool STEADY>
+// LAZY_MG: the MG joint's position-control frame (0xA4: velocity limit from the step since the last target, position)
+// is a function of this tick's target and the previous one only, and nobody reads it inside the launch unless a trace
+// is attached -- the loop carries the two targets and loop_finish_mg() forms the frame of the last tick once.
+template <int DIVC>
+RK_DEV void mg_posctrl_frame(ArmLoop &a, const ArmConsts &c, float tgt, float pre) {
+  const float d = fsub(tgt, pre);
+  float       q;
+  if(DIVC == 2) {
+    q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
+  } else if(DIVC == 1) { // proven for zero and 2^-40 <= |d| <= 2^64; anything else takes the IEEE division
+    const float ad = fabsf(d);
+    if(d == 0.0f || (ad >= 9.094947017729282e-13f && ad <= 18446744073709551616.0f)) q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
+    else q = fdiv(d, c.mg_ctrl_time);
+  } else { // 0 / c = 0 with the numerator's sign for c > 0; keeps an idle joint off the division's slow path
+    q = (d == 0.0f && c.mg_ctrl_time > 0.0f) ? d : fdiv(d, c.mg_ctrl_time);
+  }
+  const float    v  = fabsf(fmul(q, -10.0f));
+  const uint32_t vl = (uint32_t)f2i_x86((v > 1800.0f) ? 1800.0f : v) & 0xFFFFu;
+  const uint32_t w1 = (uint32_t)f2i_x86(fmul(tgt, -100.0f * 10.0f));
+  a.mg_tx0   = 0xA4u | (vl << 16);
+  a.mg_tx1   = w1;
+  a.mg_valid = 1u;
+}
+template <int DIVC>
+RK_DEV void loop_finish_mg(ArmLoop &a, const ArmConsts &c) { mg_posctrl_frame<DIVC>(a, c, a.mg_pre, a.mg_pp); }
+
+template <int DIVC, bool MGSLOW, bool LAZY_Y0, bool STEADY, bool LAZY_MG>
 RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c, uint4 *st, int64_t n, int64_t i) {
   // ---- JointMgServo::update -> subproc_posctrl  AD_joint_mg_servo.cpp:50-73,136-149
   if(MGSLOW) {
@@ -448,26 +496,12 @@ RK_DEV void loop_joints(ArmLoop &a, const rk_adt_params_t &p, const ArmConsts &c
     a.mg_tx0 = f.tx0, a.mg_tx1 = f.tx1, a.mg_valid = f.valid;
     a.mg_prev = c.mg_on;
     a.mg_pre  = a.tgt[1];
+  } else if(LAZY_MG) {
+    a.mg_pp  = a.mg_pre;
+    a.mg_pre = a.tgt[1];
   } else {
-    const float tgt = a.tgt[1];
-    const float d   = fsub(tgt, a.mg_pre);
-    float q;
-    if(DIVC == 2) {
-      q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
-    } else if(DIVC == 1) { // proven for zero and 2^-40 <= |d| <= 2^64; anything else takes the IEEE division
-      const float ad = fabsf(d);
-      if(d == 0.0f || (ad >= 9.094947017729282e-13f && ad <= 18446744073709551616.0f)) q = div_const(d, c.mg_ctrl_time, c.mg_rcp);
-      else q = fdiv(d, c.mg_ctrl_time);
-    } else { // 0 / c = 0 with the numerator's sign for c > 0; keeps an idle joint off the division's slow path
-      q = (d == 0.0f && c.mg_ctrl_time > 0.0f) ? d : fdiv(d, c.mg_ctrl_time);
-    }
-    const float v   = fabsf(fmul(q, -10.0f));
-    const uint32_t vl = (uint32_t)f2i_x86((v > 1800.0f) ? 1800.0f : v) & 0xFFFFu;
-    const uint32_t w1 = (uint32_t)f2i_x86(fmul(tgt, -100.0f * 10.0f));
-    a.mg_tx0   = 0xA4u | (vl << 16);
-    a.mg_tx1   = w1;
-    a.mg_valid = 1u;
-    a.mg_pre   = tgt;
+    mg_posctrl_frame<DIVC>(a, c, a.tgt[1], a.mg_pre);
+    a.mg_pre = a.tgt[1];
   }
   // ---- JointMyBldcServo::update x3  AD_joint_mybldc_servo.cpp:7-36
 #pragma unroll
@@ -559,14 +593,16 @@ RK_DEV void adt_update_body(int64_t i, const rk_adt_params_t &p, uint4 *__restri
     a.pf_key = ring_key(fs, fi);
   }
   if(c.mg_pos) {
+    constexpr bool LZ = RK_ARM_LAZY_MG && !TRACE, LT = RK_ARM_LAZY_TGT && LZ;
     if(K > 0) { // the first tick sees the stored is_torque_on_prev flags, the others run on launch constants (STEADY)
-      loop_tick<DIVC, false, false>(a, p, c, state, tab, n, i);
+      loop_tick<DIVC, false, false, LZ, LT>(a, p, c, state, tab, n, i, K <= 2);
       if(TRACE) arm_trace_row(trace + i, n, a, a.state, a.cmd_idx);
     }
     for(int t = 1; t < K; t++) {
-      loop_tick<DIVC, false, RK_ARM_PEEL != 0>(a, p, c, state, tab, n, i);
+      loop_tick<DIVC, false, RK_ARM_PEEL != 0, LZ, LT>(a, p, c, state, tab, n, i, t >= K - 2);
       if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, a.state, a.cmd_idx);
     }
+    if(LZ && K > 0) loop_finish_mg<DIVC>(a, c);
   } else {
 #pragma unroll 1
     for(int t = 0; t < K; t++) {

@@ -91,6 +91,29 @@ def test_arm_random_states_vs_port():
     assert_same(gpu_script(n, script, st0, tab), run_script("port", n, script, st0, tab))
 
 
+@pytest.mark.parametrize("mg_any", [False, True])
+def test_arm_untraced_launches_of_any_length_vs_port(mg_any):
+    """The kernel WITHOUT a trace attached (what rk_tick_rollout and the bench launch) forms values nobody can read inside
+    a launch lazily -- the MG position frame once after the last tick, targets of axes 1..4 on ticks that end a segment and
+    on the last two ticks, the torque-edge logic from the second tick on.  Launch lengths 1, 2, 3, ... from random mid-move
+    states (and with MG joints in every control branch) must leave the same block as the port after every launch."""
+    n = 2500
+    st0 = random_arm_states(n, seed=11, mg_any_branch=mg_any)
+    taos = np.zeros((n, layout.ACMD_WORDS), dtype=np.uint32)
+    for s in range(4):
+        taos[:, s * 260 : (s + 1) * 260] = streams.arm_sequences(n, seed=40 + s, seq_id=s + 1, max_len=6)
+    tab = layout.aos_to_soa(taos)
+    ab = ArmBatch(n, DEV)
+    ab.load_state_soa(st0, tab)
+    es, et = st0.copy(), tab.copy()
+    for K in (1, 1, 2, 3, 2, 5, 1, 17, 64, 2, 1, 200):
+        ab.update(K)
+        torch.cuda.synchronize()
+        ol.arm_batch("port", "update", es, et, n, K=K)
+        np.testing.assert_array_equal(ab.state_host(), es, err_msg=f"after a launch of {K} ticks")
+    np.testing.assert_array_equal(ab.cmdtab_host(), et)
+
+
 def test_mg_torque_control_branches_vs_port():
     """Every flag combination of the MG joint: PI_D reset on the torque-off edge, torque control while not
     initialised / limp (CMSIS sine, double-precision current->raw map), position control."""
