@@ -280,6 +280,12 @@ RK_DEV void loop_store(uint4 *st, int64_t n, int64_t i, const ArmLoop &a, uint32
   for(int s = 0; s < 3; s++) st_plane(st, n, (RK_AS_BLDC_TX0 + 4 * s) / 4, i, make_uint4(a.bl0[s], a.bl1[s], a.bl2[s], 1u));
 }
 
+// Unroll of the tick loop.  Alone, 4 ticks per iteration is fastest (5.40 -> 5.09 ms per 2^20 x 1000); beside the vehicle
+// rollout of rk_tick_rollout the larger loop loses far more in the shared instruction caches than it gains (full tick
+// 162.6 -> 188.5 ms per pass), so a capped launch (max_ctas > 0: the side stream) runs the rolled instantiation.
+#ifndef RK_ARM_UNROLL
+#define RK_ARM_UNROLL 4
+#endif
 #ifndef RK_ARM_LAZY_TGT
 #define RK_ARM_LAZY_TGT 1
 #endif
@@ -573,7 +579,7 @@ RK_DEV void arm_trace_row(uint32_t *tr, int64_t n, const ArmLoop &a, uint32_t w1
   tr[14 * n] = 0u, tr[15 * n] = 0u;
 }
 
-template <bool TRACE, int DIVC>
+template <bool TRACE, int DIVC, int UNROLL>
 RK_DEV void adt_update_body(int64_t i, const rk_adt_params_t &p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
                             uint32_t *__restrict__ trace, float mg_rcp) {
   ArmLoop  a;
@@ -598,6 +604,7 @@ RK_DEV void adt_update_body(int64_t i, const rk_adt_params_t &p, uint4 *__restri
       loop_tick<DIVC, false, false, LZ, LT>(a, p, c, state, tab, n, i, K <= 2);
       if(TRACE) arm_trace_row(trace + i, n, a, a.state, a.cmd_idx);
     }
+#pragma unroll UNROLL
     for(int t = 1; t < K; t++) {
       loop_tick<DIVC, false, RK_ARM_PEEL != 0, LZ, LT>(a, p, c, state, tab, n, i, t >= K - 2);
       if(TRACE) arm_trace_row(trace + (int64_t)t * RK_ADT_TRACE_WORDS * n + i, n, a, a.state, a.cmd_idx);
@@ -617,12 +624,12 @@ RK_DEV void adt_update_body(int64_t i, const rk_adt_params_t &p, uint4 *__restri
 #ifndef RK_ARM_OCC
 #define RK_ARM_OCC 5
 #endif
-template <bool TRACE, int DIVC>
+template <bool TRACE, int DIVC, int UNROLL = 1>
 __global__ void __launch_bounds__(128, RK_ARM_OCC)
 adt_update_kernel(const rk_adt_params_t p, uint4 *__restrict__ state, const uint4 *__restrict__ tab, int64_t n, int K,
                   uint32_t *__restrict__ trace, float mg_rcp) {
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    adt_update_body<TRACE, DIVC>(i, p, state, tab, n, K, trace, mg_rcp);
+    adt_update_body<TRACE, DIVC, UNROLL>(i, p, state, tab, n, K, trace, mg_rcp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1298,10 +1305,17 @@ int rk::adt_update_launch(const rk_adt_params_t *p, void *d_state, const void *d
     if(divc == 2) RK_LAUNCH_ADT(true, 2);
     else if(divc == 1) RK_LAUNCH_ADT(true, 1);
     else RK_LAUNCH_ADT(true, 0);
-  } else {
+  } else if(max_ctas > 0) { // beside another kernel: the rolled loop (see RK_ARM_UNROLL)
     if(divc == 2) RK_LAUNCH_ADT(false, 2);
     else if(divc == 1) RK_LAUNCH_ADT(false, 1);
     else RK_LAUNCH_ADT(false, 0);
+  } else {
+#define RK_LAUNCH_ADT_U(DV) \
+  adt_update_kernel<false, DV, RK_ARM_UNROLL><<<grid, 128, 0, st>>>(*p, (uint4 *)d_state, (const uint4 *)d_cmdtab, n, K, d_trace, rcp)
+    if(divc == 2) RK_LAUNCH_ADT_U(2);
+    else if(divc == 1) RK_LAUNCH_ADT_U(1);
+    else RK_LAUNCH_ADT_U(0);
+#undef RK_LAUNCH_ADT_U
   }
 #undef RK_LAUNCH_ADT
   RK_CUDA(cudaGetLastError());
