@@ -288,6 +288,11 @@ RK_DEV void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) 
 // the bytes have landed, empty[s] when the four warps have taken their cells out of the stage.
 constexpr int kWireStages = 16;
 
+// NC4: every update brings four cells (the 55-byte WT901 burst of one 100 Hz period fits).  The update's 16 words are
+// then in registers at once, and the frames that sit back to back from the start of the update -- the healthy case --
+// are taken at STATIC byte offsets 0, 11, 22, 33, 44 (wit_try_frame on constant funnel shifts); whatever does not fit
+// that pattern goes through the same byte-exact generic path as before.
+template <bool NC4>
 __global__ void __launch_bounds__(128)
 imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int64_t n, int K, int ncells, const uint4 *__restrict__ cells,
                       const uint16_t *__restrict__ nbytes, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init, float nz_src) {
@@ -347,7 +352,7 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
   const float nz    = fmul(-0.0f, nz_src);
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   // two cells in registers: A is being parsed, B follows it (a frame may straddle into it)
-  uint4    B = total > 0 ? fetch(0) : zero4;
+  uint4    B = (!NC4 && total > 0) ? fetch(0) : zero4; // (generic path: cell t is in B when its update starts)
   int64_t  t = 0;
   uint32_t nb_next = (nbytes && K > 0 && live) ? (uint32_t)__ldcs(nbytes + i) : 0xFFFFFFFFu;
   for(int u = 0; u < K; u++) {
@@ -359,6 +364,50 @@ imt_feed_bytes_kernel(uint4 *__restrict__ state, uint4 *__restrict__ parser, int
     const uint32_t nb = live ? min(nb_next, 16u * (uint32_t)ncells) : 0u; // bytes on the wire in this update
     if(nbytes && live && u + 1 < K) nb_next = (uint32_t)__ldcs(nbytes + (int64_t)(u + 1) * n + i); // consumed an update later
     uint32_t done = 0u; // bytes of this update already parsed
+    if(NC4) {
+      uint32_t w[17]; // the update's 64 bytes (+ a zero word for the shifts at the end)
+#pragma unroll
+      for(int c = 0; c < 4; c++) {
+        const uint4 v = fetch(t++);
+        w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
+      }
+      w[16] = 0u;
+#pragma unroll
+      for(int f = 0; f < 5; f++) { // frame f at byte 11 f, as long as the frames before it were taken whole
+        const int  wi = (11 * f) >> 2, sh = 8 * ((11 * f) & 3);
+        const bool can = p.cnt == 0u && done == 11u * (uint32_t)f && nb >= 11u * (uint32_t)(f + 1);
+        if(can && wit_try_frame(p, __funnelshift_r(w[wi], w[wi + 1], sh), __funnelshift_r(w[wi + 1], w[wi + 2], sh),
+                                __funnelshift_r(w[wi + 2], w[wi + 3], sh)))
+          done += 11u;
+      }
+      if(done < nb) { // the rest, byte-exact: cell c = words 4c .. 4c + 3, looked up with selects (static register indices)
+        for(int c = 0; c < 4; c++) {
+          uint4 A, Bc;
+          A.x = c == 0 ? w[0] : (c == 1 ? w[4] : (c == 2 ? w[8] : w[12])), A.y = c == 0 ? w[1] : (c == 1 ? w[5] : (c == 2 ? w[9] : w[13]));
+          A.z = c == 0 ? w[2] : (c == 1 ? w[6] : (c == 2 ? w[10] : w[14])), A.w = c == 0 ? w[3] : (c == 1 ? w[7] : (c == 2 ? w[11] : w[15]));
+          Bc.x = c == 0 ? w[4] : (c == 1 ? w[8] : (c == 2 ? w[12] : 0u)), Bc.y = c == 0 ? w[5] : (c == 1 ? w[9] : (c == 2 ? w[13] : 0u));
+          Bc.z = c == 0 ? w[6] : (c == 1 ? w[10] : (c == 2 ? w[14] : 0u)), Bc.w = c == 0 ? w[7] : (c == 1 ? w[11] : (c == 2 ? w[15] : 0u));
+          const uint32_t lo = 16u * (uint32_t)c, end = min(nb, lo + 16u);
+          const uint32_t span = min(nb, (c + 1 < 4) ? lo + 32u : lo + 16u);
+          while(done < end) {
+            const uint32_t off = done - lo, wi = off >> 2, sh = 8u * (off & 3u);
+            const uint32_t x0 = wi == 0u ? A.x : (wi == 1u ? A.y : (wi == 2u ? A.z : A.w));
+            if(p.cnt == 0u && span - done >= 11u) {
+              const uint32_t x1 = wi == 0u ? A.y : (wi == 1u ? A.z : (wi == 2u ? A.w : Bc.x));
+              const uint32_t x2 = wi == 0u ? A.z : (wi == 1u ? A.w : (wi == 2u ? Bc.x : Bc.y));
+              const uint32_t x3 = wi == 0u ? A.w : (wi == 1u ? Bc.x : (wi == 2u ? Bc.y : Bc.z));
+              if(wit_try_frame(p, __funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh))) {
+                done += 11u;
+                continue;
+              }
+            }
+            const uint32_t k = min(4u - (off & 3u), end - done);
+            wit_bytes(p, x0 >> sh, k);
+            done += k;
+          }
+        }
+      }
+    } else
     for(int c = 0; c < ncells; c++) {
       const uint4 A = B;
       t++;
@@ -489,9 +538,13 @@ int rk_imt_feed_bytes(void *d_state, void *d_parser, int64_t n, int32_t K, int32
     return RK_ERR_ARG;
   }
   if(int rc = require_device()) return rc;
-  imt_feed_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4 *)d_state, (uint4 *)d_parser, n, K, ncells,
-                                                                                       (const uint4 *)d_cells, d_nbytes, (float4 *)d_out,
-                                                                                       d_yaw_rad, do_init, 1.0f);
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if(ncells == 4)
+    imt_feed_bytes_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>((uint4 *)d_state, (uint4 *)d_parser, n, K, ncells, (const uint4 *)d_cells,
+                                                                       d_nbytes, (float4 *)d_out, d_yaw_rad, do_init, 1.0f);
+  else
+    imt_feed_bytes_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>((uint4 *)d_state, (uint4 *)d_parser, n, K, ncells, (const uint4 *)d_cells,
+                                                                        d_nbytes, (float4 *)d_out, d_yaw_rad, do_init, 1.0f);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
 }

@@ -42,7 +42,8 @@ def test_wire_golden():
 
 
 @pytest.mark.parametrize("n,K,ncells,seed,full", [(1, 6, 1, 1, False), (300, 40, 4, 2, False), (1031, 12, 2, 3, False),
-                                                   (129, 7, 10, 4, False), (513, 20, 3, 5, True)])
+                                                   (129, 7, 10, 4, False), (513, 20, 3, 5, True),
+                                                   (2049, 30, 4, 6, True), (700, 25, 4, 7, False)])  # ncells == 4: the static-offset path
 def test_wire_fuzz_vs_port(n, K, ncells, seed, full):
     wire, nb = streams.imu_wire_fuzz(n, K, ncells=ncells, seed=seed, full_slots=full)
     if full:
