@@ -51,10 +51,14 @@ RK_DEV float my_atanf(const AtanTab &s, float x) {
   return neg ? -r : r;
 }
 // mymath::atan2f :117-126
+// The three quadrant cases share ONE evaluation of atanf(y / x): lanes of a warp that sit in different quadrants would
+// otherwise run the table search three times over.
 RK_DEV float my_atan2f(const AtanTab &s, float y, float x) {
-  if(x > 0.0f) return my_atanf(s, fdiv(y, x));
-  if(y >= 0.0f && x < 0.0f) return fadd(my_atanf(s, fdiv(y, x)), RK_PI);
-  if(y < 0.0f && x < 0.0f) return fsub(my_atanf(s, fdiv(y, x)), RK_PI);
+  const bool q1 = x > 0.0f, q2 = y >= 0.0f && x < 0.0f, q3 = y < 0.0f && x < 0.0f;
+  if(q1 || q2 || q3) {
+    const float a = my_atanf(s, fdiv(y, x));
+    return q1 ? a : (q2 ? fadd(a, RK_PI) : fsub(a, RK_PI));
+  }
   if(y > 0.0f && x == 0.0f) return (float)((double)RK_PI / 2.0);
   if(y < 0.0f && x == 0.0f) return (float)(-(double)RK_PI / 2.0);
   return 0.0f;
