@@ -151,7 +151,7 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
 #endif
 constexpr int kFastThreads = RK_FAST_THREADS;
 constexpr int kFastUnroll  = RK_FAST_UNROLL;
-constexpr int kMaxChunk    = 262144; // ticks per chunk: keeps the 32-bit per-chunk angle sum far from overflow
+constexpr int kMaxChunk    = 2048; // ticks per chunk: keeps the per-chunk angle sum exact (int32, or integers in float: |step| <= 4474)
 
 template <bool TRACE>
 RK_DEV void trace_row(uint32_t *d_trace, int64_t n, int64_t i, int t, float px, float py, float pth, const float vel[3],
@@ -238,7 +238,8 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
     // (always a transcription tick).  Lanes of a warp whose countdowns fire at different ticks leave
     // the fast loop at different times; results do not depend on it.
     const int t_end = min(min(min(sch.next_cmd, sched_fire_tick(v, a, sch)), K - 1), t + kMaxChunk);
-    if(t < t_end && fast_ok<D0, D1, D2, D3>(v, p) && fast_u_bounded<false>(v, p, fc)) {
+    if(t < t_end && fast_ok<D0, D1, D2, D3>(v, p) && fast_u_bounded<false>(v, p, fc) &&
+       !(PACKED && RK_FAST_FDANG && (f2u(v.pos[0]) == 0x80000000u || f2u(v.pos[1]) == 0x80000000u))) {
       const int t0  = t;
       float     pth = v.pos[2];
       if(PACKED) { // FADD2 / FFMA2 form of the same tick (rk_vehicle_fast2.cuh)

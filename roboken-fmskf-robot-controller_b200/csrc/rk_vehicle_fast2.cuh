@@ -66,6 +66,8 @@ struct FastInterp1 { // the theta interpolator, same scheme
 };
 struct FastWheel2 { // two wheels of equal direction, lane-paired
   int32_t rpm[2], cur[2], dsum[2];
+  float2  dsf; // RK_FAST_FDANG: the chunk's angle sums kept as exact integers in float (|sum| < 2^24, see kMaxChunk);
+               // w01.dsf = {wheel 0, wheel 2}, w23.dsf = {wheel 1, wheel 3} -- the pairing the odometry consumes the steps in
   float2  prev_val, integ, lpf_y, b0x;
   float2  x_l; // the IIR input of the last executed tick (prev_X_)
 };
@@ -145,7 +147,7 @@ RK_DEV float fast_interp1_update(FastInterp1 &f, float ts) {
 
 RK_DEV void to_fast_wheel2(FastWheel2 &w, const Veh &v, int a, int b, float b0) {
   w.rpm[0] = v.m[a].p_rpm, w.rpm[1] = v.m[b].p_rpm, w.cur[0] = v.m[a].cur_tgt, w.cur[1] = v.m[b].cur_tgt;
-  w.dsum[0] = 0, w.dsum[1] = 0;
+  w.dsum[0] = 0, w.dsum[1] = 0, w.dsf = make_float2(0.0f, 0.0f);
   w.prev_val = make_float2(v.c[a].prev_val, v.c[b].prev_val), w.integ = make_float2(v.c[a].integ, v.c[b].integ);
   w.lpf_y = make_float2(v.c[a].lpf_y, v.c[b].lpf_y);
   w.x_l   = make_float2(v.c[a].lpf_x, v.c[b].lpf_x);
@@ -171,6 +173,8 @@ RK_DEV void from_fast2_common(Veh &v, const FastVeh2 &f, FastWheel w[4]) {
   fast_interp2_store(f.xy, v.it[0], v.it[1]);
   fast_interp1_store(f.th, v.it[2]);
   w[0] = lane_wheel(f.w01, 0), w[1] = lane_wheel(f.w01, 1), w[2] = lane_wheel(f.w23, 0), w[3] = lane_wheel(f.w23, 1);
+  // the float angle sums (RK_FAST_FDANG; zero otherwise) in their odometry pairing
+  w[0].dsum += (int32_t)f.w01.dsf.x, w[2].dsum += (int32_t)f.w01.dsf.y, w[1].dsum += (int32_t)f.w23.dsf.x, w[3].dsum += (int32_t)f.w23.dsf.y;
 #pragma unroll
   for(int k = 0; k < 4; k++) v.c[k].prev_val = w[k].prev_val, v.c[k].integ = w[k].integ, v.c[k].lpf_y = w[k].lpf_y, v.c[k].lpf_x = w[k].lpf_x;
 }
@@ -188,7 +192,8 @@ RK_DEV void from_fast2(Veh &v, const FastVeh2 &f, int nticks) {
 // One tick's wheel feedback as the core consumes it: wheel-frame rpm and encoder step, as floats.
 struct Sense {
   float2 rw01, rw23; // (float)s16_rawSpeedRpm, direction applied        VD_motor_if_m2006.cpp:45
-  float  d0, d1, d2, d3; // (float)(s64_rawAngleSum - s64_rawAngleSumPrev)   VD_vehicle_controller.cpp:37-41
+  float  d0, d2;     // (float)(s64_rawAngleSum - s64_rawAngleSumPrev) of wheels 0, 2   VD_vehicle_controller.cpp:37-41
+  float2 d13;        // ... and of wheels 1, 3, paired as the odometry consumes them
 };
 
 // plant step + collapsed rx_callback for one wheel (see fast_wheel_sense)
@@ -312,7 +317,7 @@ RK_DEV void fast_tick2_core(FastVeh2 &f, const rk_vdt_params_t &p, const FastCon
   const float2 khi = fc.khi_pm, klo = fc.klo_pm; // {K, -K}
   const float2 M0  = fma2(bc2(s.d0), khi, mul2(bc2(s.d0), klo, nz)); // {m0, -m0}
   const float2 M2  = fma2(bc2(s.d2), khi, mul2(bc2(s.d2), klo, nz)); // {m2, -m2}
-  const float2 d13 = make_float2(s.d1, s.d3);
+  const float2 d13 = s.d13;
   const float2 M13 = fma2(d13, bc2(fc.k_hi), mul2(d13, bc2(fc.k_lo), nz)); // {m1, m3}
   // {((m0 + m1) + m2) + m3, ((-m0 + m1) - m2) + m3} * (0.25 * R) = local {dx, dy}
   const float2 l = mul2(add2(add2(add2(make_float2(M0.x, M0.y), bc2(M13.x)), make_float2(M2.x, M2.y)), bc2(M13.y)), bc2(qR), nz);
@@ -332,14 +337,42 @@ RK_DEV void fast_tick2_core(FastVeh2 &f, const rk_vdt_params_t &p, const FastCon
   fast_wheel_ctrl2<-1, FFSAT, KD0>(f.w23, p, fc, t23, now23, nz);
 }
 
+// RK_FAST_FDANG: the plant's encoder step rpm * 8192 / 60000 (truncating) formed in FLOAT from the float wheel speed the
+// tick needs anyway: trunc(RN(rw * C)) with C = RN(8192 / 60000) equals the integer division for every int16 rw (all
+// 65536 checked by tests/test_cabi_cpu.py::test_float_encoder_step_is_exact and on the device by rk_exact.cu's
+// proof_small_kernel); FRND runs on the otherwise idle conversion unit, the products and the angle sums pair up as
+// packed ops, and six half-rate ALU cycles per wheel (sign fix, I2FP, integer accumulate) disappear.  A negative speed
+// below one count gives -0.0 where the integer path gives +0.0; the step only enters the position sums, where the sign of
+// a zero term is immaterial unless the position word itself is -0.0 -- fast_ok2() keeps such a (never produced) state out.
+#ifndef RK_FAST_FDANG
+#define RK_FAST_FDANG 1
+#endif
+constexpr float kDangC = 0.13653333485126495f; // RN(8192 / 60000)
+template <int DIR>
+RK_DEV void fast_wheel_rpm2(int32_t &rpm, int32_t cur, float &rwf) {
+  rpm += ((cur * 4 - rpm) >> 4);
+  rwf = (float)((DIR == 1) ? rpm : -rpm);
+}
 template <bool FFSAT, bool TRACE, bool KD0>
 RK_DEV void fast_tick2(FastVeh2 &f, const rk_vdt_params_t &p, const FastConsts &fc, float2 cs, float2 sc, float nz,
                        float vel[3], float tgt[3]) {
   Sense s;
-  fast_wheel_sense2<1>(f.w01.rpm[0], f.w01.cur[0], f.w01.dsum[0], s.rw01.x, s.d0);
-  fast_wheel_sense2<1>(f.w01.rpm[1], f.w01.cur[1], f.w01.dsum[1], s.rw01.y, s.d1);
-  fast_wheel_sense2<-1>(f.w23.rpm[0], f.w23.cur[0], f.w23.dsum[0], s.rw23.x, s.d2);
-  fast_wheel_sense2<-1>(f.w23.rpm[1], f.w23.cur[1], f.w23.dsum[1], s.rw23.y, s.d3);
+  if(RK_FAST_FDANG) {
+    fast_wheel_rpm2<1>(f.w01.rpm[0], f.w01.cur[0], s.rw01.x);
+    fast_wheel_rpm2<1>(f.w01.rpm[1], f.w01.cur[1], s.rw01.y);
+    fast_wheel_rpm2<-1>(f.w23.rpm[0], f.w23.cur[0], s.rw23.x);
+    fast_wheel_rpm2<-1>(f.w23.rpm[1], f.w23.cur[1], s.rw23.y);
+    const float2 q01 = mul2(s.rw01, bc2(kDangC), nz), q23 = mul2(s.rw23, bc2(kDangC), nz);
+    s.d0 = truncf(q01.x), s.d2 = truncf(q23.x), s.d13 = make_float2(truncf(q01.y), truncf(q23.y));
+    f.w01.dsf = add2(f.w01.dsf, make_float2(s.d0, s.d2)), f.w23.dsf = add2(f.w23.dsf, s.d13);
+  } else {
+    float d1, d3;
+    fast_wheel_sense2<1>(f.w01.rpm[0], f.w01.cur[0], f.w01.dsum[0], s.rw01.x, s.d0);
+    fast_wheel_sense2<1>(f.w01.rpm[1], f.w01.cur[1], f.w01.dsum[1], s.rw01.y, d1);
+    fast_wheel_sense2<-1>(f.w23.rpm[0], f.w23.cur[0], f.w23.dsum[0], s.rw23.x, s.d2);
+    fast_wheel_sense2<-1>(f.w23.rpm[1], f.w23.cur[1], f.w23.dsum[1], s.rw23.y, d3);
+    s.d13 = make_float2(d1, d3);
+  }
   fast_tick2_core<FFSAT, TRACE, KD0>(f, p, fc, cs, sc, nz, vel, tgt, s);
 }
 // the same tick fed by four recorded frames (RK_SENSOR_STREAM)
@@ -347,10 +380,12 @@ template <bool FFSAT, bool TRACE, bool KD0>
 RK_DEV void fast_tick2_stream(FastVeh2 &f, StreamSense &ss, const uint64_t fr[4], const rk_vdt_params_t &p, const FastConsts &fc,
                               float2 cs, float2 sc, float nz, float vel[3], float tgt[3]) {
   Sense s;
+  float d1, d3;
   fast_wheel_rx2<1>(ss, 0, f.w01.dsum[0], fr[0], s.rw01.x, s.d0);
-  fast_wheel_rx2<1>(ss, 1, f.w01.dsum[1], fr[1], s.rw01.y, s.d1);
+  fast_wheel_rx2<1>(ss, 1, f.w01.dsum[1], fr[1], s.rw01.y, d1);
   fast_wheel_rx2<-1>(ss, 2, f.w23.dsum[0], fr[2], s.rw23.x, s.d2);
-  fast_wheel_rx2<-1>(ss, 3, f.w23.dsum[1], fr[3], s.rw23.y, s.d3);
+  fast_wheel_rx2<-1>(ss, 3, f.w23.dsum[1], fr[3], s.rw23.y, d3);
+  s.d13 = make_float2(d1, d3);
   fast_tick2_core<FFSAT, TRACE, KD0>(f, p, fc, cs, sc, nz, vel, tgt, s);
 }
 

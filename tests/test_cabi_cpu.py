@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 import roboken_fmskf_robot_controller_b200 as rk
@@ -163,3 +165,15 @@ def test_ctypes_structs_match_the_header(tmp_path):
             assert getattr(cls, fname).offset == int(val), f"{cname}.{fname}: header {val}, ctypes {getattr(cls, fname).offset}"
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+
+
+def test_float_encoder_step_is_exact():
+    """The packed vehicle tick forms the plant's encoder step rpm * 8192 / 60000 (C truncating division) in float as
+    trunc(RN(rpm * C)), C = RN(8192 / 60000) (rk_vehicle_fast2.cuh, RK_FAST_FDANG): equal for every int16 rpm.  The same
+    check runs on the device before the fast path is enabled (rk_exact.cu)."""
+    rw = np.arange(-32768, 32768, dtype=np.int64)
+    want = np.sign(rw) * ((np.abs(rw) * 8192) // 60000)
+    c = np.float32(0.13653333485126495)
+    assert c == np.float32(8192 / 60000)
+    got = np.trunc((rw.astype(np.float32) * c).astype(np.float32)).astype(np.int64)
+    np.testing.assert_array_equal(got, want)

@@ -358,6 +358,37 @@ def test_fast_kernel_equals_transcription_kernel():
     assert_same(fast_st, pst, "fast state vs port")
 
 
+def test_float_encoder_step_zero_signs_and_crawl_speeds():
+    """The packed tick forms the encoder step in float (trunc(rpm * C)): a wheel crawling backwards at less than one
+    count per tick gives -0.0 where the integer path gives +0.0.  That only matters for a position word that is itself
+    -0.0, which the fast path refuses (transcription instead).  Crawl commands (a few mm/s, both signs) from blocks whose
+    position words are +0.0, -0.0 and tiny values of both signs, traced and untraced, against the port bit for bit."""
+    n, steps = 2048, 300
+    rng = np.random.default_rng(5)
+    aos = np.zeros((n, layout.VS_WORDS), dtype=np.uint32)
+    pos = np.zeros((n, 2), dtype=np.float32)
+    kind = np.arange(n) % 4
+    pos[kind == 1] = -0.0
+    pos[kind == 2] = rng.uniform(-1e-30, 1e-30, ((kind == 2).sum(), 2)).astype(np.float32)
+    pos[kind == 3, 0] = -0.0  # mixed: x = -0.0, y = +0.0
+    aos[:, layout.VS_POS_X] = pos[:, 0].copy().view(np.uint32)
+    aos[:, layout.VS_POS_Y] = pos[:, 1].copy().view(np.uint32)
+    st0 = layout.aos_to_soa(aos)
+    cmd = np.zeros((3, n), dtype=np.dtype([("vx", "<f4"), ("vy", "<f4"), ("vth", "<f4"), ("kind", "<i4")]))
+    for sgm in range(3):
+        cmd["vx"][sgm] = rng.uniform(-6.0, 6.0, n).astype(np.float32)
+        cmd["vy"][sgm] = rng.uniform(-6.0, 6.0, n).astype(np.float32)
+        cmd["vth"][sgm] = rng.uniform(-0.05, 0.05, n).astype(np.float32)
+        cmd["kind"][sgm] = _cabi.RK_CMD_MOVE
+    inp = dict(n=n, steps=steps, cmd=cmd, seg_len=100)
+    pst, ptr = port_run(inp, state=st0, nthreads=8)
+    gst, gtr = gpu_run(inp, state=st0)
+    assert_same(gtr, ptr, "crawl trace vs port")
+    assert_same(gst, pst, "crawl state vs port")
+    ust, _ = gpu_run(inp, state=st0, trace=False)
+    assert_same(ust, pst, "crawl state (untraced) vs port")
+
+
 def test_packed_and_scalar_fast_ticks_agree():
     """The fast kernel has two bit-identical forms: packed FADD2/FFMA2 (default) and scalar
     (RK_OPT_FAST_PACKED = 0).  Every other test here runs the packed one; this one runs both."""
