@@ -31,10 +31,13 @@ RK_DEV uint32_t h32_prefix(uint32_t seed, uint32_t stream, uint64_t inst) { // t
 }
 RK_DEV uint32_t h32_idx(uint32_t prefix, uint32_t idx) { return mix32(prefix ^ (idx * 0x85EBCA6Bu)); }
 RK_DEV uint32_t sub32(uint32_t h, uint32_t k) { return mix32(h + (k + 1u) * 0x9E3779B9u); }
-// k-th draw under an already mixed hash at a third of sub32's cost (streams.lite32): the per-sample streams use it
+// k-th draw under an already mixed hash at a fraction of sub32's cost (streams.lite32): one wide multiply by an odd
+// per-draw constant (FMA pipe) and one xor of the two halves -- the generators run beside rollouts that are bound by the
+// half-rate ALU pipe, so the draws stay off it
 RK_DEV uint32_t lite32(uint32_t h, uint32_t k) {
-  const uint32_t x = (h ^ ((k + 1u) * 0x9E3779B9u)) * 0x85EBCA6Bu;
-  return x ^ (x >> 13);
+  const uint32_t           m = (0x85EBCA6Bu + 2u * (k + 1u) * 0x9E3779B9u) | 1u;
+  const unsigned long long x = (unsigned long long)h * m;
+  return (uint32_t)x ^ (uint32_t)(x >> 32);
 }
 RK_DEV float    u01_32(uint32_t h) { return fmul((float)(h >> 8), 1.0f / 16777216.0f); }
 
@@ -157,7 +160,7 @@ stream_arm_sequences_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, 
 // a planner that expands the next batch's streams while the current rollout runs keeps them out of the rollout's way
 static int g_stream_ctas_per_sm = 0;
 int        stream_set_ctas(int v) {
-  if(v < 0 || v > 32) return RK_ERR_ARG;
+  if(v < -100000 || v > 32) return RK_ERR_ARG; // v < 0: -v CTAs in total (a trickle: less than one CTA per SM)
   g_stream_ctas_per_sm = v;
   return RK_OK;
 }
@@ -167,6 +170,9 @@ static unsigned stream_grid(int64_t n) {
     int dev = 0, sms = 148;
     if(cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned cap = (unsigned)(g_stream_ctas_per_sm * sms);
+    if(g > cap) g = cap;
+  } else if(g_stream_ctas_per_sm < 0) {
+    const unsigned cap = (unsigned)(-g_stream_ctas_per_sm);
     if(g > cap) g = cap;
   }
   return g;

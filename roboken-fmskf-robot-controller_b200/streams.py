@@ -410,11 +410,12 @@ def sub32(h, k):
 
 
 def lite32(h, k):
-    """k-th draw under one (already mixed) hash at a third of sub32's cost: one xor, one odd multiply, one xor-shift.
-    The per-sample streams (IMU registers, arm waypoints) use it; 16.8 M robots x 100 samples are expanded per pass."""
-    with np.errstate(over="ignore"):
-        x = (np.asarray(h, dtype=np.uint32) ^ _U32(((k + 1) * 0x9E3779B9) & 0xFFFFFFFF)) * _U32(0x85EBCA6B)
-    return x ^ (x >> _U32(13))
+    """k-th draw under one (already mixed) hash at a fraction of sub32's cost: the 64-bit product with an odd per-draw
+    constant, high half folded onto the low half (one wide multiply and one xor on the device).  The per-sample streams
+    (IMU registers, arm waypoints) use it; 16.8 M robots x 100 samples are expanded per pass."""
+    m = np.uint64(((0x85EBCA6B + 2 * (k + 1) * 0x9E3779B9) | 1) & 0xFFFFFFFF)
+    x = np.asarray(h, dtype=np.uint32).astype(np.uint64) * m
+    return ((x & np.uint64(0xFFFFFFFF)) ^ (x >> np.uint64(32))).astype(np.uint32)
 
 
 def _u01_32(h):
