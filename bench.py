@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--gen-ctas", type=int, default=2, help="e2e: RK_OPT_STREAM_CTAS while the stream generators run beside the rollout")
     ap.add_argument("--side-ctas", type=int, default=-1, help="RK_OPT_TICK_SIDE_CTAS override (tuning; -1 = library default)")
     ap.add_argument("--no-modules", action="store_true", help="workload full: skip the configs[1..3] module measurements")
+    ap.add_argument("--no-yaw-column", action="store_true", help="workload full: the vehicle reads the yaw from the IMU register cells instead of the 2-byte Yaw column")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-skip", default="", help="tuning only: comma list of gen,reset,d2h left out of the e2e pass (its number is then not an e2e number)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -704,7 +705,7 @@ def run_ours_full(a):
 
     # ---- synthetic inputs: every chunk's tables expanded on the device from its 48-byte descriptor; resident in HBM
     # for the `value` region (distinct per chunk when they fit, else one set replayed by every chunk) ----------------
-    per_robot_in = n_seg * 16 + n_slow * 33 + layout.ACMD_SLOT_WORDS * 4
+    per_robot_in = n_seg * 16 + n_slow * (33 if a.no_yaw_column else 35) + layout.ACMD_SLOT_WORDS * 4
     free_b, _ = torch.cuda.mem_get_info(dev)
     distinct = n_chunks * n * (per_robot_in + 4 * (layout.VS_WORDS + layout.IS_WORDS + layout.AS_WORDS)) + 4 * n * (per_robot_in + 4 * layout.ACMD_WORDS) < 0.85 * free_b
 
@@ -712,11 +713,12 @@ def run_ours_full(a):
         return dict(cmd=torch.empty((n_seg, n, 4), dtype=torch.int32, device=dev),
                     regs=torch.empty((n_slow, 2, n, 8), dtype=torch.int16, device=dev),
                     have=torch.empty((n_slow, n), dtype=torch.uint8, device=dev),
+                    yawc=None if a.no_yaw_column else torch.empty((n_slow, n), dtype=torch.int16, device=dev),
                     seq=torch.empty(layout.ACMD_SLOT_WORDS * n, dtype=torch.int32, device=dev))
 
     def generate(ds, tb, st=None):
         ds.vehicle_commands(tb["cmd"], st)
-        ds.imu_samples(tb["regs"], tb["have"], st)
+        ds.imu_samples(tb["regs"], tb["have"], st, yaw_reg=tb["yawc"])  # + the Yaw register as a 2-byte column for the vehicle
         ds.arm_sequences(tb["seq"], st)
 
     def chunk_desc(c):
@@ -740,7 +742,7 @@ def run_ours_full(a):
         DeviceStreams(dev, seed=seed, first=lo + c * n, first_update=0).imu_samples(boot, None)
         rb.imu.update(boot, None, None, do_init=True)  # IMU_IF_WT901C::init() at boot consumes sample 0
         cost = torch.zeros(n, dtype=torch.float32, device=dev)
-        args = rb.make_args(T, slow, cmd=tb["cmd"], seg_len=a.seg_len, regs=tb["regs"], have_quat=tb["have"], yaw=yaws[c % lanes],
+        args = rb.make_args(T, slow, cmd=tb["cmd"], seg_len=a.seg_len, regs=tb["regs"], have_quat=tb["have"], yaw_reg=tb["yawc"], yaw=yaws[c % lanes],
                             goal=goal_d, cost=cost)
         chunks.append(dict(rb=rb, cost=cost, args=args, tb=tb, ds=ds))
     torch.cuda.synchronize()
@@ -859,7 +861,7 @@ def run_ours_full(a):
         "launch_ms_note": "timed region / vehicle launches in it: the kernel's slot including the IMU, arm and ring-push kernels that "
                           "run in its shadow (CUDA events on the launching streams' parent)",
         "launch_ms_alone": alone_ms, "frac_alone": FLOP_PER_TICK * n * T / (alone_ms * 1e-3) / 1e12 / ffma_tflops,
-        "traffic": traffic_note("vdt_rollout_imu_regs_bytes_per_launch"),
+        "traffic": traffic_note("vdt_rollout_imu_regs_bytes_per_launch" if a.no_yaw_column else "vdt_rollout_yaw_column_bytes_per_launch"),
         "step": {"algorithmic_flop_per_robot_step": FLOP_PER_FULL_STEP,
                  "achieved_tflops": FLOP_PER_FULL_STEP * n_rank * T / step_s / 1e12,
                  "frac_of_ffma_peak": FLOP_PER_FULL_STEP * n_rank * T / step_s / 1e12 / ffma_tflops,
@@ -905,7 +907,7 @@ def run_ours_full(a):
                     rb.arm.push_cmdseq(b["seq"], stream=ls)
                     key = (c, g % NB)
                     if key not in argcache:  # reset_vehicle: every rollout starts from the power-on vehicle
-                        argcache[key] = rb.make_args(T, slow, cmd=b["cmd"], seg_len=a.seg_len, regs=b["regs"], have_quat=b["have"],
+                        argcache[key] = rb.make_args(T, slow, cmd=b["cmd"], seg_len=a.seg_len, regs=b["regs"], have_quat=b["have"], yaw_reg=b["yawc"],
                                                      yaw=yaws[c % lanes], goal=goal_d, cost=b["cost"], reset_vehicle="reset" not in skip)
                     rb.rollout_args(argcache[key], stream=ls)
                     b["done"].record(ls)

@@ -159,6 +159,7 @@ class TickRollout(C.Structure):
         ("d_vdt_trace", C.c_void_p),
         ("d_adt_trace", C.c_void_p),
         ("reset_vehicle", C.c_int32),
+        ("d_yaw_reg", C.c_void_p),
     ]
 
 
@@ -205,6 +206,7 @@ def _proto(lib):
     lib.rk_stream_vehicle_commands.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
     lib.rk_stream_vehicle_yaw_reg.argtypes = [vp, C.c_int64, C.c_int32, vp, vp]
     lib.rk_stream_imu_samples.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp]
+    lib.rk_stream_imu_samples_yaw.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
     lib.rk_stream_arm_sequences.argtypes = [vp, C.c_int64, vp, vp]
     lib.rk_adt_bldc_rx.argtypes = [C.POINTER(AdtParams), vp, C.c_int64, C.c_int, vp, vp, vp, vp]
     lib.rk_adt_mg_rx.argtypes = [C.POINTER(AdtParams), vp, C.c_int64, vp, vp, vp]

@@ -98,7 +98,7 @@ stream_vehicle_yaw_reg_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n
 // streams.imu_samples_v2 in the cell layout rk_imt_update takes: int16 [n_upd][2][n][8] + have_quat uint8 [n_upd][n]
 __global__ void __launch_bounds__(RK_STREAM_BLOCK)
 stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, int n_upd, uint4 *__restrict__ cells,
-                          uint8_t *__restrict__ have) {
+                          uint8_t *__restrict__ have, int16_t *__restrict__ yaw_reg) {
   const rk_stream_desc_t d = *dd;
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
   const uint32_t px = h32_prefix(d.seed, 20u, (uint64_t)(d.first + i));
@@ -120,6 +120,7 @@ stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, in
     w[6] = q[0] | (q[1] << 16), w[7] = q[2] | (q[3] << 16);
     __stcs(cells + ((int64_t)u * 2 + 0) * n + i, make_uint4(w[0], w[1], w[2], w[3]));
     __stcs(cells + ((int64_t)u * 2 + 1) * n + i, make_uint4(w[4], w[5], w[6], w[7]));
+    if(yaw_reg) yaw_reg[(int64_t)u * n + i] = (int16_t)(w[5] >> 16); // register RK_IMT_REG_YAW again, as a 2-byte column
     if(have) have[(int64_t)u * n + i] = (d.drop_every == 0u || (lite32(b, 8u) % d.drop_every) != 0u) ? 1u : 0u;
   }
   }
@@ -216,12 +217,20 @@ int rk_stream_vehicle_yaw_reg(const rk_stream_desc_t *d_desc, int64_t n, int32_t
   return RK_OK;
 }
 
-int rk_stream_imu_samples(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat, void *stream) {
+int rk_stream_imu_samples_yaw(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat,
+                              int16_t *d_yaw_reg, void *stream) {
   if(n == 0 || n_upd <= 0) return RK_OK;
   if(int rc = stream_check("rk_stream_imu_samples", d_desc, d_regs, n)) return rc;
-  stream_imu_samples_kernel<<<stream_grid(n), RK_STREAM_BLOCK, 0, (cudaStream_t)stream>>>(d_desc, n, n_upd, (uint4 *)d_regs, d_have_quat);
+  if((uintptr_t)d_yaw_reg & 1u) {
+    set_error("rk_stream_imu_samples_yaw: d_yaw_reg must be 2-byte aligned");
+    return RK_ERR_ARG;
+  }
+  stream_imu_samples_kernel<<<stream_grid(n), RK_STREAM_BLOCK, 0, (cudaStream_t)stream>>>(d_desc, n, n_upd, (uint4 *)d_regs, d_have_quat, d_yaw_reg);
   RK_CUDA(cudaGetLastError());
   return RK_OK;
+}
+int rk_stream_imu_samples(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat, void *stream) {
+  return rk_stream_imu_samples_yaw(d_desc, n, n_upd, d_regs, d_have_quat, nullptr, stream);
 }
 
 int rk_stream_arm_sequences(const rk_stream_desc_t *d_desc, int64_t n, void *d_seq, void *stream) {

@@ -112,7 +112,9 @@ extern "C" int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t 
     rk_vdt_rollout_t v = {};
     v.steps = a->steps, v.sensor_mode = RK_SENSOR_PLANT;
     v.d_cmd = a->d_cmd, v.n_seg = a->n_seg, v.seg_len = a->seg_len;
-    v.d_imu_regs = a->d_regs, v.d_imu_have_quat = a->d_have_quat, v.d_imu_yaw0_deg = a->d_yaw;
+    if(a->d_yaw_reg) v.d_yaw_reg = a->d_yaw_reg; // the Yaw column in 2 bytes per sample (same hold semantics)
+    else v.d_imu_regs = a->d_regs;
+    v.d_imu_have_quat = a->d_have_quat, v.d_imu_yaw0_deg = a->d_yaw;
     v.n_yaw = n_slow, v.yaw_period = a->slow_period;
     v.d_trace = a->d_vdt_trace, v.d_goal = a->d_goal, v.d_cost = a->d_cost;
     v.reset_state = a->reset_vehicle;

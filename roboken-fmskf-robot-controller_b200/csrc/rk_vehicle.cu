@@ -37,6 +37,7 @@ RK_DEV YawPf load_yaw_pf(const rk_vdt_rollout_t &a, int64_t n, int64_t i, int yk
     pf.raw = __float_as_uint(__ldcs(a.d_yaw + idx));
   } else if(a.d_yaw_reg) {
     pf.raw = (uint32_t)(int)__ldcs(a.d_yaw_reg + idx);
+    if(a.d_imu_have_quat) pf.have = (uint32_t)__ldcs(a.d_imu_have_quat + idx);
   } else {
     pf.raw = (uint32_t)(int)__ldcs(a.d_imu_regs + (((int64_t)yk * 2 + 1) * n + i) * 8 + (RK_IMT_REG_YAW - 8));
     if(a.d_imu_have_quat) pf.have = (uint32_t)__ldcs(a.d_imu_have_quat + idx);

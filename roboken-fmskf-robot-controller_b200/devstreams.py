@@ -50,11 +50,14 @@ class DeviceStreams:
         _cabi.check(self.lib.rk_stream_vehicle_yaw_reg(self.dev.data_ptr(), out.shape[1], out.shape[0], out.data_ptr(), self._st(stream)))
         return out
 
-    def imu_samples(self, regs, have=None, stream=None):
-        """regs: int16 [n_upd, 2, n, 8]; have: uint8 [n_upd, n] or None"""
+    def imu_samples(self, regs, have=None, stream=None, yaw_reg=None):
+        """regs: int16 [n_upd, 2, n, 8]; have: uint8 [n_upd, n] or None; yaw_reg: int16 [n_upd, n] or None (receives the Yaw
+        register column, what rk_tick_rollout_t::d_yaw_reg takes)"""
         n_upd, n = regs.shape[0], regs.shape[2]
-        _cabi.check(self.lib.rk_stream_imu_samples(self.dev.data_ptr(), n, n_upd, regs.data_ptr(),
-                                                   None if have is None else have.data_ptr(), self._st(stream)))
+        assert yaw_reg is None or (yaw_reg.dtype == torch.int16 and tuple(yaw_reg.shape) == (n_upd, n) and yaw_reg.is_contiguous())
+        _cabi.check(self.lib.rk_stream_imu_samples_yaw(self.dev.data_ptr(), n, n_upd, regs.data_ptr(),
+                                                       None if have is None else have.data_ptr(),
+                                                       None if yaw_reg is None else yaw_reg.data_ptr(), self._st(stream)))
         return regs, have
 
     def arm_sequences(self, out, stream=None):

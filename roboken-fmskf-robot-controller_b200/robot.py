@@ -30,7 +30,7 @@ class RobotBatch:
         self.arm.mode_init()
 
     def make_args(self, steps, slow_period, cmd, seg_len, regs, have_quat, yaw, goal=None, cost=None, vdt_trace=None,
-                  adt_trace=None, reset_vehicle=False):
+                  adt_trace=None, reset_vehicle=False, yaw_reg=None):
         """cmd: [n_seg, n, 4] rk_vdt_cmd_t records; regs: int16 [n_slow, 2, n, 8] (streams.imu_cells); have_quat: uint8
         [n_slow, n] or None; yaw: float32 scratch, >= n words (receives the IMU yaw as it was at launch)."""
         n_slow = (steps + slow_period - 1) // slow_period
@@ -45,13 +45,16 @@ class RobotBatch:
         a.d_regs = regs.data_ptr()
         a.d_have_quat = None if have_quat is None else have_quat.data_ptr()
         a.d_yaw = yaw.data_ptr()
+        if yaw_reg is not None:  # the Yaw register column of regs, int16 [n_slow, n]
+            assert yaw_reg.is_cuda and yaw_reg.dtype == torch.int16 and tuple(yaw_reg.shape) == (n_slow, self.n) and yaw_reg.is_contiguous()
+            a.d_yaw_reg = yaw_reg.data_ptr()
         if goal is not None and cost is not None:
             a.d_goal, a.d_cost = goal.data_ptr(), cost.data_ptr()
         if vdt_trace is not None:
             a.d_vdt_trace = vdt_trace.data_ptr()
         if adt_trace is not None:
             a.d_adt_trace = adt_trace.data_ptr()
-        self._keep = [cmd, regs, have_quat, yaw, goal, cost, vdt_trace, adt_trace]
+        self._keep = [cmd, regs, have_quat, yaw, goal, cost, vdt_trace, adt_trace, yaw_reg]
         return a
 
     def rollout_args(self, args, stream=None):

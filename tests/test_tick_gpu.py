@@ -183,6 +183,40 @@ def test_side_kernel_cap_does_not_change_results():
         RobotBatch(1, DEV).lib.rk_set_option(_cabi.RK_OPT_TICK_SIDE_CTAS, 1)
 
 
+def test_yaw_column_equals_register_cells():
+    """rk_tick_rollout_t::d_yaw_reg: the vehicle reading the Yaw register from the 2-byte column the generator writes beside
+    the register cells gives the same blocks and costs as reading it from the cells -- with every third quaternion frame
+    missing, so that the hold semantics (and the yaw the IMU block held at launch) are exercised in both forms."""
+    from roboken_fmskf_robot_controller_b200.devstreams import DeviceStreams
+
+    n, steps, slow, seg_len = 3000, 400, 10, 125
+    n_seg, n_slow = (steps + seg_len - 1) // seg_len, (steps + slow - 1) // slow
+    ds = DeviceStreams(DEV, seed=91, first=7, first_update=1, arm_seq_id=1, drop_every=3)
+    cmd = ds.vehicle_commands(torch.empty((n_seg, n, 4), dtype=torch.int32, device=DEV))
+    yawc = torch.empty((n_slow, n), dtype=torch.int16, device=DEV)
+    regs, have = ds.imu_samples(torch.empty((n_slow, 2, n, 8), dtype=torch.int16, device=DEV), torch.empty((n_slow, n), dtype=torch.uint8, device=DEV),
+                                yaw_reg=yawc)
+    seq = ds.arm_sequences(torch.empty(layout.ACMD_SLOT_WORDS * n, dtype=torch.int32, device=DEV))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(yawc.cpu().numpy(), regs.cpu().numpy()[:, 1, :, 3])  # register 11 = Yaw
+    assert 0.2 < 1.0 - have.float().mean().item() < 0.45
+    out = []
+    for col in (None, yawc):
+        rb = RobotBatch(n, DEV)
+        rb.reset()
+        boot = DeviceStreams(DEV, seed=91, first=7, first_update=0).imu_samples(torch.empty((1, 2, n, 8), dtype=torch.int16, device=DEV), None)[0]
+        rb.imu.update(boot, None, None, do_init=True)
+        rb.arm.push_cmdseq(seq)
+        cost = torch.zeros(n, dtype=torch.float32, device=DEV)
+        for _ in range(2):  # the second launch starts from an IMU block that holds a yaw
+            rb.rollout(steps, slow, cmd=cmd, seg_len=seg_len, regs=regs, have_quat=have, yaw_reg=col, yaw=torch.zeros(n, dtype=torch.float32, device=DEV),
+                       goal=torch.zeros((n, 2), dtype=torch.float32, device=DEV), cost=cost)
+        torch.cuda.synchronize()
+        out.append([rb.vehicle.state.cpu().numpy().copy(), rb.imu.state.cpu().numpy().copy(), rb.arm.state.cpu().numpy().copy(), cost.cpu().numpy().view(np.uint32).copy()])
+    for x, y in zip(*out):
+        np.testing.assert_array_equal(x, y)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_two_gpu_slices_equal_one_gpu_run():
     """SURVEY 8e on real devices: the two halves of a batch run on cuda:0 and cuda:1 (contiguous slices of the global
