@@ -225,7 +225,8 @@ typedef struct rk_vdt_rollout {
   const float *d_imu_yaw0_deg;
   /* != 0: every vehicle starts this rollout from the power-on block (all zeros: the firmware's static initialisation)
    * instead of the contents of d_state -- a planner's "reset and roll out" in one call (the block is cleared on the
-   * stream in front of the kernel). */
+   * stream in front of the kernel; the default closed-loop configuration runs an instantiation of the kernel that starts
+   * from zeros in registers instead: no clear and no state load at all). */
   int32_t reset_state;
 } rk_vdt_rollout_t;
 

@@ -144,6 +144,9 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
 // the launch and any thread outside the fast path's domain run the transcription (veh_update), so the
 // stored state is complete and identical.
 // -----------------------------------------------------------------------------------------
+#ifndef RK_FAST_RESET_KERNEL
+#define RK_FAST_RESET_KERNEL 1
+#endif
 #ifndef RK_FAST_THREADS
 #define RK_FAST_THREADS 128
 #endif
@@ -202,7 +205,7 @@ RK_DEV void yaw_feed_take(YawFeed &y, const rk_vdt_rollout_t &a, int64_t n, int6
 }
 
 // FLAGS: bit 0 FFSAT (ff_limit == 1: FMUL.SAT form of the feed-forward clamp), bit 1 KD0 (kd == 0, packed tick only)
-template <bool TRACE, int OCC, int FLAGS, bool PACKED>
+template <bool TRACE, int OCC, int FLAGS, bool PACKED, bool RESET = false>
 #if defined(RK_FAST_MAXNREG) // tuning builds: the register budget given directly (finer occupancy steps with small CTAs)
 __global__ void __maxnreg__(RK_FAST_MAXNREG)
 #elif defined(RK_FAST_MINBLOCKS)
@@ -219,7 +222,8 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
   if(i >= n) return;
 
   Veh v;
-  load_veh(state, n, i, v);
+  if(RESET) v = Veh{}; // reset_state: the power-on block is all zeros -- nothing to load (and no memset in front of the kernel)
+  else load_veh(state, n, i, v);
   const Derived d = derive(p);
   FastConsts    fc;
   fast_consts(fc, p, d);
@@ -657,7 +661,12 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
   cudaError_t  e;
   // reset_state: the power-on block is all zeros (static initialisation).  Done as a memset in front of the kernel: a
   // second load path inside the rollout kernels cost the hot loop 2 % through ptxas' register allocation (8.83 -> 8.99 ms).
-  if(args->reset_state) RK_CUDA(cudaMemsetAsync(d_state, 0, (size_t)n * RK_VS_WORDS * 4u, st));
+  // ... except in the default configuration of the packed fast kernel, which has an instantiation that starts from
+  // zeros in registers (RK_FAST_RESET_KERNEL): no memset, no state load.
+  const bool reset_in_kernel = RK_FAST_RESET_KERNEL && args->reset_state && args->sensor_mode == RK_SENSOR_PLANT && !args->d_trace &&
+                               fast_path_usable(*p) && g_fast_packed && g_fast_occupancy != 3 && p->kd == 0.0f &&
+                               !(p->ff_limit == 1.0f && g_fast_ffsat);
+  if(args->reset_state && !reset_in_kernel) RK_CUDA(cudaMemsetAsync(d_state, 0, (size_t)n * RK_VS_WORDS * 4u, st));
   switch(args->sensor_mode) {
   case RK_SENSOR_HOLD: e = launch_rollout<RK_SENSOR_HOLD>(*p, d_state, n, *args, st); break;
   case RK_SENSOR_PLANT:
@@ -679,7 +688,9 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
       }                                                            \
     }                                                              \
   } while(0)
-      if(args->d_trace) {
+      if(reset_in_kernel) {
+        vdt_rollout_fast_kernel<false, 4, 2, true, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+      } else if(args->d_trace) {
         RK_LAUNCH_FAST(true, 4);
       } else {
         switch(g_fast_occupancy) { // resident CTAs per SM the kernel is compiled for (register budget)
