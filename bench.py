@@ -71,6 +71,7 @@ def parse():
     ap.add_argument("--side-ctas", type=int, default=-1, help="RK_OPT_TICK_SIDE_CTAS override (tuning; -1 = library default)")
     ap.add_argument("--no-modules", action="store_true", help="workload full: skip the configs[1..3] module measurements")
     ap.add_argument("--no-yaw-column", action="store_true", help="workload full: the vehicle reads the yaw from the IMU register cells instead of the 2-byte Yaw column")
+    ap.add_argument("--e2e-tables", action="store_true", help="workload full: the e2e path materialises the IMU register table instead of drawing the samples inside the IMU update")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-skip", default="", help="tuning only: comma list of gen,reset,d2h left out of the e2e pass (its number is then not an e2e number)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -878,6 +879,7 @@ def run_ours_full(a):
         # table sets: one being generated, one per compute lane in flight
         NB = lanes + 1
         skip = set(x for x in a.e2e_skip.split(",") if x)
+        fused = not (a.e2e_tables or a.no_yaw_column)  # the IMU update draws its samples from the descriptor in registers
         bufs = []
         for b in range(NB):
             d = alloc_tables()
@@ -898,7 +900,12 @@ def run_ours_full(a):
                     gen_s.wait_event(b["done"])  # the rollout that last used this table set has finished
                     ch["ds"].upload(gen_s)
                     if "gen" not in skip or s < 0:
-                        generate(ch["ds"], b, gen_s)
+                        if fused:  # commands, the two IMU columns the vehicle reads, arm waypoints; the IMU samples are drawn in the update
+                            ch["ds"].vehicle_commands(b["cmd"], gen_s)
+                            ch["ds"].imu_columns(b["yawc"], b["have"], gen_s)
+                            ch["ds"].arm_sequences(b["seq"], gen_s)
+                        else:
+                            generate(ch["ds"], b, gen_s)
                     b["up"].record(gen_s)
                 with torch.cuda.stream(ls):
                     ls.wait_event(b["up"])
@@ -907,7 +914,8 @@ def run_ours_full(a):
                     rb.arm.push_cmdseq(b["seq"], stream=ls)
                     key = (c, g % NB)
                     if key not in argcache:  # reset_vehicle: every rollout starts from the power-on vehicle
-                        argcache[key] = rb.make_args(T, slow, cmd=b["cmd"], seg_len=a.seg_len, regs=b["regs"], have_quat=b["have"], yaw_reg=b["yawc"],
+                        argcache[key] = rb.make_args(T, slow, cmd=b["cmd"], seg_len=a.seg_len, regs=None if fused else b["regs"],
+                                                     imu_desc=ch["ds"] if fused else None, have_quat=b["have"], yaw_reg=b["yawc"],
                                                      yaw=yaws[c % lanes], goal=goal_d, cost=b["cost"], reset_vehicle="reset" not in skip)
                     rb.rollout_args(argcache[key], stream=ls)
                     b["done"].record(ls)
@@ -944,10 +952,16 @@ def run_ours_full(a):
             raise SystemExit("bench e2e parity check failed: costs returned through the end-to-end path differ from the oracle")
         e2e = {"value": a.total * T * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / K,
-               "path": "per chunk: 48-byte stream descriptor pinned host -> device; rk_stream_vehicle_commands / rk_stream_imu_samples / "
-                       "rk_stream_arm_sequences expand it into the command, IMU-register and arm-sequence tables on the device (4.5 KB per "
-                       "robot that never cross PCIe); rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout (vehicles from power-on) via "
-                       "ctypes; cost vector D2H; generation (high-priority stream, capped grid), compute (the lanes of the value path) and D2H overlap",
+               "path": ("per chunk: 48-byte stream descriptor pinned host -> device; rk_stream_vehicle_commands / rk_stream_imu_samples_yaw / "
+                        "rk_stream_arm_sequences expand it on the device into the command table, the two IMU columns the vehicle reads (Yaw "
+                        "register, quaternion-frame flag) and the arm-sequence table; the IMU update draws its 100 register snapshots per "
+                        "robot from the same descriptor in registers (rk_tick_rollout_t::d_imu_desc: 3.2 KB per robot neither written nor "
+                        "read); rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout (vehicles from power-on) via ctypes; cost vector D2H; "
+                        "generation (high-priority stream, capped grid), compute (the lanes of the value path) and D2H overlap") if fused else
+                       ("per chunk: 48-byte stream descriptor pinned host -> device; rk_stream_vehicle_commands / rk_stream_imu_samples / "
+                        "rk_stream_arm_sequences expand it into the command, IMU-register and arm-sequence tables on the device (4.5 KB per "
+                        "robot that never cross PCIe); rk_adt_mode_init + rk_adt_push_cmdseq + rk_tick_rollout (vehicles from power-on) via "
+                        "ctypes; cost vector D2H; generation (high-priority stream, capped grid), compute (the lanes of the value path) and D2H overlap"),
                "parity": "costs copied back by the last rollout bit-exact vs the oracle on the sampled robots of that chunk, every rank"}
 
     # ---- the module configurations (BASELINE configs[1..3]) on this GPU, outside the timed regions ----------------------

@@ -554,6 +554,7 @@ int  rk_adt_set_state(rk_adt_t *h, const uint32_t words[RK_AS_WORDS]);
  * The call is asynchronous on `stream` like every other batch call; concurrent callers on one
  * device are serialised while they enqueue.
  * ===================================================================================== */
+struct rk_stream_desc;
 typedef struct rk_tick_rollout {
   int32_t steps;             /* K vehicle ticks */
   int32_t slow_period;       /* vehicle ticks per IMU / arm tick (firmware: 10) */
@@ -571,6 +572,10 @@ typedef struct rk_tick_rollout {
                                 2 bytes per sample.  The vehicle rollout then reads the yaw from here instead of from the 16-byte
                                 register cells (16 B of sector traffic per sample): same values, same hold semantics, 1.6 GB less
                                 DRAM traffic per 2^20 robots x 1000 ticks.  rk_stream_imu_samples_yaw() writes it as a by-product. */
+  const struct rk_stream_desc *d_imu_desc; /* optional (needs d_yaw_reg; d_regs may then be NULL): the IMU samples are those of
+                                rk_stream_imu_samples(d_imu_desc, ...) and the IMU update draws them in registers instead of reading
+                                a table -- 3.2 KB per robot and launch that are neither written nor read.  d_yaw_reg / d_have_quat
+                                are the columns rk_stream_imu_samples_yaw(d_imu_desc, n, n_slow, NULL, d_have_quat, d_yaw_reg) wrote. */
 } rk_tick_rollout_t;
 
 int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t *ap, void *d_vdt_state, void *d_imt_state,
@@ -604,7 +609,8 @@ int rk_stream_vehicle_commands(const rk_stream_desc_t *d_desc, int64_t n, int32_
 /* int16 [n_yaw][n]: the WT901C Yaw register of a vehicle turning at a constant 1..5 x 182 counts per sample */
 int rk_stream_vehicle_yaw_reg(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_yaw, int16_t *d_yaw_reg, void *stream);
 /* rk_stream_imu_samples() that also writes the Yaw register of every sample as a 2-byte column [n_upd][n]
- * (rk_tick_rollout_t::d_yaw_reg); d_yaw_reg NULL = rk_stream_imu_samples() */
+ * (rk_tick_rollout_t::d_yaw_reg); d_yaw_reg NULL = rk_stream_imu_samples(); d_regs NULL (d_yaw_reg 16-byte aligned): only
+ * the columns are written, for a rollout whose IMU update draws the samples itself (rk_tick_rollout_t::d_imu_desc) */
 int rk_stream_imu_samples_yaw(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat,
                               int16_t *d_yaw_reg, void *stream);
 /* WT901 register snapshots in the two-cells-per-sample layout of rk_imt_update (+ have_quat [n_upd][n], may be NULL) */

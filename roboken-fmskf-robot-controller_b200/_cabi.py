@@ -160,6 +160,7 @@ class TickRollout(C.Structure):
         ("d_adt_trace", C.c_void_p),
         ("reset_vehicle", C.c_int32),
         ("d_yaw_reg", C.c_void_p),
+        ("d_imu_desc", C.c_void_p),
     ]
 
 

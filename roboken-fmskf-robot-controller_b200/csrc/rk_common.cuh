@@ -57,7 +57,7 @@ int         cuda_fail(cudaError_t e, const char *what);
 int         require_device();
 // rk_imt_update_yaw / rk_adt_update with a cap on the grid (rk_tick.cu runs them beside the vehicle rollout)
 int imt_update_launch(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
-                      float *d_yaw_rad, int do_init, int max_ctas, void *stream);
+                      float *d_yaw_rad, int do_init, int max_ctas, void *stream, const void *d_desc = nullptr);
 int adt_update_launch(const rk_adt_params_t *p, void *d_state, const void *d_cmdtab, int64_t n, int32_t K, uint32_t *d_trace,
                       int max_ctas, void *stream);
 } // namespace rk

@@ -7,6 +7,7 @@
 
 #include "rk_common.cuh"
 #include "rk_math.cuh"
+#include "rk_stream.cuh"
 
 namespace rk {
 
@@ -57,10 +58,13 @@ RK_DEV void imu_update_data_w(const ImuQ &k, const uint32_t rw[8], float nz, Imu
   o.d[14] = -ra.x, o.d[13] = ra.y, o.d[12] = -rb.x, o.d[15] = rb.y;
 }
 
-template <bool OUT, bool YAW>
+// GEN: the register snapshots are not read from a table but drawn in registers from the stream descriptor (the same
+// stream_imu_sample() the table generator runs, so the samples are those of rk_stream_imu_samples bit for bit): a planner
+// that samples its sensor noise on the device never materialises 3.2 KB of snapshots per robot and launch.
+template <bool OUT, bool YAW, bool GEN>
 RK_DEV void imt_update_body(int64_t i, uint4 *__restrict__ state, int64_t n, int K, const int16_t *__restrict__ regs,
                             const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init,
-                            float nz) {
+                            float nz, const rk_stream_desc_t &sd) {
   float   qi[4];
   ImuData cur;
   {
@@ -79,10 +83,16 @@ RK_DEV void imt_update_body(int64_t i, uint4 *__restrict__ state, int64_t n, int
   const uint8_t *hsrc = have_quat ? have_quat + i : nullptr;
   uint4          c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
   bool           nhq = true;
+  const uint32_t px  = GEN ? h32_prefix(sd.seed, 20u, (uint64_t)(sd.first + i)) : 0u;
+  uint32_t       upd = sd.first_update;
   auto           fetch = [&]() {
-    c0 = __ldcs(src), c1 = __ldcs(src + n);
-    src += 2 * n;
-    if(hsrc) nhq = __ldcs(hsrc) != 0, hsrc += n;
+    if(GEN) {
+      stream_imu_sample(px, upd++, sd.drop_every, c0, c1, nhq);
+    } else {
+      c0 = __ldcs(src), c1 = __ldcs(src + n);
+      src += 2 * n;
+      if(hsrc) nhq = __ldcs(hsrc) != 0, hsrc += n;
+    }
   };
   auto publish = [&](int u) {
     // what the vehicle ISR reads each tick: mymath::deg2rad(IMT::get_status_now_yaw())
@@ -131,13 +141,15 @@ RK_DEV void imt_update_body(int64_t i, uint4 *__restrict__ state, int64_t n, int
 // issue-bound vehicle rollout on a capped number of CTAs), so CTAs stride over the blocks of 256 IMUs.
 // nz_src: any finite positive float; -0.0f is formed from it at run time so that ptxas cannot fold the packed
 // products' "+ (-0)" into the adds that follow (see rk_vehicle_fast2.cuh).
-template <bool OUT, bool YAW>
+template <bool OUT, bool YAW, bool GEN = false>
 __global__ void __launch_bounds__(256, 4) // 64 registers: one CTA fits the slot a retiring vehicle CTA frees (rk_tick.cu)
 imt_update_kernel(uint4 *__restrict__ state, int64_t n, int K, const int16_t *__restrict__ regs,
-                  const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init, float nz_src) {
-  const float nz = fmul(-0.0f, nz_src);
+                  const uint8_t *__restrict__ have_quat, float4 *__restrict__ out, float *__restrict__ yaw_rad, int do_init, float nz_src,
+                  const rk_stream_desc_t *__restrict__ desc) {
+  const float            nz = fmul(-0.0f, nz_src);
+  const rk_stream_desc_t sd = GEN ? *desc : rk_stream_desc_t{};
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    imt_update_body<OUT, YAW>(i, state, n, K, regs, have_quat, out, yaw_rad, do_init, nz);
+    imt_update_body<OUT, YAW, GEN>(i, state, n, K, regs, have_quat, out, yaw_rad, do_init, nz, sd);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -486,15 +498,17 @@ int rk_imt_update(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, co
 
 int rk_imt_update_yaw(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
                       float *d_yaw_rad, int do_init, void *stream) {
-  return rk::imt_update_launch(d_state, n, K, d_regs, d_have_quat, d_out, d_yaw_rad, do_init, 0, stream);
+  return rk::imt_update_launch(d_state, n, K, d_regs, d_have_quat, d_out, d_yaw_rad, do_init, 0, stream, nullptr);
 }
 } // extern "C"
 
 // max_ctas > 0: at most that many CTAs (each strides over the batch)
+// d_desc != NULL (and no output page): the samples are drawn from the stream descriptor instead of read from d_regs
 int rk::imt_update_launch(void *d_state, int64_t n, int32_t K, const int16_t *d_regs, const uint8_t *d_have_quat, float *d_out,
-                          float *d_yaw_rad, int do_init, int max_ctas, void *stream) {
+                          float *d_yaw_rad, int do_init, int max_ctas, void *stream, const void *d_desc) {
   if(n == 0 || K == 0) return RK_OK;
-  if(n < 0 || K < 0 || !d_regs || ((uintptr_t)d_regs & 15u)) {
+  const bool gen = d_desc != nullptr && !d_out && !d_yaw_rad;
+  if(n < 0 || K < 0 || (!gen && !d_regs) || ((uintptr_t)d_regs & 15u) || ((uintptr_t)d_desc & 7u)) {
     set_error("rk_imt_update: bad n / K, or d_regs NULL / not 16-byte aligned");
     return RK_ERR_ARG;
   }
@@ -507,8 +521,11 @@ int rk::imt_update_launch(void *d_state, int64_t n, int32_t K, const int16_t *d_
   if(max_ctas > 0 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;
   cudaStream_t st = (cudaStream_t)stream;
 #define RK_LAUNCH_IMT(O, Y) \
-  imt_update_kernel<O, Y><<<grid, 256, 0, st>>>((uint4 *)d_state, n, K, d_regs, d_have_quat, (float4 *)d_out, d_yaw_rad, do_init, 1.0f)
-  if(d_out) {
+  imt_update_kernel<O, Y><<<grid, 256, 0, st>>>((uint4 *)d_state, n, K, d_regs, d_have_quat, (float4 *)d_out, d_yaw_rad, do_init, 1.0f, nullptr)
+  if(gen) {
+    imt_update_kernel<false, false, true><<<grid, 256, 0, st>>>((uint4 *)d_state, n, K, nullptr, nullptr, nullptr, nullptr, do_init, 1.0f,
+                                                                 (const rk_stream_desc_t *)d_desc);
+  } else if(d_out) {
     if(d_yaw_rad) RK_LAUNCH_IMT(true, true);
     else RK_LAUNCH_IMT(true, false);
   } else {

@@ -10,36 +10,13 @@
 // compares the blocks bit for bit.
 #include <math.h>
 
-#include "rk_common.cuh"
+#include "rk_stream.cuh"
 
 #ifndef RK_STREAM_BLOCK
 #define RK_STREAM_BLOCK 256
 #endif
 
 namespace rk {
-
-RK_DEV uint32_t mix32(uint32_t x) {
-  x ^= x >> 16;
-  x *= 0x7FEB352Du;
-  x ^= x >> 15;
-  x *= 0x846CA68Bu;
-  x ^= x >> 16;
-  return x;
-}
-RK_DEV uint32_t h32_prefix(uint32_t seed, uint32_t stream, uint64_t inst) { // the part that does not depend on the index
-  return mix32(mix32(seed ^ (stream * 0x9E3779B9u)) ^ (uint32_t)inst);
-}
-RK_DEV uint32_t h32_idx(uint32_t prefix, uint32_t idx) { return mix32(prefix ^ (idx * 0x85EBCA6Bu)); }
-RK_DEV uint32_t sub32(uint32_t h, uint32_t k) { return mix32(h + (k + 1u) * 0x9E3779B9u); }
-// k-th draw under an already mixed hash at a fraction of sub32's cost (streams.lite32): one wide multiply by an odd
-// per-draw constant (FMA pipe) and one xor of the two halves -- the generators run beside rollouts that are bound by the
-// half-rate ALU pipe, so the draws stay off it
-RK_DEV uint32_t lite32(uint32_t h, uint32_t k) {
-  const uint32_t           m = (0x85EBCA6Bu + 2u * (k + 1u) * 0x9E3779B9u) | 1u;
-  const unsigned long long x = (unsigned long long)h * m;
-  return (uint32_t)x ^ (uint32_t)(x >> 32);
-}
-RK_DEV float    u01_32(uint32_t h) { return fmul((float)(h >> 8), 1.0f / 16777216.0f); }
 
 // streams.vehicle_commands_v2: [n_seg][n] rk_vdt_cmd_t
 __global__ void __launch_bounds__(RK_STREAM_BLOCK)
@@ -103,25 +80,21 @@ stream_imu_samples_kernel(const rk_stream_desc_t *__restrict__ dd, int64_t n, in
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
   const uint32_t px = h32_prefix(d.seed, 20u, (uint64_t)(d.first + i));
   for(int u = 0; u < n_upd; u++) {
-    const uint32_t b = h32_idx(px, d.first_update + (uint32_t)u);
-    uint32_t       w[8];
-#pragma unroll
-    for(int k = 0; k < 6; k++) w[k] = lite32(b, (uint32_t)k); // AX..Yaw, two registers a word
-    const uint32_t w6 = lite32(b, 6u), w7 = lite32(b, 7u);
-    const uint32_t gu[4] = {w6 & 0xFFFFu, w6 >> 16, w7 & 0xFFFFu, w7 >> 16};
-    float          g[4];
-#pragma unroll
-    for(int k = 0; k < 4; k++) g[k] = fsub(fmul(fadd((float)gu[k], 0.5f), 1.0f / 32768.0f), 1.0f);
-    const float nrm = fsqrt(fadd(fadd(fadd(fmul(g[0], g[0]), fmul(g[1], g[1])), fmul(g[2], g[2])), fmul(g[3], g[3])));
-    const float sc  = fdiv(32767.0f, nrm);
-    uint32_t    q[4];
-#pragma unroll
-    for(int k = 0; k < 4; k++) q[k] = (uint32_t)__float2int_rn(fmul(g[k], sc)) & 0xFFFFu;
-    w[6] = q[0] | (q[1] << 16), w[7] = q[2] | (q[3] << 16);
-    __stcs(cells + ((int64_t)u * 2 + 0) * n + i, make_uint4(w[0], w[1], w[2], w[3]));
-    __stcs(cells + ((int64_t)u * 2 + 1) * n + i, make_uint4(w[4], w[5], w[6], w[7]));
-    if(yaw_reg) yaw_reg[(int64_t)u * n + i] = (int16_t)(w[5] >> 16); // register RK_IMT_REG_YAW again, as a 2-byte column
-    if(have) have[(int64_t)u * n + i] = (d.drop_every == 0u || (lite32(b, 8u) % d.drop_every) != 0u) ? 1u : 0u;
+    if(cells) {
+      uint4 c0, c1;
+      bool  hv;
+      stream_imu_sample(px, d.first_update + (uint32_t)u, d.drop_every, c0, c1, hv);
+      __stcs(cells + ((int64_t)u * 2 + 0) * n + i, c0);
+      __stcs(cells + ((int64_t)u * 2 + 1) * n + i, c1);
+      if(yaw_reg) yaw_reg[(int64_t)u * n + i] = (int16_t)(c1.y >> 16); // register RK_IMT_REG_YAW again, as a 2-byte column
+      if(have) have[(int64_t)u * n + i] = hv ? 1u : 0u;
+    } else { // columns only: the IMU update draws the samples itself (rk_tick_rollout_t::d_imu_desc)
+      int16_t y;
+      bool    hv;
+      stream_imu_yaw(px, d.first_update + (uint32_t)u, d.drop_every, y, hv);
+      if(yaw_reg) yaw_reg[(int64_t)u * n + i] = y;
+      if(have) have[(int64_t)u * n + i] = hv ? 1u : 0u;
+    }
   }
   }
 }
@@ -220,7 +193,8 @@ int rk_stream_vehicle_yaw_reg(const rk_stream_desc_t *d_desc, int64_t n, int32_t
 int rk_stream_imu_samples_yaw(const rk_stream_desc_t *d_desc, int64_t n, int32_t n_upd, int16_t *d_regs, uint8_t *d_have_quat,
                               int16_t *d_yaw_reg, void *stream) {
   if(n == 0 || n_upd <= 0) return RK_OK;
-  if(int rc = stream_check("rk_stream_imu_samples", d_desc, d_regs, n)) return rc;
+  // d_regs NULL: only the columns are written (the IMU update then draws the samples itself, rk_tick_rollout_t::d_imu_desc)
+  if(int rc = stream_check("rk_stream_imu_samples", d_desc, d_regs ? (const void *)d_regs : (const void *)d_yaw_reg, n)) return rc;
   if((uintptr_t)d_yaw_reg & 1u) {
     set_error("rk_stream_imu_samples_yaw: d_yaw_reg must be 2-byte aligned");
     return RK_ERR_ARG;

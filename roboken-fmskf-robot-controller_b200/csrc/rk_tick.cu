@@ -77,8 +77,9 @@ extern "C" int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t 
     return RK_ERR_ARG;
   }
   if(n == 0 || a->steps == 0) return RK_OK;
-  if(n < 0 || a->steps < 0 || a->slow_period <= 0 || !a->d_regs || !a->d_yaw || !d_imt_state || ((uintptr_t)d_imt_state & 15u)) {
-    set_error("rk_tick_rollout: bad n / steps / slow_period, or d_regs / d_yaw / d_imt_state NULL or misaligned");
+  if(n < 0 || a->steps < 0 || a->slow_period <= 0 || (!a->d_regs && !(a->d_imu_desc && a->d_yaw_reg)) || !a->d_yaw || !d_imt_state ||
+     ((uintptr_t)d_imt_state & 15u)) {
+    set_error("rk_tick_rollout: bad n / steps / slow_period, or d_regs (or d_imu_desc + d_yaw_reg) / d_yaw / d_imt_state NULL or misaligned");
     return RK_ERR_ARG;
   }
   if(int rc = require_device()) return rc;
@@ -103,7 +104,9 @@ extern "C" int rk_tick_rollout(const rk_vdt_params_t *vp, const rk_adt_params_t 
   RK_CUDA(cudaEventRecord(ts->fork, st));
   RK_CUDA(cudaStreamWaitEvent(ts->side, ts->fork, 0));
   mark(1, ts->side);
-  int rc = imt_update_launch(d_imt_state, n, n_slow, a->d_regs, a->d_have_quat, nullptr, nullptr, 0, cap, ts->side);
+  // d_imu_desc: the IMU update draws its samples in registers (the vehicle reads the Yaw column the generator wrote)
+  int rc = imt_update_launch(d_imt_state, n, n_slow, a->d_regs, a->d_have_quat, nullptr, nullptr, 0, cap, ts->side,
+                             (a->d_imu_desc && a->d_yaw_reg) ? (const void *)a->d_imu_desc : nullptr);
   mark(2, ts->side);
   if(rc == RK_OK) rc = adt_update_launch(ap, d_adt_state, d_adt_cmdtab, n, n_slow, a->d_adt_trace, cap, ts->side);
   mark(3, ts->side);

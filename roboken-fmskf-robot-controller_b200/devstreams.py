@@ -60,6 +60,15 @@ class DeviceStreams:
                                                        None if yaw_reg is None else yaw_reg.data_ptr(), self._st(stream)))
         return regs, have
 
+    def imu_columns(self, yaw_reg, have=None, stream=None):
+        """Only the columns of the IMU stream a vehicle rollout reads: yaw_reg int16 [n_upd, n] (the Yaw register), have
+        uint8 [n_upd, n] or None -- for RobotBatch.make_args(imu_desc=self), whose IMU update draws the samples itself."""
+        n_upd, n = yaw_reg.shape
+        assert yaw_reg.dtype == torch.int16 and yaw_reg.is_contiguous()
+        _cabi.check(self.lib.rk_stream_imu_samples_yaw(self.dev.data_ptr(), n, n_upd, None, None if have is None else have.data_ptr(),
+                                                       yaw_reg.data_ptr(), self._st(stream)))
+        return yaw_reg, have
+
     def arm_sequences(self, out, stream=None):
         """out: int32 [ACMD_SLOT_WORDS * n] (65 planes of 128-bit cells)"""
         n = out.numel() // layout.ACMD_SLOT_WORDS

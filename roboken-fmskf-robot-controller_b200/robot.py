@@ -30,11 +30,17 @@ class RobotBatch:
         self.arm.mode_init()
 
     def make_args(self, steps, slow_period, cmd, seg_len, regs, have_quat, yaw, goal=None, cost=None, vdt_trace=None,
-                  adt_trace=None, reset_vehicle=False, yaw_reg=None):
+                  adt_trace=None, reset_vehicle=False, yaw_reg=None, imu_desc=None):
         """cmd: [n_seg, n, 4] rk_vdt_cmd_t records; regs: int16 [n_slow, 2, n, 8] (streams.imu_cells); have_quat: uint8
         [n_slow, n] or None; yaw: float32 scratch, >= n words (receives the IMU yaw as it was at launch)."""
         n_slow = (steps + slow_period - 1) // slow_period
-        assert regs.is_cuda and regs.dtype == torch.int16 and tuple(regs.shape) == (n_slow, 2, self.n, 8) and regs.is_contiguous()
+        # imu_desc: a DeviceStreams whose IMU stream the update draws in registers (regs may then be None; yaw_reg / have_quat are
+        # the columns DeviceStreams.imu_columns wrote)
+        assert imu_desc is not None or regs is not None
+        if regs is not None:
+            assert regs.is_cuda and regs.dtype == torch.int16 and tuple(regs.shape) == (n_slow, 2, self.n, 8) and regs.is_contiguous()
+        if imu_desc is not None:
+            assert yaw_reg is not None
         assert yaw.is_cuda and yaw.dtype == torch.float32 and yaw.numel() >= self.n
         a = _cabi.TickRollout()
         a.steps, a.slow_period = int(steps), int(slow_period)
@@ -42,7 +48,8 @@ class RobotBatch:
         if cmd is not None:
             assert cmd.is_cuda and cmd.is_contiguous() and cmd.shape[1] == self.n
             a.d_cmd, a.n_seg, a.seg_len = cmd.data_ptr(), cmd.shape[0], int(seg_len)
-        a.d_regs = regs.data_ptr()
+        a.d_regs = None if regs is None else regs.data_ptr()
+        a.d_imu_desc = None if imu_desc is None else imu_desc.dev.data_ptr()
         a.d_have_quat = None if have_quat is None else have_quat.data_ptr()
         a.d_yaw = yaw.data_ptr()
         if yaw_reg is not None:  # the Yaw register column of regs, int16 [n_slow, n]
@@ -54,7 +61,7 @@ class RobotBatch:
             a.d_vdt_trace = vdt_trace.data_ptr()
         if adt_trace is not None:
             a.d_adt_trace = adt_trace.data_ptr()
-        self._keep = [cmd, regs, have_quat, yaw, goal, cost, vdt_trace, adt_trace, yaw_reg]
+        self._keep = [cmd, regs, have_quat, yaw, goal, cost, vdt_trace, adt_trace, yaw_reg, imu_desc]
         return a
 
     def rollout_args(self, args, stream=None):

@@ -215,6 +215,23 @@ def test_yaw_column_equals_register_cells():
         out.append([rb.vehicle.state.cpu().numpy().copy(), rb.imu.state.cpu().numpy().copy(), rb.arm.state.cpu().numpy().copy(), cost.cpu().numpy().view(np.uint32).copy()])
     for x, y in zip(*out):
         np.testing.assert_array_equal(x, y)
+    # ... and with the IMU update drawing the samples from the descriptor in registers (d_imu_desc): no register table at all
+    yc2, hv2 = ds.imu_columns(torch.empty((n_slow, n), dtype=torch.int16, device=DEV), torch.empty((n_slow, n), dtype=torch.uint8, device=DEV))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(yc2.cpu().numpy(), yawc.cpu().numpy())
+    np.testing.assert_array_equal(hv2.cpu().numpy(), have.cpu().numpy())
+    rb = RobotBatch(n, DEV)
+    rb.reset()
+    boot = DeviceStreams(DEV, seed=91, first=7, first_update=0).imu_samples(torch.empty((1, 2, n, 8), dtype=torch.int16, device=DEV), None)[0]
+    rb.imu.update(boot, None, None, do_init=True)
+    rb.arm.push_cmdseq(seq)
+    cost = torch.zeros(n, dtype=torch.float32, device=DEV)
+    for _ in range(2):
+        rb.rollout(steps, slow, cmd=cmd, seg_len=seg_len, regs=None, imu_desc=ds, have_quat=hv2, yaw_reg=yc2, yaw=torch.zeros(n, dtype=torch.float32, device=DEV),
+                   goal=torch.zeros((n, 2), dtype=torch.float32, device=DEV), cost=cost)
+    torch.cuda.synchronize()
+    for x, y in zip(out[0], [rb.vehicle.state.cpu().numpy(), rb.imu.state.cpu().numpy(), rb.arm.state.cpu().numpy(), cost.cpu().numpy().view(np.uint32)]):
+        np.testing.assert_array_equal(x, y)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
