@@ -144,6 +144,9 @@ vdt_rollout_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n
 // the launch and any thread outside the fast path's domain run the transcription (veh_update), so the
 // stored state is complete and identical.
 // -----------------------------------------------------------------------------------------
+#ifndef RK_FAST_CMDRCP
+#define RK_FAST_CMDRCP 1
+#endif
 #ifndef RK_FAST_RESET_KERNEL
 #define RK_FAST_RESET_KERNEL 1
 #endif
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kFastThreads, RK_FAST_MINBLOCKS)
 #else
 __global__ void __launch_bounds__(kFastThreads, OCC * 128 / kFastThreads)
 #endif
-vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
+vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a, const CmdRcp rcp) {
   constexpr int  D0 = 1, D1 = 1, D2 = -1, D3 = -1; // VD_task_main.cpp:75-78 (host checks params match)
   constexpr bool FFSAT = (FLAGS & 1) != 0, KD0 = (FLAGS & 2) != 0;
   __shared__ float s_tab[513];
@@ -238,7 +241,7 @@ vdt_rollout_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int6
 
   int t = 0;
   while(t < K) {
-    sched_events(v, p, a, n, i, t, sch); // commands, VDT::main messages and the move-time countdown due at this tick
+    sched_events(v, p, a, n, i, t, sch, RK_FAST_CMDRCP ? &rcp : nullptr); // commands, VDT::main messages and the move-time countdown due at this tick
     // run to the next event: a command, the countdown's automatic stop, or the last tick of the launch
     // (always a transcription tick).  Lanes of a warp whose countdowns fire at different ticks leave
     // the fast loop at different times; results do not depend on it.
@@ -673,7 +676,11 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
     if(fast_path_usable(*p)) {
       const unsigned grid  = (unsigned)((n + kFastThreads - 1) / kFastThreads);
       const int      flags = ((p->ff_limit == 1.0f && g_fast_ffsat) ? 1 : 0) | ((p->kd == 0.0f && g_fast_packed) ? 2 : 0);
-#define RK_LAUNCH_FAST3(TR, OCC, FL, PK) vdt_rollout_fast_kernel<TR, OCC, FL, PK><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args)
+      CmdRcp rcp;
+      for(int k = 0; k < 3; k++)
+        rcp.ra_move[k] = 1.0f / p->accel_move[k], rcp.rj_move[k] = 1.0f / p->jerk_move[k], rcp.ra_stop[k] = 1.0f / p->accel_stop[k],
+        rcp.rj_stop[k] = 1.0f / p->jerk_stop[k];
+#define RK_LAUNCH_FAST3(TR, OCC, FL, PK) vdt_rollout_fast_kernel<TR, OCC, FL, PK><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args, rcp)
 #define RK_LAUNCH_FAST(TR, OCC)                                    \
   do {                                                             \
     if(!g_fast_packed) {                                           \
@@ -689,7 +696,7 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
     }                                                              \
   } while(0)
       if(reset_in_kernel) {
-        vdt_rollout_fast_kernel<false, 4, 2, true, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args);
+        vdt_rollout_fast_kernel<false, 4, 2, true, true><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args, rcp);
       } else if(args->d_trace) {
         RK_LAUNCH_FAST(true, 4);
       } else {

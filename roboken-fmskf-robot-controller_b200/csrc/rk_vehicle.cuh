@@ -160,6 +160,36 @@ RK_DEV void interp_set(Interp &t, float v_t, float a_m, float jrk) {
   t.vel_tgt = vel_tgt, t.acl_max = acl_max, t.jerk_p = jerk_p, t.jerk_m = jerk_m;
   t.dt1 = dt1, t.dt2 = dt2, t.dt3 = dt3, t.vel_ini = vel_ini, t.acl_ini = acl_ini, t.dt = 0.0f;
 }
+// set_target_params with the three reciprocals it forms -- 1 / jerk_m, 1 / jerk_p, 1 / acl_max, each +-1 / a launch
+// constant -- taken from the host's IEEE divisions: 1 / (-x) == -(1 / x) exactly, zeros and infinities included.
+RK_DEV void interp_set_rcp(Interp &t, float v_t, float a_m, float jrk, float ra, float rj) {
+  float vel_tgt = v_t, acl_max = a_m, am_inv = ra, vel_ini = t.vel, acl_ini = t.acl;
+  if(fsub(vel_tgt, vel_ini) < 0.0f) acl_max = -a_m, am_inv = -ra;
+  const bool  mneg   = acl_max >= 0.0f;
+  float       jerk_m = mneg ? -jrk : jrk;
+  const float jm_inv = mneg ? -rj : rj;
+  const bool  ppos   = fsub(acl_max, acl_ini) >= 0.0f;
+  float       jerk_p = ppos ? jrk : -jrk;
+  const float jp_inv = ppos ? rj : -rj;
+  float dt1    = fmul(fsub(acl_max, acl_ini), jp_inv);
+  float dt3    = fmul(acl_max, -jm_inv);
+  float inner = fsub(fsub(fsub(vel_tgt, vel_ini), fmul(fmul(acl_ini, dt1), 0.5f)),
+                     fmul(fmul(acl_max, fadd(dt1, dt3)), 0.5f));
+  float dt2   = fmul(am_inv, inner);
+  if(dt2 < 0.0f) {
+    float q     = fmul(acl_ini, jp_inv);
+    float sq_in = fadd(fmul(fmul(q, q), 0.5f), fmul(fsub(vel_tgt, vel_ini), jp_inv));
+    float sq    = arm_sqrt(sq_in);
+    dt1         = fsub(sq, fmul(acl_ini, jp_inv));
+    acl_max     = fadd(acl_ini, fmul(jerk_p, dt1));
+    dt2         = 0.0f;
+    dt3         = fmul(acl_max, -jm_inv);
+  }
+  dt1 = (dt1 < 0.0f) ? 0.0f : dt1;
+  dt3 = (dt3 < 0.0f) ? 0.0f : dt3;
+  t.vel_tgt = vel_tgt, t.acl_max = acl_max, t.jerk_p = jerk_p, t.jerk_m = jerk_m;
+  t.dt1 = dt1, t.dt2 = dt2, t.dt3 = dt3, t.vel_ini = vel_ini, t.acl_ini = acl_ini, t.dt = 0.0f;
+}
 // update  util_vel_interp.hpp:110-136
 RK_DEV float interp_update(Interp &t, float ts) {
   float t1 = fadd(t.dt1, ts);
@@ -393,7 +423,11 @@ RK_DEV void sched_init(Sched &s, const rk_vdt_rollout_t &a) {
   s.next_cmd = has_cmd ? 0 : INT_MAX, s.seg = 0;
   s.next_task = (a.task_period > 0) ? 0 : INT_MAX;
 }
-RK_DEV void sched_events(Veh &v, const rk_vdt_params_t &p, const rk_vdt_rollout_t &a, int64_t n, int64_t i, int t, Sched &s) {
+struct CmdRcp { // host-side RN(1 / x) of the command layer's acceleration / jerk constants (interp_set_rcp)
+  float ra_move[3], rj_move[3], ra_stop[3], rj_stop[3];
+};
+RK_DEV void sched_events(Veh &v, const rk_vdt_params_t &p, const rk_vdt_rollout_t &a, int64_t n, int64_t i, int t, Sched &s,
+                         const CmdRcp *rc = nullptr) {
   uint4 cq   = make_uint4(0u, 0u, 0u, 0u);
   bool  have = false;
   if(t == s.next_cmd) {
@@ -403,7 +437,13 @@ RK_DEV void sched_events(Veh &v, const rk_vdt_params_t &p, const rk_vdt_rollout_
     if(kind == RK_CMD_MOVE || kind == RK_CMD_STOP) { // VDT::main -> start(); set_target_vel()   VD_task_main.cpp:280-281,294-295
       const float vv[3] = {u2f(cq.x), u2f(cq.y), u2f(cq.z)};
       v.flags |= RK_VS_FLAG_POWER_ON;
-      if(kind == RK_CMD_STOP) veh_set_target(v, vv, p.accel_stop, p.jerk_stop);
+      if(rc) {
+        const bool stop = kind == RK_CMD_STOP;
+#pragma unroll
+        for(int k = 0; k < 3; k++)
+          interp_set_rcp(v.it[k], vv[k], stop ? p.accel_stop[k] : p.accel_move[k], stop ? p.jerk_stop[k] : p.jerk_move[k],
+                         stop ? rc->ra_stop[k] : rc->ra_move[k], stop ? rc->rj_stop[k] : rc->rj_move[k]);
+      } else if(kind == RK_CMD_STOP) veh_set_target(v, vv, p.accel_stop, p.jerk_stop);
       else veh_set_target(v, vv, p.accel_move, p.jerk_move);
     }
     s.seg++;
