@@ -350,7 +350,7 @@ RK_DEV void frame_ring_take(const FrameRing &r, int t, uint64_t fr[4]) { // grou
 }
 template <bool TRACE, int FLAGS>
 __global__ void __launch_bounds__(kFastThreads, RK_STREAM_OCC)
-vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a) {
+vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ state, int64_t n, const rk_vdt_rollout_t a, const CmdRcp rcp) {
   constexpr int  D0 = 1, D1 = 1, D2 = -1, D3 = -1;
   constexpr bool FFSAT = (FLAGS & 1) != 0, KD0 = (FLAGS & 2) != 0;
   __shared__ float s_tab[513];
@@ -380,7 +380,7 @@ vdt_rollout_stream_fast_kernel(const rk_vdt_params_t p, uint4 *__restrict__ stat
 
   int t = 0;
   while(t < K) {
-    sched_events(v, p, a, n, i, t, sch);
+    sched_events(v, p, a, n, i, t, sch, RK_FAST_CMDRCP ? &rcp : nullptr);
     // chunks are capped so the 32-bit per-chunk angle sum cannot overflow (|step| <= 40960)
     const int t_end = min(min(min(sch.next_cmd, sched_fire_tick(v, a, sch)), K - 1), t + 32768);
     if(t < t_end && fast_ok<D0, D1, D2, D3, true>(v, p) && fast_u_bounded<true>(v, p, fc)) {
@@ -534,6 +534,12 @@ static cudaError_t launch_rollout(const rk_vdt_params_t &p, void *d_state, int64
 }
 
 bool fast_path_proven(const rk_vdt_params_t &p); // rk_exact.cu
+static CmdRcp make_cmd_rcp(const rk_vdt_params_t &p) { // the host's IEEE divisions (interp_set_rcp)
+  CmdRcp r;
+  for(int k = 0; k < 3; k++)
+    r.ra_move[k] = 1.0f / p.accel_move[k], r.rj_move[k] = 1.0f / p.jerk_move[k], r.ra_stop[k] = 1.0f / p.accel_stop[k], r.rj_stop[k] = 1.0f / p.jerk_stop[k];
+  return r;
+}
 int  tick_set_side_ctas(int v);                     // rk_tick.cu
 int  stream_set_ctas(int v);                        // rk_stream.cu
 
@@ -676,10 +682,7 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
     if(fast_path_usable(*p)) {
       const unsigned grid  = (unsigned)((n + kFastThreads - 1) / kFastThreads);
       const int      flags = ((p->ff_limit == 1.0f && g_fast_ffsat) ? 1 : 0) | ((p->kd == 0.0f && g_fast_packed) ? 2 : 0);
-      CmdRcp rcp;
-      for(int k = 0; k < 3; k++)
-        rcp.ra_move[k] = 1.0f / p->accel_move[k], rcp.rj_move[k] = 1.0f / p->jerk_move[k], rcp.ra_stop[k] = 1.0f / p->accel_stop[k],
-        rcp.rj_stop[k] = 1.0f / p->jerk_stop[k];
+      const CmdRcp rcp = make_cmd_rcp(*p);
 #define RK_LAUNCH_FAST3(TR, OCC, FL, PK) vdt_rollout_fast_kernel<TR, OCC, FL, PK><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args, rcp)
 #define RK_LAUNCH_FAST(TR, OCC)                                    \
   do {                                                             \
@@ -716,13 +719,14 @@ int rk_vdt_rollout(const rk_vdt_params_t *p, void *d_state, int64_t n, const rk_
     if(fast_path_usable(*p)) {
       const unsigned grid  = (unsigned)((n + kFastThreads - 1) / kFastThreads);
       const int      flags = ((p->ff_limit == 1.0f && g_fast_ffsat) ? 1 : 0) | ((p->kd == 0.0f) ? 2 : 0);
+      const CmdRcp   rcp   = make_cmd_rcp(*p);
 #define RK_LAUNCH_STREAM(TR)                                                                                                  \
   do {                                                                                                                        \
     switch(flags) {                                                                                                           \
-    case 3: vdt_rollout_stream_fast_kernel<TR, 3><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); break;      \
-    case 2: vdt_rollout_stream_fast_kernel<TR, 2><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); break;      \
-    case 1: vdt_rollout_stream_fast_kernel<TR, 1><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); break;      \
-    default: vdt_rollout_stream_fast_kernel<TR, 0><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args); break;     \
+    case 3: vdt_rollout_stream_fast_kernel<TR, 3><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args, rcp); break;      \
+    case 2: vdt_rollout_stream_fast_kernel<TR, 2><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args, rcp); break;      \
+    case 1: vdt_rollout_stream_fast_kernel<TR, 1><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args, rcp); break;      \
+    default: vdt_rollout_stream_fast_kernel<TR, 0><<<grid, kFastThreads, 0, st>>>(*p, (uint4 *)d_state, n, *args, rcp); break;     \
     }                                                                                                                         \
   } while(0)
       if(args->d_trace) RK_LAUNCH_STREAM(true);
